@@ -1,0 +1,219 @@
+/*
+ * lasr.h -- C ABI of the B200-native lightning-asr hot path (liblasr_b200.so).
+ *
+ * The reference (kouyt5/lightning-asr) is pure Python/PyTorch and has NO plugin / operator / FFI
+ * interface of its own: its hot path is the chain of torch / torchaudio library
+ * calls made by
+ *     data_module.py:150-174   AudioParser.parse_audio            (log-mel frontend)
+ *     models/QuartNet.py:8-52  SeprationConv.forward              (dw conv, 1x1 conv, mask, BN, ReLU)
+ *     models/QuartNet.py:55-78 QuartNetBlock.forward              (+ residual 1x1 conv + BN, add, ReLU)
+ *     models/QuartNet.py:264-291 MyModel2.forward                 (decoder 1x1 conv, log_softmax)
+ *     models/QuartNetContextSE.py:8-23 SELayer.forward            (squeeze-excitation)
+ *     train.py:76-78,196       torch.nn.CTCLoss(blank=V, reduction='none')
+ *     utils/asr_metrics.py:138-171 WER.ctc_decoder_predictions_tensor (greedy CTC decode)
+ * Each entry point below replaces one of those library call sites (cited per function) and is what a
+ * ctypes binding inside the reference's modules would call (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *   - every function returns 0 (LASR_OK) or a negative LASR_ERR_* code; never throws, never
+ *     synchronises, never allocates device memory; all launches go to `stream`;
+ *   - all pointers are DEVICE pointers owned by the caller unless stated otherwise;
+ *   - activations are channels-last: a [N, T, C] tensor is a row-major matrix of N*T rows ("frames")
+ *     and C contiguous channels; `ld*` arguments are row pitches in ELEMENTS;
+ *   - `dtype` selects the activation element type: LASR_F32 or LASR_BF16.  Statistics, weights
+ *     gradients, losses and all accumulators are fp32 regardless;
+ *   - `lengths[n]` = int(float32(T) * percents[n]) is computed by the caller exactly as
+ *     models/QuartNet.py:311 does, and frames t >= lengths[n] of utterance n are "masked".
+ */
+#ifndef LASR_H_
+#define LASR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* lasr_stream_t; /* == cudaStream_t */
+
+enum { LASR_F32 = 0, LASR_BF16 = 1 };
+
+enum {
+  LASR_OK = 0,
+  LASR_ERR_BAD_SHAPE = -1,
+  LASR_ERR_BAD_DTYPE = -2,
+  LASR_ERR_WORKSPACE = -3,
+  LASR_ERR_CUDA = -4,
+  LASR_ERR_ALIGNMENT = -5,
+  LASR_ERR_UNSUPPORTED = -6,
+  LASR_ERR_DRIVER = -7
+};
+
+/* activation flags for lasr_bn_apply_act_* */
+enum { LASR_ACT_NONE = 0, LASR_ACT_RELU = 1 };
+
+const char* lasr_strerror(int code);
+int lasr_abi_version(void);
+/* compute capability check: returns LASR_OK only on an sm_100 device */
+int lasr_check_device(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layout conversion at the module boundary.
+ * replaces: `input.squeeze(dim=1).contiguous()` models/QuartNet.py:154 (input [N,1,F,T] fp32, NCT)
+ * x [N, C, T] fp32  ->  y [N, T, C] dtype
+ * ---------------------------------------------------------------------------------------------- */
+int lasr_nct_to_ntc(const float* x, void* y, int N, int C, int T, int dtype, lasr_stream_t stream);
+/* y [N, T, C] dtype -> x [N, C, T] fp32 (used for gradients / debugging at the boundary) */
+int lasr_ntc_to_nct(const void* y, float* x, int N, int C, int T, int dtype, lasr_stream_t stream);
+/* fp32 master weights -> compute-dtype shadow, optionally transposed: w [R, Ccols] -> out [R,Ccols] or [Ccols,R] */
+int lasr_cast_weight(const float* w, void* out, int rows, int cols, int transpose, int dtype, lasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Depthwise Conv1d  (replaces nn.Conv1d(C, C, k, stride, padding=k//2, groups=C, bias=False),
+ * models/QuartNet.py:14-21,30).  x [N, T_in, C], w [C, K] fp32, y [N, T_out, C],
+ * T_out = (T_in + 2*(K/2) - K)/stride + 1.
+ *   flip = 0: y[n,t,c] = sum_j w[c,j] * x[n, t*stride + j - K/2, c]                (forward)
+ *   flip = 1: same with w reversed along j (stride must be 1): the data gradient of the forward.
+ *   addend (nullable, [N, T_out, C]): added to the result (used to fuse the residual-branch dgrad).
+ * ---------------------------------------------------------------------------------------------- */
+int lasr_dwconv1d_fwd(const void* x, const float* w, void* y, const void* addend, int N, int T_in, int T_out, int C,
+                      int K, int stride, int flip, int dtype, lasr_stream_t stream);
+/* weight gradient: dw[c,j] += sum_{n,t} dy[n,t,c] * x[n, t*stride + j - K/2, c]; dw fp32 [C,K], ACCUMULATED
+ * (caller zeroes).  Deterministic only up to fp32 atomic ordering. */
+int lasr_dwconv1d_wgrad(const void* x, const void* dy, float* dw, int N, int T_in, int T_out, int C, int K, int stride,
+                        int dtype, lasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Pointwise (1x1) Conv1d as a GEMM over frames (replaces nn.Conv1d(Cin, Cout, 1), models/QuartNet.py:22-23,31,
+ * :62-63, :145-146, :275).  bf16: tcgen05/TMEM tensor-core kernel; fp32: FFMA kernel (exact fp32 parity mode).
+ *
+ * fwd:   y[M, Cout] = x[M, Cin] * w[Cout, Cin]^T (+ bias[Cout])
+ *        epilogue options (all nullable):
+ *          lengths/T : zero rows whose frame index t = row % T is >= lengths[row / T]   (MaskCNN, :309-321)
+ *          stats     : fp32 [stat_groups, 2, Cout] per-32-row-group partial sum / sum of squares of the
+ *                      (masked) output, the BatchNorm batch statistics; stat_groups = lasr_pwconv_stat_groups(M)
+ * dgrad: dx[M, Cin] = dy[M, Cout] * wT[Cin, Cout]^T   -- same kernel, caller passes the transposed weight
+ * wgrad: dw[Cout, Cin] (fp32) += dy[M, Cout]^T * x[M, Cin]   (split over M, fp32 atomics; caller zeroes)
+ * w / wT are in the activation dtype (see lasr_cast_weight).
+ * ---------------------------------------------------------------------------------------------- */
+int lasr_pwconv_stat_groups(int M);
+int lasr_pwconv_fwd(const void* x, const void* w, void* y, const float* bias, const int32_t* lengths, int T,
+                    float* stats, int M, int Cin, int Cout, int ldx, int ldw, int ldy, int dtype,
+                    lasr_stream_t stream);
+int lasr_pwconv_wgrad(const void* dy, const void* x, float* dw, int M, int Cin, int Cout, int lddy, int ldx, int lddw,
+                      int dtype, lasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm1d(eps=1e-3) pieces (replaces nn.BatchNorm1d, models/QuartNet.py:24,35,64,147).
+ * ---------------------------------------------------------------------------------------------- */
+/* reduce the per-group partials, produce mean / invstd (biased variance), the folded scale/shift
+ * (scale = gamma*invstd, shift = beta - mean*scale) and update running stats (momentum, unbiased var). */
+int lasr_bn_finalize(const float* stats, int groups, int C, int count, float eps, float momentum, const float* gamma,
+                     const float* beta, float* mean, float* invstd, float* scale, float* shift, float* running_mean,
+                     float* running_var, lasr_stream_t stream);
+/* eval mode: scale/shift from the running statistics */
+int lasr_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                        float eps, float* scale, float* shift, int C, lasr_stream_t stream);
+/* generic per-channel column sums of a [M, C] matrix: out partials [groups, nstat?]; used for SE squeeze:
+ * sums[n, c] = sum_t y[n, t, c]  (y [N, T, C]) */
+int lasr_sum_over_time(const void* y, float* sums, int N, int T, int C, int dtype, lasr_stream_t stream);
+
+/* out = act( scale1*y + shift1 [* gate[n,c]] [+ scale2*r + shift2] )   (fused BN-apply, SE scale, residual
+ * add, ReLU: models/QuartNet.py:35-37,75-77, models/QuartNetContextSE.py:55) */
+int lasr_bn_apply_act_fwd(const void* y, const float* scale1, const float* shift1, const void* r, const float* scale2,
+                          const float* shift2, const float* gate, void* out, int M, int C, int T, int act, int dtype,
+                          lasr_stream_t stream);
+/* backward, pass 1: with g = dout * (act==RELU ? out > 0 : 1):
+ * partials[group, 0..3, C] = sum g, sum g*y, sum g*r (r nullable -> 0), over the group's rows.
+ * when gate != NULL: sums use g*gate for the first branch: [0]=sum g*gate, [1]=sum g*gate*y, [2]=sum g*r, [3]=sum g.
+ * groups = lasr_bn_bwd_groups(M) */
+int lasr_bn_bwd_groups(int M);
+int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, const void* r, const float* gate,
+                           float* partials, int M, int C, int T, int act, int dtype, lasr_stream_t stream);
+/* pass 1b: fold partials into parameter grads and per-channel coefficients.
+ * dgamma/dbeta are ACCUMULATED (+=).  coef [3, C]: dy = coef[0]*g + coef[1]*y + coef[2] */
+int lasr_bn_bwd_finalize(const float* partials, int groups, int C, int count, int sum_idx_g, int sum_idx_gx,
+                         const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                         float* coef, lasr_stream_t stream);
+/* pass 2: dy = mask(coef1[0]*g*gate + coef1[1]*y + coef1[2]);  dr = coef2[0]*g + coef2[1]*r + coef2[2]
+ * (dr / r / coef2 nullable together; lengths nullable = no mask; gate nullable) */
+int lasr_bn_act_bwd_apply(const void* dout, const void* out, const void* y, const void* r, const float* gate,
+                          const float* coef1, const float* coef2, const int32_t* lengths, int T, void* dy, void* dr,
+                          int M, int C, int act, int dtype, lasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Squeeze-excitation (models/QuartNetContextSE.py:8-23): gate[n,:] = sigmoid(W2 * relu(W1 * s[n,:]))
+ * s [N, C] fp32 (mean over ALL T frames of the BN output), W1 [C/r, C], W2 [C, C/r] fp32.
+ * hidden [N, C/r] is written for the backward.
+ * ---------------------------------------------------------------------------------------------- */
+int lasr_se_excite_fwd(const float* s, const float* w1, const float* w2, float* hidden, float* gate, int N, int C,
+                       int Cr, lasr_stream_t stream);
+/* backward: dgate [N,C] -> ds [N,C], dW1 +=, dW2 += */
+int lasr_se_excite_bwd(const float* dgate, const float* s, const float* w1, const float* w2, const float* hidden,
+                       const float* gate, float* ds, float* dw1, float* dw2, int N, int C, int Cr,
+                       lasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * log_softmax over classes (replaces nn.functional.log_softmax, models/QuartNet.py:290).
+ * logits [M, ld] dtype (V valid columns) -> lse [M] fp32 and, if lp != NULL, log-probs lp [M, V] fp32 dense.
+ * ---------------------------------------------------------------------------------------------- */
+int lasr_log_softmax_fwd(const void* logits, float* lse, float* lp, int M, int V, int ld, int dtype,
+                         lasr_stream_t stream);
+/* dlogits[m, c] = dlp[m,c] - exp(lp[m,c]) * sum_c dlp[m,c]; dlogits [M, ld] dtype */
+int lasr_log_softmax_bwd(const float* dlp, const float* lp, void* dlogits, int M, int V, int ld, int dtype,
+                         lasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * CTC loss (replaces torch.nn.CTCLoss(blank=V, reduction='none'), train.py:196, calls :76-78).
+ * Input either log-probs (lse == NULL) or raw logits + their row log-sum-exp (fused log-softmax).
+ *   x        [N, T, ldx] dtype, class c of frame t of utterance n at x[(n*T+t)*ldx + c]
+ *   targets  [N, S_max] int64 (zero padded), input_lengths / target_lengths [N] int32
+ *   alpha    workspace fp32 [N, T, 2*S_max+1]  (kept for the backward)
+ *   nll      [N] fp32 out: -log p(target | x); +inf when no alignment exists
+ * bwd: grad [N, T, ldg] dtype = (softmax - occupancy) * grad_out[n] for t < input_lengths[n], 0 after
+ *      (this is also torch's "gradient w.r.t. log-probs"); beta workspace like alpha.
+ * ---------------------------------------------------------------------------------------------- */
+int lasr_ctc_fwd(const void* x, const float* lse, const int64_t* targets, const int32_t* input_lengths,
+                 const int32_t* target_lengths, float* alpha, float* nll, int N, int T, int V, int ldx, int S_max,
+                 int blank, int dtype, lasr_stream_t stream);
+int lasr_ctc_bwd(const void* x, const float* lse, const int64_t* targets, const int32_t* input_lengths,
+                 const int32_t* target_lengths, const float* alpha, float* beta, const float* nll,
+                 const float* grad_out, void* grad, int N, int T, int V, int ldx, int ldg, int S_max, int blank,
+                 int dtype, int grad_dtype, lasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Greedy CTC decode (replaces out.argmax(-1) train.py:80 + the collapse loop utils/asr_metrics.py:153-171).
+ *   x [N, T, ldx] dtype scores (log-probs or logits; argmax ties -> lowest index, like torch.argmax)
+ *   lengths [N] int32 or NULL (decode all T frames, predict.py:60)
+ *   argmax  [N, T] int64 out (nullable): the raw per-frame argmax
+ *   tokens  [N, T] int32 out: collapsed label ids, first counts[n] entries valid
+ * ---------------------------------------------------------------------------------------------- */
+int lasr_greedy_decode(const void* x, const int32_t* lengths, int64_t* argmax, int32_t* tokens, int32_t* counts, int N,
+                       int T, int V, int ldx, int blank, int dtype, lasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Log-mel frontend (replaces data_module.py:155-172 from the waveform onward, dither excluded):
+ * pre-emphasis 0.97 -> zero-pad 32 -> reflect-pad 256 -> frames (hop 160) -> Hann(320) in n_fft 512 -> |rFFT|^2
+ * -> 64 HTK mel filters (0..8000 Hz) -> 10*log10(max(.,1e-10)) -> per-utterance (x-mean)/std (unbiased).
+ *   wave      [N, S_max] fp32, wave_len [N] int32 valid samples per utterance
+ *   feats_nct [N, 64, T_max] fp32 out (nullable) -- the reference's layout, zero padded past T_n
+ *   feats_ntc [N, T_max, 64] dtype out (nullable) -- the internal layout
+ *   T_n = 1 + (wave_len[n] + 64) / 160
+ *   workspace: lasr_logmel_workspace(N, S_max) bytes
+ * ---------------------------------------------------------------------------------------------- */
+size_t lasr_logmel_workspace(int N, int S_max);
+int lasr_logmel_fwd(const float* wave, const int32_t* wave_len, float* feats_nct, void* feats_ntc, int N, int S_max,
+                    int T_max, int dtype, void* workspace, size_t workspace_bytes, lasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused Novograd step over a flat parameter segment list (scheduler/novograd.py:75-145).
+ * ---------------------------------------------------------------------------------------------- */
+int lasr_novograd_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* seg_offsets,
+                       int num_segs, float lr, float beta1, float beta2, float eps, float weight_decay, int first_step,
+                       float* seg_norm_ws, lasr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LASR_H_ */

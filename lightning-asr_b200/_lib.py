@@ -1,0 +1,139 @@
+"""ctypes binding of liblasr_b200.so (the C ABI declared in include/lasr.h).
+
+There is deliberately NO fallback: if the shared library is missing, or the device is not an
+sm_100 part, every op raises.  Signatures are spelled with one character per argument:
+  p = device pointer (torch.Tensor / int / None), i = int, f = float, z = size_t, s = cudaStream_t
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblasr_b200.so")
+
+LASR_F32 = 0
+LASR_BF16 = 1
+ACT_NONE = 0
+ACT_RELU = 1
+
+# name -> (restype, argument codes)
+SIGNATURES = {
+    "lasr_strerror": ("str", "i"),
+    "lasr_abi_version": ("int", ""),
+    "lasr_check_device": ("int", ""),
+    "lasr_nct_to_ntc": ("int", "ppiiiis"),
+    "lasr_ntc_to_nct": ("int", "ppiiiis"),
+    "lasr_cast_weight": ("int", "ppiiiis"),
+    "lasr_dwconv1d_fwd": ("int", "ppppiiiiiiiis"),
+    "lasr_dwconv1d_wgrad": ("int", "pppiiiiiiis"),
+    "lasr_pwconv_stat_groups": ("int", "i"),
+    "lasr_pwconv_fwd": ("int", "pppppipiiiiiiis"),
+    "lasr_pwconv_wgrad": ("int", "pppiiiiiiis"),
+    "lasr_bn_finalize": ("int", "piiiffppppppppps"[:0] + "piiiffpppppppps"),
+    "lasr_bn_eval_coeffs": ("int", "ppppfppis"),
+    "lasr_sum_over_time": ("int", "ppiiiis"),
+    "lasr_bn_apply_act_fwd": ("int", "ppppppppiiiiis"),
+    "lasr_bn_bwd_groups": ("int", "i"),
+    "lasr_bn_act_bwd_reduce": ("int", "ppppppiiiiis"),
+    "lasr_bn_bwd_finalize": ("int", "piiiiipppppps"),
+    "lasr_bn_act_bwd_apply": ("int", "ppppppppippiiiis"),
+    "lasr_se_excite_fwd": ("int", "pppppiiis"),
+    "lasr_se_excite_bwd": ("int", "pppppppppiiis"),
+    "lasr_log_softmax_fwd": ("int", "pppiiiis"),
+    "lasr_log_softmax_bwd": ("int", "pppiiiis"),
+    "lasr_ctc_fwd": ("int", "pppppppiiiiiiis"),
+    "lasr_ctc_bwd": ("int", "ppppppppppiiiiiiiiis"),
+    "lasr_greedy_decode": ("int", "pppppiiiiiis"),
+    "lasr_logmel_workspace": ("size_t", "ii"),
+    "lasr_logmel_fwd": ("int", "ppppiiiipzs"),
+    "lasr_novograd_step": ("int", "pppppifffffips"),
+}
+
+_CODES = {
+    "p": ctypes.c_void_p,
+    "i": ctypes.c_int,
+    "f": ctypes.c_float,
+    "z": ctypes.c_size_t,
+    "s": ctypes.c_void_p,
+}
+
+_lib = None
+
+
+class LasrError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LasrError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C lightning-asr_b200/csrc`. There is no CPU / eager fallback."
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, codes) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.argtypes = [_CODES[c] for c in codes]
+        fn.restype = {"int": ctypes.c_int, "str": ctypes.c_char_p, "size_t": ctypes.c_size_t}[res]
+    _lib = lib
+    return lib
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor):
+        return x.data_ptr()
+    return int(x)
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point on the current torch CUDA stream; raise on a non-zero code.
+
+    The trailing stream argument is appended automatically.
+    """
+    lib = load()
+    codes = SIGNATURES[name][1]
+    assert codes.endswith("s"), name
+    if len(args) != len(codes) - 1:
+        raise TypeError(f"{name}: expected {len(codes) - 1} arguments, got {len(args)}")
+    conv = []
+    for c, a in zip(codes, args):
+        if c == "p":
+            conv.append(_ptr(a))
+        elif c == "f":
+            conv.append(float(a))
+        else:
+            conv.append(int(a))
+    conv.append(stream_ptr())
+    rc = getattr(lib, name)(*conv)
+    if rc != 0:
+        msg = lib.lasr_strerror(rc).decode()
+        raise LasrError(f"{name} failed: {msg} (code {rc})")
+    return rc
+
+
+def dtype_code(dt):
+    if dt == torch.float32:
+        return LASR_F32
+    if dt == torch.bfloat16:
+        return LASR_BF16
+    raise LasrError(f"unsupported activation dtype {dt}")
+
+
+def require_device():
+    lib = load()
+    if not torch.cuda.is_available():
+        raise LasrError("lightning_asr_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    rc = lib.lasr_check_device()
+    if rc != 0:
+        raise LasrError("lightning_asr_b200 kernels are built for sm_100a only: " + lib.lasr_strerror(rc).decode())

@@ -1,0 +1,182 @@
+// C-ABI glue: error strings, device check, layout conversion, weight shadows, pointwise-conv dispatch.
+#include "common.cuh"
+
+#include <atomic>
+#include <cstdio>
+
+static std::atomic<int> g_last_cuda_error{0};
+void lasr_set_cuda_error(cudaError_t e) { g_last_cuda_error.store(static_cast<int>(e)); }
+
+namespace lasr {
+int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const int32_t* lengths, int T, float* stats,
+               int M, int N, int K, int lda, int ldb, int ldc, int out_f32, cudaStream_t stream);
+int gemm_tc_tn_accum(const void* dy, const void* x, float* dw, int R, int Cout, int Cin, int lddy, int ldx, int lddw,
+                     cudaStream_t stream);
+int gemm_simt_nt(const float* a, const float* b, float* c, const float* bias, const int32_t* lengths, int T, int M,
+                 int N, int K, int lda, int ldb, int ldc, cudaStream_t stream);
+int gemm_simt_tn_accum(const float* dy, const float* x, float* dw, int R, int Cout, int Cin, int lddy, int ldx,
+                       int lddw, cudaStream_t stream);
+int colstats(const void* y, float* stats, int M, int N, int ld, int dtype, cudaStream_t stream);
+
+// [N, C, T] fp32 -> [N, T, C] out-type through a 32x32 smem transpose
+template <typename OutT>
+__global__ void nct_to_ntc_kernel(const float* __restrict__ x, OutT* __restrict__ y, int C, int T) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const float* xn = x + static_cast<size_t>(n) * C * T;
+  OutT* yn = y + static_cast<size_t>(n) * C * T;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? xn[static_cast<size_t>(c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < C) yn[static_cast<size_t>(t) * C + c] = from_f32<OutT>(tile[threadIdx.x][i]);
+  }
+}
+template <typename InT>
+__global__ void ntc_to_nct_kernel(const InT* __restrict__ y, float* __restrict__ x, int C, int T) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const InT* yn = y + static_cast<size_t>(n) * C * T;
+  float* xn = x + static_cast<size_t>(n) * C * T;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < T && c < C) ? to_f32<InT>(yn[static_cast<size_t>(t) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (c < C && t < T) xn[static_cast<size_t>(c) * T + t] = tile[threadIdx.x][i];
+  }
+}
+
+template <typename OutT>
+__global__ void cast_weight_kernel(const float* __restrict__ w, OutT* __restrict__ out, int rows, int cols,
+                                   int transpose) {
+  const size_t total = static_cast<size_t>(rows) * cols;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
+    const float v = w[i];
+    if (transpose)
+      out[static_cast<size_t>(c) * rows + r] = from_f32<OutT>(v);
+    else
+      out[i] = from_f32<OutT>(v);
+  }
+}
+}  // namespace lasr
+
+using namespace lasr;
+
+extern "C" {
+
+const char* lasr_strerror(int code) {
+  switch (code) {
+    case LASR_OK: return "ok";
+    case LASR_ERR_BAD_SHAPE: return "bad shape";
+    case LASR_ERR_BAD_DTYPE: return "unsupported dtype";
+    case LASR_ERR_WORKSPACE: return "workspace too small";
+    case LASR_ERR_CUDA: {
+      static thread_local char buf[256];
+      const int e = g_last_cuda_error.load();
+      snprintf(buf, sizeof(buf), "CUDA error %d: %s", e, cudaGetErrorString(static_cast<cudaError_t>(e)));
+      return buf;
+    }
+    case LASR_ERR_ALIGNMENT: return "pointer or pitch not 16-byte aligned";
+    case LASR_ERR_UNSUPPORTED: return "unsupported configuration";
+    case LASR_ERR_DRIVER: return "CUDA driver entry point (cuTensorMapEncodeTiled) unavailable or failed";
+    default: return "unknown error";
+  }
+}
+
+int lasr_abi_version(void) { return 1; }
+
+int lasr_check_device(void) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    lasr_set_cuda_error(e);
+    return LASR_ERR_CUDA;
+  }
+  int major = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) {
+    lasr_set_cuda_error(e);
+    return LASR_ERR_CUDA;
+  }
+  return major == 10 ? LASR_OK : LASR_ERR_UNSUPPORTED;
+}
+
+int lasr_nct_to_ntc(const float* x, void* y, int N, int C, int T, int dtype, lasr_stream_t stream) {
+  if (N <= 0 || C <= 0 || T <= 0) return LASR_ERR_BAD_SHAPE;
+  dim3 grid(cdiv(T, 32), cdiv(C, 32), N), block(32, 8);
+  if (dtype == LASR_F32)
+    nct_to_ntc_kernel<float><<<grid, block, 0, stream>>>(x, static_cast<float*>(y), C, T);
+  else if (dtype == LASR_BF16)
+    nct_to_ntc_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(x, static_cast<__nv_bfloat16*>(y), C, T);
+  else
+    return LASR_ERR_BAD_DTYPE;
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+int lasr_ntc_to_nct(const void* y, float* x, int N, int C, int T, int dtype, lasr_stream_t stream) {
+  if (N <= 0 || C <= 0 || T <= 0) return LASR_ERR_BAD_SHAPE;
+  dim3 grid(cdiv(T, 32), cdiv(C, 32), N), block(32, 8);
+  if (dtype == LASR_F32)
+    ntc_to_nct_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(y), x, C, T);
+  else if (dtype == LASR_BF16)
+    ntc_to_nct_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), x, C, T);
+  else
+    return LASR_ERR_BAD_DTYPE;
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+int lasr_cast_weight(const float* w, void* out, int rows, int cols, int transpose, int dtype, lasr_stream_t stream) {
+  if (rows <= 0 || cols <= 0) return LASR_ERR_BAD_SHAPE;
+  const size_t total = static_cast<size_t>(rows) * cols;
+  const int grid = static_cast<int>(total / 256 + 1 > 1184 ? 1184 : total / 256 + 1);
+  if (dtype == LASR_F32)
+    cast_weight_kernel<float><<<grid, 256, 0, stream>>>(w, static_cast<float*>(out), rows, cols, transpose);
+  else if (dtype == LASR_BF16)
+    cast_weight_kernel<__nv_bfloat16>
+        <<<grid, 256, 0, stream>>>(w, static_cast<__nv_bfloat16*>(out), rows, cols, transpose);
+  else
+    return LASR_ERR_BAD_DTYPE;
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+int lasr_pwconv_stat_groups(int M) { return cdiv(M, 128) * 4; }
+
+int lasr_pwconv_fwd(const void* x, const void* w, void* y, const float* bias, const int32_t* lengths, int T,
+                    float* stats, int M, int Cin, int Cout, int ldx, int ldw, int ldy, int dtype,
+                    lasr_stream_t stream) {
+  if (lengths != nullptr && T <= 0) return LASR_ERR_BAD_SHAPE;
+  if (dtype == LASR_BF16) {
+    return gemm_tc_nt(x, w, y, bias, lengths, T, stats, M, Cout, Cin, ldx, ldw, ldy, /*out_f32=*/0, stream);
+  } else if (dtype == LASR_F32) {
+    int rc = gemm_simt_nt(static_cast<const float*>(x), static_cast<const float*>(w), static_cast<float*>(y), bias,
+                          lengths, T, M, Cout, Cin, ldx, ldw, ldy, stream);
+    if (rc) return rc;
+    if (stats != nullptr) return colstats(y, stats, M, Cout, ldy, dtype, stream);
+    return LASR_OK;
+  }
+  return LASR_ERR_BAD_DTYPE;
+}
+
+int lasr_pwconv_wgrad(const void* dy, const void* x, float* dw, int M, int Cin, int Cout, int lddy, int ldx, int lddw,
+                      int dtype, lasr_stream_t stream) {
+  if (dtype == LASR_BF16) return gemm_tc_tn_accum(dy, x, dw, M, Cout, Cin, lddy, ldx, lddw, stream);
+  if (dtype == LASR_F32)
+    return gemm_simt_tn_accum(static_cast<const float*>(dy), static_cast<const float*>(x), dw, M, Cout, Cin, lddy, ldx,
+                              lddw, stream);
+  return LASR_ERR_BAD_DTYPE;
+}
+
+}  // extern "C"

@@ -1,0 +1,481 @@
+// Pointwise (1x1) convolution as a tcgen05 / TMEM GEMM for sm_100a.
+//
+//   D[M, N] (+)= A[M, K] * B[N, K]^T          bf16 operands, fp32 accumulation in tensor memory
+//
+// K-major mode (forward / data-gradient):  A = activations [frames, Cin] (channels-last, so K is the
+//   contiguous axis), B = weights [Cout, Cin].  Both operands are TMA-loaded as 128-byte-swizzled
+//   {64 x rows} boxes and consumed by tcgen05.mma through K-major shared-memory descriptors.
+// MN-major mode (weight-gradient):  dW[Cout, Cin] = dY[frames, Cout]^T * X[frames, Cin]; the reduction
+//   runs over frames, so both operands are "MN-major" (the M / N axis is the contiguous one).  They are
+//   loaded as {64 channels x 64 frames} swizzled boxes and described to the MMA unit with MN-major
+//   descriptors; the frame axis is split over CTAs and partial products are reduced with fp32 vector RED.
+//
+// Structure: persistent, warp-specialised CTA of 256 threads, one CTA per SM.
+//   warp 0   TMA producer (one elected lane)      smem ring of STAGES x {A 16 KB, B BN*128 B}
+//   warp 1   MMA issuer   (one elected lane)      4 x tcgen05.mma (K=16) per 64-wide k-block
+//   warp 2   TMEM allocator / deallocator         2 accumulator buffers of BN columns each
+//   warps 4-7 epilogue: tcgen05.ld 32x32b -> registers -> bias / MaskCNN row mask / BatchNorm partial
+//            statistics (warp butterfly transpose-reduce) -> bf16|fp32 global stores, overlapped with the
+//            next tile's MMAs through the double-buffered accumulator.
+//
+// Replaces: nn.Conv1d(Cin, Cout, kernel_size=1) call sites models/QuartNet.py:22-23,31 / :62-63 / :145-146 / :275
+// and MaskCNN (:309-321) + the statistics pass of nn.BatchNorm1d (:24,35) which are folded into the epilogue.
+#include "common.cuh"
+
+namespace lasr {
+
+struct GemmTcParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int k_splits, kb_per_split;
+  void* out;
+  int ldc;
+  int out_f32;
+  int vec_ok;
+  const float* bias;
+  const int32_t* lengths;
+  int T;
+  float* stats;
+};
+
+template <int BN>
+struct GemmTcCfg {
+  static constexpr int BM = 128;
+  static constexpr int BK = 64;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// warp-level transpose-reduce: on entry lane r holds f[0..31] (row r, 32 columns); on exit every lane j
+// returns sum over the 32 rows of column j.  31 shuffles instead of 32*5.
+__device__ __forceinline__ float warp_column_sums(const float (&f)[32], int lane) {
+  float a[16];
+  {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float send = hi ? f[i] : f[i + 16];
+      float keep = hi ? f[i + 16] : f[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  float b[8];
+  {
+    const bool hi = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float send = hi ? a[i] : a[i + 8];
+      float keep = hi ? a[i + 8] : a[i];
+      b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  float c[4];
+  {
+    const bool hi = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float send = hi ? b[i] : b[i + 4];
+      float keep = hi ? b[i + 4] : b[i];
+      c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  float d[2];
+  {
+    const bool hi = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      float send = hi ? c[i] : c[i + 2];
+      float keep = hi ? c[i + 2] : c[i];
+      d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+  }
+  const bool hi = lane & 1;
+  float send = hi ? d[0] : d[1];
+  float keep = hi ? d[1] : d[0];
+  return keep + __shfl_xor_sync(0xffffffffu, send, 1);
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+// EPI: 0 = store (bias / mask / stats), 1 = fp32 RED accumulate (split-K weight gradient)
+template <int BN, bool MN_MAJOR, int EPI>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const GemmTcParams p) {
+  using Cfg = GemmTcCfg<BN>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  constexpr int A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  // 128B-swizzled tiles need 1024-byte aligned bases
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar[0], 1);
+    mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 4);
+    mbar_init(&tmem_empty_bar[1], 4);
+    mbar_fence_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_ptr_smem, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
+  const int num_tiles = tiles_mn * p.k_splits;
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int split = tile / tiles_mn;
+        const int mn = tile - split * tiles_mn;
+        const int m_blk = mn / p.num_n_blocks;
+        const int n_blk = mn - m_blk * p.num_n_blocks;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          if constexpr (!MN_MAJOR) {
+            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
+#pragma unroll
+            for (int c = 0; c < BM / 64; ++c)
+              tma_load_2d(sa + c * (64 * BK * 2), &tma_a, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c)
+              tma_load_2d(sb + c * (64 * BK * 2), &tma_b, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, MN_MAJOR ? 1 : 0, MN_MAJOR ? 1 : 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local_tile = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+        const int split = tile / tiles_mn;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        const int acc = local_tile & 1;
+        const uint32_t acc_phase = (local_tile >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            uint64_t da, db;
+            if constexpr (!MN_MAJOR) {
+              // K-major, SW128: 8-row groups 1024 B apart; 16 bf16 of K = 32 B inside the swizzle atom
+              da = umma_desc_sw128(sa + k * 32, 16, 1024);
+              db = umma_desc_sw128(sb + k * 32, 16, 1024);
+            } else {
+              // MN-major, SW128: 64-channel chunks 8192 B apart (LBO), 8-frame groups 1024 B apart (SBO);
+              // 16 frames of K = 2048 B
+              da = umma_desc_sw128(sa + k * 2048, 64 * BK * 2, 1024);
+              db = umma_desc_sw128(sb + k * 2048, 64 * BK * 2, 1024);
+            }
+            umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp_idx >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp_idx - 4;  // == warp_idx % 4: the TMEM lane quarter this warp may access
+    int local_tile = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
+      const int split = tile / tiles_mn;
+      const int mn = tile - split * tiles_mn;
+      const int m_blk = mn / p.num_n_blocks;
+      const int n_blk = mn - m_blk * p.num_n_blocks;
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = (local_tile >> 1) & 1;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+
+      const int row = m_blk * BM + ew * 32 + lane;
+      const bool row_ok = row < p.M;
+      bool keep = true;
+      if (EPI == 0 && p.lengths != nullptr && row_ok) {
+        const int n = row / p.T;
+        keep = (row - n * p.T) < p.lengths[n];
+      }
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int col0 = n_blk * BN + ch * 32;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(taddr0 + ch * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+
+        if constexpr (EPI == 0) {
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
+          }
+          if (!keep || !row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          }
+          if (p.stats != nullptr) {
+            const float s = warp_column_sums(f, lane);
+            float q[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) q[j] = f[j] * f[j];
+            const float ss = warp_column_sums(q, lane);
+            if (col0 + lane < p.N) {
+              float* dst = p.stats + static_cast<size_t>(m_blk * 4 + ew) * 2 * p.N + col0 + lane;
+              dst[0] = s;
+              dst[p.N] = ss;
+            }
+          }
+          if (row_ok) {
+            const bool full = (col0 + 32 <= p.N) && p.vec_ok;
+            if (p.out_f32) {
+              float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc + col0;
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) dst[j] = f[j];
+              }
+            } else {
+              __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<size_t>(row) * p.ldc + col0;
+              if (full) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 u;
+                  u.x = f32x2_to_bf16x2(f[j], f[j + 1]);
+                  u.y = f32x2_to_bf16x2(f[j + 2], f[j + 3]);
+                  u.z = f32x2_to_bf16x2(f[j + 4], f[j + 5]);
+                  u.w = f32x2_to_bf16x2(f[j + 6], f[j + 7]);
+                  *reinterpret_cast<uint4*>(dst + j) = u;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) dst[j] = __float2bfloat16_rn(f[j]);
+              }
+            }
+          }
+        } else {
+          if (row_ok) {
+            float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc + col0;
+            if ((col0 + 32 <= p.N) && p.vec_ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(dst + j, f[j]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t pitch_bytes,
+                      uint32_t box0, uint32_t box1, bool swizzle128) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (fn == nullptr) return LASR_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0) return LASR_ERR_ALIGNMENT;
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? LASR_OK : LASR_ERR_DRIVER;
+}
+
+template <int BN, bool MN_MAJOR, int EPI>
+static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p, int grid,
+                       cudaStream_t stream) {
+  using Cfg = GemmTcCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MN_MAJOR, EPI>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      lasr_set_cuda_error(e);
+      return LASR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  gemm_tc_kernel<BN, MN_MAJOR, EPI><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+static int pick_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256)); }
+
+// y[M, N] = x[M, K] w[N, K]^T, bf16 in, bf16/fp32 out
+int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const int32_t* lengths, int T, float* stats,
+               int M, int N, int K, int lda, int ldb, int ldc, int out_f32, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return LASR_ERR_BAD_SHAPE;
+  if ((lda % 8) || (ldb % 8)) return LASR_ERR_ALIGNMENT;
+  const int BN = pick_bn(N);
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d_bf16(&ta, a, K, M, static_cast<uint64_t>(lda) * 2, 64, 128, true);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tb, b, K, N, static_cast<uint64_t>(ldb) * 2, 64, BN, true);
+  if (rc) return rc;
+  GemmTcParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_m_blocks = cdiv(M, 128);
+  p.num_n_blocks = cdiv(N, BN);
+  p.num_k_blocks = cdiv(K, 64);
+  p.k_splits = 1;
+  p.kb_per_split = p.num_k_blocks;
+  p.out = out;
+  p.ldc = ldc;
+  p.out_f32 = out_f32;
+  const int esz = out_f32 ? 4 : 2;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((static_cast<size_t>(ldc) * esz) % 16 == 0);
+  p.bias = bias;
+  p.lengths = lengths;
+  p.T = T;
+  p.stats = stats;
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  switch (BN) {
+    case 32: return launch_inst<32, false, 0>(ta, tb, p, grid, stream);
+    case 64: return launch_inst<64, false, 0>(ta, tb, p, grid, stream);
+    case 128: return launch_inst<128, false, 0>(ta, tb, p, grid, stream);
+    default: return launch_inst<256, false, 0>(ta, tb, p, grid, stream);
+  }
+}
+
+// dw[M=Cout, N=Cin] += dy[R, Cout]^T x[R, Cin]   (R = frames), fp32 RED accumulate
+int gemm_tc_tn_accum(const void* dy, const void* x, float* dw, int R, int Cout, int Cin, int lddy, int ldx, int lddw,
+                     cudaStream_t stream) {
+  if (R <= 0 || Cout <= 0 || Cin <= 0) return LASR_ERR_BAD_SHAPE;
+  if ((lddy % 8) || (ldx % 8)) return LASR_ERR_ALIGNMENT;
+  const int BN = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d_bf16(&ta, dy, Cout, R, static_cast<uint64_t>(lddy) * 2, 64, 64, true);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tb, x, Cin, R, static_cast<uint64_t>(ldx) * 2, 64, 64, true);
+  if (rc) return rc;
+  GemmTcParams p{};
+  p.M = Cout;
+  p.N = Cin;
+  p.K = R;
+  p.num_m_blocks = cdiv(Cout, 128);
+  p.num_n_blocks = cdiv(Cin, BN);
+  p.num_k_blocks = cdiv(R, 64);
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  int splits = (2 * kNumSMs) / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > p.num_k_blocks) splits = p.num_k_blocks;
+  p.kb_per_split = cdiv(p.num_k_blocks, splits);
+  p.k_splits = cdiv(p.num_k_blocks, p.kb_per_split);
+  p.out = dw;
+  p.ldc = lddw;
+  p.out_f32 = 1;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(dw) & 15) == 0) && ((static_cast<size_t>(lddw) * 4) % 16 == 0);
+  const int total = tiles * p.k_splits;
+  const int grid = total < kNumSMs ? total : kNumSMs;
+  switch (BN) {
+    case 64: return launch_inst<64, true, 1>(ta, tb, p, grid, stream);
+    case 128: return launch_inst<128, true, 1>(ta, tb, p, grid, stream);
+    default: return launch_inst<256, true, 1>(ta, tb, p, grid, stream);
+  }
+}
+
+}  // namespace lasr
