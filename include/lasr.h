@@ -71,17 +71,17 @@ int lasr_cast_weight(const float* w, void* out, int rows, int cols, int transpos
 
 /* ------------------------------------------------------------------------------------------------
  * Depthwise Conv1d  (replaces nn.Conv1d(C, C, k, stride, padding=k//2, groups=C, bias=False),
- * models/QuartNet.py:14-21,30).  x [N, T_in, C], w [C, K] fp32, y [N, T_out, C],
+ * models/QuartNet.py:14-21,30).  x [N, T_in, C], wt [K, C] fp32 (TAP-MAJOR: wt[j,c] = weight[c,0,j]; lasr_cast_weight(transpose=1)), y [N, T_out, C],
  * T_out = (T_in + 2*(K/2) - K)/stride + 1.
  *   flip = 0: y[n,t,c] = sum_j w[c,j] * x[n, t*stride + j - K/2, c]                (forward)
  *   flip = 1: same with w reversed along j (stride must be 1): the data gradient of the forward.
  *   addend (nullable, [N, T_out, C]): added to the result (used to fuse the residual-branch dgrad).
  * ---------------------------------------------------------------------------------------------- */
-int lasr_dwconv1d_fwd(const void* x, const float* w, void* y, const void* addend, int N, int T_in, int T_out, int C,
+int lasr_dwconv1d_fwd(const void* x, const float* wt, void* y, const void* addend, int N, int T_in, int T_out, int C,
                       int K, int stride, int flip, int dtype, lasr_stream_t stream);
-/* weight gradient: dw[c,j] += sum_{n,t} dy[n,t,c] * x[n, t*stride + j - K/2, c]; dw fp32 [C,K], ACCUMULATED
+/* weight gradient: dwt[j,c] += sum_{n,t} dy[n,t,c] * x[n, t*stride + j - K/2, c]; dwt fp32 [K,C] tap-major, ACCUMULATED
  * (caller zeroes).  Deterministic only up to fp32 atomic ordering. */
-int lasr_dwconv1d_wgrad(const void* x, const void* dy, float* dw, int N, int T_in, int T_out, int C, int K, int stride,
+int lasr_dwconv1d_wgrad(const void* x, const void* dy, float* dwt, int N, int T_in, int T_out, int C, int K, int stride,
                         int dtype, lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -105,54 +105,65 @@ int lasr_pwconv_wgrad(const void* dy, const void* x, float* dw, int M, int Cin, 
                       int dtype, lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * BatchNorm1d(eps=1e-3) pieces (replaces nn.BatchNorm1d, models/QuartNet.py:24,35,64,147).
+ * BatchNorm1d(eps=1e-3) pieces (replaces nn.BatchNorm1d, models/QuartNet.py:24,35,64,147), fused with ReLU
+ * (:36-37, :77), the residual add (:76) and the squeeze-excitation scale (models/QuartNetContextSE.py:23,55).
  * ---------------------------------------------------------------------------------------------- */
-/* reduce the per-group partials, produce mean / invstd (biased variance), the folded scale/shift
- * (scale = gamma*invstd, shift = beta - mean*scale) and update running stats (momentum, unbiased var). */
+/* fold the per-group partials (layout of lasr_pwconv_fwd's `stats`) into mean / invstd (biased variance), the
+ * folded scale = gamma*invstd and shift = beta - mean*scale, and update the running statistics
+ * (momentum, unbiased variance; running_* nullable). count = number of rows reduced (N*T). */
 int lasr_bn_finalize(const float* stats, int groups, int C, int count, float eps, float momentum, const float* gamma,
                      const float* beta, float* mean, float* invstd, float* scale, float* shift, float* running_mean,
                      float* running_var, lasr_stream_t stream);
 /* eval mode: scale/shift from the running statistics */
 int lasr_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                         float eps, float* scale, float* shift, int C, lasr_stream_t stream);
-/* generic per-channel column sums of a [M, C] matrix: out partials [groups, nstat?]; used for SE squeeze:
- * sums[n, c] = sum_t y[n, t, c]  (y [N, T, C]) */
+/* sums[n, c] = sum_t y[n, t, c] over ALL T frames (SE squeeze numerator, models/QuartNetContextSE.py:11,21) */
 int lasr_sum_over_time(const void* y, float* sums, int N, int T, int C, int dtype, lasr_stream_t stream);
 
-/* out = act( scale1*y + shift1 [* gate[n,c]] [+ scale2*r + shift2] )   (fused BN-apply, SE scale, residual
- * add, ReLU: models/QuartNet.py:35-37,75-77, models/QuartNetContextSE.py:55) */
+/* out = act( (scale1*y + shift1) [* gate[n,c]] [+ scale2*r + shift2] );  y, r, out [M, C]; gate [M/T, C] nullable;
+ * r/scale2/shift2 nullable together.  One pass. */
 int lasr_bn_apply_act_fwd(const void* y, const float* scale1, const float* shift1, const void* r, const float* scale2,
                           const float* shift2, const float* gate, void* out, int M, int C, int T, int act, int dtype,
                           lasr_stream_t stream);
-/* backward, pass 1: with g = dout * (act==RELU ? out > 0 : 1):
- * partials[group, 0..3, C] = sum g, sum g*y, sum g*r (r nullable -> 0), over the group's rows.
- * when gate != NULL: sums use g*gate for the first branch: [0]=sum g*gate, [1]=sum g*gate*y, [2]=sum g*r, [3]=sum g.
- * groups = lasr_bn_bwd_groups(M) */
-int lasr_bn_bwd_groups(int M);
-int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, const void* r, const float* gate,
-                           float* partials, int M, int C, int T, int act, int dtype, lasr_stream_t stream);
-/* pass 1b: fold partials into parameter grads and per-channel coefficients.
- * dgamma/dbeta are ACCUMULATED (+=).  coef [3, C]: dy = coef[0]*g + coef[1]*y + coef[2] */
-int lasr_bn_bwd_finalize(const float* partials, int groups, int C, int count, int sum_idx_g, int sum_idx_gx,
+
+/* backward pass 1.  With g = dout * (act == RELU ? out > 0 : 1), per (utterance n, time chunk k):
+ *   partials[(n*chunks + k), 0, c] = sum_t g, [.,1,c] = sum_t g*y, [.,2,c] = sum_t g*r (0 if r == NULL)
+ * chunks = lasr_bn_bwd_chunks(N, T); chunks never straddle utterances so per-(n,c) sums (SE) fall out too. */
+int lasr_bn_bwd_chunks(int N, int T);
+int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, const void* r, float* partials, int N,
+                           int T, int C, int chunks, int act, int dtype, lasr_stream_t stream);
+/* pass 1b: sum slots idx_g / idx_gx of partials [groups, nslots, C] over the groups, accumulate (+=) the
+ * parameter gradients dgamma / dbeta (nullable) and emit coef [3, C] such that
+ *   d(input of this BN) = coef[0]*g + coef[1]*x + coef[2]      (x = the BN input y or r) */
+int lasr_bn_bwd_finalize(const float* partials, int groups, int nslots, int C, int count, int idx_g, int idx_gx,
                          const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
                          float* coef, lasr_stream_t stream);
-/* pass 2: dy = mask(coef1[0]*g*gate + coef1[1]*y + coef1[2]);  dr = coef2[0]*g + coef2[1]*r + coef2[2]
- * (dr / r / coef2 nullable together; lengths nullable = no mask; gate nullable) */
+/* pass 2: dy = mask_t<len( coef1[0]*(g*gate[n,c] + extra[n,c]) + coef1[1]*y + coef1[2] ),
+ *         dr =            coef2[0]*g + coef2[1]*r + coef2[2]
+ * (gate/extra nullable together; r/dr/coef2 nullable together; lengths nullable = no MaskCNN).  The mask zeroes
+ * the gradient that reaches the pointwise conv at padded frames exactly like masked_fill's backward
+ * (models/QuartNet.py:320). */
 int lasr_bn_act_bwd_apply(const void* dout, const void* out, const void* y, const void* r, const float* gate,
-                          const float* coef1, const float* coef2, const int32_t* lengths, int T, void* dy, void* dr,
-                          int M, int C, int act, int dtype, lasr_stream_t stream);
+                          const float* extra, const float* coef1, const float* coef2, const int32_t* lengths, int T,
+                          void* dy, void* dr, int M, int C, int act, int dtype, lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Squeeze-excitation (models/QuartNetContextSE.py:8-23): gate[n,:] = sigmoid(W2 * relu(W1 * s[n,:]))
- * s [N, C] fp32 (mean over ALL T frames of the BN output), W1 [C/r, C], W2 [C, C/r] fp32.
- * hidden [N, C/r] is written for the backward.
+ * Squeeze-excitation (models/QuartNetContextSE.py:8-23): gate[n,:] = sigmoid(W2 * relu(W1 * s[n,:])),
+ * s[n,c] = mean_t BN(y)[n,t,c] = scale[c]*sums[n,c]/T + shift[c]  (sums from lasr_sum_over_time).
+ * W1 [C/r, C], W2 [C, C/r] fp32 (nn.Linear layout, no bias).  s [N,C], hidden [N,C/r], gate [N,C] are written.
  * ---------------------------------------------------------------------------------------------- */
-int lasr_se_excite_fwd(const float* s, const float* w1, const float* w2, float* hidden, float* gate, int N, int C,
-                       int Cr, lasr_stream_t stream);
-/* backward: dgate [N,C] -> ds [N,C], dW1 +=, dW2 += */
-int lasr_se_excite_bwd(const float* dgate, const float* s, const float* w1, const float* w2, const float* hidden,
-                       const float* gate, float* ds, float* dw1, float* dw2, int N, int C, int Cr,
+int lasr_se_excite_fwd(const float* sums, const float* scale, const float* shift, int T, const float* w1,
+                       const float* w2, float* s, float* hidden, float* gate, int N, int C, int Cr,
                        lasr_stream_t stream);
+/* backward of the excitation from the bn_act_bwd_reduce partials: dgate[n,c] = sum_t g*BN(y) -> through sigmoid, W2,
+ * ReLU, W1 -> extra[n,c] = d s[n,c] / T (the term every frame of (n,c) receives); dW1 += , dW2 += */
+int lasr_se_excite_bwd(const float* partials, int chunks, const float* scale, const float* shift, int T,
+                       const float* w1, const float* w2, const float* s, const float* hidden, const float* gate,
+                       float* extra, float* dw1, float* dw2, int N, int C, int Cr, lasr_stream_t stream);
+/* lasr_bn_bwd_finalize for the gated branch (its upstream gradient is g*gate + extra) */
+int lasr_se_bn_bwd_finalize(const float* partials, int N, int chunks, int C, int T, const float* gate,
+                            const float* extra, const float* sums_y, const float* gamma, const float* mean,
+                            const float* invstd, float* dgamma, float* dbeta, float* coef, lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * log_softmax over classes (replaces nn.functional.log_softmax, models/QuartNet.py:290).
@@ -170,15 +181,17 @@ int lasr_log_softmax_bwd(const float* dlp, const float* lp, void* dlogits, int M
  *   x        [N, T, ldx] dtype, class c of frame t of utterance n at x[(n*T+t)*ldx + c]
  *   targets  [N, S_max] int64 (zero padded), input_lengths / target_lengths [N] int32
  *   alpha    workspace fp32 [N, T, 2*S_max+1]  (kept for the backward)
+ *   beta     same shape, nullable: when given, the beta lattice is computed CONCURRENTLY with alpha
+ *            (separate CTAs) so the backward is just the parallel combine pass
  *   nll      [N] fp32 out: -log p(target | x); +inf when no alignment exists
- * bwd: grad [N, T, ldg] dtype = (softmax - occupancy) * grad_out[n] for t < input_lengths[n], 0 after
- *      (this is also torch's "gradient w.r.t. log-probs"); beta workspace like alpha.
+ * bwd: grad [N, T, ldg] grad_dtype = (softmax - occupancy) * grad_out[n] for t < input_lengths[n], 0 after
+ *      (this is also torch's "gradient w.r.t. log-probs").
  * ---------------------------------------------------------------------------------------------- */
 int lasr_ctc_fwd(const void* x, const float* lse, const int64_t* targets, const int32_t* input_lengths,
-                 const int32_t* target_lengths, float* alpha, float* nll, int N, int T, int V, int ldx, int S_max,
-                 int blank, int dtype, lasr_stream_t stream);
+                 const int32_t* target_lengths, float* alpha, float* beta, float* nll, int N, int T, int V, int ldx,
+                 int S_max, int blank, int dtype, lasr_stream_t stream);
 int lasr_ctc_bwd(const void* x, const float* lse, const int64_t* targets, const int32_t* input_lengths,
-                 const int32_t* target_lengths, const float* alpha, float* beta, const float* nll,
+                 const int32_t* target_lengths, const float* alpha, const float* beta, const float* nll,
                  const float* grad_out, void* grad, int N, int T, int V, int ldx, int ldg, int S_max, int blank,
                  int dtype, int grad_dtype, lasr_stream_t stream);
 
@@ -186,32 +199,14 @@ int lasr_ctc_bwd(const void* x, const float* lse, const int64_t* targets, const 
  * Greedy CTC decode (replaces out.argmax(-1) train.py:80 + the collapse loop utils/asr_metrics.py:153-171).
  *   x [N, T, ldx] dtype scores (log-probs or logits; argmax ties -> lowest index, like torch.argmax)
  *   lengths [N] int32 or NULL (decode all T frames, predict.py:60)
- *   argmax  [N, T] int64 out (nullable): the raw per-frame argmax
- *   tokens  [N, T] int32 out: collapsed label ids, first counts[n] entries valid
+ *   argmax  [N, T] int64 out: the raw per-frame argmax (torch.argmax semantics)
+ *   tokens  [N, T] int32 out (nullable: argmax only): collapsed label ids, first counts[n] entries valid
  * ---------------------------------------------------------------------------------------------- */
 int lasr_greedy_decode(const void* x, const int32_t* lengths, int64_t* argmax, int32_t* tokens, int32_t* counts, int N,
                        int T, int V, int ldx, int blank, int dtype, lasr_stream_t stream);
-
-/* ------------------------------------------------------------------------------------------------
- * Log-mel frontend (replaces data_module.py:155-172 from the waveform onward, dither excluded):
- * pre-emphasis 0.97 -> zero-pad 32 -> reflect-pad 256 -> frames (hop 160) -> Hann(320) in n_fft 512 -> |rFFT|^2
- * -> 64 HTK mel filters (0..8000 Hz) -> 10*log10(max(.,1e-10)) -> per-utterance (x-mean)/std (unbiased).
- *   wave      [N, S_max] fp32, wave_len [N] int32 valid samples per utterance
- *   feats_nct [N, 64, T_max] fp32 out (nullable) -- the reference's layout, zero padded past T_n
- *   feats_ntc [N, T_max, 64] dtype out (nullable) -- the internal layout
- *   T_n = 1 + (wave_len[n] + 64) / 160
- *   workspace: lasr_logmel_workspace(N, S_max) bytes
- * ---------------------------------------------------------------------------------------------- */
-size_t lasr_logmel_workspace(int N, int S_max);
-int lasr_logmel_fwd(const float* wave, const int32_t* wave_len, float* feats_nct, void* feats_ntc, int N, int S_max,
-                    int T_max, int dtype, void* workspace, size_t workspace_bytes, lasr_stream_t stream);
-
-/* ------------------------------------------------------------------------------------------------
- * Fused Novograd step over a flat parameter segment list (scheduler/novograd.py:75-145).
- * ---------------------------------------------------------------------------------------------- */
-int lasr_novograd_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* seg_offsets,
-                       int num_segs, float lr, float beta1, float beta2, float eps, float weight_decay, int first_step,
-                       float* seg_norm_ws, lasr_stream_t stream);
+/* the collapse rule alone (utils/asr_metrics.py:159-167) on caller-supplied predictions [N, T] int64 */
+int lasr_ctc_collapse(const int64_t* predictions, const int32_t* lengths, int32_t* tokens, int32_t* counts, int N,
+                      int T, int blank, lasr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -17,38 +17,38 @@ LASR_BF16 = 1
 ACT_NONE = 0
 ACT_RELU = 1
 
+def _parse_header(path):
+    """Derive the ctypes signatures from include/lasr.h so the binding cannot drift from the C ABI."""
+    import re
+
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    sigs = {}
+    for m in re.finditer(r"\n(const char\*|int|size_t)\s+(lasr_\w+)\s*\(([^)]*)\)\s*;", text):
+        res, name, args = m.group(1), m.group(2), m.group(3).strip()
+        codes = ""
+        if args and args != "void":
+            for a in args.split(","):
+                a = a.strip()
+                if "lasr_stream_t" in a:
+                    codes += "s"
+                elif "*" in a:
+                    codes += "p"
+                elif a.startswith("size_t"):
+                    codes += "z"
+                elif a.startswith("float"):
+                    codes += "f"
+                elif a.startswith("int") or a.startswith("int32_t"):
+                    codes += "i"
+                else:
+                    raise ValueError(f"unparsed argument {a!r} in {name}")
+        sigs[name] = ({"const char*": "str", "int": "int", "size_t": "size_t"}[res], codes)
+    return sigs
+
+
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "lasr.h")
 # name -> (restype, argument codes)
-SIGNATURES = {
-    "lasr_strerror": ("str", "i"),
-    "lasr_abi_version": ("int", ""),
-    "lasr_check_device": ("int", ""),
-    "lasr_nct_to_ntc": ("int", "ppiiiis"),
-    "lasr_ntc_to_nct": ("int", "ppiiiis"),
-    "lasr_cast_weight": ("int", "ppiiiis"),
-    "lasr_dwconv1d_fwd": ("int", "ppppiiiiiiiis"),
-    "lasr_dwconv1d_wgrad": ("int", "pppiiiiiiis"),
-    "lasr_pwconv_stat_groups": ("int", "i"),
-    "lasr_pwconv_fwd": ("int", "pppppipiiiiiiis"),
-    "lasr_pwconv_wgrad": ("int", "pppiiiiiiis"),
-    "lasr_bn_finalize": ("int", "piiiffppppppppps"[:0] + "piiiffpppppppps"),
-    "lasr_bn_eval_coeffs": ("int", "ppppfppis"),
-    "lasr_sum_over_time": ("int", "ppiiiis"),
-    "lasr_bn_apply_act_fwd": ("int", "ppppppppiiiiis"),
-    "lasr_bn_bwd_groups": ("int", "i"),
-    "lasr_bn_act_bwd_reduce": ("int", "ppppppiiiiis"),
-    "lasr_bn_bwd_finalize": ("int", "piiiiipppppps"),
-    "lasr_bn_act_bwd_apply": ("int", "ppppppppippiiiis"),
-    "lasr_se_excite_fwd": ("int", "pppppiiis"),
-    "lasr_se_excite_bwd": ("int", "pppppppppiiis"),
-    "lasr_log_softmax_fwd": ("int", "pppiiiis"),
-    "lasr_log_softmax_bwd": ("int", "pppiiiis"),
-    "lasr_ctc_fwd": ("int", "pppppppiiiiiiis"),
-    "lasr_ctc_bwd": ("int", "ppppppppppiiiiiiiiis"),
-    "lasr_greedy_decode": ("int", "pppppiiiiiis"),
-    "lasr_logmel_workspace": ("size_t", "ii"),
-    "lasr_logmel_fwd": ("int", "ppppiiiipzs"),
-    "lasr_novograd_step": ("int", "pppppifffffips"),
-}
+SIGNATURES = _parse_header(HEADER_PATH)
 
 _CODES = {
     "p": ctypes.c_void_p,

@@ -1,0 +1,415 @@
+// log-softmax, CTC loss (alpha/beta lattices in log space + fused softmax-minus-occupancy gradient) and the
+// greedy CTC decode.  Replaces nn.functional.log_softmax (models/QuartNet.py:290),
+// torch.nn.CTCLoss(blank=V, reduction='none') (train.py:196, :76-78) and out.argmax(-1) +
+// WER.ctc_decoder_predictions_tensor (train.py:80, utils/asr_metrics.py:153-171).
+//
+// Lattice kernels: one CTA per (utterance, direction) -- the alpha and beta recursions of an utterance are
+// independent, so they run concurrently on different SMs.  Threads own lattice states; the previous column lives
+// in double-buffered shared memory, the emission log-prob gather for frame t+1 is issued before frame t's barrier
+// so the HBM/L2 latency overlaps the recursion.  (A single warp per utterance would be MUFU-bound: ~4 ex2/lg2 per
+// state per frame x 13-24 states per lane x 8 cycles per warp-MUFU; spreading the states over 8 warps divides that.)
+// The emission term can be read from raw logits + their row log-sum-exp, so log-probs need not be materialised.
+#include "common.cuh"
+
+#include <math_constants.h>
+
+namespace lasr {
+
+// ------------------------------------------------------------------------------------------------
+// log-softmax: one warp per row
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+log_softmax_fwd_kernel(const T* __restrict__ x, float* __restrict__ lse_out, float* __restrict__ lp, int M, int V,
+                       int ld) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const T* xr = x + static_cast<size_t>(row) * ld;
+  float m = -CUDART_INF_F;
+  for (int c = lane; c < V; c += 32) m = fmaxf(m, to_f32<T>(xr[c]));
+  m = warp_max(m);
+  float s = 0.f;
+  for (int c = lane; c < V; c += 32) s += expf(to_f32<T>(xr[c]) - m);
+  s = warp_sum(s);
+  const float lse = m + logf(s);
+  if (lane == 0) lse_out[row] = lse;
+  if (lp != nullptr) {
+    float* lr = lp + static_cast<size_t>(row) * V;
+    for (int c = lane; c < V; c += 32) lr[c] = to_f32<T>(xr[c]) - lse;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+log_softmax_bwd_kernel(const float* __restrict__ dlp, const float* __restrict__ lp, T* __restrict__ dx, int M, int V,
+                       int ld) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* dr = dlp + static_cast<size_t>(row) * V;
+  const float* lr = lp + static_cast<size_t>(row) * V;
+  float s = 0.f;
+  for (int c = lane; c < V; c += 32) s += dr[c];
+  s = warp_sum(s);
+  T* o = dx + static_cast<size_t>(row) * ld;
+  for (int c = lane; c < ld; c += 32) o[c] = from_f32<T>(c < V ? dr[c] - expf(lr[c]) * s : 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTC lattices
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  if (m == -CUDART_INF_F) return -CUDART_INF_F;
+  return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
+}
+
+constexpr int CTC_THREADS = 256;
+constexpr int CTC_MAX_SPT = 8;  // states per thread -> up to 2048 lattice states (S_max <= 1023)
+
+template <typename T>
+__global__ void __launch_bounds__(CTC_THREADS)
+ctc_lattice_kernel(const T* __restrict__ x, const float* __restrict__ lse, const int64_t* __restrict__ targets,
+                   const int32_t* __restrict__ in_len, const int32_t* __restrict__ tgt_len, float* __restrict__ alpha,
+                   float* __restrict__ beta, float* __restrict__ nll, int T_len, int ldx, int S_max, int blank) {
+  extern __shared__ float sm[];  // [2][Lp_max] lattice columns
+  const int n = blockIdx.x;
+  const bool backward = blockIdx.y == 1;
+  const int Lp_max = 2 * S_max + 1;
+  float* col[2] = {sm, sm + Lp_max};
+  const int Tn = in_len[n];
+  const int Sn = tgt_len[n];
+  const int Lp = 2 * Sn + 1;
+  const int64_t* tg = targets + static_cast<size_t>(n) * S_max;
+  float* lat = (backward ? beta : alpha) + static_cast<size_t>(n) * T_len * Lp_max;
+  const T* xn = x + static_cast<size_t>(n) * T_len * ldx;
+  const float* lsen = lse ? lse + static_cast<size_t>(n) * T_len : nullptr;
+
+  // infeasible / degenerate cases (torch: loss = inf when the target does not fit)
+  if (Tn <= 0 || Sn > S_max || Tn > T_len) {
+    if (!backward && threadIdx.x == 0) nll[n] = (Tn == 0 && Sn == 0) ? 0.f : CUDART_INF_F;
+    return;
+  }
+
+  int lab[CTC_MAX_SPT];
+  bool skip_ok[CTC_MAX_SPT];  // may take the s-2 (fwd) / s+2 (bwd) transition
+#pragma unroll
+  for (int i = 0; i < CTC_MAX_SPT; ++i) {
+    const int s = threadIdx.x + i * CTC_THREADS;
+    lab[i] = blank;
+    skip_ok[i] = false;
+    if (s < Lp && (s & 1)) {
+      lab[i] = static_cast<int>(tg[s >> 1]);
+      if (!backward)
+        skip_ok[i] = (s >= 2) && lab[i] != static_cast<int>(tg[(s >> 1) - 1]);
+      else
+        skip_ok[i] = (s + 2 < Lp) && lab[i] != static_cast<int>(tg[(s >> 1) + 1]);
+    }
+  }
+  auto emit = [&](int t, int i) -> float {
+    const float v = to_f32<T>(xn[static_cast<size_t>(t) * ldx + lab[i]]);
+    return lsen ? v - lsen[t] : v;
+  };
+
+  const int t_first = backward ? Tn - 1 : 0;
+  const int dt = backward ? -1 : 1;
+  // initial column
+  float e_cur[CTC_MAX_SPT];
+#pragma unroll
+  for (int i = 0; i < CTC_MAX_SPT; ++i) {
+    const int s = threadIdx.x + i * CTC_THREADS;
+    if (s < Lp) {
+      float v = -CUDART_INF_F;
+      const bool start = backward ? (s == Lp - 1 || s == Lp - 2) : (s == 0 || s == 1);
+      if (start) v = emit(t_first, i);
+      col[0][s] = v;
+      lat[static_cast<size_t>(t_first) * Lp_max + s] = v;
+    }
+  }
+  if (Tn > 1) {
+#pragma unroll
+    for (int i = 0; i < CTC_MAX_SPT; ++i) {
+      const int s = threadIdx.x + i * CTC_THREADS;
+      e_cur[i] = (s < Lp) ? emit(t_first + dt, i) : 0.f;
+    }
+  }
+  __syncthreads();
+
+  int cur = 0;
+  for (int step = 1; step < Tn; ++step) {
+    const int t = t_first + dt * step;
+    const float* prev = col[cur];
+    float* next = col[cur ^ 1];
+    float e_next[CTC_MAX_SPT];
+    const bool more = step + 1 < Tn;
+#pragma unroll
+    for (int i = 0; i < CTC_MAX_SPT; ++i) {
+      const int s = threadIdx.x + i * CTC_THREADS;
+      e_next[i] = (more && s < Lp) ? emit(t + dt, i) : 0.f;  // prefetch next frame's emission
+    }
+#pragma unroll
+    for (int i = 0; i < CTC_MAX_SPT; ++i) {
+      const int s = threadIdx.x + i * CTC_THREADS;
+      if (s < Lp) {
+        const float a = prev[s];
+        float b, c = -CUDART_INF_F;
+        if (!backward) {
+          b = s >= 1 ? prev[s - 1] : -CUDART_INF_F;
+          if (skip_ok[i]) c = prev[s - 2];
+        } else {
+          b = s + 1 < Lp ? prev[s + 1] : -CUDART_INF_F;
+          if (skip_ok[i]) c = prev[s + 2];
+        }
+        const float v = lse3(a, b, c) + e_cur[i];
+        next[s] = v;
+        lat[static_cast<size_t>(t) * Lp_max + s] = v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < CTC_MAX_SPT; ++i) e_cur[i] = e_next[i];
+    cur ^= 1;
+    __syncthreads();
+  }
+  if (!backward && threadIdx.x == 0) {
+    const float a = col[cur][Lp - 1];
+    const float b = Lp >= 2 ? col[cur][Lp - 2] : -CUDART_INF_F;
+    const float m = fmaxf(a, b);
+    nll[n] = (m == -CUDART_INF_F) ? CUDART_INF_F : -(m + logf(expf(a - m) + expf(b - m)));
+  }
+}
+
+// gradient: one warp per frame row.  occ[c] accumulated in warp-private shared memory.
+template <typename T, typename GT>
+__global__ void __launch_bounds__(256)
+ctc_grad_kernel(const T* __restrict__ x, const float* __restrict__ lse, const int64_t* __restrict__ targets,
+                const int32_t* __restrict__ in_len, const int32_t* __restrict__ tgt_len,
+                const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ nll,
+                const float* __restrict__ grad_out, GT* __restrict__ grad, int N, int T_len, int V, int ldx, int ldg,
+                int S_max, int blank, int warps) {
+  extern __shared__ float occ_all[];  // [warps][V]
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * warps + w;
+  if (w >= warps || row >= static_cast<long long>(N) * T_len) return;
+  float* occ = occ_all + static_cast<size_t>(w) * V;
+  const int n = static_cast<int>(row / T_len);
+  const int t = static_cast<int>(row - static_cast<long long>(n) * T_len);
+  GT* gr = grad + static_cast<size_t>(row) * ldg;
+  const int Tn = in_len[n];
+  if (t >= Tn) {
+    for (int c = lane; c < ldg; c += 32) gr[c] = from_f32<GT>(0.f);
+    return;
+  }
+  const int Sn = tgt_len[n];
+  const int Lp = 2 * Sn + 1;
+  const int Lp_max = 2 * S_max + 1;
+  const T* xr = x + static_cast<size_t>(row) * ldx;
+  const float l = lse ? lse[row] : 0.f;
+  const float nl = nll[n];
+  const float go = grad_out[n];
+  for (int c = lane; c < V; c += 32) occ[c] = 0.f;
+  __syncwarp();
+  const float* ar = alpha + static_cast<size_t>(row) * Lp_max;
+  const float* br = beta + static_cast<size_t>(row) * Lp_max;
+  const int64_t* tg = targets + static_cast<size_t>(n) * S_max;
+  for (int s = lane; s < Lp; s += 32) {
+    const int label = (s & 1) ? static_cast<int>(tg[s >> 1]) : blank;
+    const float lpv = to_f32<T>(xr[label]) - l;
+    atomicAdd(&occ[label], expf(ar[s] + br[s] + nl - lpv));
+  }
+  __syncwarp();
+  for (int c = lane; c < ldg; c += 32) {
+    float g = 0.f;
+    if (c < V) g = (expf(to_f32<T>(xr[c]) - l) - occ[c]) * go;
+    gr[c] = from_f32<GT>(g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// greedy decode
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+argmax_kernel(const T* __restrict__ x, int64_t* __restrict__ amax, long long M, int V, int ldx) {
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const T* xr = x + static_cast<size_t>(row) * ldx;
+  float best = -CUDART_INF_F;
+  int bi = 0x7fffffff;
+  for (int c = lane; c < V; c += 32) {
+    const float v = to_f32<T>(xr[c]);
+    if (v > best || (bi == 0x7fffffff)) {  // strictly greater keeps the lowest index within a lane
+      best = v;
+      bi = c;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  if (lane == 0) amax[row] = bi;
+}
+
+// one warp per utterance: keep p iff (p != prev || prev == blank) && p != blank, prev = previous FRAME's argmax
+__global__ void __launch_bounds__(32)
+ctc_collapse_kernel(const int64_t* __restrict__ amax, const int32_t* __restrict__ lengths, int32_t* __restrict__ tokens,
+                    int32_t* __restrict__ counts, int T_len, int blank) {
+  const int n = blockIdx.x, lane = threadIdx.x;
+  int len = lengths ? lengths[n] : T_len;
+  len = min(max(len, 0), T_len);
+  const int64_t* a = amax + static_cast<size_t>(n) * T_len;
+  int32_t* out = tokens + static_cast<size_t>(n) * T_len;
+  int count = 0;
+  int carry = blank;  // argmax of the frame before this chunk
+  for (int t0 = 0; t0 < len; t0 += 32) {
+    const int t = t0 + lane;
+    const int p = t < len ? static_cast<int>(a[t]) : blank;
+    int prev = __shfl_up_sync(0xffffffffu, p, 1);
+    if (lane == 0) prev = carry;
+    const bool keep = t < len && (p != prev || prev == blank) && p != blank;
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) out[count + __popc(m & ((1u << lane) - 1u))] = p;
+    count += __popc(m);
+    carry = __shfl_sync(0xffffffffu, p, 31);
+  }
+  if (lane == 0) counts[n] = count;
+}
+
+template <typename T, typename GT>
+static int ctc_grad_launch(const void* x, const float* lse, const int64_t* targets, const int32_t* il,
+                           const int32_t* tl, const float* alpha, const float* beta, const float* nll,
+                           const float* grad_out, void* grad, int N, int Tn, int V, int ldx, int ldg, int S_max,
+                           int blank, cudaStream_t stream) {
+  int warps = (96 * 1024) / (V * 4);
+  if (warps > 8) warps = 8;
+  if (warps < 1) warps = 1;
+  const int smem = warps * V * static_cast<int>(sizeof(float));
+  if (smem > 200 * 1024) return LASR_ERR_UNSUPPORTED;
+  static int configured_smem = 0;
+  if (smem > 48 * 1024 && smem > configured_smem) {
+    cudaError_t e =
+        cudaFuncSetAttribute(ctc_grad_kernel<T, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      lasr_set_cuda_error(e);
+      return LASR_ERR_CUDA;
+    }
+    configured_smem = 200 * 1024;
+  }
+  const long long rows = static_cast<long long>(N) * Tn;
+  const int grid = static_cast<int>((rows + warps - 1) / warps);
+  ctc_grad_kernel<T, GT><<<grid, 256, smem, stream>>>(static_cast<const T*>(x), lse, targets, il, tl, alpha, beta, nll,
+                                                      grad_out, static_cast<GT*>(grad), N, Tn, V, ldx, ldg, S_max,
+                                                      blank, warps);
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+}  // namespace lasr
+
+using namespace lasr;
+
+extern "C" {
+
+int lasr_log_softmax_fwd(const void* logits, float* lse, float* lp, int M, int V, int ld, int dtype,
+                         lasr_stream_t stream) {
+  if (M <= 0 || V <= 0 || ld < V) return LASR_ERR_BAD_SHAPE;
+  const int grid = cdiv(M, 8);
+  if (dtype == LASR_F32)
+    log_softmax_fwd_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(logits), lse, lp, M, V, ld);
+  else if (dtype == LASR_BF16)
+    log_softmax_fwd_kernel<__nv_bfloat16>
+        <<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(logits), lse, lp, M, V, ld);
+  else
+    return LASR_ERR_BAD_DTYPE;
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+int lasr_log_softmax_bwd(const float* dlp, const float* lp, void* dlogits, int M, int V, int ld, int dtype,
+                         lasr_stream_t stream) {
+  if (M <= 0 || V <= 0 || ld < V) return LASR_ERR_BAD_SHAPE;
+  const int grid = cdiv(M, 8);
+  if (dtype == LASR_F32)
+    log_softmax_bwd_kernel<float><<<grid, 256, 0, stream>>>(dlp, lp, static_cast<float*>(dlogits), M, V, ld);
+  else if (dtype == LASR_BF16)
+    log_softmax_bwd_kernel<__nv_bfloat16>
+        <<<grid, 256, 0, stream>>>(dlp, lp, static_cast<__nv_bfloat16*>(dlogits), M, V, ld);
+  else
+    return LASR_ERR_BAD_DTYPE;
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+int lasr_ctc_fwd(const void* x, const float* lse, const int64_t* targets, const int32_t* input_lengths,
+                 const int32_t* target_lengths, float* alpha, float* beta, float* nll, int N, int T, int V, int ldx,
+                 int S_max, int blank, int dtype, lasr_stream_t stream) {
+  if (N <= 0 || T <= 0 || V <= 0 || ldx < V || S_max < 0 || blank < 0 || blank >= V) return LASR_ERR_BAD_SHAPE;
+  const int Lp_max = 2 * S_max + 1;
+  if (Lp_max > CTC_THREADS * CTC_MAX_SPT) return LASR_ERR_UNSUPPORTED;
+  const int smem = 2 * Lp_max * static_cast<int>(sizeof(float));
+  dim3 grid(N, beta != nullptr ? 2 : 1);
+  if (dtype == LASR_F32)
+    ctc_lattice_kernel<float><<<grid, CTC_THREADS, smem, stream>>>(static_cast<const float*>(x), lse, targets,
+                                                                   input_lengths, target_lengths, alpha, beta, nll, T,
+                                                                   ldx, S_max, blank);
+  else if (dtype == LASR_BF16)
+    ctc_lattice_kernel<__nv_bfloat16><<<grid, CTC_THREADS, smem, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), lse, targets, input_lengths, target_lengths, alpha, beta, nll, T, ldx,
+        S_max, blank);
+  else
+    return LASR_ERR_BAD_DTYPE;
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+int lasr_ctc_bwd(const void* x, const float* lse, const int64_t* targets, const int32_t* input_lengths,
+                 const int32_t* target_lengths, const float* alpha, const float* beta, const float* nll,
+                 const float* grad_out, void* grad, int N, int T, int V, int ldx, int ldg, int S_max, int blank,
+                 int dtype, int grad_dtype, lasr_stream_t stream) {
+  if (N <= 0 || T <= 0 || V <= 0 || ldx < V || ldg < V || S_max < 0) return LASR_ERR_BAD_SHAPE;
+  if (alpha == nullptr || beta == nullptr) return LASR_ERR_BAD_SHAPE;
+#define LASR_CTC_ARGS \
+  x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, grad_out, grad, N, T, V, ldx, ldg, S_max, blank, stream
+  if (dtype == LASR_F32 && grad_dtype == LASR_F32) return ctc_grad_launch<float, float>(LASR_CTC_ARGS);
+  if (dtype == LASR_BF16 && grad_dtype == LASR_BF16)
+    return ctc_grad_launch<__nv_bfloat16, __nv_bfloat16>(LASR_CTC_ARGS);
+  if (dtype == LASR_BF16 && grad_dtype == LASR_F32) return ctc_grad_launch<__nv_bfloat16, float>(LASR_CTC_ARGS);
+  if (dtype == LASR_F32 && grad_dtype == LASR_BF16) return ctc_grad_launch<float, __nv_bfloat16>(LASR_CTC_ARGS);
+  return LASR_ERR_BAD_DTYPE;
+}
+
+int lasr_greedy_decode(const void* x, const int32_t* lengths, int64_t* argmax, int32_t* tokens, int32_t* counts, int N,
+                       int T, int V, int ldx, int blank, int dtype, lasr_stream_t stream) {
+  if (N <= 0 || T <= 0 || V <= 0 || ldx < V || argmax == nullptr) return LASR_ERR_BAD_SHAPE;
+  const long long M = static_cast<long long>(N) * T;
+  const int grid = static_cast<int>((M + 7) / 8);
+  if (dtype == LASR_F32)
+    argmax_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), argmax, M, V, ldx);
+  else if (dtype == LASR_BF16)
+    argmax_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), argmax, M, V, ldx);
+  else
+    return LASR_ERR_BAD_DTYPE;
+  LASR_CHECK_LAUNCH();
+  if (tokens != nullptr) {
+    ctc_collapse_kernel<<<N, 32, 0, stream>>>(argmax, lengths, tokens, counts, T, blank);
+    LASR_CHECK_LAUNCH();
+  }
+  return LASR_OK;
+}
+
+/* collapse only: predictions [N, T] int64 (e.g. an argmax computed elsewhere) -> tokens / counts */
+int lasr_ctc_collapse(const int64_t* predictions, const int32_t* lengths, int32_t* tokens, int32_t* counts, int N,
+                      int T, int blank, lasr_stream_t stream) {
+  if (N <= 0 || T <= 0 || predictions == nullptr || tokens == nullptr || counts == nullptr) return LASR_ERR_BAD_SHAPE;
+  ctc_collapse_kernel<<<N, 32, 0, stream>>>(predictions, lengths, tokens, counts, T, blank);
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,268 @@
+"""Drop-in modules for the reference's three encoder variants.
+
+Mirrors (same class names, constructor signatures, forward contract and state_dict key schema):
+    models/QuartNet.py           SeprationConv :8-52, QuartNetBlock :55-78, QuartNet12 :120-173, MyModel2 :264-291
+    models/QuartNetContext.py    QuartNet12 :125-184 (BiLSTM(256->40) splice :171-173, block6), BatchLSTM :186-199
+    models/QuartNetContextSE.py  SELayer :8-23, SeprationConv :25-72 (SE between BN and ReLU, :55)
+
+The nn.Conv1d / nn.BatchNorm1d / nn.Linear sub-modules are PARAMETER CONTAINERS only: they are created in the
+reference's order so that (a) reference checkpoints load with strict=True and vice versa, (b) the default
+initialisation under a given torch seed is identical.  Their forward() is never called: compute goes through the
+hand-written sm_100a kernels in functions.py, on channels-last activations.  Only MyModel2 is a layout boundary:
+it takes the reference's [N, 1, F, T] fp32 features and returns [N, T', V+1] fp32 log-probs.
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .functions import (Conv1x1BNReLUFn, DecoderLogSoftmaxFn, FusedDecoderCTCFn, SepConvBNFn)
+
+_PRECISION = {"default": "auto"}
+
+
+def set_default_precision(p):
+    """'bf16' (tcgen05 path), 'fp32' (exact-parity FFMA path) or 'auto' (bf16 under torch.autocast(bf16/fp16))."""
+    if p not in ("auto", "bf16", "fp32"):
+        raise ValueError(p)
+    _PRECISION["default"] = p
+
+
+def resolve_dtype(precision=None):
+    p = precision or _PRECISION["default"]
+    if p == "auto":
+        if torch.is_autocast_enabled():
+            return torch.bfloat16  # the reference's fp16 AMP (conf/conf.yaml:27-29) maps to bf16 on B200
+        return torch.float32
+    return torch.bfloat16 if p == "bf16" else torch.float32
+
+
+def _bn_buffers(bn):
+    return (bn.running_mean, bn.running_var, bn.num_batches_tracked)
+
+
+class SELayer(nn.Module):
+    """Parameter container for models/QuartNetContextSE.py:8-23 (fc.0: C->C/r, fc.2: C/r->C, no biases)."""
+
+    def __init__(self, channel, reduction=16):
+        super().__init__()
+        self.fc = nn.Sequential(
+            nn.Linear(channel, channel // reduction, bias=False),
+            nn.ReLU(inplace=True),
+            nn.Linear(channel // reduction, channel, bias=False),
+            nn.Sigmoid(),
+        )
+
+
+class SeprationConv(nn.Module):
+    """dw conv -> 1x1 conv -> (identity shuffle) -> MaskCNN -> BN -> [SE] -> ReLU(if not last) -> dropout."""
+
+    def __init__(self, in_ch, out_ch, k=33, last=False, mask=True, dilation=1, stride=1, drop_rate=0.1, se=False,
+                 _with_se=False):
+        super().__init__()
+        if dilation != 1:
+            raise NotImplementedError("dilation > 1 is never used by the reference's in-scope models")
+        self.last = last
+        self.mask = mask
+        self.k = k
+        self.stride = stride
+        self.depthwise_conv = nn.Conv1d(in_ch, in_ch, kernel_size=(k,), stride=(stride,), padding=(k // 2,),
+                                        groups=in_ch, dilation=(dilation,), bias=False)
+        self.pointwise_conv = nn.Conv1d(in_ch, out_ch, kernel_size=(1,), stride=(1,), bias=False)
+        self.bn = nn.BatchNorm1d(out_ch, eps=1e-3)
+        self.se = SELayer(out_ch, reduction=8) if _with_se else None  # ContextSE: `se=` kwarg is ignored (:46)
+        self.drop_rate = drop_rate
+
+    def _se_weights(self):
+        if self.se is None:
+            return None, None
+        return self.se.fc[0].weight, self.se.fc[2].weight
+
+    def forward(self, x, lengths, residual=None, res_x=None):
+        """x [N, T, Cin] channels-last.  `residual` = (conv1x1, bn) of the enclosing block to fuse (then ReLU is
+        applied after the add, models/QuartNet.py:75-77)."""
+        lens = lengths if self.mask else None
+        se1, se2 = self._se_weights()
+        if residual is not None:
+            rconv, rbn = residual
+            return SepConvBNFn.apply(x, res_x, lens, self.depthwise_conv.weight, self.pointwise_conv.weight,
+                                     self.bn.weight, self.bn.bias, rconv.weight, rbn.weight, rbn.bias, se1, se2,
+                                     _bn_buffers(self.bn), _bn_buffers(rbn), self.stride, True, self.training)
+        out = SepConvBNFn.apply(x, None, lens, self.depthwise_conv.weight, self.pointwise_conv.weight, self.bn.weight,
+                                self.bn.bias, None, None, None, se1, se2, _bn_buffers(self.bn), None, self.stride,
+                                not self.last, self.training)
+        if self.drop_rate > 0.0 and self.training:
+            out = torch.nn.functional.dropout(out, p=self.drop_rate, training=True)
+        return out
+
+
+class QuartNetBlock(nn.Module):
+    def __init__(self, repeat=3, in_ch=1, out_ch=32, k=33, mask=True, drop_rate=0., _with_se=False):
+        super().__init__()
+        seq = []
+        for _ in range(0, repeat - 1):
+            # reference quirk (models/QuartNet.py:60): `mask` lands in the positional `last` slot, so inner seps get
+            # last=mask and the constructor default mask=True
+            seq.append(SeprationConv(in_ch, in_ch, k, mask, drop_rate=drop_rate, _with_se=_with_se))
+        self.reside = nn.Sequential(
+            nn.Conv1d(in_ch, out_ch, kernel_size=(1,), bias=False),
+            nn.BatchNorm1d(out_ch, eps=1e-3),
+        )
+        seq.append(SeprationConv(in_ch, out_ch, k=k, last=True, mask=mask, drop_rate=drop_rate, _with_se=_with_se))
+        self.seq = nn.ModuleList(seq)
+        self.drop_rate = drop_rate
+
+    def forward(self, x, lengths):
+        start = x
+        for m in self.seq[:-1]:
+            x = m(x, lengths)
+        last = self.seq[-1]
+        if self.drop_rate > 0.0 and self.training:
+            # dropout sits between BN and the residual add (models/QuartNet.py:38,76): unfused path
+            y = last(x, lengths)
+            r = Conv1x1BNReLUFn.apply(start, self.reside[0].weight, self.reside[1].weight, self.reside[1].bias,
+                                      _bn_buffers(self.reside[1]), self.training, False)
+            return torch.relu(y + r)
+        return last(x, lengths, residual=(self.reside[0], self.reside[1]), res_x=None if x is start else start)
+
+
+class BatchLSTM(nn.Module):
+    """models/QuartNetContext.py:186-199 -- stays a torch/cuDNN call."""
+
+    def __init__(self, in_ch=128, out_ch=128, batch_first=True, bidirection=True, num_layers=1, dropout=0.):
+        super().__init__()
+        self.batch_first = batch_first
+        self.rnn = nn.LSTM(in_ch, out_ch, num_layers=num_layers, batch_first=batch_first, bidirectional=bidirection,
+                           dropout=dropout)
+
+    def forward(self, x, length, total_length=None):
+        x = nn.utils.rnn.pack_padded_sequence(x, enforce_sorted=False, lengths=length, batch_first=self.batch_first)
+        x, h = self.rnn(x)
+        x, _ = nn.utils.rnn.pad_packed_sequence(x, batch_first=self.batch_first, total_length=total_length)
+        return x, h
+
+
+_ASR13X1 = [  # (name, in, out, k)   models/QuartNet.py:130-144
+    ("block1", 256, 256, 33), ("block12", 256, 256, 33), ("block13", 256, 256, 33),
+    ("block2", 256, 256, 39), ("block22", 256, 256, 39), ("block23", 256, 256, 39),
+    ("block3", 256, 512, 51), ("block32", 512, 512, 51), ("block33", 512, 512, 51),
+    ("block4", 512, 512, 63), ("block42", 512, 512, 63), ("block43", 512, 512, 63),
+    ("block5", 512, 512, 75),
+]
+
+
+class QuartNet12(nn.Module):
+    """variant: 'base' (models/QuartNet.py), 'context' (QuartNetContext.py), 'contextse' (QuartNetContextSE.py)."""
+
+    def __init__(self, drop_rate=0., mask=False, in_c=64, variant="base"):
+        super().__init__()
+        if variant not in ("base", "context", "contextse"):
+            raise ValueError(variant)
+        self.variant = variant
+        se = variant == "contextse"
+        ctx = variant != "base"
+        self.first_cnn = SeprationConv(in_ch=in_c, out_ch=256, k=33, last=False, mask=mask, stride=2,
+                                       drop_rate=drop_rate, _with_se=se)
+        self.block_names = []
+        for name, cin, cout, k in _ASR13X1:
+            if ctx and name == "block3":
+                cin = 336  # 256 + 2*40 context channels (models/QuartNetContext.py:143)
+            setattr(self, name, QuartNetBlock(repeat=1, in_ch=cin, out_ch=cout, k=k, mask=mask, drop_rate=drop_rate,
+                                              _with_se=se))
+            self.block_names.append(name)
+        if ctx:
+            self.block6 = QuartNetBlock(repeat=1, in_ch=512, out_ch=512, k=87, mask=mask, drop_rate=drop_rate,
+                                        _with_se=se)
+            self.block_names.append("block6")
+        self.last_cnn2 = nn.Sequential(
+            nn.Conv1d(512, 1024, kernel_size=(1,), stride=(1,), bias=False),
+            nn.BatchNorm1d(1024, eps=1e-3),
+            nn.ReLU(inplace=True),
+            nn.Dropout(drop_rate),
+        )
+        if ctx:
+            self.context_rnn = BatchLSTM(in_ch=256, out_ch=40, batch_first=True, bidirection=True)
+        self.drop_rate = drop_rate
+
+    def forward_ntc(self, x, percents):
+        """x [N, T, F] channels-last features -> [N, T', 1024] channels-last."""
+        T_out = (x.shape[1] - 1) // 2 + 1
+        lengths = ops.out_lengths(T_out, percents.to(x.device))
+        x = self.first_cnn(x, lengths)
+        for name in self.block_names:
+            x = getattr(self, name)(x, lengths)
+            if name == "block23" and self.variant != "base":
+                # models/QuartNetContext.py:171-173; lengths go to the host exactly like the reference's `.cpu()`
+                c, _ = self.context_rnn(x.float(), lengths.cpu(), total_length=x.shape[1])
+                x = torch.cat((x, c.to(x.dtype)), dim=2).contiguous()
+        x = Conv1x1BNReLUFn.apply(x, self.last_cnn2[0].weight, self.last_cnn2[1].weight, self.last_cnn2[1].bias,
+                                  _bn_buffers(self.last_cnn2[1]), self.training, True)
+        if self.drop_rate > 0.0 and self.training:
+            x = torch.nn.functional.dropout(x, p=self.drop_rate, training=True)
+        return x
+
+    def forward(self, input, percents, precision=None):
+        """input [N, 1, F, T] fp32 (reference layout) -> [N, T', 1024] channels-last (internal layout)."""
+        _lib.require_device()
+        dt = resolve_dtype(precision)
+        feats = input.squeeze(dim=1).contiguous().float()
+        return self.forward_ntc(ops.nct_to_ntc(feats, dt), percents)
+
+
+class MyModel2(nn.Module):
+    """MyModel2(labels, drop_rate=0., mask=False[, in_c=64]) -- models/QuartNet.py:264-291 and siblings.
+
+    forward(input [N,1,F,T] float, percents [N] float) -> log_probs [N, T', len(labels)+1] fp32.
+    """
+
+    variant = "base"
+
+    def __init__(self, labels, drop_rate=0., mask=False, in_c=64, precision=None):
+        super().__init__()
+        self.labels = labels
+        self.precision = precision
+        self.encoder = QuartNet12(drop_rate=drop_rate, mask=mask, in_c=in_c, variant=self.variant)
+        self.decoder = nn.Conv1d(1024, len(self.labels) + 1, kernel_size=(1,))
+
+    def encode(self, input, percents):
+        return self.encoder(input, percents, precision=self.precision)
+
+    def forward(self, input, percents):
+        x = self.encode(input, percents)
+        return DecoderLogSoftmaxFn.apply(x, self.decoder.weight, self.decoder.bias)
+
+    def forward_fused_ctc(self, input, percents, targets, target_lengths):
+        """Training fast path: encoder -> decoder -> log-softmax -> CTC in one chain, log-probs never materialised.
+        Returns (nll [N], logits [N, T', ld] for decoding, t_lengths)."""
+        x = self.encode(input, percents)
+        return self.fused_ctc_from_encoded(x, percents, targets, target_lengths)
+
+    def fused_ctc_from_encoded(self, x, percents, targets, target_lengths):
+        t_lengths = ops.out_lengths(x.shape[1], percents.to(x.device))
+        nll, logits = FusedDecoderCTCFn.apply(x, self.decoder.weight, self.decoder.bias,
+                                              targets.to(x.device).long().contiguous(), t_lengths,
+                                              target_lengths.to(x.device).int().contiguous(), len(self.labels))
+        return nll, logits, t_lengths
+
+
+class MyModel2Context(MyModel2):
+    variant = "context"
+
+
+class MyModel2ContextSE(MyModel2):
+    variant = "contextse"
+
+
+# model_name -> class.  In the reference `model_name` (conf/conf.yaml:1) is only a label and the model is chosen by a
+# hard-coded import (train.py:13-14); this registry is the switch SURVEY.md 8b asks for.
+MODEL_REGISTRY = {
+    "asr12x1": MyModel2, "asr13x1": MyModel2, "quartnet": MyModel2,
+    "asr13x1context": MyModel2Context, "quartnetcontext": MyModel2Context,
+    "asr13x1contextse": MyModel2ContextSE, "quartnetcontextse": MyModel2ContextSE,
+}
+
+
+def build_model(model_name, labels, drop_rate=0., mask=False, in_c=64, precision=None):
+    key = model_name.lower().replace("_", "").replace("-", "")
+    if key not in MODEL_REGISTRY:
+        raise KeyError(f"unknown model_name {model_name!r}; known: {sorted(MODEL_REGISTRY)}")
+    return MODEL_REGISTRY[key](labels, drop_rate=drop_rate, mask=mask, in_c=in_c, precision=precision)

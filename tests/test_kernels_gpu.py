@@ -1,0 +1,181 @@
+"""Per-kernel parity (through the C ABI) against plain torch fp32/fp64 restatements of the same op.
+Tolerances: fp32 path rel 1e-4 (north_star), bf16 path rel 1e-2."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+DTYPES = [(torch.float32, 1e-4), (torch.bfloat16, 1e-2)]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from lightning_asr_b200 import _lib, ops
+    _lib.require_device()
+    return ops
+
+
+def ntc(x):  # [N, C, T] -> [N, T, C]
+    return x.transpose(1, 2).contiguous()
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("C,K,stride,T", [(64, 33, 2, 401), (256, 33, 1, 501), (256, 39, 1, 130), (336, 51, 1, 257),
+                                           (512, 63, 1, 300), (512, 75, 1, 129), (512, 87, 1, 64), (256, 33, 1, 7)])
+def test_dwconv_fwd_wgrad_dgrad(ops, dtype, tol, C, K, stride, T):
+    torch.manual_seed(C + K)
+    N = 3
+    x = torch.randn(N, C, T, device="cuda").to(dtype)
+    w = torch.randn(C, 1, K, device="cuda") / K ** 0.5
+    wt = ops.cast_weight(w.view(C, K), torch.float32, transpose=True)
+    y = ops.dwconv_fwd(ntc(x), wt, stride=stride)
+    xr = x.double().requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    yr = F.conv1d(xr, wr, stride=stride, padding=K // 2, groups=C)
+    assert y.shape == (N, yr.shape[2], C)
+    assert rel_err(y.float(), ntc(yr)) < tol
+    dy = torch.randn_like(yr).to(dtype)
+    yr.backward(dy.double())
+    dwt = ops.dwconv_wgrad(ntc(x), ntc(dy), K, stride=stride)
+    assert rel_err(dwt.t(), wr.grad.view(C, K)) < tol
+    if stride == 1:
+        addend = torch.randn(N, T, C, device="cuda").to(dtype)
+        dx = ops.dwconv_fwd(ntc(dy), wt, stride=1, flip=True, addend=addend)
+        assert rel_err(dx.float(), ntc(xr.grad) + addend.double()) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("M,Cin,Cout,T", [(1002, 64, 256, 501), (900, 256, 256, 300), (1000, 336, 512, 250),
+                                           (777, 512, 1024, 777), (640, 1024, 32, 320), (300, 1024, 4336, 100)])
+def test_pwconv_fwd_mask_stats_wgrad(ops, dtype, tol, M, Cin, Cout, T):
+    torch.manual_seed(M)
+    x = torch.randn(M, Cin, device="cuda").to(dtype)
+    w = (torch.randn(Cout, Cin, device="cuda") / Cin ** 0.5).to(dtype)
+    nb = M // T
+    lengths = torch.randint(T // 2, T + 1, (nb,), device="cuda", dtype=torch.int32)
+    y, stats = ops.pwconv_fwd(x, w, lengths=lengths, T=T, want_stats=True)
+    ref = x.double() @ w.double().t()
+    t = torch.arange(M, device="cuda")
+    ref = ref * ((t % T) < lengths[(t // T).clamp_max(nb - 1)]).unsqueeze(1)
+    assert rel_err(y.float(), ref) < tol
+    assert rel_err(stats[:, 0].sum(0), ref.sum(0)) < 10 * tol or ref.sum(0).norm() < 1e-3
+    assert rel_err(stats[:, 1].sum(0), (ref * ref).sum(0)) < tol
+    bias = torch.randn(Cout, device="cuda")
+    y2, _ = ops.pwconv_fwd(x, w, bias=bias)
+    assert rel_err(y2.float(), x.double() @ w.double().t() + bias.double()) < tol
+    dy = torch.randn(M, Cout, device="cuda").to(dtype)
+    dw = ops.pwconv_wgrad(dy, x)
+    assert rel_err(dw, dy.double().t() @ x.double()) < tol
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+@pytest.mark.parametrize("C,with_res", [(256, True), (512, False), (336, True), (1024, False)])
+def test_bn_fwd_bwd(ops, dtype, tol, C, with_res):
+    """BN(train) + residual + ReLU forward and backward vs autograd on the same (rounded) inputs."""
+    torch.manual_seed(C)
+    N, T = 4, 203
+    y = (torch.randn(N, T, C, device="cuda") * 2 + 0.5).to(dtype)
+    r = (torch.randn(N, T, C, device="cuda") - 0.3).to(dtype) if with_res else None
+    lengths = torch.tensor([T, T - 20, T // 2, 1], device="cuda", dtype=torch.int32)
+    g1, b1 = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
+    g2, b2 = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
+    from lightning_asr_b200 import _lib
+    groups = ((N * T + 127) // 128) * 4
+
+    def stats_of(t):
+        st = torch.empty(groups, 2, C, device="cuda")
+        _lib.call("lasr_pwconv_fwd", t, torch.eye(C, device="cuda").to(dtype), torch.empty_like(t), None, None, 0, st,
+                  N * T, C, C, C, C, C, _lib.dtype_code(dtype))
+        return st
+
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    st1 = ops.bn_finalize(stats_of(y), N * T, g1, b1, rm, rv, 1e-3, 0.1)
+    st2 = ops.bn_finalize(stats_of(r), N * T, g2, b2, None, None, 1e-3, 0.1) if with_res else None
+    out = ops.bn_apply_act(y, st1, r, st2, None, ops.ACT_RELU)
+
+    yd = y.double().requires_grad_(True)
+    rd = r.double().requires_grad_(True) if with_res else None
+    g1d, b1d = g1.double().requires_grad_(True), b1.double().requires_grad_(True)
+    g2d, b2d = g2.double().requires_grad_(True), b2.double().requires_grad_(True)
+    rmd, rvd = torch.zeros(C, device="cuda", dtype=torch.double), torch.ones(C, device="cuda", dtype=torch.double)
+    z = F.batch_norm(yd.reshape(-1, C), rmd, rvd, g1d, b1d, True, 0.1, 1e-3).reshape(N, T, C)
+    if with_res:
+        z = z + F.batch_norm(rd.reshape(-1, C), None, None, g2d, b2d, True, 0.1, 1e-3).reshape(N, T, C)
+    ref = torch.relu(z)
+    assert rel_err(out.float(), ref) < tol
+    assert rel_err(rm, rmd) < 1e-4 and rel_err(rv, rvd) < 1e-4
+
+    dout = torch.randn(N, T, C, device="cuda").to(dtype)
+    # the reference masks the conv output BEFORE BN, so d(conv out) is zeroed at masked frames
+    keep = (torch.arange(T, device="cuda")[None, :] < lengths[:, None]).unsqueeze(-1)
+    # autograd reference uses the forward values actually produced (out) for the ReLU mask to avoid ties
+    ref.backward(dout.double())
+    partials, chunks = ops.bn_act_bwd_reduce(dout, out, y, r, ops.ACT_RELU)
+    dg1, db1 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    coef1 = ops.bn_bwd_finalize(partials, N * T, 0, 1, g1, st1, dg1, db1)
+    coef2 = None
+    if with_res:
+        dg2, db2 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+        coef2 = ops.bn_bwd_finalize(partials, N * T, 0, 2, g2, st2, dg2, db2)
+    dy, dr = ops.bn_act_bwd_apply(dout, out, y, r, None, None, coef1, coef2, lengths, ops.ACT_RELU)
+    gtol = tol * 3
+    assert rel_err(dy.float(), yd.grad * keep) < gtol
+    assert rel_err(dg1, g1d.grad) < gtol and rel_err(db1, b1d.grad) < gtol
+    if with_res:
+        assert rel_err(dr.float(), rd.grad) < gtol
+        assert rel_err(dg2, g2d.grad) < gtol and rel_err(db2, b2d.grad) < gtol
+
+
+@pytest.mark.parametrize("V,dtype", [(29, torch.float32), (29, torch.bfloat16), (4334, torch.float32),
+                                      (4334, torch.bfloat16)])
+def test_ctc_matches_torch(ops, V, dtype):
+    torch.manual_seed(V)
+    N, T = 5, 120
+    ld = (V + 7) // 8 * 8
+    logits = torch.zeros(N, T, ld, device="cuda")
+    logits[:, :, :V] = torch.randn(N, T, V, device="cuda") * 2
+    logits = logits.to(dtype)
+    in_len = torch.tensor([T, T - 7, 60, 33, 2], device="cuda", dtype=torch.int32)
+    tgt_len = torch.tensor([30, 25, 29, 1, 5], device="cuda", dtype=torch.int32)  # last one infeasible (5 > 2)
+    S = 30
+    targets = torch.randint(0, V - 1, (N, S), device="cuda")
+    targets[2, :10] = 3  # repeated labels need the blank between them
+    blank = V - 1
+    lse, lp = ops.log_softmax_fwd(logits, V, want_lp=True)
+    lp_ref = F.log_softmax(logits[..., :V].double(), dim=-1)
+    assert rel_err(lp, lp_ref) < 1e-5
+    lpd = lp_ref.clone().requires_grad_(True)
+    nll_ref = F.ctc_loss(lpd.transpose(0, 1), targets, in_len.long(), tgt_len.long(), blank=blank, reduction="none")
+    gout = torch.rand(N, device="cuda") + 0.5
+    (nll_ref[:4] * gout[:4].double()).sum().backward()
+    for x, l in ((lp, None), (logits, lse)):
+        nll, alpha, beta = ops.ctc_fwd(x, l, targets, in_len, tgt_len, V, blank, want_beta=True)
+        assert torch.isinf(nll[4]) and nll[4] > 0
+        assert rel_err(nll[:4], nll_ref[:4]) < 1e-4
+        grad = ops.ctc_bwd(x, l, targets, in_len, tgt_len, alpha, beta, nll, gout, V, blank, x.shape[-1],
+                           torch.float32)
+        # torch's own fp32 CTC gradient is only ~2e-4 accurate; compare against the fp64 run
+        assert rel_err(grad[:4, :, :V], lpd.grad[:4]) < 5e-4
+        assert grad[:4, :, V:].abs().max().item() == 0 if x.shape[-1] > V else True
+        assert grad[1, T - 7:].abs().max().item() == 0
+
+
+def test_greedy_decode_bit_exact(ops, labels28):
+    from oracle import ctc_oracle
+    torch.manual_seed(3)
+    N, T, V = 6, 257, 29
+    x = torch.randn(N, T, V, device="cuda")
+    x[:, :, 28] += 1.5  # plenty of blanks
+    x[0, 10:20] = x[0, 10:11]  # repeated frames -> repeats collapse
+    x[1, 5, 3] = x[1, 5, 7] = 9.0  # exact tie -> lowest index
+    lens = torch.tensor([T, 200, 1, 0, 131, 64], device="cuda", dtype=torch.int32)
+    for ln in (lens, None):
+        amax, tokens, counts = ops.greedy_decode(x, ln, V, 28)
+        assert torch.equal(amax, x.argmax(-1))
+        toks_ref, _ = ctc_oracle.ctc_decoder_predictions(x.argmax(-1).cpu().tolist(), labels28,
+                                                         None if ln is None else ln.cpu().tolist())
+        for i in range(N):
+            assert tokens[i, : counts[i]].cpu().tolist() == toks_ref[i]
