@@ -192,7 +192,9 @@ class QuartNet12(nn.Module):
             x = getattr(self, name)(x, lengths)
             if name == "block23" and self.variant != "base":
                 # models/QuartNetContext.py:171-173; lengths go to the host exactly like the reference's `.cpu()`
-                c, _ = self.context_rnn(x.float(), lengths.cpu(), total_length=x.shape[1])
+                # fp32 mode keeps cuDNN's RNN GEMMs in true fp32 (TF32 alone breaks rel 1e-4)
+                with torch.backends.cudnn.flags(enabled=True, allow_tf32=(x.dtype != torch.float32)):
+                    c, _ = self.context_rnn(x.float(), lengths.cpu(), total_length=x.shape[1])
                 x = torch.cat((x, c.to(x.dtype)), dim=2).contiguous()
         x = Conv1x1BNReLUFn.apply(x, self.last_cnn2[0].weight, self.last_cnn2[1].weight, self.last_cnn2[1].bias,
                                   _bn_buffers(self.last_cnn2[1]), self.training, True)

@@ -89,8 +89,10 @@ def sep_conv(x, percents, sd, prefix, last, mask, stride, training, update_buffe
     return x
 
 
-def block(x, percents, sd, prefix, mask, training, update_buffers):
-    """models/QuartNet.py:71-78 for repeat == 1 (+ the repeat > 1 quirk of :60 is exercised by its own test)."""
+def block(x, percents, sd, prefix, mask, training, update_buffers, relu_mask=None):
+    """models/QuartNet.py:71-78 for repeat == 1 (+ the repeat > 1 quirk of :60 is exercised by its own test).
+    relu_mask (parity hook, like drop_mask): replaces the final ReLU's own gate by a supplied 0/1 tensor so a
+    reduced-precision implementation can be checked on an identical gating pattern."""
     start = x
     i = 0
     while (prefix + f".seq.{i + 1}.depthwise_conv.weight") in sd:
@@ -102,6 +104,8 @@ def block(x, percents, sd, prefix, mask, training, update_buffers):
                  update_buffers=update_buffers)
     r = F.conv1d(start, sd[prefix + ".reside.0.weight"])
     r = batch_norm(r, sd, prefix + ".reside.1", training, update_buffers)
+    if relu_mask is not None:
+        return (x + r) * relu_mask
     return torch.relu(x + r)
 
 
