@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- the north-star measurement: QuartzNet asr13x1 + CTC training throughput in audio-seconds / second.
+
+    python bench.py --gpus N --steps K --warmup W                 (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's CPU path on the host cores)
+
+A "step" is one pass of the hot path over one per-GPU batch of synthetic input (SURVEY.md section 8d, config 2:
+batch 32 x 16 s, bf16): H2D of the batch is excluded for `value` (inputs resident in HBM) and included for `e2e`.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LABELS28 = [" ", "'"] + [chr(ord("a") + i) for i in range(26)]  # conf/conf.yaml:12-13
+
+WORKLOADS = {
+    # name: (model_name, per-GPU batch, seconds, vocabulary, precision)
+    "asr13x1_b32_16s_bf16": ("asr13x1", 32, 16.0, "labels28", "bf16"),
+    "asr13x1_b4_10s_fp32": ("asr13x1", 4, 10.0, "labels28", "fp32"),
+    "contextse_b64_20s_bf16": ("asr13x1contextse", 64, 20.0, "labels28", "bf16"),
+    "context_aishell_b32_16s_bf16": ("asr13x1context", 32, 16.0, "aishell", "bf16"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def labels_for(vocab):
+    if vocab == "labels28":
+        return LABELS28
+    # AISHELL-1 char vocabulary (data/aishell1-vocab.txt has 4333 entries): only its SIZE matters for synthetic data
+    return [chr(0x4E00 + i) for i in range(4333)]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# algorithmic bytes / flops per C-ABI call (DESIGN.md "kernels"): args are the call's int/float arguments in order
+# ---------------------------------------------------------------------------------------------------------------
+def algorithmic(name, a, has):
+    """-> (family, bytes, flops) for one entry-point call; es = element size of the activation dtype."""
+    def es(code):
+        return 4 if code == 0 else 2
+    if name == "lasr_pwconv_fwd":  # T, M, Cin, Cout, ldx, ldw, ldy, dtype
+        T, M, Cin, Cout, ldx, ldw, ldy, dt = a
+        return "pwconv_gemm", es(dt) * M * (Cin + Cout), 2.0 * M * Cin * Cout
+    if name == "lasr_pwconv_wgrad":  # M, Cin, Cout, lddy, ldx, lddw, dtype
+        M, Cin, Cout, _, _, _, dt = a
+        return "pwconv_gemm", es(dt) * M * (Cin + Cout) + 4 * Cin * Cout, 2.0 * M * Cin * Cout
+    if name == "lasr_dwconv1d_fwd":  # N, T_in, T_out, C, K, stride, flip, dtype
+        N, Ti, To, C, K, s, flip, dt = a
+        return "dwconv", es(dt) * N * C * (Ti + To) + 4 * C * K, 2.0 * N * To * C * K
+    if name == "lasr_dwconv1d_wgrad":  # N, T_in, T_out, C, K, stride, dtype
+        N, Ti, To, C, K, s, dt = a
+        return "dwconv", es(dt) * N * C * (Ti + To), 2.0 * N * To * C * K
+    if name == "lasr_bn_apply_act_fwd":  # M, C, T, act, dtype  (inputs counted by the caller: y [+ r] + out)
+        M, C, T, act, dt = a
+        return "bn_pass", es(dt) * M * C * (3 if has[3] else 2), 4.0 * M * C
+    if name == "lasr_bn_act_bwd_reduce":  # N, T, C, chunks, act, dtype
+        N, T, C, ch, act, dt = a
+        return "bn_pass", es(dt) * N * T * C * ((3 if act else 2) + (1 if has[3] else 0)), 6.0 * N * T * C
+    if name == "lasr_bn_act_bwd_apply":  # T, M, C, act, dtype
+        T, M, C, act, dt = a
+        return "bn_pass", es(dt) * M * C * ((4 if act else 3) + (2 if has[3] else 0)), 6.0 * M * C
+    if name in ("lasr_ctc_fwd", "lasr_ctc_bwd", "lasr_log_softmax_fwd", "lasr_log_softmax_bwd", "lasr_greedy_decode"):
+        return "ctc", 0, 0.0
+    return "other", 0, 0.0
+
+
+def kernel_breakdown(engine, steps=3):
+    """Eager (non-graph) steps with CUDA events around every C-ABI call on the launching stream."""
+    import torch
+    from lightning_asr_b200 import _lib
+
+    fam = {}
+    calls = 0
+    for i in range(steps):
+        _lib.PROFILE = []
+        _lib.CALLS["n"] = 0
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        engine._step_eager()
+        t1.record()
+        torch.cuda.synchronize()
+        prof, _lib.PROFILE = _lib.PROFILE, None
+        calls = _lib.CALLS["n"]
+        if i == 0:
+            continue  # warm-up of the instrumented path
+        for name, args, has, e0, e1 in prof:
+            f, b, fl = algorithmic(name, args, has)
+            d = fam.setdefault(f, {"ms": 0.0, "bytes": 0, "flops": 0.0, "calls": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["bytes"] += b
+            d["flops"] += fl
+            d["calls"] += 1
+    n = max(steps - 1, 1)
+    for d in fam.values():
+        for k in d:
+            d[k] = d[k] / n
+    return fam, calls
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = max(smax, float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return None
+        busy = [v for v in sm if v > 0.5 * max(sm)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arms: the reference's own algorithm (oracle port: the reference is pure Python on torch, it cannot travel to the
+# GPU box, so the restated oracle is what runs there) timed on the host cores
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_training_throughput(model_name, seconds, labels, sample_n, steps, warmup, precision_note="fp32"):
+    import torch
+    from lightning_asr_b200.quartznet import build_model
+    from lightning_asr_b200.trainer import synthetic_batch
+    from oracle import train_oracle
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in build_model(model_name, labels, mask=True).state_dict().items()}
+    params = [v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k]
+    batch = synthetic_batch(sample_n, seconds, len(labels), seed=1234, ragged=False)
+    times = []
+    for i in range(warmup + steps):
+        for p in params:
+            p.grad = None
+        t0 = time.perf_counter()
+        loss, _, _ = train_oracle.training_step(sd, batch, labels, mask=True, training=True, update_buffers=True)
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    med = statistics.median(times)
+    return {"value": sample_n * seconds / med, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{sample_n} x {seconds:g} s utterances of the workload, fp32 fwd+bwd+CTC, median of {steps} "
+                      f"steps ({med * 1e3:.0f} ms/step)", "ms_per_step": med * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model_name, n, seconds, vocab, precision = WORKLOADS[args.workload]
+    labels = labels_for(vocab)
+    sample_n = min(n, 4)
+    steps = max(1, min(args.steps, 5))
+    warmup = max(1, min(args.warmup, 2))
+    cb = cpu_training_throughput(model_name, seconds, labels, sample_n, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "train audio-seconds/sec (QuartzNet+CTC)", "value": cb["value"],
+        "unit": "audio-s/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "model_name": model_name, "per_gpu_batch": n, "seconds": seconds,
+                   "note": "reference algorithm (oracle port of models/QuartNet.py + torch CTCLoss) on the host cores; "
+                           "each step is a bounded sample of the workload"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from lightning_asr_b200 import _lib, ddp
+    from lightning_asr_b200.trainer import LightingModule, TrainEngine, synthetic_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    _lib.require_device()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    model_name, n, seconds, vocab, precision = WORKLOADS[args.workload]
+    labels = labels_for(vocab)
+    peaks = load_peaks()
+
+    torch.manual_seed(0)
+    module = LightingModule(labels=labels, mask=True, drop_rate=0.0, model_name=model_name,
+                            precision=precision).cuda().train()
+    grad_sync = None
+    if world > 1:
+        ddp.broadcast_parameters(module)
+        grad_sync = ddp.GradSync(module, bucket_mb=8.0, overlap=True)
+    batch = synthetic_batch(n, seconds, len(labels), seed=1234 + rank, ragged=False)
+    use_graph = not args.no_graph and "context" not in model_name  # the BiLSTM splice syncs lengths to the host
+    engine = TrainEngine(module, batch, graph=use_graph, grad_sync=grad_sync, fused=True)
+    graph_note = use_graph
+    try:
+        for _ in range(max(args.warmup, 3)):
+            engine.step_device()
+        torch.cuda.synchronize()
+    except Exception as e:  # graph capture refused (e.g. a collective that cannot be captured): eager launches
+        if not use_graph:
+            raise
+        sys.stderr.write(f"[bench] CUDA-graph capture failed ({type(e).__name__}: {e}); falling back to eager\n")
+        torch.cuda.synchronize()
+        engine.use_graph, engine.graph, graph_note = False, None, False
+        for _ in range(max(args.warmup, 3)):
+            engine.step_device()
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- device-resident timing (value) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        engine.step_device()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    # ---- end-to-end timing (pinned host batch -> H2D -> step -> loss on the host, every step) ----
+    barrier()
+    t0 = time.perf_counter()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    loss_val = 0.0
+    for _ in range(args.steps):
+        loss_val = engine.step_host()
+    f1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3))
+    clocks = sampler.stop() if rank == 0 else None
+
+    ms_per_step = ms_total / args.steps
+    audio_s = n * seconds * world
+    value = audio_s / (ms_per_step * 1e-3)
+    e2e_value = audio_s / (e2e_ms / args.steps * 1e-3)
+
+    # ---- per-kernel breakdown with CUDA events (eager, after the timed region) ----
+    fam, calls = kernel_breakdown(engine, steps=3)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total_ms = sum(d["ms"] for d in fam.values())
+    top = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    tname, t = top
+    if tname == "pwconv_gemm":
+        peak = peaks["bf16_tflops_sustained"]
+        ach = t["flops"] / (t["ms"] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
+    else:
+        peak = peaks["hbm_gbs"]
+        ach = t["bytes"] / (t["ms"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+    roof.update({"traffic": None, "kernel": tname, "peak_source": peaks["source"] + " (sustained)",
+                 "share_of_step": t["ms"] / total_ms if total_ms else None,
+                 "families": {k: {"ms": round(v["ms"], 4), "GB/s": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
+                                  "TFLOP/s": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1), "calls": v["calls"]}
+                              for k, v in fam.items()}})
+    # schedule-L bytes of the whole step: asr13x1 V'=29: 159 726 elements per encoder step
+    T = 1 + (int(seconds * 16000) + 64) // 160
+    Tp = (T - 1) // 2 + 1
+    es = 2 if precision == "bf16" else 4
+    if model_name == "asr13x1":
+        sched_bytes = 159726 * es * n * Tp
+        roof["step_hbm_frac_scheduleL"] = sched_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]
+
+    cb = None
+    if not args.no_cpu_baseline:
+        cb = cpu_training_throughput(model_name, seconds, labels, min(n, 4), 3, 1)
+        cb = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {
+        "metric": "train audio-seconds/sec (QuartzNet+CTC)", "value": value, "unit": "audio-s/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
+        "config": {"workload": args.workload, "model_name": model_name, "per_gpu_batch": n, "seconds": seconds,
+                   "frames": T, "encoder_steps": Tp, "vocab": len(labels) + 1, "mask": True, "parallelism": f"dp{world}",
+                   "step": "forward + CTC + backward" + (" + NCCL grad all-reduce" if world > 1 else ""),
+                   "cuda_graph": bool(graph_note),
+                   "l2": "no flush needed: each step streams ~8 GB of activations >> 126 MB L2"},
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": engine.h2d_bytes,
+                "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": calls * args.steps, "roofline": roof, "cpu_baseline": cb, "clocks": clocks,
+        "loss": loss_val,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="asr13x1_b32_16s_bf16", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

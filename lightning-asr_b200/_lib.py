@@ -16,6 +16,7 @@ LASR_F32 = 0
 LASR_BF16 = 1
 ACT_NONE = 0
 ACT_RELU = 1
+ABI_VERSION = 1
 
 def _parse_header(path):
     """Derive the ctypes signatures from include/lasr.h so the binding cannot drift from the C ABI."""
@@ -59,6 +60,11 @@ _CODES = {
 }
 
 _lib = None
+
+# Optional instrumentation (bench.py / tools only): when PROFILE is a list, every call() appends
+# (name, int/float args, pointer-non-null flags, start_event, end_event) recorded on the launching stream; CALLS counts entry-point calls.
+PROFILE = None
+CALLS = {"n": 0}
 
 
 class LasrError(RuntimeError):
@@ -115,7 +121,16 @@ def call(name, *args):
         else:
             conv.append(int(a))
     conv.append(stream_ptr())
-    rc = getattr(lib, name)(*conv)
+    CALLS["n"] += 1
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib, name)(*conv)
+        e1.record()
+        PROFILE.append((name, tuple(a for c, a in zip(codes, conv) if c in "if"),
+                        tuple(a is not None for c, a in zip(codes, conv) if c == "p"), e0, e1))
+    else:
+        rc = getattr(lib, name)(*conv)
     if rc != 0:
         msg = lib.lasr_strerror(rc).decode()
         raise LasrError(f"{name} failed: {msg} (code {rc})")

@@ -255,3 +255,13 @@ def greedy_decode(x, lengths, V, blank, collapse=True):
     counts = torch.empty((N,), device=x.device, dtype=torch.int32) if collapse else None
     call("lasr_greedy_decode", x, lengths, amax, tokens, counts, N, T, V, ld, blank, dtype_code(x.dtype))
     return amax, tokens, counts
+
+
+def ctc_collapse(predictions, lengths, blank):
+    """predictions [N, T] int64 -> (tokens [N, T] int32, counts [N] int32): utils/asr_metrics.py:159-167."""
+    _chk(predictions, "predictions")
+    N, T = predictions.shape
+    tokens = torch.empty((N, T), device=predictions.device, dtype=torch.int32)
+    counts = torch.empty((N,), device=predictions.device, dtype=torch.int32)
+    call("lasr_ctc_collapse", predictions, lengths, tokens, counts, N, T, blank)
+    return tokens, counts

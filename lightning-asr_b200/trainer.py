@@ -1,0 +1,219 @@
+"""The caller of the hot path: a PyTorch-Lightning-free mirror of train.py's LightingModule (train.py:23-198) and a
+step engine that runs one training step (H2D -> forward -> CTC -> backward [-> gradient all-reduce] [-> optimizer])
+on one GPU, optionally replayed from a CUDA graph.
+
+  LightingModule.training_step / validation_step / forward keep the reference's batch contract
+      batch = (inputs [N,1,64,T] fp32, targets [N,S] long, percents [N] fp32, target_sizes [N] int32, paths)
+  and its arithmetic: t_lengths = torch.mul(T', percents).int() (:76), loss = mean(CTCLoss(...)) (:77-78).
+
+pytorch_lightning / hydra / comet are the reference's control plane and are out of scope;
+`self.log` becomes a plain dict (`self.logged`).
+"""
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .ctc import CTCLoss
+from .metrics import WER
+from .quartznet import build_model
+
+SAMPLE_RATE = 16000
+
+
+def num_frames(num_samples):
+    """T = 1 + (S + 2*pad) // hop with pad=32, hop=160 (data_module.py:68-70)."""
+    return 1 + (num_samples + 64) // 160
+
+
+def synthetic_batch(n, seconds, n_labels, seed=1234, ragged=False, features=True):
+    """SURVEY.md section 8d synthetic inputs.  features=True draws the normalised log-mel tensor directly
+    (randn [N,1,64,T], zero after each utterance's length like _collate_fn's padding); features=False returns raw
+    waveforms 0.05*randn clamped to [-1, 1] ([N, S] fp32) plus per-utterance sample counts for the GPU frontend."""
+    g = torch.Generator().manual_seed(seed)
+    S = int(round(seconds * SAMPLE_RATE))
+    T = num_frames(S)
+    frac = torch.linspace(0.6, 1.0, n) if ragged else torch.ones(n)
+    if features:
+        lens_t = torch.clamp((frac * T).round().long(), 1, T)
+        lens_t[-1] = T
+        x = torch.randn(n, 1, 64, T, generator=g)
+        t = torch.arange(T)
+        x = x * (t[None, :] < lens_t[:, None])[:, None, None, :]
+        percents = lens_t.float() / float(T)  # data_module.py:244
+        first = x
+    else:
+        lens_s = torch.clamp((frac * S).round().long(), 400, S)
+        lens_s[-1] = S
+        w = (0.05 * torch.randn(n, S, generator=g)).clamp_(-1.0, 1.0)
+        s = torch.arange(S)
+        first = (w * (s[None, :] < lens_s[:, None]), lens_s.int())
+        lens_t = 1 + (lens_s + 64) // 160
+        percents = lens_t.float() / float(T)
+    Tp = (T - 1) // 2 + 1
+    t_len = torch.mul(Tp, percents).int()
+    tgt_len = torch.clamp(t_len // 4, min=1).int()
+    S_max = int(tgt_len.max())
+    targets = torch.randint(0, n_labels, (n, S_max), generator=g)
+    targets = targets * (torch.arange(S_max)[None, :] < tgt_len[:, None])
+    return first, targets.long(), percents, tgt_len, [f"synthetic_{i}" for i in range(n)]
+
+
+class LightingModule(nn.Module):
+    """train.py:23-198 without pytorch_lightning.  `encoder` is the drop-in MyModel2 of `model_name`."""
+
+    def __init__(self, learning_rate=5e-3, weight_decay=1e-4, labels=None, total_epoch=50, drop_rate=0., mask=False,
+                 use_cer=False, model_name="asr13x1", precision=None, in_c=64):
+        super().__init__()
+        self.learning_rate = learning_rate
+        self.weight_decay = weight_decay
+        self.total_epoch = total_epoch
+        self.labels = labels
+        self.wer = WER(vocabulary=labels, use_cer=use_cer)  # :195
+        self.loss = CTCLoss(blank=len(labels), reduction="none")  # :196
+        self.encoder = build_model(model_name, labels, drop_rate=drop_rate, mask=mask, in_c=in_c,
+                                   precision=precision)  # :197
+        self.logged = {}
+
+    def log(self, name, value, **_):
+        self.logged[name] = value
+
+    def forward(self, inputs, percentage):
+        return self.encoder(inputs, percentage)  # :34
+
+    # -- reference-shaped steps ---------------------------------------------------------------------------------
+    def training_step_tensors(self, batch):
+        """train.py:71-78 -> (loss, out [N,T',V'], t_lengths)."""
+        input, trans, percentage, trans_lengths = batch[0], batch[1], batch[2], batch[3]
+        out = self.encoder(input, percentage)
+        t_lengths = torch.mul(out.size(1), percentage).int()
+        loss = torch.mean(self.loss(out.transpose(0, 1), trans, t_lengths, trans_lengths))
+        return loss, out, t_lengths
+
+    def training_step(self, batch, batch_idx=0, log_wer=True):
+        loss, out, t_lengths = self.training_step_tensors(batch)
+        self.log("train_loss", loss)
+        if log_wer:  # train.py:80 does this every step (a D2H sync); callers may make it periodic
+            self.log("train_wer", self.wer(out.argmax(dim=-1, keepdim=False), batch[1], batch[3], t_lengths))
+        return loss
+
+    def validation_step(self, batch, batch_idx=0):
+        """train.py:88-116 (model must be in eval mode, as PL puts it)."""
+        with torch.no_grad():
+            loss, out, t_lengths = self.training_step_tensors(batch)
+            pred = out.argmax(dim=-1, keepdim=False)
+            wer = self.wer(pred, batch[1], batch[3], t_lengths)
+            self.log("val_wer", wer)
+            self.log("val_loss", loss)
+            return {"val_loss": loss, "input": batch[0], "val_wer": wer,
+                    "pred": self.wer.ctc_decoder_predictions_tensor(pred, t_lengths),
+                    "true": self.wer.decode_reference(batch[1], batch[3]), "path": batch[-1]}
+
+    def test_step(self, batch, batch_idx=0):
+        r = self.validation_step(batch, batch_idx)
+        return {"test_loss": r["val_loss"], "input": r["input"], "test_wer": r["val_wer"], "pred": r["pred"],
+                "true": r["true"], "path": r["path"]}
+
+    # -- fast path: same arithmetic, log-probs never materialised ------------------------------------------------
+    def training_step_fused(self, batch):
+        """loss = mean_n CTC(log_softmax(decoder(encoder(x)))) with the decoder GEMM, the row log-sum-exp, the CTC
+        lattices and the (softmax - occupancy) gradient fused (functions.FusedDecoderCTCFn).  -> (loss, logits, t_len)"""
+        nll, logits, t_lengths = self.encoder.forward_fused_ctc(batch[0], batch[2], batch[1], batch[3])
+        return torch.mean(nll), logits, t_lengths
+
+
+class TrainEngine:
+    """One process per GPU.  step_host(batch) is the end-to-end call (pinned host batch -> H2D -> step -> loss on the
+    host); step_device() re-runs the step on the batch already resident in HBM.  With graph=True the whole
+    forward + backward (+ optimizer) is captured once into a CUDA graph and replayed: ~600 kernel launches per step
+    would otherwise cost more host time than the kernels take."""
+
+    def __init__(self, module, example_batch, graph=True, optimizer=None, grad_sync=None, fused=True):
+        _lib.require_device()
+        self.module = module
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.optimizer = optimizer
+        self.grad_sync = grad_sync  # callable(module) launching the gradient all-reduce (ddp.GradSync)
+        self.fused = fused
+        self.host = [t.pin_memory() if torch.is_tensor(t) else t for t in example_batch[:4]]
+        self.static = [t.to(self.dev, non_blocking=True) if torch.is_tensor(t) else t for t in self.host]
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host if torch.is_tensor(t))
+        self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        self.loss_dev = torch.zeros((), device=self.dev, dtype=torch.float32)
+        self.graph = None
+        self.use_graph = graph
+        self.launches_per_step = None
+
+    def _zero_grads(self):
+        if self.grad_sync is not None:
+            self.grad_sync.zero_and_attach()  # gradients are views of the flat all-reduce buckets
+        else:
+            for p in self.module.parameters():
+                p.grad = None
+
+    def _step_body(self):
+        m = self.module
+        if self.fused:
+            loss, _, _ = m.training_step_fused(self.static)
+        else:
+            loss, _, _ = m.training_step_tensors(self.static)
+        loss.backward()
+        if self.grad_sync is not None:
+            self.grad_sync(m)
+        if self.optimizer is not None:
+            self.optimizer.step()
+        self.loss_dev.copy_(loss.detach())
+
+    def _step_eager(self):
+        self._zero_grads()
+        self._step_body()
+
+    def _capture(self):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._step_eager()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        if self.grad_sync is None:
+            for p in self.module.parameters():
+                p.grad = None  # re-created inside the graph's private pool, then refilled by every replay
+        with torch.cuda.graph(graph):
+            if self.grad_sync is not None:
+                self.grad_sync.zero_and_attach()
+            self._step_body()
+        torch.cuda.synchronize()
+        self.graph = graph
+
+    def step_device(self):
+        """One step on the resident batch; returns the device loss scalar (no sync)."""
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        else:
+            self._step_eager()
+        return self.loss_dev
+
+    def load_batch(self, batch):
+        """Pinned-host staging + async H2D of a new batch of the SAME shapes."""
+        for h, d, src in zip(self.host, self.static, batch[:4]):
+            if torch.is_tensor(src):
+                if src.shape != h.shape:
+                    raise ValueError(f"TrainEngine batches must keep their shape: {tuple(src.shape)} vs {tuple(h.shape)}")
+                h.copy_(src)
+                d.copy_(h, non_blocking=True)
+
+    def step_host(self, batch=None):
+        """End-to-end step: H2D of the batch from pinned memory, the step, D2H of the loss.  Returns a float."""
+        if batch is not None:
+            self.load_batch(batch)
+        else:
+            for h, d in zip(self.host, self.static):
+                if torch.is_tensor(h):
+                    d.copy_(h, non_blocking=True)
+        self.step_device()
+        self.loss_host.copy_(self.loss_dev, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.loss_host)
