@@ -1,0 +1,71 @@
+"""Seeded inputs shared by make_golden.py (which runs the reference in the build container) and the tests (which
+run the oracle / the CUDA path anywhere): everything is regenerated from fixed seeds so only OUTPUTS are stored."""
+import zlib
+
+import torch
+
+LABELS28 = [" ", "'"] + [chr(ord("a") + i) for i in range(26)]  # conf/conf.yaml:12-13
+
+
+def _gen(key):
+    return torch.Generator().manual_seed(zlib.crc32(key.encode()) & 0x7FFFFFFF)
+
+
+def golden_weights(schema):
+    """Deterministic, non-trivial state dict for a (key, shape, dtype) schema: conv / linear / LSTM weights
+    ~ N(0, 1/fan_in), BatchNorm gamma ~ U(0.5, 1.5), beta / running_mean ~ N(0, 0.1), running_var ~ U(0.5, 1.5)."""
+    sd = {}
+    for key, shape, dtype in schema:
+        g = _gen(key)
+        shape = tuple(shape)
+        if key.endswith("num_batches_tracked"):
+            sd[key] = torch.zeros(shape, dtype=torch.long)
+        elif key.endswith("running_var") or (key.endswith(".weight") and len(shape) == 1):
+            sd[key] = torch.rand(shape, generator=g) + 0.5
+        elif key.endswith("running_mean") or key.endswith(".bias") or "bias_" in key:
+            sd[key] = torch.randn(shape, generator=g) * 0.1
+        else:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            sd[key] = torch.randn(shape, generator=g) / max(fan_in, 1) ** 0.5
+    return sd
+
+
+def model_inputs(n=3, frames=131, n_labels=28):
+    """features [n,1,64,frames] (zero beyond each utterance, like _collate_fn), percents with max == 1 (needed by the
+    Context variants), targets / target lengths with S_i = T'_i // 4."""
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(n, 1, 64, frames, generator=g)
+    lens = torch.tensor([frames, int(frames * 0.8), int(frames * 0.61)][:n])
+    x = x * (torch.arange(frames)[None, :] < lens[:, None])[:, None, None, :]
+    percents = lens.float() / float(frames)
+    Tp = (frames - 1) // 2 + 1
+    t_len = torch.mul(Tp, percents).int()
+    tgt_len = (t_len // 4).int()
+    targets = torch.randint(0, n_labels, (n, int(tgt_len.max())), generator=g)
+    targets = targets * (torch.arange(targets.shape[1])[None, :] < tgt_len[:, None])
+    return x, percents, targets.long(), tgt_len
+
+
+def seeded_wave(num_samples, seed):
+    """SURVEY.md 8d waveform: 0.05 * randn clamped to [-1, 1], with a slow sine so the spectrum is not flat."""
+    g = torch.Generator().manual_seed(1000 + seed)
+    t = torch.arange(num_samples, dtype=torch.float32)
+    w = 0.05 * torch.randn(num_samples, generator=g) + 0.2 * torch.sin(2 * torch.pi * (220.0 + 30 * seed) * t / 16000)
+    return w.clamp_(-1.0, 1.0)
+
+
+CTC_CASES = {"v29": (29, 40, 4, 9), "v4334": (4334, 12, 2, 4)}  # V, T, N, S
+
+
+def ctc_inputs(name):
+    """-> (log_probs [N,T,V] fp64, targets [N,S], in_len [N], tg_len [N], blank)."""
+    V, T, N, S = CTC_CASES[name]
+    g = _gen("ctc/" + name)
+    lp = torch.log_softmax(torch.randn(N, T, V, generator=g, dtype=torch.float64) * 2, dim=-1)
+    targets = torch.randint(0, V - 1, (N, S), generator=g)
+    targets[0, :3] = 2  # repeated labels need a blank between them
+    in_len = torch.tensor([T, T - 3, T // 2, 3][:N])
+    tg_len = torch.tensor([S, S - 2, 1, 5][:N])  # v29's last utterance is infeasible (5 labels in 3 frames) -> inf
+    return lp, targets, in_len, tg_len, V - 1

