@@ -57,23 +57,26 @@ def algorithmic(name, a, has):
     if name == "lasr_pwconv_fwd":  # T, M, Cin, Cout, ldx, ldw, ldy, dtype
         T, M, Cin, Cout, ldx, ldw, ldy, dt = a
         return "pwconv_gemm", es(dt) * M * (Cin + Cout), 2.0 * M * Cin * Cout
+    if name == "lasr_pwconv_dgrad":  # M, Cin, Cout, lddy, ldw, lddx, dtype
+        M, Cin, Cout, _, _, _, dt = a
+        return "pwconv_gemm", es(dt) * M * (Cin + Cout), 2.0 * M * Cin * Cout
     if name == "lasr_pwconv_wgrad":  # M, Cin, Cout, lddy, ldx, lddw, dtype
         M, Cin, Cout, _, _, _, dt = a
         return "pwconv_gemm", es(dt) * M * (Cin + Cout) + 4 * Cin * Cout, 2.0 * M * Cin * Cout
     if name == "lasr_dwconv1d_fwd":  # N, T_in, T_out, C, K, stride, flip, dtype
         N, Ti, To, C, K, s, flip, dt = a
-        return "dwconv", es(dt) * N * C * (Ti + To) + 4 * C * K, 2.0 * N * To * C * K
+        return "dwconv", es(dt) * N * C * (Ti + To + (To if has[3] else 0)) + 4 * C * K, 2.0 * N * To * C * K
     if name == "lasr_dwconv1d_wgrad":  # N, T_in, T_out, C, K, stride, dtype
         N, Ti, To, C, K, s, dt = a
         return "dwconv", es(dt) * N * C * (Ti + To), 2.0 * N * To * C * K
-    if name == "lasr_bn_apply_act_fwd":  # M, C, T, act, dtype  (inputs counted by the caller: y [+ r] + out)
-        M, C, T, act, dt = a
-        return "bn_pass", es(dt) * M * C * (3 if has[3] else 2), 4.0 * M * C
-    if name == "lasr_bn_act_bwd_reduce":  # N, T, C, chunks, act, dtype
-        N, T, C, ch, act, dt = a
+    if name == "lasr_bn_apply_act_fwd":  # M, C, T, count, eps, momentum, act, side_effects, dtype; ptrs y,bn1,r,bn2,gate,out
+        M, C, dt = a[0], a[1], a[8]
+        return "bn_pass", es(dt) * M * C * (3 if has[2] else 2), 4.0 * M * C
+    if name == "lasr_bn_act_bwd_reduce":  # N, T, C, act, dtype; ptrs dout,out,y,r,totals,per_n
+        N, T, C, act, dt = a
         return "bn_pass", es(dt) * N * T * C * ((3 if act else 2) + (1 if has[3] else 0)), 6.0 * N * T * C
-    if name == "lasr_bn_act_bwd_apply":  # T, M, C, act, dtype
-        T, M, C, act, dt = a
+    if name == "lasr_bn_act_bwd_apply":  # count, T, M, C, act, dtype; ptrs dout,out,y,r,...
+        _, T, M, C, act, dt = a
         return "bn_pass", es(dt) * M * C * ((4 if act else 3) + (2 if has[3] else 0)), 6.0 * M * C
     if name in ("lasr_ctc_fwd", "lasr_ctc_bwd", "lasr_log_softmax_fwd", "lasr_log_softmax_bwd", "lasr_greedy_decode"):
         return "ctc", 0, 0.0
@@ -235,13 +238,11 @@ def run_b200(args):
     torch.manual_seed(0)
     module = LightingModule(labels=labels, mask=True, drop_rate=0.0, model_name=model_name,
                             precision=precision).cuda().train()
-    grad_sync = None
     if world > 1:
         ddp.broadcast_parameters(module)
-        grad_sync = ddp.GradSync(module, bucket_mb=8.0, overlap=True)
     batch = synthetic_batch(n, seconds, len(labels), seed=1234 + rank, ragged=False)
     use_graph = not args.no_graph and "context" not in model_name  # the BiLSTM splice syncs lengths to the host
-    engine = TrainEngine(module, batch, graph=use_graph, grad_sync=grad_sync, fused=True)
+    engine = TrainEngine(module, batch, graph=use_graph, fused=True, world_sync=(None, 8.0) if world > 1 else None)
     graph_note = use_graph
     try:
         for _ in range(max(args.warmup, 3)):

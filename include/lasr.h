@@ -66,86 +66,105 @@ int lasr_check_device(void);
 int lasr_nct_to_ntc(const float* x, void* y, int N, int C, int T, int dtype, lasr_stream_t stream);
 /* y [N, T, C] dtype -> x [N, C, T] fp32 (used for gradients / debugging at the boundary) */
 int lasr_ntc_to_nct(const void* y, float* x, int N, int C, int T, int dtype, lasr_stream_t stream);
-/* fp32 master weights -> compute-dtype shadow, optionally transposed: w [R, Ccols] -> out [R,Ccols] or [Ccols,R] */
+/* fp32 master weights -> compute-dtype shadow (rows = 1: a whole flat parameter buffer in one launch), optionally
+ * transposed: w [R, Ccols] -> out [R,Ccols] or [Ccols,R] */
 int lasr_cast_weight(const float* w, void* out, int rows, int cols, int transpose, int dtype, lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Depthwise Conv1d  (replaces nn.Conv1d(C, C, k, stride, padding=k//2, groups=C, bias=False),
- * models/QuartNet.py:14-21,30).  x [N, T_in, C], wt [K, C] fp32 (TAP-MAJOR: wt[j,c] = weight[c,0,j]; lasr_cast_weight(transpose=1)), y [N, T_out, C],
+ * models/QuartNet.py:14-21,30).  x [N, T_in, C], w fp32 in the reference's own layout [C, 1, K], y [N, T_out, C],
  * T_out = (T_in + 2*(K/2) - K)/stride + 1.
  *   flip = 0: y[n,t,c] = sum_j w[c,j] * x[n, t*stride + j - K/2, c]                (forward)
  *   flip = 1: same with w reversed along j (stride must be 1): the data gradient of the forward.
  *   addend (nullable, [N, T_out, C]): added to the result (used to fuse the residual-branch dgrad).
  * ---------------------------------------------------------------------------------------------- */
-int lasr_dwconv1d_fwd(const void* x, const float* wt, void* y, const void* addend, int N, int T_in, int T_out, int C,
+int lasr_dwconv1d_fwd(const void* x, const float* w, void* y, const void* addend, int N, int T_in, int T_out, int C,
                       int K, int stride, int flip, int dtype, lasr_stream_t stream);
-/* weight gradient: dwt[j,c] += sum_{n,t} dy[n,t,c] * x[n, t*stride + j - K/2, c]; dwt fp32 [K,C] tap-major, ACCUMULATED
+/* weight gradient: dw[c,j] += sum_{n,t} dy[n,t,c] * x[n, t*stride + j - K/2, c]; dw fp32 [C, 1, K], ACCUMULATED
  * (caller zeroes).  Deterministic only up to fp32 atomic ordering. */
-int lasr_dwconv1d_wgrad(const void* x, const void* dy, float* dwt, int N, int T_in, int T_out, int C, int K, int stride,
+int lasr_dwconv1d_wgrad(const void* x, const void* dy, float* dw, int N, int T_in, int T_out, int C, int K, int stride,
                         int dtype, lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pointwise (1x1) Conv1d as a GEMM over frames (replaces nn.Conv1d(Cin, Cout, 1), models/QuartNet.py:22-23,31,
  * :62-63, :145-146, :275).  bf16: tcgen05/TMEM tensor-core kernel; fp32: FFMA kernel (exact fp32 parity mode).
+ * w is the weight in the reference's layout [Cout, Cin, 1], in the activation dtype (see lasr_cast_weight).
  *
  * fwd:   y[M, Cout] = x[M, Cin] * w[Cout, Cin]^T (+ bias[Cout])
  *        epilogue options (all nullable):
  *          lengths/T : zero rows whose frame index t = row % T is >= lengths[row / T]   (MaskCNN, :309-321)
- *          stats     : fp32 [stat_groups, 2, Cout] per-32-row-group partial sum / sum of squares of the
- *                      (masked) output, the BatchNorm batch statistics; stat_groups = lasr_pwconv_stat_groups(M)
- * dgrad: dx[M, Cin] = dy[M, Cout] * wT[Cin, Cout]^T   -- same kernel, caller passes the transposed weight
- * wgrad: dw[Cout, Cin] (fp32) += dy[M, Cout]^T * x[M, Cin]   (split over M, fp32 atomics; caller zeroes)
- * w / wT are in the activation dtype (see lasr_cast_weight).
+ *          stats     : double [2, Cout]: column sum / sum of squares of the (masked) output ACCUMULATED with
+ *                      RED.f64 (caller zeroes) -- the BatchNorm batch statistics, consumed by lasr_bn_*
+ * dgrad: dx[M, Cin] = dy[M, Cout] * w[Cout, Cin]          (w read as an MN-major operand: no transposed copy)
+ * wgrad: dw[Cout, Cin] (fp32) += dy[M, Cout]^T * x[M, Cin]   (split over M, fp32 RED; caller zeroes)
  * ---------------------------------------------------------------------------------------------- */
-int lasr_pwconv_stat_groups(int M);
 int lasr_pwconv_fwd(const void* x, const void* w, void* y, const float* bias, const int32_t* lengths, int T,
-                    float* stats, int M, int Cin, int Cout, int ldx, int ldw, int ldy, int dtype,
+                    double* stats, int M, int Cin, int Cout, int ldx, int ldw, int ldy, int dtype,
                     lasr_stream_t stream);
+int lasr_pwconv_dgrad(const void* dy, const void* w, void* dx, int M, int Cin, int Cout, int lddy, int ldw, int lddx,
+                      int dtype, lasr_stream_t stream);
 int lasr_pwconv_wgrad(const void* dy, const void* x, float* dw, int M, int Cin, int Cout, int lddy, int ldx, int lddw,
                       int dtype, lasr_stream_t stream);
+/* out[c] += sum_m x[m, c], c < C (fp32, caller zeroes): the decoder bias gradient (models/QuartNet.py:275) */
+int lasr_colsum(const void* x, float* out, int M, int C, int ld, int dtype, lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * BatchNorm1d(eps=1e-3) pieces (replaces nn.BatchNorm1d, models/QuartNet.py:24,35,64,147), fused with ReLU
- * (:36-37, :77), the residual add (:76) and the squeeze-excitation scale (models/QuartNetContextSE.py:23,55).
+ * BatchNorm1d(eps=1e-3) (replaces nn.BatchNorm1d, models/QuartNet.py:24,35,64,147), fused with ReLU (:36-37, :77),
+ * the residual add (:76) and the squeeze-excitation scale (models/QuartNetContextSE.py:23,55).
+ * There is no separate "finalize" launch: the apply passes fold the raw statistics into per-channel coefficients
+ * in their prologue.  The two descriptor structs are HOST structs of DEVICE pointers.
  * ---------------------------------------------------------------------------------------------- */
-/* fold the per-group partials (layout of lasr_pwconv_fwd's `stats`) into mean / invstd (biased variance), the
- * folded scale = gamma*invstd and shift = beta - mean*scale, and update the running statistics
- * (momentum, unbiased variance; running_* nullable). count = number of rows reduced (N*T). */
-int lasr_bn_finalize(const float* stats, int groups, int C, int count, float eps, float momentum, const float* gamma,
-                     const float* beta, float* mean, float* invstd, float* scale, float* shift, float* running_mean,
-                     float* running_var, lasr_stream_t stream);
-/* eval mode: scale/shift from the running statistics */
-int lasr_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
-                        float eps, float* scale, float* shift, int C, lasr_stream_t stream);
+typedef struct lasr_bn {
+  const double* sums;           /* [2, C] batch sum / sum of squares of the BN input (training); NULL = eval mode */
+  const float* gamma;           /* [C] */
+  const float* beta;            /* [C] */
+  float* running_mean;          /* [C] training: updated (momentum, nullable); eval: read */
+  float* running_var;           /* [C] training: updated with the UNBIASED variance; eval: read */
+  int64_t* num_batches_tracked; /* += 1 in training (nullable) */
+  float* save_mean;             /* [C] out (training, nullable): batch mean, kept for the backward */
+  float* save_invstd;           /* [C] out (training, nullable): 1/sqrt(biased var + eps) */
+} lasr_bn_t;
+
+typedef struct lasr_bn_bwd {
+  const float* gamma;  /* [C] */
+  const float* mean;   /* [C] save_mean of the forward */
+  const float* invstd; /* [C] save_invstd of the forward */
+  float* dgamma;       /* [C] += (nullable) */
+  float* dbeta;        /* [C] += (nullable) */
+} lasr_bn_bwd_t;
+
+/* scale = gamma*invstd, shift = beta - mean*scale ([C] each) from the descriptor; side_effects != 0 also performs the
+ * training side effects (save_mean/save_invstd, running statistics, num_batches_tracked).  count = N*T rows. */
+int lasr_bn_coeffs(const lasr_bn_t* bn, int C, int count, float eps, float momentum, float* scale, float* shift,
+                   int side_effects, lasr_stream_t stream);
 /* sums[n, c] = sum_t y[n, t, c] over ALL T frames (SE squeeze numerator, models/QuartNetContextSE.py:11,21) */
 int lasr_sum_over_time(const void* y, float* sums, int N, int T, int C, int dtype, lasr_stream_t stream);
 
-/* out = act( (scale1*y + shift1) [* gate[n,c]] [+ scale2*r + shift2] );  y, r, out [M, C]; gate [M/T, C] nullable;
- * r/scale2/shift2 nullable together.  One pass. */
-int lasr_bn_apply_act_fwd(const void* y, const float* scale1, const float* shift1, const void* r, const float* scale2,
-                          const float* shift2, const float* gate, void* out, int M, int C, int T, int act, int dtype,
-                          lasr_stream_t stream);
+/* out = act( BN1(y) [* gate[n,c]] [+ BN2(r)] );  y, r, out [M, C]; gate [M/T, C] nullable; r / bn2 nullable together.
+ * One pass; side_effects != 0 performs the training side effects of bn1 and bn2 exactly once. */
+int lasr_bn_apply_act_fwd(const void* y, const lasr_bn_t* bn1, const void* r, const lasr_bn_t* bn2, const float* gate,
+                          void* out, int M, int C, int T, int count, float eps, float momentum, int act,
+                          int side_effects, int dtype, lasr_stream_t stream);
 
-/* backward pass 1.  With g = dout * (act == RELU ? out > 0 : 1), per (utterance n, time chunk k):
- *   partials[(n*chunks + k), 0, c] = sum_t g, [.,1,c] = sum_t g*y, [.,2,c] = sum_t g*r (0 if r == NULL)
- * chunks = lasr_bn_bwd_chunks(N, T); chunks never straddle utterances so per-(n,c) sums (SE) fall out too. */
+/* backward pass 1.  With g = dout * (act == RELU ? out > 0 : 1):
+ *   totals[0][c] += sum g, totals[1][c] += sum g*y, totals[2][c] += sum g*r      double [3, C], caller zeroes
+ *   per_n[n][0][c] += sum_t g, per_n[n][1][c] += sum_t g*y                        float [N, 3, C], nullable (SE) */
 int lasr_bn_bwd_chunks(int N, int T);
-int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, const void* r, float* partials, int N,
-                           int T, int C, int chunks, int act, int dtype, lasr_stream_t stream);
-/* pass 1b: sum slots idx_g / idx_gx of partials [groups, nslots, C] over the groups, accumulate (+=) the
- * parameter gradients dgamma / dbeta (nullable) and emit coef [3, C] such that
- *   d(input of this BN) = coef[0]*g + coef[1]*x + coef[2]      (x = the BN input y or r) */
-int lasr_bn_bwd_finalize(const float* partials, int groups, int nslots, int C, int count, int idx_g, int idx_gx,
-                         const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
-                         float* coef, lasr_stream_t stream);
-/* pass 2: dy = mask_t<len( coef1[0]*(g*gate[n,c] + extra[n,c]) + coef1[1]*y + coef1[2] ),
- *         dr =            coef2[0]*g + coef2[1]*r + coef2[2]
- * (gate/extra nullable together; r/dr/coef2 nullable together; lengths nullable = no MaskCNN).  The mask zeroes
- * the gradient that reaches the pointwise conv at padded frames exactly like masked_fill's backward
- * (models/QuartNet.py:320). */
+int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, const void* r, double* totals,
+                           float* per_n, int N, int T, int C, int act, int dtype, lasr_stream_t stream);
+/* standalone: coef [3, C] with d(BN input) = coef[0]*g + coef[1]*x + coef[2], from totals slots (0, slot_gx);
+ * dgamma / dbeta += (nullable) */
+int lasr_bn_bwd_coef(const double* totals, int C, int count, int slot_gx, const float* gamma, const float* mean,
+                     const float* invstd, float* dgamma, float* dbeta, float* coef, lasr_stream_t stream);
+/* pass 2: dy = mask_t<len( c1[0]*(g*gate[n,c] + extra[n,c]) + c1[1]*y + c1[2] ),  dr = c2[0]*g + c2[1]*r + c2[2]
+ * c1 / c2 are folded from `totals` and bn1 / bn2 in the prologue (dgamma / dbeta accumulated once), unless coef1 is
+ * given (the gated SE branch).  gate/extra nullable together; r/dr/bn2 nullable together; lengths nullable = no
+ * MaskCNN.  The mask zeroes the gradient that reaches the pointwise conv at padded frames exactly like
+ * masked_fill's backward (models/QuartNet.py:320). */
 int lasr_bn_act_bwd_apply(const void* dout, const void* out, const void* y, const void* r, const float* gate,
-                          const float* extra, const float* coef1, const float* coef2, const int32_t* lengths, int T,
-                          void* dy, void* dr, int M, int C, int act, int dtype, lasr_stream_t stream);
+                          const float* extra, const double* totals, const float* coef1, const lasr_bn_bwd_t* bn1,
+                          const lasr_bn_bwd_t* bn2, int count, const int32_t* lengths, int T, void* dy, void* dr,
+                          int M, int C, int act, int dtype, lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Squeeze-excitation (models/QuartNetContextSE.py:8-23): gate[n,:] = sigmoid(W2 * relu(W1 * s[n,:])),
@@ -155,8 +174,9 @@ int lasr_bn_act_bwd_apply(const void* dout, const void* out, const void* y, cons
 int lasr_se_excite_fwd(const float* sums, const float* scale, const float* shift, int T, const float* w1,
                        const float* w2, float* s, float* hidden, float* gate, int N, int C, int Cr,
                        lasr_stream_t stream);
-/* backward of the excitation from the bn_act_bwd_reduce partials: dgate[n,c] = sum_t g*BN(y) -> through sigmoid, W2,
- * ReLU, W1 -> extra[n,c] = d s[n,c] / T (the term every frame of (n,c) receives); dW1 += , dW2 += */
+/* backward of the excitation from lasr_bn_act_bwd_reduce's per_n sums (partials [N*chunks, 3, C] with chunks = 1):
+ * dgate[n,c] = sum_t g*BN(y) -> through sigmoid, W2, ReLU, W1 -> extra[n,c] = d s[n,c] / T (the term every frame
+ * of (n,c) receives); dW1 += , dW2 += */
 int lasr_se_excite_bwd(const float* partials, int chunks, const float* scale, const float* shift, int T,
                        const float* w1, const float* w2, const float* s, const float* hidden, const float* gate,
                        float* extra, float* dw1, float* dw2, int N, int C, int Cr, lasr_stream_t stream);

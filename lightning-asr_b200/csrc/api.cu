@@ -8,15 +8,19 @@ static std::atomic<int> g_last_cuda_error{0};
 void lasr_set_cuda_error(cudaError_t e) { g_last_cuda_error.store(static_cast<int>(e)); }
 
 namespace lasr {
-int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const int32_t* lengths, int T, float* stats,
+int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const int32_t* lengths, int T, double* stats,
                int M, int N, int K, int lda, int ldb, int ldc, int out_f32, cudaStream_t stream);
+int gemm_tc_nn(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldc, int out_f32,
+               cudaStream_t stream);
+int gemm_simt_nn(const float* a, const float* b, float* c, int M, int N, int K, int lda, int ldb, int ldc,
+                 cudaStream_t stream);
 int gemm_tc_tn_accum(const void* dy, const void* x, float* dw, int R, int Cout, int Cin, int lddy, int ldx, int lddw,
                      cudaStream_t stream);
 int gemm_simt_nt(const float* a, const float* b, float* c, const float* bias, const int32_t* lengths, int T, int M,
                  int N, int K, int lda, int ldb, int ldc, cudaStream_t stream);
 int gemm_simt_tn_accum(const float* dy, const float* x, float* dw, int R, int Cout, int Cin, int lddy, int ldx,
                        int lddw, cudaStream_t stream);
-int colstats(const void* y, float* stats, int M, int N, int ld, int dtype, cudaStream_t stream);
+int colstats(const void* y, double* stats, int M, int N, int ld, int dtype, cudaStream_t stream);
 
 // [N, C, T] fp32 -> [N, T, C] out-type through a 32x32 smem transpose
 template <typename OutT>
@@ -152,10 +156,8 @@ int lasr_cast_weight(const float* w, void* out, int rows, int cols, int transpos
   return LASR_OK;
 }
 
-int lasr_pwconv_stat_groups(int M) { return cdiv(M, 128) * 4; }
-
 int lasr_pwconv_fwd(const void* x, const void* w, void* y, const float* bias, const int32_t* lengths, int T,
-                    float* stats, int M, int Cin, int Cout, int ldx, int ldw, int ldy, int dtype,
+                    double* stats, int M, int Cin, int Cout, int ldx, int ldw, int ldy, int dtype,
                     lasr_stream_t stream) {
   if (lengths != nullptr && T <= 0) return LASR_ERR_BAD_SHAPE;
   if (dtype == LASR_BF16) {
@@ -167,6 +169,15 @@ int lasr_pwconv_fwd(const void* x, const void* w, void* y, const float* bias, co
     if (stats != nullptr) return colstats(y, stats, M, Cout, ldy, dtype, stream);
     return LASR_OK;
   }
+  return LASR_ERR_BAD_DTYPE;
+}
+
+int lasr_pwconv_dgrad(const void* dy, const void* w, void* dx, int M, int Cin, int Cout, int lddy, int ldw, int lddx,
+                      int dtype, lasr_stream_t stream) {
+  if (dtype == LASR_BF16) return gemm_tc_nn(dy, w, dx, M, Cin, Cout, lddy, ldw, lddx, /*out_f32=*/0, stream);
+  if (dtype == LASR_F32)
+    return gemm_simt_nn(static_cast<const float*>(dy), static_cast<const float*>(w), static_cast<float*>(dx), M, Cin,
+                        Cout, lddy, ldw, lddx, stream);
   return LASR_ERR_BAD_DTYPE;
 }
 

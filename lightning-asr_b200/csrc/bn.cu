@@ -43,82 +43,108 @@ struct Vec8<float> {
   }
 };
 __device__ __forceinline__ void load8f(const float* p, float (&v)[8]) { Vec8<float>::load(p, v); }
+// 8 consecutive floats from shared memory as two 128-bit loads
+__device__ __forceinline__ void lds8(const float* p, float (&v)[8]) { Vec8<float>::load(p, v); }
 
 // ------------------------------------------------------------------------------------------------
-// statistics finalize: grid = C/32 blocks of (32 channels x 8 group slices)
+// BatchNorm coefficients.  The pointwise-GEMM epilogue leaves the batch sum / sum of squares of every channel in a
+// double [2, C] buffer (RED.f64); there is NO separate finalize launch: every CTA of the apply pass folds them into
+// scale = gamma * invstd, shift = beta - mean * scale in its prologue (C <= 1024 channels, a few hundred ns), and
+// CTA 0 also stores mean / invstd for the backward and updates the running statistics (momentum, unbiased variance)
+// and num_batches_tracked.  Eval mode (sums == NULL) reads the running statistics instead.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-bn_finalize_kernel(const float* __restrict__ stats, int groups, int C, double count, float eps, float momentum,
-                   const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ mean_o,
-                   float* __restrict__ invstd_o, float* __restrict__ scale_o, float* __restrict__ shift_o,
-                   float* __restrict__ running_mean, float* __restrict__ running_var) {
-  __shared__ double ss[8][32], sq[8][32];
-  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
-  double s = 0.0, q = 0.0;
-  if (c < C) {
-    for (int g = slice; g < groups; g += 8) {
-      s += static_cast<double>(stats[(static_cast<size_t>(g) * 2 + 0) * C + c]);
-      q += static_cast<double>(stats[(static_cast<size_t>(g) * 2 + 1) * C + c]);
-    }
-  }
-  ss[slice][lane] = s;
-  sq[slice][lane] = q;
-  __syncthreads();
-  if (slice == 0 && c < C) {
-#pragma unroll
-    for (int i = 1; i < 8; ++i) {
-      s += ss[i][lane];
-      q += sq[i][lane];
-    }
-    const double mean = s / count;
-    double var = q / count - mean * mean;
+__device__ __forceinline__ void bn_coeffs(const lasr_bn_t& bn, int c, int C, double count, float eps, float& scale,
+                                          float& shift, float& mean_f, float& invstd_f, double& var_out) {
+  double mean, var;
+  if (bn.sums != nullptr) {
+    mean = bn.sums[c] / count;
+    var = bn.sums[C + c] / count - mean * mean;
     if (var < 0.0) var = 0.0;
-    const double invstd = 1.0 / sqrt(var + static_cast<double>(eps));
-    mean_o[c] = static_cast<float>(mean);
-    invstd_o[c] = static_cast<float>(invstd);
-    const double g = gamma[c], b = beta[c];
-    scale_o[c] = static_cast<float>(g * invstd);
-    shift_o[c] = static_cast<float>(b - mean * g * invstd);
-    if (running_mean != nullptr) {
-      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-      running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * mean);
-      running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * unbiased);
-    }
+  } else {
+    mean = bn.running_mean[c];
+    var = bn.running_var[c];
   }
+  const double invstd = 1.0 / sqrt(var + static_cast<double>(eps));
+  const double g = bn.gamma[c], b = bn.beta[c];
+  scale = static_cast<float>(g * invstd);
+  shift = static_cast<float>(b - mean * g * invstd);
+  mean_f = static_cast<float>(mean);
+  invstd_f = static_cast<float>(invstd);
+  var_out = var;
 }
 
-__global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
-                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps,
-                                      float* __restrict__ scale, float* __restrict__ shift, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C) {
-    const float s = gamma[c] / sqrtf(rv[c] + eps);
-    scale[c] = s;
-    shift[c] = beta[c] - rm[c] * s;
+__device__ __forceinline__ void bn_side_effects(const lasr_bn_t& bn, int c, double count, float momentum, float mean_f,
+                                                float invstd_f, double var) {
+  if (bn.sums == nullptr) return;
+  if (bn.save_mean != nullptr) bn.save_mean[c] = mean_f;
+  if (bn.save_invstd != nullptr) bn.save_invstd[c] = invstd_f;
+  if (bn.running_mean != nullptr) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    bn.running_mean[c] = static_cast<float>((1.0 - momentum) * bn.running_mean[c] + momentum * mean_f);
+    bn.running_var[c] = static_cast<float>((1.0 - momentum) * bn.running_var[c] + momentum * unbiased);
   }
+  if (c == 0 && bn.num_batches_tracked != nullptr) *bn.num_batches_tracked += 1;
+}
+
+// standalone coefficient kernel (used by the squeeze-excitation path, which needs scale / shift before the apply
+// pass, and by tests): writes scale / shift [C] (+ the training side effects when side_effects != 0)
+__global__ void bn_coeffs_kernel(const lasr_bn_t bn, int C, double count, float eps, float momentum,
+                                 float* __restrict__ scale, float* __restrict__ shift, int side_effects) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float sc, sh, mf, isf;
+  double var;
+  bn_coeffs(bn, c, C, count, eps, sc, sh, mf, isf, var);
+  scale[c] = sc;
+  shift[c] = sh;
+  if (side_effects) bn_side_effects(bn, c, count, momentum, mf, isf, var);
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward apply
+// forward apply: out = act( (scale1*y + shift1) [* gate[n,c]] [+ scale2*r + shift2] )
+// persistent CTAs of 512 threads; smem: scale1, shift1, scale2, shift2 [C] each
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool HAS_R, bool HAS_GATE>
-__global__ void __launch_bounds__(256)
-bn_apply_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale1, const float* __restrict__ shift1,
-                    const T* __restrict__ r, const float* __restrict__ scale2, const float* __restrict__ shift2,
+__global__ void __launch_bounds__(512)
+bn_apply_fwd_kernel(const T* __restrict__ y, const lasr_bn_t bn1, const T* __restrict__ r, const lasr_bn_t bn2,
                     const float* __restrict__ gate, T* __restrict__ out, long long total_vec, int CV, int C, int T_len,
-                    int act) {
+                    double count, float eps, float momentum, int act, int side_effects) {
+  extern __shared__ float coef_s[];  // [4][C]
+  float* s_scale1 = coef_s;
+  float* s_shift1 = coef_s + C;
+  float* s_scale2 = coef_s + 2 * C;
+  float* s_shift2 = coef_s + 3 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float sc, sh, mf, isf;
+    double var;
+    bn_coeffs(bn1, c, C, count, eps, sc, sh, mf, isf, var);
+    s_scale1[c] = sc;
+    s_shift1[c] = sh;
+    if (blockIdx.x == 0 && side_effects) bn_side_effects(bn1, c, count, momentum, mf, isf, var);
+    if constexpr (HAS_R) {
+      bn_coeffs(bn2, c, C, count, eps, sc, sh, mf, isf, var);
+      s_scale2[c] = sc;
+      s_shift2[c] = sh;
+      if (blockIdx.x == 0 && side_effects) bn_side_effects(bn2, c, count, momentum, mf, isf, var);
+    }
+  }
+  __syncthreads();
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total_vec;
        v += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long row = v / CV;
     const int c = static_cast<int>(v - row * CV) * 8;
     const size_t off = static_cast<size_t>(row) * C + c;
-    float a[8], s1[8], b1[8], o[8];
+    float a[8], o[8];
     Vec8<T>::load(y + off, a);
-    load8f(scale1 + c, s1);
-    load8f(shift1 + c, b1);
+    float rr[8];
+    if constexpr (HAS_R) Vec8<T>::load(r + off, rr);
+    {
+      float sc[8], sh[8];
+      lds8(s_scale1 + c, sc);
+      lds8(s_shift1 + c, sh);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = fmaf(a[i], s1[i], b1[i]);
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(a[i], sc[i], sh[i]);
+    }
     if constexpr (HAS_GATE) {
       const int n = static_cast<int>(row / T_len);
       float g[8];
@@ -127,12 +153,11 @@ bn_apply_fwd_kernel(const T* __restrict__ y, const float* __restrict__ scale1, c
       for (int i = 0; i < 8; ++i) o[i] *= g[i];
     }
     if constexpr (HAS_R) {
-      float rr[8], s2[8], b2[8];
-      Vec8<T>::load(r + off, rr);
-      load8f(scale2 + c, s2);
-      load8f(shift2 + c, b2);
+      float sc[8], sh[8];
+      lds8(s_scale2 + c, sc);
+      lds8(s_shift2 + c, sh);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += fmaf(rr[i], s2[i], b2[i]);
+      for (int i = 0; i < 8; ++i) o[i] += fmaf(rr[i], sc[i], sh[i]);
     }
     if (act == LASR_ACT_RELU) {
 #pragma unroll
@@ -170,14 +195,19 @@ sum_over_time_kernel(const T* __restrict__ y, float* __restrict__ sums, int T_le
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward reduce: one block per (utterance n, chunk k); partials[(n*chunks + k), s, c], s in 0..2:
-//   s=0: sum g, s=1: sum g*y, s=2: sum g*r        with g = dout * (act ? out > 0 : 1)
+// backward reduce: one CTA per (utterance n, time chunk k).  With g = dout * (act ? out > 0 : 1):
+//   totals[0][c] += sum g, totals[1][c] += sum g*y, totals[2][c] += sum g*r      (double, RED.f64; pre-zeroed)
+//   per_n[n][0][c] += sum_t g, per_n[n][1][c] += sum_t g*y                       (float, only when per_n != NULL: SE)
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_f64(double* addr, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+
 template <typename T, bool HAS_R>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, const T* __restrict__ y,
-                     const T* __restrict__ r, float* __restrict__ partials, int T_len, int C, int chunks,
-                     int rows_per_chunk, int act) {
+                     const T* __restrict__ r, double* __restrict__ totals, float* __restrict__ per_n, int T_len, int C,
+                     int chunks, int rows_per_chunk, int act) {
   extern __shared__ float red[];  // [rows_par][3][C]
   const int n = blockIdx.x / chunks, k = blockIdx.x - n * chunks;
   const int CV = C / 8;
@@ -191,11 +221,12 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
   if (tr < rows_par) {
     for (int t = t0 + tr; t < t1; t += rows_par) {
       const size_t off = (static_cast<size_t>(n) * T_len + t) * C + cv * 8;
-      float g[8], o[8], yy[8];
+      float g[8], o[8], yy[8], rr[8];
       Vec8<T>::load(dout + off, g);
       Vec8<T>::load(y + off, yy);
+      if (act == LASR_ACT_RELU) Vec8<T>::load(out + off, o);
+      if constexpr (HAS_R) Vec8<T>::load(r + off, rr);
       if (act == LASR_ACT_RELU) {
-        Vec8<T>::load(out + off, o);
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
       }
@@ -205,8 +236,6 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
         sgy[i] = fmaf(g[i], yy[i], sgy[i]);
       }
       if constexpr (HAS_R) {
-        float rr[8];
-        Vec8<T>::load(r + off, rr);
 #pragma unroll
         for (int i = 0; i < 8; ++i) sgr[i] = fmaf(g[i], rr[i], sgr[i]);
       }
@@ -220,60 +249,95 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
     }
   }
   __syncthreads();
-  float* pdst = partials + static_cast<size_t>(blockIdx.x) * 3 * C;
-  for (int i = threadIdx.x; i < 3 * C; i += 256) {
+  const int nred = HAS_R ? 3 * C : 2 * C;
+  for (int i = threadIdx.x; i < nred; i += 256) {
     float s = 0.f;
     for (int j = 0; j < rows_par; ++j) s += red[static_cast<size_t>(j) * 3 * C + i];
-    pdst[i] = s;
+    red_add_f64(totals + i, static_cast<double>(s));
+    if (per_n != nullptr && i < 2 * C) atomicAdd(per_n + static_cast<size_t>(n) * 3 * C + i, s);
   }
 }
 
-// per-channel finalize: sums partial slots idx_g / idx_gx over all groups
-__global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const float* __restrict__ partials, int groups, int nslots, int C, double count, int idx_g,
-                       int idx_gx, const float* __restrict__ gamma, const float* __restrict__ mean,
-                       const float* __restrict__ invstd, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                       float* __restrict__ coef) {
-  __shared__ double s0[8][32], s1[8][32];
-  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
-  double a = 0.0, b = 0.0;
-  if (c < C) {
-    for (int g = slice; g < groups; g += 8) {
-      a += static_cast<double>(partials[(static_cast<size_t>(g) * nslots + idx_g) * C + c]);
-      b += static_cast<double>(partials[(static_cast<size_t>(g) * nslots + idx_gx) * C + c]);
-    }
-  }
-  s0[slice][lane] = a;
-  s1[slice][lane] = b;
-  __syncthreads();
-  if (slice == 0 && c < C) {
-#pragma unroll
-    for (int i = 1; i < 8; ++i) {
-      a += s0[i][lane];
-      b += s1[i][lane];
-    }
-    const double mu = mean[c], is = invstd[c], ga = gamma[c];
-    const double dga = is * (b - mu * a);
-    if (dgamma != nullptr) dgamma[c] += static_cast<float>(dga);
-    if (dbeta != nullptr) dbeta[c] += static_cast<float>(a);
-    const double c0 = ga * is;
-    const double c1 = -ga * is * is * dga / count;
-    const double c2 = -ga * is * a / count - c1 * mu;
-    coef[c] = static_cast<float>(c0);
-    coef[C + c] = static_cast<float>(c1);
-    coef[2 * C + c] = static_cast<float>(c2);
-  }
+// coefficients of the BatchNorm input gradient: d(input) = c0*g + c1*x + c2, from a = sum g and b = sum g*x
+__device__ __forceinline__ void bn_bwd_coef(double a, double b, double count, float gamma, float mean, float invstd,
+                                            float& c0, float& c1, float& c2, float& dgamma, float& dbeta) {
+  const double mu = mean, is = invstd, ga = gamma;
+  const double dga = is * (b - mu * a);
+  const double k0 = ga * is;
+  const double k1 = -ga * is * is * dga / count;
+  const double k2 = -ga * is * a / count - k1 * mu;
+  c0 = static_cast<float>(k0);
+  c1 = static_cast<float>(k1);
+  c2 = static_cast<float>(k2);
+  dgamma = static_cast<float>(dga);
+  dbeta = static_cast<float>(a);
+}
+
+// standalone variant (tests / tools): coef [3, C] from totals slots (0, slot_gx)
+__global__ void bn_bwd_coef_kernel(const double* __restrict__ totals, int C, double count, int slot_gx,
+                                   const float* __restrict__ gamma, const float* __restrict__ mean,
+                                   const float* __restrict__ invstd, float* __restrict__ dgamma,
+                                   float* __restrict__ dbeta, float* __restrict__ coef) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float c0, c1, c2, dg, db;
+  bn_bwd_coef(totals[c], totals[slot_gx * C + c], count, gamma[c], mean[c], invstd[c], c0, c1, c2, dg, db);
+  coef[c] = c0;
+  coef[C + c] = c1;
+  coef[2 * C + c] = c2;
+  if (dgamma != nullptr) dgamma[c] += dg;
+  if (dbeta != nullptr) dbeta[c] += db;
 }
 
 // backward apply: dy = mask(coef1[0]*(g*gate + extra) + coef1[1]*y + coef1[2]); dr = coef2[0]*g + coef2[1]*r + coef2[2]
+// coefficients come from `totals` (folded in the prologue; CTA 0 accumulates dgamma / dbeta) unless coef1_in is given
+// (the squeeze-excitation branch, whose upstream gradient is not g).
+struct BnBwdSide {
+  const float* gamma;
+  const float* mean;
+  const float* invstd;
+  float* dgamma;
+  float* dbeta;
+};
+
 template <typename T, bool HAS_R, bool HAS_GATE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const T* __restrict__ y,
                     const T* __restrict__ r, const float* __restrict__ gate, const float* __restrict__ extra,
-                    const float* __restrict__ coef1, const float* __restrict__ coef2,
-                    const int32_t* __restrict__ lengths, int T_len, T* __restrict__ dy, T* __restrict__ dr,
-                    long long total_vec, int CV, int C, int act) {
+                    const double* __restrict__ totals, const float* __restrict__ coef1_in, const BnBwdSide bn1,
+                    const BnBwdSide bn2, double count, const int32_t* __restrict__ lengths, int T_len,
+                    T* __restrict__ dy, T* __restrict__ dr, long long total_vec, int CV, int C, int act) {
+  extern __shared__ float coef_s[];  // coef1 [3][C], coef2 [3][C]
+  float* k1 = coef_s;
+  float* k2 = coef_s + 3 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float c0, c1, c2, dg, db;
+    if (coef1_in != nullptr) {
+      k1[c] = coef1_in[c];
+      k1[C + c] = coef1_in[C + c];
+      k1[2 * C + c] = coef1_in[2 * C + c];
+    } else {
+      bn_bwd_coef(totals[c], totals[C + c], count, bn1.gamma[c], bn1.mean[c], bn1.invstd[c], c0, c1, c2, dg, db);
+      k1[c] = c0;
+      k1[C + c] = c1;
+      k1[2 * C + c] = c2;
+      if (blockIdx.x == 0) {
+        if (bn1.dgamma != nullptr) bn1.dgamma[c] += dg;
+        if (bn1.dbeta != nullptr) bn1.dbeta[c] += db;
+      }
+    }
+    if constexpr (HAS_R) {
+      bn_bwd_coef(totals[c], totals[2 * C + c], count, bn2.gamma[c], bn2.mean[c], bn2.invstd[c], c0, c1, c2, dg, db);
+      k2[c] = c0;
+      k2[C + c] = c1;
+      k2[2 * C + c] = c2;
+      if (blockIdx.x == 0) {
+        if (bn2.dgamma != nullptr) bn2.dgamma[c] += dg;
+        if (bn2.dbeta != nullptr) bn2.dbeta[c] += db;
+      }
+    }
+  }
+  __syncthreads();
   for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total_vec;
        v += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long row = v / CV;
@@ -281,28 +345,28 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
     const size_t off = static_cast<size_t>(row) * C + c;
     const int n = static_cast<int>(row / T_len);
     const int t = static_cast<int>(row - static_cast<long long>(n) * T_len);
-    float g[8], yy[8];
+    const bool keep = lengths == nullptr || t < lengths[n];
+    float g[8], yy[8], rr[8];
     Vec8<T>::load(dout + off, g);
+    float o[8];
+    if (act == LASR_ACT_RELU) Vec8<T>::load(out + off, o);
+    if constexpr (HAS_R) Vec8<T>::load(r + off, rr);
+    if (keep) Vec8<T>::load(y + off, yy);
     if (act == LASR_ACT_RELU) {
-      float o[8];
-      Vec8<T>::load(out + off, o);
 #pragma unroll
       for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
     }
     if constexpr (HAS_R) {
-      float rr[8], a0[8], a1[8], a2[8], d[8];
-      Vec8<T>::load(r + off, rr);
-      load8f(coef2 + c, a0);
-      load8f(coef2 + C + c, a1);
-      load8f(coef2 + 2 * C + c, a2);
+      float a0[8], a1[8], a2[8], d[8];
+      lds8(k2 + c, a0);
+      lds8(k2 + C + c, a1);
+      lds8(k2 + 2 * C + c, a2);
 #pragma unroll
       for (int i = 0; i < 8; ++i) d[i] = fmaf(a0[i], g[i], fmaf(a1[i], rr[i], a2[i]));
       Vec8<T>::store(dr + off, d);
     }
-    const bool keep = lengths == nullptr || t < lengths[n];
     float d[8];
     if (keep) {
-      Vec8<T>::load(y + off, yy);
       if constexpr (HAS_GATE) {
         float gt[8], ex[8];
         load8f(gate + static_cast<size_t>(n) * C + c, gt);
@@ -311,9 +375,9 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
         for (int i = 0; i < 8; ++i) g[i] = fmaf(g[i], gt[i], ex[i]);
       }
       float a0[8], a1[8], a2[8];
-      load8f(coef1 + c, a0);
-      load8f(coef1 + C + c, a1);
-      load8f(coef1 + 2 * C + c, a2);
+      lds8(k1 + c, a0);
+      lds8(k1 + C + c, a1);
+      lds8(k1 + 2 * C + c, a2);
 #pragma unroll
       for (int i = 0; i < 8; ++i) d[i] = fmaf(a0[i], g[i], fmaf(a1[i], yy[i], a2[i]));
     } else {
@@ -324,10 +388,58 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
   }
 }
 
-static inline int ew_grid(long long total_vec) {
-  long long b = (total_vec + 255) / 256;
-  const long long cap = 8LL * kNumSMs;
+static inline int persistent_grid(long long total_vec, int threads) {
+  long long b = (total_vec + threads - 1) / threads;
+  const long long cap = 2LL * kNumSMs;
   return static_cast<int>(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+template <typename TT>
+static int bn_fwd_launch(const void* y, const lasr_bn_t& b1, const void* r, const lasr_bn_t& b2, const float* gate,
+                         void* out, long long total, int CV, int C, int T, double count, float eps, float momentum,
+                         int act, int side_effects, cudaStream_t stream) {
+  const int grid = persistent_grid(total, 512);
+  const int smem = 4 * C * static_cast<int>(sizeof(float));
+  const TT* yy = static_cast<const TT*>(y);
+  const TT* rr = static_cast<const TT*>(r);
+  TT* oo = static_cast<TT*>(out);
+#define LASR_BN_FWD_ARGS yy, b1, rr, b2, gate, oo, total, CV, C, T, count, eps, momentum, act, side_effects
+  if (r != nullptr && gate != nullptr)
+    bn_apply_fwd_kernel<TT, true, true><<<grid, 512, smem, stream>>>(LASR_BN_FWD_ARGS);
+  else if (r != nullptr)
+    bn_apply_fwd_kernel<TT, true, false><<<grid, 512, smem, stream>>>(LASR_BN_FWD_ARGS);
+  else if (gate != nullptr)
+    bn_apply_fwd_kernel<TT, false, true><<<grid, 512, smem, stream>>>(LASR_BN_FWD_ARGS);
+  else
+    bn_apply_fwd_kernel<TT, false, false><<<grid, 512, smem, stream>>>(LASR_BN_FWD_ARGS);
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+template <typename TT>
+static int bn_bwd_launch(const void* dout, const void* out, const void* y, const void* r, const float* gate,
+                         const float* extra, const double* totals, const float* coef1, const BnBwdSide& s1,
+                         const BnBwdSide& s2, double count, const int32_t* lengths, int T, void* dy, void* dr,
+                         long long total, int CV, int C, int act, cudaStream_t stream) {
+  const int grid = persistent_grid(total, 512);
+  const int smem = 6 * C * static_cast<int>(sizeof(float));
+  const TT* a0 = static_cast<const TT*>(dout);
+  const TT* a1 = static_cast<const TT*>(out);
+  const TT* a2 = static_cast<const TT*>(y);
+  const TT* a3 = static_cast<const TT*>(r);
+  TT* o0 = static_cast<TT*>(dy);
+  TT* o1 = static_cast<TT*>(dr);
+#define LASR_BN_BWD_ARGS a0, a1, a2, a3, gate, extra, totals, coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, act
+  if (r != nullptr && gate != nullptr)
+    bn_bwd_apply_kernel<TT, true, true><<<grid, 512, smem, stream>>>(LASR_BN_BWD_ARGS);
+  else if (r != nullptr)
+    bn_bwd_apply_kernel<TT, true, false><<<grid, 512, smem, stream>>>(LASR_BN_BWD_ARGS);
+  else if (gate != nullptr)
+    bn_bwd_apply_kernel<TT, false, true><<<grid, 512, smem, stream>>>(LASR_BN_BWD_ARGS);
+  else
+    bn_bwd_apply_kernel<TT, false, false><<<grid, 512, smem, stream>>>(LASR_BN_BWD_ARGS);
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
 }
 
 }  // namespace lasr
@@ -336,22 +448,11 @@ using namespace lasr;
 
 extern "C" {
 
-int lasr_bn_finalize(const float* stats, int groups, int C, int count, float eps, float momentum, const float* gamma,
-                     const float* beta, float* mean, float* invstd, float* scale, float* shift, float* running_mean,
-                     float* running_var, lasr_stream_t stream) {
-  if (groups <= 0 || C <= 0 || count <= 0) return LASR_ERR_BAD_SHAPE;
-  bn_finalize_kernel<<<cdiv(C, 32), 256, 0, stream>>>(stats, groups, C, static_cast<double>(count), eps, momentum,
-                                                      gamma, beta, mean, invstd, scale, shift, running_mean,
-                                                      running_var);
-  LASR_CHECK_LAUNCH();
-  return LASR_OK;
-}
-
-int lasr_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
-                        float eps, float* scale, float* shift, int C, lasr_stream_t stream) {
-  if (C <= 0) return LASR_ERR_BAD_SHAPE;
-  bn_eval_coeffs_kernel<<<cdiv(C, 256), 256, 0, stream>>>(gamma, beta, running_mean, running_var, eps, scale, shift,
-                                                          C);
+int lasr_bn_coeffs(const lasr_bn_t* bn, int C, int count, float eps, float momentum, float* scale, float* shift,
+                   int side_effects, lasr_stream_t stream) {
+  if (bn == nullptr || C <= 0 || count <= 0) return LASR_ERR_BAD_SHAPE;
+  bn_coeffs_kernel<<<cdiv(C, 128), 128, 0, stream>>>(*bn, C, static_cast<double>(count), eps, momentum, scale, shift,
+                                                      side_effects);
   LASR_CHECK_LAUNCH();
   return LASR_OK;
 }
@@ -379,41 +480,23 @@ int lasr_sum_over_time(const void* y, float* sums, int N, int T, int C, int dtyp
   return LASR_OK;
 }
 
-#define LASR_BN_FWD_LAUNCH(TT)                                                                                       \
-  do {                                                                                                               \
-    const TT* yy = static_cast<const TT*>(y);                                                                        \
-    const TT* rr = static_cast<const TT*>(r);                                                                        \
-    TT* oo = static_cast<TT*>(out);                                                                                  \
-    if (r != nullptr && gate != nullptr)                                                                             \
-      bn_apply_fwd_kernel<TT, true, true>                                                                            \
-          <<<grid, 256, 0, stream>>>(yy, scale1, shift1, rr, scale2, shift2, gate, oo, total, CV, C, T, act);        \
-    else if (r != nullptr)                                                                                           \
-      bn_apply_fwd_kernel<TT, true, false>                                                                           \
-          <<<grid, 256, 0, stream>>>(yy, scale1, shift1, rr, scale2, shift2, gate, oo, total, CV, C, T, act);        \
-    else if (gate != nullptr)                                                                                        \
-      bn_apply_fwd_kernel<TT, false, true>                                                                           \
-          <<<grid, 256, 0, stream>>>(yy, scale1, shift1, rr, scale2, shift2, gate, oo, total, CV, C, T, act);        \
-    else                                                                                                             \
-      bn_apply_fwd_kernel<TT, false, false>                                                                          \
-          <<<grid, 256, 0, stream>>>(yy, scale1, shift1, rr, scale2, shift2, gate, oo, total, CV, C, T, act);        \
-  } while (0)
-
-int lasr_bn_apply_act_fwd(const void* y, const float* scale1, const float* shift1, const void* r, const float* scale2,
-                          const float* shift2, const float* gate, void* out, int M, int C, int T, int act, int dtype,
-                          lasr_stream_t stream) {
-  if (M <= 0 || C <= 0 || (C % 8)) return LASR_ERR_BAD_SHAPE;
+int lasr_bn_apply_act_fwd(const void* y, const lasr_bn_t* bn1, const void* r, const lasr_bn_t* bn2, const float* gate,
+                          void* out, int M, int C, int T, int count, float eps, float momentum, int act,
+                          int side_effects, int dtype, lasr_stream_t stream) {
+  if (M <= 0 || C <= 0 || (C % 8) || C > 2048 || count <= 0 || bn1 == nullptr) return LASR_ERR_BAD_SHAPE;
+  if ((r != nullptr) != (bn2 != nullptr)) return LASR_ERR_BAD_SHAPE;
   if (gate != nullptr && T <= 0) return LASR_ERR_BAD_SHAPE;
   const int CV = C / 8;
   const long long total = static_cast<long long>(M) * CV;
-  const int grid = ew_grid(total);
+  const lasr_bn_t none{};
+  const lasr_bn_t& b2 = bn2 ? *bn2 : none;
   if (dtype == LASR_F32)
-    LASR_BN_FWD_LAUNCH(float);
-  else if (dtype == LASR_BF16)
-    LASR_BN_FWD_LAUNCH(__nv_bfloat16);
-  else
-    return LASR_ERR_BAD_DTYPE;
-  LASR_CHECK_LAUNCH();
-  return LASR_OK;
+    return bn_fwd_launch<float>(y, *bn1, r, b2, gate, out, total, CV, C, T, count, eps, momentum, act, side_effects,
+                                stream);
+  if (dtype == LASR_BF16)
+    return bn_fwd_launch<__nv_bfloat16>(y, *bn1, r, b2, gate, out, total, CV, C, T, count, eps, momentum, act,
+                                        side_effects, stream);
+  return LASR_ERR_BAD_DTYPE;
 }
 
 int lasr_bn_bwd_chunks(int N, int T) {
@@ -425,9 +508,10 @@ int lasr_bn_bwd_chunks(int N, int T) {
   return cdiv(T, rows);
 }
 
-int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, const void* r, float* partials, int N,
-                           int T, int C, int chunks, int act, int dtype, lasr_stream_t stream) {
-  if (N <= 0 || T <= 0 || C <= 0 || (C % 8) || C > 2048 || chunks <= 0) return LASR_ERR_BAD_SHAPE;
+int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, const void* r, double* totals,
+                           float* per_n, int N, int T, int C, int act, int dtype, lasr_stream_t stream) {
+  if (N <= 0 || T <= 0 || C <= 0 || (C % 8) || C > 2048 || totals == nullptr) return LASR_ERR_BAD_SHAPE;
+  const int chunks = lasr_bn_bwd_chunks(N, T);
   const int rows_per_chunk = cdiv(T, chunks);
   const int CV = C / 8;
   const int rows_par = 256 / CV;
@@ -438,11 +522,11 @@ int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, con
     if (r != nullptr)                                                                                              \
       bn_bwd_reduce_kernel<TT, true><<<grid, 256, smem, stream>>>(                                                 \
           static_cast<const TT*>(dout), static_cast<const TT*>(out), static_cast<const TT*>(y),                    \
-          static_cast<const TT*>(r), partials, T, C, chunks, rows_per_chunk, act);                                 \
+          static_cast<const TT*>(r), totals, per_n, T, C, chunks, rows_per_chunk, act);                            \
     else                                                                                                           \
       bn_bwd_reduce_kernel<TT, false><<<grid, 256, smem, stream>>>(                                                \
           static_cast<const TT*>(dout), static_cast<const TT*>(out), static_cast<const TT*>(y),                    \
-          static_cast<const TT*>(r), partials, T, C, chunks, rows_per_chunk, act);                                 \
+          static_cast<const TT*>(r), totals, per_n, T, C, chunks, rows_per_chunk, act);                            \
   } while (0)
   if (dtype == LASR_F32)
     LASR_BN_RED_LAUNCH(float);
@@ -454,54 +538,36 @@ int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, con
   return LASR_OK;
 }
 
-int lasr_bn_bwd_finalize(const float* partials, int groups, int nslots, int C, int count, int idx_g, int idx_gx,
-                         const float* gamma, const float* mean, const float* invstd, float* dgamma, float* dbeta,
-                         float* coef, lasr_stream_t stream) {
-  if (groups <= 0 || C <= 0 || count <= 0 || idx_g >= nslots || idx_gx >= nslots) return LASR_ERR_BAD_SHAPE;
-  bn_bwd_finalize_kernel<<<cdiv(C, 32), 256, 0, stream>>>(partials, groups, nslots, C, static_cast<double>(count),
-                                                          idx_g, idx_gx, gamma, mean, invstd, dgamma, dbeta, coef);
+int lasr_bn_bwd_coef(const double* totals, int C, int count, int slot_gx, const float* gamma, const float* mean,
+                     const float* invstd, float* dgamma, float* dbeta, float* coef, lasr_stream_t stream) {
+  if (C <= 0 || count <= 0 || slot_gx < 1 || slot_gx > 2 || totals == nullptr) return LASR_ERR_BAD_SHAPE;
+  bn_bwd_coef_kernel<<<cdiv(C, 128), 128, 0, stream>>>(totals, C, static_cast<double>(count), slot_gx, gamma, mean,
+                                                        invstd, dgamma, dbeta, coef);
   LASR_CHECK_LAUNCH();
   return LASR_OK;
 }
 
 int lasr_bn_act_bwd_apply(const void* dout, const void* out, const void* y, const void* r, const float* gate,
-                          const float* extra, const float* coef1, const float* coef2, const int32_t* lengths, int T,
-                          void* dy, void* dr, int M, int C, int act, int dtype, lasr_stream_t stream) {
-  if (M <= 0 || C <= 0 || (C % 8) || T <= 0) return LASR_ERR_BAD_SHAPE;
-  if ((r != nullptr) != (dr != nullptr) || (r != nullptr) != (coef2 != nullptr)) return LASR_ERR_BAD_SHAPE;
+                          const float* extra, const double* totals, const float* coef1, const lasr_bn_bwd_t* bn1,
+                          const lasr_bn_bwd_t* bn2, int count, const int32_t* lengths, int T, void* dy, void* dr,
+                          int M, int C, int act, int dtype, lasr_stream_t stream) {
+  if (M <= 0 || C <= 0 || (C % 8) || C > 2048 || T <= 0 || count <= 0) return LASR_ERR_BAD_SHAPE;
+  if ((r != nullptr) != (dr != nullptr) || (r != nullptr) != (bn2 != nullptr)) return LASR_ERR_BAD_SHAPE;
   if ((gate != nullptr) != (extra != nullptr)) return LASR_ERR_BAD_SHAPE;
+  if (coef1 == nullptr && (bn1 == nullptr || totals == nullptr)) return LASR_ERR_BAD_SHAPE;
+  if (r != nullptr && totals == nullptr) return LASR_ERR_BAD_SHAPE;
   const int CV = C / 8;
   const long long total = static_cast<long long>(M) * CV;
-  const int grid = ew_grid(total);
-#define LASR_BN_BAPPLY_LAUNCH(TT)                                                                                   \
-  do {                                                                                                              \
-    const TT* a0 = static_cast<const TT*>(dout);                                                                    \
-    const TT* a1 = static_cast<const TT*>(out);                                                                     \
-    const TT* a2 = static_cast<const TT*>(y);                                                                       \
-    const TT* a3 = static_cast<const TT*>(r);                                                                       \
-    TT* o0 = static_cast<TT*>(dy);                                                                                  \
-    TT* o1 = static_cast<TT*>(dr);                                                                                  \
-    if (r != nullptr && gate != nullptr)                                                                            \
-      bn_bwd_apply_kernel<TT, true, true><<<grid, 256, 0, stream>>>(a0, a1, a2, a3, gate, extra, coef1, coef2,      \
-                                                                    lengths, T, o0, o1, total, CV, C, act);         \
-    else if (r != nullptr)                                                                                          \
-      bn_bwd_apply_kernel<TT, true, false><<<grid, 256, 0, stream>>>(a0, a1, a2, a3, gate, extra, coef1, coef2,     \
-                                                                     lengths, T, o0, o1, total, CV, C, act);        \
-    else if (gate != nullptr)                                                                                       \
-      bn_bwd_apply_kernel<TT, false, true><<<grid, 256, 0, stream>>>(a0, a1, a2, a3, gate, extra, coef1, coef2,     \
-                                                                     lengths, T, o0, o1, total, CV, C, act);        \
-    else                                                                                                            \
-      bn_bwd_apply_kernel<TT, false, false><<<grid, 256, 0, stream>>>(a0, a1, a2, a3, gate, extra, coef1, coef2,    \
-                                                                      lengths, T, o0, o1, total, CV, C, act);       \
-  } while (0)
+  BnBwdSide s1{}, s2{};
+  if (bn1) s1 = BnBwdSide{bn1->gamma, bn1->mean, bn1->invstd, bn1->dgamma, bn1->dbeta};
+  if (bn2) s2 = BnBwdSide{bn2->gamma, bn2->mean, bn2->invstd, bn2->dgamma, bn2->dbeta};
   if (dtype == LASR_F32)
-    LASR_BN_BAPPLY_LAUNCH(float);
-  else if (dtype == LASR_BF16)
-    LASR_BN_BAPPLY_LAUNCH(__nv_bfloat16);
-  else
-    return LASR_ERR_BAD_DTYPE;
-  LASR_CHECK_LAUNCH();
-  return LASR_OK;
+    return bn_bwd_launch<float>(dout, out, y, r, gate, extra, totals, coef1, s1, s2, count, lengths, T, dy, dr, total,
+                                CV, C, act, stream);
+  if (dtype == LASR_BF16)
+    return bn_bwd_launch<__nv_bfloat16>(dout, out, y, r, gate, extra, totals, coef1, s1, s2, count, lengths, T, dy,
+                                        dr, total, CV, C, act, stream);
+  return LASR_ERR_BAD_DTYPE;
 }
 
 }  // extern "C"

@@ -65,26 +65,46 @@ __device__ __forceinline__ float lse3(float a, float b, float c) {
   return m + logf(expf(a - m) + expf(b - m) + expf(c - m));
 }
 
-constexpr int CTC_THREADS = 256;
-constexpr int CTC_MAX_SPT = 8;  // states per thread -> up to 2048 lattice states (S_max <= 1023)
+constexpr int CTC_THREADS = 128;
+constexpr int CTC_MAX_SPT = 16;  // states per thread -> up to 2048 lattice states (S_max <= 1023)
+constexpr int CTC_RING = 8;      // frames of emissions in flight (cp.async ring)
 
-template <typename T>
+__device__ __forceinline__ float lse3_fast(float a, float b, float c) {
+  const float m = fmaxf(a, fmaxf(b, c));
+  if (m == -CUDART_INF_F) return -CUDART_INF_F;
+  return m + __logf(__expf(a - m) + __expf(b - m) + __expf(c - m));
+}
+__device__ __forceinline__ void cp_async_4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// One CTA per (utterance, direction).  Thread i owns lattice states i, i+128, ...  The emission of state s at frame
+// t is ONE element of the [T, V] score matrix; the 4-byte word holding it is fetched CTC_RING frames ahead with
+// cp.async into a per-thread slot of a shared-memory ring, so the sequential recursion never waits on HBM/L2.
+template <typename T, int SPT>
 __global__ void __launch_bounds__(CTC_THREADS)
 ctc_lattice_kernel(const T* __restrict__ x, const float* __restrict__ lse, const int64_t* __restrict__ targets,
                    const int32_t* __restrict__ in_len, const int32_t* __restrict__ tgt_len, float* __restrict__ alpha,
                    float* __restrict__ beta, float* __restrict__ nll, int T_len, int ldx, int S_max, int blank) {
-  extern __shared__ float sm[];  // [2][Lp_max] lattice columns
+  extern __shared__ float sm[];
   const int n = blockIdx.x;
   const bool backward = blockIdx.y == 1;
   const int Lp_max = 2 * S_max + 1;
-  float* col[2] = {sm, sm + Lp_max};
+  float* col[2] = {sm, sm + Lp_max};                                     // previous / next lattice column
+  uint32_t* ring = reinterpret_cast<uint32_t*>(sm + 2 * Lp_max);         // [CTC_RING][SPT * CTC_THREADS] raw words
+  float* lring = reinterpret_cast<float*>(ring + CTC_RING * SPT * CTC_THREADS);  // [CTC_RING] row log-sum-exp
   const int Tn = in_len[n];
   const int Sn = tgt_len[n];
   const int Lp = 2 * Sn + 1;
   const int64_t* tg = targets + static_cast<size_t>(n) * S_max;
   float* lat = (backward ? beta : alpha) + static_cast<size_t>(n) * T_len * Lp_max;
-  const T* xn = x + static_cast<size_t>(n) * T_len * ldx;
-  const float* lsen = lse ? lse + static_cast<size_t>(n) * T_len : nullptr;
+  const size_t row0 = static_cast<size_t>(n) * T_len;
+  const uint32_t* xw = reinterpret_cast<const uint32_t*>(x);
 
   // infeasible / degenerate cases (torch: loss = inf when the target does not fit)
   if (Tn <= 0 || Sn > S_max || Tn > T_len) {
@@ -92,10 +112,10 @@ ctc_lattice_kernel(const T* __restrict__ x, const float* __restrict__ lse, const
     return;
   }
 
-  int lab[CTC_MAX_SPT];
-  bool skip_ok[CTC_MAX_SPT];  // may take the s-2 (fwd) / s+2 (bwd) transition
+  int lab[SPT];
+  bool skip_ok[SPT];  // may take the s-2 (fwd) / s+2 (bwd) transition
 #pragma unroll
-  for (int i = 0; i < CTC_MAX_SPT; ++i) {
+  for (int i = 0; i < SPT; ++i) {
     const int s = threadIdx.x + i * CTC_THREADS;
     lab[i] = blank;
     skip_ok[i] = false;
@@ -107,49 +127,68 @@ ctc_lattice_kernel(const T* __restrict__ x, const float* __restrict__ lse, const
         skip_ok[i] = (s + 2 < Lp) && lab[i] != static_cast<int>(tg[(s >> 1) + 1]);
     }
   }
-  auto emit = [&](int t, int i) -> float {
-    const float v = to_f32<T>(xn[static_cast<size_t>(t) * ldx + lab[i]]);
-    return lsen ? v - lsen[t] : v;
-  };
-
   const int t_first = backward ? Tn - 1 : 0;
   const int dt = backward ? -1 : 1;
-  // initial column
-  float e_cur[CTC_MAX_SPT];
+
+  // fetch the emissions of step `st` (frame t_first + dt*st) into ring slot st % CTC_RING
+  auto issue = [&](int st) {
+    if (st < Tn) {
+      const int t = t_first + dt * st;
+      const size_t e0 = (row0 + t) * static_cast<size_t>(ldx);
+      uint32_t* slot = ring + (st % CTC_RING) * (SPT * CTC_THREADS);
 #pragma unroll
-  for (int i = 0; i < CTC_MAX_SPT; ++i) {
+      for (int i = 0; i < SPT; ++i) {
+        const int s = threadIdx.x + i * CTC_THREADS;
+        if (s < Lp) {
+          const size_t e = e0 + lab[i];
+          cp_async_4(slot + s, xw + (sizeof(T) == 4 ? e : (e >> 1)));
+        }
+      }
+      if (lse != nullptr && threadIdx.x == 0) cp_async_4(lring + (st % CTC_RING), lse + row0 + t);
+    }
+    cp_async_commit();
+  };
+  auto emission = [&](int st, int i) -> float {
+    const int s = threadIdx.x + i * CTC_THREADS;
+    const uint32_t w = ring[(st % CTC_RING) * (SPT * CTC_THREADS) + s];
+    float v;
+    if (sizeof(T) == 4) {
+      v = __uint_as_float(w);
+    } else {
+      const int t = t_first + dt * st;
+      const size_t e = (row0 + t) * static_cast<size_t>(ldx) + lab[i];
+      v = __uint_as_float((e & 1) ? (w & 0xffff0000u) : (w << 16));
+    }
+    return lse != nullptr ? v - lring[st % CTC_RING] : v;
+  };
+
+#pragma unroll 1
+  for (int st = 0; st < CTC_RING; ++st) issue(st);
+  cp_async_wait<CTC_RING - 1>();
+  __syncthreads();
+  // initial column
+#pragma unroll
+  for (int i = 0; i < SPT; ++i) {
     const int s = threadIdx.x + i * CTC_THREADS;
     if (s < Lp) {
       float v = -CUDART_INF_F;
       const bool start = backward ? (s == Lp - 1 || s == Lp - 2) : (s == 0 || s == 1);
-      if (start) v = emit(t_first, i);
+      if (start) v = emission(0, i);
       col[0][s] = v;
       lat[static_cast<size_t>(t_first) * Lp_max + s] = v;
     }
   }
-  if (Tn > 1) {
-#pragma unroll
-    for (int i = 0; i < CTC_MAX_SPT; ++i) {
-      const int s = threadIdx.x + i * CTC_THREADS;
-      e_cur[i] = (s < Lp) ? emit(t_first + dt, i) : 0.f;
-    }
-  }
-  __syncthreads();
 
   int cur = 0;
+#pragma unroll 1
   for (int step = 1; step < Tn; ++step) {
+    cp_async_wait<CTC_RING - 2>();  // this thread's words of frame `step` have landed
+    __syncthreads();                // previous column (and the lse word) visible to everyone
     const int t = t_first + dt * step;
     const float* prev = col[cur];
     float* next = col[cur ^ 1];
-    float e_next[CTC_MAX_SPT];
-    const bool more = step + 1 < Tn;
 #pragma unroll
-    for (int i = 0; i < CTC_MAX_SPT; ++i) {
-      const int s = threadIdx.x + i * CTC_THREADS;
-      e_next[i] = (more && s < Lp) ? emit(t + dt, i) : 0.f;  // prefetch next frame's emission
-    }
-#pragma unroll
-    for (int i = 0; i < CTC_MAX_SPT; ++i) {
+    for (int i = 0; i < SPT; ++i) {
       const int s = threadIdx.x + i * CTC_THREADS;
       if (s < Lp) {
         const float a = prev[s];
@@ -161,16 +200,16 @@ ctc_lattice_kernel(const T* __restrict__ x, const float* __restrict__ lse, const
           b = s + 1 < Lp ? prev[s + 1] : -CUDART_INF_F;
           if (skip_ok[i]) c = prev[s + 2];
         }
-        const float v = lse3(a, b, c) + e_cur[i];
+        const float v = lse3_fast(a, b, c) + emission(step, i);
         next[s] = v;
         lat[static_cast<size_t>(t) * Lp_max + s] = v;
       }
     }
-#pragma unroll
-    for (int i = 0; i < CTC_MAX_SPT; ++i) e_cur[i] = e_next[i];
     cur ^= 1;
-    __syncthreads();
+    issue(step - 1 + CTC_RING);  // slot (step-1) % RING was consumed by the previous iteration
   }
+  cp_async_wait<0>();
+  __syncthreads();
   if (!backward && threadIdx.x == 0) {
     const float a = col[cur][Lp - 1];
     const float b = Lp >= 2 ? col[cur][Lp - 2] : -CUDART_INF_F;
@@ -281,6 +320,31 @@ ctc_collapse_kernel(const int64_t* __restrict__ amax, const int32_t* __restrict_
   if (lane == 0) counts[n] = count;
 }
 
+// column sums of a [M, ld] matrix (decoder bias gradient = sum over frames of d(logits)): out[c] += sum_m x[m, c]
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long M, int C, int ld, int cols_par,
+              int rows_per_block) {
+  __shared__ float red[256];
+  const int rows_par = 256 / cols_par;
+  const int cc = threadIdx.x % cols_par, rr = threadIdx.x / cols_par;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = min(M, r0 + rows_per_block);
+  for (int c0 = blockIdx.y * cols_par; c0 < C; c0 += gridDim.y * cols_par) {
+    const int c = c0 + cc;
+    float acc = 0.f;
+    if (c < C)
+      for (long long r = r0 + rr; r < r1; r += rows_par) acc += to_f32<T>(x[static_cast<size_t>(r) * ld + c]);
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (rr == 0 && c < C) {
+      for (int j = 1; j < rows_par; ++j) acc += red[j * cols_par + cc];
+      atomicAdd(out + c, acc);
+    }
+    __syncthreads();
+  }
+}
+
 template <typename T, typename GT>
 static int ctc_grad_launch(const void* x, const float* lse, const int64_t* targets, const int32_t* il,
                            const int32_t* tl, const float* alpha, const float* beta, const float* nll,
@@ -308,6 +372,44 @@ static int ctc_grad_launch(const void* x, const float* lse, const int64_t* targe
                                                       blank, warps);
   LASR_CHECK_LAUNCH();
   return LASR_OK;
+}
+
+template <typename T, int SPT>
+static int ctc_lattice_launch(const void* x, const float* lse, const int64_t* targets, const int32_t* il,
+                              const int32_t* tl, float* alpha, float* beta, float* nll, int N, int T_len, int ldx,
+                              int S_max, int blank, cudaStream_t stream) {
+  const int Lp_max = 2 * S_max + 1;
+  const int smem = (2 * Lp_max + CTC_RING * SPT * CTC_THREADS + CTC_RING) * static_cast<int>(sizeof(float));
+  static bool configured = false;
+  if (!configured && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(ctc_lattice_kernel<T, SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (2 * (2 * 1023 + 1) + CTC_RING * SPT * CTC_THREADS + CTC_RING) * 4);
+    if (e != cudaSuccess) {
+      lasr_set_cuda_error(e);
+      return LASR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid(N, beta != nullptr ? 2 : 1);
+  ctc_lattice_kernel<T, SPT><<<grid, CTC_THREADS, smem, stream>>>(static_cast<const T*>(x), lse, targets, il, tl,
+                                                                  alpha, beta, nll, T_len, ldx, S_max, blank);
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+template <typename T>
+static int ctc_lattice_dispatch(const void* x, const float* lse, const int64_t* targets, const int32_t* il,
+                                const int32_t* tl, float* alpha, float* beta, float* nll, int N, int T_len, int ldx,
+                                int S_max, int blank, cudaStream_t stream) {
+  const int spt = cdiv(2 * S_max + 1, CTC_THREADS);
+#define LASR_CTC_LAT(SPT) \
+  return ctc_lattice_launch<T, SPT>(x, lse, targets, il, tl, alpha, beta, nll, N, T_len, ldx, S_max, blank, stream)
+  if (spt <= 1) LASR_CTC_LAT(1);
+  if (spt <= 2) LASR_CTC_LAT(2);
+  if (spt <= 4) LASR_CTC_LAT(4);
+  if (spt <= 8) LASR_CTC_LAT(8);
+  if (spt <= 16) LASR_CTC_LAT(16);
+  return LASR_ERR_UNSUPPORTED;
 }
 
 }  // namespace lasr
@@ -350,22 +452,14 @@ int lasr_ctc_fwd(const void* x, const float* lse, const int64_t* targets, const 
                  const int32_t* target_lengths, float* alpha, float* beta, float* nll, int N, int T, int V, int ldx,
                  int S_max, int blank, int dtype, lasr_stream_t stream) {
   if (N <= 0 || T <= 0 || V <= 0 || ldx < V || S_max < 0 || blank < 0 || blank >= V) return LASR_ERR_BAD_SHAPE;
-  const int Lp_max = 2 * S_max + 1;
-  if (Lp_max > CTC_THREADS * CTC_MAX_SPT) return LASR_ERR_UNSUPPORTED;
-  const int smem = 2 * Lp_max * static_cast<int>(sizeof(float));
-  dim3 grid(N, beta != nullptr ? 2 : 1);
+  if ((reinterpret_cast<uintptr_t>(x) & 3) != 0) return LASR_ERR_ALIGNMENT;
   if (dtype == LASR_F32)
-    ctc_lattice_kernel<float><<<grid, CTC_THREADS, smem, stream>>>(static_cast<const float*>(x), lse, targets,
-                                                                   input_lengths, target_lengths, alpha, beta, nll, T,
-                                                                   ldx, S_max, blank);
-  else if (dtype == LASR_BF16)
-    ctc_lattice_kernel<__nv_bfloat16><<<grid, CTC_THREADS, smem, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), lse, targets, input_lengths, target_lengths, alpha, beta, nll, T, ldx,
-        S_max, blank);
-  else
-    return LASR_ERR_BAD_DTYPE;
-  LASR_CHECK_LAUNCH();
-  return LASR_OK;
+    return ctc_lattice_dispatch<float>(x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, N, T, ldx,
+                                       S_max, blank, stream);
+  if (dtype == LASR_BF16)
+    return ctc_lattice_dispatch<__nv_bfloat16>(x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, N, T,
+                                               ldx, S_max, blank, stream);
+  return LASR_ERR_BAD_DTYPE;
 }
 
 int lasr_ctc_bwd(const void* x, const float* lse, const int64_t* targets, const int32_t* input_lengths,
@@ -408,6 +502,31 @@ int lasr_ctc_collapse(const int64_t* predictions, const int32_t* lengths, int32_
                       int T, int blank, lasr_stream_t stream) {
   if (N <= 0 || T <= 0 || predictions == nullptr || tokens == nullptr || counts == nullptr) return LASR_ERR_BAD_SHAPE;
   ctc_collapse_kernel<<<N, 32, 0, stream>>>(predictions, lengths, tokens, counts, T, blank);
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+/* out[c] += sum_m x[m, c] for c < C (out fp32, caller zeroes): the decoder bias gradient */
+int lasr_colsum(const void* x, float* out, int M, int C, int ld, int dtype, lasr_stream_t stream) {
+  if (M <= 0 || C <= 0 || ld < C) return LASR_ERR_BAD_SHAPE;
+  int cols_par = 32;
+  while (cols_par < C && cols_par < 256) cols_par *= 2;
+  const int col_groups = cdiv(C, cols_par);
+  int gy = col_groups < 8 ? col_groups : 8;
+  int gx = (2 * kNumSMs) / gy;
+  if (gx < 1) gx = 1;
+  int rows_per_block = cdiv(M, gx);
+  if (rows_per_block < 64) rows_per_block = 64;
+  gx = cdiv(M, rows_per_block);
+  dim3 grid(gx, gy);
+  if (dtype == LASR_F32)
+    colsum_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), out, M, C, ld, cols_par,
+                                                   rows_per_block);
+  else if (dtype == LASR_BF16)
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), out, M, C, ld,
+                                                           cols_par, rows_per_block);
+  else
+    return LASR_ERR_BAD_DTYPE;
   LASR_CHECK_LAUNCH();
   return LASR_OK;
 }

@@ -13,7 +13,7 @@
 //           sliding register window, fully unrolled at compile time (k is a template parameter).
 //   wgrad : warp = contiguous chunk of taps, lane = channel pair; accumulators stay in registers across all the
 //           time tiles a CTA walks (double-buffered TMA), then one fp32 RED per (tap, channel).
-// Weights are "tap-major" fp32 [K, C] (see lasr_cast_weight(transpose=1)).
+// Weights and weight gradients keep the reference's layout: fp32 [C, 1, K] (nn.Conv1d(groups=C).weight).
 #include "common.cuh"
 
 namespace lasr {
@@ -118,14 +118,15 @@ dwconv_fwd_kernel(const __grid_constant__ CUtensorMap tmap_x, const float* __res
     for (int b = 0; b < Cfg::BOXES; ++b)
       tma_load_3d(sx + b * DW_TMA_ROWS * ROW_BYTES, &tmap_x, &bar, c0, tin0 + b * DW_TMA_ROWS, n);
   }
-  // taps -> smem (tap-major global layout [K][C]); flip reverses the tap order (data-gradient)
+  // taps -> smem as [K][32] channel pairs from the reference's native layout weight[c, 0, j] (global reads run
+  // along j, i.e. coalesced); flip reverses the tap order (data-gradient)
   for (int i = tid; i < K * 32; i += Cfg::THREADS) {
-    const int j = i >> 5, p = i & 31;
+    const int p = i / K, j = i - p * K;
     const int c = c0 + 2 * p;
     const int jj = flip ? (K - 1 - j) : j;
     float2 v = make_float2(0.f, 0.f);
-    if (c < C) v = *reinterpret_cast<const float2*>(wt + static_cast<size_t>(jj) * C + c);
-    sw[i] = v;
+    if (c < C) v = make_float2(wt[static_cast<size_t>(c) * K + jj], wt[static_cast<size_t>(c + 1) * K + jj]);
+    sw[j * 32 + p] = v;
   }
   __syncthreads();
   mbar_wait(&bar, 0);
@@ -278,8 +279,8 @@ dwconv_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     for (int jj = 0; jj < JW; ++jj) {
       const int j = j0 + jj;
       if (j < K) {
-        atomicAdd(dwt + static_cast<size_t>(j) * C + c, acc[jj].x);
-        atomicAdd(dwt + static_cast<size_t>(j) * C + c + 1, acc[jj].y);
+        atomicAdd(dwt + static_cast<size_t>(c) * K + j, acc[jj].x);
+        atomicAdd(dwt + static_cast<size_t>(c + 1) * K + j, acc[jj].y);
       }
     }
   }

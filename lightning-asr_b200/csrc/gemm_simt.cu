@@ -128,25 +128,94 @@ gemm_simt_tn_kernel(const float* __restrict__ DY, const float* __restrict__ X, f
   }
 }
 
-// per-32-row-group column statistics: stats[g, 0, c] = sum_r y[r, c], stats[g, 1, c] = sum_r y[r,c]^2
+// column statistics of a [M, N] matrix: stats[0][c] += sum_r y[r, c], stats[1][c] += sum_r y[r, c]^2 (double, RED)
 template <typename T>
 __global__ void __launch_bounds__(256)
-colstats_kernel(const T* __restrict__ y, float* __restrict__ stats, int M, int N, int ld) {
-  const int g = blockIdx.x;
-  const int r0 = g * 32;
+colstats_kernel(const T* __restrict__ y, double* __restrict__ stats, int M, int N, int ld, int rows_per_block) {
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(M, r0 + rows_per_block);
   for (int c = threadIdx.x; c < N; c += blockDim.x) {
-    float s = 0.f, q = 0.f;
-#pragma unroll 4
-    for (int r = r0; r < r0 + 32; ++r) {
-      if (r < M) {
+    double s = 0.0, q = 0.0;
+    for (int rb = r0; rb < r1; rb += 32) {
+      float ps = 0.f, pq = 0.f;
+      const int re = min(r1, rb + 32);
+      for (int r = rb; r < re; ++r) {
         const float v = to_f32<T>(y[static_cast<size_t>(r) * ld + c]);
-        s += v;
-        q += v * v;
+        ps += v;
+        pq = fmaf(v, v, pq);
       }
+      s += ps;
+      q += pq;
     }
-    stats[(static_cast<size_t>(g) * 2 + 0) * N + c] = s;
-    stats[(static_cast<size_t>(g) * 2 + 1) * N + c] = q;
+    atomicAdd(stats + c, s);
+    atomicAdd(stats + N + c, q);
   }
+}
+
+// C[M, N] = A[M, K] * B[K, N] (row-major B): fp32 data gradient dx = dy * W with W in its native [Cout, Cin] layout
+__global__ void __launch_bounds__(256)
+gemm_simt_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ C, int M, int N,
+                    int K, int lda, int ldb, int ldc) {
+  constexpr int BM = 128, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int tx = tid & 15, ty = tid >> 4;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 256;
+      const int r = idx >> 4, kk = idx & 15;
+      const int gr = m0 + r, gk = k0 + kk;
+      As[kk][r] = (gr < M && gk < K) ? A[static_cast<size_t>(gr) * lda + gk] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      const int kk = idx >> 6, c = idx & 63;
+      const int gk = k0 + kk, gc = n0 + c;
+      Bs[kk][c] = (gk < K && gc < N) ? B[static_cast<size_t>(gk) * ldb + gc] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[8], b[4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = As[kk][ty * 8 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = m0 + ty * 8 + i;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = n0 + tx * 4 + j;
+      if (c < N) C[static_cast<size_t>(r) * ldc + c] = acc[i][j];
+    }
+  }
+}
+
+int gemm_simt_nn(const float* a, const float* b, float* c, int M, int N, int K, int lda, int ldb, int ldc,
+                 cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return LASR_ERR_BAD_SHAPE;
+  dim3 grid(cdiv(M, 128), cdiv(N, 64));
+  gemm_simt_nn_kernel<<<grid, 256, 0, stream>>>(a, b, c, M, N, K, lda, ldb, ldc);
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
 }
 
 int gemm_simt_nt(const float* a, const float* b, float* c, const float* bias, const int32_t* lengths, int T, int M,
@@ -173,13 +242,14 @@ int gemm_simt_tn_accum(const float* dy, const float* x, float* dw, int R, int Co
   return LASR_OK;
 }
 
-int colstats(const void* y, float* stats, int M, int N, int ld, int dtype, cudaStream_t stream) {
-  const int groups = cdiv(M, 128) * 4;
+int colstats(const void* y, double* stats, int M, int N, int ld, int dtype, cudaStream_t stream) {
+  const int rows_per_block = 128;
+  const int blocks = cdiv(M, rows_per_block);
   if (dtype == LASR_F32)
-    colstats_kernel<float><<<groups, 256, 0, stream>>>(static_cast<const float*>(y), stats, M, N, ld);
+    colstats_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(y), stats, M, N, ld, rows_per_block);
   else
     colstats_kernel<__nv_bfloat16>
-        <<<groups, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), stats, M, N, ld);
+        <<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(y), stats, M, N, ld, rows_per_block);
   LASR_CHECK_LAUNCH();
   return LASR_OK;
 }

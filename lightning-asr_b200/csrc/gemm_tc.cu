@@ -35,7 +35,7 @@ struct GemmTcParams {
   const float* bias;
   const int32_t* lengths;
   int T;
-  float* stats;
+  double* stats;  // [2, N] column sum / sum of squares, accumulated with RED.f64 (caller zeroes)
 };
 
 template <int BN>
@@ -99,13 +99,16 @@ __device__ __forceinline__ float warp_column_sums(const float (&f)[32], int lane
   return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
+__device__ __forceinline__ void red_add_f64(double* addr, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
 
 // EPI: 0 = store (bias / mask / stats), 1 = fp32 RED accumulate (split-K weight gradient)
-template <int BN, bool MN_MAJOR, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const GemmTcParams p) {
@@ -171,13 +174,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          if constexpr (!MN_MAJOR) {
+          if constexpr (!A_MN) {
             tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
           } else {
 #pragma unroll
             for (int c = 0; c < BM / 64; ++c)
               tma_load_2d(sa + c * (64 * BK * 2), &tma_a, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+          } else {
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c)
               tma_load_2d(sb + c * (64 * BK * 2), &tma_b, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
@@ -192,7 +198,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, MN_MAJOR ? 1 : 0, MN_MAJOR ? 1 : 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int local_tile = 0;
@@ -212,17 +218,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint32_t sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
-            uint64_t da, db;
-            if constexpr (!MN_MAJOR) {
-              // K-major, SW128: 8-row groups 1024 B apart; 16 bf16 of K = 32 B inside the swizzle atom
-              da = umma_desc_sw128(sa + k * 32, 16, 1024);
-              db = umma_desc_sw128(sb + k * 32, 16, 1024);
-            } else {
-              // MN-major, SW128: 64-channel chunks 8192 B apart (LBO), 8-frame groups 1024 B apart (SBO);
-              // 16 frames of K = 2048 B
-              da = umma_desc_sw128(sa + k * 2048, 64 * BK * 2, 1024);
-              db = umma_desc_sw128(sb + k * 2048, 64 * BK * 2, 1024);
-            }
+            // K-major, SW128: 8-row groups 1024 B apart; 16 bf16 of K = 32 B inside the swizzle atom.
+            // MN-major, SW128: 64-channel chunks 8192 B apart (LBO), 8-row (K) groups 1024 B apart (SBO);
+            // 16 rows of K = 2048 B.
+            const uint64_t da = A_MN ? umma_desc_sw128(sa + k * 2048, 64 * BK * 2, 1024)
+                                     : umma_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, 64 * BK * 2, 1024)
+                                     : umma_desc_sw128(sb + k * 32, 16, 1024);
             umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
@@ -282,10 +284,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) q[j] = f[j] * f[j];
             const float ss = warp_column_sums(q, lane);
-            if (col0 + lane < p.N) {
-              float* dst = p.stats + static_cast<size_t>(m_blk * 4 + ew) * 2 * p.N + col0 + lane;
-              dst[0] = s;
-              dst[p.N] = ss;
+            if (col0 + lane < p.N) {  // one 128-byte RED transaction per warp and statistic
+              red_add_f64(p.stats + col0 + lane, static_cast<double>(s));
+              red_add_f64(p.stats + p.N + col0 + lane, static_cast<double>(ss));
             }
           }
           if (row_ok) {
@@ -381,13 +382,13 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
   return r == CUDA_SUCCESS ? LASR_OK : LASR_ERR_DRIVER;
 }
 
-template <int BN, bool MN_MAJOR, int EPI>
+template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p, int grid,
                        cudaStream_t stream) {
   using Cfg = GemmTcCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, MN_MAJOR, EPI>,
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, EPI>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) {
       lasr_set_cuda_error(e);
@@ -395,7 +396,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmT
     }
     configured = true;
   }
-  gemm_tc_kernel<BN, MN_MAJOR, EPI><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_tc_kernel<BN, A_MN, B_MN, EPI><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
   LASR_CHECK_LAUNCH();
   return LASR_OK;
 }
@@ -403,7 +404,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmT
 static int pick_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256)); }
 
 // y[M, N] = x[M, K] w[N, K]^T, bf16 in, bf16/fp32 out
-int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const int32_t* lengths, int T, float* stats,
+int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const int32_t* lengths, int T, double* stats,
                int M, int N, int K, int lda, int ldb, int ldc, int out_f32, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return LASR_ERR_BAD_SHAPE;
   if ((lda % 8) || (ldb % 8)) return LASR_ERR_ALIGNMENT;
@@ -434,10 +435,45 @@ int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   const int grid = tiles < kNumSMs ? tiles : kNumSMs;
   switch (BN) {
-    case 32: return launch_inst<32, false, 0>(ta, tb, p, grid, stream);
-    case 64: return launch_inst<64, false, 0>(ta, tb, p, grid, stream);
-    case 128: return launch_inst<128, false, 0>(ta, tb, p, grid, stream);
-    default: return launch_inst<256, false, 0>(ta, tb, p, grid, stream);
+    case 32: return launch_inst<32, false, false, 0>(ta, tb, p, grid, stream);
+    case 64: return launch_inst<64, false, false, 0>(ta, tb, p, grid, stream);
+    case 128: return launch_inst<128, false, false, 0>(ta, tb, p, grid, stream);
+    default: return launch_inst<256, false, false, 0>(ta, tb, p, grid, stream);
+  }
+}
+
+// y[M, N] = a[M, K] b[K, N]: the data gradient dx = dy * W with W in its native [Cout = K, Cin = N] layout, i.e. an
+// MN-major B operand (no transposed weight copy).  bf16 in, bf16/fp32 out.
+int gemm_tc_nn(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldc, int out_f32,
+               cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return LASR_ERR_BAD_SHAPE;
+  if ((lda % 8) || (ldb % 8)) return LASR_ERR_ALIGNMENT;
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  CUtensorMap ta, tb;
+  int rc = make_tmap_2d_bf16(&ta, a, K, M, static_cast<uint64_t>(lda) * 2, 64, 128, true);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tb, b, N, K, static_cast<uint64_t>(ldb) * 2, 64, 64, true);
+  if (rc) return rc;
+  GemmTcParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_m_blocks = cdiv(M, 128);
+  p.num_n_blocks = cdiv(N, BN);
+  p.num_k_blocks = cdiv(K, 64);
+  p.k_splits = 1;
+  p.kb_per_split = p.num_k_blocks;
+  p.out = out;
+  p.ldc = ldc;
+  p.out_f32 = out_f32;
+  const int esz = out_f32 ? 4 : 2;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((static_cast<size_t>(ldc) * esz) % 16 == 0);
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  switch (BN) {
+    case 64: return launch_inst<64, false, true, 0>(ta, tb, p, grid, stream);
+    case 128: return launch_inst<128, false, true, 0>(ta, tb, p, grid, stream);
+    default: return launch_inst<256, false, true, 0>(ta, tb, p, grid, stream);
   }
 }
 
@@ -472,9 +508,9 @@ int gemm_tc_tn_accum(const void* dy, const void* x, float* dw, int R, int Cout, 
   const int total = tiles * p.k_splits;
   const int grid = total < kNumSMs ? total : kNumSMs;
   switch (BN) {
-    case 64: return launch_inst<64, true, 1>(ta, tb, p, grid, stream);
-    case 128: return launch_inst<128, true, 1>(ta, tb, p, grid, stream);
-    default: return launch_inst<256, true, 1>(ta, tb, p, grid, stream);
+    case 64: return launch_inst<64, true, true, 1>(ta, tb, p, grid, stream);
+    case 128: return launch_inst<128, true, true, 1>(ta, tb, p, grid, stream);
+    default: return launch_inst<256, true, true, 1>(ta, tb, p, grid, stream);
   }
 }
 

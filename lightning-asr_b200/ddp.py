@@ -25,65 +25,80 @@ def broadcast_parameters(module, src=0, group=None):
 class GradSync:
     """Flat-bucket gradient all-reduce.
 
-    grad_sync = GradSync(module, bucket_mb=8); after `loss.backward()` call `grad_sync(module)` (synchronous variant),
-    or install hooks with `overlap=True` so each bucket's all-reduce starts when its last gradient is produced.
+    With a runtime.ParamBank (the step engine's mode) the buckets are contiguous slices of the bank's flat gradient
+    buffer -- the wgrad kernels have already accumulated into them, nothing is copied -- and a bucket is launched the
+    moment the last of its parameters is reported by runtime.grad_ready().  Without a bank (generic autograd usage,
+    the CPU tests) gradients are attached as views of private flat buckets and post-accumulate hooks do the
+    reporting.  Call the object after backward to drain: it reduces whatever has not fired and joins the side stream.
     """
 
-    def __init__(self, module, group=None, bucket_mb=8.0, overlap=True):
+    def __init__(self, module, group=None, bucket_mb=8.0, overlap=True, bank=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bank = bank
         self.params = [p for p in module.parameters() if p.requires_grad]
-        # reverse registration order ~ backward completion order (decoder / last layers first)
-        order = list(reversed(self.params))
-        self.buckets = []  # list of (flat fp32 tensor, [(param, offset, numel)])
+        order = list(reversed(self.params))  # ~ backward completion order (decoder / last layers first)
         cap = int(bucket_mb * 1024 * 1024 / 4)
-        cur, cur_n = [], 0
+        groups, cur, cur_n = [], [], 0
         for p in order:
             if cur and cur_n + p.numel() > cap:
-                self._close(cur, cur_n)
+                groups.append(cur)
                 cur, cur_n = [], 0
             cur.append(p)
             cur_n += p.numel()
         if cur:
-            self._close(cur, cur_n)
+            groups.append(cur)
+        self.buckets = []  # (flat fp32 tensor, [(param, offset, numel)])
+        for g in groups:
+            if bank is not None:
+                lo = min(bank.offsets[id(p)] for p in g)
+                hi = max(bank.offsets[id(p)] + p.numel() for p in g)
+                flat = bank.grads[lo:hi]
+                items = [(p, bank.offsets[id(p)] - lo, p.numel()) for p in g]
+            else:
+                flat = torch.zeros(sum(p.numel() for p in g), device=g[0].device, dtype=torch.float32)
+                items, off = [], 0
+                for p in g:
+                    items.append((p, off, p.numel()))
+                    off += p.numel()
+            self.buckets.append((flat, items))
         self.overlap = overlap and self.world > 1
         self.comm_stream = None
-        self._pending = {}
-        self._events = []
         if self.overlap and self.params and self.params[0].is_cuda:
             self.comm_stream = torch.cuda.Stream()
         self._bucket_of = {}
         for bi, (_, items) in enumerate(self.buckets):
             for p, _, _ in items:
                 self._bucket_of[id(p)] = bi
-        if self.overlap:
+        self._left = [len(items) for _, items in self.buckets]
+        self._fired = [False] * len(self.buckets)
+        if bank is not None:
+            bank.on_grad_ready = self._ready if self.overlap else None
+        elif self.overlap:
             for p in self.params:
-                p.register_post_accumulate_grad_hook(self._hook)
+                p.register_post_accumulate_grad_hook(self._ready)
 
-    def _close(self, params, n):
-        dev = params[0].device
-        flat = torch.zeros(n, device=dev, dtype=torch.float32)
-        items, off = [], 0
-        for p in params:
-            items.append((p, off, p.numel()))
-            off += p.numel()
-        self.buckets.append((flat, items))
-
-    # gradients are views of the flat buckets, so backward's accumulation writes straight into them (no copy)
+    # no-bank mode: gradients are views of the private flat buckets, so backward's accumulation writes into them
     def attach_grad_views(self):
+        if self.bank is not None:
+            return
         for flat, items in self.buckets:
             for p, off, n in items:
                 p.grad = flat[off:off + n].view_as(p)
 
     def zero_and_attach(self):
-        for flat, _ in self.buckets:
-            flat.zero_()
-        self.attach_grad_views()
-        self._pending = {}
+        """Start of a step (no-bank mode zeroes its own buckets; the bank zeroes itself in begin_step)."""
+        if self.bank is None:
+            for flat, _ in self.buckets:
+                flat.zero_()
+            self.attach_grad_views()
+        self._left = [len(items) for _, items in self.buckets]
+        self._fired = [False] * len(self.buckets)
 
     def _reduce_bucket(self, bi):
         flat, items = self.buckets[bi]
-        views = all(p.grad is not None and p.grad.data_ptr() == flat[off:off + n].data_ptr() for p, off, n in items)
+        views = self.bank is not None or all(
+            p.grad is not None and p.grad.data_ptr() == flat[off:off + n].data_ptr() for p, off, n in items)
         if not views:
             for p, off, n in items:
                 if p.grad is None:
@@ -101,35 +116,29 @@ class GradSync:
                 if p.grad is not None:
                     p.grad.copy_(flat[off:off + n].view_as(p.grad))
 
-    def _hook(self, p):
-        bi = self._bucket_of[id(p)]
-        left = self._pending.get(bi)
-        if left is None:
-            left = len(self.buckets[bi][1])
-        left -= 1
-        self._pending[bi] = left
-        if left == 0:
-            self._pending[bi] = None
-            if self.comm_stream is not None:
-                self.comm_stream.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(self.comm_stream):
-                    self._reduce_bucket(bi)
-            else:
+    def _launch(self, bi):
+        self._fired[bi] = True
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
                 self._reduce_bucket(bi)
+        else:
+            self._reduce_bucket(bi)
+
+    def _ready(self, p):
+        bi = self._bucket_of.get(id(p))
+        if bi is None or self._fired[bi]:
+            return
+        self._left[bi] -= 1
+        if self._left[bi] == 0:
+            self._launch(bi)
 
     def __call__(self, module=None):
-        """Finish the exchange: in overlap mode wait for the side stream; otherwise reduce every bucket now."""
+        """Finish the exchange: reduce every bucket that has not fired, then join the side stream."""
         if self.world == 1:
             return
-        if self.overlap:
-            # buckets whose parameters received no gradient this step never fired: reduce them now
-            for bi, left in list(self._pending.items()):
-                if left is not None:
-                    self._pending[bi] = None
-                    self._reduce_bucket(bi)
-            self._pending = {}
-            if self.comm_stream is not None:
-                torch.cuda.current_stream().wait_stream(self.comm_stream)
-        else:
-            for bi in range(len(self.buckets)):
-                self._reduce_bucket(bi)
+        for bi in range(len(self.buckets)):
+            if not self._fired[bi]:
+                self._launch(bi)
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)

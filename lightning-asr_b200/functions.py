@@ -13,16 +13,15 @@ Backward passes are hand-scheduled kernel sequences, not autograd graphs.
 """
 import torch
 
-from . import ops
+from . import ops, runtime
 from .ops import ACT_NONE, ACT_RELU
 
 BN_EPS = 1e-3  # nn.BatchNorm1d(out_ch, eps=1e-3)  models/QuartNet.py:24,64,147
 BN_MOMENTUM = 0.1
 
 
-def _bump(nbt):
-    if nbt is not None:
-        nbt.add_(1)
+def _stats(C, device):
+    return runtime.zeros((2, C), torch.float64, device)
 
 
 class SepConvBNFn(torch.autograd.Function):
@@ -36,45 +35,46 @@ class SepConvBNFn(torch.autograd.Function):
       se_w1 [Cout/8, Cout], se_w2 [Cout, Cout/8] or None (SELayer.fc.0 / fc.2)
       bn_buffers = (running_mean, running_var, num_batches_tracked) for bn; rbn_buffers likewise
       stride, relu (bool), training (bool)
+    Kernel sequence (training): dwconv -> pw GEMM (+mask, +BN sums) [-> residual GEMM (+BN sums)] [-> SE squeeze /
+    excite] -> ONE apply pass.  Backward: reduce -> apply -> pw wgrad, pw dgrad [-> res wgrad, res dgrad] -> dw wgrad,
+    dw dgrad (+ residual dgrad fused as addend).
     """
 
     @staticmethod
     def forward(ctx, x, res_x, lengths, dw_w, pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2, bn_buffers,
                 rbn_buffers, stride, relu, training):
         dt = x.dtype
+        dev = x.device
         N, T_in, Cin = x.shape
         K = dw_w.shape[-1]
         Cout = pw_w.shape[0]
         act = ACT_RELU if relu else ACT_NONE
-        wt = ops.cast_weight(dw_w.view(Cin, K), torch.float32, transpose=True)  # [K, Cin] tap-major
-        d = ops.dwconv_fwd(x, wt, stride=stride)
+        d = ops.dwconv_fwd(x, dw_w.detach(), stride=stride)
         T = d.shape[1]
-        pw_s = ops.cast_weight(pw_w.view(Cout, Cin), dt)
-        y, stats1 = ops.pwconv_fwd(d, pw_s, lengths=lengths, T=T, want_stats=training)
+        pw_s = runtime.weight(pw_w, dt).view(Cout, Cin)
+        sums1 = _stats(Cout, dev) if training else None
+        y = ops.pwconv_fwd(d, pw_s, lengths=lengths, T=T, stats=sums1)
         has_res = res_w is not None
-        r = stats2 = res_s = None
+        r = res_s = bn2 = None
         if has_res:
-            res_s = ops.cast_weight(res_w.view(Cout, res_w.shape[1]), dt)
-            r, stats2 = ops.pwconv_fwd(x if res_x is None else res_x, res_s, want_stats=training)
-        count = N * T
-        if training:
-            st1 = ops.bn_finalize(stats1, count, bn_w, bn_b, bn_buffers[0], bn_buffers[1], BN_EPS, BN_MOMENTUM)
-            _bump(bn_buffers[2])
-            st2 = None
-            if has_res:
-                st2 = ops.bn_finalize(stats2, count, rbn_w, rbn_b, rbn_buffers[0], rbn_buffers[1], BN_EPS, BN_MOMENTUM)
-                _bump(rbn_buffers[2])
-        else:
-            st1 = ops.bn_eval_coeffs(bn_w, bn_b, bn_buffers[0], bn_buffers[1], BN_EPS)
-            st2 = ops.bn_eval_coeffs(rbn_w, rbn_b, rbn_buffers[0], rbn_buffers[1], BN_EPS) if has_res else None
-        gate = s = hidden = sums_y = None
+            rin = x if res_x is None else res_x
+            res_s = runtime.weight(res_w, dt).view(Cout, rin.shape[-1])
+            sums2 = _stats(Cout, dev) if training else None
+            r = ops.pwconv_fwd(rin, res_s, stats=sums2)
+            bn2 = ops.BNForward(rbn_w.detach(), rbn_b.detach(), rbn_buffers[0], rbn_buffers[1], rbn_buffers[2], sums2)
+        bn1 = ops.BNForward(bn_w.detach(), bn_b.detach(), bn_buffers[0], bn_buffers[1], bn_buffers[2], sums1)
+        gate = s = hidden = sums_y = scale1 = shift1 = None
+        se_side = True
         if se_w1 is not None:
+            # the excitation needs BN1's coefficients before the apply pass: s = scale*mean_t(y) + shift
+            scale1, shift1 = ops.bn_coeffs(bn1, N * T, BN_EPS, BN_MOMENTUM, side_effects=False)
             sums_y = ops.sum_over_time(y)
-            s, hidden, gate = ops.se_excite_fwd(sums_y, st1, T, se_w1, se_w2)
-        out = ops.bn_apply_act(y, st1, r, st2, gate, act)
+            s, hidden, gate = ops.se_excite_fwd(sums_y, scale1, shift1, T, se_w1.detach(), se_w2.detach())
+        out = ops.bn_apply_act(y, bn1, r, bn2, gate, act, BN_EPS, BN_MOMENTUM, side_effects=se_side)
 
-        ctx.saved = (x, res_x, lengths, wt, d, y, r, out, st1, st2, gate, s, hidden, sums_y)
-        ctx.params = (dw_w, pw_w, bn_w, res_w, rbn_w, se_w1, se_w2)
+        ctx.saved = (x, res_x, lengths, d, y, r, out, bn1.save, bn2.save if bn2 is not None else None, gate, s, hidden,
+                     sums_y, scale1, shift1, pw_s, res_s)
+        ctx.params = (dw_w, pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2)
         ctx.cfg = (stride, act, training, K, Cin, Cout)
         ctx.set_materialize_grads(False)
         return out
@@ -83,60 +83,68 @@ class SepConvBNFn(torch.autograd.Function):
     def backward(ctx, dout):
         if dout is None:
             return (None,) * 17
-        x, res_x, lengths, wt, d, y, r, out, st1, st2, gate, s, hidden, sums_y = ctx.saved
-        dw_w, pw_w, bn_w, res_w, rbn_w, se_w1, se_w2 = ctx.params
+        (x, res_x, lengths, d, y, r, out, save1, save2, gate, s, hidden, sums_y, scale1, shift1, pw_s,
+         res_s) = ctx.saved
+        dw_w, pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2 = ctx.params
         stride, act, training, K, Cin, Cout = ctx.cfg
         if not training:
             raise RuntimeError("lightning_asr_b200: backward through eval-mode BatchNorm is not implemented")
-        dt = x.dtype
+        dev = x.device
         dout = dout.contiguous()
         N, T, _ = y.shape
-        count = N * T
         has_res = r is not None
-        partials, chunks = ops.bn_act_bwd_reduce(dout, out, y, r, act)
-        d_bn_w = torch.zeros_like(bn_w)
-        d_bn_b = torch.zeros_like(bn_w)
-        d_rbn_w = d_rbn_b = None
-        extra = d_se1 = d_se2 = None
-        if gate is not None:
-            extra, d_se1, d_se2 = ops.se_excite_bwd(partials, chunks, st1, T, se_w1, se_w2, s, hidden, gate)
-            coef1 = ops.se_bn_bwd_finalize(partials, N, chunks, T, gate, extra, sums_y, bn_w, st1, d_bn_w, d_bn_b)
-        else:
-            coef1 = ops.bn_bwd_finalize(partials, count, 0, 1, bn_w, st1, d_bn_w, d_bn_b)
-        coef2 = None
+        g_bn_w, ret_bn_w = runtime.grad_sink(bn_w)
+        g_bn_b, ret_bn_b = runtime.grad_sink(bn_b)
+        g_rbn_w = ret_rbn_w = g_rbn_b = ret_rbn_b = None
         if has_res:
-            d_rbn_w = torch.zeros_like(rbn_w)
-            d_rbn_b = torch.zeros_like(rbn_w)
-            coef2 = ops.bn_bwd_finalize(partials, count, 0, 2, rbn_w, st2, d_rbn_w, d_rbn_b)
-        dy, dr = ops.bn_act_bwd_apply(dout, out, y, r, gate, extra, coef1, coef2, lengths, act)
+            g_rbn_w, ret_rbn_w = runtime.grad_sink(rbn_w)
+            g_rbn_b, ret_rbn_b = runtime.grad_sink(rbn_b)
+        totals = runtime.zeros((3, Cout), torch.float64, dev)
+        per_n = runtime.zeros((N, 3, Cout), torch.float32, dev) if gate is not None else None
+        ops.bn_act_bwd_reduce(dout, out, y, r, act, totals, per_n)
+        extra = coef1 = None
+        ret_se1 = ret_se2 = None
+        bn1_side = (bn_w.detach(), save1, g_bn_w, g_bn_b)
+        if gate is not None:
+            g_se1, ret_se1 = runtime.grad_sink(se_w1)
+            g_se2, ret_se2 = runtime.grad_sink(se_w2)
+            extra = ops.se_excite_bwd(per_n, scale1, shift1, T, se_w1.detach(), se_w2.detach(), s, hidden, gate,
+                                      g_se1, g_se2)
+            coef1 = ops.se_bn_bwd_finalize(per_n, N, T, gate, extra, sums_y, bn_w.detach(), save1, g_bn_w, g_bn_b)
+            bn1_side = None
+        bn2_side = (rbn_w.detach(), save2, g_rbn_w, g_rbn_b) if has_res else None
+        dy, dr = ops.bn_act_bwd_apply(dout, out, y, r, gate, extra, totals, coef1, bn1_side, bn2_side, lengths, act)
+        runtime.grad_ready(bn_w, bn_b, rbn_w, rbn_b, se_w1, se_w2)
 
-        # pointwise conv: weight grads (split-K tcgen05 MN-major GEMM) and data grads (same NT kernel, W^T)
-        d_pw = ops.pwconv_wgrad(dy, d).view(Cout, Cin, 1)
-        pw_t = ops.cast_weight(pw_w.view(Cout, Cin), dt, transpose=True)  # [Cin, Cout]
-        dd, _ = ops.pwconv_fwd(dy, pw_t)
-        d_res = None
+        # pointwise conv: weight gradient (split-K tcgen05 MN-major GEMM) and data gradient (W as MN-major B operand)
+        g_pw, ret_pw = runtime.grad_sink(pw_w)
+        ops.pwconv_wgrad(dy, d, out=g_pw)
+        runtime.grad_ready(pw_w)
+        dd = ops.pwconv_dgrad(dy, pw_s)
+        ret_res = None
         dxr = None
         d_res_x = None
         need_dx = ctx.needs_input_grad[0]
         if has_res:
             rin = x if res_x is None else res_x
-            Cres = rin.shape[-1]
-            d_res = ops.pwconv_wgrad(dr, rin).view(Cout, Cres, 1)
+            g_res, ret_res = runtime.grad_sink(res_w)
+            ops.pwconv_wgrad(dr, rin, out=g_res)
+            runtime.grad_ready(res_w)
             if (res_x is None and need_dx) or (res_x is not None and ctx.needs_input_grad[1]):
-                res_t = ops.cast_weight(res_w.view(Cout, Cres), dt, transpose=True)
-                dxr, _ = ops.pwconv_fwd(dr, res_t)
+                dxr = ops.pwconv_dgrad(dr, res_s)
                 if res_x is not None:
                     d_res_x, dxr = dxr, None
         # depthwise conv
-        dwt = ops.dwconv_wgrad(x, dd, K, stride=stride)  # [K, Cin]
-        d_dw = ops.cast_weight(dwt, torch.float32, transpose=True).view(Cin, 1, K)
+        g_dw, ret_dw = runtime.grad_sink(dw_w)
+        ops.dwconv_wgrad(x, dd, K, stride=stride, out=g_dw)
+        runtime.grad_ready(dw_w)
         dx = None
         if need_dx:
             if stride != 1:
                 raise RuntimeError("lightning_asr_b200: data gradient of the stride-2 first conv is not needed/implemented")
-            dx = ops.dwconv_fwd(dd, wt, stride=1, flip=True, addend=dxr)
-        return (dx, d_res_x, None, d_dw, d_pw, d_bn_w, d_bn_b, d_res, d_rbn_w, d_rbn_b, d_se1, d_se2, None, None, None,
-                None, None)
+            dx = ops.dwconv_fwd(dd, dw_w.detach(), stride=1, flip=True, addend=dxr)
+        return (dx, d_res_x, None, ret_dw, ret_pw, ret_bn_w, ret_bn_b, ret_res, ret_rbn_w, ret_rbn_b, ret_se1, ret_se2,
+                None, None, None, None, None)
 
 
 class Conv1x1BNReLUFn(torch.autograd.Function):
@@ -148,43 +156,40 @@ class Conv1x1BNReLUFn(torch.autograd.Function):
         dt = x.dtype
         N, T, Cin = x.shape
         Cout = w.shape[0]
-        w_s = ops.cast_weight(w.view(Cout, Cin), dt)
-        y, stats = ops.pwconv_fwd(x, w_s, want_stats=training)
-        if training:
-            st = ops.bn_finalize(stats, N * T, bn_w, bn_b, bn_buffers[0], bn_buffers[1], BN_EPS, BN_MOMENTUM)
-            _bump(bn_buffers[2])
-        else:
-            st = ops.bn_eval_coeffs(bn_w, bn_b, bn_buffers[0], bn_buffers[1], BN_EPS)
+        w_s = runtime.weight(w, dt).view(Cout, Cin)
+        sums = _stats(Cout, x.device) if training else None
+        y = ops.pwconv_fwd(x, w_s, stats=sums)
+        bn = ops.BNForward(bn_w.detach(), bn_b.detach(), bn_buffers[0], bn_buffers[1], bn_buffers[2], sums)
         act = ACT_RELU if relu else ACT_NONE
-        out = ops.bn_apply_act(y, st, act=act)
-        ctx.saved = (x, y, out, st)
-        ctx.params = (w, bn_w)
+        out = ops.bn_apply_act(y, bn, act=act, eps=BN_EPS, momentum=BN_MOMENTUM)
+        ctx.saved = (x, y, out, bn.save, w_s)
+        ctx.params = (w, bn_w, bn_b)
         ctx.training = training
         ctx.act = act
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, y, out, st = ctx.saved
-        w, bn_w = ctx.params
+        x, y, out, save, w_s = ctx.saved
+        w, bn_w, bn_b = ctx.params
         if not ctx.training:
             raise RuntimeError("lightning_asr_b200: backward through eval-mode BatchNorm is not implemented")
-        dt = x.dtype
         dout = dout.contiguous()
         N, T, Cin = x.shape
         Cout = w.shape[0]
         act = ctx.act
-        partials, _ = ops.bn_act_bwd_reduce(dout, out, y, None, act)
-        d_bn_w = torch.zeros_like(bn_w)
-        d_bn_b = torch.zeros_like(bn_w)
-        coef = ops.bn_bwd_finalize(partials, N * T, 0, 1, bn_w, st, d_bn_w, d_bn_b)
-        dy, _ = ops.bn_act_bwd_apply(dout, out, y, None, None, None, coef, None, None, act)
-        d_w = ops.pwconv_wgrad(dy, x).view(Cout, Cin, 1)
-        dx = None
-        if ctx.needs_input_grad[0]:
-            w_t = ops.cast_weight(w.view(Cout, Cin), dt, transpose=True)
-            dx, _ = ops.pwconv_fwd(dy, w_t)
-        return dx, d_w, d_bn_w, d_bn_b, None, None, None
+        totals = runtime.zeros((3, Cout), torch.float64, x.device)
+        ops.bn_act_bwd_reduce(dout, out, y, None, act, totals)
+        g_w, ret_w = runtime.grad_sink(bn_w)
+        g_b, ret_b = runtime.grad_sink(bn_b)
+        dy, _ = ops.bn_act_bwd_apply(dout, out, y, None, None, None, totals, None, (bn_w.detach(), save, g_w, g_b),
+                                     None, None, act)
+        runtime.grad_ready(bn_w, bn_b)
+        g_cw, ret_cw = runtime.grad_sink(w)
+        ops.pwconv_wgrad(dy, x, out=g_cw)
+        runtime.grad_ready(w)
+        dx = ops.pwconv_dgrad(dy, w_s) if ctx.needs_input_grad[0] else None
+        return dx, ret_cw, ret_w, ret_b, None, None, None
 
 
 def _pad8(v):
@@ -192,33 +197,25 @@ def _pad8(v):
 
 
 def _decoder_logits(x, w, b):
-    """logits [N, T, ld] with ld = V rounded up to 8 (16-byte rows for TMA); padded columns are exactly 0."""
+    """logits [N, T, ld] with ld = V rounded up to 8 (16-byte rows for TMA).  Only the first V columns are written /
+    meaningful: the weight's missing rows are zero-filled by TMA, every consumer reads columns < V only."""
     dt = x.dtype
     V, Cin = w.shape[0], w.shape[1]
-    ld = _pad8(V)
-    w_s = ops.cast_weight(w.view(V, Cin), dt, pad_rows=ld)
-    bias = torch.zeros((ld,), device=x.device, dtype=torch.float32)
-    bias[:V] = b
-    logits, _ = ops.pwconv_fwd(x, w_s, bias=bias)
-    return logits
+    w_s = runtime.weight(w, dt).view(V, Cin)
+    logits = ops.pwconv_fwd(x, w_s, bias=b.detach(), ldy=_pad8(V))
+    return logits, w_s
 
 
-def _decoder_backward(x, w, dlogits, need_dx):
-    """dlogits [N, T, ld] (padded columns zero) -> dx, dw [V, Cin, 1], db [V]."""
-    dt = x.dtype
-    V, Cin = w.shape[0], w.shape[1]
-    ld = dlogits.shape[-1]
-    dw_pad = ops.pwconv_wgrad(dlogits, x)  # [ld, Cin]
-    d_w = dw_pad[:V].reshape(V, Cin, 1)
-    # bias gradient = column sums of dlogits: reuse the pointwise wgrad against a ones column
-    ones = torch.ones(x.shape[:-1] + (8,), device=x.device, dtype=dt)
-    d_b = ops.pwconv_wgrad(dlogits, ones)[:V, 0].contiguous()
-    dx = None
-    if need_dx:
-        w_t = torch.zeros((Cin, ld), device=x.device, dtype=dt)
-        w_t[:, :V] = w.view(V, Cin).t().to(dt)
-        dx, _ = ops.pwconv_fwd(dlogits, w_t)
-    return dx, d_w, d_b
+def _decoder_backward(x, w, b, w_s, dlogits, need_dx):
+    """dlogits [N, T, ld] (columns >= V are zero) -> dx; accumulates dw [V, Cin, 1] and db [V]."""
+    V = w.shape[0]
+    g_w, ret_w = runtime.grad_sink(w)
+    ops.pwconv_wgrad(dlogits, x, out=g_w, Cout=V)
+    g_b, ret_b = runtime.grad_sink(b)
+    ops.colsum(dlogits, V, out=g_b)
+    runtime.grad_ready(w, b)
+    dx = ops.pwconv_dgrad(dlogits, w_s, lddy=dlogits.shape[-1]) if need_dx else None
+    return dx, ret_w, ret_b
 
 
 class DecoderLogSoftmaxFn(torch.autograd.Function):
@@ -227,19 +224,18 @@ class DecoderLogSoftmaxFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b):
         V = w.shape[0]
-        logits = _decoder_logits(x, w, b)
+        logits, w_s = _decoder_logits(x, w, b)
         _, lp = ops.log_softmax_fwd(logits, V, want_lp=True)
-        ctx.saved = (x, lp, logits.shape[-1])
-        ctx.params = (w,)
+        ctx.saved = (x, lp, logits.shape[-1], w_s)
+        ctx.params = (w, b)
         return lp
 
     @staticmethod
     def backward(ctx, dlp):
-        x, lp, ld = ctx.saved
-        (w,) = ctx.params
+        x, lp, ld, w_s = ctx.saved
+        w, b = ctx.params
         dlogits = ops.log_softmax_bwd(dlp.contiguous().float(), lp, ld, x.dtype)
-        dx, d_w, d_b = _decoder_backward(x, w, dlogits, ctx.needs_input_grad[0])
-        return dx, d_w, d_b
+        return _decoder_backward(x, w, b, w_s, dlogits, ctx.needs_input_grad[0])
 
 
 def _as_ntv(log_probs):
@@ -283,22 +279,22 @@ class FusedDecoderCTCFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, targets, input_lengths, target_lengths, blank):
         V = w.shape[0]
-        logits = _decoder_logits(x, w, b)
+        logits, w_s = _decoder_logits(x, w, b)
         lse, _ = ops.log_softmax_fwd(logits, V, want_lp=False)
         nll, alpha, beta = ops.ctc_fwd(logits, lse, targets, input_lengths, target_lengths, V, blank, want_beta=True)
-        ctx.saved = (x, logits, lse, targets, input_lengths, target_lengths, alpha, beta, nll)
-        ctx.params = (w,)
+        ctx.saved = (x, logits, lse, targets, input_lengths, target_lengths, alpha, beta, nll, w_s)
+        ctx.params = (w, b)
         ctx.blank = blank
         ctx.mark_non_differentiable(logits)
         return nll, logits
 
     @staticmethod
     def backward(ctx, gout, _glogits):
-        x, logits, lse, targets, il, tl, alpha, beta, nll = ctx.saved
-        (w,) = ctx.params
+        x, logits, lse, targets, il, tl, alpha, beta, nll, w_s = ctx.saved
+        w, b = ctx.params
         V = w.shape[0]
         ld = logits.shape[-1]
         dlogits = ops.ctc_bwd(logits, lse, targets, il, tl, alpha, beta, nll, gout.contiguous().float(), V, ctx.blank,
                               ld, x.dtype)
-        dx, d_w, d_b = _decoder_backward(x, w, dlogits, ctx.needs_input_grad[0])
+        dx, d_w, d_b = _decoder_backward(x, w, b, w_s, dlogits, ctx.needs_input_grad[0])
         return dx, d_w, d_b, None, None, None, None

@@ -5,6 +5,8 @@ eager / CPU fallback: inputs must be CUDA tensors and the shared library must be
 
 Activations are channels-last: [N, T, C] contiguous (C fastest).
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -41,16 +43,11 @@ def ntc_to_nct(y):
     return x
 
 
-def cast_weight(w2d, dtype, transpose=False, pad_rows=0):
-    """fp32 [R, C] master weight -> dtype shadow ([R, C] or [C, R]); optional zero rows appended (non-transposed)."""
+def cast_weight(w2d, dtype, transpose=False):
+    """fp32 [R, C] master weight -> dtype copy ([R, C] or [C, R])."""
     _chk(w2d, "w")
     R, C = w2d.shape
-    if transpose:
-        out = torch.empty((C, R), device=w2d.device, dtype=dtype)
-    elif pad_rows > R:
-        out = torch.zeros((pad_rows, C), device=w2d.device, dtype=dtype)
-    else:
-        out = torch.empty((R, C), device=w2d.device, dtype=dtype)
+    out = torch.empty((C, R) if transpose else (R, C), device=w2d.device, dtype=dtype)
     call("lasr_cast_weight", w2d, out, R, C, 1 if transpose else 0, dtype_code(dtype))
     return out
 
@@ -59,79 +56,110 @@ def dw_out_len(T_in, K, stride):
     return (T_in + 2 * (K // 2) - K) // stride + 1
 
 
-def dwconv_fwd(x, wt, stride=1, flip=False, addend=None):
-    """x [N, T_in, C], wt [K, C] fp32 tap-major -> y [N, T_out, C]."""
-    _chk(x, "x"), _chk(wt, "wt")
+def dwconv_fwd(x, w, stride=1, flip=False, addend=None):
+    """x [N, T_in, C], w [C, 1, K] fp32 (nn.Conv1d(groups=C).weight) -> y [N, T_out, C]."""
+    _chk(x, "x"), _chk(w, "w")
     N, T_in, C = x.shape
-    K = wt.shape[0]
+    K = w.shape[-1]
     T_out = dw_out_len(T_in, K, stride)
     y = torch.empty((N, T_out, C), device=x.device, dtype=x.dtype)
-    call("lasr_dwconv1d_fwd", x, wt, y, addend, N, T_in, T_out, C, K, stride, 1 if flip else 0, dtype_code(x.dtype))
+    call("lasr_dwconv1d_fwd", x, w, y, addend, N, T_in, T_out, C, K, stride, 1 if flip else 0, dtype_code(x.dtype))
     return y
 
 
-def dwconv_wgrad(x, dy, K, stride=1):
-    """-> dwt [K, C] fp32 tap-major."""
+def dwconv_wgrad(x, dy, K, stride=1, out=None):
+    """dw [C, 1, K] fp32 += sum dy * shifted x  (out: a zeroed / accumulating buffer, e.g. the flat-bucket view)."""
     _chk(x, "x"), _chk(dy, "dy")
     N, T_in, C = x.shape
     T_out = dy.shape[1]
-    dwt = torch.zeros((K, C), device=x.device, dtype=torch.float32)
-    call("lasr_dwconv1d_wgrad", x, dy, dwt, N, T_in, T_out, C, K, stride, dtype_code(x.dtype))
-    return dwt
+    dw = out if out is not None else torch.zeros((C, 1, K), device=x.device, dtype=torch.float32)
+    call("lasr_dwconv1d_wgrad", x, dy, dw, N, T_in, T_out, C, K, stride, dtype_code(x.dtype))
+    return dw
 
 
-def pwconv_fwd(x2d, w, bias=None, lengths=None, T=0, want_stats=False, out=None):
-    """y[M, Cout] = x[M, Cin] w[Cout, Cin]^T (+bias), MaskCNN row mask, BN partial statistics.
-
-    x2d may be a [N, T, Cin] tensor (flattened).  Returns (y, stats or None)."""
+def pwconv_fwd(x2d, w, bias=None, lengths=None, T=0, stats=None, out=None, ldy=None):
+    """y[M, Cout] = x[M, Cin] w[Cout, Cin]^T (+bias), MaskCNN row mask; `stats` (double [2, Cout], zeroed) receives the
+    BatchNorm batch sums.  x2d may be [N, T, Cin]; w [Cout, Cin(, 1)] in x's dtype.  Output row pitch ldy >= Cout."""
     _chk(x2d, "x"), _chk(w, "w")
     Cin = x2d.shape[-1]
     M = x2d.numel() // Cin
     Cout = w.shape[0]
     if w.shape[1] != Cin or w.dtype != x2d.dtype:
         raise _lib.LasrError(f"pwconv weight {tuple(w.shape)}/{w.dtype} does not match input Cin={Cin}/{x2d.dtype}")
-    y = out if out is not None else torch.empty(x2d.shape[:-1] + (Cout,), device=x2d.device, dtype=x2d.dtype)
-    stats = None
-    if want_stats:
-        groups = ((M + 127) // 128) * 4
-        stats = torch.empty((groups, 2, Cout), device=x2d.device, dtype=torch.float32)
-    call("lasr_pwconv_fwd", x2d, w, y, bias, lengths, T, stats, M, Cin, Cout, Cin, Cin, Cout, dtype_code(x2d.dtype))
-    return y, stats
+    ldy = Cout if ldy is None else ldy
+    y = out if out is not None else torch.empty(x2d.shape[:-1] + (ldy,), device=x2d.device, dtype=x2d.dtype)
+    call("lasr_pwconv_fwd", x2d, w, y, bias, lengths, T, stats, M, Cin, Cout, Cin, Cin, ldy, dtype_code(x2d.dtype))
+    return y
 
 
-def pwconv_wgrad(dy, x, out=None):
-    """dw[Cout, Cin] fp32 = dy[M, Cout]^T x[M, Cin]."""
+def pwconv_dgrad(dy, w, lddy=None):
+    """dx[M, Cin] = dy[M, Cout] w[Cout, Cin]   (w in its native layout; dy row pitch lddy >= Cout)."""
+    _chk(dy, "dy"), _chk(w, "w")
+    Cout, Cin = w.shape[0], w.shape[1]
+    lddy = dy.shape[-1] if lddy is None else lddy
+    M = dy.numel() // lddy
+    dx = torch.empty(dy.shape[:-1] + (Cin,), device=dy.device, dtype=dy.dtype)
+    call("lasr_pwconv_dgrad", dy, w, dx, M, Cin, Cout, lddy, Cin, Cin, dtype_code(dy.dtype))
+    return dx
+
+
+def pwconv_wgrad(dy, x, out=None, Cout=None):
+    """dw[Cout, Cin] fp32 += dy[M, :Cout]^T x[M, Cin]   (out zeroed / accumulating)."""
     _chk(dy, "dy"), _chk(x, "x")
-    Cout, Cin = dy.shape[-1], x.shape[-1]
+    lddy, Cin = dy.shape[-1], x.shape[-1]
+    Cout = lddy if Cout is None else Cout
     M = x.numel() // Cin
     dw = out if out is not None else torch.zeros((Cout, Cin), device=x.device, dtype=torch.float32)
-    call("lasr_pwconv_wgrad", dy, x, dw, M, Cin, Cout, Cout, Cin, Cin, dtype_code(x.dtype))
+    call("lasr_pwconv_wgrad", dy, x, dw, M, Cin, Cout, lddy, Cin, Cin, dtype_code(x.dtype))
     return dw
 
 
-class BNState:
-    """Per-call BatchNorm coefficients (all fp32 [C])."""
-
-    __slots__ = ("mean", "invstd", "scale", "shift")
-
-    def __init__(self, C, device):
-        buf = torch.empty((4, C), device=device, dtype=torch.float32)
-        self.mean, self.invstd, self.scale, self.shift = buf[0], buf[1], buf[2], buf[3]
-
-
-def bn_finalize(stats, count, gamma, beta, running_mean, running_var, eps, momentum):
-    groups, _, C = stats.shape
-    st = BNState(C, stats.device)
-    call("lasr_bn_finalize", stats, groups, C, count, eps, momentum, gamma, beta, st.mean, st.invstd, st.scale,
-         st.shift, running_mean, running_var)
-    return st
+def colsum(x, C, out=None):
+    """out[c] += sum over rows of x[..., c], c < C."""
+    ld = x.shape[-1]
+    M = x.numel() // ld
+    o = out if out is not None else torch.zeros((C,), device=x.device, dtype=torch.float32)
+    call("lasr_colsum", x, o, M, C, ld, dtype_code(x.dtype))
+    return o
 
 
-def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps):
-    C = gamma.numel()
-    st = BNState(C, gamma.device)
-    call("lasr_bn_eval_coeffs", gamma, beta, running_mean, running_var, eps, st.scale, st.shift, C)
-    return st
+class _BN(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("sums", "gamma", "beta", "running_mean", "running_var",
+                                               "num_batches_tracked", "save_mean", "save_invstd")]
+
+
+class _BNBwd(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("gamma", "mean", "invstd", "dgamma", "dbeta")]
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class BNForward:
+    """lasr_bn_t for one BatchNorm call.  training: `sums` = double [2, C] batch statistics (from the GEMM epilogue),
+    save [2, C] receives mean / invstd.  eval: sums None, running statistics are read."""
+
+    def __init__(self, gamma, beta, running_mean, running_var, nbt, sums=None):
+        self.gamma, self.beta = gamma, beta
+        self.running_mean, self.running_var, self.nbt = running_mean, running_var, nbt
+        self.sums = sums
+        self.training = sums is not None
+        self.save = torch.empty((2, gamma.numel()), device=gamma.device, dtype=torch.float32) if self.training else None
+        self.c = _BN(_p(sums), _p(gamma), _p(beta), _p(running_mean), _p(running_var),
+                     _p(nbt) if self.training else None, _p(self.save[0]) if self.training else None,
+                     _p(self.save[1]) if self.training else None)
+
+    @property
+    def ptr(self):
+        return ctypes.addressof(self.c)
+
+
+def bn_coeffs(bn, count, eps, momentum, side_effects):
+    C = bn.gamma.numel()
+    coef = torch.empty((2, C), device=bn.gamma.device, dtype=torch.float32)
+    call("lasr_bn_coeffs", bn.ptr, C, count, eps, momentum, coef[0], coef[1], 1 if side_effects else 0)
+    return coef[0], coef[1]
 
 
 def sum_over_time(y):
@@ -141,11 +169,12 @@ def sum_over_time(y):
     return sums
 
 
-def bn_apply_act(y, st1, r=None, st2=None, gate=None, act=ACT_RELU):
+def bn_apply_act(y, bn1, r=None, bn2=None, gate=None, act=ACT_RELU, eps=1e-3, momentum=0.1, side_effects=True):
+    """out = act(BN1(y) [* gate] [+ BN2(r)]) in one pass; performs the training side effects of both BNs."""
     N, T, C = y.shape
     out = torch.empty_like(y)
-    call("lasr_bn_apply_act_fwd", y, st1.scale, st1.shift, r, st2.scale if st2 else None,
-         st2.shift if st2 else None, gate, out, N * T, C, T, act, dtype_code(y.dtype))
+    call("lasr_bn_apply_act_fwd", y, bn1.ptr, r, bn2.ptr if bn2 is not None else None, gate, out, N * T, C, T, N * T,
+         eps, momentum, act, 1 if (side_effects and bn1.training) else 0, dtype_code(y.dtype))
     return out
 
 
@@ -153,57 +182,55 @@ def bn_bwd_chunks(N, T):
     return _lib.load().lasr_bn_bwd_chunks(N, T)
 
 
-def bn_act_bwd_reduce(dout, out, y, r, act):
+def bn_act_bwd_reduce(dout, out, y, r, act, totals, per_n=None):
     N, T, C = y.shape
-    chunks = bn_bwd_chunks(N, T)
-    partials = torch.empty((N * chunks, 3, C), device=y.device, dtype=torch.float32)
-    call("lasr_bn_act_bwd_reduce", dout, out, y, r, partials, N, T, C, chunks, act, dtype_code(y.dtype))
-    return partials, chunks
+    call("lasr_bn_act_bwd_reduce", dout, out, y, r, totals, per_n, N, T, C, act, dtype_code(y.dtype))
+    return totals
 
 
-def bn_bwd_finalize(partials, count, idx_g, idx_gx, gamma, st, dgamma, dbeta):
-    groups, nslots, C = partials.shape
-    coef = torch.empty((3, C), device=partials.device, dtype=torch.float32)
-    call("lasr_bn_bwd_finalize", partials, groups, nslots, C, count, idx_g, idx_gx, gamma, st.mean, st.invstd, dgamma,
-         dbeta, coef)
+def bn_bwd_coef(totals, count, slot_gx, gamma, save, dgamma, dbeta):
+    C = gamma.numel()
+    coef = torch.empty((3, C), device=gamma.device, dtype=torch.float32)
+    call("lasr_bn_bwd_coef", totals, C, count, slot_gx, gamma, save[0], save[1], dgamma, dbeta, coef)
     return coef
 
 
-def bn_act_bwd_apply(dout, out, y, r, gate, extra, coef1, coef2, lengths, act):
+def bn_act_bwd_apply(dout, out, y, r, gate, extra, totals, coef1, bn1, bn2, lengths, act):
+    """bn1 / bn2: (gamma, save [2,C], dgamma, dbeta) tuples or None."""
     N, T, C = y.shape
     dy = torch.empty_like(y)
     dr = torch.empty_like(y) if r is not None else None
-    call("lasr_bn_act_bwd_apply", dout, out, y, r, gate, extra, coef1, coef2, lengths, T, dy, dr, N * T, C, act,
-         dtype_code(y.dtype))
+    s1 = _BNBwd(_p(bn1[0]), _p(bn1[1][0]), _p(bn1[1][1]), _p(bn1[2]), _p(bn1[3])) if bn1 is not None else None
+    s2 = _BNBwd(_p(bn2[0]), _p(bn2[1][0]), _p(bn2[1][1]), _p(bn2[2]), _p(bn2[3])) if bn2 is not None else None
+    call("lasr_bn_act_bwd_apply", dout, out, y, r, gate, extra, totals, coef1,
+         ctypes.addressof(s1) if s1 is not None else None, ctypes.addressof(s2) if s2 is not None else None, N * T,
+         lengths, T, dy, dr, N * T, C, act, dtype_code(y.dtype))
     return dy, dr
 
 
-def se_excite_fwd(sums, st, T, w1, w2):
+def se_excite_fwd(sums, scale, shift, T, w1, w2):
     N, C = sums.shape
     Cr = w1.shape[0]
     s = torch.empty((N, C), device=sums.device, dtype=torch.float32)
     hidden = torch.empty((N, Cr), device=sums.device, dtype=torch.float32)
     gate = torch.empty((N, C), device=sums.device, dtype=torch.float32)
-    call("lasr_se_excite_fwd", sums, st.scale, st.shift, T, w1, w2, s, hidden, gate, N, C, Cr)
+    call("lasr_se_excite_fwd", sums, scale, shift, T, w1, w2, s, hidden, gate, N, C, Cr)
     return s, hidden, gate
 
 
-def se_excite_bwd(partials, chunks, st, T, w1, w2, s, hidden, gate):
+def se_excite_bwd(per_n, scale, shift, T, w1, w2, s, hidden, gate, dw1, dw2):
     N, C = gate.shape
     Cr = w1.shape[0]
     extra = torch.empty((N, C), device=gate.device, dtype=torch.float32)
-    dw1 = torch.zeros_like(w1)
-    dw2 = torch.zeros_like(w2)
-    call("lasr_se_excite_bwd", partials, chunks, st.scale, st.shift, T, w1, w2, s, hidden, gate, extra, dw1, dw2, N, C,
-         Cr)
-    return extra, dw1, dw2
+    call("lasr_se_excite_bwd", per_n, 1, scale, shift, T, w1, w2, s, hidden, gate, extra, dw1, dw2, N, C, Cr)
+    return extra
 
 
-def se_bn_bwd_finalize(partials, N, chunks, T, gate, extra, sums_y, gamma, st, dgamma, dbeta):
+def se_bn_bwd_finalize(per_n, N, T, gate, extra, sums_y, gamma, save, dgamma, dbeta):
     C = gate.shape[1]
     coef = torch.empty((3, C), device=gate.device, dtype=torch.float32)
-    call("lasr_se_bn_bwd_finalize", partials, N, chunks, C, T, gate, extra, sums_y, gamma, st.mean, st.invstd, dgamma,
-         dbeta, coef)
+    call("lasr_se_bn_bwd_finalize", per_n, N, 1, C, T, gate, extra, sums_y, gamma, save[0], save[1], dgamma, dbeta,
+         coef)
     return coef
 
 

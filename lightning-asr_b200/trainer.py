@@ -12,7 +12,7 @@ pytorch_lightning / hydra / comet are the reference's control plane and are out 
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, runtime
 from .ctc import CTCLoss
 from .metrics import WER
 from .quartznet import build_model
@@ -123,16 +123,24 @@ class LightingModule(nn.Module):
 
 class TrainEngine:
     """One process per GPU.  step_host(batch) is the end-to-end call (pinned host batch -> H2D -> step -> loss on the
-    host); step_device() re-runs the step on the batch already resident in HBM.  With graph=True the whole
-    forward + backward (+ optimizer) is captured once into a CUDA graph and replayed: ~600 kernel launches per step
-    would otherwise cost more host time than the kernels take."""
+    host); step_device() re-runs the step on the batch already resident in HBM.
 
-    def __init__(self, module, example_batch, graph=True, optimizer=None, grad_sync=None, fused=True):
+    The engine owns a runtime.ParamBank (flat fp32 masters / bf16 shadows / fp32 gradients + zeroed arena: one memset
+    and one cast launch per step) and, with graph=True, captures the whole step -- memset, cast, forward, CTC,
+    backward, gradient all-reduce, optimizer -- into ONE CUDA graph that is replayed every step."""
+
+    def __init__(self, module, example_batch, graph=True, optimizer=None, grad_sync=None, fused=True, world_sync=None):
         _lib.require_device()
         self.module = module
         self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.bank = runtime.ParamBank(module)
+        runtime.install(self.bank)
         self.optimizer = optimizer
-        self.grad_sync = grad_sync  # callable(module) launching the gradient all-reduce (ddp.GradSync)
+        self.grad_sync = grad_sync
+        if world_sync is not None:  # (group, bucket_mb): build the gradient exchange over the bank's flat buffer
+            from . import ddp
+            self.grad_sync = ddp.GradSync(module, group=world_sync[0], bucket_mb=world_sync[1], overlap=True,
+                                          bank=self.bank)
         self.fused = fused
         self.host = [t.pin_memory() if torch.is_tensor(t) else t for t in example_batch[:4]]
         self.static = [t.to(self.dev, non_blocking=True) if torch.is_tensor(t) else t for t in self.host]
@@ -141,17 +149,12 @@ class TrainEngine:
         self.loss_dev = torch.zeros((), device=self.dev, dtype=torch.float32)
         self.graph = None
         self.use_graph = graph
-        self.launches_per_step = None
 
-    def _zero_grads(self):
-        if self.grad_sync is not None:
-            self.grad_sync.zero_and_attach()  # gradients are views of the flat all-reduce buckets
-        else:
-            for p in self.module.parameters():
-                p.grad = None
-
-    def _step_body(self):
+    def _step_eager(self):
         m = self.module
+        self.bank.begin_step()
+        if self.grad_sync is not None:
+            self.grad_sync.zero_and_attach()
         if self.fused:
             loss, _, _ = m.training_step_fused(self.static)
         else:
@@ -159,13 +162,10 @@ class TrainEngine:
         loss.backward()
         if self.grad_sync is not None:
             self.grad_sync(m)
+        self.bank.end_step()
         if self.optimizer is not None:
             self.optimizer.step()
         self.loss_dev.copy_(loss.detach())
-
-    def _step_eager(self):
-        self._zero_grads()
-        self._step_body()
 
     def _capture(self):
         s = torch.cuda.Stream()
@@ -176,13 +176,8 @@ class TrainEngine:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        if self.grad_sync is None:
-            for p in self.module.parameters():
-                p.grad = None  # re-created inside the graph's private pool, then refilled by every replay
         with torch.cuda.graph(graph):
-            if self.grad_sync is not None:
-                self.grad_sync.zero_and_attach()
-            self._step_body()
+            self._step_eager()
         torch.cuda.synchronize()
         self.graph = graph
 

@@ -30,8 +30,7 @@ def test_dwconv_fwd_wgrad_dgrad(ops, dtype, tol, C, K, stride, T):
     N = 3
     x = torch.randn(N, C, T, device="cuda").to(dtype)
     w = torch.randn(C, 1, K, device="cuda") / K ** 0.5
-    wt = ops.cast_weight(w.view(C, K), torch.float32, transpose=True)
-    y = ops.dwconv_fwd(ntc(x), wt, stride=stride)
+    y = ops.dwconv_fwd(ntc(x), w, stride=stride)
     xr = x.double().requires_grad_(True)
     wr = w.double().requires_grad_(True)
     yr = F.conv1d(xr, wr, stride=stride, padding=K // 2, groups=C)
@@ -39,36 +38,46 @@ def test_dwconv_fwd_wgrad_dgrad(ops, dtype, tol, C, K, stride, T):
     assert rel_err(y.float(), ntc(yr)) < tol
     dy = torch.randn_like(yr).to(dtype)
     yr.backward(dy.double())
-    dwt = ops.dwconv_wgrad(ntc(x), ntc(dy), K, stride=stride)
-    assert rel_err(dwt.t(), wr.grad.view(C, K)) < tol
+    dw = ops.dwconv_wgrad(ntc(x), ntc(dy), K, stride=stride)
+    assert dw.shape == (C, 1, K)
+    assert rel_err(dw, wr.grad) < tol
     if stride == 1:
         addend = torch.randn(N, T, C, device="cuda").to(dtype)
-        dx = ops.dwconv_fwd(ntc(dy), wt, stride=1, flip=True, addend=addend)
+        dx = ops.dwconv_fwd(ntc(dy), w, stride=1, flip=True, addend=addend)
         assert rel_err(dx.float(), ntc(xr.grad) + addend.double()) < tol
 
 
 @pytest.mark.parametrize("dtype,tol", DTYPES)
 @pytest.mark.parametrize("M,Cin,Cout,T", [(1002, 64, 256, 501), (900, 256, 256, 300), (1000, 336, 512, 250),
-                                           (777, 512, 1024, 777), (640, 1024, 32, 320), (300, 1024, 4336, 100)])
-def test_pwconv_fwd_mask_stats_wgrad(ops, dtype, tol, M, Cin, Cout, T):
+                                           (777, 512, 1024, 777), (640, 1024, 29, 320), (300, 1024, 4334, 100)])
+def test_pwconv_fwd_mask_stats_dgrad_wgrad(ops, dtype, tol, M, Cin, Cout, T):
     torch.manual_seed(M)
     x = torch.randn(M, Cin, device="cuda").to(dtype)
     w = (torch.randn(Cout, Cin, device="cuda") / Cin ** 0.5).to(dtype)
     nb = M // T
     lengths = torch.randint(T // 2, T + 1, (nb,), device="cuda", dtype=torch.int32)
-    y, stats = ops.pwconv_fwd(x, w, lengths=lengths, T=T, want_stats=True)
+    ld = (Cout + 7) // 8 * 8  # odd widths (decoder: V' = 29 / 4334) use a padded row pitch
+    stats = torch.zeros(2, Cout, device="cuda", dtype=torch.float64)
+    y = ops.pwconv_fwd(x, w, lengths=lengths, T=T, stats=stats, ldy=ld)
+    assert y.shape == (M, ld)
     ref = x.double() @ w.double().t()
     t = torch.arange(M, device="cuda")
     ref = ref * ((t % T) < lengths[(t // T).clamp_max(nb - 1)]).unsqueeze(1)
-    assert rel_err(y.float(), ref) < tol
-    assert rel_err(stats[:, 0].sum(0), ref.sum(0)) < 10 * tol or ref.sum(0).norm() < 1e-3
-    assert rel_err(stats[:, 1].sum(0), (ref * ref).sum(0)) < tol
+    assert rel_err(y[:, :Cout].float(), ref) < tol
+    assert rel_err(stats[0], ref.sum(0)) < 10 * tol or ref.sum(0).norm() < 1e-3
+    assert rel_err(stats[1], (ref * ref).sum(0)) < tol
     bias = torch.randn(Cout, device="cuda")
-    y2, _ = ops.pwconv_fwd(x, w, bias=bias)
-    assert rel_err(y2.float(), x.double() @ w.double().t() + bias.double()) < tol
-    dy = torch.randn(M, Cout, device="cuda").to(dtype)
-    dw = ops.pwconv_wgrad(dy, x)
-    assert rel_err(dw, dy.double().t() @ x.double()) < tol
+    y2 = ops.pwconv_fwd(x, w, bias=bias, ldy=ld)
+    assert rel_err(y2[:, :Cout].float(), x.double() @ w.double().t() + bias.double()) < tol
+    dy = torch.zeros(M, ld, device="cuda", dtype=dtype)
+    dy[:, :Cout] = torch.randn(M, Cout, device="cuda").to(dtype)
+    dw = ops.pwconv_wgrad(dy, x, Cout=Cout)
+    assert dw.shape == (Cout, Cin)
+    assert rel_err(dw, dy[:, :Cout].double().t() @ x.double()) < tol
+    dx = ops.pwconv_dgrad(dy, w, lddy=ld)
+    assert rel_err(dx.float(), dy[:, :Cout].double() @ w.double()) < tol
+    db = ops.colsum(dy, Cout)
+    assert rel_err(db, dy[:, :Cout].double().sum(0)) < tol
 
 
 @pytest.mark.parametrize("dtype,tol", DTYPES)
@@ -82,19 +91,18 @@ def test_bn_fwd_bwd(ops, dtype, tol, C, with_res):
     lengths = torch.tensor([T, T - 20, T // 2, 1], device="cuda", dtype=torch.int32)
     g1, b1 = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
     g2, b2 = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
-    from lightning_asr_b200 import _lib
-    groups = ((N * T + 127) // 128) * 4
 
-    def stats_of(t):
-        st = torch.empty(groups, 2, C, device="cuda")
-        _lib.call("lasr_pwconv_fwd", t, torch.eye(C, device="cuda").to(dtype), torch.empty_like(t), None, None, 0, st,
-                  N * T, C, C, C, C, C, _lib.dtype_code(dtype))
+    def stats_of(t):  # the statistics epilogue of the pointwise GEMM, through an identity weight
+        st = torch.zeros(2, C, device="cuda", dtype=torch.float64)
+        ops.pwconv_fwd(t, torch.eye(C, device="cuda").to(dtype), stats=st)
         return st
 
     rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
-    st1 = ops.bn_finalize(stats_of(y), N * T, g1, b1, rm, rv, 1e-3, 0.1)
-    st2 = ops.bn_finalize(stats_of(r), N * T, g2, b2, None, None, 1e-3, 0.1) if with_res else None
-    out = ops.bn_apply_act(y, st1, r, st2, None, ops.ACT_RELU)
+    nbt = torch.zeros((), device="cuda", dtype=torch.long)
+    bn1 = ops.BNForward(g1, b1, rm, rv, nbt, stats_of(y))
+    bn2 = ops.BNForward(g2, b2, None, None, None, stats_of(r)) if with_res else None
+    out = ops.bn_apply_act(y, bn1, r, bn2, None, ops.ACT_RELU)
+    assert int(nbt) == 1
 
     yd = y.double().requires_grad_(True)
     rd = r.double().requires_grad_(True) if with_res else None
@@ -107,26 +115,33 @@ def test_bn_fwd_bwd(ops, dtype, tol, C, with_res):
     ref = torch.relu(z)
     assert rel_err(out.float(), ref) < tol
     assert rel_err(rm, rmd) < 1e-4 and rel_err(rv, rvd) < 1e-4
+    # eval mode reads the running statistics
+    bn_eval = ops.BNForward(g1, b1, rm, rv, nbt)
+    out_eval = ops.bn_apply_act(y, bn_eval, None, None, None, ops.ACT_NONE)
+    ref_eval = F.batch_norm(y.double().reshape(-1, C), rmd, rvd, g1.double(), b1.double(), False, 0.1, 1e-3)
+    assert rel_err(out_eval.float().reshape(-1, C), ref_eval) < tol and int(nbt) == 1
 
     dout = torch.randn(N, T, C, device="cuda").to(dtype)
     # the reference masks the conv output BEFORE BN, so d(conv out) is zeroed at masked frames
     keep = (torch.arange(T, device="cuda")[None, :] < lengths[:, None]).unsqueeze(-1)
-    # autograd reference uses the forward values actually produced (out) for the ReLU mask to avoid ties
     ref.backward(dout.double())
-    partials, chunks = ops.bn_act_bwd_reduce(dout, out, y, r, ops.ACT_RELU)
+    totals = torch.zeros(3, C, device="cuda", dtype=torch.float64)
+    ops.bn_act_bwd_reduce(dout, out, y, r, ops.ACT_RELU, totals)
     dg1, db1 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-    coef1 = ops.bn_bwd_finalize(partials, N * T, 0, 1, g1, st1, dg1, db1)
-    coef2 = None
-    if with_res:
-        dg2, db2 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-        coef2 = ops.bn_bwd_finalize(partials, N * T, 0, 2, g2, st2, dg2, db2)
-    dy, dr = ops.bn_act_bwd_apply(dout, out, y, r, None, None, coef1, coef2, lengths, ops.ACT_RELU)
+    dg2, db2 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dy, dr = ops.bn_act_bwd_apply(dout, out, y, r, None, None, totals, None, (g1, bn1.save, dg1, db1),
+                                  (g2, bn2.save, dg2, db2) if with_res else None, lengths, ops.ACT_RELU)
     gtol = tol * 3
     assert rel_err(dy.float(), yd.grad * keep) < gtol
     assert rel_err(dg1, g1d.grad) < gtol and rel_err(db1, b1d.grad) < gtol
     if with_res:
         assert rel_err(dr.float(), rd.grad) < gtol
         assert rel_err(dg2, g2d.grad) < gtol and rel_err(db2, b2d.grad) < gtol
+    # standalone coefficient kernel agrees with the fused prologue
+    coef = ops.bn_bwd_coef(totals, N * T, 1, g1, bn1.save, None, None)
+    g = dout.float() * (out.float() > 0)
+    dy2 = (coef[0] * g + coef[1] * y.float() + coef[2]) * keep
+    assert rel_err(dy2, yd.grad * keep) < gtol
 
 
 @pytest.mark.parametrize("V,dtype", [(29, torch.float32), (29, torch.bfloat16), (4334, torch.float32),

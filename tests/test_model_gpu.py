@@ -120,14 +120,16 @@ def test_model_fp32_train_parity(lasr, labels28, variant):
     # SURVEY.md 10.1 protocol: train-mode BatchNorm amplifies fp32 rounding ~20x on the way down, so the fp32
     # oracle itself is only 3-5e-3 accurate on early-layer gradients.  Every per-block op of ours is as accurate as
     # torch's (tools/diag_block.py: 3-5e-7 vs fp64, same as torch fp32), so the whole-network numbers are two
-    # independent samples of the same noise: require each tensor within 3x of the oracle's own deviation and the
-    # median ratio within 2x.
+    # independent samples of the same noise (tools/diag_head.py: fed the SAME activations our head is 1.1e-5..3.6e-5
+    # from fp64 where torch fp32 is 1.4e-5..4.7e-5; a single ReLU gate that flips on a 1e-7 forward difference moves a
+    # layer's gradient by ~1/sqrt(#elements) ~ 1e-3): require each tensor within max(3x the oracle's own deviation,
+    # 5e-3) and the median ratio within 2x.
     ratios = []
     for name, prm in model.named_parameters():
         ours = rel_err(prm.grad, sd64[name].grad)
         theirs = rel_err(sd32[name].grad, sd64[name].grad)
         ratios.append(ours / max(theirs, 1e-4))
-        assert ours < max(3 * theirs, 2e-3), (name, ours, theirs)
+        assert ours < max(3 * theirs, 5e-3), (name, ours, theirs)
     ratios.sort()
     assert ratios[len(ratios) // 2] < 2.0, ratios
     # running statistics after one training step
@@ -182,3 +184,34 @@ def test_fused_ctc_equals_modular(lasr, labels28):
     assert torch.equal(tl.cpu(), t_len)
     for n, q in model.named_parameters():
         assert rel_err(q.grad, g_mod[n]) < 2e-4, n
+
+
+@pytest.mark.parametrize("precision,graph", [("fp32", False), ("fp32", True), ("bf16", True)])
+def test_train_engine_matches_plain_autograd(lasr, labels28, precision, graph):
+    """The step engine (flat parameter bank, arena accumulators, gradients accumulated in place, CUDA graph) must
+    produce the same loss / gradients / running statistics as the plain autograd path on the same kernels."""
+    from lightning_asr_b200 import runtime
+    from lightning_asr_b200.trainer import LightingModule, TrainEngine, synthetic_batch
+    batch = synthetic_batch(3, 2.0, 28, seed=3, ragged=True)
+    dev_batch = tuple(t.cuda() if torch.is_tensor(t) else t for t in batch)
+    torch.manual_seed(4)
+    ref = LightingModule(labels=labels28, mask=True, precision=precision).cuda().train()
+    sd0 = copy.deepcopy(ref.state_dict())
+    loss_ref, _, _ = ref.training_step_fused(dev_batch)
+    loss_ref.backward()
+    mod = LightingModule(labels=labels28, mask=True, precision=precision).cuda().train()
+    mod.load_state_dict(sd0)
+    try:
+        eng = TrainEngine(mod, batch, graph=graph)
+        for _ in range(2):  # the second step exercises re-zeroing / replay
+            mod.load_state_dict(sd0)  # restore the BatchNorm buffers (in place: the bank's views stay valid)
+            loss = eng.step_host()
+    finally:
+        runtime.uninstall()
+    tol = 1e-5 if precision == "fp32" else 2e-2
+    assert abs(loss - float(loss_ref)) <= tol * abs(float(loss_ref))
+    for (n1, p1), (n2, p2) in zip(ref.named_parameters(), mod.named_parameters()):
+        assert rel_err(p2.grad, p1.grad) < (1e-4 if precision == "fp32" else 5e-2), n1
+    for (k1, v1), (k2, v2) in zip(ref.state_dict().items(), mod.state_dict().items()):
+        if "running" in k1:
+            assert rel_err(v2.float(), v1.float()) < 1e-4, k1
