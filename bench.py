@@ -78,9 +78,7 @@ def algorithmic(name, a, has):
     if name == "lasr_bn_act_bwd_apply":  # count, T, M, C, act, dtype; ptrs dout,out,y,r,...
         _, T, M, C, act, dt = a
         return "bn_pass", es(dt) * M * C * ((4 if act else 3) + (2 if has[3] else 0)), 6.0 * M * C
-    if name in ("lasr_ctc_fwd", "lasr_ctc_bwd", "lasr_log_softmax_fwd", "lasr_log_softmax_bwd", "lasr_greedy_decode"):
-        return "ctc", 0, 0.0
-    return "other", 0, 0.0
+    return name.replace("lasr_", ""), 0, 0.0
 
 
 def kernel_breakdown(engine, steps=3):

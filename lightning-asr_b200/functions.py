@@ -72,9 +72,11 @@ class SepConvBNFn(torch.autograd.Function):
             s, hidden, gate = ops.se_excite_fwd(sums_y, scale1, shift1, T, se_w1.detach(), se_w2.detach())
         out = ops.bn_apply_act(y, bn1, r, bn2, gate, act, BN_EPS, BN_MOMENTUM, side_effects=se_side)
 
-        ctx.saved = (x, res_x, lengths, d, y, r, out, bn1.save, bn2.save if bn2 is not None else None, gate, s, hidden,
-                     sums_y, scale1, shift1, pw_s, res_s)
-        ctx.params = (dw_w, pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2)
+        # save_for_backward (not attributes): holding `out` on ctx directly would create an uncollectable
+        # node <-> tensor cycle and leak every step's activations
+        ctx.save_for_backward(x, res_x, lengths, d, y, r, out, bn1.save, bn2.save if bn2 is not None else None, gate, s,
+                              hidden, sums_y, scale1, shift1, pw_s, res_s, dw_w, pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b,
+                              se_w1, se_w2)
         ctx.cfg = (stride, act, training, K, Cin, Cout)
         ctx.set_materialize_grads(False)
         return out
@@ -83,9 +85,8 @@ class SepConvBNFn(torch.autograd.Function):
     def backward(ctx, dout):
         if dout is None:
             return (None,) * 17
-        (x, res_x, lengths, d, y, r, out, save1, save2, gate, s, hidden, sums_y, scale1, shift1, pw_s,
-         res_s) = ctx.saved
-        dw_w, pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2 = ctx.params
+        (x, res_x, lengths, d, y, r, out, save1, save2, gate, s, hidden, sums_y, scale1, shift1, pw_s, res_s, dw_w,
+         pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2) = ctx.saved_tensors
         stride, act, training, K, Cin, Cout = ctx.cfg
         if not training:
             raise RuntimeError("lightning_asr_b200: backward through eval-mode BatchNorm is not implemented")
@@ -162,16 +163,14 @@ class Conv1x1BNReLUFn(torch.autograd.Function):
         bn = ops.BNForward(bn_w.detach(), bn_b.detach(), bn_buffers[0], bn_buffers[1], bn_buffers[2], sums)
         act = ACT_RELU if relu else ACT_NONE
         out = ops.bn_apply_act(y, bn, act=act, eps=BN_EPS, momentum=BN_MOMENTUM)
-        ctx.saved = (x, y, out, bn.save, w_s)
-        ctx.params = (w, bn_w, bn_b)
+        ctx.save_for_backward(x, y, out, bn.save, w_s, w, bn_w, bn_b)
         ctx.training = training
         ctx.act = act
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, y, out, save, w_s = ctx.saved
-        w, bn_w, bn_b = ctx.params
+        x, y, out, save, w_s, w, bn_w, bn_b = ctx.saved_tensors
         if not ctx.training:
             raise RuntimeError("lightning_asr_b200: backward through eval-mode BatchNorm is not implemented")
         dout = dout.contiguous()
@@ -226,14 +225,14 @@ class DecoderLogSoftmaxFn(torch.autograd.Function):
         V = w.shape[0]
         logits, w_s = _decoder_logits(x, w, b)
         _, lp = ops.log_softmax_fwd(logits, V, want_lp=True)
-        ctx.saved = (x, lp, logits.shape[-1], w_s)
-        ctx.params = (w, b)
+        ctx.save_for_backward(x, lp, w_s, w, b)
+        ctx.ld = logits.shape[-1]
         return lp
 
     @staticmethod
     def backward(ctx, dlp):
-        x, lp, ld, w_s = ctx.saved
-        w, b = ctx.params
+        x, lp, w_s, w, b = ctx.saved_tensors
+        ld = ctx.ld
         dlogits = ops.log_softmax_bwd(dlp.contiguous().float(), lp, ld, x.dtype)
         return _decoder_backward(x, w, b, w_s, dlogits, ctx.needs_input_grad[0])
 
@@ -258,14 +257,14 @@ class CTCLossFn(torch.autograd.Function):
         V = x.shape[-1]
         need_grad = log_probs.requires_grad
         nll, alpha, beta = ops.ctc_fwd(x, None, targets, input_lengths, target_lengths, V, blank, want_beta=need_grad)
-        ctx.saved = (x, targets, input_lengths, target_lengths, alpha, beta, nll)
+        ctx.save_for_backward(x, targets, input_lengths, target_lengths, alpha, beta, nll)
         ctx.blank = blank
         ctx.in_dtype = log_probs.dtype
         return nll
 
     @staticmethod
     def backward(ctx, gout):
-        x, targets, il, tl, alpha, beta, nll = ctx.saved
+        x, targets, il, tl, alpha, beta, nll = ctx.saved_tensors
         V = x.shape[-1]
         grad = ops.ctc_bwd(x, None, targets, il, tl, alpha, beta, nll, gout.contiguous().float(), V, ctx.blank, V,
                            torch.float32)
@@ -282,16 +281,14 @@ class FusedDecoderCTCFn(torch.autograd.Function):
         logits, w_s = _decoder_logits(x, w, b)
         lse, _ = ops.log_softmax_fwd(logits, V, want_lp=False)
         nll, alpha, beta = ops.ctc_fwd(logits, lse, targets, input_lengths, target_lengths, V, blank, want_beta=True)
-        ctx.saved = (x, logits, lse, targets, input_lengths, target_lengths, alpha, beta, nll, w_s)
-        ctx.params = (w, b)
+        ctx.save_for_backward(x, logits, lse, targets, input_lengths, target_lengths, alpha, beta, nll, w_s, w, b)
         ctx.blank = blank
         ctx.mark_non_differentiable(logits)
         return nll, logits
 
     @staticmethod
     def backward(ctx, gout, _glogits):
-        x, logits, lse, targets, il, tl, alpha, beta, nll, w_s = ctx.saved
-        w, b = ctx.params
+        x, logits, lse, targets, il, tl, alpha, beta, nll, w_s, w, b = ctx.saved_tensors
         V = w.shape[0]
         ld = logits.shape[-1]
         dlogits = ops.ctc_bwd(logits, lse, targets, il, tl, alpha, beta, nll, gout.contiguous().float(), V, ctx.blank,
