@@ -186,6 +186,31 @@ int lasr_se_bn_bwd_finalize(const float* partials, int N, int chunks, int C, int
                             const float* invstd, float* dgamma, float* dbeta, float* coef, lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Log-mel frontend (replaces AudioParser.parse_audio from the waveform tensor onward, data_module.py:155-172, with the
+ * transforms built at :66-71: MelSpectrogram(sr=16000, n_fft=512, pad=32, win_length=320, hop_length=160, n_mels=64)
+ * and AmplitudeToDB(stype="power")).  Batched: wave [N, S_max] fp32 zero padded, num_samples [N] int32;
+ * T_n = 1 + (num_samples[n] + 64) / 160 frames per utterance, T_max = frames of the longest.
+ *   prepare   : optional dither (y += 1e-5 * dither, :155), pre-emphasis (:157), zero pad 32, reflect pad 256 ->
+ *               the sample stream the 320 non-zero window taps of each frame read, split into 3 bf16 terms
+ *               parts [3, N, lasr_logmel_padded_len(T_max)] bf16
+ *   fwd       : error-compensated (products = 6, or 3) bf16 tcgen05 windowed-DFT GEMM -> power -> mel -> dB.
+ *               basis [3, 512, 320] bf16: the three bf16 terms of win[i]*cos / win[i]*sin(2 pi f i / 512); row 2f = re,
+ *               2f+1 = im of bin f, except row 1 = the (real) Nyquist bin 256.  mel_idx / mel_w [257, 2]: the (at most
+ *               two) triangular filters each bin feeds.  db [N, T_max, 64] fp32; stats [N, 2] double (sum, sum of
+ *               squares over the utterance's own 64 * T_n values), ACCUMULATED (caller zeroes).
+ *   normalize : (db - mean) / unbiased std (:171-172), zero for frames t >= T_n (the collate padding, :230,243);
+ *               out_nct [N, 1, 64, T_max] fp32 (the reference layout) and / or out_ntc [N, T_max, 64] dtype, nullable.
+ * ---------------------------------------------------------------------------------------------- */
+int lasr_logmel_padded_len(int T_max);
+int lasr_logmel_prepare(const float* wave, const float* dither, const int32_t* num_samples, void* parts, int N,
+                        int S_max, int T_max, lasr_stream_t stream);
+int lasr_logmel_fwd(const void* parts, const void* basis, const int32_t* mel_idx, const float* mel_w,
+                    const int32_t* num_samples, float* db, double* stats, int N, int T_max, int products,
+                    lasr_stream_t stream);
+int lasr_logmel_normalize(const float* db, const double* stats, const int32_t* num_samples, float* out_nct,
+                          void* out_ntc, int N, int T_max, int dtype, lasr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * log_softmax over classes (replaces nn.functional.log_softmax, models/QuartNet.py:290).
  * logits [M, ld] dtype (V valid columns) -> lse [M] fp32 and, if lp != NULL, log-probs lp [M, V] fp32 dense.
  * ---------------------------------------------------------------------------------------------- */

@@ -206,4 +206,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t pitch_bytes,
                       uint32_t box0, uint32_t box1, bool swizzle128);
 
+int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, bool swizzle128);
+
 }  // namespace lasr

@@ -382,6 +382,30 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
   return r == CUDA_SUCCESS ? LASR_OK : LASR_ERR_DRIVER;
 }
 
+// rank-N bf16 tensor map, dim0 contiguous; strides_bytes has rank-1 entries (dims 1..rank-1); 128B swizzle optional
+int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, bool swizzle128) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (fn == nullptr) return LASR_ERR_DRIVER;
+  if (rank < 1 || rank > 5) return LASR_ERR_BAD_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return LASR_ERR_ALIGNMENT;
+  cuuint64_t d[5], st[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) {
+      if (strides_bytes[i - 1] & 15) return LASR_ERR_ALIGNMENT;
+      st[i - 1] = strides_bytes[i - 1];
+    }
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), d, st, bx, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? LASR_OK : LASR_ERR_DRIVER;
+}
+
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p, int grid,
                        cudaStream_t stream) {

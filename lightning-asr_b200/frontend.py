@@ -1,0 +1,185 @@
+"""Log-mel frontend + collate: the host-side mirror of data_module.py's AudioParser / _collate_fn.
+
+  AudioParser(win_len=0.02, sr=16000).parse_audio(audio, mask=False) -> [1, 64, T]      data_module.py:58-174
+  logmel_batch(waves [N, S_max], num_samples [N])  -> (inputs [N,1,64,T_max], percents [N])   the batched GPU entry point
+  collate(batch)                                                                        data_module.py:222-248
+
+All arithmetic runs in csrc/logmel.cu (tcgen05 windowed-DFT GEMM, error-compensated); this file only builds the
+constant tables (window x DFT basis split in three bf16 terms, sparse HTK mel filterbank) once per device.
+The reference runs this per utterance on CPU DataLoader workers; here it is batched on the GPU and can emit the
+encoder's channels-last input directly (out_ntc).  Random train-time augmentation (crop :158-159, SpecAugment
+:163-165) uses an unseeded host RNG in the reference and is not part of the parity contract.
+"""
+import math
+
+import torch
+
+from . import _lib
+
+SR = 16000
+N_FFT = 512
+WIN = 320
+HOP = 160
+PAD = 32
+N_MELS = 64
+N_BINS = N_FFT // 2 + 1
+
+_CONST = {}
+
+
+def num_frames(num_samples):
+    """T = 1 + (S + 2*pad) // hop  (MelSpectrogram(pad=32, hop_length=160, center=True), data_module.py:68-70)."""
+    return 1 + (num_samples + 2 * PAD) // HOP
+
+
+def _hz_to_mel(f):
+    return 2595.0 * math.log10(1.0 + f / 700.0)
+
+
+def mel_filterbank(sr=SR):
+    """torchaudio.functional.melscale_fbanks(257, 0, sr/2, 64, sr, norm=None, mel_scale='htk') -> [257, 64] fp32."""
+    all_freqs = torch.linspace(0, sr // 2, N_BINS, dtype=torch.float64)
+    m_pts = torch.linspace(_hz_to_mel(0.0), _hz_to_mel(sr / 2.0), N_MELS + 2, dtype=torch.float64)
+    f_pts = 700.0 * (10.0 ** (m_pts / 2595.0) - 1.0)
+    f_diff = f_pts[1:] - f_pts[:-1]
+    slopes = f_pts.unsqueeze(0) - all_freqs.unsqueeze(1)
+    down = (-1.0 * slopes[:, :-2]) / f_diff[:-1]
+    up = slopes[:, 2:] / f_diff[1:]
+    return torch.clamp(torch.min(down, up), min=0.0).to(torch.float32)
+
+
+def _split3(x64):
+    """fp32 value -> three bf16 terms h + m + l (24 mantissa bits)."""
+    x = x64.to(torch.float32)
+    h = x.to(torch.bfloat16)
+    r1 = x - h.float()
+    m = r1.to(torch.bfloat16)
+    r2 = r1 - m.float()
+    return torch.stack([h, m, r2.to(torch.bfloat16)])
+
+
+def constants(device, sr=SR):
+    """(basis [3, 512, 320] bf16, mel_idx [257, 2] int32, mel_w [257, 2] fp32) on `device`, built once."""
+    key = (str(device), sr)
+    if key in _CONST:
+        return _CONST[key]
+    i = torch.arange(WIN, dtype=torch.float64)
+    win = torch.hann_window(WIN, periodic=True, dtype=torch.float64)
+    f = torch.arange(N_FFT // 2, dtype=torch.float64)  # bins 0..255
+    ang = 2.0 * math.pi * f[:, None] * i[None, :] / N_FFT
+    basis = torch.empty(N_FFT, WIN, dtype=torch.float64)
+    basis[0::2] = torch.cos(ang) * win
+    basis[1::2] = torch.sin(ang) * win
+    basis[1] = torch.cos(math.pi * i) * win  # the purely real Nyquist bin takes the slot of im(0) == 0
+    fb = mel_filterbank(sr)
+    idx = torch.zeros(N_BINS, 2, dtype=torch.int32)
+    w = torch.zeros(N_BINS, 2, dtype=torch.float32)
+    for b in range(N_BINS):
+        nz = torch.nonzero(fb[b]).flatten().tolist()
+        if len(nz) > 2:
+            raise _lib.LasrError("mel filterbank is not 2-sparse per bin; unsupported sample rate")
+        for j, m in enumerate(nz):
+            idx[b, j] = m
+            w[b, j] = fb[b, m]
+    out = (_split3(basis).contiguous().to(device), idx.contiguous().to(device), w.contiguous().to(device))
+    _CONST[key] = out
+    return out
+
+
+def logmel_batch(waves, num_samples, dither=None, out_dtype=None, want_nct=True, products=6, sr=SR):
+    """waves [N, S_max] fp32 CUDA (zero padded), num_samples [N] int -> dict with
+         'inputs'  [N, 1, 64, T_max] fp32 (reference layout, if want_nct)
+         'ntc'     [N, T_max, 64] out_dtype (channels-last encoder input, if out_dtype is not None)
+         'percents'[N] fp32 = T_n / T_max  (data_module.py:244), 'frames' [N] int32
+    """
+    if not waves.is_cuda:
+        raise _lib.LasrError("logmel_batch needs CUDA tensors (no CPU fallback)")
+    waves = waves.contiguous().float()
+    N, S_max = waves.shape
+    ns_host = num_samples.cpu() if isinstance(num_samples, torch.Tensor) else torch.tensor(num_samples)
+    if int(ns_host.max()) > S_max or int(ns_host.min()) <= N_FFT // 2:
+        raise _lib.LasrError("num_samples must be in (256, S_max] (reflect padding needs more than n_fft/2 samples)")
+    T_max = num_frames(int(ns_host.max()))
+    ns = ns_host.to(device=waves.device, dtype=torch.int32)
+    dev = waves.device
+    basis, mel_idx, mel_w = constants(dev, sr)
+    Lp = _lib.load().lasr_logmel_padded_len(T_max)
+    parts = torch.empty((3, N, Lp), device=dev, dtype=torch.bfloat16)
+    _lib.call("lasr_logmel_prepare", waves, dither, ns, parts, N, S_max, T_max)
+    db = torch.empty((N, T_max, N_MELS), device=dev, dtype=torch.float32)
+    stats = torch.zeros((N, 2), device=dev, dtype=torch.float64)
+    _lib.call("lasr_logmel_fwd", parts, basis, mel_idx, mel_w, ns, db, stats, N, T_max, products)
+    out_nct = torch.empty((N, 1, N_MELS, T_max), device=dev, dtype=torch.float32) if want_nct else None
+    out_ntc = torch.empty((N, T_max, N_MELS), device=dev, dtype=out_dtype) if out_dtype is not None else None
+    _lib.call("lasr_logmel_normalize", db, stats, ns, out_nct, out_ntc, N, T_max,
+              _lib.dtype_code(out_dtype) if out_dtype is not None else _lib.LASR_F32)
+    frames = num_frames(ns_host.long())
+    return {"inputs": out_nct, "ntc": out_ntc, "percents": frames.float() / float(T_max), "frames": frames.int(),
+            "db": db}
+
+
+def _load_wav(path_or_file):
+    """PCM wav -> float32 [1, S] in [-1, 1) and its sample rate (torchaudio.load(..., normalize=True) contract,
+    data_module.py:153).  Decoding is I/O, outside the hot path: stdlib `wave` covers the 16-bit PCM files that
+    scripts/get_libri.py / get_aishell.py produce."""
+    import wave
+
+    import numpy as np
+
+    with wave.open(path_or_file, "rb") as wf:
+        sr, ch, sw, n = wf.getframerate(), wf.getnchannels(), wf.getsampwidth(), wf.getnframes()
+        raw = wf.readframes(n)
+    if sw != 2:
+        raise _lib.LasrError("only 16-bit PCM wav files are supported")
+    a = np.frombuffer(raw, dtype="<i2").reshape(-1, ch).T.astype(np.float32) / 32768.0
+    return torch.from_numpy(a.copy()), sr
+
+
+class AudioParser:
+    """data_module.py:58-174.  parse_audio(audio_path, mask=False) -> [1, 64, T] fp32 (on the GPU).
+    `audio_path` may be a path / file-like (as in the reference) or an already decoded waveform tensor [S] / [1, S].
+    mask=True (train-time crop + SpecAugment, unseeded host RNG in the reference) is not reproduced: it raises."""
+
+    def __init__(self, win_len=0.02, sr=16000, device="cuda", dither=True):
+        self.sr = sr
+        self.win_len = win_len  # kept for signature parity; the reference hard-codes 320/160 too (:68-70)
+        self.device = torch.device(device)
+        self.dither = dither
+
+    def parse_audio(self, audio_path, mask=False):
+        if mask:
+            raise _lib.LasrError("train-time augmentation (crop / SpecAugment) is host-side and out of the hot path")
+        if isinstance(audio_path, torch.Tensor):
+            y = audio_path.reshape(1, -1)
+        else:
+            import os
+
+            if isinstance(audio_path, str) and not os.path.exists(audio_path):
+                raise FileExistsError("audio_path not exits")  # data_module.py:151-152 (sic)
+            y, _ = _load_wav(audio_path)
+            y = y[:1]
+        y = y.to(self.device, torch.float32)
+        d = torch.randn_like(y) if self.dither else None  # :155
+        out = logmel_batch(y, [y.shape[1]], dither=d, sr=self.sr)
+        return out["inputs"][0]
+
+
+def collate(batch):
+    """data_module.py:222-248.  batch: list of (feats [1,64,T_i], token ids, path) -> the training-step tuple."""
+    longest = max(batch, key=lambda s: s[0].size(2))[0]
+    freq, max_t = longest.size(1), longest.size(2)
+    max_s = len(max(batch, key=lambda s: len(s[1]))[1])
+    n = len(batch)
+    inputs = torch.zeros(n, 1, freq, max_t, device=longest.device)
+    percents = torch.zeros(n, dtype=torch.float32)
+    target_sizes = torch.zeros(n, dtype=torch.int32)
+    targets = torch.zeros(n, max_s)
+    paths = []
+    for i, (feat, txt, path) in enumerate(batch):
+        t = feat.size(2)
+        inputs[i, 0, :, :t] = feat.squeeze(0)
+        percents[i] = t / float(max_t)
+        target_sizes[i] = len(txt)
+        targets[i, : len(txt)] = torch.tensor(txt, dtype=torch.float32)
+        paths.append(path)
+    return inputs, targets.long(), percents, target_sizes, paths

@@ -1,0 +1,104 @@
+"""Log-mel frontend (csrc/logmel.cu) against the reference's torchaudio pipeline: the committed golden features
+(tests/golden/frontend.pt, generated from torchaudio.transforms in the build container) and the CPU oracle."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from golden_common import seeded_wave  # noqa: E402
+
+from conftest import rel_err  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def frontend():
+    from lightning_asr_b200 import _lib, frontend
+
+    _lib.require_device()
+    return frontend
+
+
+def _batch(waves):
+    S_max = max(w.numel() for w in waves)
+    x = torch.zeros(len(waves), S_max)
+    for i, w in enumerate(waves):
+        x[i, : w.numel()] = w
+    return x.cuda(), [w.numel() for w in waves]
+
+
+def test_logmel_matches_golden_torchaudio_features(frontend):
+    """fp32 tolerance of the north star: rel 1e-4 (features are ~N(0,1) per utterance); also the collate contract."""
+    fx = torch.load(os.path.join(GOLDEN, "frontend.pt"))
+    names = ["w8000", "w12345", "w400"]
+    waves = [seeded_wave(8000, 1), seeded_wave(12345, 2), seeded_wave(400, 3)]
+    x, ns = _batch(waves)
+    out = frontend.logmel_batch(x, ns, out_dtype=torch.float32)
+    T_max = out["inputs"].shape[-1]
+    for i, name in enumerate(names):
+        ref = fx["features"][name]
+        T = ref.shape[-1]
+        got = out["inputs"][i, :, :, :T].cpu()
+        assert rel_err(got, ref) < 1e-4, name
+        assert (got - ref).abs().max().item() < 2e-3, name
+        assert float(out["inputs"][i, :, :, T:].abs().max()) == 0.0 if T < T_max else True
+        # channels-last twin is the same data
+        assert torch.equal(out["ntc"][i].t().cpu(), out["inputs"][i, 0].cpu())
+    # batched output == the reference's collate of per-utterance features (data_module.py:222-248)
+    c = fx["collate"]
+    order = [0, 1, 2]
+    assert rel_err(out["inputs"][order].cpu(), c["inputs"]) < 1e-4
+    assert torch.allclose(out["percents"], c["percents"])
+
+
+@pytest.mark.parametrize("products,tol", [(6, 1e-4), (3, 1e-3)])
+def test_logmel_matches_oracle_ragged_with_dither(frontend, products, tol):
+    from oracle import frontend_oracle
+
+    g = torch.Generator().manual_seed(5)
+    lens = [16000 * 3, 16000 * 2 + 123, 9000, 16000 * 3 - 1]
+    # speech-like dynamic range: a decaying spectrum, not white noise (exercises the cancellation-heavy low bins)
+    waves = []
+    for n in lens:
+        w = torch.randn(n, generator=g)
+        w = torch.cumsum(w, 0)
+        w = w - w.mean()
+        waves.append((0.3 * w / w.abs().max()).float())
+    dither = [torch.randn(n, generator=g) for n in lens]
+    x, ns = _batch(waves)
+    d, _ = _batch(dither)
+    out = frontend.logmel_batch(x, ns, dither=d, products=products)
+    for i, n in enumerate(lens):
+        ref = frontend_oracle.logmel(waves[i], dither=dither[i])
+        T = ref.shape[-1]
+        assert T == int(out["frames"][i])
+        assert rel_err(out["inputs"][i, :, :, :T].cpu(), ref) < tol, (i, products)
+
+
+def test_audio_parser_contract(frontend, tmp_path):
+    """AudioParser.parse_audio(path) -> [1, 64, T] (data_module.py:150-174); missing file raises like :151-152."""
+    import wave
+
+    import numpy as np
+
+    w = seeded_wave(8000, 1)
+    pcm = (w.clamp(-1, 1) * 32767).round().to(torch.int16).numpy()
+    path = str(tmp_path / "a.wav")
+    with wave.open(path, "wb") as wf:
+        wf.setnchannels(1)
+        wf.setsampwidth(2)
+        wf.setframerate(16000)
+        wf.writeframes(pcm.astype("<i2").tobytes())
+    parser = frontend.AudioParser(dither=False)
+    feat = parser.parse_audio(path)
+    from oracle import frontend_oracle
+
+    ref = frontend_oracle.logmel(torch.from_numpy(pcm.astype(np.float32) / 32768.0))
+    assert feat.shape == ref.shape
+    assert rel_err(feat.cpu(), ref) < 1e-4
+    with pytest.raises(FileExistsError):
+        parser.parse_audio(str(tmp_path / "missing.wav"))
