@@ -22,6 +22,8 @@
 // and MaskCNN (:309-321) + the statistics pass of nn.BatchNorm1d (:24,35) which are folded into the epilogue.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace lasr {
 
 struct GemmTcParams {
@@ -350,6 +352,298 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Weight-stationary forward / data-gradient kernel (bf16 out).
+//
+// The 1x1 convs of this network are short-K GEMMs (K = 64..512) over ~25 k frames: with a streamed B operand every
+// 128-frame tile re-loads the whole weight slice (2x the bytes of the activation tile itself) and the L2 -> SM path,
+// not the tensor pipe, sets the pace.  Here a CTA owns ONE 128-column slice of the output for its whole life:
+//   - its weight slice [128 x K] (<= 128 KB) is TMA-loaded once and stays in shared memory;
+//   - only activation tiles stream through the TMA ring (CTAs that share a row block run adjacently -> L2 hits);
+//   - the epilogue warps pack the accumulator to bf16 into a 128B-swizzled staging tile that ONE thread hands to
+//     the TMA store unit (full-line, asynchronous stores);
+//   - four more warps read the same staging tile column-wise and keep the BatchNorm sum / sum of squares of the
+//     CTA's 128 columns in registers across all its tiles: one fp64 RED per column and CTA at the very end
+//     (the per-tile RED.f64 of the streamed kernel serialised ~800 atomics on every statistics address).
+// warps: 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4-7 epilogue (TMEM -> staging), 8-11 statistics.
+// ------------------------------------------------------------------------------------------------
+struct GemmWsParams {
+  int M, N, K;
+  int num_m_blocks, num_n_blocks, num_k_blocks;
+  int ctas_per_n;
+  int stages;
+  int cluster;  // CTAs per cluster = num_n_blocks when the activation tiles are multicast, else 1
+  const float* bias;
+  const int32_t* lengths;
+  int T;
+  double* stats;
+  unsigned long long* trace;  // debug timeline (tools/trace_gemm.py), normally NULL
+};
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define WS_TRACE(slot, idx)                                                                       \
+  do {                                                                                            \
+    if (p.trace != nullptr && (idx) < 16) p.trace[(blockIdx.x * 8 + (slot)) * 16 + (idx)] = gtimer(); \
+  } while (0)
+
+constexpr int WS_BM = 128, WS_BN = 128, WS_BK = 64;
+constexpr int WS_A_BYTES = WS_BM * WS_BK * 2;        // 16 KB per ring stage
+constexpr int WS_WKB_BYTES = WS_BN * WS_BK * 2;      // 16 KB of the weight slice per k-block
+constexpr int WS_STG_BYTES = WS_BM * WS_BN * 2;      // 32 KB staging tile (two 64-column sub-tiles)
+constexpr int WS_MAX_STAGES = 8;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <bool B_MN>
+__global__ void __launch_bounds__(384, 1)
+gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_c, const GemmWsParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* s_w = smem;                                        // [num_k_blocks][16 KB]
+  uint8_t* s_a = s_w + p.num_k_blocks * WS_WKB_BYTES;         // [stages][16 KB]
+  uint8_t* s_stg = s_a + p.stages * WS_A_BYTES;               // [2][128 rows x 128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stg + WS_STG_BYTES);
+  uint64_t* empty_bar = full_bar + WS_MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + WS_MAX_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint64_t* w_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_blk = blockIdx.x % p.num_n_blocks;
+  const int m_first = blockIdx.x / p.num_n_blocks;
+  if (threadIdx.x == 0) WS_TRACE(0, 0);
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_c);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], p.cluster);  // every CTA of the cluster must have consumed the slot
+    }
+    mbar_init(&tmem_full_bar[0], 1);
+    mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 4);
+    mbar_init(&tmem_empty_bar[1], 4);
+    mbar_init(w_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_ptr_smem, 2 * WS_BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (p.cluster > 1) cluster_sync_all();  // peers' barriers exist before any multicast / remote arrive
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint16_t mc_mask = static_cast<uint16_t>((1u << p.cluster) - 1u);
+  const int slice_rows = WS_BM / p.cluster;
+  const int crank = p.cluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  if (threadIdx.x == 0) WS_TRACE(0, 1);
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      // the CTA's weight slice, once
+      mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(p.num_k_blocks) * WS_WKB_BYTES);
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        uint8_t* dst = s_w + kb * WS_WKB_BYTES;
+        if constexpr (!B_MN) {
+          tma_load_2d(dst, &tma_b, w_bar, kb * WS_BK, n_blk * WS_BN);
+        } else {
+#pragma unroll
+          for (int c = 0; c < WS_BN / 64; ++c)
+            tma_load_2d(dst + c * (64 * WS_BK * 2), &tma_b, w_bar, n_blk * WS_BN + c * 64, kb * WS_BK);
+        }
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int m_blk = m_first; m_blk < p.num_m_blocks; m_blk += p.ctas_per_n) {
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[stage], WS_A_BYTES);
+          if (p.cluster == 1) {
+            tma_load_2d(s_a + stage * WS_A_BYTES, &tma_a, &full_bar[stage], kb * WS_BK, m_blk * WS_BM);
+          } else {
+            // this CTA fetches its slice of rows and multicasts it; the peers deliver the other slices
+            tma_load_2d_mc(s_a + stage * WS_A_BYTES + crank * slice_rows * 128, &tma_a, &full_bar[stage], kb * WS_BK,
+                           m_blk * WS_BM + crank * slice_rows, mc_mask);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(WS_BM, WS_BN, 0, B_MN ? 1 : 0);
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+      WS_TRACE(0, 2);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local_tile = 0;
+      for (int m_blk = m_first; m_blk < p.num_m_blocks; m_blk += p.ctas_per_n, ++local_tile) {
+        const int acc = local_tile & 1;
+        const uint32_t acc_phase = (local_tile >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        WS_TRACE(1, local_tile);
+        const uint32_t tmem_d = tmem_base + acc * WS_BN;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (kb == 0) WS_TRACE(2, local_tile);
+          const uint32_t sa = smem_u32(s_a + stage * WS_A_BYTES);
+          const uint32_t sb = smem_u32(s_w + kb * WS_WKB_BYTES);
+#pragma unroll
+          for (int k = 0; k < WS_BK / 16; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, 64 * WS_BK * 2, 1024)
+                                     : umma_desc_sw128(sb + k * 32, 16, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          if (p.cluster == 1)
+            umma_commit(&empty_bar[stage]);
+          else
+            umma_commit_mc(&empty_bar[stage], mc_mask);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full_bar[acc]);
+        WS_TRACE(3, local_tile);
+      }
+    }
+  } else if (warp_idx >= 4 && warp_idx < 8) {
+    // ===================== epilogue: TMEM -> bf16 staging tile -> TMA store =====================
+    const int ew = warp_idx - 4;
+    const int r = ew * 32 + lane;  // row inside the tile
+    int local_tile = 0;
+    for (int m_blk = m_first; m_blk < p.num_m_blocks; m_blk += p.ctas_per_n, ++local_tile) {
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = (local_tile >> 1) & 1;
+      const int row = m_blk * WS_BM + r;
+      bool keep = row < p.M;
+      if (keep && p.lengths != nullptr) {
+        const int n = row / p.T;
+        keep = (row - n * p.T) < p.lengths[n];
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      if (threadIdx.x == 128) WS_TRACE(4, local_tile);
+      // staging tile free: the previous TMA store has read it and the statistics warps are done with it
+      if (threadIdx.x == 128) tma_store_wait_read<0>();
+      named_bar_sync(1, 256);
+      if (threadIdx.x == 128) WS_TRACE(5, local_tile);
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * WS_BN;
+#pragma unroll
+      for (int ch = 0; ch < WS_BN / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr0 + ch * 32, v);
+        tmem_ld_wait();
+        const int col0 = n_blk * WS_BN + ch * 32;
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
+        }
+        if (!keep) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = 0.f;
+        }
+        uint8_t* sub = s_stg + (ch >> 1) * (WS_BM * 128) + r * 128;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = f32x2_to_bf16x2(f[8 * q + 0], f[8 * q + 1]);
+          u.y = f32x2_to_bf16x2(f[8 * q + 2], f[8 * q + 3]);
+          u.z = f32x2_to_bf16x2(f[8 * q + 4], f[8 * q + 5]);
+          u.w = f32x2_to_bf16x2(f[8 * q + 6], f[8 * q + 7]);
+          const int c16 = (ch & 1) * 4 + q;  // 16-byte chunk inside the 128-byte row
+          *reinterpret_cast<uint4*>(sub + ((c16 ^ (r & 7)) << 4)) = u;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      fence_proxy_async_smem();
+      named_bar_sync(2, 256);  // staging tile complete
+      if (threadIdx.x == 128) WS_TRACE(6, local_tile);
+      if (threadIdx.x == 128) {
+#pragma unroll
+        for (int j = 0; j < WS_BN / 64; ++j)
+          tma_store_2d(&tma_c, s_stg + j * (WS_BM * 128), n_blk * WS_BN + j * 64, m_blk * WS_BM);
+        tma_store_commit();
+      }
+    }
+    if (threadIdx.x == 128) tma_store_wait<0>();
+    if (threadIdx.x == 128) WS_TRACE(0, 3);
+  } else if (warp_idx >= 8) {
+    // ===================== BatchNorm statistics from the staging tile =====================
+    const int sw = warp_idx - 8;
+    const int sub = sw & 1;          // 64-column sub-tile
+    const int r0 = (sw >> 1) * 64;   // row half
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    const bool want = p.stats != nullptr;
+    for (int m_blk = m_first; m_blk < p.num_m_blocks; m_blk += p.ctas_per_n) {
+      named_bar_sync(1, 256);
+      named_bar_sync(2, 256);
+      if (want) {
+        const uint8_t* base = s_stg + sub * (WS_BM * 128);
+#pragma unroll 8
+        for (int rr = 0; rr < 64; ++rr) {
+          const int r = r0 + rr;
+          const uint32_t w =
+              *reinterpret_cast<const uint32_t*>(base + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+          const float2 v = bf16x2_to_f32x2(w);
+          s0 += v.x;
+          s1 += v.y;
+          q0 = fmaf(v.x, v.x, q0);
+          q1 = fmaf(v.y, v.y, q1);
+        }
+      }
+    }
+    if (want) {
+      const int col = n_blk * WS_BN + sub * 64 + 2 * lane;
+      if (col < p.N) {
+        red_add_f64(p.stats + col, static_cast<double>(s0));
+        red_add_f64(p.stats + p.N + col, static_cast<double>(q0));
+      }
+      if (col + 1 < p.N) {
+        red_add_f64(p.stats + col + 1, static_cast<double>(s1));
+        red_add_f64(p.stats + p.N + col + 1, static_cast<double>(q1));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * WS_BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -425,6 +719,109 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmT
   return LASR_OK;
 }
 
+static unsigned long long* g_ws_trace = nullptr;
+extern "C" void lasr_debug_set_gemm_trace(unsigned long long* buf) { g_ws_trace = buf; }
+
+// weight-stationary launch; returns LASR_ERR_UNSUPPORTED when the shape does not qualify (caller falls back)
+static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const float* bias, const int32_t* lengths, int T,
+                     double* stats, int M, int N, int K, int lda, int ldb, int ldc, cudaStream_t stream) {
+  const int kbs = cdiv(K, WS_BK);
+  static const bool disabled = getenv("LASR_GEMM_STREAMED") != nullptr;  // A/B switch for profiling
+  if (disabled) return LASR_ERR_UNSUPPORTED;
+  if (kbs * WS_WKB_BYTES > 131072) return LASR_ERR_UNSUPPORTED;
+  if ((ldc % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return LASR_ERR_UNSUPPORTED;
+  const int nblk = cdiv(N, WS_BN);
+  // Cluster multicast of the activation tiles (each CTA fetches 1/cluster of the rows for all n-slices) is implemented
+  // but OFF by default: measured on B200 it does not shorten the tile period (L2 already de-duplicates the <= 4
+  // concurrent readers of a tile) and co-residency of clusters costs CTAs.  LASR_GEMM_MULTICAST=1 enables it.
+  static const bool use_mc = getenv("LASR_GEMM_MULTICAST") != nullptr;
+  const int cluster = (use_mc && (nblk == 2 || nblk == 4 || nblk == 8)) ? nblk : 1;
+  CUtensorMap ta, tb, tc;
+  int rc = make_tmap_2d_bf16(&ta, a, K, M, static_cast<uint64_t>(lda) * 2, 64, 128 / cluster, true);
+  if (rc) return rc;
+  if (!b_mn)
+    rc = make_tmap_2d_bf16(&tb, b, K, N, static_cast<uint64_t>(ldb) * 2, 64, WS_BN, true);
+  else
+    rc = make_tmap_2d_bf16(&tb, b, N, K, static_cast<uint64_t>(ldb) * 2, 64, 64, true);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tc, out, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
+  if (rc) return rc;
+  GemmWsParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_m_blocks = cdiv(M, WS_BM);
+  p.num_n_blocks = cdiv(N, WS_BN);
+  p.num_k_blocks = kbs;
+  if (p.num_n_blocks > kNumSMs) return LASR_ERR_UNSUPPORTED;
+  int per_n = kNumSMs / p.num_n_blocks;
+  if (per_n > p.num_m_blocks) per_n = p.num_m_blocks;
+  // equalise: the same number of rounds with as few CTAs as needed keeps every CTA's tile count within one
+  p.cluster = cluster;
+  const int budget = 232448 - 1024 - 512 - kbs * WS_WKB_BYTES - WS_STG_BYTES;
+  int stages = budget / WS_A_BYTES;
+  if (stages > WS_MAX_STAGES) stages = WS_MAX_STAGES;
+  if (stages < 2) return LASR_ERR_UNSUPPORTED;
+  p.stages = stages;
+  p.bias = bias;
+  p.lengths = lengths;
+  p.T = T;
+  p.stats = stats;
+  p.trace = g_ws_trace;
+  const int smem = 1024 + 512 + kbs * WS_WKB_BYTES + stages * WS_A_BYTES + WS_STG_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) {
+      lasr_set_cuda_error(e);
+      return LASR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cluster > 1) {
+    // clusters must be co-resident (persistent kernel): cap the grid at what the GPCs can hold at once
+    static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (max_clusters[cluster] == 0) {
+      cfg.gridDim = dim3(cluster * 16);
+      cfg.dynamicSmemBytes = 232448;
+      int n = 0;
+      cudaError_t e = b_mn ? cudaOccupancyMaxActiveClusters(&n, gemm_ws_kernel<true>, &cfg)
+                           : cudaOccupancyMaxActiveClusters(&n, gemm_ws_kernel<false>, &cfg);
+      if (e != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        n = (kNumSMs / cluster) * 3 / 4;
+      }
+      max_clusters[cluster] = n;
+      cfg.dynamicSmemBytes = smem;
+    }
+    if (per_n > max_clusters[cluster]) per_n = max_clusters[cluster];
+  }
+  const int rounds = cdiv(p.num_m_blocks, per_n);
+  per_n = cdiv(p.num_m_blocks, rounds);
+  p.ctas_per_n = per_n;
+  cfg.gridDim = dim3(p.num_n_blocks * per_n);
+  cudaError_t le = b_mn ? cudaLaunchKernelEx(&cfg, gemm_ws_kernel<true>, ta, tb, tc, p)
+                        : cudaLaunchKernelEx(&cfg, gemm_ws_kernel<false>, ta, tb, tc, p);
+  if (le != cudaSuccess) {
+    lasr_set_cuda_error(le);
+    return LASR_ERR_CUDA;
+  }
+  return LASR_OK;
+}
+
 static int pick_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256)); }
 
 // y[M, N] = x[M, K] w[N, K]^T, bf16 in, bf16/fp32 out
@@ -432,6 +829,10 @@ int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const
                int M, int N, int K, int lda, int ldb, int ldc, int out_f32, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return LASR_ERR_BAD_SHAPE;
   if ((lda % 8) || (ldb % 8)) return LASR_ERR_ALIGNMENT;
+  if (!out_f32 && N > 64) {
+    const int rc_ws = launch_ws(false, a, b, out, bias, lengths, T, stats, M, N, K, lda, ldb, ldc, stream);
+    if (rc_ws != LASR_ERR_UNSUPPORTED) return rc_ws;
+  }
   const int BN = pick_bn(N);
   CUtensorMap ta, tb;
   int rc = make_tmap_2d_bf16(&ta, a, K, M, static_cast<uint64_t>(lda) * 2, 64, 128, true);
@@ -472,6 +873,10 @@ int gemm_tc_nn(const void* a, const void* b, void* out, int M, int N, int K, int
                cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return LASR_ERR_BAD_SHAPE;
   if ((lda % 8) || (ldb % 8)) return LASR_ERR_ALIGNMENT;
+  if (!out_f32 && N > 64) {
+    const int rc_ws = launch_ws(true, a, b, out, nullptr, nullptr, 0, nullptr, M, N, K, lda, ldb, ldc, stream);
+    if (rc_ws != LASR_ERR_UNSUPPORTED) return rc_ws;
+  }
   const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
   CUtensorMap ta, tb;
   int rc = make_tmap_2d_bf16(&ta, a, K, M, static_cast<uint64_t>(lda) * 2, 64, 128, true);

@@ -49,7 +49,8 @@ def test_dwconv_fwd_wgrad_dgrad(ops, dtype, tol, C, K, stride, T):
 
 @pytest.mark.parametrize("dtype,tol", DTYPES)
 @pytest.mark.parametrize("M,Cin,Cout,T", [(1002, 64, 256, 501), (900, 256, 256, 300), (1000, 336, 512, 250),
-                                           (777, 512, 1024, 777), (640, 1024, 29, 320), (300, 1024, 4334, 100)])
+                                           (777, 512, 1024, 777), (640, 1024, 29, 320), (300, 1024, 4334, 100),
+                                           (25632, 256, 256, 801), (12800, 512, 512, 400)])
 def test_pwconv_fwd_mask_stats_dgrad_wgrad(ops, dtype, tol, M, Cin, Cout, T):
     torch.manual_seed(M)
     x = torch.randn(M, Cin, device="cuda").to(dtype)
