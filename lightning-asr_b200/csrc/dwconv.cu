@@ -380,6 +380,13 @@ static int wgrad_t(const void* x, const void* dy, float* dwt, int N, int T_in, i
 
 }  // namespace lasr
 
+namespace lasr {
+int dwconv_tc_supported(int C, int K, int stride);
+int dwconv_tc_fwd(const void* x, const float* w, void* y, const void* addend, int N, int T, int C, int K, int flip,
+                  cudaStream_t stream);
+int dwconv_tc_wgrad(const void* x, const void* dy, float* dw, int N, int T, int C, int K, cudaStream_t stream);
+}  // namespace lasr
+
 using namespace lasr;
 
 extern "C" {
@@ -390,6 +397,8 @@ int lasr_dwconv1d_fwd(const void* x, const float* wt, void* y, const void* adden
   if (T_out != (T_in + 2 * (K / 2) - K) / stride + 1) return LASR_ERR_BAD_SHAPE;
   if (flip && stride != 1) return LASR_ERR_UNSUPPORTED;
   if (dtype == LASR_F32) return fwd_t<float>(x, wt, y, addend, N, T_in, T_out, C, K, stride, flip, dtype, stream);
+  if (dtype == LASR_BF16 && dwconv_tc_supported(C, K, stride))  // tensor-core Toeplitz path (dwconv_tc.cu)
+    return dwconv_tc_fwd(x, wt, y, addend, N, T_in, C, K, flip, stream);
   if (dtype == LASR_BF16)
     return fwd_t<__nv_bfloat16>(x, wt, y, addend, N, T_in, T_out, C, K, stride, flip, dtype, stream);
   return LASR_ERR_BAD_DTYPE;
@@ -400,6 +409,7 @@ int lasr_dwconv1d_wgrad(const void* x, const void* dy, float* dwt, int N, int T_
   if (N <= 0 || T_in <= 0 || C <= 0 || (C & 1)) return LASR_ERR_BAD_SHAPE;
   if (T_out != (T_in + 2 * (K / 2) - K) / stride + 1) return LASR_ERR_BAD_SHAPE;
   if (dtype == LASR_F32) return wgrad_t<float>(x, dy, dwt, N, T_in, T_out, C, K, stride, dtype, stream);
+  if (dtype == LASR_BF16 && dwconv_tc_supported(C, K, stride)) return dwconv_tc_wgrad(x, dy, dwt, N, T_in, C, K, stream);
   if (dtype == LASR_BF16) return wgrad_t<__nv_bfloat16>(x, dy, dwt, N, T_in, T_out, C, K, stride, dtype, stream);
   return LASR_ERR_BAD_DTYPE;
 }

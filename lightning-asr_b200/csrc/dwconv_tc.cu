@@ -1,0 +1,448 @@
+// Depthwise Conv1d on the tensor cores (bf16, stride 1): forward, data gradient (flipped taps, fused residual addend)
+// and weight gradient.  Replaces nn.Conv1d(C, C, k, groups=C) at models/QuartNet.py:14-21,30 and its autograd backward.
+//
+// Why: with k = 33..87 taps the op costs k FMAs per element -- on the fp32 pipe (dwconv.cu, packed FFMA2) that is
+// 22 us for a 512-channel layer at 100 % pipe utilisation against 8 us of HBM time.  A depthwise conv is a banded
+// Toeplitz product per channel, y_c = Toep(w_c) z_c, and tcgen05 can consume BOTH factors without materialising them:
+//
+//   * the channel's time series z_c (bf16, frames contiguous) is a legal K-major, no-swizzle A operand of the HANKEL
+//     matrix A[m, k] = z_c[8 m + k]: canonical layout ((8,m),(8,2)) : ((16 B, SBO), (2 B, LBO)) with SBO = 128 B and
+//     LBO = 16 B -- the core matrices overlap, row m simply starts 8 frames after row m-1.  128 rows x 8 frames =
+//     1024 output frames per MMA, K-steps advance the start address by 32 B (16 frames);
+//   * the Toeplitz factor B[t, s] = w_c[s - t] (t < 8 output frames of a row, s < KS = 16*ceil((k+7)/16) inputs) is
+//     KS/8 core matrices of 128 B per channel, built once per CTA.
+//   D[m, t] = sum_s z_c[8 m + s] w_c[s - t] = y_c[8 m + t].  N = 16 is the smallest legal N at M = 128, columns 8..15
+//   are ignored.  One MMA (K = 16) costs the 4 KB shared-memory read of A (32 cycles): 6-10 outputs / cycle / SM, i.e.
+//   about the HBM time of the layer, against 1.5 outputs / cycle for FFMA2.
+//
+// Activations are channels-last, so the per-channel series do not exist in memory: producer warps load 8 frames x 8
+// channels per thread (16-byte loads, a 16-lane group covers both halves of every 32-byte sector), transpose the 8x8
+// bf16 block with byte permutes and store 16-byte chunks of 8 consecutive frames into the channel's series.  Out of
+// range frames (the conv zero padding, utterance edges) are stored as zeros.
+//
+// CTA = 16 channels, persistent over (utterance, 1024-frame chunk) items; warps 0-3 epilogue (TMEM -> bf16 -> 32-byte
+// global stores, + addend), warp 4 MMA issuer, warp 5 TMEM allocator, warps 6-9 producers; series and accumulators
+// double buffered, so load/transpose, MMA and store of consecutive items overlap.
+//
+// wgrad: dw_c[j] = sum_tau dy_c[tau] z_c[tau + j].  With windows of 8 frames in the K dimension both operands are again
+// plain series: A[t', w] = z_c[8 w + t'] and B[w, t] = dy_c[8 w + t] are MN-major no-swizzle operands (LBO = 128 B
+// between groups of 8 windows, SBO = 16 B between groups of 8 t'), D[t', t] += sum_w z_c[8w + t'] dy_c[8w + t] and
+// dw_c[j] = sum_{t<8} D[t + j, t].  The accumulator stays in TMEM over all items of the CTA; one RED pass at the end.
+#include "common.cuh"
+
+#include <cstdlib>
+
+namespace lasr {
+
+constexpr int DT_CG = 16;        // channels per CTA
+constexpr int DT_ROWS = 128;     // MMA M: windows of 8 frames
+constexpr int DT_CHUNK = 1024;   // output frames per item
+constexpr int DT_THREADS = 320;
+constexpr int DT_MAX_KS = 112;
+
+struct DwTcParams {
+  const __nv_bfloat16* x;
+  const float* w;
+  __nv_bfloat16* y;
+  const __nv_bfloat16* addend;
+  const __nv_bfloat16* dy;  // wgrad only
+  float* dw;                // wgrad only
+  int N, T, C, K, KS, flip;
+  int num_cg, t_chunks, items_per_cg, ctas_per_cg;
+  int ZL;  // series length in frames (multiple of 8)
+};
+
+__device__ __forceinline__ uint64_t umma_desc_none(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell); layout type 0 = no swizzle
+  return d;
+}
+
+__device__ __forceinline__ void tmem_ld_32x32_x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+
+// global [frames, C] -> per-channel series in shared memory.  series[c][sigma] (bf16, pitch ZL) for sigma in
+// [0, ZL): frame f = f_base + sigma of utterance rows `src` (nullptr / out of [0, T): zero).  Called by 4 producer
+// warps (pw = 0..3); a warp handles 128 frames x 16 channels per pass.
+__device__ __forceinline__ void load_series(const __nv_bfloat16* __restrict__ src, int C, int T, int f_base, int ZL,
+                                            uint8_t* series, int pw, int lane) {
+  const int h = lane >> 4;    // channel half: channels 8h .. 8h+7
+  const int b = lane & 15;    // 8-frame block within the pass
+  for (int s0 = pw * 128; s0 < ZL; s0 += 4 * 128) {
+    const int sigma = s0 + 8 * b;
+    if (sigma >= ZL) continue;
+    uint4 r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = f_base + sigma + i;
+      r[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (f >= 0 && f < T) r[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(f) * C + 8 * h));
+    }
+    // 8 frames x 8 channels -> 8 channels x 8 frames
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint32_t o[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const uint32_t a = (&r[2 * m].x)[q >> 1], bb = (&r[2 * m + 1].x)[q >> 1];
+        o[m] = __byte_perm(a, bb, (q & 1) ? 0x7632 : 0x5410);
+      }
+      *reinterpret_cast<uint4*>(series + (static_cast<size_t>(8 * h + q) * ZL + sigma) * 2) =
+          make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_fwd_kernel(const DwTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((128u - (raw_addr & 127u)) & 127u);
+  const int cores = p.KS / 8;
+  const int series_bytes = DT_CG * p.ZL * 2;
+  uint8_t* s_toep = smem;                                   // [16][cores][128 B]
+  uint8_t* s_ser = s_toep + DT_CG * cores * 128;            // [2][16][ZL] bf16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ser + 2 * series_bytes);
+  uint64_t* full_bar = bars;            // [2] producers -> MMA
+  uint64_t* empty_bar = bars + 2;       // [2] MMA -> producers
+  uint64_t* tmem_full_bar = bars + 4;   // [2] MMA -> epilogue
+  uint64_t* tmem_empty_bar = bars + 6;  // [2] epilogue -> MMA
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cg = blockIdx.x % p.num_cg;
+  const int first = blockIdx.x / p.num_cg;
+  const int c0 = cg * DT_CG;
+  const int P = p.K / 2;
+
+  // Toeplitz cores: core kk, row r (= output frame t of the window), element e: w[8 kk + e - r]
+  for (int i = threadIdx.x; i < DT_CG * cores * 64; i += DT_THREADS) {
+    const int c = i / (cores * 64);
+    const int rem = i - c * cores * 64;
+    const int kk = rem >> 6, r = (rem >> 3) & 7, e = rem & 7;
+    const int j = 8 * kk + e - r;
+    float v = 0.f;
+    if (j >= 0 && j < p.K && c0 + c < p.C) v = p.w[static_cast<size_t>(c0 + c) * p.K + (p.flip ? p.K - 1 - j : j)];
+    reinterpret_cast<__nv_bfloat16*>(s_toep)[i] = __float2bfloat16_rn(v);
+  }
+  if (warp_idx == 4 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full_bar[s], 4);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp_idx == 5) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();  // Toeplitz cores were written through the generic proxy, the MMA reads them asynchronously
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx >= 6) {
+    // ===================== producers =====================
+    const int pw = warp_idx - 6;
+    int it = 0;
+    for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
+      const int stage = it & 1;
+      const uint32_t phase = (it >> 1) & 1;
+      const int n = idx / p.t_chunks, tc = idx - n * p.t_chunks;
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      load_series(p.x + static_cast<size_t>(n) * p.T * p.C + c0, p.C, p.T, tc * DT_CHUNK - P, p.ZL,
+                  s_ser + stage * series_bytes, pw, lane);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+    }
+  } else if (warp_idx == 4) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(DT_ROWS, 16, 0, 0);
+      const int ksteps = p.KS / 16;
+      int it = 0;
+      for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
+        const int stage = it & 1;
+        const uint32_t phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[stage], phase ^ 1u);
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t ser = smem_u32(s_ser + stage * series_bytes);
+        const uint32_t toep = smem_u32(s_toep);
+        for (int c = 0; c < DT_CG; ++c) {
+          const uint32_t tmem_d = tmem_base + stage * 256 + c * 16;
+          for (int kc = 0; kc < ksteps; ++kc) {
+            const uint64_t da = umma_desc_none(ser + c * p.ZL * 2 + kc * 32, 16, 128);
+            const uint64_t db = umma_desc_none(toep + (c * cores + 2 * kc) * 128, 128, 128);
+            umma_bf16(tmem_d, da, db, idesc, kc > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tmem_full_bar[stage]);
+      }
+    }
+  } else if (warp_idx < 4) {
+    // ===================== epilogue =====================
+    const int row = warp_idx * 32 + lane;  // window: output frames 8 row .. 8 row + 7 of the chunk
+    int it = 0;
+    for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
+      const int stage = it & 1;
+      const uint32_t phase = (it >> 1) & 1;
+      const int n = idx / p.t_chunks, tc = idx - n * p.t_chunks;
+      mbar_wait(&tmem_full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16) + stage * 256;
+      const int f0 = tc * DT_CHUNK + 8 * row;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {  // 8 channels at a time: 64 accumulator registers
+        uint32_t v[8][8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) tmem_ld_32x32_x8(taddr + (half * 8 + c) * 16, v[c]);
+        tmem_ld_wait();
+        if (c0 + half * 8 < p.C) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int f = f0 + t;
+            if (f < p.T) {
+              const size_t off = (static_cast<size_t>(n) * p.T + f) * p.C + c0 + half * 8;
+              float o[8];
+#pragma unroll
+              for (int c = 0; c < 8; ++c) o[c] = __uint_as_float(v[c][t]);
+              if (p.addend != nullptr) {
+                const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.addend + off));
+                const float2 a0 = bf16x2_to_f32x2(a.x), a1 = bf16x2_to_f32x2(a.y), a2 = bf16x2_to_f32x2(a.z),
+                             a3 = bf16x2_to_f32x2(a.w);
+                o[0] += a0.x; o[1] += a0.y; o[2] += a1.x; o[3] += a1.y;
+                o[4] += a2.x; o[5] += a2.y; o[6] += a3.x; o[7] += a3.y;
+              }
+              uint4 u;
+              u.x = f32x2_to_bf16x2(o[0], o[1]);
+              u.y = f32x2_to_bf16x2(o[2], o[3]);
+              u.z = f32x2_to_bf16x2(o[4], o[5]);
+              u.w = f32x2_to_bf16x2(o[6], o[7]);
+              *reinterpret_cast<uint4*>(p.y + off) = u;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[stage]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_wgrad_kernel(const DwTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((128u - (raw_addr & 127u)) & 127u);
+  // per stage: x series [16][ZL] (ZL = 1024 + 128 frames incl. halo) and dy series [16][1024]
+  const int xs_bytes = DT_CG * p.ZL * 2;
+  const int dys_bytes = DT_CG * DT_CHUNK * 2;
+  const int stage_bytes = xs_bytes + dys_bytes;
+  uint8_t* s_ser = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ser + 2 * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + 2;
+  uint64_t* done_bar = bars + 4;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cg = blockIdx.x % p.num_cg;
+  const int first = blockIdx.x / p.num_cg;
+  const int c0 = cg * DT_CG;
+  const int P = p.K / 2;
+
+  if (warp_idx == 4 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full_bar[s], 4);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp_idx == 5) {
+    tmem_alloc(tmem_ptr_smem, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const bool has_items = first < p.items_per_cg;
+
+  if (warp_idx >= 6) {
+    const int pw = warp_idx - 6;
+    int it = 0;
+    for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
+      const int stage = it & 1;
+      const uint32_t phase = (it >> 1) & 1;
+      const int n = idx / p.t_chunks, tc = idx - n * p.t_chunks;
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      uint8_t* base = s_ser + stage * stage_bytes;
+      const size_t uoff = static_cast<size_t>(n) * p.T * p.C + c0;
+      load_series(p.x + uoff, p.C, p.T, tc * DT_CHUNK - P, p.ZL, base, pw, lane);
+      load_series(p.dy + uoff, p.C, p.T, tc * DT_CHUNK, DT_CHUNK, base + xs_bytes, pw, lane);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+    }
+  } else if (warp_idx == 4) {
+    if (lane == 0) {
+      // D[t' (M = 128), t (N = 16)] += sum_w z[8w + t'] dy[8w + t]: A and B both MN-major
+      constexpr uint32_t idesc = umma_idesc_bf16(DT_ROWS, 16, 1, 1);
+      int it = 0;
+      for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
+        const int stage = it & 1;
+        const uint32_t phase = (it >> 1) & 1;
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t xs = smem_u32(s_ser + stage * stage_bytes);
+        const uint32_t dys = xs + xs_bytes;
+        for (int c = 0; c < DT_CG; ++c) {
+          const uint32_t tmem_d = tmem_base + c * 16;
+          // 1024 frames = 128 windows of 8 = 8 K-steps of 16 windows (256 B of either series per step)
+          for (int kc = 0; kc < DT_CHUNK / 128; ++kc) {
+            const uint64_t da = umma_desc_none(xs + c * p.ZL * 2 + kc * 256, 128, 16);
+            const uint64_t db = umma_desc_none(dys + c * DT_CHUNK * 2 + kc * 256, 128, 16);
+            umma_bf16(tmem_d, da, db, idesc, (it > 0 || kc > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      umma_commit(done_bar);
+    }
+  } else if (warp_idx < 4) {
+    if (has_items) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      const int tp = warp_idx * 32 + lane;  // t'
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < DT_CG; ++c) {
+        uint32_t v[8];
+        tmem_ld_32x32_x8(taddr + c * 16, v);
+        tmem_ld_wait();
+        if (c0 + c < p.C) {
+          // dw[j] += D[t + j, t]: this thread holds row t' = t + j
+          float* dst = p.dw + static_cast<size_t>(c0 + c) * p.K;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int j = tp - t;
+            if (j >= 0 && j < p.K) atomicAdd(dst + j, __uint_as_float(v[t]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+static void dt_schedule(DwTcParams& p) {
+  p.num_cg = cdiv(p.C, DT_CG);
+  p.t_chunks = cdiv(p.T, DT_CHUNK);
+  p.items_per_cg = p.N * p.t_chunks;
+  int per = kNumSMs / p.num_cg;
+  if (per < 1) per = 1;
+  if (per > p.items_per_cg) per = p.items_per_cg;
+  const int rounds = cdiv(p.items_per_cg, per);
+  p.ctas_per_cg = cdiv(p.items_per_cg, rounds);
+}
+
+int dwconv_tc_supported(int C, int K, int stride) {
+  static const bool off = getenv("LASR_DWCONV_FFMA") != nullptr;  // A/B switch: force the fp32-pipe kernels
+  return !off && stride == 1 && (C % DT_CG) == 0 && K >= 3 && (K & 1) && K + 7 <= DT_MAX_KS;
+}
+
+int dwconv_tc_fwd(const void* x, const float* w, void* y, const void* addend, int N, int T, int C, int K, int flip,
+                  cudaStream_t stream) {
+  DwTcParams p{};
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.w = w;
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.addend = static_cast<const __nv_bfloat16*>(addend);
+  p.N = N;
+  p.T = T;
+  p.C = C;
+  p.K = K;
+  p.KS = cdiv(K + 7, 16) * 16;
+  p.flip = flip;
+  p.ZL = DT_CHUNK + p.KS - 8;
+  dt_schedule(p);
+  int smem = 128 + DT_CG * (p.KS / 8) * 128 + 2 * DT_CG * p.ZL * 2 + 128;
+  if (smem < 116 * 1024) smem = 116 * 1024;  // one CTA per SM: each allocates all 512 TMEM columns
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    if (e != cudaSuccess) {
+      lasr_set_cuda_error(e);
+      return LASR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  dwconv_tc_fwd_kernel<<<p.num_cg * p.ctas_per_cg, DT_THREADS, smem, stream>>>(p);
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+int dwconv_tc_wgrad(const void* x, const void* dy, float* dw, int N, int T, int C, int K, cudaStream_t stream) {
+  DwTcParams p{};
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.dy = static_cast<const __nv_bfloat16*>(dy);
+  p.dw = dw;
+  p.N = N;
+  p.T = T;
+  p.C = C;
+  p.K = K;
+  p.KS = 0;
+  // rows t' = t + j <= 7 + K - 1 < 128; the x series must cover frames up to 8*127 + 127 of the chunk: 1024 + 128
+  p.ZL = DT_CHUNK + 128;
+  dt_schedule(p);
+  const int smem = 128 + 2 * (DT_CG * p.ZL * 2 + DT_CG * DT_CHUNK * 2) + 128;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e =
+        cudaFuncSetAttribute(dwconv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) {
+      lasr_set_cuda_error(e);
+      return LASR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  dwconv_tc_wgrad_kernel<<<p.num_cg * p.ctas_per_cg, DT_THREADS, smem, stream>>>(p);
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+}  // namespace lasr

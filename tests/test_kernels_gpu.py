@@ -24,7 +24,8 @@ def ntc(x):  # [N, C, T] -> [N, T, C]
 
 @pytest.mark.parametrize("dtype,tol", DTYPES)
 @pytest.mark.parametrize("C,K,stride,T", [(64, 33, 2, 401), (256, 33, 1, 501), (256, 39, 1, 130), (336, 51, 1, 257),
-                                           (512, 63, 1, 300), (512, 75, 1, 129), (512, 87, 1, 64), (256, 33, 1, 7)])
+                                           (512, 63, 1, 300), (512, 75, 1, 129), (512, 87, 1, 64), (256, 33, 1, 7),
+                                           (256, 33, 1, 1501), (512, 63, 1, 2100), (64, 87, 1, 1024)])
 def test_dwconv_fwd_wgrad_dgrad(ops, dtype, tol, C, K, stride, T):
     torch.manual_seed(C + K)
     N = 3
