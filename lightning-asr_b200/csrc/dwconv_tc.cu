@@ -37,8 +37,10 @@ namespace lasr {
 constexpr int DT_CG = 16;        // channels per CTA
 constexpr int DT_ROWS = 128;     // MMA M: windows of 8 frames
 constexpr int DT_CHUNK = 1024;   // output frames per item
-constexpr int DT_THREADS = 320;
+constexpr int DT_PROD_WARPS = 8;  // two groups of 4: group g fills series stage g
+constexpr int DT_THREADS = 32 * (6 + DT_PROD_WARPS);
 constexpr int DT_MAX_KS = 112;
+constexpr int DT_STAGES = 4;     // series buffers of the forward kernel
 
 struct DwTcParams {
   const __nv_bfloat16* x;
@@ -50,7 +52,21 @@ struct DwTcParams {
   int N, T, C, K, KS, flip;
   int num_cg, t_chunks, items_per_cg, ctas_per_cg;
   int ZL;  // series length in frames (multiple of 8)
+  unsigned long long* trace;  // debug timeline (tools/trace_dw.py), normally NULL
+  int exp;                    // debug: descriptor experiments (timing only, results are garbage when != 0)
 };
+
+__device__ __forceinline__ unsigned long long dt_gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define DT_TRACE(slot, idx)                                                                          \
+  do {                                                                                               \
+    if (p.trace != nullptr && (idx) < 16) p.trace[(blockIdx.x * 8 + (slot)) * 16 + (idx)] = dt_gtimer(); \
+  } while (0)
+static unsigned long long* g_dt_trace = nullptr;
+extern "C" void lasr_debug_set_dw_trace(unsigned long long* buf) { g_dt_trace = buf; }
 
 __device__ __forceinline__ uint64_t umma_desc_none(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -61,6 +77,20 @@ __device__ __forceinline__ uint64_t umma_desc_none(uint32_t smem_addr, uint32_t 
   return d;
 }
 
+__device__ __forceinline__ void umma_bf16_first(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32_x8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -68,30 +98,54 @@ __device__ __forceinline__ void tmem_ld_32x32_x8(uint32_t taddr, uint32_t (&v)[8
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32_x4(uint32_t taddr, uint32_t (&v)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void ldg_v8(const void* p, uint32_t (&a)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(void* p, const uint32_t (&a)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]),
+               "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7])
+               : "memory");
+}
+
 // global [frames, C] -> per-channel series in shared memory.  series[c][sigma] (bf16, pitch ZL) for sigma in
-// [0, ZL): frame f = f_base + sigma of utterance rows `src` (nullptr / out of [0, T): zero).  Called by 4 producer
-// warps (pw = 0..3); a warp handles 128 frames x 16 channels per pass.
+// [0, ZL): frame f = f_base + sigma of utterance rows `src` (out of [0, T): zero).  Called by the 4 warps of a producer
+// group (pw = 0..3); a warp handles 128 frames x 16 channels per pass and keeps the loads of ALL its passes (<= 3,
+// ZL <= 1536) in flight before transposing: the step is latency-bound otherwise.
 __device__ __forceinline__ void load_series(const __nv_bfloat16* __restrict__ src, int C, int T, int f_base, int ZL,
                                             uint8_t* series, int pw, int lane) {
   const int h = lane >> 4;    // channel half: channels 8h .. 8h+7
   const int b = lane & 15;    // 8-frame block within the pass
-  for (int s0 = pw * 128; s0 < ZL; s0 += 4 * 128) {
-    const int sigma = s0 + 8 * b;
-    if (sigma >= ZL) continue;
-    uint4 r[8];
+  uint4 r[3][8];
+#pragma unroll
+  for (int ps = 0; ps < 3; ++ps) {
+    const int sigma = (pw + 4 * ps) * 128 + 8 * b;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int f = f_base + sigma + i;
-      r[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (f >= 0 && f < T) r[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(f) * C + 8 * h));
+      r[ps][i] = make_uint4(0u, 0u, 0u, 0u);
+      if (sigma < ZL && f >= 0 && f < T)
+        r[ps][i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(f) * C + 8 * h));
     }
+  }
+#pragma unroll
+  for (int ps = 0; ps < 3; ++ps) {
+    const int sigma = (pw + 4 * ps) * 128 + 8 * b;
+    if (sigma >= ZL) continue;
     // 8 frames x 8 channels -> 8 channels x 8 frames
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       uint32_t o[4];
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
-        const uint32_t a = (&r[2 * m].x)[q >> 1], bb = (&r[2 * m + 1].x)[q >> 1];
+        const uint32_t a = (&r[ps][2 * m].x)[q >> 1], bb = (&r[ps][2 * m + 1].x)[q >> 1];
         o[m] = __byte_perm(a, bb, (q & 1) ? 0x7632 : 0x5410);
       }
       *reinterpret_cast<uint4*>(series + (static_cast<size_t>(8 * h + q) * ZL + sigma) * 2) =
@@ -107,13 +161,13 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_fwd_kernel(const DwTc
   const int cores = p.KS / 8;
   const int series_bytes = DT_CG * p.ZL * 2;
   uint8_t* s_toep = smem;                                   // [16][cores][128 B]
-  uint8_t* s_ser = s_toep + DT_CG * cores * 128;            // [2][16][ZL] bf16
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ser + 2 * series_bytes);
-  uint64_t* full_bar = bars;            // [2] producers -> MMA
-  uint64_t* empty_bar = bars + 2;       // [2] MMA -> producers
-  uint64_t* tmem_full_bar = bars + 4;   // [2] MMA -> epilogue
-  uint64_t* tmem_empty_bar = bars + 6;  // [2] epilogue -> MMA
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint8_t* s_ser = s_toep + DT_CG * cores * 128;            // [DT_STAGES][16][ZL] bf16
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ser + DT_STAGES * series_bytes);
+  uint64_t* full_bar = bars;                         // [DT_STAGES] producers -> MMA
+  uint64_t* empty_bar = bars + DT_STAGES;            // [DT_STAGES] MMA -> producers
+  uint64_t* tmem_full_bar = bars + 2 * DT_STAGES;    // [2] MMA -> epilogue
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2] epilogue -> MMA
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,9 +187,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_fwd_kernel(const DwTc
     reinterpret_cast<__nv_bfloat16*>(s_toep)[i] = __float2bfloat16_rn(v);
   }
   if (warp_idx == 4 && lane == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < DT_STAGES; ++s) {
       mbar_init(&full_bar[s], 4);
       mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], 4);
     }
@@ -152,44 +208,68 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_fwd_kernel(const DwTc
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp_idx >= 6) {
-    // ===================== producers =====================
-    const int pw = warp_idx - 6;
-    int it = 0;
-    for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
-      const int stage = it & 1;
-      const uint32_t phase = (it >> 1) & 1;
+    // ===================== producers: two groups of 4 warps take alternate items; with DT_STAGES = 4 series
+    // buffers a group loads item it+2 while the MMAs of item it+1 (the other group's) are still running ==========
+    const int pw = (warp_idx - 6) & 3;
+    const int grp = (warp_idx - 6) >> 2;
+    int it = grp;
+    for (int idx = first + grp * p.ctas_per_cg; idx < p.items_per_cg; idx += 2 * p.ctas_per_cg, it += 2) {
+      const int stage = it % DT_STAGES;
+      const uint32_t phase = (it / DT_STAGES) & 1;
       const int n = idx / p.t_chunks, tc = idx - n * p.t_chunks;
       mbar_wait(&empty_bar[stage], phase ^ 1u);
+      if (pw == 0 && lane == 0) DT_TRACE(0, it);
       load_series(p.x + static_cast<size_t>(n) * p.T * p.C + c0, p.C, p.T, tc * DT_CHUNK - P, p.ZL,
                   s_ser + stage * series_bytes, pw, lane);
       fence_proxy_async_smem();
       __syncwarp();
+      if (pw == 0 && lane == 0) DT_TRACE(1, it);
       if (lane == 0) mbar_arrive(&full_bar[stage]);
     }
   } else if (warp_idx == 4) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(DT_ROWS, 16, 0, 0);
       const int ksteps = p.KS / 16;
       int it = 0;
       for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
-        const int stage = it & 1;
-        const uint32_t phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[stage], phase ^ 1u);
+        const int stage = it % DT_STAGES;
+        const uint32_t phase = (it / DT_STAGES) & 1;
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        if (leader) DT_TRACE(2, it);
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t ser = smem_u32(s_ser + stage * series_bytes);
-        const uint32_t toep = smem_u32(s_toep);
+        if (leader) DT_TRACE(3, it);
+        // The issuing thread, not the tensor pipe, paces these small MMAs (N = 16): keep the loop to two 64-bit adds
+        // per instruction -- descriptors advance by 32 B (A: 16 frames) and 256 B (B: 2 cores) in their 16-byte address
+        // field.
+        uint64_t da_c = umma_desc_none(smem_u32(s_ser + stage * series_bytes), 16, 128);
+        uint64_t db_c = umma_desc_none(smem_u32(s_toep), 128, 128);
+        uint32_t tmem_d = tmem_base + acc * 256;
+        const uint64_t da_step = static_cast<uint64_t>(p.ZL * 2 >> 4), db_step = static_cast<uint64_t>(cores * 128 >> 4);
+#pragma unroll 1
         for (int c = 0; c < DT_CG; ++c) {
-          const uint32_t tmem_d = tmem_base + stage * 256 + c * 16;
-          for (int kc = 0; kc < ksteps; ++kc) {
-            const uint64_t da = umma_desc_none(ser + c * p.ZL * 2 + kc * 32, 16, 128);
-            const uint64_t db = umma_desc_none(toep + (c * cores + 2 * kc) * 128, 128, 128);
-            umma_bf16(tmem_d, da, db, idesc, kc > 0 ? 1u : 0u);
+          uint64_t da = da_c, db = db_c;
+          if (leader) umma_bf16_first(tmem_d, da, db, idesc);
+#pragma unroll 1
+          for (int kc = 1; kc < ksteps; ++kc) {
+            da += 2;
+            db += 16;
+            if (leader) umma_bf16_acc(tmem_d, da, db, idesc);
           }
+          da_c += da_step;
+          db_c += db_step;
+          tmem_d += 16;
         }
-        umma_commit(&empty_bar[stage]);
-        umma_commit(&tmem_full_bar[stage]);
+        if (leader) {
+          umma_commit(&empty_bar[stage]);
+          umma_commit(&tmem_full_bar[acc]);
+          DT_TRACE(4, it);
+        }
+        __syncwarp();
       }
     }
   } else if (warp_idx < 4) {
@@ -200,44 +280,54 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_fwd_kernel(const DwTc
       const int stage = it & 1;
       const uint32_t phase = (it >> 1) & 1;
       const int n = idx / p.t_chunks, tc = idx - n * p.t_chunks;
+      const int f0 = tc * DT_CHUNK + 8 * row;
+      const size_t off0 = (static_cast<size_t>(n) * p.T + f0) * p.C + c0;
+      // the residual-branch gradient this kernel adds (dgrad): fetched before waiting on the accumulator
+      uint32_t add[2][4][8];
+      if (p.addend != nullptr) {
+#pragma unroll
+        for (int th = 0; th < 2; ++th)
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) add[th][t][c] = 0u;
+            if (f0 + 4 * th + t < p.T) ldg_v8(p.addend + off0 + static_cast<size_t>(4 * th + t) * p.C, add[th][t]);
+          }
+      }
       mbar_wait(&tmem_full_bar[stage], phase);
       tc_fence_after();
+      if (threadIdx.x == 0) DT_TRACE(5, it);
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16) + stage * 256;
-      const int f0 = tc * DT_CHUNK + 8 * row;
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {  // 8 channels at a time: 64 accumulator registers
-        uint32_t v[8][8];
+      for (int th = 0; th < 2; ++th) {  // 4 frames x 16 channels at a time: one 32-byte store per frame
+        uint32_t v[DT_CG][4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) tmem_ld_32x32_x8(taddr + (half * 8 + c) * 16, v[c]);
+        for (int c = 0; c < DT_CG; ++c) tmem_ld_32x32_x4(taddr + c * 16 + 4 * th, v[c]);
         tmem_ld_wait();
-        if (c0 + half * 8 < p.C) {
 #pragma unroll
-          for (int t = 0; t < 8; ++t) {
-            const int f = f0 + t;
-            if (f < p.T) {
-              const size_t off = (static_cast<size_t>(n) * p.T + f) * p.C + c0 + half * 8;
-              float o[8];
+        for (int t = 0; t < 4; ++t) {
+          const int f = f0 + 4 * th + t;
+          if (f < p.T) {
+            const size_t off = off0 + static_cast<size_t>(4 * th + t) * p.C;
+            uint32_t u[8];
+            if (p.addend != nullptr) {
 #pragma unroll
-              for (int c = 0; c < 8; ++c) o[c] = __uint_as_float(v[c][t]);
-              if (p.addend != nullptr) {
-                const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.addend + off));
-                const float2 a0 = bf16x2_to_f32x2(a.x), a1 = bf16x2_to_f32x2(a.y), a2 = bf16x2_to_f32x2(a.z),
-                             a3 = bf16x2_to_f32x2(a.w);
-                o[0] += a0.x; o[1] += a0.y; o[2] += a1.x; o[3] += a1.y;
-                o[4] += a2.x; o[5] += a2.y; o[6] += a3.x; o[7] += a3.y;
+              for (int c = 0; c < 8; ++c) {
+                const float2 av = bf16x2_to_f32x2(add[th][t][c]);
+                u[c] = f32x2_to_bf16x2(__uint_as_float(v[2 * c][t]) + av.x, __uint_as_float(v[2 * c + 1][t]) + av.y);
               }
-              uint4 u;
-              u.x = f32x2_to_bf16x2(o[0], o[1]);
-              u.y = f32x2_to_bf16x2(o[2], o[3]);
-              u.z = f32x2_to_bf16x2(o[4], o[5]);
-              u.w = f32x2_to_bf16x2(o[6], o[7]);
-              *reinterpret_cast<uint4*>(p.y + off) = u;
+            } else {
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                u[c] = f32x2_to_bf16x2(__uint_as_float(v[2 * c][t]), __uint_as_float(v[2 * c + 1][t]));
             }
+            stg_v8(p.y + off, u);
           }
         }
       }
       tc_fence_before();
       __syncwarp();
+      if (threadIdx.x == 0) DT_TRACE(6, it);
       if (lane == 0) mbar_arrive(&tmem_empty_bar[stage]);
     }
   }
@@ -294,10 +384,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_wgrad_kernel(const Dw
   const bool has_items = first < p.items_per_cg;
 
   if (warp_idx >= 6) {
-    const int pw = warp_idx - 6;
-    int it = 0;
-    for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
-      const int stage = it & 1;
+    const int pw = (warp_idx - 6) & 3;
+    const int grp = (warp_idx - 6) >> 2;
+    int it = grp;
+    for (int idx = first + grp * p.ctas_per_cg; idx < p.items_per_cg; idx += 2 * p.ctas_per_cg, it += 2) {
+      const int stage = grp;
       const uint32_t phase = (it >> 1) & 1;
       const int n = idx / p.t_chunks, tc = idx - n * p.t_chunks;
       mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -310,8 +401,9 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_wgrad_kernel(const Dw
       if (lane == 0) mbar_arrive(&full_bar[stage]);
     }
   } else if (warp_idx == 4) {
-    if (lane == 0) {
+    {
       // D[t' (M = 128), t (N = 16)] += sum_w z[8w + t'] dy[8w + t]: A and B both MN-major
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(DT_ROWS, 16, 1, 1);
       int it = 0;
       for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
@@ -320,19 +412,34 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_wgrad_kernel(const Dw
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         const uint32_t xs = smem_u32(s_ser + stage * stage_bytes);
-        const uint32_t dys = xs + xs_bytes;
+        uint64_t da_c = umma_desc_none(xs, 128, 16);
+        uint64_t db_c = umma_desc_none(xs + xs_bytes, 128, 16);
+        uint32_t tmem_d = tmem_base;
+        const uint64_t da_step = static_cast<uint64_t>(p.ZL * 2 >> 4);
+#pragma unroll 1
         for (int c = 0; c < DT_CG; ++c) {
-          const uint32_t tmem_d = tmem_base + c * 16;
           // 1024 frames = 128 windows of 8 = 8 K-steps of 16 windows (256 B of either series per step)
-          for (int kc = 0; kc < DT_CHUNK / 128; ++kc) {
-            const uint64_t da = umma_desc_none(xs + c * p.ZL * 2 + kc * 256, 128, 16);
-            const uint64_t db = umma_desc_none(dys + c * DT_CHUNK * 2 + kc * 256, 128, 16);
-            umma_bf16(tmem_d, da, db, idesc, (it > 0 || kc > 0) ? 1u : 0u);
+          uint64_t da = da_c, db = db_c;
+          if (leader) {
+            if (it == 0)
+              umma_bf16_first(tmem_d, da, db, idesc);
+            else
+              umma_bf16_acc(tmem_d, da, db, idesc);
           }
+#pragma unroll
+          for (int kc = 1; kc < DT_CHUNK / 128; ++kc) {
+            da += 16;
+            db += 16;
+            if (leader) umma_bf16_acc(tmem_d, da, db, idesc);
+          }
+          da_c += da_step;
+          db_c += DT_CHUNK * 2 >> 4;
+          tmem_d += 16;
         }
-        umma_commit(&empty_bar[stage]);
+        if (leader) umma_commit(&empty_bar[stage]);
+        __syncwarp();
       }
-      umma_commit(done_bar);
+      if (leader) umma_commit(done_bar);
     }
   } else if (warp_idx < 4) {
     if (has_items) {
@@ -398,13 +505,15 @@ int dwconv_tc_fwd(const void* x, const float* w, void* y, const void* addend, in
   p.K = K;
   p.KS = cdiv(K + 7, 16) * 16;
   p.flip = flip;
+  p.trace = g_dt_trace;
+  p.exp = getenv("LASR_DW_EXP") ? atoi(getenv("LASR_DW_EXP")) : 0;
   p.ZL = DT_CHUNK + p.KS - 8;
   dt_schedule(p);
-  int smem = 128 + DT_CG * (p.KS / 8) * 128 + 2 * DT_CG * p.ZL * 2 + 128;
+  int smem = 128 + DT_CG * (p.KS / 8) * 128 + DT_STAGES * DT_CG * p.ZL * 2 + 128;
   if (smem < 116 * 1024) smem = 116 * 1024;  // one CTA per SM: each allocates all 512 TMEM columns
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(dwconv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 120 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(dwconv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) {
       lasr_set_cuda_error(e);
       return LASR_ERR_CUDA;
