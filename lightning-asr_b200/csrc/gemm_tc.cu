@@ -160,8 +160,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int num_tiles = tiles_mn * p.k_splits;
 
   if (warp_idx == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (converged warp, elected lane issues) =====================
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -175,21 +176,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
-          if constexpr (!A_MN) {
-            tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
-          } else {
+          if (leader) {
+            mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+            if constexpr (!A_MN) {
+              tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c)
-              tma_load_2d(sa + c * (64 * BK * 2), &tma_a, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
-          }
-          if constexpr (!B_MN) {
-            tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
-          } else {
+              for (int c = 0; c < BM / 64; ++c)
+                tma_load_2d(sa + c * (64 * BK * 2), &tma_a, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c)
-              tma_load_2d(sb + c * (64 * BK * 2), &tma_b, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
+              for (int c = 0; c < BN / 64; ++c)
+                tma_load_2d(sb + c * (64 * BK * 2), &tma_b, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -198,8 +202,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else if (warp_idx == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer: the whole warp stays converged (uniform loops, descriptors in uniform
+    // registers), one elected lane issues =====================
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -227,15 +233,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                                      : umma_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, 64 * BK * 2, 1024)
                                      : umma_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (leader) umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (leader) umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (leader) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else if (warp_idx >= 4) {
@@ -454,33 +462,40 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (threadIdx.x == 0) WS_TRACE(0, 1);
 
   if (warp_idx == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (converged warp, elected lane issues) =====================
+    {
+      const bool leader = elect_one();
       // the CTA's weight slice, once
-      mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(p.num_k_blocks) * WS_WKB_BYTES);
+      if (leader) mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(p.num_k_blocks) * WS_WKB_BYTES);
       for (int kb = 0; kb < p.num_k_blocks; ++kb) {
         uint8_t* dst = s_w + kb * WS_WKB_BYTES;
-        if constexpr (!B_MN) {
-          tma_load_2d(dst, &tma_b, w_bar, kb * WS_BK, n_blk * WS_BN);
-        } else {
+        if (leader) {
+          if constexpr (!B_MN) {
+            tma_load_2d(dst, &tma_b, w_bar, kb * WS_BK, n_blk * WS_BN);
+          } else {
 #pragma unroll
-          for (int c = 0; c < WS_BN / 64; ++c)
-            tma_load_2d(dst + c * (64 * WS_BK * 2), &tma_b, w_bar, n_blk * WS_BN + c * 64, kb * WS_BK);
+            for (int c = 0; c < WS_BN / 64; ++c)
+              tma_load_2d(dst + c * (64 * WS_BK * 2), &tma_b, w_bar, n_blk * WS_BN + c * 64, kb * WS_BK);
+          }
         }
       }
+      __syncwarp();
       int stage = 0;
       uint32_t phase = 0;
       for (int m_blk = m_first; m_blk < p.num_m_blocks; m_blk += p.ctas_per_n) {
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[stage], WS_A_BYTES);
-          if (p.cluster == 1) {
-            tma_load_2d(s_a + stage * WS_A_BYTES, &tma_a, &full_bar[stage], kb * WS_BK, m_blk * WS_BM);
-          } else {
-            // this CTA fetches its slice of rows and multicasts it; the peers deliver the other slices
-            tma_load_2d_mc(s_a + stage * WS_A_BYTES + crank * slice_rows * 128, &tma_a, &full_bar[stage], kb * WS_BK,
-                           m_blk * WS_BM + crank * slice_rows, mc_mask);
+          if (leader) {
+            mbar_arrive_expect_tx(&full_bar[stage], WS_A_BYTES);
+            if (p.cluster == 1) {
+              tma_load_2d(s_a + stage * WS_A_BYTES, &tma_a, &full_bar[stage], kb * WS_BK, m_blk * WS_BM);
+            } else {
+              // this CTA fetches its slice of rows and multicasts it; the peers deliver the other slices
+              tma_load_2d_mc(s_a + stage * WS_A_BYTES + crank * slice_rows * 128, &tma_a, &full_bar[stage],
+                             kb * WS_BK, m_blk * WS_BM + crank * slice_rows, mc_mask);
+            }
           }
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
@@ -489,12 +504,13 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     }
   } else if (warp_idx == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (converged warp, elected lane) =====================
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(WS_BM, WS_BN, 0, B_MN ? 1 : 0);
       mbar_wait(w_bar, 0);
       tc_fence_after();
-      WS_TRACE(0, 2);
+      if (leader) WS_TRACE(0, 2);
       int stage = 0;
       uint32_t phase = 0;
       int local_tile = 0;
@@ -503,12 +519,12 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const uint32_t acc_phase = (local_tile >> 1) & 1;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
         tc_fence_after();
-        WS_TRACE(1, local_tile);
+        if (leader) WS_TRACE(1, local_tile);
         const uint32_t tmem_d = tmem_base + acc * WS_BN;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          if (kb == 0) WS_TRACE(2, local_tile);
+          if (kb == 0 && leader) WS_TRACE(2, local_tile);
           const uint32_t sa = smem_u32(s_a + stage * WS_A_BYTES);
           const uint32_t sb = smem_u32(s_w + kb * WS_WKB_BYTES);
 #pragma unroll
@@ -516,19 +532,25 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, 64 * WS_BK * 2, 1024)
                                      : umma_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (leader) umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           }
-          if (p.cluster == 1)
-            umma_commit(&empty_bar[stage]);
-          else
-            umma_commit_mc(&empty_bar[stage], mc_mask);
+          if (leader) {
+            if (p.cluster == 1)
+              umma_commit(&empty_bar[stage]);
+            else
+              umma_commit_mc(&empty_bar[stage], mc_mask);
+          }
+          __syncwarp();
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tmem_full_bar[acc]);
-        WS_TRACE(3, local_tile);
+        if (leader) {
+          umma_commit(&tmem_full_bar[acc]);
+          WS_TRACE(3, local_tile);
+        }
+        __syncwarp();
       }
     }
   } else if (warp_idx >= 4 && warp_idx < 8) {

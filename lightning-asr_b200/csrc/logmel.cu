@@ -155,7 +155,8 @@ logmel_fwd_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_const
   const int kbs = p.products * LM_KB;
 
   if (warp_idx == 0) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -167,11 +168,14 @@ logmel_fwd_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_const
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* sa = smem + stage * LM_STAGE_BYTES;
             uint8_t* sb = sa + LM_A_BYTES;
-            mbar_arrive_expect_tx(&full_bar[stage], LM_STAGE_BYTES);
-            const int ap = p.pa[prod];
-            const CUtensorMap* ma = ap == 0 ? &tma_a0 : (ap == 1 ? &tma_a1 : &tma_a2);
-            tma_load_3d(sa, ma, &full_bar[stage], k0, t0, n);
-            tma_load_2d(sb, &tma_b, &full_bar[stage], k0, p.pb[prod] * LM_NFFT + half * LM_BN);
+            if (leader) {
+              mbar_arrive_expect_tx(&full_bar[stage], LM_STAGE_BYTES);
+              const int ap = p.pa[prod];
+              const CUtensorMap* ma = ap == 0 ? &tma_a0 : (ap == 1 ? &tma_a1 : &tma_a2);
+              tma_load_3d(sa, ma, &full_bar[stage], k0, t0, n);
+              tma_load_2d(sb, &tma_b, &full_bar[stage], k0, p.pb[prod] * LM_NFFT + half * LM_BN);
+            }
+            __syncwarp();
             if (++stage == LM_STAGES) {
               stage = 0;
               phase ^= 1u;
@@ -181,7 +185,8 @@ logmel_fwd_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_const
       }
     }
   } else if (warp_idx == 1) {
-    if (lane == 0) {
+    {
+      const bool leader = elect_one();
       constexpr uint32_t idesc = umma_idesc_bf16(LM_BM, LM_BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -202,15 +207,17 @@ logmel_fwd_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_const
             for (int k = 0; k < LM_BK / 16; ++k) {
               const uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
               const uint64_t db = umma_desc_sw128(sb + k * 32, 16, 1024);
-              umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              if (leader) umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
-            umma_commit(&empty_bar[stage]);
+            if (leader) umma_commit(&empty_bar[stage]);
+            __syncwarp();
             if (++stage == LM_STAGES) {
               stage = 0;
               phase ^= 1u;
             }
           }
-          umma_commit(&tmem_full_bar[acc]);
+          if (leader) umma_commit(&tmem_full_bar[acc]);
+          __syncwarp();
         }
       }
     }
