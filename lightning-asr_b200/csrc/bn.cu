@@ -219,6 +219,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
 #pragma unroll
   for (int i = 0; i < 8; ++i) sg[i] = sgy[i] = sgr[i] = 0.f;
   if (tr < rows_par) {
+#pragma unroll 2
     for (int t = t0 + tr; t < t1; t += rows_par) {
       const size_t off = (static_cast<size_t>(n) * T_len + t) * C + cv * 8;
       float g[8], o[8], yy[8], rr[8];
@@ -511,7 +512,21 @@ int lasr_bn_bwd_chunks(int N, int T) {
 int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, const void* r, double* totals,
                            float* per_n, int N, int T, int C, int act, int dtype, lasr_stream_t stream) {
   if (N <= 0 || T <= 0 || C <= 0 || (C % 8) || C > 2048 || totals == nullptr) return LASR_ERR_BAD_SHAPE;
-  const int chunks = lasr_bn_bwd_chunks(N, T);
+  // Without per-utterance sums (no SE) the rows are one flat [N*T, C] matrix: two fat CTAs per SM instead of 4 thin
+  // ones per SM and utterance halve the fp64 REDs that all land on the same 3*C addresses.
+  if (per_n == nullptr) {
+    const long long rows = static_cast<long long>(N) * T;
+    if (rows < (1ll << 30)) {
+      T = static_cast<int>(rows);
+      N = 1;
+    }
+  }
+  int chunks = lasr_bn_bwd_chunks(N, T);
+  if (N == 1) {
+    chunks = 2 * kNumSMs;
+    if (chunks > cdiv(T, 8)) chunks = cdiv(T, 8);
+    chunks = cdiv(T, cdiv(T, chunks));
+  }
   const int rows_per_chunk = cdiv(T, chunks);
   const int CV = C / 8;
   const int rows_par = 256 / CV;

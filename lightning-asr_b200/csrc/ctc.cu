@@ -189,6 +189,9 @@ ctc_lattice_kernel(const T* __restrict__ x, const float* __restrict__ lse, const
   for (int step = 1; step < Tn; ++step) {
     cp_async_wait<CTC_RING - 2>();  // this thread's words of frame `step` have landed
     __syncthreads();                // previous column (and the lse word) visible to everyone
+    // refill the ring slot consumed by the previous iteration now: the address arithmetic and the cp.async issue then
+    // overlap the shared-memory latency of this frame's recursion instead of extending the critical path
+    issue(step - 1 + CTC_RING);
     const int t = t_first + dt * step;
     const float* prev = col[cur];
     float* next = col[cur ^ 1];
@@ -211,7 +214,6 @@ ctc_lattice_kernel(const T* __restrict__ x, const float* __restrict__ lse, const
       }
     }
     cur ^= 1;
-    issue(step - 1 + CTC_RING);  // slot (step-1) % RING was consumed by the previous iteration
   }
   cp_async_wait<0>();
   __syncthreads();
