@@ -115,14 +115,52 @@ def kernel_breakdown(engine, steps=3):
 
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: an NVML polling thread (5 ms period; the timed
+    region is only ~100 ms long, nvidia-smi's 100 ms loop would see one or two samples).  Falls back to an
+    `nvidia-smi -lms` child process if NVML cannot be opened."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index = index
         self.proc = None
+        self.thread = None
+        self.samples = []
+        self.smax = 0.0
+        self.reason_bits = 0
+        self._stop = False
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
+
+    def _poll(self, nv, h):
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import threading
+
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nv = nv
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -131,6 +169,19 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            nv = self.nv
+            names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                     ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                     ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                     ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)]
+            if not self.samples:
+                return None
+            return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.smax,
+                    "reasons": sorted(n for n, bit in names if self.reason_bits & bit), "samples": len(self.samples),
+                    "source": "nvml, 5 ms period, during the timed regions"}
         if self.proc is None:
             return None
         self.proc.terminate()
@@ -156,7 +207,8 @@ class ClockSampler:
         if not sm:
             return None
         busy = [v for v in sm if v > 0.5 * max(sm)] or sm
-        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -300,10 +352,15 @@ def run_b200(args):
 
     # ---- per-kernel breakdown with CUDA events (eager, after the timed region) ----
     fam, calls = kernel_breakdown(engine, steps=3)
+    if world > 1:
+        # every rank is done with the device; leave together.  The process group is NOT torn down explicitly: with
+        # NCCL all-reduces captured in a live CUDA graph destroy_process_group() can block forever, so the ranks
+        # simply exit (os._exit below) once rank 0 has printed its line.
+        barrier()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     total_ms = sum(d["ms"] for d in fam.values())
     top = max(fam.items(), key=lambda kv: kv[1]["ms"])
     tname, t = top
@@ -346,9 +403,10 @@ def run_b200(args):
         "gpu_launches": calls * args.steps, "roofline": roof, "cpu_baseline": cb, "clocks": clocks,
         "loss": loss_val,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

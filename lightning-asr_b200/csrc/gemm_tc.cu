@@ -50,6 +50,9 @@ struct GemmTcCfg {
   static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  // weight-gradient epilogue: per epilogue warp two 32 x 32 fp32 staging tiles handed to the TMA reduce-add unit
+  static constexpr int RED_STG_BYTES = 4 * 2 * 4096;
+  static constexpr int SMEM_BYTES_RED = SMEM_BYTES + RED_STG_BYTES;
 };
 
 // warp-level transpose-reduce: on entry lane r holds f[0..31] (row r, 32 columns); on exit every lane j
@@ -113,7 +116,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const GemmTcParams p) {
+               const __grid_constant__ CUtensorMap tma_c, const GemmTcParams p) {
   using Cfg = GemmTcCfg<BN>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
   constexpr int A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
@@ -122,7 +125,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   // 128B-swizzled tiles need 1024-byte aligned bases
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  constexpr int RED_STG = (EPI == 1) ? Cfg::RED_STG_BYTES : 0;
+  uint8_t* s_red = smem + STAGES * STAGE_BYTES;  // [4 warps][2][32 rows x 128 B], 1024-byte aligned (EPI == 1)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + RED_STG);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -134,6 +139,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
+    if (EPI == 1) tma_prefetch_desc(&tma_c);
   }
   if (warp_idx == 1 && lane == 0) {
 #pragma unroll
@@ -250,6 +256,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ===================== epilogue =====================
     const int ew = warp_idx - 4;  // == warp_idx % 4: the TMEM lane quarter this warp may access
     int local_tile = 0;
+    int nred = 0;  // staging tiles this warp has handed to the TMA reduce unit (EPI == 1)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
       const int split = tile / tiles_mn;
       const int mn = tile - split * tiles_mn;
@@ -332,16 +339,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
         } else {
-          if (row_ok) {
-            float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc + col0;
-            if ((col0 + 32 <= p.N) && p.vec_ok) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) red_add_v4(dst + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) atomicAdd(dst + j, f[j]);
+          if (p.vec_ok) {
+            // split-K reduction through the TMA unit: the warp's 32 x 32 fp32 sub-tile goes to a 128B-swizzled staging
+            // buffer and ONE bulk reduce-add covers it with full 128-byte lines (a per-thread RED.v4 touches 32
+            // half-used sectors per instruction and 150-300 CTAs walk the same addresses in the same order); rows
+            // and columns outside [M, N) are clipped by the tensor map
+            uint8_t* buf = s_red + ew * 8192 + (nred & 1) * 4096;
+            if (nred >= 2) {
+              if (lane == 0) tma_store_wait_read<1>();  // the reduce issued from this buffer two chunks ago has read it
+              __syncwarp();
             }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              *reinterpret_cast<float4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+                  make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_2d(&tma_c, buf, col0, m_blk * BM + ew * 32);
+              tma_store_commit();
+            }
+            ++nred;
+          } else if (row_ok) {
+            float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) atomicAdd(dst + j, f[j]);
           }
         }
       }
@@ -349,6 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
+    if (EPI == 1 && lane == 0) tma_store_wait<0>();
   }
 
   tc_fence_before();
@@ -698,6 +722,21 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t dim0, uint64_
   return r == CUDA_SUCCESS ? LASR_OK : LASR_ERR_DRIVER;
 }
 
+int make_tmap_2d_f32(CUtensorMap* out, const void* base, uint64_t dim0, uint64_t dim1, uint64_t pitch_bytes,
+                     uint32_t box0, uint32_t box1, bool swizzle128) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (fn == nullptr) return LASR_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0) return LASR_ERR_ALIGNMENT;
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? LASR_OK : LASR_ERR_DRIVER;
+}
+
 // rank-N bf16 tensor map, dim0 contiguous; strides_bytes has rank-1 entries (dims 1..rank-1); 128B swizzle optional
 int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                       const uint32_t* box, bool swizzle128) {
@@ -724,19 +763,20 @@ int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p, int grid,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const CUtensorMap* tc = nullptr) {
   using Cfg = GemmTcCfg<BN>;
+  constexpr int kSmem = EPI == 1 ? Cfg::SMEM_BYTES_RED : Cfg::SMEM_BYTES;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, A_MN, B_MN, EPI>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) {
       lasr_set_cuda_error(e);
       return LASR_ERR_CUDA;
     }
     configured = true;
   }
-  gemm_tc_kernel<BN, A_MN, B_MN, EPI><<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+  gemm_tc_kernel<BN, A_MN, B_MN, EPI><<<grid, 256, kSmem, stream>>>(ta, tb, tc != nullptr ? *tc : ta, p);
   LASR_CHECK_LAUNCH();
   return LASR_OK;
 }
@@ -947,7 +987,9 @@ int gemm_tc_tn_accum(const void* dy, const void* x, float* dw, int R, int Cout, 
   p.num_n_blocks = cdiv(Cin, BN);
   p.num_k_blocks = cdiv(R, 64);
   const int tiles = p.num_m_blocks * p.num_n_blocks;
-  int splits = (2 * kNumSMs) / tiles;
+  // one tile per CTA: every extra split adds a full Cout x Cin pass of L2 reductions
+  static const int split_mult = getenv("LASR_WGRAD_SPLIT_MULT") ? atoi(getenv("LASR_WGRAD_SPLIT_MULT")) : 1;
+  int splits = (split_mult * kNumSMs) / tiles;
   if (splits < 1) splits = 1;
   if (splits > p.num_k_blocks) splits = p.num_k_blocks;
   p.kb_per_split = cdiv(p.num_k_blocks, splits);
@@ -955,13 +997,20 @@ int gemm_tc_tn_accum(const void* dy, const void* x, float* dw, int R, int Cout, 
   p.out = dw;
   p.ldc = lddw;
   p.out_f32 = 1;
-  p.vec_ok = ((reinterpret_cast<uintptr_t>(dw) & 15) == 0) && ((static_cast<size_t>(lddw) * 4) % 16 == 0);
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(dw) & 15) == 0) && ((static_cast<size_t>(lddw) * 4) % 16 == 0) && Cin >= 32;
+  static const bool no_tma_red = getenv("LASR_WGRAD_NO_TMA_REDUCE") != nullptr;
+  if (no_tma_red) p.vec_ok = 0;
+  CUtensorMap tc = ta;
+  if (p.vec_ok) {
+    rc = make_tmap_2d_f32(&tc, dw, Cin, Cout, static_cast<uint64_t>(lddw) * 4, 32, 32, true);
+    if (rc) return rc;
+  }
   const int total = tiles * p.k_splits;
   const int grid = total < kNumSMs ? total : kNumSMs;
   switch (BN) {
-    case 64: return launch_inst<64, true, true, 1>(ta, tb, p, grid, stream);
-    case 128: return launch_inst<128, true, true, 1>(ta, tb, p, grid, stream);
-    default: return launch_inst<256, true, true, 1>(ta, tb, p, grid, stream);
+    case 64: return launch_inst<64, true, true, 1>(ta, tb, p, grid, stream, &tc);
+    case 128: return launch_inst<128, true, true, 1>(ta, tb, p, grid, stream, &tc);
+    default: return launch_inst<256, true, true, 1>(ta, tb, p, grid, stream, &tc);
   }
 }
 
