@@ -57,6 +57,12 @@ const char* lasr_strerror(int code);
 int lasr_abi_version(void);
 /* compute capability check: returns LASR_OK only on an sm_100 device */
 int lasr_check_device(void);
+/* Caller's promise about PARAMETER tensors (conv weights / taps and their bf16 shadows) passed to the kernels: with
+ * on != 0 they were last written before a full stream-order barrier (e.g. by the step prologue: memset + cast +
+ * layout kernels), so kernels launched with programmatic dependent launch may prefetch them while the previous
+ * kernel is still draining.  Default 0: parameters are read only after the previous kernel has completed, like every
+ * other operand.  Returns the previous setting.  (The reference has no counterpart: torch's stream order covers it.) */
+int lasr_set_early_param_loads(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * Layout conversion at the module boundary.

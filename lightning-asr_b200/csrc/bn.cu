@@ -16,11 +16,15 @@ template <typename T>
 struct Vec8;
 template <>
 struct Vec8<__nv_bfloat16> {
-  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
+  // Raw = the bits as loaded: kernels issue the loads of several vectors first and unpack afterwards, so every thread
+  // keeps 4-8 independent 16-byte requests in flight (the passes are pure HBM streams)
+  using Raw = uint4;
+  static __device__ __forceinline__ Raw ldraw(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& u, float (&v)[8]) {
     float2 a = bf16x2_to_f32x2(u.x), b = bf16x2_to_f32x2(u.y), c = bf16x2_to_f32x2(u.z), d = bf16x2_to_f32x2(u.w);
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
   }
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) { unpack(ldraw(p), v); }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
     uint4 u;
     u.x = f32x2_to_bf16x2(v[0], v[1]);
@@ -32,11 +36,19 @@ struct Vec8<__nv_bfloat16> {
 };
 template <>
 struct Vec8<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
-    const float4 a = *reinterpret_cast<const float4*>(p);
-    const float4 b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  struct Raw {
+    float4 a, b;
+  };
+  static __device__ __forceinline__ Raw ldraw(const float* p) {
+    Raw r;
+    r.a = *reinterpret_cast<const float4*>(p);
+    r.b = *reinterpret_cast<const float4*>(p + 4);
+    return r;
   }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) { unpack(ldraw(p), v); }
   static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
@@ -53,24 +65,48 @@ __device__ __forceinline__ void lds8(const float* p, float (&v)[8]) { Vec8<float
 // CTA 0 also stores mean / invstd for the backward and updates the running statistics (momentum, unbiased variance)
 // and num_batches_tracked.  Eval mode (sums == NULL) reads the running statistics instead.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bn_coeffs(const lasr_bn_t& bn, int c, int C, double count, float eps, float& scale,
-                                          float& shift, float& mean_f, float& invstd_f, double& var_out) {
-  double mean, var;
+// Raw inputs of one channel's coefficients: loaded up front (one memory round trip for both BatchNorms of a pass)
+struct BnRaw {
+  double s1, s2;
+  float gamma, beta;
+};
+__device__ __forceinline__ BnRaw bn_load_raw(const lasr_bn_t& bn, int c, int C) {
+  BnRaw r;
   if (bn.sums != nullptr) {
-    mean = bn.sums[c] / count;
-    var = bn.sums[C + c] / count - mean * mean;
+    r.s1 = bn.sums[c];
+    r.s2 = bn.sums[C + c];
+  } else {
+    r.s1 = bn.running_mean[c];
+    r.s2 = bn.running_var[c];
+  }
+  r.gamma = bn.gamma[c];
+  r.beta = bn.beta[c];
+  return r;
+}
+// no fp64 divisions or square roots (software sequences of ~50 dependent instructions each): 1/count comes from the
+// host, 1/sqrt is rsqrt (<= 1 ulp in double, the results are rounded to fp32 anyway)
+__device__ __forceinline__ void bn_coeffs_raw(const BnRaw& r, bool batch, double inv_count, float eps, float& scale,
+                                              float& shift, float& mean_f, float& invstd_f, double& var_out) {
+  double mean, var;
+  if (batch) {
+    mean = r.s1 * inv_count;
+    var = r.s2 * inv_count - mean * mean;
     if (var < 0.0) var = 0.0;
   } else {
-    mean = bn.running_mean[c];
-    var = bn.running_var[c];
+    mean = r.s1;
+    var = r.s2;
   }
-  const double invstd = 1.0 / sqrt(var + static_cast<double>(eps));
-  const double g = bn.gamma[c], b = bn.beta[c];
+  const double invstd = rsqrt(var + static_cast<double>(eps));
+  const double g = r.gamma, b = r.beta;
   scale = static_cast<float>(g * invstd);
   shift = static_cast<float>(b - mean * g * invstd);
   mean_f = static_cast<float>(mean);
   invstd_f = static_cast<float>(invstd);
   var_out = var;
+}
+__device__ __forceinline__ void bn_coeffs(const lasr_bn_t& bn, int c, int C, double count, float eps, float& scale,
+                                          float& shift, float& mean_f, float& invstd_f, double& var_out) {
+  bn_coeffs_raw(bn_load_raw(bn, c, C), bn.sums != nullptr, 1.0 / count, eps, scale, shift, mean_f, invstd_f, var_out);
 }
 
 __device__ __forceinline__ void bn_side_effects(const lasr_bn_t& bn, int c, double count, float momentum, float mean_f,
@@ -105,65 +141,85 @@ __global__ void bn_coeffs_kernel(const lasr_bn_t bn, int C, double count, float 
 // persistent CTAs of 512 threads; smem: scale1, shift1, scale2, shift2 [C] each
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool HAS_R, bool HAS_GATE>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 bn_apply_fwd_kernel(const T* __restrict__ y, const lasr_bn_t bn1, const T* __restrict__ r, const lasr_bn_t bn2,
                     const float* __restrict__ gate, T* __restrict__ out, long long total_vec, int CV, int C, int T_len,
                     double count, float eps, float momentum, int act, int side_effects) {
+  pdl_launch_dependents();
+  pdl_wait();  // the statistics come from the GEMM right before this pass
   extern __shared__ float coef_s[];  // [4][C]
   float* s_scale1 = coef_s;
   float* s_shift1 = coef_s + C;
   float* s_scale2 = coef_s + 2 * C;
   float* s_shift2 = coef_s + 3 * C;
+  const double inv_count = 1.0 / count;  // one division per thread, overlapped with the loads below
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const BnRaw r1 = bn_load_raw(bn1, c, C);
+    BnRaw r2{};
+    if constexpr (HAS_R) r2 = bn_load_raw(bn2, c, C);
     float sc, sh, mf, isf;
     double var;
-    bn_coeffs(bn1, c, C, count, eps, sc, sh, mf, isf, var);
+    bn_coeffs_raw(r1, bn1.sums != nullptr, inv_count, eps, sc, sh, mf, isf, var);
     s_scale1[c] = sc;
     s_shift1[c] = sh;
     if (blockIdx.x == 0 && side_effects) bn_side_effects(bn1, c, count, momentum, mf, isf, var);
     if constexpr (HAS_R) {
-      bn_coeffs(bn2, c, C, count, eps, sc, sh, mf, isf, var);
+      bn_coeffs_raw(r2, bn2.sums != nullptr, inv_count, eps, sc, sh, mf, isf, var);
       s_scale2[c] = sc;
       s_shift2[c] = sh;
       if (blockIdx.x == 0 && side_effects) bn_side_effects(bn2, c, count, momentum, mf, isf, var);
     }
   }
   __syncthreads();
-  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total_vec;
-       v += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = v / CV;
-    const int c = static_cast<int>(v - row * CV) * 8;
-    const size_t off = static_cast<size_t>(row) * C + c;
-    float a[8], o[8];
-    Vec8<T>::load(y + off, a);
-    float rr[8];
-    if constexpr (HAS_R) Vec8<T>::load(r + off, rr);
-    {
-      float sc[8], sh[8];
-      lds8(s_scale1 + c, sc);
-      lds8(s_shift1 + c, sh);
+  using Raw = typename Vec8<T>::Raw;
+  constexpr int U = sizeof(T) == 2 ? 4 : 2;  // vectors per thread and trip, all loads issued before the first use
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long v0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v0 < total_vec; v0 += U * stride) {
+    Raw ya[U], ra[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaf(a[i], sc[i], sh[i]);
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * stride;
+      if (v < total_vec) {
+        ya[u] = Vec8<T>::ldraw(y + v * 8);  // element offset row*C + c == 8*v
+        if constexpr (HAS_R) ra[u] = Vec8<T>::ldraw(r + v * 8);
+      }
     }
-    if constexpr (HAS_GATE) {
-      const int n = static_cast<int>(row / T_len);
-      float g[8];
-      load8f(gate + static_cast<size_t>(n) * C + c, g);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] *= g[i];
-    }
-    if constexpr (HAS_R) {
-      float sc[8], sh[8];
-      lds8(s_scale2 + c, sc);
-      lds8(s_shift2 + c, sh);
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * stride;
+      if (v >= total_vec) break;
+      const long long row = v / CV;
+      const int c = static_cast<int>(v - row * CV) * 8;
+      float a[8], o[8];
+      Vec8<T>::unpack(ya[u], a);
+      {
+        float sc[8], sh[8];
+        lds8(s_scale1 + c, sc);
+        lds8(s_shift1 + c, sh);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += fmaf(rr[i], sc[i], sh[i]);
-    }
-    if (act == LASR_ACT_RELU) {
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(a[i], sc[i], sh[i]);
+      }
+      if constexpr (HAS_GATE) {
+        const int n = static_cast<int>(row / T_len);
+        float g[8];
+        load8f(gate + static_cast<size_t>(n) * C + c, g);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+        for (int i = 0; i < 8; ++i) o[i] *= g[i];
+      }
+      if constexpr (HAS_R) {
+        float rr[8], sc[8], sh[8];
+        Vec8<T>::unpack(ra[u], rr);
+        lds8(s_scale2 + c, sc);
+        lds8(s_shift2 + c, sh);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] += fmaf(rr[i], sc[i], sh[i]);
+      }
+      if (act == LASR_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
+      }
+      Vec8<T>::store(out + v * 8, o);
     }
-    Vec8<T>::store(out + off, o);
   }
 }
 
@@ -208,6 +264,8 @@ __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, const T* __restrict__ y,
                      const T* __restrict__ r, double* __restrict__ totals, float* __restrict__ per_n, int T_len, int C,
                      int chunks, int rows_per_chunk, int act) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];  // [rows_par][3][C]
   const int n = blockIdx.x / chunks, k = blockIdx.x - n * chunks;
   const int CV = C / 8;
@@ -219,26 +277,48 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
 #pragma unroll
   for (int i = 0; i < 8; ++i) sg[i] = sgy[i] = sgr[i] = 0.f;
   if (tr < rows_par) {
-#pragma unroll 2
-    for (int t = t0 + tr; t < t1; t += rows_par) {
-      const size_t off = (static_cast<size_t>(n) * T_len + t) * C + cv * 8;
-      float g[8], o[8], yy[8], rr[8];
-      Vec8<T>::load(dout + off, g);
-      Vec8<T>::load(y + off, yy);
-      if (act == LASR_ACT_RELU) Vec8<T>::load(out + off, o);
-      if constexpr (HAS_R) Vec8<T>::load(r + off, rr);
-      if (act == LASR_ACT_RELU) {
+    using Raw = typename Vec8<T>::Raw;
+    constexpr int U = sizeof(T) == 2 ? 2 : 1;  // rows per trip: up to 8 independent 16-byte loads in flight per thread
+    const T* base_g = dout + static_cast<size_t>(n) * T_len * C + cv * 8;
+    const T* base_y = y + static_cast<size_t>(n) * T_len * C + cv * 8;
+    const T* base_o = out + static_cast<size_t>(n) * T_len * C + cv * 8;
+    const T* base_r = HAS_R ? r + static_cast<size_t>(n) * T_len * C + cv * 8 : nullptr;
+    const bool relu = act == LASR_ACT_RELU;
+    for (int tt = t0 + tr; tt < t1; tt += U * rows_par) {
+      Raw gr[U], yr[U], orr[U], rrr[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+      for (int u = 0; u < U; ++u) {
+        const int t = tt + u * rows_par;
+        if (t < t1) {
+          const size_t off = static_cast<size_t>(t) * C;
+          gr[u] = Vec8<T>::ldraw(base_g + off);
+          yr[u] = Vec8<T>::ldraw(base_y + off);
+          if (relu) orr[u] = Vec8<T>::ldraw(base_o + off);
+          if constexpr (HAS_R) rrr[u] = Vec8<T>::ldraw(base_r + off);
+        }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        sg[i] += g[i];
-        sgy[i] = fmaf(g[i], yy[i], sgy[i]);
-      }
-      if constexpr (HAS_R) {
+      for (int u = 0; u < U; ++u) {
+        const int t = tt + u * rows_par;
+        if (t >= t1) break;
+        float g[8], o[8], yy[8], rr[8];
+        Vec8<T>::unpack(gr[u], g);
+        Vec8<T>::unpack(yr[u], yy);
+        if (relu) {
+          Vec8<T>::unpack(orr[u], o);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sgr[i] = fmaf(g[i], rr[i], sgr[i]);
+          for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sg[i] += g[i];
+          sgy[i] = fmaf(g[i], yy[i], sgy[i]);
+        }
+        if constexpr (HAS_R) {
+          Vec8<T>::unpack(rrr[u], rr);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sgr[i] = fmaf(g[i], rr[i], sgr[i]);
+        }
       }
     }
     float* dst = red + static_cast<size_t>(tr) * 3 * C + cv * 8;
@@ -263,10 +343,11 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
 __device__ __forceinline__ void bn_bwd_coef(double a, double b, double count, float gamma, float mean, float invstd,
                                             float& c0, float& c1, float& c2, float& dgamma, float& dbeta) {
   const double mu = mean, is = invstd, ga = gamma;
+  const double inv_count = 1.0 / count;
   const double dga = is * (b - mu * a);
   const double k0 = ga * is;
-  const double k1 = -ga * is * is * dga / count;
-  const double k2 = -ga * is * a / count - k1 * mu;
+  const double k1 = -ga * is * is * dga * inv_count;
+  const double k2 = -ga * is * a * inv_count - k1 * mu;
   c0 = static_cast<float>(k0);
   c1 = static_cast<float>(k1);
   c2 = static_cast<float>(k2);
@@ -302,23 +383,41 @@ struct BnBwdSide {
 };
 
 template <typename T, bool HAS_R, bool HAS_GATE>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const T* __restrict__ y,
                     const T* __restrict__ r, const float* __restrict__ gate, const float* __restrict__ extra,
                     const double* __restrict__ totals, const float* __restrict__ coef1_in, const BnBwdSide bn1,
                     const BnBwdSide bn2, double count, const int32_t* __restrict__ lengths, int T_len,
                     T* __restrict__ dy, T* __restrict__ dr, long long total_vec, int CV, int C, int act) {
+  pdl_launch_dependents();
+  pdl_wait();  // totals come from the reduce pass right before
   extern __shared__ float coef_s[];  // coef1 [3][C], coef2 [3][C]
   float* k1 = coef_s;
   float* k2 = coef_s + 3 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float c0, c1, c2, dg, db;
+    // all global loads of this channel first: one round trip instead of one per BatchNorm
+    double t_a = 0.0, t_b1 = 0.0, t_b2 = 0.0;
+    float g1 = 0.f, m1 = 0.f, i1 = 0.f, g2 = 0.f, m2 = 0.f, i2 = 0.f;
+    if (totals != nullptr) t_a = totals[c];
+    if (coef1_in == nullptr) {
+      t_b1 = totals[C + c];
+      g1 = bn1.gamma[c];
+      m1 = bn1.mean[c];
+      i1 = bn1.invstd[c];
+    }
+    if constexpr (HAS_R) {
+      t_b2 = totals[2 * C + c];
+      g2 = bn2.gamma[c];
+      m2 = bn2.mean[c];
+      i2 = bn2.invstd[c];
+    }
     if (coef1_in != nullptr) {
       k1[c] = coef1_in[c];
       k1[C + c] = coef1_in[C + c];
       k1[2 * C + c] = coef1_in[2 * C + c];
     } else {
-      bn_bwd_coef(totals[c], totals[C + c], count, bn1.gamma[c], bn1.mean[c], bn1.invstd[c], c0, c1, c2, dg, db);
+      bn_bwd_coef(t_a, t_b1, count, g1, m1, i1, c0, c1, c2, dg, db);
       k1[c] = c0;
       k1[C + c] = c1;
       k1[2 * C + c] = c2;
@@ -328,7 +427,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
       }
     }
     if constexpr (HAS_R) {
-      bn_bwd_coef(totals[c], totals[2 * C + c], count, bn2.gamma[c], bn2.mean[c], bn2.invstd[c], c0, c1, c2, dg, db);
+      bn_bwd_coef(t_a, t_b2, count, g2, m2, i2, c0, c1, c2, dg, db);
       k2[c] = c0;
       k2[C + c] = c1;
       k2[2 * C + c] = c2;
@@ -339,53 +438,77 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
     }
   }
   __syncthreads();
-  for (long long v = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v < total_vec;
-       v += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long row = v / CV;
-    const int c = static_cast<int>(v - row * CV) * 8;
-    const size_t off = static_cast<size_t>(row) * C + c;
-    const int n = static_cast<int>(row / T_len);
-    const int t = static_cast<int>(row - static_cast<long long>(n) * T_len);
-    const bool keep = lengths == nullptr || t < lengths[n];
-    float g[8], yy[8], rr[8];
-    Vec8<T>::load(dout + off, g);
-    float o[8];
-    if (act == LASR_ACT_RELU) Vec8<T>::load(out + off, o);
-    if constexpr (HAS_R) Vec8<T>::load(r + off, rr);
-    if (keep) Vec8<T>::load(y + off, yy);
-    if (act == LASR_ACT_RELU) {
+  using Raw = typename Vec8<T>::Raw;
+  constexpr int U = sizeof(T) == 2 ? 2 : 1;
+  const bool relu = act == LASR_ACT_RELU;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long v0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v0 < total_vec; v0 += U * stride) {
+    Raw gr[U], orr[U], yr[U], rrr[U];
+    bool keep_u[U];
+    int n_u[U], c_u[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
-    }
-    if constexpr (HAS_R) {
-      float a0[8], a1[8], a2[8], d[8];
-      lds8(k2 + c, a0);
-      lds8(k2 + C + c, a1);
-      lds8(k2 + 2 * C + c, a2);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = fmaf(a0[i], g[i], fmaf(a1[i], rr[i], a2[i]));
-      Vec8<T>::store(dr + off, d);
-    }
-    float d[8];
-    if (keep) {
-      if constexpr (HAS_GATE) {
-        float gt[8], ex[8];
-        load8f(gate + static_cast<size_t>(n) * C + c, gt);
-        load8f(extra + static_cast<size_t>(n) * C + c, ex);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = fmaf(g[i], gt[i], ex[i]);
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * stride;
+      keep_u[u] = false;
+      if (v < total_vec) {
+        const long long row = v / CV;
+        c_u[u] = static_cast<int>(v - row * CV) * 8;
+        n_u[u] = static_cast<int>(row / T_len);
+        const int t = static_cast<int>(row - static_cast<long long>(n_u[u]) * T_len);
+        keep_u[u] = lengths == nullptr || t < lengths[n_u[u]];
+        gr[u] = Vec8<T>::ldraw(dout + v * 8);
+        if (relu) orr[u] = Vec8<T>::ldraw(out + v * 8);
+        if constexpr (HAS_R) rrr[u] = Vec8<T>::ldraw(r + v * 8);
+        if (keep_u[u]) yr[u] = Vec8<T>::ldraw(y + v * 8);
       }
-      float a0[8], a1[8], a2[8];
-      lds8(k1 + c, a0);
-      lds8(k1 + C + c, a1);
-      lds8(k1 + 2 * C + c, a2);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = fmaf(a0[i], g[i], fmaf(a1[i], yy[i], a2[i]));
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d[i] = 0.f;
     }
-    Vec8<T>::store(dy + off, d);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * stride;
+      if (v >= total_vec) break;
+      const int c = c_u[u], n = n_u[u];
+      const bool keep = keep_u[u];
+      float g[8];
+      Vec8<T>::unpack(gr[u], g);
+      if (relu) {
+        float o[8];
+        Vec8<T>::unpack(orr[u], o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+      }
+      if constexpr (HAS_R) {
+        float rr[8], a0[8], a1[8], a2[8], d[8];
+        Vec8<T>::unpack(rrr[u], rr);
+        lds8(k2 + c, a0);
+        lds8(k2 + C + c, a1);
+        lds8(k2 + 2 * C + c, a2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = fmaf(a0[i], g[i], fmaf(a1[i], rr[i], a2[i]));
+        Vec8<T>::store(dr + v * 8, d);
+      }
+      float d[8];
+      if (keep) {
+        float yy[8];
+        Vec8<T>::unpack(yr[u], yy);
+        if constexpr (HAS_GATE) {
+          float gt[8], ex[8];
+          load8f(gate + static_cast<size_t>(n) * C + c, gt);
+          load8f(extra + static_cast<size_t>(n) * C + c, ex);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = fmaf(g[i], gt[i], ex[i]);
+        }
+        float a0[8], a1[8], a2[8];
+        lds8(k1 + c, a0);
+        lds8(k1 + C + c, a1);
+        lds8(k1 + 2 * C + c, a2);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = fmaf(a0[i], g[i], fmaf(a1[i], yy[i], a2[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = 0.f;
+      }
+      Vec8<T>::store(dy + v * 8, d);
+    }
   }
 }
 
@@ -405,15 +528,16 @@ static int bn_fwd_launch(const void* y, const lasr_bn_t& b1, const void* r, cons
   const TT* rr = static_cast<const TT*>(r);
   TT* oo = static_cast<TT*>(out);
 #define LASR_BN_FWD_ARGS yy, b1, rr, b2, gate, oo, total, CV, C, T, count, eps, momentum, act, side_effects
+  cudaError_t le;
   if (r != nullptr && gate != nullptr)
-    bn_apply_fwd_kernel<TT, true, true><<<grid, 512, smem, stream>>>(LASR_BN_FWD_ARGS);
+    le = launch_pdl(4, bn_apply_fwd_kernel<TT, true, true>, dim3(grid), dim3(512), smem, stream, LASR_BN_FWD_ARGS);
   else if (r != nullptr)
-    bn_apply_fwd_kernel<TT, true, false><<<grid, 512, smem, stream>>>(LASR_BN_FWD_ARGS);
+    le = launch_pdl(4, bn_apply_fwd_kernel<TT, true, false>, dim3(grid), dim3(512), smem, stream, LASR_BN_FWD_ARGS);
   else if (gate != nullptr)
-    bn_apply_fwd_kernel<TT, false, true><<<grid, 512, smem, stream>>>(LASR_BN_FWD_ARGS);
+    le = launch_pdl(4, bn_apply_fwd_kernel<TT, false, true>, dim3(grid), dim3(512), smem, stream, LASR_BN_FWD_ARGS);
   else
-    bn_apply_fwd_kernel<TT, false, false><<<grid, 512, smem, stream>>>(LASR_BN_FWD_ARGS);
-  LASR_CHECK_LAUNCH();
+    le = launch_pdl(4, bn_apply_fwd_kernel<TT, false, false>, dim3(grid), dim3(512), smem, stream, LASR_BN_FWD_ARGS);
+  LASR_CHECK_PDL(le);
   return LASR_OK;
 }
 
@@ -431,15 +555,16 @@ static int bn_bwd_launch(const void* dout, const void* out, const void* y, const
   TT* o0 = static_cast<TT*>(dy);
   TT* o1 = static_cast<TT*>(dr);
 #define LASR_BN_BWD_ARGS a0, a1, a2, a3, gate, extra, totals, coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, act
+  cudaError_t le;
   if (r != nullptr && gate != nullptr)
-    bn_bwd_apply_kernel<TT, true, true><<<grid, 512, smem, stream>>>(LASR_BN_BWD_ARGS);
+    le = launch_pdl(4, bn_bwd_apply_kernel<TT, true, true>, dim3(grid), dim3(512), smem, stream, LASR_BN_BWD_ARGS);
   else if (r != nullptr)
-    bn_bwd_apply_kernel<TT, true, false><<<grid, 512, smem, stream>>>(LASR_BN_BWD_ARGS);
+    le = launch_pdl(4, bn_bwd_apply_kernel<TT, true, false>, dim3(grid), dim3(512), smem, stream, LASR_BN_BWD_ARGS);
   else if (gate != nullptr)
-    bn_bwd_apply_kernel<TT, false, true><<<grid, 512, smem, stream>>>(LASR_BN_BWD_ARGS);
+    le = launch_pdl(4, bn_bwd_apply_kernel<TT, false, true>, dim3(grid), dim3(512), smem, stream, LASR_BN_BWD_ARGS);
   else
-    bn_bwd_apply_kernel<TT, false, false><<<grid, 512, smem, stream>>>(LASR_BN_BWD_ARGS);
-  LASR_CHECK_LAUNCH();
+    le = launch_pdl(4, bn_bwd_apply_kernel<TT, false, false>, dim3(grid), dim3(512), smem, stream, LASR_BN_BWD_ARGS);
+  LASR_CHECK_PDL(le);
   return LASR_OK;
 }
 
@@ -532,16 +657,17 @@ int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, con
   const int rows_par = 256 / CV;
   const int smem = rows_par * 3 * C * static_cast<int>(sizeof(float));
   const int grid = N * chunks;
+  cudaError_t le = cudaSuccess;
 #define LASR_BN_RED_LAUNCH(TT)                                                                                     \
   do {                                                                                                             \
     if (r != nullptr)                                                                                              \
-      bn_bwd_reduce_kernel<TT, true><<<grid, 256, smem, stream>>>(                                                 \
-          static_cast<const TT*>(dout), static_cast<const TT*>(out), static_cast<const TT*>(y),                    \
-          static_cast<const TT*>(r), totals, per_n, T, C, chunks, rows_per_chunk, act);                            \
+      le = launch_pdl(4, bn_bwd_reduce_kernel<TT, true>, dim3(grid), dim3(256), smem, stream,                         \
+                      static_cast<const TT*>(dout), static_cast<const TT*>(out), static_cast<const TT*>(y),        \
+                      static_cast<const TT*>(r), totals, per_n, T, C, chunks, rows_per_chunk, act);                \
     else                                                                                                           \
-      bn_bwd_reduce_kernel<TT, false><<<grid, 256, smem, stream>>>(                                                \
-          static_cast<const TT*>(dout), static_cast<const TT*>(out), static_cast<const TT*>(y),                    \
-          static_cast<const TT*>(r), totals, per_n, T, C, chunks, rows_per_chunk, act);                            \
+      le = launch_pdl(4, bn_bwd_reduce_kernel<TT, false>, dim3(grid), dim3(256), smem, stream,                        \
+                      static_cast<const TT*>(dout), static_cast<const TT*>(out), static_cast<const TT*>(y),        \
+                      static_cast<const TT*>(r), totals, per_n, T, C, chunks, rows_per_chunk, act);                \
   } while (0)
   if (dtype == LASR_F32)
     LASR_BN_RED_LAUNCH(float);
@@ -549,7 +675,7 @@ int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, con
     LASR_BN_RED_LAUNCH(__nv_bfloat16);
   else
     return LASR_ERR_BAD_DTYPE;
-  LASR_CHECK_LAUNCH();
+  LASR_CHECK_PDL(le);
   return LASR_OK;
 }
 

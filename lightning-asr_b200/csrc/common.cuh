@@ -18,6 +18,45 @@ void lasr_set_cuda_error(cudaError_t e);
 
 namespace lasr {
 
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  A training step is ~190 short kernels (10-40 us) in one stream / one CUDA graph:
+// with plain stream order every kernel pays its launch latency and its prologue (barrier init, TMEM allocation,
+// tensor-map fetch) after the previous grid has fully drained.  Kernels launched through launch_pdl() may start as
+// soon as every CTA of the previous kernel has executed pdl_launch_dependents() (first statement of each kernel); they
+// run their prologue and then block in pdl_wait() until the previous grid has completed and flushed.  Rules:
+//   * a kernel launched with launch_pdl() MUST execute pdl_wait() in every thread before its first global-memory
+//     access that another kernel of the stream may have produced, or may still read (transitivity of the chain
+//     relies on every link waiting);
+//   * nothing before pdl_wait() may write global memory.
+// LASR_NO_PDL=1 turns the attribute off (plain stream order) for A/B runs.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled(int family);  // family bit in LASR_PDL_MASK: 1 GEMM, 2 depthwise, 4 BatchNorm, 8 CTC
+bool early_param_loads();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(int family, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled(family) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define LASR_CHECK_PDL(expr)                                       \
+  do {                                                             \
+    cudaError_t e__ = (expr);                                      \
+    if (e__ != cudaSuccess) { lasr_set_cuda_error(e__); return LASR_ERR_CUDA; } \
+  } while (0)
+
 static constexpr int kNumSMs = 148;
 
 __host__ __device__ __forceinline__ int cdiv(int a, int b) { return (a + b - 1) / b; }

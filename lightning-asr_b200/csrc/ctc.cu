@@ -96,6 +96,8 @@ __global__ void __launch_bounds__(CTC_THREADS)
 ctc_lattice_kernel(const T* __restrict__ x, const float* __restrict__ lse, const int64_t* __restrict__ targets,
                    const int32_t* __restrict__ in_len, const int32_t* __restrict__ tgt_len, float* __restrict__ alpha,
                    float* __restrict__ beta, float* __restrict__ nll, int T_len, int ldx, int S_max, int blank) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   const int n = blockIdx.x;
   const bool backward = blockIdx.y == 1;
@@ -233,6 +235,8 @@ ctc_grad_kernel(const T* __restrict__ x, const float* __restrict__ lse, const in
                 const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ nll,
                 const float* __restrict__ grad_out, GT* __restrict__ grad, int N, int T_len, int V, int ldx, int ldg,
                 int S_max, int blank, int warps) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float occ_all[];  // [warps][V]
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * warps + w;
@@ -374,10 +378,9 @@ static int ctc_grad_launch(const void* x, const float* lse, const int64_t* targe
   }
   const long long rows = static_cast<long long>(N) * Tn;
   const int grid = static_cast<int>((rows + warps - 1) / warps);
-  ctc_grad_kernel<T, GT><<<grid, 256, smem, stream>>>(static_cast<const T*>(x), lse, targets, il, tl, alpha, beta, nll,
-                                                      grad_out, static_cast<GT*>(grad), N, Tn, V, ldx, ldg, S_max,
-                                                      blank, warps);
-  LASR_CHECK_LAUNCH();
+  LASR_CHECK_PDL(launch_pdl(8, ctc_grad_kernel<T, GT>, dim3(grid), dim3(256), smem, stream, static_cast<const T*>(x), lse,
+                            targets, il, tl, alpha, beta, nll, grad_out, static_cast<GT*>(grad), N, Tn, V, ldx, ldg,
+                            S_max, blank, warps));
   return LASR_OK;
 }
 
@@ -399,9 +402,8 @@ static int ctc_lattice_launch(const void* x, const float* lse, const int64_t* ta
     configured = true;
   }
   dim3 grid(N, beta != nullptr ? 2 : 1);
-  ctc_lattice_kernel<T, SPT, CTC_THREADS><<<grid, CTC_THREADS, smem, stream>>>(
-      static_cast<const T*>(x), lse, targets, il, tl, alpha, beta, nll, T_len, ldx, S_max, blank);
-  LASR_CHECK_LAUNCH();
+  LASR_CHECK_PDL(launch_pdl(8, ctc_lattice_kernel<T, SPT, CTC_THREADS>, grid, dim3(CTC_THREADS), smem, stream,
+                            static_cast<const T*>(x), lse, targets, il, tl, alpha, beta, nll, T_len, ldx, S_max, blank));
   return LASR_OK;
 }
 

@@ -54,6 +54,7 @@ struct DwTcParams {
   int ZL;  // series length in frames (multiple of 8)
   unsigned long long* trace;  // debug timeline (tools/trace_dw.py), normally NULL
   int exp;                    // debug: descriptor experiments (timing only, results are garbage when != 0)
+  int w_early;                // taps may be read before griddepcontrol.wait (lasr_set_early_param_loads)
 };
 
 __device__ __forceinline__ unsigned long long dt_gtimer() {
@@ -155,6 +156,8 @@ __device__ __forceinline__ void load_series(const __nv_bfloat16* __restrict__ sr
 }
 
 __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_fwd_kernel(const DwTcParams p) {
+  pdl_launch_dependents();  // the Toeplitz build / TMEM allocation below overlap the previous kernel's tail; taps are
+                            // parameters (written behind a full stream barrier), see common.cuh
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((128u - (raw_addr & 127u)) & 127u);
@@ -176,6 +179,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_fwd_kernel(const DwTc
   const int c0 = cg * DT_CG;
   const int P = p.K / 2;
 
+  if (!p.w_early) pdl_wait();
   // Toeplitz cores: core kk, row r (= output frame t of the window), element e: w[8 kk + e - r]
   for (int i = threadIdx.x; i < DT_CG * cores * 64; i += DT_THREADS) {
     const int c = i / (cores * 64);
@@ -206,6 +210,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_fwd_kernel(const DwTc
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp_idx >= 6) {
     // ===================== producers: two groups of 4 warps take alternate items; with DT_STAGES = 4 series
@@ -344,6 +349,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_fwd_kernel(const DwTc
 // weight gradient
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_wgrad_kernel(const DwTcParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((128u - (raw_addr & 127u)) & 127u);
@@ -381,6 +387,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_wgrad_kernel(const Dw
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
   const bool has_items = first < p.items_per_cg;
 
   if (warp_idx >= 6) {
@@ -507,6 +514,7 @@ int dwconv_tc_fwd(const void* x, const float* w, void* y, const void* addend, in
   p.flip = flip;
   p.trace = g_dt_trace;
   p.exp = getenv("LASR_DW_EXP") ? atoi(getenv("LASR_DW_EXP")) : 0;
+  p.w_early = early_param_loads() ? 1 : 0;
   p.ZL = DT_CHUNK + p.KS - 8;
   dt_schedule(p);
   int smem = 128 + DT_CG * (p.KS / 8) * 128 + DT_STAGES * DT_CG * p.ZL * 2 + 128;
@@ -520,8 +528,7 @@ int dwconv_tc_fwd(const void* x, const float* w, void* y, const void* addend, in
     }
     configured = true;
   }
-  dwconv_tc_fwd_kernel<<<p.num_cg * p.ctas_per_cg, DT_THREADS, smem, stream>>>(p);
-  LASR_CHECK_LAUNCH();
+  LASR_CHECK_PDL(launch_pdl(2, dwconv_tc_fwd_kernel, dim3(p.num_cg * p.ctas_per_cg), dim3(DT_THREADS), smem, stream, p));
   return LASR_OK;
 }
 
@@ -549,8 +556,7 @@ int dwconv_tc_wgrad(const void* x, const void* dy, float* dw, int N, int T, int 
     }
     configured = true;
   }
-  dwconv_tc_wgrad_kernel<<<p.num_cg * p.ctas_per_cg, DT_THREADS, smem, stream>>>(p);
-  LASR_CHECK_LAUNCH();
+  LASR_CHECK_PDL(launch_pdl(2, dwconv_tc_wgrad_kernel, dim3(p.num_cg * p.ctas_per_cg), dim3(DT_THREADS), smem, stream, p));
   return LASR_OK;
 }
 

@@ -121,6 +121,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
   constexpr int A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
 
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte aligned bases
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -161,6 +162,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();  // prologue above overlapped the previous kernel; operands and outputs are touched only from here on
 
   const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
   const int num_tiles = tiles_mn * p.k_splits;
@@ -404,6 +406,7 @@ struct GemmWsParams {
   int ctas_per_n;
   int stages;
   int cluster;  // CTAs per cluster = num_n_blocks when the activation tiles are multicast, else 1
+  int w_early;  // weight slice may be fetched before griddepcontrol.wait (lasr_set_early_param_loads)
   const float* bias;
   const int32_t* lengths;
   int T;
@@ -435,6 +438,7 @@ template <bool B_MN>
 __global__ void __launch_bounds__(384, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_c, const GemmWsParams p) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -484,11 +488,16 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int slice_rows = WS_BM / p.cluster;
   const int crank = p.cluster > 1 ? static_cast<int>(cluster_ctarank()) : 0;
   if (threadIdx.x == 0) WS_TRACE(0, 1);
+  // Programmatic dependent launch: everything above, and the weight-slice load below, overlaps the tail of the previous
+  // kernel.  Weights are safe to read early: parameters and their bf16 shadows are only written by kernels that never
+  // trigger their dependents early (cast_weight, the optimizer), i.e. behind a full stream-order barrier.
+  if (warp_idx != 0) pdl_wait();
 
   if (warp_idx == 0) {
     // ===================== TMA producer (converged warp, elected lane issues) =====================
     {
       const bool leader = elect_one();
+      if (!p.w_early) pdl_wait();
       // the CTA's weight slice, once
       if (leader) mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(p.num_k_blocks) * WS_WKB_BYTES);
       for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -504,6 +513,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
       }
       __syncwarp();
+      pdl_wait();  // activations come from the previous kernel
       int stage = 0;
       uint32_t phase = 0;
       for (int m_blk = m_first; m_blk < p.num_m_blocks; m_blk += p.ctas_per_n) {
@@ -776,8 +786,8 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmT
     }
     configured = true;
   }
-  gemm_tc_kernel<BN, A_MN, B_MN, EPI><<<grid, 256, kSmem, stream>>>(ta, tb, tc != nullptr ? *tc : ta, p);
-  LASR_CHECK_LAUNCH();
+  LASR_CHECK_PDL(launch_pdl(1, gemm_tc_kernel<BN, A_MN, B_MN, EPI>, dim3(grid), dim3(256), kSmem, stream, ta, tb,
+                            tc != nullptr ? *tc : ta, p));
   return LASR_OK;
 }
 
@@ -830,6 +840,7 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
   p.T = T;
   p.stats = stats;
   p.trace = g_ws_trace;
+  p.w_early = early_param_loads() ? 1 : 0;
   const int smem = 1024 + 512 + kbs * WS_WKB_BYTES + stages * WS_A_BYTES + WS_STG_BYTES;
   static bool configured = false;
   if (!configured) {
@@ -846,13 +857,15 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
   cfg.blockDim = dim3(384);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cluster;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled(1) ? 2 : 1;
   if (cluster > 1) {
     // clusters must be co-resident (persistent kernel): cap the grid at what the GPCs can hold at once
     static int max_clusters[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};

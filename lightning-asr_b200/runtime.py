@@ -101,11 +101,16 @@ _BANK = {"bank": None}
 
 
 def install(bank):
+    """Make `bank` the step runtime.  From here on parameters and their bf16 shadows are only written by the step
+    prologue (memset + cast launches, full stream-order barriers), so the kernels may prefetch them under programmatic
+    dependent launch (include/lasr.h: lasr_set_early_param_loads)."""
     _BANK["bank"] = bank
+    _lib.load().lasr_set_early_param_loads(1)
 
 
 def uninstall():
     _BANK["bank"] = None
+    _lib.load().lasr_set_early_param_loads(0)
 
 
 def current():
