@@ -78,6 +78,8 @@ def algorithmic(name, a, has):
     if name == "lasr_bn_act_bwd_apply":  # count, T, M, C, act, dtype; ptrs dout,out,y,r,...
         _, T, M, C, act, dt = a
         return "bn_pass", es(dt) * M * C * ((4 if act else 3) + (2 if has[3] else 0)), 6.0 * M * C
+    if name == "lasr_novograd_step":  # reads p, g, m; writes p, m (+ bf16 shadow): 22 B per parameter element
+        return "novograd", 0, 0.0
     return name.replace("lasr_", ""), 0, 0.0
 
 
@@ -292,7 +294,8 @@ def run_b200(args):
         ddp.broadcast_parameters(module)
     batch = synthetic_batch(n, seconds, len(labels), seed=1234 + rank, ragged=False)
     use_graph = not args.no_graph and "context" not in model_name  # the BiLSTM splice syncs lengths to the host
-    engine = TrainEngine(module, batch, graph=use_graph, fused=True, world_sync=(None, 8.0) if world > 1 else None)
+    engine = TrainEngine(module, batch, graph=use_graph, fused=True, world_sync=(None, 8.0) if world > 1 else None,
+                         optimizer=None if args.no_optimizer else "novograd")
     graph_note = use_graph
     try:
         for _ in range(max(args.warmup, 3)):
@@ -395,7 +398,8 @@ def run_b200(args):
         "scaling": "weak", "vs_baseline": None, "dtype": precision, "data": "synthetic",
         "config": {"workload": args.workload, "model_name": model_name, "per_gpu_batch": n, "seconds": seconds,
                    "frames": T, "encoder_steps": Tp, "vocab": len(labels) + 1, "mask": True, "parallelism": f"dp{world}",
-                   "step": "forward + CTC + backward" + (" + NCCL grad all-reduce" if world > 1 else ""),
+                   "step": "forward + CTC + backward" + (" + NCCL grad all-reduce" if world > 1 else "")
+                           + ("" if args.no_optimizer else " + fused Novograd/LR-schedule update"),
                    "cuda_graph": bool(graph_note),
                    "l2": "no flush needed: each step streams ~8 GB of activations >> 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": engine.h2d_bytes,
@@ -418,6 +422,7 @@ def main():
     ap.add_argument("--workload", default="asr13x1_b32_16s_bf16", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-optimizer", action="store_true", help="time fwd+bwd only (diagnostics; not the headline)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

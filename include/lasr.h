@@ -259,6 +259,30 @@ int lasr_greedy_decode(const void* x, const int32_t* lengths, int64_t* argmax, i
 int lasr_ctc_collapse(const int64_t* predictions, const int32_t* lengths, int32_t* tokens, int32_t* counts, int N,
                       int T, int blank, lasr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Novograd optimizer step + cosine-annealing-with-warm-restarts schedule over flat buffers.
+ * Replaces scheduler/novograd.py:75-145 (Novograd.step, betas=(0.8, 0.5), weight decay added after the layer-wise
+ * normalisation, train.py:46) and scheduler/cosine_annearing_with_warmup.py:53-89 (per-step LR schedule, train.py:53-55).
+ *   params / grads / exp_avg   flat fp32 buffers of the same length (runtime.ParamBank layout), 16-byte aligned
+ *   shadow_bf16                nullable: bf16 copy of params refreshed in the same pass
+ *   chunk_off/len/param        [num_chunks] int32: consecutive pieces (<= a few thousand elements, offsets multiple of
+ *                              4) that each lie inside ONE parameter tensor, and that tensor's index
+ *   norms                      [num_params] fp64, ZEROED by the caller: receives |grad_p|^2
+ *   exp_avg_sq, denom          [num_params] fp32: second-moment state (0 = uninitialised, like the reference) / scratch
+ *   sched                      nullable device struct: when given, the step uses sched->lr and then advances the
+ *                              schedule like CosineAnnealingWarmupRestarts.step(); when NULL the scalar `lr` is used
+ *   lr_use                     [1] fp32 scratch (the learning rate this step applied; readable afterwards)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  double base_max_lr, max_lr, min_lr, cycle_mult, gamma, lr;
+  int32_t first_cycle_steps, cur_cycle_steps, warmup_steps, cycle, step_in_cycle, last_epoch;
+} lasr_lr_sched_t;
+int lasr_novograd_step(float* params, const float* grads, float* exp_avg, void* shadow_bf16, const int32_t* chunk_off,
+                       const int32_t* chunk_len, const int32_t* chunk_param, int num_chunks, double* norms,
+                       float* exp_avg_sq, float* denom, int num_params, lasr_lr_sched_t* sched, float* lr_use,
+                       float lr, float beta1, float beta2, float eps, float weight_decay, int grad_averaging,
+                       lasr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

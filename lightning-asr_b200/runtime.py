@@ -22,7 +22,8 @@ _ALIGN = 64  # elements: keeps bf16 views 128-byte and fp32 views 256-byte align
 
 class ParamBank:
     def __init__(self, module, arena_bytes=16 << 20):
-        params = [p for p in module.parameters()]
+        # a module, or (optim.Novograd without an engine) a plain list of parameters
+        params = [p for p in (module.parameters() if hasattr(module, "parameters") else module)]
         if not params or not params[0].is_cuda:
             raise _lib.LasrError("ParamBank needs a module that already lives on the GPU")
         self.device = params[0].device
@@ -44,6 +45,7 @@ class ParamBank:
         self.arena_high = 0
         self.armed = False
         self.shadow_fresh = False
+        self.shadow_synced = False  # set by optim.Novograd: its update pass already rewrote the bf16 shadows
         self.on_grad_ready = None  # callable(param) installed by ddp.GradSync
         with torch.no_grad():
             for p in params:
@@ -55,10 +57,13 @@ class ParamBank:
 
     # -- per-step protocol -----------------------------------------------------------------------------------
     def begin_step(self):
-        """One memset (gradients + arena) and one cast (bf16 weight shadows)."""
+        """One memset (gradients + arena) and one cast (bf16 weight shadows; skipped when the fused optimizer of the
+        previous step already refreshed them)."""
         self._zeroed.zero_()
         self._arena_off = 0
-        _lib.call("lasr_cast_weight", self.master, self.shadow, 1, self.numel, 0, _lib.LASR_BF16)
+        if not self.shadow_synced:
+            _lib.call("lasr_cast_weight", self.master, self.shadow, 1, self.numel, 0, _lib.LASR_BF16)
+        self.shadow_synced = False
         self.shadow_fresh = True
         self.armed = True
         for p in self.params:  # an optimizer or user code may have replaced .grad
@@ -69,6 +74,11 @@ class ParamBank:
     def end_step(self):
         self.armed = False
         self.shadow_fresh = False  # the optimizer is about to change the masters
+
+    def invalidate_shadow(self):
+        """Call after changing parameters behind the runtime's back (load_state_dict, manual edits)."""
+        self.shadow_synced = False
+        self.shadow_fresh = False
 
     # -- services --------------------------------------------------------------------------------------------
     def zeros(self, shape, dtype):

@@ -77,6 +77,19 @@ class LightingModule(nn.Module):
     def log(self, name, value, **_):
         self.logged[name] = value
 
+    def configure_optimizers(self, steps_per_epoch=1000, bank=None):
+        """train.py:36-62: Novograd(lr, weight_decay, betas=(0.8, 0.5)) + CosineAnnealingWarmupRestarts stepped once
+        per optimizer step.  Returns the same ([optimizer], [{'scheduler', 'interval', 'monitor'}]) pair; the schedule
+        is also attached to the fused optimizer so the per-step LR update happens on the device."""
+        from .optim import CosineAnnealingWarmupRestarts, Novograd
+        novo_optim = Novograd(self.parameters(), lr=self.learning_rate, weight_decay=self.weight_decay,
+                              betas=(0.8, 0.5), bank=bank)
+        lr_scheduler = CosineAnnealingWarmupRestarts(novo_optim, first_cycle_steps=self.total_epoch * steps_per_epoch,
+                                                     cycle_mult=2, max_lr=self.learning_rate, min_lr=1e-4,
+                                                     warmup_steps=1000, gamma=0.5)
+        novo_optim.attach_schedule(lr_scheduler)
+        return [novo_optim], [{"scheduler": lr_scheduler, "interval": "step", "monitor": "val_loss"}]
+
     def forward(self, inputs, percentage):
         return self.encoder(inputs, percentage)  # :34
 
@@ -135,6 +148,10 @@ class TrainEngine:
         self.dev = torch.device("cuda", torch.cuda.current_device())
         self.bank = runtime.ParamBank(module)
         runtime.install(self.bank)
+        if optimizer == "novograd":  # the reference's configure_optimizers (train.py:36-62) over this engine's bank
+            optimizer = module.configure_optimizers(bank=self.bank)[0][0]
+        elif callable(optimizer) and not isinstance(optimizer, torch.optim.Optimizer):
+            optimizer = optimizer(self.bank)
         self.optimizer = optimizer
         self.grad_sync = grad_sync
         if world_sync is not None:  # (group, bucket_mb): build the gradient exchange over the bank's flat buffer
@@ -162,9 +179,9 @@ class TrainEngine:
         loss.backward()
         if self.grad_sync is not None:
             self.grad_sync(m)
-        self.bank.end_step()
         if self.optimizer is not None:
-            self.optimizer.step()
+            self.optimizer.step()  # optim.Novograd: three launches over the flat buffers, arena still armed
+        self.bank.end_step()
         self.loss_dev.copy_(loss.detach())
 
     def _capture(self):

@@ -69,3 +69,24 @@ def ctc_inputs(name):
     in_len = torch.tensor([T, T - 3, T // 2, 3][:N])
     tg_len = torch.tensor([S, S - 2, 1, 5][:N])  # v29's last utterance is infeasible (5 labels in 3 frames) -> inf
     return lp, targets, in_len, tg_len, V - 1
+
+
+class optim_case:
+    """Seeded parameters / gradients for the optimizer fixtures (tests/golden/make_golden_optim.py)."""
+    SHAPES = [(64, 32, 1), (32, 1, 33), (64,), (29, 130, 1), (29,), (7,)]
+    SNAP_STEPS = (0, 1, 4, 9)
+    # name: (Novograd kwargs, scheduler kwargs or None, steps)
+    CASES = {
+        "train_py": (dict(lr=5e-3, weight_decay=1e-4, betas=(0.8, 0.5)),  # train.py:46, conf/conf.yaml:21-22
+                     dict(first_cycle_steps=6, cycle_mult=2, max_lr=5e-3, min_lr=1e-4, warmup_steps=2, gamma=0.5), 24),
+        "fixed_lr_avg": (dict(lr=1e-2, weight_decay=0.0, betas=(0.95, 0.98), grad_averaging=True), None, 5),
+    }
+
+    @staticmethod
+    def params():
+        return [torch.randn(s, generator=_gen(f"optim.p{i}")) * 0.1 for i, s in enumerate(optim_case.SHAPES)]
+
+    @staticmethod
+    def grads(step):
+        return [torch.randn(s, generator=_gen(f"optim.g{i}.{step}")) * (0.01 + 0.003 * i)
+                for i, s in enumerate(optim_case.SHAPES)]

@@ -113,3 +113,30 @@ def test_mask_lengths_truncation():
     x = torch.ones(4, 2, 801)
     y = quartznet_oracle.mask_cnn(x, p)
     assert y.sum(dim=(1, 2)).tolist() == [1602.0, 1600.0, 800.0, 2.0]
+
+
+def test_optimizer_oracle_matches_reference():
+    """oracle/optim_oracle.py vs tests/golden/optim.pt (the reference's own Novograd + CosineAnnealingWarmupRestarts)."""
+    from golden_common import optim_case
+    from oracle import optim_oracle
+
+    fx = _load("optim.pt")
+    for name, (hyper, sched, steps) in optim_case.CASES.items():
+        params = optim_case.params()
+        state = [{} for _ in params]
+        sch = optim_oracle.CosineWarmupOracle(**sched) if sched else None
+        h = dict(hyper)
+        lr0 = h.pop("lr")
+        snaps = dict(fx[name]["snaps"])
+        for k in range(steps):
+            lr = sch.lr if sch else lr0
+            assert abs(lr - fx[name]["lrs"][k]) <= 1e-15
+            optim_oracle.novograd_step(params, optim_case.grads(k), state, lr, **h)
+            if sch:
+                sch.step()
+            if k in snaps:
+                for a, b in zip(params, snaps[k]):
+                    assert torch.allclose(a, b, rtol=1e-6, atol=1e-8), (name, k)
+        for st, v, m in zip(state, fx[name]["exp_avg_sq"], fx[name]["exp_avg"]):
+            assert abs(float(st["exp_avg_sq"]) - v) <= 1e-6 * abs(v)
+            assert torch.allclose(st["exp_avg"], m, rtol=1e-6, atol=1e-8)
