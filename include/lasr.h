@@ -283,6 +283,24 @@ int lasr_novograd_step(float* params, const float* grads, float* exp_avg, void* 
                        float lr, float beta1, float beta2, float eps, float weight_decay, int grad_averaging,
                        lasr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Context BiLSTM recurrence.  Replaces pack_padded_sequence -> nn.LSTM(256, 40, bidirectional=True)
+ * -> pad_packed_sequence at models/QuartNetContext.py:171-173,186-199 (and the `.cpu()` length sync at :171).  The
+ * input projections are a pointwise-conv GEMM issued by the caller (lasr_pwconv_fwd with bias b_ih + b_hh):
+ *   pre    [N, T, 320] dtype: column d*160 + g*40 + u = gate g (i, f, g, o) of unit u, direction d (0 fwd, 1 reverse)
+ *   whh    [2, 160, 40] fp32 (weight_hh_l0, weight_hh_l0_reverse)
+ *   lengths [N] int32 or NULL; frames >= lengths[n] give zeros (pad_packed_sequence) and no gradient
+ *   out    [N, T, 80] dtype: [h_fwd | h_reverse]
+ *   gates  [N, T, 2, 40, 4] fp32 (16-byte aligned) and cells [N, T, 2, 40] fp32: saved for the backward
+ * bwd: dpre [N, T, 320] dtype out; dwhh [2, 160, 40] fp32 ACCUMULATED.  dW_ih / db / dx follow from dpre through
+ *      lasr_pwconv_wgrad / lasr_colsum / lasr_pwconv_dgrad.   hidden must be 40 (the reference's only use).
+ * ---------------------------------------------------------------------------------------------- */
+int lasr_bilstm_fwd(const void* pre, const float* whh, const int32_t* lengths, void* out, float* gates, float* cells,
+                    int N, int T, int hidden, int dtype, lasr_stream_t stream);
+int lasr_bilstm_bwd(const void* dout, const void* out, const float* gates, const float* cells, const float* whh,
+                    const int32_t* lengths, void* dpre, float* dwhh, int N, int T, int hidden, int dtype,
+                    lasr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

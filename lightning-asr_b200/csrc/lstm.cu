@@ -1,0 +1,266 @@
+// Context BiLSTM (256 -> 2 x 40, one layer) recurrence, forward and backward, variable lengths, no host sync.
+// Replaces models/QuartNetContext.py:157,171-173,186-199: `length = (T' * percents).int().cpu()` ->
+// pack_padded_sequence(enforce_sorted=False) -> nn.LSTM(256, 40, bidirectional) -> pad_packed_sequence.
+//
+// Split of the work:
+//   * the input projections of all frames and both directions, pre[n, t, d*160 + g*40 + u] = W_ih x_t + b_ih + b_hh,
+//     are ONE pointwise-conv GEMM (256 -> 320, gemm_tc.cu / gemm_simt.cu) issued by the caller; likewise dW_ih and dx
+//     in the backward are the regular weight-gradient / data-gradient GEMMs over dpre;
+//   * this file is the sequential part.  One CTA per (utterance, direction), 160 threads = one per gate row
+//     (PyTorch order i, f, g, o).  The 160 x 40 recurrent matrix lives in registers (40 per thread), h_{t-1} in shared
+//     memory (broadcast reads), the cell state in the registers of the first 40 threads.  Two barriers per frame.
+//     The forward direction walks t = 0 .. len-1, the reverse direction t = len-1 .. 0; frames >= len produce zeros,
+//     exactly what pad_packed_sequence returns.  `pre` rows are prefetched 8 frames ahead through registers.
+//   * backward: same CTA shape walking the frames in the opposite order.  Thread u < 40 turns dh into the four
+//     pre-activation gate gradients of unit u; then every thread j adds dgate_j * h_prev[k] to its 40 register
+//     accumulators of dW_hh[j, :] (one atomicAdd pass at the end) and the threads, regrouped as (unit k, gate q),
+//     reduce dh_prev[k] = sum_j W_hh[j, k] dgate_j with two shuffles.
+#include "common.cuh"
+
+namespace lasr {
+
+constexpr int LS_H = 40;          // hidden units per direction
+constexpr int LS_G = 4 * LS_H;    // gate rows per direction
+constexpr int LS_PF = 8;          // frames of prefetch distance
+
+// full-accuracy libm versions: the recurrence is latency-bound by its two barriers per frame, not by these, and
+// whole-network gradient parity (train-mode BatchNorm amplifies rounding ~20x) wants every ulp
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float tanhf_(float x) { return tanhf(x); }
+
+// pre [N, T, 2*160] (T_), whh [2, 160, 40] fp32, lengths [N] (nullable: all T)
+// out  [N, T, 80]  (T_): h of (direction d, unit u) at column d*40 + u; zero for t >= len
+// gates [N, T, 2, 40] float4 (i, f, g, o after the non-linearities), cells [N, T, 2, 40] fp32: kept for the backward
+template <typename T_>
+__global__ void __launch_bounds__(LS_G)
+bilstm_fwd_kernel(const T_* __restrict__ pre, const float* __restrict__ whh, const int32_t* __restrict__ lengths,
+                  T_* __restrict__ out, float4* __restrict__ gates, float* __restrict__ cells, int T) {
+  const int n = blockIdx.x, d = blockIdx.y, j = threadIdx.x;
+  __shared__ float h_s[2][LS_H];
+  __shared__ float g_s[LS_G];
+  float w[LS_H];
+#pragma unroll
+  for (int k = 0; k < LS_H; ++k) w[k] = whh[(static_cast<size_t>(d) * LS_G + j) * LS_H + k];
+  int len = lengths != nullptr ? lengths[n] : T;
+  len = max(0, min(len, T));
+  if (j < LS_H) h_s[0][j] = 0.f;
+  float c = 0.f;
+  const int gate_type = j / LS_H;
+  const T_* pre_n = pre + static_cast<size_t>(n) * T * (2 * LS_G) + d * LS_G + j;
+  auto frame = [&](int s) { return d == 0 ? s : len - 1 - s; };
+  float pf[LS_PF];
+#pragma unroll
+  for (int i = 0; i < LS_PF; ++i) pf[i] = (i < len) ? to_f32<T_>(pre_n[static_cast<size_t>(frame(i)) * (2 * LS_G)]) : 0.f;
+  __syncthreads();
+  int cur = 0;
+  for (int s0 = 0; s0 < len; s0 += LS_PF) {
+#pragma unroll
+    for (int i = 0; i < LS_PF; ++i) {
+      const int s = s0 + i;
+      if (s >= len) break;
+      float acc0 = pf[i], acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      // refill this slot for frame s + LS_PF: the load has LS_PF frames of recurrence to land
+      if (s + LS_PF < len) pf[i] = to_f32<T_>(pre_n[static_cast<size_t>(frame(s + LS_PF)) * (2 * LS_G)]);
+      const float* hp = h_s[cur];
+#pragma unroll
+      for (int k = 0; k < LS_H; k += 4) {
+        const float4 hv = *reinterpret_cast<const float4*>(hp + k);
+        acc0 = fmaf(w[k], hv.x, acc0);
+        acc1 = fmaf(w[k + 1], hv.y, acc1);
+        acc2 = fmaf(w[k + 2], hv.z, acc2);
+        acc3 = fmaf(w[k + 3], hv.w, acc3);
+      }
+      const float a = (acc0 + acc1) + (acc2 + acc3);
+      g_s[j] = gate_type == 2 ? tanhf_(a) : sigmoidf_(a);
+      __syncthreads();
+      if (j < LS_H) {
+        const float gi = g_s[j], gf = g_s[LS_H + j], gg = g_s[2 * LS_H + j], go = g_s[3 * LS_H + j];
+        c = fmaf(gf, c, gi * gg);
+        const float h = go * tanhf_(c);
+        h_s[cur ^ 1][j] = h;
+        const int t = frame(s);
+        const size_t row = static_cast<size_t>(n) * T + t;
+        out[row * (2 * LS_H) + d * LS_H + j] = from_f32<T_>(h);
+        gates[(row * 2 + d) * LS_H + j] = make_float4(gi, gf, gg, go);
+        cells[(row * 2 + d) * LS_H + j] = c;
+      }
+      __syncthreads();
+      cur ^= 1;
+    }
+  }
+  // pad_packed_sequence: zeros after the utterance's last frame
+  if (j < LS_H)
+    for (int t = len; t < T; ++t) out[(static_cast<size_t>(n) * T + t) * (2 * LS_H) + d * LS_H + j] = from_f32<T_>(0.f);
+}
+
+// dout [N, T, 80] (T_) gradient of `out`; out / gates / cells from the forward
+// dpre [N, T, 320] (T_) out: gradient of the pre-activations (zero for t >= len)
+// dwhh [2, 160, 40] fp32: ACCUMULATED (atomicAdd)
+template <typename T_>
+__global__ void __launch_bounds__(LS_G)
+bilstm_bwd_kernel(const T_* __restrict__ dout, const T_* __restrict__ out, const float4* __restrict__ gates,
+                  const float* __restrict__ cells, const float* __restrict__ whh, const int32_t* __restrict__ lengths,
+                  T_* __restrict__ dpre, float* __restrict__ dwhh, int T) {
+  const int n = blockIdx.x, d = blockIdx.y, j = threadIdx.x;
+  __shared__ float dg_s[LS_G];
+  __shared__ float hprev_s[LS_H];
+  __shared__ float dhrec_s[LS_H];
+  // regrouped view for the dh_prev reduction: thread = (unit k, gate q); it owns W_hh[q*40 + jj, k], jj < 40
+  const int k_own = j >> 2, q_own = j & 3;
+  float wt[LS_H];
+#pragma unroll
+  for (int jj = 0; jj < LS_H; ++jj)
+    wt[jj] = whh[(static_cast<size_t>(d) * LS_G + q_own * LS_H + jj) * LS_H + k_own];
+  float acc[LS_H];
+#pragma unroll
+  for (int k = 0; k < LS_H; ++k) acc[k] = 0.f;
+  int len = lengths != nullptr ? lengths[n] : T;
+  len = max(0, min(len, T));
+  if (j < LS_H) dhrec_s[j] = 0.f;
+  float dc_carry = 0.f;
+  __syncthreads();
+  // recurrence order of direction d was: forward t = 0..len-1, reverse t = len-1..0.  Walk it backwards; position s
+  // of the recurrence is frame t(s), its predecessor (whose h / c fed it) is position s-1.
+  auto frame = [&](int s) { return d == 0 ? s : len - 1 - s; };
+  struct Ld {
+    float4 g4;
+    float ct, cp, hp, dh;
+  };
+  auto load = [&](int s) {
+    Ld v;
+    const size_t row = static_cast<size_t>(n) * T + frame(s);
+    v.g4 = gates[(row * 2 + d) * LS_H + j];
+    v.ct = cells[(row * 2 + d) * LS_H + j];
+    v.dh = to_f32<T_>(dout[row * (2 * LS_H) + d * LS_H + j]);
+    v.cp = 0.f;
+    v.hp = 0.f;
+    if (s > 0) {
+      const size_t rowp = static_cast<size_t>(n) * T + frame(s - 1);
+      v.cp = cells[(rowp * 2 + d) * LS_H + j];
+      v.hp = to_f32<T_>(out[rowp * (2 * LS_H) + d * LS_H + j]);
+    }
+    return v;
+  };
+  constexpr int PF = 4;  // positions of prefetch distance (unit threads only)
+  Ld q[PF];
+  if (j < LS_H) {
+#pragma unroll
+    for (int i = 0; i < PF; ++i)
+      if (len - 1 - i >= 0) q[i] = load(len - 1 - i);
+  }
+  for (int s0 = len - 1; s0 >= 0; s0 -= PF) {
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int s = s0 - i;
+      if (s < 0) break;
+      if (j < LS_H) {
+        const Ld v = q[i];
+        if (s - PF >= 0) q[i] = load(s - PF);
+        const float4 g4 = v.g4;
+        const float dh = v.dh + dhrec_s[j];
+        const float tc = tanhf_(v.ct);
+        const float d_o = dh * tc;
+        const float dc = fmaf(dh * g4.w, 1.f - tc * tc, dc_carry);
+        const float d_i = dc * g4.z, d_g = dc * g4.x, d_f = dc * v.cp;
+        dc_carry = dc * g4.y;
+        const float pi = d_i * g4.x * (1.f - g4.x);
+        const float pf_ = d_f * g4.y * (1.f - g4.y);
+        const float pg = d_g * (1.f - g4.z * g4.z);
+        const float po = d_o * g4.w * (1.f - g4.w);
+        dg_s[j] = pi;
+        dg_s[LS_H + j] = pf_;
+        dg_s[2 * LS_H + j] = pg;
+        dg_s[3 * LS_H + j] = po;
+        hprev_s[j] = v.hp;
+        T_* dp = dpre + (static_cast<size_t>(n) * T + frame(s)) * (2 * LS_G) + d * LS_G + j;
+        dp[0] = from_f32<T_>(pi);
+        dp[LS_H] = from_f32<T_>(pf_);
+        dp[2 * LS_H] = from_f32<T_>(pg);
+        dp[3 * LS_H] = from_f32<T_>(po);
+      }
+      __syncthreads();
+      {
+        const float dgj = dg_s[j];
+#pragma unroll
+        for (int k = 0; k < LS_H; k += 4) {
+          const float4 hv = *reinterpret_cast<const float4*>(hprev_s + k);
+          acc[k] = fmaf(dgj, hv.x, acc[k]);
+          acc[k + 1] = fmaf(dgj, hv.y, acc[k + 1]);
+          acc[k + 2] = fmaf(dgj, hv.z, acc[k + 2]);
+          acc[k + 3] = fmaf(dgj, hv.w, acc[k + 3]);
+        }
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+        const float* dq = dg_s + q_own * LS_H;
+#pragma unroll
+        for (int jj = 0; jj < LS_H; jj += 4) {
+          const float4 dv = *reinterpret_cast<const float4*>(dq + jj);
+          p0 = fmaf(wt[jj], dv.x, p0);
+          p1 = fmaf(wt[jj + 1], dv.y, p1);
+          p2 = fmaf(wt[jj + 2], dv.z, p2);
+          p3 = fmaf(wt[jj + 3], dv.w, p3);
+        }
+        float part = (p0 + p1) + (p2 + p3);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        if (q_own == 0) dhrec_s[k_own] = part;  // its readers (the unit threads) finished before the barrier above
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < LS_H; ++k) atomicAdd(dwhh + (static_cast<size_t>(d) * LS_G + j) * LS_H + k, acc[k]);
+  // frames past the end: no gradient
+  for (int t = len; t < T; ++t) dpre[(static_cast<size_t>(n) * T + t) * (2 * LS_G) + d * LS_G + j] = from_f32<T_>(0.f);
+}
+
+}  // namespace lasr
+
+using namespace lasr;
+
+extern "C" {
+
+int lasr_bilstm_fwd(const void* pre, const float* whh, const int32_t* lengths, void* out, float* gates, float* cells,
+                    int N, int T, int hidden, int dtype, lasr_stream_t stream) {
+  if (N <= 0 || T <= 0 || pre == nullptr || whh == nullptr || out == nullptr || gates == nullptr || cells == nullptr)
+    return LASR_ERR_BAD_SHAPE;
+  if (hidden != LS_H) return LASR_ERR_UNSUPPORTED;  // the reference's only configuration (QuartNetContext.py:157)
+  if (reinterpret_cast<uintptr_t>(gates) & 15) return LASR_ERR_ALIGNMENT;
+  dim3 grid(N, 2);
+  if (dtype == LASR_F32)
+    bilstm_fwd_kernel<float><<<grid, LS_G, 0, stream>>>(static_cast<const float*>(pre), whh, lengths,
+                                                        static_cast<float*>(out), reinterpret_cast<float4*>(gates),
+                                                        cells, T);
+  else if (dtype == LASR_BF16)
+    bilstm_fwd_kernel<__nv_bfloat16><<<grid, LS_G, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(pre), whh, lengths, static_cast<__nv_bfloat16*>(out),
+        reinterpret_cast<float4*>(gates), cells, T);
+  else
+    return LASR_ERR_BAD_DTYPE;
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+int lasr_bilstm_bwd(const void* dout, const void* out, const float* gates, const float* cells, const float* whh,
+                    const int32_t* lengths, void* dpre, float* dwhh, int N, int T, int hidden, int dtype,
+                    lasr_stream_t stream) {
+  if (N <= 0 || T <= 0 || dout == nullptr || out == nullptr || gates == nullptr || cells == nullptr ||
+      whh == nullptr || dpre == nullptr || dwhh == nullptr)
+    return LASR_ERR_BAD_SHAPE;
+  if (hidden != LS_H) return LASR_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(gates) & 15) return LASR_ERR_ALIGNMENT;
+  dim3 grid(N, 2);
+  if (dtype == LASR_F32)
+    bilstm_bwd_kernel<float><<<grid, LS_G, 0, stream>>>(
+        static_cast<const float*>(dout), static_cast<const float*>(out), reinterpret_cast<const float4*>(gates), cells,
+        whh, lengths, static_cast<float*>(dpre), dwhh, T);
+  else if (dtype == LASR_BF16)
+    bilstm_bwd_kernel<__nv_bfloat16><<<grid, LS_G, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(out),
+        reinterpret_cast<const float4*>(gates), cells, whh, lengths, static_cast<__nv_bfloat16*>(dpre), dwhh, T);
+  else
+    return LASR_ERR_BAD_DTYPE;
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+}  // extern "C"

@@ -295,3 +295,50 @@ class FusedDecoderCTCFn(torch.autograd.Function):
                               ld, x.dtype)
         dx, d_w, d_b = _decoder_backward(x, w, b, w_s, dlogits, ctx.needs_input_grad[0])
         return dx, d_w, d_b, None, None, None, None
+
+
+class BiLstmFn(torch.autograd.Function):
+    """Bidirectional single-layer LSTM over variable-length utterances, channels-last, no host sync:
+        c[n, t, :] = [h_fwd(t) | h_reverse(t)] for t < lengths[n], zeros after          models/QuartNetContext.py:171-173,186-199
+    = pack_padded_sequence(enforce_sorted=False) -> nn.LSTM(Cin, 40, bidirectional=True) -> pad_packed_sequence.
+    Kernel sequence: ONE pointwise GEMM (Cin -> 320, bias b_ih + b_hh) for the input projections of all frames and both
+    directions -> lasr_bilstm_fwd (recurrence).  Backward: lasr_bilstm_bwd (recurrence, dW_hh) -> weight-gradient GEMM
+    (dW_ih), column sums (biases), data-gradient GEMM (dx).  Parameters are nn.LSTM's own (state_dict schema)."""
+
+    @staticmethod
+    def forward(ctx, x, lengths, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        dt, dev = x.dtype, x.device
+        N, T, Cin = x.shape
+        H = w_hh.shape[1]
+        w_cat = torch.cat((runtime.weight(w_ih, dt), runtime.weight(w_ih_r, dt)), dim=0).contiguous()  # [8H, Cin]
+        bias = torch.cat((b_ih.detach() + b_hh.detach(), b_ih_r.detach() + b_hh_r.detach()), dim=0).float().contiguous()
+        whh = torch.stack((w_hh.detach(), w_hh_r.detach()), dim=0).float().contiguous()  # [2, 4H, H]
+        pre = ops.pwconv_fwd(x, w_cat, bias=bias)  # [N, T, 8H]
+        out, gates, cells = ops.bilstm_fwd(pre, whh, lengths, H)
+        ctx.save_for_backward(x, lengths, w_cat, whh, out, gates, cells, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r,
+                              b_hh_r)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x, lengths, w_cat, whh, out, gates, cells, w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r,
+         b_hh_r) = ctx.saved_tensors
+        H = w_hh.shape[1]
+        G = 4 * H
+        dwhh = runtime.zeros((2, G, H), torch.float32, x.device)
+        dpre = ops.bilstm_bwd(dout.contiguous(), out, gates, cells, whh, lengths, dwhh, H)  # [N, T, 2G]
+        dwcat = runtime.zeros((2 * G, x.shape[-1]), torch.float32, x.device)
+        ops.pwconv_wgrad(dpre, x, out=dwcat, Cout=2 * G)
+        db = ops.colsum(dpre, 2 * G, out=runtime.zeros((2 * G,), torch.float32, x.device))
+        rets = []
+        for p, g in ((w_ih, dwcat[:G]), (w_hh, dwhh[0]), (b_ih, db[:G]), (b_hh, db[:G]),
+                     (w_ih_r, dwcat[G:]), (w_hh_r, dwhh[1]), (b_ih_r, db[G:]), (b_hh_r, db[G:])):
+            sink, ret = runtime.grad_sink(p)
+            if ret is None:
+                sink.add_(g.view_as(sink))  # flat-bucket view: accumulate in place, autograd gets nothing
+                rets.append(None)
+            else:
+                rets.append(g.reshape(p.shape).clone())
+        runtime.grad_ready(w_ih, w_hh, b_ih, b_hh, w_ih_r, w_hh_r, b_ih_r, b_hh_r)
+        dx = ops.pwconv_dgrad(dpre, w_cat) if ctx.needs_input_grad[0] else None
+        return (dx, None) + tuple(rets)

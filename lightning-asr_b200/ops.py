@@ -234,6 +234,28 @@ def se_bn_bwd_finalize(per_n, N, T, gate, extra, sums_y, gamma, save, dgamma, db
     return coef
 
 
+def bilstm_fwd(pre, whh, lengths, hidden):
+    """pre [N, T, 8H] input projections (+ biases) -> (out [N, T, 2H], gates [N, T, 2, H, 4] f32, cells [N, T, 2, H] f32)."""
+    _chk(pre, "pre"), _chk(whh, "whh")
+    N, T = pre.shape[0], pre.shape[1]
+    if pre.shape[2] != 8 * hidden or tuple(whh.shape) != (2, 4 * hidden, hidden) or whh.dtype != torch.float32:
+        raise _lib.LasrError(f"bilstm: pre {tuple(pre.shape)} / whh {tuple(whh.shape)} do not match hidden={hidden}")
+    out = torch.empty((N, T, 2 * hidden), device=pre.device, dtype=pre.dtype)
+    gates = torch.empty((N, T, 2, hidden, 4), device=pre.device, dtype=torch.float32)
+    cells = torch.empty((N, T, 2, hidden), device=pre.device, dtype=torch.float32)
+    call("lasr_bilstm_fwd", pre, whh, lengths, out, gates, cells, N, T, hidden, dtype_code(pre.dtype))
+    return out, gates, cells
+
+
+def bilstm_bwd(dout, out, gates, cells, whh, lengths, dwhh, hidden):
+    """-> dpre [N, T, 8H] in dout's dtype; dwhh [2, 4H, H] f32 is accumulated into."""
+    _chk(dout, "dout"), _chk(out, "out")
+    N, T = out.shape[0], out.shape[1]
+    dpre = torch.empty((N, T, 8 * hidden), device=out.device, dtype=out.dtype)
+    call("lasr_bilstm_bwd", dout, out, gates, cells, whh, lengths, dpre, dwhh, N, T, hidden, dtype_code(out.dtype))
+    return dpre
+
+
 def log_softmax_fwd(logits, V, want_lp=True):
     """logits [..., ld] -> (lse [...], lp [..., V] fp32 or None)."""
     ld = logits.shape[-1]

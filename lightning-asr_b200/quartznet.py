@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .functions import (Conv1x1BNReLUFn, DecoderLogSoftmaxFn, FusedDecoderCTCFn, SepConvBNFn)
+from .functions import (BiLstmFn, Conv1x1BNReLUFn, DecoderLogSoftmaxFn, FusedDecoderCTCFn, SepConvBNFn)
 
 _PRECISION = {"default": "auto"}
 
@@ -126,19 +126,28 @@ class QuartNetBlock(nn.Module):
 
 
 class BatchLSTM(nn.Module):
-    """models/QuartNetContext.py:186-199 -- stays a torch/cuDNN call."""
+    """models/QuartNetContext.py:186-199.  `self.rnn` is a plain nn.LSTM and stays the owner of the parameters, so the
+    checkpoint keys (`context_rnn.rnn.weight_ih_l0`, ..., `..._reverse`) are the reference's; the arithmetic runs in
+    functions.BiLstmFn (one input-projection GEMM + the recurrence kernels of csrc/lstm.cu), channels-last, with the
+    utterance lengths read on the device: no `.cpu()` sync, no pack / pad copies, CUDA-graph capturable.
+
+    forward(x [N, T, in_ch], length int32 [N] on the device) -> (c [N, T, 2*out_ch], None); frames >= length are zero
+    exactly as pad_packed_sequence leaves them."""
 
     def __init__(self, in_ch=128, out_ch=128, batch_first=True, bidirection=True, num_layers=1, dropout=0.):
         super().__init__()
+        if not (batch_first and bidirection and num_layers == 1 and dropout == 0. and out_ch == 40):
+            raise NotImplementedError("BatchLSTM: the B200 kernel implements the reference's only configuration "
+                                      "(batch_first, bidirectional, 1 layer, hidden 40; QuartNetContext.py:157)")
         self.batch_first = batch_first
         self.rnn = nn.LSTM(in_ch, out_ch, num_layers=num_layers, batch_first=batch_first, bidirectional=bidirection,
                            dropout=dropout)
 
     def forward(self, x, length, total_length=None):
-        x = nn.utils.rnn.pack_padded_sequence(x, enforce_sorted=False, lengths=length, batch_first=self.batch_first)
-        x, h = self.rnn(x)
-        x, _ = nn.utils.rnn.pad_packed_sequence(x, batch_first=self.batch_first, total_length=total_length)
-        return x, h
+        r = self.rnn
+        c = BiLstmFn.apply(x.contiguous(), length, r.weight_ih_l0, r.weight_hh_l0, r.bias_ih_l0, r.bias_hh_l0,
+                           r.weight_ih_l0_reverse, r.weight_hh_l0_reverse, r.bias_ih_l0_reverse, r.bias_hh_l0_reverse)
+        return c, None
 
 
 _ASR13X1 = [  # (name, in, out, k)   models/QuartNet.py:130-144
@@ -191,11 +200,10 @@ class QuartNet12(nn.Module):
         for name in self.block_names:
             x = getattr(self, name)(x, lengths)
             if name == "block23" and self.variant != "base":
-                # models/QuartNetContext.py:171-173; lengths go to the host exactly like the reference's `.cpu()`
-                # fp32 mode keeps cuDNN's RNN GEMMs in true fp32 (TF32 alone breaks rel 1e-4)
-                with torch.backends.cudnn.flags(enabled=True, allow_tf32=(x.dtype != torch.float32)):
-                    c, _ = self.context_rnn(x.float(), lengths.cpu(), total_length=x.shape[1])
-                x = torch.cat((x, c.to(x.dtype)), dim=2).contiguous()
+                # models/QuartNetContext.py:171-173: length = (T' * percents).int() is the same `lengths` tensor; it
+                # stays on the device (the reference's `.cpu()` sync is gone)
+                c, _ = self.context_rnn(x, lengths)
+                x = torch.cat((x, c), dim=2).contiguous()
         x = Conv1x1BNReLUFn.apply(x, self.last_cnn2[0].weight, self.last_cnn2[1].weight, self.last_cnn2[1].bias,
                                   _bn_buffers(self.last_cnn2[1]), self.training, True)
         if self.drop_rate > 0.0 and self.training:

@@ -166,6 +166,11 @@ class TrainEngine:
         self.loss_dev = torch.zeros((), device=self.dev, dtype=torch.float32)
         self.graph = None
         self.use_graph = graph
+        # double-buffered input pipeline: the NEXT batch's H2D runs on a copy stream while this step computes
+        self.copy_stream = torch.cuda.Stream()
+        self.staging = [torch.empty_like(t) if torch.is_tensor(t) else t for t in self.static]
+        self._staged_evt = None
+        self._consumed_evt = None
 
     def _step_eager(self):
         m = self.module
@@ -217,15 +222,47 @@ class TrainEngine:
                 h.copy_(src)
                 d.copy_(h, non_blocking=True)
 
-    def step_host(self, batch=None):
-        """End-to-end step: H2D of the batch from pinned memory, the step, D2H of the loss.  Returns a float."""
+    def prefetch(self, batch=None):
+        """Start the H2D of the NEXT batch (pinned host -> device staging buffers) on the copy stream; it overlaps
+        whatever the compute stream is doing.  `batch=None` re-sends the pinned example batch (bench.py)."""
         if batch is not None:
+            for h, src in zip(self.host, batch[:4]):
+                if torch.is_tensor(src):
+                    if src.shape != h.shape:
+                        raise ValueError(f"TrainEngine batches must keep their shape: {tuple(src.shape)} vs {tuple(h.shape)}")
+                    h.copy_(src)
+        if self._consumed_evt is not None:
+            self.copy_stream.wait_event(self._consumed_evt)  # the previous staging contents have been taken over
+        with torch.cuda.stream(self.copy_stream):
+            for h, d in zip(self.host, self.staging):
+                if torch.is_tensor(h):
+                    d.copy_(h, non_blocking=True)
+            self._staged_evt = torch.cuda.Event()
+            self._staged_evt.record(self.copy_stream)
+
+    def step_host(self, batch=None, prefetch_next=False):
+        """End-to-end step: H2D of the batch from pinned memory, the step, D2H of the loss.  Returns a float.
+        If prefetch() staged this batch earlier, the inputs are taken over with a device-to-device copy instead of
+        waiting for PCIe; `prefetch_next` (True: the pinned example batch, or a batch tuple) starts the next batch's
+        H2D before this step's loss is awaited, so the copy hides under the step."""
+        cur = torch.cuda.current_stream()
+        if batch is None and self._staged_evt is not None:
+            cur.wait_event(self._staged_evt)
+            for s, d in zip(self.staging, self.static):
+                if torch.is_tensor(s):
+                    d.copy_(s, non_blocking=True)
+            self._consumed_evt = torch.cuda.Event()
+            self._consumed_evt.record(cur)
+            self._staged_evt = None
+        elif batch is not None:
             self.load_batch(batch)
         else:
             for h, d in zip(self.host, self.static):
                 if torch.is_tensor(h):
                     d.copy_(h, non_blocking=True)
         self.step_device()
+        if prefetch_next is not False and prefetch_next is not None:
+            self.prefetch(None if prefetch_next is True else prefetch_next)
         self.loss_host.copy_(self.loss_dev, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        cur.synchronize()
         return float(self.loss_host)

@@ -196,3 +196,38 @@ def test_greedy_decode_bit_exact(ops, labels28):
                                                          None if ln is None else ln.cpu().tolist())
         for i in range(N):
             assert tokens[i, : counts[i]].cpu().tolist() == toks_ref[i]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_bilstm_matches_torch_packed_lstm(dtype, tol):
+    """functions.BiLstmFn vs the reference's BatchLSTM arithmetic (models/QuartNetContext.py:186-199):
+    pack_padded_sequence -> nn.LSTM(256, 40, bidirectional) -> pad_packed_sequence on the CPU in fp32,
+    forward and every gradient, ragged lengths including a length-1 and a full-length utterance."""
+    from lightning_asr_b200.functions import BiLstmFn
+
+    torch.manual_seed(3)
+    N, T, Cin, H = 5, 37, 256, 40
+    lens = torch.tensor([37, 1, 20, 36, 9], dtype=torch.int32)
+    ref = torch.nn.LSTM(Cin, H, num_layers=1, batch_first=True, bidirectional=True)
+    x = torch.randn(N, T, Cin) * 0.5
+    gout = torch.randn(N, T, 2 * H)
+    xr = x.clone().requires_grad_(True)
+    packed = torch.nn.utils.rnn.pack_padded_sequence(xr, lens.long(), batch_first=True, enforce_sorted=False)
+    yr, _ = ref(packed)
+    yr, _ = torch.nn.utils.rnn.pad_packed_sequence(yr, batch_first=True, total_length=T)
+    (yr * gout).sum().backward()
+
+    params = [torch.nn.Parameter(p.detach().clone().cuda()) for p in
+              (ref.weight_ih_l0, ref.weight_hh_l0, ref.bias_ih_l0, ref.bias_hh_l0, ref.weight_ih_l0_reverse,
+               ref.weight_hh_l0_reverse, ref.bias_ih_l0_reverse, ref.bias_hh_l0_reverse)]
+    xg = x.cuda().to(dtype).requires_grad_(True)
+    y = BiLstmFn.apply(xg, lens.cuda(), *params)
+    (y.float() * gout.cuda()).sum().backward()
+    assert rel_err(y.float().cpu(), yr.detach()) < tol
+    assert torch.count_nonzero(y[1, 1:]) == 0 and torch.count_nonzero(y[4, 9:]) == 0  # pad_packed_sequence zeros
+    assert rel_err(xg.grad.float().cpu(), xr.grad) < tol
+    refs = (ref.weight_ih_l0, ref.weight_hh_l0, ref.bias_ih_l0, ref.bias_hh_l0, ref.weight_ih_l0_reverse,
+            ref.weight_hh_l0_reverse, ref.bias_ih_l0_reverse, ref.bias_hh_l0_reverse)
+    for p, r in zip(params, refs):
+        assert rel_err(p.grad.cpu(), r.grad) < tol
