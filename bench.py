@@ -28,6 +28,8 @@ WORKLOADS = {
     "asr13x1_b4_10s_fp32": ("asr13x1", 4, 10.0, "labels28", "fp32"),
     "contextse_b64_20s_bf16": ("asr13x1contextse", 64, 20.0, "labels28", "bf16"),
     "context_aishell_b32_16s_bf16": ("asr13x1context", 32, 16.0, "aishell", "bf16"),
+    # BASELINE config 5: validation / inference path (frontend + encoder in eval mode + greedy CTC decode)
+    "infer_asr13x1_b256_30s_bf16": ("asr13x1", 256, 30.0, "labels28", "bf16"),
 }
 
 
@@ -269,6 +271,110 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def run_infer(args):
+    """Inference workload: waveforms (pinned host) -> H2D -> log-mel -> encoder (eval) -> greedy decode -> tokens D2H."""
+    import torch
+    import torch.distributed as dist
+
+    from lightning_asr_b200 import _lib
+    from lightning_asr_b200.trainer import InferEngine, LightingModule, synthetic_batch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    _lib.require_device()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    model_name, n, seconds, vocab, precision = WORKLOADS[args.workload]
+    labels = labels_for(vocab)
+    peaks = load_peaks()
+    torch.manual_seed(0)
+    module = LightingModule(labels=labels, mask=True, drop_rate=0.0, model_name=model_name,
+                            precision=precision).cuda().eval()
+    (waves, lens), _, _, _, _ = synthetic_batch(n, seconds, len(labels), seed=1234 + rank, ragged=False, features=False)
+    engine = InferEngine(module, waves, lens, graph=not args.no_graph)
+    for _ in range(max(args.warmup, 3)):
+        engine.step_device()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        engine.step_device()
+    e1.record()
+    barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    f0.record()
+    engine.prefetch()
+    for i in range(args.steps):
+        toks, cnts = engine.step_host(prefetch_next=(i + 1 < args.steps))
+    f1.record()
+    barrier()
+    e2e_ms = max_over_ranks(max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3))
+    clocks = sampler.stop() if rank == 0 else None
+    fam, calls = kernel_breakdown(engine, steps=3)
+    if world > 1:
+        barrier()
+    if rank != 0:
+        sys.stdout.flush()
+        os._exit(0)
+    ms_per_step = ms_total / args.steps
+    audio_s = n * seconds * world
+    T = 1 + (int(seconds * 16000) + 64) // 160
+    Tp = (T - 1) // 2 + 1
+    # schedule-L forward bytes (SURVEY.md 8d): asr13x1 V'=29 fwd = 50 775 elements per encoder step, + the waveform
+    sched_bytes = 50775 * 2 * n * Tp + 4 * n * int(seconds * 16000)
+    total_ms = sum(d["ms"] for d in fam.values())
+    tname, t = max(fam.items(), key=lambda kv: kv[1]["ms"])
+    ach = (t["flops"] / (t["ms"] * 1e-3) / 1e12) if tname == "pwconv_gemm" else (t["bytes"] / (t["ms"] * 1e-3) / 1e9)
+    peak = peaks["bf16_tflops_sustained"] if tname == "pwconv_gemm" else peaks["hbm_gbs"]
+    roof = {"bound": "tensor" if tname == "pwconv_gemm" else "hbm", "achieved": ach, "peak": peak,
+            "unit": "TFLOP/s" if tname == "pwconv_gemm" else "GB/s", "frac": ach / peak, "traffic": None,
+            "kernel": tname, "peak_source": peaks["source"] + " (sustained)",
+            "share_of_step": t["ms"] / total_ms if total_ms else None,
+            "families": {k: {"ms": round(v["ms"], 4), "calls": v["calls"]} for k, v in fam.items()},
+            "step_hbm_frac_scheduleL": sched_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+    line = {
+        "metric": "inference audio-seconds/sec (log-mel + QuartzNet + greedy CTC decode)",
+        "value": audio_s / (ms_per_step * 1e-3), "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": precision, "data": "synthetic",
+        "config": {"workload": args.workload, "model_name": model_name, "per_gpu_batch": n, "seconds": seconds,
+                   "frames": T, "encoder_steps": Tp, "vocab": len(labels) + 1, "mask": True,
+                   "parallelism": f"dp{world} (independent replicas, no collective)",
+                   "step": "H2D waveforms -> log-mel -> encoder (eval) -> decoder -> greedy CTC decode -> tokens D2H",
+                   "cuda_graph": not args.no_graph,
+                   "l2": "no flush needed: each pass streams tens of GB of activations >> 126 MB L2"},
+        "e2e": {"value": audio_s / (e2e_ms / args.steps * 1e-3), "unit": "audio-s/s", "h2d_bytes_per_step": engine.h2d_bytes,
+                "d2h_bytes_per_step": int(toks.numel() * 4 + cnts.numel() * 4), "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": calls * args.steps, "roofline": roof, "cpu_baseline": None, "clocks": clocks,
+        "tokens_decoded": int(cnts.sum()),
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        os._exit(0)
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -427,6 +533,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload.startswith("infer_"):
+        run_infer(args)
     else:
         run_b200(args)
 

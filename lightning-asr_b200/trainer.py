@@ -266,3 +266,127 @@ class TrainEngine:
         self.loss_host.copy_(self.loss_dev, non_blocking=True)
         cur.synchronize()
         return float(self.loss_host)
+
+
+class InferEngine:
+    """Validation / inference path on one GPU (BASELINE config 5; predict.py:43-62, train.py:88-116 without the loss):
+    raw waveforms -> log-mel frontend (csrc/logmel.cu) -> encoder in eval mode -> decoder logits -> greedy CTC decode
+    (argmax + collapse, utils/asr_metrics.py:153-171).  Everything between the H2D of the waveforms and the D2H of the
+    token ids runs on the device with static buffers, so the whole pass is ONE CUDA graph.
+
+      step_device()             re-runs the pass on the resident waveforms -> (tokens [N, T'] int32, counts [N] int32)
+      step_host(prefetch_next)  pinned waveforms -> H2D (double buffered, like TrainEngine) -> pass -> tokens on host
+      transcripts()             strings through WER.decode_tokens (host side, like the reference)
+    """
+
+    def __init__(self, module, waves, num_samples, graph=True):
+        from . import frontend, ops
+        _lib.require_device()
+        self.module = module.eval()
+        self.dev = torch.device("cuda", torch.cuda.current_device())
+        self.frontend, self.ops = frontend, ops
+        waves = waves.float().contiguous()
+        self.N, self.S = waves.shape
+        ns = torch.as_tensor(num_samples, dtype=torch.int64)
+        if int(ns.max()) > self.S or int(ns.min()) <= frontend.N_FFT // 2:
+            raise _lib.LasrError("num_samples must be in (256, S_max]")
+        self.T = frontend.num_frames(int(ns.max()))
+        self.ns = ns.to(self.dev, dtype=torch.int32)
+        frames = frontend.num_frames(ns)
+        self.percents = (frames.float() / float(self.T)).to(self.dev)  # data_module.py:244
+        self.host = waves.pin_memory()
+        self.static = self.host.to(self.dev, non_blocking=True)
+        self.staging = torch.empty_like(self.static)
+        self.h2d_bytes = self.host.numel() * 4
+        from .quartznet import resolve_dtype
+        self.dtype = resolve_dtype(module.encoder.precision)
+        self.basis, self.mel_idx, self.mel_w = frontend.constants(self.dev)
+        Lp = _lib.load().lasr_logmel_padded_len(self.T)
+        self.parts = torch.empty((3, self.N, Lp), device=self.dev, dtype=torch.bfloat16)
+        self.db = torch.empty((self.N, self.T, frontend.N_MELS), device=self.dev, dtype=torch.float32)
+        self.stats = torch.zeros((self.N, 2), device=self.dev, dtype=torch.float64)
+        self.feats = torch.empty((self.N, self.T, frontend.N_MELS), device=self.dev, dtype=self.dtype)
+        self.tokens = self.counts = None
+        self.tokens_host = self.counts_host = None
+        self.copy_stream = torch.cuda.Stream()
+        self._staged_evt = self._consumed_evt = None
+        self.use_graph, self.graph = graph, None
+
+    def _run(self):
+        fe, ops = self.frontend, self.ops
+        model = self.module.encoder  # MyModel2
+        with torch.no_grad():
+            self.stats.zero_()
+            _lib.call("lasr_logmel_prepare", self.static, None, self.ns, self.parts, self.N, self.S, self.T)
+            _lib.call("lasr_logmel_fwd", self.parts, self.basis, self.mel_idx, self.mel_w, self.ns, self.db, self.stats,
+                      self.N, self.T, 6)
+            _lib.call("lasr_logmel_normalize", self.db, self.stats, self.ns, None, self.feats, self.N, self.T,
+                      _lib.dtype_code(self.dtype))
+            x = model.encoder.forward_ntc(self.feats, self.percents)  # [N, T', 1024]
+            V = len(model.labels) + 1
+            w = runtime.weight(model.decoder.weight, x.dtype).view(V, -1)
+            logits = ops.pwconv_fwd(x, w, bias=model.decoder.bias.detach(), ldy=(V + 7) // 8 * 8)
+            t_len = ops.out_lengths(x.shape[1], self.percents)  # train.py:76
+            _, tokens, counts = ops.greedy_decode(logits, t_len, V, V - 1)
+        if self.tokens is None:
+            self.tokens, self.counts = torch.empty_like(tokens), torch.empty_like(counts)
+            self.tokens_host = torch.empty(tokens.shape, dtype=tokens.dtype).pin_memory()
+            self.counts_host = torch.empty(counts.shape, dtype=counts.dtype).pin_memory()
+        self.tokens.copy_(tokens)
+        self.counts.copy_(counts)
+
+    _step_eager = _run  # bench.py's per-kernel breakdown hook
+
+    def step_device(self):
+        if self.use_graph:
+            if self.graph is None:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    for _ in range(2):
+                        self._run()
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run()
+                torch.cuda.synchronize()
+                self.graph = g
+            self.graph.replay()
+        else:
+            self._run()
+        return self.tokens, self.counts
+
+    def prefetch(self, waves=None):
+        if waves is not None:
+            self.host.copy_(waves)
+        if self._consumed_evt is not None:
+            self.copy_stream.wait_event(self._consumed_evt)
+        with torch.cuda.stream(self.copy_stream):
+            self.staging.copy_(self.host, non_blocking=True)
+            self._staged_evt = torch.cuda.Event()
+            self._staged_evt.record(self.copy_stream)
+
+    def step_host(self, prefetch_next=False):
+        cur = torch.cuda.current_stream()
+        if self._staged_evt is not None:
+            cur.wait_event(self._staged_evt)
+            self.static.copy_(self.staging, non_blocking=True)
+            self._consumed_evt = torch.cuda.Event()
+            self._consumed_evt.record(cur)
+            self._staged_evt = None
+        else:
+            self.static.copy_(self.host, non_blocking=True)
+        self.step_device()
+        if prefetch_next is not False and prefetch_next is not None:
+            self.prefetch(None if prefetch_next is True else prefetch_next)
+        self.tokens_host.copy_(self.tokens, non_blocking=True)
+        self.counts_host.copy_(self.counts, non_blocking=True)
+        cur.synchronize()
+        return self.tokens_host, self.counts_host
+
+    def transcripts(self):
+        """Collapsed token ids -> strings (labels_map join, utils/asr_metrics.py:168)."""
+        labels = self.module.labels
+        toks, cnts = self.tokens.cpu(), self.counts.cpu()
+        return ["".join(labels[int(c)] for c in toks[i, :int(cnts[i])]) for i in range(toks.shape[0])]

@@ -219,3 +219,30 @@ def test_train_engine_matches_plain_autograd(lasr, labels28, precision, graph):
     for (k1, v1), (k2, v2) in zip(ref.state_dict().items(), mod.state_dict().items()):
         if "running" in k1:
             assert rel_err(v2.float(), v1.float()) < 1e-4, k1
+
+
+@pytest.mark.gpu
+def test_infer_engine_matches_module_eval_path():
+    """InferEngine (waveform -> log-mel -> encoder eval -> greedy decode, CUDA graph) gives the same token ids as the
+    reference-shaped path LightingModule.forward(features, percents) -> argmax -> WER.ctc_decoder_predictions_tensor."""
+    from lightning_asr_b200 import frontend
+    from lightning_asr_b200.trainer import InferEngine, LightingModule, synthetic_batch
+
+    labels = [" ", "'"] + [chr(ord("a") + i) for i in range(26)]
+    torch.manual_seed(0)
+    module = LightingModule(labels=labels, mask=True, model_name="asr13x1", precision="fp32").cuda().eval()
+    with torch.no_grad():  # make the untrained net emit something other than one constant class
+        module.encoder.decoder.bias.normal_(0.0, 1.0)
+        module.encoder.decoder.weight.mul_(30.0)
+    (waves, lens), _, _, _, _ = synthetic_batch(3, 1.5, len(labels), seed=5, ragged=True, features=False)
+    eng = InferEngine(module, waves, lens, graph=True)
+    toks, cnts = eng.step_host()
+    feats = frontend.logmel_batch(waves.cuda(), lens, want_nct=True)
+    with torch.no_grad():
+        out = module(feats["inputs"], feats["percents"].cuda())
+    t_len = torch.mul(out.size(1), feats["percents"]).int()
+    ref = module.wer.ctc_decoder_predictions_tensor(out.argmax(dim=-1), t_len)
+    got = eng.transcripts()
+    assert got == ref
+    assert [len(s) for s in got] == [int(c) for c in cnts]
+    assert sum(len(s) for s in got) > 0
