@@ -120,6 +120,8 @@ class GradSync:
         self._fired[bi] = True
         if self.comm_stream is not None:
             self.comm_stream.wait_stream(torch.cuda.current_stream())
+            if self.bank is not None and getattr(self.bank, "side", None) is not None:
+                self.comm_stream.wait_stream(self.bank.side)  # weight gradients are produced on the side stream
             with torch.cuda.stream(self.comm_stream):
                 self._reduce_bucket(bi)
         else:

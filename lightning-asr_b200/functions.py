@@ -119,8 +119,11 @@ class SepConvBNFn(torch.autograd.Function):
 
         # pointwise conv: weight gradient (split-K tcgen05 MN-major GEMM) and data gradient (W as MN-major B operand)
         g_pw, ret_pw = runtime.grad_sink(pw_w)
-        ops.pwconv_wgrad(dy, d, out=g_pw)
-        runtime.grad_ready(pw_w)
+
+        def _pw_wgrad():
+            ops.pwconv_wgrad(dy, d, out=g_pw)
+            runtime.grad_ready(pw_w)
+        runtime.defer(_pw_wgrad, dy, d)
         dd = ops.pwconv_dgrad(dy, pw_s)
         ret_res = None
         dxr = None
@@ -129,16 +132,22 @@ class SepConvBNFn(torch.autograd.Function):
         if has_res:
             rin = x if res_x is None else res_x
             g_res, ret_res = runtime.grad_sink(res_w)
-            ops.pwconv_wgrad(dr, rin, out=g_res)
-            runtime.grad_ready(res_w)
+
+            def _res_wgrad():
+                ops.pwconv_wgrad(dr, rin, out=g_res)
+                runtime.grad_ready(res_w)
+            runtime.defer(_res_wgrad, dr, rin)
             if (res_x is None and need_dx) or (res_x is not None and ctx.needs_input_grad[1]):
                 dxr = ops.pwconv_dgrad(dr, res_s)
                 if res_x is not None:
                     d_res_x, dxr = dxr, None
         # depthwise conv
         g_dw, ret_dw = runtime.grad_sink(dw_w)
-        ops.dwconv_wgrad(x, dd, K, stride=stride, out=g_dw)
-        runtime.grad_ready(dw_w)
+
+        def _dw_wgrad():
+            ops.dwconv_wgrad(x, dd, K, stride=stride, out=g_dw)
+            runtime.grad_ready(dw_w)
+        runtime.defer(_dw_wgrad, x, dd)
         dx = None
         if need_dx:
             if stride != 1:
@@ -185,8 +194,11 @@ class Conv1x1BNReLUFn(torch.autograd.Function):
                                      None, None, act)
         runtime.grad_ready(bn_w, bn_b)
         g_cw, ret_cw = runtime.grad_sink(w)
-        ops.pwconv_wgrad(dy, x, out=g_cw)
-        runtime.grad_ready(w)
+
+        def _wgrad():
+            ops.pwconv_wgrad(dy, x, out=g_cw)
+            runtime.grad_ready(w)
+        runtime.defer(_wgrad, dy, x)
         dx = ops.pwconv_dgrad(dy, w_s) if ctx.needs_input_grad[0] else None
         return dx, ret_cw, ret_w, ret_b, None, None, None
 
@@ -209,10 +221,13 @@ def _decoder_backward(x, w, b, w_s, dlogits, need_dx):
     """dlogits [N, T, ld] (columns >= V are zero) -> dx; accumulates dw [V, Cin, 1] and db [V]."""
     V = w.shape[0]
     g_w, ret_w = runtime.grad_sink(w)
-    ops.pwconv_wgrad(dlogits, x, out=g_w, Cout=V)
     g_b, ret_b = runtime.grad_sink(b)
-    ops.colsum(dlogits, V, out=g_b)
-    runtime.grad_ready(w, b)
+
+    def _wgrad():
+        ops.pwconv_wgrad(dlogits, x, out=g_w, Cout=V)
+        ops.colsum(dlogits, V, out=g_b)
+        runtime.grad_ready(w, b)
+    runtime.defer(_wgrad, dlogits, x)
     dx = ops.pwconv_dgrad(dlogits, w_s, lddy=dlogits.shape[-1]) if need_dx else None
     return dx, ret_w, ret_b
 

@@ -13,6 +13,8 @@ its own launch costs more than the kernels take, so the step engine (trainer.Tra
 Without an installed bank (plain `module(x)` / `loss.backward()` usage, unit tests) every helper falls back to
 per-call torch allocations and per-call casts: same kernels, same results, more launches.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -47,6 +49,13 @@ class ParamBank:
         self.shadow_fresh = False
         self.shadow_synced = False  # set by optim.Novograd: its update pass already rewrote the bf16 shadows
         self.on_grad_ready = None  # callable(param) installed by ddp.GradSync
+        # weight-gradient kernels are off the critical path of backward (nothing reads them before the step ends):
+        # defer() launches them on a lower-priority side stream so they fill the SMs that the main chain leaves idle
+        # at kernel boundaries and tails.  Their inputs are kept alive until join_side().  OPT-IN (LASR_SIDE_WGRAD=1):
+        # measured on B200 it is a loss (asr13x1 step 3.88 -> 4.01 ms) -- the persistent kernels are bound by L2 / HBM
+        # throughput, not by idle SMs, so co-running them only disturbs their static work partition.
+        self.side = torch.cuda.Stream(priority=0) if os.environ.get("LASR_SIDE_WGRAD", "0") == "1" else None
+        self.keepalive = []
         with torch.no_grad():
             for p in params:
                 o = self.offsets[id(p)]
@@ -74,6 +83,12 @@ class ParamBank:
     def end_step(self):
         self.armed = False
         self.shadow_fresh = False  # the optimizer is about to change the masters
+
+    def join_side(self):
+        """The current stream waits for every deferred weight-gradient kernel; their inputs may be freed again."""
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        self.keepalive.clear()
 
     def invalidate_shadow(self):
         """Call after changing parameters behind the runtime's back (load_state_dict, manual edits)."""
@@ -162,6 +177,19 @@ def grad_sink(p):
             return v, None
     g = torch.zeros_like(p, dtype=torch.float32)
     return g, g
+
+
+def defer(fn, *keep):
+    """Run fn() -- kernels whose results nothing in the rest of backward reads (weight gradients) -- on the bank's side
+    stream, ordered after everything enqueued so far on the current stream.  Without an armed bank: just fn()."""
+    b = _BANK["bank"]
+    if b is None or not b.armed or b.side is None:
+        fn()
+        return
+    b.side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(b.side):
+        fn()
+    b.keepalive.extend(keep)
 
 
 def grad_ready(*params):

@@ -182,6 +182,7 @@ class TrainEngine:
         else:
             loss, _, _ = m.training_step_tensors(self.static)
         loss.backward()
+        self.bank.join_side()  # deferred weight-gradient kernels (runtime.defer) are part of this step
         if self.grad_sync is not None:
             self.grad_sync(m)
         if self.optimizer is not None:
@@ -190,7 +191,9 @@ class TrainEngine:
         self.loss_dev.copy_(loss.detach())
 
     def _capture(self):
-        s = torch.cuda.Stream()
+        # the step's main chain is captured from a HIGH-priority stream; the deferred weight-gradient kernels
+        # (runtime.defer) sit on the bank's default-priority side stream and only fill SMs the chain leaves idle
+        s = torch.cuda.Stream(priority=-1)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(3):
@@ -198,7 +201,7 @@ class TrainEngine:
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=s):
             self._step_eager()
         torch.cuda.synchronize()
         self.graph = graph
