@@ -42,6 +42,19 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def load_traffic(family):
+    """Mean DRAM bytes (read + write) per launch of a kernel family, from the committed `ncu --set full` capture of
+    the same workload (profiles/traffic.json, written by tools/ncu_traffic.py).  None if the family was not captured."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        d = json.load(open(p)).get(family)
+        return None if d is None else d["dram_bytes_per_launch"]
+    except (ValueError, KeyError):
+        return None
+
+
 def labels_for(vocab):
     if vocab == "labels28":
         return LABELS28
@@ -482,7 +495,7 @@ def run_b200(args):
         peak = peaks["hbm_gbs"]
         ach = t["bytes"] / (t["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
-    roof.update({"traffic": None, "kernel": tname, "peak_source": peaks["source"] + " (sustained)",
+    roof.update({"traffic": load_traffic(tname), "kernel": tname, "peak_source": peaks["source"] + " (sustained)",
                  "share_of_step": t["ms"] / total_ms if total_ms else None,
                  "families": {k: {"ms": round(v["ms"], 4), "GB/s": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
                                   "TFLOP/s": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1), "calls": v["calls"]}

@@ -210,6 +210,20 @@ int lasr_se_bn_bwd_finalize(const float* partials, int N, int chunks, int C, int
 int lasr_logmel_padded_len(int T_max);
 int lasr_logmel_prepare(const float* wave, const float* dither, const int32_t* num_samples, void* parts, int N,
                         int S_max, int T_max, lasr_stream_t stream);
+/* Train-time augmentation on the device, same arithmetic as the reference's host code:
+ *   prepare_crop : sub_secquence (data_module.py:138-148, applied at :158-159 AFTER dither + pre-emphasis): utterance n
+ *                  keeps samples [starts[n], starts[n] + num_samples[n]) of its pre-emphasised waveform
+ *                  (starts == NULL: no crop).  The reference's slice x[:, loc:L] is starts = loc, num_samples = L - loc.
+ *   spec_augment : spec_augment (data_module.py:97-122, applied to the dB spectrogram at :163-165, before the
+ *                  normalisation): bands [N, 4] int32 = (f0, fw, t0, tw): mel bins [f0, f0+fw) of every frame and
+ *                  frames [t0, t0+tw) of every bin are set to 0 and `stats` is corrected accordingly.  Call between
+ *                  lasr_logmel_fwd and lasr_logmel_normalize.  The caller draws the band positions (the reference uses
+ *                  an unseeded random.Random(), :65,112-116). */
+int lasr_logmel_prepare_crop(const float* wave, const float* dither, const int32_t* starts,
+                             const int32_t* num_samples, void* parts, int N, int S_max, int T_max,
+                             lasr_stream_t stream);
+int lasr_spec_augment(float* db, double* stats, const int32_t* num_samples, const int32_t* bands, int N, int T_max,
+                      lasr_stream_t stream);
 int lasr_logmel_fwd(const void* parts, const void* basis, const int32_t* mel_idx, const float* mel_w,
                     const int32_t* num_samples, float* db, double* stats, int N, int T_max, int products,
                     lasr_stream_t stream);

@@ -40,13 +40,17 @@ __device__ __forceinline__ int lm_frames(int num_samples) { return 1 + (num_samp
 // prepare: parts[p][n][k] = bf16 term p of e_n[k], k < Lp
 // ------------------------------------------------------------------------------------------------
 __global__ void logmel_prepare_kernel(const float* __restrict__ wave, const float* __restrict__ dither,
-                                      const int32_t* __restrict__ num_samples, __nv_bfloat16* __restrict__ parts,
-                                      int N, int S_max, int Lp) {
+                                      const int32_t* __restrict__ starts, const int32_t* __restrict__ num_samples,
+                                      __nv_bfloat16* __restrict__ parts, int N, int S_max, int Lp) {
   const int n = blockIdx.y;
   const int S = num_samples[n];
   const int L = S + 2 * LM_PAD;  // after MelSpectrogram(pad=32)
-  const float* w = wave + static_cast<size_t>(n) * S_max;
-  const float* dth = dither ? dither + static_cast<size_t>(n) * S_max : nullptr;
+  // train-time crop (sub_secquence, data_module.py:138-148,158-159) happens AFTER dither + pre-emphasis of the whole
+  // utterance: the cropped stream starts at sample `st` of the pre-emphasised signal, so its first sample still sees
+  // its predecessor
+  const int st = starts != nullptr ? starts[n] : 0;
+  const float* w = wave + static_cast<size_t>(n) * S_max + st;
+  const float* dth = dither ? dither + static_cast<size_t>(n) * S_max + st : nullptr;
   const size_t plane = static_cast<size_t>(N) * Lp;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < Lp; k += gridDim.x * blockDim.x) {
     // k + 96 indexes the reflect-padded stream; j indexes the zero-padded one
@@ -63,7 +67,7 @@ __global__ void logmel_prepare_kernel(const float* __restrict__ wave, const floa
           return x;
         };
         v = sample(s);
-        if (s > 0) v = __fsub_rn(v, __fmul_rn(0.97f, sample(s - 1)));  // :157, two roundings like torch
+        if (s + st > 0) v = __fsub_rn(v, __fmul_rn(0.97f, sample(s - 1)));  // :157, two roundings like torch
       }
     }
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -308,6 +312,43 @@ logmel_fwd_kernel(const __grid_constant__ CUtensorMap tma_a0, const __grid_const
 // ------------------------------------------------------------------------------------------------
 // normalise
 // ------------------------------------------------------------------------------------------------
+// SpecAugment in the dB domain, BEFORE the normalisation (spec_augment, data_module.py:97-122,163-165): one frequency
+// band [f0, f0+fw) over all frames and one time band [t0, t0+tw) over all mel bins are set to 0; the utterance's
+// (sum, sum of squares) statistics are corrected by what was removed, so the normalise pass sees exactly the masked
+// spectrogram.  Band positions come from the host (the reference draws them from an unseeded random.Random()).
+// grid (chunks, N), 256 threads.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+spec_augment_kernel(float* __restrict__ db, double* __restrict__ stats, const int32_t* __restrict__ num_samples,
+                    const int32_t* __restrict__ bands, int T_max) {
+  const int n = blockIdx.y;
+  const int T_n = lm_frames(num_samples[n]);
+  const int f0 = bands[4 * n], fw = bands[4 * n + 1], t0 = bands[4 * n + 2], tw = bands[4 * n + 3];
+  float* d = db + static_cast<size_t>(n) * T_max * LM_MELS;
+  double s1 = 0.0, s2 = 0.0;
+  const int total = T_n * LM_MELS;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int t = i / LM_MELS, m = i - t * LM_MELS;
+    const bool masked = (m >= f0 && m < f0 + fw) || (t >= t0 && t < t0 + tw);
+    if (masked) {
+      const float v = d[i];
+      s1 += static_cast<double>(v);
+      s2 += static_cast<double>(v) * static_cast<double>(v);
+      d[i] = 0.f;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if ((threadIdx.x & 31) == 0 && (s1 != 0.0 || s2 != 0.0)) {
+    atomicAdd(stats + 2 * n, -s1);
+    atomicAdd(stats + 2 * n + 1, -s2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 template <typename OutT>
 __global__ void logmel_normalize_kernel(const float* __restrict__ db, const double* __restrict__ stats,
                                         const int32_t* __restrict__ num_samples, float* __restrict__ out_nct,
@@ -348,13 +389,28 @@ extern "C" {
 
 int lasr_logmel_padded_len(int T_max) { return LM_HOP * (T_max + 1); }
 
-int lasr_logmel_prepare(const float* wave, const float* dither, const int32_t* num_samples, void* parts, int N,
-                        int S_max, int T_max, lasr_stream_t stream) {
+int lasr_logmel_prepare_crop(const float* wave, const float* dither, const int32_t* starts,
+                             const int32_t* num_samples, void* parts, int N, int S_max, int T_max,
+                             lasr_stream_t stream) {
   if (N <= 0 || S_max <= 0 || T_max <= 0) return LASR_ERR_BAD_SHAPE;
   const int Lp = lasr_logmel_padded_len(T_max);
   dim3 grid(cdiv(Lp, 256 * 4) < 1 ? 1 : cdiv(Lp, 256 * 4), N);
-  logmel_prepare_kernel<<<grid, 256, 0, stream>>>(wave, dither, num_samples, static_cast<__nv_bfloat16*>(parts), N,
-                                                  S_max, Lp);
+  logmel_prepare_kernel<<<grid, 256, 0, stream>>>(wave, dither, starts, num_samples,
+                                                  static_cast<__nv_bfloat16*>(parts), N, S_max, Lp);
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+int lasr_logmel_prepare(const float* wave, const float* dither, const int32_t* num_samples, void* parts, int N,
+                        int S_max, int T_max, lasr_stream_t stream) {
+  return lasr_logmel_prepare_crop(wave, dither, nullptr, num_samples, parts, N, S_max, T_max, stream);
+}
+
+int lasr_spec_augment(float* db, double* stats, const int32_t* num_samples, const int32_t* bands, int N, int T_max,
+                      lasr_stream_t stream) {
+  if (N <= 0 || T_max <= 0 || db == nullptr || stats == nullptr || bands == nullptr) return LASR_ERR_BAD_SHAPE;
+  dim3 grid(8, N);
+  spec_augment_kernel<<<grid, 256, 0, stream>>>(db, stats, num_samples, bands, T_max);
   LASR_CHECK_LAUNCH();
   return LASR_OK;
 }

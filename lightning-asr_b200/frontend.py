@@ -86,17 +86,43 @@ def constants(device, sr=SR):
     return out
 
 
-def logmel_batch(waves, num_samples, dither=None, out_dtype=None, want_nct=True, products=6, sr=SR):
+def draw_augment(num_samples, rng):
+    """The random draws of parse_audio(mask=True) (data_module.py:158-165) for one utterance of `num_samples` samples,
+    in the reference's order and arithmetic: sub_secquence(weight=0.98) (:138-148; the slice is x[:, loc:L], so
+    L - loc samples survive) then spec_augment(freq_mask=27, time_mask=0.07) (:97-122) on the cropped spectrogram.
+    `rng`: anything with .uniform(a, b), e.g. a seeded random.Random -- the reference's own generators are unseeded.
+    -> (start, kept_samples, (f0, fw, t0, tw)) for logmel_batch(starts=..., num_samples=kept, bands=...)."""
+    target_length = int(num_samples * rng.uniform(0.98, 1))
+    location = int(rng.uniform(0, num_samples - target_length))
+    kept = max(target_length - location, 0)
+    T = num_frames(kept)
+    w_x = int(rng.uniform(0, 27))
+    w_y = int(rng.uniform(0, int(T * 0.07)))
+    rect_x = int(rng.uniform(0, N_MELS - w_x))
+    rect_y = int(rng.uniform(0, T - w_y))
+    return location, kept, (rect_x, w_x, rect_y, w_y)
+
+
+def logmel_batch(waves, num_samples, dither=None, out_dtype=None, want_nct=True, products=6, sr=SR, starts=None,
+                 bands=None):
     """waves [N, S_max] fp32 CUDA (zero padded), num_samples [N] int -> dict with
          'inputs'  [N, 1, 64, T_max] fp32 (reference layout, if want_nct)
          'ntc'     [N, T_max, 64] out_dtype (channels-last encoder input, if out_dtype is not None)
          'percents'[N] fp32 = T_n / T_max  (data_module.py:244), 'frames' [N] int32
+       Train-time augmentation on the device (draw_augment): starts [N] int = first kept sample of each utterance's
+       pre-emphasised waveform (num_samples then counts the KEPT samples), bands [N, 4] int = SpecAugment
+       (f0, fw, t0, tw) applied in the dB domain before the normalisation.
     """
     if not waves.is_cuda:
         raise _lib.LasrError("logmel_batch needs CUDA tensors (no CPU fallback)")
     waves = waves.contiguous().float()
     N, S_max = waves.shape
     ns_host = num_samples.cpu() if isinstance(num_samples, torch.Tensor) else torch.tensor(num_samples)
+    st_host = None
+    if starts is not None:
+        st_host = (starts.cpu() if isinstance(starts, torch.Tensor) else torch.tensor(starts)).long()
+        if int(st_host.min()) < 0 or int((st_host + ns_host.long()).max()) > S_max:
+            raise _lib.LasrError("starts + num_samples must stay inside the waveform")
     if int(ns_host.max()) > S_max or int(ns_host.min()) <= N_FFT // 2:
         raise _lib.LasrError("num_samples must be in (256, S_max] (reflect padding needs more than n_fft/2 samples)")
     T_max = num_frames(int(ns_host.max()))
@@ -105,10 +131,16 @@ def logmel_batch(waves, num_samples, dither=None, out_dtype=None, want_nct=True,
     basis, mel_idx, mel_w = constants(dev, sr)
     Lp = _lib.load().lasr_logmel_padded_len(T_max)
     parts = torch.empty((3, N, Lp), device=dev, dtype=torch.bfloat16)
-    _lib.call("lasr_logmel_prepare", waves, dither, ns, parts, N, S_max, T_max)
+    st = st_host.to(device=dev, dtype=torch.int32) if st_host is not None else None
+    _lib.call("lasr_logmel_prepare_crop", waves, dither, st, ns, parts, N, S_max, T_max)
     db = torch.empty((N, T_max, N_MELS), device=dev, dtype=torch.float32)
     stats = torch.zeros((N, 2), device=dev, dtype=torch.float64)
     _lib.call("lasr_logmel_fwd", parts, basis, mel_idx, mel_w, ns, db, stats, N, T_max, products)
+    if bands is not None:
+        b = (bands if isinstance(bands, torch.Tensor) else torch.tensor(bands)).to(device=dev, dtype=torch.int32)
+        if tuple(b.shape) != (N, 4):
+            raise _lib.LasrError("bands must be [N, 4] = (f0, fw, t0, tw) per utterance")
+        _lib.call("lasr_spec_augment", db, stats, ns, b.contiguous(), N, T_max)
     out_nct = torch.empty((N, 1, N_MELS, T_max), device=dev, dtype=torch.float32) if want_nct else None
     out_ntc = torch.empty((N, T_max, N_MELS), device=dev, dtype=out_dtype) if out_dtype is not None else None
     _lib.call("lasr_logmel_normalize", db, stats, ns, out_nct, out_ntc, N, T_max,

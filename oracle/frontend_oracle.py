@@ -51,12 +51,35 @@ def num_frames(num_samples):
     return 1 + (num_samples + 2 * PAD) // HOP
 
 
-def logmel(wave, dither=None, dtype=torch.float32):
-    """wave [S] (one utterance) -> normalised log-mel [1, 64, T]; data_module.py:155-172 with mask=False."""
+def draw_augment(num_samples, rng):
+    """The random draws of parse_audio(mask=True) for one utterance, in the reference's order and arithmetic:
+    sub_secquence(weight=0.98) :138-148 -> (location, target_length), the slice is x[:, location:target_length] (sic);
+    spec_augment(freq_mask=27, time_mask=0.07) :97-122 -> (w_x, w_y, rect_x, rect_y) on the cropped spectrogram.
+    `rng` is anything with .uniform(a, b) (the reference uses np.random for the crop and an unseeded random.Random()
+    for the bands).  -> (start, kept_samples, (f0, fw, t0, tw))"""
+    length = num_samples
+    target_length = int(length * rng.uniform(0.98, 1))
+    location = int(rng.uniform(0, length - target_length))
+    kept = max(target_length - location, 0)
+    T = num_frames(kept)
+    freq_mask, time_mask = 27, int(T * 0.07)
+    w_x = int(rng.uniform(0, freq_mask))
+    w_y = int(rng.uniform(0, time_mask))
+    rect_x = int(rng.uniform(0, N_MELS - w_x))
+    rect_y = int(rng.uniform(0, T - w_y))
+    return location, kept, (rect_x, w_x, rect_y, w_y)
+
+
+def logmel(wave, dither=None, dtype=torch.float32, crop=None, bands=None):
+    """wave [S] (one utterance) -> normalised log-mel [1, 64, T]; data_module.py:155-172.  mask=False by default;
+    crop=(start, kept_samples) and bands=(f0, fw, t0, tw) replay the train-time augmentation (:158-159, :163-165) with
+    explicit draws."""
     y = wave.reshape(1, -1).to(dtype)
     if dither is not None:
         y = y + 1e-5 * dither.reshape(1, -1).to(dtype)  # :155 (torch.randn_like in the reference)
     y = preemphasis(y)
+    if crop is not None:
+        y = y[:, crop[0]:crop[0] + crop[1]]  # :158-159
     y = torch.nn.functional.pad(y, (PAD, PAD), "constant")  # MelSpectrogram(pad=32)
     window = torch.hann_window(WIN, periodic=True, dtype=dtype)
     spec = torch.stft(y, N_FFT, hop_length=HOP, win_length=WIN, window=window, center=True, pad_mode="reflect",
@@ -65,6 +88,11 @@ def logmel(wave, dither=None, dtype=torch.float32):
     fb = mel_filterbank(dtype=dtype)  # [257, 64]
     mel = torch.matmul(power.transpose(1, 2), fb).transpose(1, 2)  # [1, 64, T]
     db = 10.0 * torch.log10(torch.clamp(mel, min=1e-10))  # AmplitudeToDB(stype="power"), ref 1.0
+    if bands is not None:  # :110-121: both bands set to 0 in the dB domain, before the statistics
+        f0, fw, t0, tw = bands
+        db = db.clone()
+        db[0, f0:f0 + fw, :] = 0
+        db[0, :, t0:t0 + tw] = 0
     std, mean = torch.std_mean(db)  # :171 global, unbiased
     return (db - mean) / std  # :172
 

@@ -102,3 +102,32 @@ def test_audio_parser_contract(frontend, tmp_path):
     assert rel_err(feat.cpu(), ref) < 1e-4
     with pytest.raises(FileExistsError):
         parser.parse_audio(str(tmp_path / "missing.wav"))
+
+
+def test_device_augmentation_matches_reference_fixture(frontend):
+    """logmel_batch(starts=, bands=) -- crop after pre-emphasis + SpecAugment in the dB domain + statistics correction,
+    all on the device -- against the reference's own parse_audio(mask=True) output (tests/golden/augment.pt)."""
+    import os
+    import random
+
+    fx = torch.load(os.path.join(GOLDEN, "augment.pt"), weights_only=False)
+    names = sorted(fx)
+    waves = [seeded_wave(fx[k]["samples"], fx[k]["seed"]) for k in names]
+    draws = [frontend.draw_augment(fx[k]["samples"], random.Random(fx[k]["rng_seed"])) for k in names]
+    S = max(len(w) for w in waves)
+    x = torch.zeros(len(waves), S)
+    for i, w in enumerate(waves):
+        x[i, :len(w)] = w
+    out = frontend.logmel_batch(x.cuda(), [d[1] for d in draws], starts=[d[0] for d in draws],
+                                bands=[list(d[2]) for d in draws])
+    for i, k in enumerate(names):
+        ref = fx[k]["features"]
+        T = ref.shape[-1]
+        assert T == int(out["frames"][i])
+        got = out["inputs"][i, :, :, :T].cpu()
+        assert rel_err(got, ref) < 1e-4, k
+        f0, fw, t0, tw = draws[i][2]
+        # masked cells hold exactly the normalised zero: -mean/std, one constant
+        if fw > 0:
+            band = got[0, f0:f0 + fw, :]
+            assert float(band.max() - band.min()) == 0.0

@@ -140,3 +140,20 @@ def test_optimizer_oracle_matches_reference():
         for st, v, m in zip(state, fx[name]["exp_avg_sq"], fx[name]["exp_avg"]):
             assert abs(float(st["exp_avg_sq"]) - v) <= 1e-6 * abs(v)
             assert torch.allclose(st["exp_avg"], m, rtol=1e-6, atol=1e-8)
+
+
+def test_augment_oracle_matches_reference():
+    """oracle.frontend_oracle.draw_augment + logmel(crop=, bands=) vs tests/golden/augment.pt = the reference's own
+    AudioParser.parse_audio(mask=True) with its random generators seeded (tests/golden/make_golden_augment.py)."""
+    import random
+
+    fx = _load("augment.pt")
+    for name, d in fx.items():
+        w = seeded_wave(d["samples"], d["seed"])
+        start, kept, bands = frontend_oracle.draw_augment(d["samples"], random.Random(d["rng_seed"]))
+        got = frontend_oracle.logmel(w, crop=(start, kept), bands=bands)
+        assert got.shape == d["features"].shape, name
+        assert rel_err(got, d["features"]) < 1e-5, name
+        # the product's host-side draw (no oracle import there) follows the same arithmetic
+        from lightning_asr_b200 import frontend
+        assert frontend.draw_augment(d["samples"], random.Random(d["rng_seed"])) == (start, kept, bands)

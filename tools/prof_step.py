@@ -10,7 +10,7 @@ model_name, n, seconds, vocab, precision = bench.WORKLOADS[wl]
 labels = bench.labels_for(vocab)
 torch.manual_seed(0)
 mod = LightingModule(labels=labels, mask=True, model_name=model_name, precision=precision).cuda().train()
-eng = TrainEngine(mod, synthetic_batch(n, seconds, len(labels), seed=1234), graph=False)
+eng = TrainEngine(mod, synthetic_batch(n, seconds, len(labels), seed=1234), graph=False, optimizer="novograd")
 for _ in range(steps):
     eng.step_device()
 torch.cuda.synchronize()
