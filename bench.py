@@ -413,7 +413,7 @@ def run_b200(args):
         ddp.broadcast_parameters(module)
     batch = synthetic_batch(n, seconds, len(labels), seed=1234 + rank, ragged=False)
     use_graph = not args.no_graph
-    engine = TrainEngine(module, batch, graph=use_graph, fused=True, world_sync=(None, 8.0) if world > 1 else None,
+    engine = TrainEngine(module, batch, graph=use_graph, fused=True, world_sync=(None, float(os.environ.get("LASR_BUCKET_MB", "8"))) if world > 1 else None,
                          optimizer=None if args.no_optimizer else "novograd")
     graph_note = use_graph
     try:

@@ -700,6 +700,266 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant of the weight-stationary kernel (cta_group::2): the two SMs of a TPC work on one 256-row x 256-column
+// output tile.  Each CTA streams ITS 128 activation rows and keeps ITS 128 weight rows (half of the pair's 256-column
+// slice) resident; the pair-MMA (M = 256, N = 256, issued by the leader CTA) reads both halves of B across the pair,
+// so every activation tile fetched from L2 now feeds 256 output columns instead of 128 -- the L2 -> SM activation
+// traffic that paces the single-CTA kernel (tile period = activation tile / ~57 GB/s per SM) is halved.
+// Barriers: TMA loads of both CTAs count bytes on the LEADER's full / weight barriers; the leader's MMA commits
+// multicast to both CTAs' empty and accumulator-full barriers; both CTAs' epilogue warps arrive on the leader's
+// accumulator-empty barrier.  Per CTA: 128 rows x 256 fp32 columns x 2 buffers = all 512 TMEM columns.
+// ------------------------------------------------------------------------------------------------
+template <bool B_MN>
+__global__ void __launch_bounds__(384, 1)
+gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                const __grid_constant__ CUtensorMap tma_c, const GemmWsParams p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* s_w = smem;                                        // [num_k_blocks][16 KB]: this CTA's 128 weight rows
+  uint8_t* s_a = s_w + p.num_k_blocks * WS_WKB_BYTES;         // [stages][16 KB]: this CTA's 128 activation rows
+  uint8_t* s_stg = s_a + p.stages * WS_A_BYTES;               // [2][128 rows x 128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_stg + WS_STG_BYTES);
+  uint64_t* empty_bar = full_bar + WS_MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + WS_MAX_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint64_t* w_bar = tmem_empty_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int crank = static_cast<int>(cluster_ctarank());
+  const bool is_leader = crank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int n_blk2 = pair % p.num_n_blocks;     // 256-column slice of the pair
+  const int m_first = pair / p.num_n_blocks;    // 256-row tiles m_first, m_first + ctas_per_n, ...
+  const int n0 = n_blk2 * 256;                  // first output column of the pair
+  const int nw0 = n0 + crank * WS_BN;           // first weight row (output column) this CTA keeps
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_c);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);   // leader's: its producer's arrive.expect_tx (bytes of BOTH CTAs)
+      mbar_init(&empty_bar[s], 1);  // each CTA's: the leader's multicast commit
+    }
+    mbar_init(&tmem_full_bar[0], 1);
+    mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 8);  // leader's: 4 epilogue warps of each CTA
+    mbar_init(&tmem_empty_bar[1], 8);
+    mbar_init(w_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc_2sm(tmem_ptr_smem, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before any remote arrive / byte count
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  if (warp_idx != 0) pdl_wait();
+
+  if (warp_idx == 0) {
+    // ===================== TMA producer (both CTAs; bytes are counted on the leader's barriers) ==================
+    const bool leader_lane = elect_one();
+    if (!p.w_early) pdl_wait();
+    if (leader_lane && is_leader) mbar_arrive_expect_tx(w_bar, 2u * static_cast<uint32_t>(p.num_k_blocks) * WS_WKB_BYTES);
+    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      uint8_t* dst = s_w + kb * WS_WKB_BYTES;
+      if (leader_lane) {
+        if constexpr (!B_MN) {
+          tma_load_2d_2sm(dst, &tma_b, w_bar, kb * WS_BK, nw0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < WS_BN / 64; ++c)
+            tma_load_2d_2sm(dst + c * (64 * WS_BK * 2), &tma_b, w_bar, nw0 + c * 64, kb * WS_BK);
+        }
+      }
+    }
+    __syncwarp();
+    pdl_wait();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int m2 = m_first; m2 < p.num_m_blocks; m2 += p.ctas_per_n) {
+      const int row0 = m2 * 256 + crank * WS_BM;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (leader_lane) {
+          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * WS_A_BYTES);
+          tma_load_2d_2sm(s_a + stage * WS_A_BYTES, &tma_a, &full_bar[stage], kb * WS_BK, row0);
+        }
+        __syncwarp();
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================== MMA issuer: leader CTA only =====================
+    if (is_leader) {
+      const bool leader_lane = elect_one();
+      constexpr uint32_t idesc = umma_idesc_bf16(256, 256, 0, B_MN ? 1 : 0);
+      mbar_wait(w_bar, 0);
+      tc_fence_after();
+      int stage = 0;
+      uint32_t phase = 0;
+      int local_tile = 0;
+      for (int m2 = m_first; m2 < p.num_m_blocks; m2 += p.ctas_per_n, ++local_tile) {
+        const int acc = local_tile & 1;
+        const uint32_t acc_phase = (local_tile >> 1) & 1;
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * 256;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(s_a + stage * WS_A_BYTES);
+          const uint32_t sb = smem_u32(s_w + kb * WS_WKB_BYTES);
+#pragma unroll
+          for (int k = 0; k < WS_BK / 16; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, 64 * WS_BK * 2, 1024)
+                                     : umma_desc_sw128(sb + k * 32, 16, 1024);
+            if (leader_lane) umma_bf16_2sm(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          if (leader_lane) umma_commit_2sm(&empty_bar[stage]);
+          __syncwarp();
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (leader_lane) umma_commit_2sm(&tmem_full_bar[acc]);
+        __syncwarp();
+      }
+    }
+  } else if (warp_idx >= 4 && warp_idx < 8) {
+    // ===================== epilogue: this CTA's 128 rows x 256 columns, two 128-column passes ================
+    const int ew = warp_idx - 4;
+    const int r = ew * 32 + lane;
+    int local_tile = 0;
+    for (int m2 = m_first; m2 < p.num_m_blocks; m2 += p.ctas_per_n, ++local_tile) {
+      const int acc = local_tile & 1;
+      const uint32_t acc_phase = (local_tile >> 1) & 1;
+      const int row = m2 * 256 + crank * WS_BM + r;
+      bool keep = row < p.M;
+      if (keep && p.lengths != nullptr) {
+        const int n = row / p.T;
+        keep = (row - n * p.T) < p.lengths[n];
+      }
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        if (threadIdx.x == 128) tma_store_wait_read<0>();
+        named_bar_sync(1, 256);
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * 256 + h * WS_BN;
+#pragma unroll
+        for (int ch = 0; ch < WS_BN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr0 + ch * 32, v);
+          tmem_ld_wait();
+          const int col0 = n0 + h * WS_BN + ch * 32;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
+          }
+          if (!keep) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          }
+          uint8_t* sub = s_stg + (ch >> 1) * (WS_BM * 128) + r * 128;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = f32x2_to_bf16x2(f[8 * q + 0], f[8 * q + 1]);
+            u.y = f32x2_to_bf16x2(f[8 * q + 2], f[8 * q + 3]);
+            u.z = f32x2_to_bf16x2(f[8 * q + 4], f[8 * q + 5]);
+            u.w = f32x2_to_bf16x2(f[8 * q + 6], f[8 * q + 7]);
+            const int c16 = (ch & 1) * 4 + q;
+            *reinterpret_cast<uint4*>(sub + ((c16 ^ (r & 7)) << 4)) = u;
+          }
+        }
+        if (h == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[acc]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(2, 256);
+        if (threadIdx.x == 128) {
+#pragma unroll
+          for (int j = 0; j < WS_BN / 64; ++j)
+            tma_store_2d(&tma_c, s_stg + j * (WS_BM * 128), n0 + h * WS_BN + j * 64, m2 * 256 + crank * WS_BM);
+          tma_store_commit();
+        }
+      }
+    }
+    if (threadIdx.x == 128) tma_store_wait<0>();
+  } else if (warp_idx >= 8) {
+    // ===================== BatchNorm statistics from the staging tile (per 128-column pass) =====================
+    const int sw = warp_idx - 8;
+    const int sub = sw & 1;
+    const int r0 = (sw >> 1) * 64;
+    float s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, q0[2] = {0.f, 0.f}, q1[2] = {0.f, 0.f};
+    const bool want = p.stats != nullptr;
+    for (int m2 = m_first; m2 < p.num_m_blocks; m2 += p.ctas_per_n) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        named_bar_sync(1, 256);
+        named_bar_sync(2, 256);
+        if (want) {
+          const uint8_t* base = s_stg + sub * (WS_BM * 128);
+#pragma unroll 8
+          for (int rr = 0; rr < 64; ++rr) {
+            const int r = r0 + rr;
+            const uint32_t w =
+                *reinterpret_cast<const uint32_t*>(base + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+            const float2 v = bf16x2_to_f32x2(w);
+            s0[h] += v.x;
+            s1[h] += v.y;
+            q0[h] = fmaf(v.x, v.x, q0[h]);
+            q1[h] = fmaf(v.y, v.y, q1[h]);
+          }
+        }
+      }
+    }
+    if (want) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int col = n0 + h * WS_BN + sub * 64 + 2 * lane;
+        if (col < p.N) {
+          red_add_f64(p.stats + col, static_cast<double>(s0[h]));
+          red_add_f64(p.stats + p.N + col, static_cast<double>(q0[h]));
+        }
+        if (col + 1 < p.N) {
+          red_add_f64(p.stats + col + 1, static_cast<double>(s1[h]));
+          red_add_f64(p.stats + p.N + col + 1, static_cast<double>(q1[h]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA leaves (or frees TMEM) while its partner may still signal it or read its operands
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -897,6 +1157,90 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
   return LASR_OK;
 }
 
+// CTA-pair launch (gemm_ws2_kernel); LASR_ERR_UNSUPPORTED when the shape does not qualify
+static int launch_ws2(bool b_mn, const void* a, const void* b, void* out, const float* bias, const int32_t* lengths,
+                      int T, double* stats, int M, int N, int K, int lda, int ldb, int ldc, cudaStream_t stream) {
+  // Measured (tools/bench_kernels.py, M = 25 632): the pair wins where the activation tile is large, K >= 512
+  // (512->512 fwd+stats 29.5 -> 25.4 us, 512->1024 48 -> 33.7 us, dgrad of 256->512 21.2 -> 19.3 us) and loses at K = 256
+  // (256->256 16.4 -> 21.5 us: 101 pair tiles over 74 pairs is two full rounds).  LASR_GEMM_PAIR=0 disables it,
+  // LASR_GEMM_PAIR=2 forces it for every N >= 256.
+  static const int mode = getenv("LASR_GEMM_PAIR") != nullptr ? atoi(getenv("LASR_GEMM_PAIR")) : 1;
+  if (mode == 0) return LASR_ERR_UNSUPPORTED;
+  const int kbs = cdiv(K, WS_BK);
+  if (mode == 1 && K < 512) return LASR_ERR_UNSUPPORTED;
+  if (N < 256 || kbs * WS_WKB_BYTES > 131072) return LASR_ERR_UNSUPPORTED;
+  if ((ldc % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return LASR_ERR_UNSUPPORTED;
+  CUtensorMap ta, tb, tc;
+  int rc = make_tmap_2d_bf16(&ta, a, K, M, static_cast<uint64_t>(lda) * 2, 64, 128, true);
+  if (rc) return rc;
+  if (!b_mn)
+    rc = make_tmap_2d_bf16(&tb, b, K, N, static_cast<uint64_t>(ldb) * 2, 64, WS_BN, true);
+  else
+    rc = make_tmap_2d_bf16(&tb, b, N, K, static_cast<uint64_t>(ldb) * 2, 64, 64, true);
+  if (rc) return rc;
+  rc = make_tmap_2d_bf16(&tc, out, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
+  if (rc) return rc;
+  GemmWsParams p{};
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.num_m_blocks = cdiv(M, 256);   // 256-row pair tiles
+  p.num_n_blocks = cdiv(N, 256);   // 256-column pair slices
+  p.num_k_blocks = kbs;
+  const int pairs = kNumSMs / 2;
+  if (p.num_n_blocks > pairs) return LASR_ERR_UNSUPPORTED;
+  int per_n = pairs / p.num_n_blocks;
+  if (per_n > p.num_m_blocks) per_n = p.num_m_blocks;
+  const int rounds = cdiv(p.num_m_blocks, per_n);
+  per_n = cdiv(p.num_m_blocks, rounds);
+  p.ctas_per_n = per_n;
+  p.cluster = 2;
+  const int budget = 232448 - 1024 - 512 - kbs * WS_WKB_BYTES - WS_STG_BYTES;
+  int stages = budget / WS_A_BYTES;
+  if (stages > WS_MAX_STAGES) stages = WS_MAX_STAGES;
+  if (stages < 2) return LASR_ERR_UNSUPPORTED;
+  p.stages = stages;
+  p.bias = bias;
+  p.lengths = lengths;
+  p.T = T;
+  p.stats = stats;
+  p.trace = nullptr;
+  p.w_early = early_param_loads() ? 1 : 0;
+  const int smem = 1024 + 512 + kbs * WS_WKB_BYTES + stages * WS_A_BYTES + WS_STG_BYTES;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_ws2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_ws2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) {
+      lasr_set_cuda_error(e);
+      return LASR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * p.num_n_blocks * per_n);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled(1) ? 2 : 1;
+  cudaError_t le = b_mn ? cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<true>, ta, tb, tc, p)
+                        : cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<false>, ta, tb, tc, p);
+  if (le != cudaSuccess) {
+    lasr_set_cuda_error(le);
+    return LASR_ERR_CUDA;
+  }
+  return LASR_OK;
+}
+
 static int pick_bn(int N) { return N <= 32 ? 32 : (N <= 64 ? 64 : (N <= 128 ? 128 : 256)); }
 
 // y[M, N] = x[M, K] w[N, K]^T, bf16 in, bf16/fp32 out
@@ -905,6 +1249,8 @@ int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const
   if (M <= 0 || N <= 0 || K <= 0) return LASR_ERR_BAD_SHAPE;
   if ((lda % 8) || (ldb % 8)) return LASR_ERR_ALIGNMENT;
   if (!out_f32 && N > 64) {
+    const int rc_ws2 = launch_ws2(false, a, b, out, bias, lengths, T, stats, M, N, K, lda, ldb, ldc, stream);
+    if (rc_ws2 != LASR_ERR_UNSUPPORTED) return rc_ws2;
     const int rc_ws = launch_ws(false, a, b, out, bias, lengths, T, stats, M, N, K, lda, ldb, ldc, stream);
     if (rc_ws != LASR_ERR_UNSUPPORTED) return rc_ws;
   }
@@ -949,6 +1295,8 @@ int gemm_tc_nn(const void* a, const void* b, void* out, int M, int N, int K, int
   if (M <= 0 || N <= 0 || K <= 0) return LASR_ERR_BAD_SHAPE;
   if ((lda % 8) || (ldb % 8)) return LASR_ERR_ALIGNMENT;
   if (!out_f32 && N > 64) {
+    const int rc_ws2 = launch_ws2(true, a, b, out, nullptr, nullptr, 0, nullptr, M, N, K, lda, ldb, ldc, stream);
+    if (rc_ws2 != LASR_ERR_UNSUPPORTED) return rc_ws2;
     const int rc_ws = launch_ws(true, a, b, out, nullptr, nullptr, 0, nullptr, M, N, K, lda, ldb, ldc, stream);
     if (rc_ws != LASR_ERR_UNSUPPORTED) return rc_ws;
   }
