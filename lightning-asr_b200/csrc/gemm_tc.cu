@@ -960,6 +960,182 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair weight gradient: dW[Cout, Cin] += dY[frames, Cout]^T X[frames, Cin] with a 256 (Cout) x 256 (Cin) pair tile.
+// Each CTA streams ITS 128 Cout columns of dY and ITS 128 Cin columns of X (32 KB per 64-frame k-block instead of the
+// 48 KB of the single-CTA 128 x 256 tile) and ends up with its 128 rows x 256 columns of the accumulator, reduced into
+// the gradient through the same TMA reduce-add epilogue.  One accumulator buffer (the split-K tiles are one per pair).
+// ------------------------------------------------------------------------------------------------
+constexpr int WG2_STAGE = 2 * 64 * 128 * 2;  // A 128 x 64 + B 128 x 64 bf16 = 32 KB
+constexpr int WG2_STAGES = 6;
+constexpr int WG2_SMEM = WG2_STAGES * WG2_STAGE + 32768 + 1024 + 256;
+
+__global__ void __launch_bounds__(256, 1)
+gemm_wgrad2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                   const __grid_constant__ CUtensorMap tma_c, const GemmTcParams p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* s_red = smem + WG2_STAGES * WG2_STAGE;  // [4 warps][2][32 rows x 128 B]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_red + 32768);
+  uint64_t* empty_bar = full_bar + WG2_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + WG2_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 1);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int crank = static_cast<int>(cluster_ctarank());
+  const bool is_leader = crank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_c);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int s = 0; s < WG2_STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(tmem_empty_bar, 8);
+    mbar_fence_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc_2sm(tmem_ptr_smem, 256);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  const int tiles_mn = p.num_m_blocks * p.num_n_blocks;  // 256 x 256 pair tiles
+  const int num_tiles = tiles_mn * p.k_splits;
+
+  if (warp_idx == 0) {
+    const bool leader_lane = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int split = tile / tiles_mn;
+      const int mn = tile - split * tiles_mn;
+      const int m_blk = mn / p.num_n_blocks;
+      const int n_blk = mn - m_blk * p.num_n_blocks;
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = smem + stage * WG2_STAGE;
+        uint8_t* sb = sa + 16384;
+        if (leader_lane) {
+          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * WG2_STAGE);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            tma_load_2d_2sm(sa + c * 8192, &tma_a, &full_bar[stage], m_blk * 256 + crank * 128 + c * 64, kb * 64);
+            tma_load_2d_2sm(sb + c * 8192, &tma_b, &full_bar[stage], n_blk * 256 + crank * 128 + c * 64, kb * 64);
+          }
+        }
+        __syncwarp();
+        if (++stage == WG2_STAGES) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (is_leader) {
+      const bool leader_lane = elect_one();
+      constexpr uint32_t idesc = umma_idesc_bf16(256, 256, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local_tile = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local_tile) {
+        const int split = tile / tiles_mn;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+        mbar_wait(tmem_empty_bar, (local_tile & 1) ^ 1u);
+        tc_fence_after();
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * WG2_STAGE);
+          const uint32_t sb = sa + 16384;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * 2048, 64 * 64 * 2, 1024);
+            const uint64_t db = umma_desc_sw128(sb + k * 2048, 64 * 64 * 2, 1024);
+            if (leader_lane) umma_bf16_2sm(tmem_base, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          if (leader_lane) umma_commit_2sm(&empty_bar[stage]);
+          __syncwarp();
+          if (++stage == WG2_STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        if (leader_lane) umma_commit_2sm(tmem_full_bar);
+        __syncwarp();
+      }
+    }
+  } else if (warp_idx >= 4) {
+    const int ew = warp_idx - 4;
+    int local_tile = 0;
+    int nred = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs, ++local_tile) {
+      const int split = tile / tiles_mn;
+      const int mn = tile - split * tiles_mn;
+      const int m_blk = mn / p.num_n_blocks;
+      const int n_blk = mn - m_blk * p.num_n_blocks;
+      mbar_wait(tmem_full_bar, local_tile & 1);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16);
+#pragma unroll 1
+      for (int ch = 0; ch < 8; ++ch) {
+        const int col0 = n_blk * 256 + ch * 32;
+        if (col0 >= p.N) break;
+        uint32_t v[32];
+        tmem_ld_32x32(taddr0 + ch * 32, v);
+        tmem_ld_wait();
+        uint8_t* buf = s_red + ew * 8192 + (nred & 1) * 4096;
+        if (nred >= 2) {
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(buf + lane * 128 + ((q ^ (lane & 7)) << 4)) =
+              make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(&tma_c, buf, col0, m_blk * 256 + crank * 128 + ew * 32);
+          tma_store_commit();
+        }
+        ++nred;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tmem_empty_bar);
+    }
+    if (lane == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp_idx == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1334,6 +1510,67 @@ int gemm_tc_tn_accum(const void* dy, const void* x, float* dw, int R, int Cout, 
                      cudaStream_t stream) {
   if (R <= 0 || Cout <= 0 || Cin <= 0) return LASR_ERR_BAD_SHAPE;
   if ((lddy % 8) || (ldx % 8)) return LASR_ERR_ALIGNMENT;
+  {
+    // CTA-pair path: 256 x 256 pair tiles, needs the TMA reduce epilogue (aligned fp32 gradient).  OPT-IN: measured
+    // equal to the single-CTA kernel (512x512: 23.5 vs 23.3 us, 1024x512: 32.8 vs 33.6 us) -- the weight gradient is
+    // paced by its split-K reduction traffic, not by operand loads.  LASR_WGRAD_PAIR=1: Cout + Cin >= 1024, =2: all.
+    static const int pair_mode = getenv("LASR_WGRAD_PAIR") != nullptr ? atoi(getenv("LASR_WGRAD_PAIR")) : 0;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dw) & 15) == 0) && ((static_cast<size_t>(lddw) * 4) % 16 == 0);
+    if (pair_mode != 0 && aligned && Cout >= 256 && Cin >= 256 && (pair_mode == 2 || Cout + Cin >= 1024)) {
+      CUtensorMap ta, tb, tc;
+      int rc = make_tmap_2d_bf16(&ta, dy, Cout, R, static_cast<uint64_t>(lddy) * 2, 64, 64, true);
+      if (rc) return rc;
+      rc = make_tmap_2d_bf16(&tb, x, Cin, R, static_cast<uint64_t>(ldx) * 2, 64, 64, true);
+      if (rc) return rc;
+      rc = make_tmap_2d_f32(&tc, dw, Cin, Cout, static_cast<uint64_t>(lddw) * 4, 32, 32, true);
+      if (rc) return rc;
+      GemmTcParams p{};
+      p.M = Cout;
+      p.N = Cin;
+      p.K = R;
+      p.num_m_blocks = cdiv(Cout, 256);
+      p.num_n_blocks = cdiv(Cin, 256);
+      p.num_k_blocks = cdiv(R, 64);
+      const int tiles = p.num_m_blocks * p.num_n_blocks;
+      const int pairs = kNumSMs / 2;
+      int splits = pairs / tiles;
+      if (splits < 1) splits = 1;
+      if (splits > p.num_k_blocks) splits = p.num_k_blocks;
+      p.kb_per_split = cdiv(p.num_k_blocks, splits);
+      p.k_splits = cdiv(p.num_k_blocks, p.kb_per_split);
+      p.out = dw;
+      p.ldc = lddw;
+      p.out_f32 = 1;
+      p.vec_ok = 1;
+      const int total = tiles * p.k_splits;
+      const int npairs = total < pairs ? total : pairs;
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM);
+        if (e != cudaSuccess) {
+          lasr_set_cuda_error(e);
+          return LASR_ERR_CUDA;
+        }
+        configured = true;
+      }
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(2 * npairs);
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = WG2_SMEM;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[2];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[1].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = pdl_enabled(1) ? 2 : 1;
+      LASR_CHECK_PDL(cudaLaunchKernelEx(&cfg, gemm_wgrad2_kernel, ta, tb, tc, p));
+      return LASR_OK;
+    }
+  }
   const int BN = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
   CUtensorMap ta, tb;
   int rc = make_tmap_2d_bf16(&ta, dy, Cout, R, static_cast<uint64_t>(lddy) * 2, 64, 64, true);
