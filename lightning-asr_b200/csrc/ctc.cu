@@ -91,6 +91,47 @@ __device__ __forceinline__ void cp_async_wait() {
 // The emission of state s at frame
 // t is ONE element of the [T, V] score matrix; the 4-byte word holding it is fetched CTC_RING frames ahead with
 // cp.async into a per-thread slot of a shared-memory ring, so the sequential recursion never waits on HBM/L2.
+// shared-memory accesses through 32-bit shared addresses (a ping-ponged `float*` makes the compiler fall back to
+// generic loads plus a shared-window conversion per access)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async_4_sa(uint32_t smem_addr, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// log(e^a + e^b + e^c), branch free: the largest term is factored out (its exponential is exactly 1: two ex2 + one lg2
+// on the MUFU pipe); an all -inf input is detected with one compare / select, and the arithmetic runs on a clamped
+// maximum so it never forms inf - inf
+__device__ __forceinline__ float lse3_bf(float a, float b, float c) {
+  const float hi = fmaxf(a, b), lo = fminf(a, b);
+  const float m = fmaxf(hi, c), mid = fminf(hi, c);
+  const float mc = fmaxf(m, -3.0e38f);
+  const float e1 = ex2_approx((mid - mc) * 1.4426950408889634f);
+  const float e2 = ex2_approx((lo - mc) * 1.4426950408889634f);
+  const float r = fmaf(lg2_approx(1.f + e1 + e2), 0.6931471805599453f, mc);
+  return m == -CUDART_INF_F ? -CUDART_INF_F : r;
+}
+
 template <typename T, int SPT, int CTC_THREADS>
 __global__ void __launch_bounds__(CTC_THREADS)
 ctc_lattice_kernel(const T* __restrict__ x, const float* __restrict__ lse, const int64_t* __restrict__ targets,
@@ -101,10 +142,14 @@ ctc_lattice_kernel(const T* __restrict__ x, const float* __restrict__ lse, const
   extern __shared__ float sm[];
   const int n = blockIdx.x;
   const bool backward = blockIdx.y == 1;
+  const int nthreads = blockDim.x;  // round_up(Lp_max, 32) for SPT == 1: no idle warps in the per-frame barrier
   const int Lp_max = 2 * S_max + 1;
-  float* col[2] = {sm, sm + Lp_max};                                     // previous / next lattice column
-  uint32_t* ring = reinterpret_cast<uint32_t*>(sm + 2 * Lp_max);         // [CTC_RING][SPT * CTC_THREADS] raw words
-  float* lring = reinterpret_cast<float*>(ring + CTC_RING * SPT * CTC_THREADS);  // [CTC_RING] row log-sum-exp
+  const int colw = Lp_max + 4;      // a lattice column: 2 cells of -inf, Lp_max states, 2 cells of -inf
+  const int W = SPT * nthreads;     // ring words per frame
+  // sm: column A [colw], column B [colw], emission ring [CTC_RING][W] raw words, lse ring [CTC_RING]
+  const uint32_t colA = smem_u32(sm), colB = colA + 4u * colw;
+  const uint32_t ring_base = colB + 4u * colw;
+  const uint32_t lring_base = ring_base + 4u * CTC_RING * W;
   const int Tn = in_len[n];
   const int Sn = tgt_len[n];
   const int Lp = 2 * Sn + 1;
@@ -112,116 +157,146 @@ ctc_lattice_kernel(const T* __restrict__ x, const float* __restrict__ lse, const
   float* lat = (backward ? beta : alpha) + static_cast<size_t>(n) * T_len * Lp_max;
   const size_t row0 = static_cast<size_t>(n) * T_len;
   const uint32_t* xw = reinterpret_cast<const uint32_t*>(x);
+  constexpr bool kHalf = sizeof(T) == 2;
 
   // infeasible / degenerate cases (torch: loss = inf when the target does not fit)
   if (Tn <= 0 || Sn > S_max || Tn > T_len) {
     if (!backward && threadIdx.x == 0) nll[n] = (Tn == 0 && Sn == 0) ? 0.f : CUDART_INF_F;
     return;
   }
-
-  int lab[SPT];
-  bool skip_ok[SPT];  // may take the s-2 (fwd) / s+2 (bwd) transition
-#pragma unroll
-  for (int i = 0; i < SPT; ++i) {
-    const int s = threadIdx.x + i * CTC_THREADS;
-    lab[i] = blank;
-    skip_ok[i] = false;
-    if (s < Lp && (s & 1)) {
-      lab[i] = static_cast<int>(tg[s >> 1]);
-      if (!backward)
-        skip_ok[i] = (s >= 2) && lab[i] != static_cast<int>(tg[(s >> 1) - 1]);
-      else
-        skip_ok[i] = (s + 2 < Lp) && lab[i] != static_cast<int>(tg[(s >> 1) + 1]);
-    }
-  }
   const int t_first = backward ? Tn - 1 : 0;
   const int dt = backward ? -1 : 1;
 
-  // fetch the emissions of step `st` (frame t_first + dt*st) into ring slot st % CTC_RING
-  auto issue = [&](int st) {
-    if (st < Tn) {
-      const int t = t_first + dt * st;
-      const size_t e0 = (row0 + t) * static_cast<size_t>(ldx);
-      uint32_t* slot = ring + (st % CTC_RING) * (SPT * CTC_THREADS);
+  // Per-state constants.  The recursion is issue-bound (one barrier and a few dozen instructions per frame and
+  // warp), so everything that does not depend on the frame lives in registers: the running global pointer of the
+  // state's emission word (advanced one row per issue), the shift that extracts a bf16 from its word (rows start on
+  // even elements: the launcher requires an even ldx), the byte offsets of the state and of its two predecessors
+  // inside a column -- a forbidden transition simply points at a cell that always holds -inf --, and the running
+  // pointer into the saved lattice.
+  const uint32_t* src[SPT];
+  uint32_t shl[SPT], off0[SPT], off1[SPT], off2[SPT];
+  bool act[SPT];
+  float* latp[SPT];
+#pragma unroll
+  for (int i = 0; i < SPT; ++i) {
+    const int st = threadIdx.x + i * nthreads;
+    act[i] = st < Lp;
+    int lab = blank;
+    bool skip_ok = false;  // may take the s-2 (alpha) / s+2 (beta) transition
+    if (act[i] && (st & 1)) {
+      lab = static_cast<int>(tg[st >> 1]);
+      if (!backward)
+        skip_ok = (st >= 2) && lab != static_cast<int>(tg[(st >> 1) - 1]);
+      else
+        skip_ok = (st + 2 < Lp) && lab != static_cast<int>(tg[(st >> 1) + 1]);
+    }
+    const size_t e = (row0 + t_first) * static_cast<size_t>(ldx) + lab;
+    src[i] = xw + (kHalf ? (e >> 1) : e);
+    shl[i] = (kHalf && !(e & 1)) ? 16u : 0u;
+    off0[i] = 4u * (st + 2);
+    // alpha: predecessors s-1, s-2 (cells 1 / 0 for s = 0 are -inf); beta: s+1, s+2, cut at Lp (cells past the
+    // utterance's own Lp are never written and stay -inf)
+    const int p1 = backward ? st + 1 : st - 1;
+    const int p2 = backward ? st + 2 : st - 2;
+    off1[i] = 4u * ((backward && p1 >= Lp) ? 0 : p1 + 2);
+    off2[i] = 4u * (skip_ok ? p2 + 2 : 0);
+    latp[i] = lat + static_cast<size_t>(t_first) * Lp_max + st;
+  }
+  const ptrdiff_t src_step = static_cast<ptrdiff_t>(dt) * (kHalf ? (ldx >> 1) : ldx);
+  const ptrdiff_t lat_step = static_cast<ptrdiff_t>(dt) * Lp_max;
+  const float* lse_src = lse != nullptr ? lse + row0 + t_first : nullptr;
+  const bool has_lse = lse != nullptr;
+  int issued = 0;                                    // frames handed to cp.async so far
+  uint32_t slot = ring_base + 4u * threadIdx.x;      // this thread's word in the ring slot of the next issue
+  uint32_t lslot = lring_base;
+  int slot_idx = 0;
+  static_assert((CTC_RING & (CTC_RING - 1)) == 0, "ring positions are masked");
+
+  auto issue = [&]() {
+    if (issued < Tn) {
 #pragma unroll
       for (int i = 0; i < SPT; ++i) {
-        const int s = threadIdx.x + i * CTC_THREADS;
-        if (s < Lp) {
-          const size_t e = e0 + lab[i];
-          cp_async_4(slot + s, xw + (sizeof(T) == 4 ? e : (e >> 1)));
-        }
+        if (act[i]) cp_async_4_sa(slot + 4u * i * nthreads, src[i]);
+        src[i] += src_step;
       }
-      if (lse != nullptr && threadIdx.x == 0) cp_async_4(lring + (st % CTC_RING), lse + row0 + t);
+      if (has_lse) {
+        if (threadIdx.x == 0) cp_async_4_sa(lslot, lse_src);
+        lse_src += dt;
+      }
+    }
+    ++issued;
+    slot += 4u * W;
+    lslot += 4u;
+    if (++slot_idx == CTC_RING) {
+      slot_idx = 0;
+      slot = ring_base + 4u * threadIdx.x;
+      lslot = lring_base;
     }
     cp_async_commit();
   };
-  auto emission = [&](int st, int i) -> float {
-    const int s = threadIdx.x + i * CTC_THREADS;
-    const uint32_t w = ring[(st % CTC_RING) * (SPT * CTC_THREADS) + s];
-    float v;
-    if (sizeof(T) == 4) {
-      v = __uint_as_float(w);
-    } else {
-      const int t = t_first + dt * st;
-      const size_t e = (row0 + t) * static_cast<size_t>(ldx) + lab[i];
-      v = __uint_as_float((e & 1) ? (w & 0xffff0000u) : (w << 16));
-    }
-    return lse != nullptr ? v - lring[st % CTC_RING] : v;
-  };
 
+  // both columns start as -inf everywhere (guard cells and states beyond this utterance's Lp stay that way)
+  for (int i = threadIdx.x; i < 2 * colw; i += nthreads) sts_f32(colA + 4u * i, -CUDART_INF_F);
 #pragma unroll 1
-  for (int st = 0; st < CTC_RING; ++st) issue(st);
+  for (int st = 0; st < CTC_RING; ++st) issue();
   cp_async_wait<CTC_RING - 1>();
   __syncthreads();
-  // initial column
+  // initial column (in A)
 #pragma unroll
   for (int i = 0; i < SPT; ++i) {
-    const int s = threadIdx.x + i * CTC_THREADS;
-    if (s < Lp) {
+    const int st = threadIdx.x + i * nthreads;
+    if (act[i]) {
       float v = -CUDART_INF_F;
-      const bool start = backward ? (s == Lp - 1 || s == Lp - 2) : (s == 0 || s == 1);
-      if (start) v = emission(0, i);
-      col[0][s] = v;
-      lat[static_cast<size_t>(t_first) * Lp_max + s] = v;
+      const bool start = backward ? (st == Lp - 1 || st == Lp - 2) : (st == 0 || st == 1);
+      if (start) {
+        const uint32_t w = lds_u32(ring_base + 4u * st);
+        v = __uint_as_float(kHalf ? ((w << shl[i]) & 0xffff0000u) : w);
+        if (has_lse) v -= lds_f32(lring_base);
+        sts_f32(colA + off0[i], v);
+      }
+      *latp[i] = v;
     }
   }
 
-  int cur = 0;
-#pragma unroll 1
-  for (int step = 1; step < Tn; ++step) {
-    cp_async_wait<CTC_RING - 2>();  // this thread's words of frame `step` have landed
-    __syncthreads();                // previous column (and the lse word) visible to everyone
-    // refill the ring slot consumed by the previous iteration now: the address arithmetic and the cp.async issue then
-    // overlap the shared-memory latency of this frame's recursion instead of extending the critical path
-    issue(step - 1 + CTC_RING);
-    const int t = t_first + dt * step;
-    const float* prev = col[cur];
-    float* next = col[cur ^ 1];
+  auto frame = [&](int step, uint32_t prev, uint32_t next) {
+    cp_async_wait<CTC_RING - 2>();  // this thread's own words of frame `step` have landed
+    const uint32_t pos = static_cast<uint32_t>(step) & (CTC_RING - 1);
+    uint32_t wv[SPT];
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) wv[i] = lds_u32(ring_base + 4u * (pos * W + threadIdx.x + i * nthreads));
+    __syncthreads();                // previous column (and thread 0's lse word) visible to everyone
+    issue();                        // refill the slot consumed by the previous frame
+    const float lr = has_lse ? lds_f32(lring_base + 4u * pos) : 0.f;
 #pragma unroll
     for (int i = 0; i < SPT; ++i) {
-      const int s = threadIdx.x + i * CTC_THREADS;
-      if (s < Lp) {
-        const float a = prev[s];
-        float b, c = -CUDART_INF_F;
-        if (!backward) {
-          b = s >= 1 ? prev[s - 1] : -CUDART_INF_F;
-          if (skip_ok[i]) c = prev[s - 2];
-        } else {
-          b = s + 1 < Lp ? prev[s + 1] : -CUDART_INF_F;
-          if (skip_ok[i]) c = prev[s + 2];
-        }
-        const float v = lse3_fast(a, b, c) + emission(step, i);
-        next[s] = v;
-        lat[static_cast<size_t>(t) * Lp_max + s] = v;
+      latp[i] += lat_step;
+      if (act[i]) {
+        const float a = lds_f32(prev + off0[i]);
+        const float b2 = lds_f32(prev + off1[i]);
+        const float c2 = lds_f32(prev + off2[i]);
+        const float em = __uint_as_float(kHalf ? ((wv[i] << shl[i]) & 0xffff0000u) : wv[i]);
+        const float v = lse3_bf(a, b2, c2) + (em - lr);
+        sts_f32(next + off0[i], v);
+        *latp[i] = v;
       }
     }
-    cur ^= 1;
+  };
+  int step = 1;
+#pragma unroll 1
+  for (; step + 1 < Tn; step += 2) {
+    frame(step, colA, colB);
+    frame(step + 1, colB, colA);
+  }
+  uint32_t last = colA;
+  if (step < Tn) {
+    frame(step, colA, colB);
+    last = colB;
   }
   cp_async_wait<0>();
   __syncthreads();
   if (!backward && threadIdx.x == 0) {
-    const float a = col[cur][Lp - 1];
-    const float b = Lp >= 2 ? col[cur][Lp - 2] : -CUDART_INF_F;
+    const float a = lds_f32(last + 4u * (Lp - 1 + 2));
+    const float b = Lp >= 2 ? lds_f32(last + 4u * (Lp - 2 + 2)) : -CUDART_INF_F;
     const float m = fmaxf(a, b);
     nll[n] = (m == -CUDART_INF_F) ? CUDART_INF_F : -(m + logf(expf(a - m) + expf(b - m)));
   }
@@ -389,12 +464,15 @@ static int ctc_lattice_launch(const void* x, const float* lse, const int64_t* ta
                               const int32_t* tl, float* alpha, float* beta, float* nll, int N, int T_len, int ldx,
                               int S_max, int blank, cudaStream_t stream) {
   const int Lp_max = 2 * S_max + 1;
-  const int smem = (2 * Lp_max + CTC_RING * SPT * CTC_THREADS + CTC_RING) * static_cast<int>(sizeof(float));
+  // SPT == 1: exactly as many warps as the widest lattice needs (every warp pays the per-frame barrier)
+  int threads = SPT == 1 ? cdiv(Lp_max, 32) * 32 : CTC_THREADS;
+  if (threads > CTC_THREADS) threads = CTC_THREADS;
+  const int smem = (2 * (Lp_max + 4) + CTC_RING * SPT * threads + CTC_RING) * static_cast<int>(sizeof(float));
   static bool configured = false;
   if (!configured && smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(ctc_lattice_kernel<T, SPT, CTC_THREADS>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (2 * (2 * 1023 + 1) + CTC_RING * SPT * CTC_THREADS + CTC_RING) * 4);
+                                         (2 * (2 * 1024 + 1 + 4) + CTC_RING * SPT * CTC_THREADS + CTC_RING) * 4);
     if (e != cudaSuccess) {
       lasr_set_cuda_error(e);
       return LASR_ERR_CUDA;
@@ -402,7 +480,7 @@ static int ctc_lattice_launch(const void* x, const float* lse, const int64_t* ta
     configured = true;
   }
   dim3 grid(N, beta != nullptr ? 2 : 1);
-  LASR_CHECK_PDL(launch_pdl(8, ctc_lattice_kernel<T, SPT, CTC_THREADS>, grid, dim3(CTC_THREADS), smem, stream,
+  LASR_CHECK_PDL(launch_pdl(8, ctc_lattice_kernel<T, SPT, CTC_THREADS>, grid, dim3(threads), smem, stream,
                             static_cast<const T*>(x), lse, targets, il, tl, alpha, beta, nll, T_len, ldx, S_max, blank));
   return LASR_OK;
 }
@@ -466,9 +544,11 @@ int lasr_ctc_fwd(const void* x, const float* lse, const int64_t* targets, const 
   if (dtype == LASR_F32)
     return ctc_lattice_dispatch<float>(x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, N, T, ldx,
                                        S_max, blank, stream);
-  if (dtype == LASR_BF16)
+  if (dtype == LASR_BF16) {
+    if (ldx & 1) return LASR_ERR_ALIGNMENT;  // rows must start on a 4-byte word (the emission gather reads words)
     return ctc_lattice_dispatch<__nv_bfloat16>(x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, N, T,
                                                ldx, S_max, blank, stream);
+  }
   return LASR_ERR_BAD_DTYPE;
 }
 
