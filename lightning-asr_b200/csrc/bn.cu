@@ -10,6 +10,8 @@
 // Every thread moves 8 channels (16 B of bf16 / 32 B of fp32) per row.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace lasr {
 
 template <typename T>
@@ -648,7 +650,8 @@ int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, con
   }
   int chunks = lasr_bn_bwd_chunks(N, T);
   if (N == 1) {
-    chunks = 2 * kNumSMs;
+    static const int mult = getenv("LASR_BN_RED_CTAS") ? atoi(getenv("LASR_BN_RED_CTAS")) : 2;
+    chunks = mult * kNumSMs;
     if (chunks > cdiv(T, 8)) chunks = cdiv(T, 8);
     chunks = cdiv(T, cdiv(T, chunks));
   }
