@@ -481,6 +481,270 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_wgrad_kernel(const Dw
 }
 
 // ------------------------------------------------------------------------------------------------
+// Forward / data gradient, 16-frame rows (LASR_DW16): halves the MMA count per output frame.
+//
+// In the kernel above a row of the A operand is 16 bytes = 8 frames (the row pitch inside a no-swizzle core matrix), so
+// only 8 of the N = 16 accumulator columns carry results.  With the 32-byte swizzle the K-major atom is 8 rows x 32 B:
+// row m of A starts at frame 16 m of the channel's series, one K-step (16 bf16) is exactly one row, the K-step j
+// operand is the same series viewed 32 j bytes later (rows still overlap: a Hankel matrix), and D[m, t] = y[16 m + t]
+// fills all 16 columns: one M = 128 MMA now yields 2048 output frames.  The swizzle is a function of the absolute
+// shared-memory address (16-byte chunk bit ^= address bit 7), so the producers store the series once, swizzled, and
+// every shifted view of it is consistent.  An item is TWO slots of 1024 series frames (64 rows each): a slot holds
+// SL = 1024 - KS valid output frames of one (utterance, chunk); rows past SL / 16 overhang into the next slot's data
+// and are discarded.  At T' = 801 a whole utterance is one slot, an item covers two utterances.
+// ------------------------------------------------------------------------------------------------
+constexpr int D16_SLOTF = 1024;                 // series frames per slot
+constexpr int D16_ROWB = 2 * D16_SLOTF * 2;     // bytes of one channel's series in a stage (2 slots)
+constexpr int D16_STAGE = DT_CG * D16_ROWB;     // 64 KB
+
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;  // LBO unused: one K-step is exactly the 32-byte swizzle span
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;  // SWIZZLE_32B
+  return d;
+}
+
+// one slot: global [frames, C] -> series[c][slot frames 0..1023] swizzled; out of [0, T) frames are zero
+__device__ __forceinline__ void load_slot_sw32(const __nv_bfloat16* __restrict__ src, int C, int T, int f_base,
+                                               uint8_t* rows, int pw, int lane) {
+  const int h = lane >> 4;
+  const int b = lane & 15;
+  uint4 r[2][8];
+#pragma unroll
+  for (int ps = 0; ps < 2; ++ps) {
+    const int sigma = (pw + 4 * ps) * 128 + 8 * b;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = f_base + sigma + i;
+      r[ps][i] = make_uint4(0u, 0u, 0u, 0u);
+      if (src != nullptr && f >= 0 && f < T)
+        r[ps][i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(f) * C + 8 * h));
+    }
+  }
+#pragma unroll
+  for (int ps = 0; ps < 2; ++ps) {
+    const int sigma = (pw + 4 * ps) * 128 + 8 * b;
+    const uint32_t L = static_cast<uint32_t>(sigma) * 2u;          // logical byte offset inside the slot's row
+    const uint32_t Ls = L ^ (((L >> 7) & 1u) << 4);               // 32-byte swizzle (slot rows are 256-byte aligned)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint32_t o[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const uint32_t a = (&r[ps][2 * m].x)[q >> 1], bb = (&r[ps][2 * m + 1].x)[q >> 1];
+        o[m] = __byte_perm(a, bb, (q & 1) ? 0x7632 : 0x5410);
+      }
+      *reinterpret_cast<uint4*>(rows + static_cast<size_t>(8 * h + q) * D16_ROWB + Ls) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+struct Dw16Params {
+  const __nv_bfloat16* x;
+  const float* w;
+  __nv_bfloat16* y;
+  const __nv_bfloat16* addend;
+  int N, T, C, K, KS, flip;
+  int SL, rows_valid, t_chunks, slots_per_cg, items_per_cg, num_cg, ctas_per_cg, stages;
+  int w_early;
+};
+
+__global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc16_fwd_kernel(const Dw16Params p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int toep_bytes_c = p.KS * 32;                       // per channel: KS/8 x 2 cores of 128 B
+  uint8_t* s_ser = smem;                                    // [stages][16][2 slots x 1024 frames] bf16, swizzled
+  uint8_t* s_toep = s_ser + p.stages * D16_STAGE;           // [16][KS/8][2][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_toep + DT_CG * toep_bytes_c);
+  uint64_t* full_bar = bars;          // [4]
+  uint64_t* empty_bar = bars + 4;     // [4]
+  uint64_t* tmem_full_bar = bars + 8;
+  uint64_t* tmem_empty_bar = bars + 10;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cg = blockIdx.x % p.num_cg;
+  const int first = blockIdx.x / p.num_cg;
+  const int c0 = cg * DT_CG;
+  const int P = p.K / 2;
+
+  if (!p.w_early) pdl_wait();
+  // Toeplitz factor B[t, s] = w[s - t], t < 16 output frames of a row, s < KS series frames: K-major no-swizzle cores
+  // [s / 8][t / 8], element (t % 8, s % 8)
+  for (int i = threadIdx.x; i < DT_CG * p.KS * 16; i += DT_THREADS) {
+    const int c = i / (p.KS * 16);
+    const int rem = i - c * p.KS * 16;
+    const int core = rem >> 6, r = (rem >> 3) & 7, e = rem & 7;
+    const int kk = core >> 1, tn = core & 1;
+    const int t = 8 * tn + r, sidx = 8 * kk + e;
+    const int j = sidx - t;
+    float v = 0.f;
+    if (j >= 0 && j < p.K && c0 + c < p.C) v = p.w[static_cast<size_t>(c0 + c) * p.K + (p.flip ? p.K - 1 - j : j)];
+    reinterpret_cast<__nv_bfloat16*>(s_toep)[i] = __float2bfloat16_rn(v);
+  }
+  if (warp_idx == 4 && lane == 0) {
+    for (int st = 0; st < 4; ++st) {
+      mbar_init(&full_bar[st], 4);
+      mbar_init(&empty_bar[st], 1);
+    }
+    for (int st = 0; st < 2; ++st) {
+      mbar_init(&tmem_full_bar[st], 1);
+      mbar_init(&tmem_empty_bar[st], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp_idx == 5) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+
+  if (warp_idx >= 6) {
+    // ===================== producers: two groups of 4 warps take alternate items =====================
+    const int pw = (warp_idx - 6) & 3;
+    const int grp = (warp_idx - 6) >> 2;
+    int it = grp;
+    for (int idx = first + grp * p.ctas_per_cg; idx < p.items_per_cg; idx += 2 * p.ctas_per_cg, it += 2) {
+      const int stage = it % p.stages;
+      const uint32_t phase = (it / p.stages) & 1;
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+#pragma unroll 1
+      for (int sl = 0; sl < 2; ++sl) {
+        const int slot = 2 * idx + sl;
+        const __nv_bfloat16* src = nullptr;
+        int f_base = 0;
+        if (slot < p.slots_per_cg) {
+          const int n = slot / p.t_chunks, tc = slot - n * p.t_chunks;
+          src = p.x + static_cast<size_t>(n) * p.T * p.C + c0;
+          f_base = tc * p.SL - P;
+        }
+        load_slot_sw32(src, p.C, p.T, f_base, s_ser + stage * D16_STAGE + sl * (D16_SLOTF * 2), pw, lane);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+    }
+  } else if (warp_idx == 4) {
+    // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(DT_ROWS, 16, 0, 0);
+    const int ksteps = p.KS / 16;
+    int it = 0;
+    for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
+      const int stage = it % p.stages;
+      const uint32_t phase = (it / p.stages) & 1;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1u);
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      uint64_t da_c = umma_desc_sw32(smem_u32(s_ser + stage * D16_STAGE), 256);
+      uint64_t db_c = umma_desc_none(smem_u32(s_toep), 256, 128);
+      uint32_t tmem_d = tmem_base + acc * 256;
+      const uint64_t da_step = static_cast<uint64_t>(D16_ROWB >> 4), db_step = static_cast<uint64_t>(toep_bytes_c >> 4);
+#pragma unroll 1
+      for (int c = 0; c < DT_CG; ++c) {
+        uint64_t da = da_c, db = db_c;
+        if (leader) umma_bf16_first(tmem_d, da, db, idesc);
+#pragma unroll 1
+        for (int kc = 1; kc < ksteps; ++kc) {
+          da += 2;    // 32 B: the series 16 frames later
+          db += 32;   // 512 B: two K-cores (x 2 N-cores)
+          if (leader) umma_bf16_acc(tmem_d, da, db, idesc);
+        }
+        da_c += da_step;
+        db_c += db_step;
+        tmem_d += 16;
+      }
+      if (leader) {
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tmem_full_bar[acc]);
+      }
+      __syncwarp();
+    }
+  } else if (warp_idx < 4) {
+    // ===================== epilogue: row = 16 output frames x 16 channels =====================
+    const int row = warp_idx * 32 + lane;
+    const int sl = row >> 6, mr = row & 63;
+    int it = 0;
+    for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
+      const int acc = it & 1;
+      const uint32_t phase = (it >> 1) & 1;
+      const int slot = 2 * idx + sl;
+      int n = 0, tc = 0;
+      bool live = slot < p.slots_per_cg && mr < p.rows_valid;
+      if (live) {
+        n = slot / p.t_chunks;
+        tc = slot - n * p.t_chunks;
+      }
+      const int f0 = tc * p.SL + 16 * mr;
+      live = live && f0 < p.T;
+      const size_t off0 = (static_cast<size_t>(n) * p.T + f0) * p.C + c0;
+      mbar_wait(&tmem_full_bar[acc], phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16) + acc * 256;
+#pragma unroll 1
+      for (int th = 0; th < 4; ++th) {  // 4 frames x 16 channels at a time
+        uint32_t add[4][8];
+        if (p.addend != nullptr) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) add[t][c] = 0u;
+            if (live && f0 + 4 * th + t < p.T) ldg_v8(p.addend + off0 + static_cast<size_t>(4 * th + t) * p.C, add[t]);
+          }
+        }
+        uint32_t v[DT_CG][4];
+#pragma unroll
+        for (int c = 0; c < DT_CG; ++c) tmem_ld_32x32_x4(taddr + c * 16 + 4 * th, v[c]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int f = f0 + 4 * th + t;
+          if (live && f < p.T) {
+            const size_t off = off0 + static_cast<size_t>(4 * th + t) * p.C;
+            uint32_t u[8];
+            if (p.addend != nullptr) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float2 av = bf16x2_to_f32x2(add[t][c]);
+                u[c] = f32x2_to_bf16x2(__uint_as_float(v[2 * c][t]) + av.x, __uint_as_float(v[2 * c + 1][t]) + av.y);
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                u[c] = f32x2_to_bf16x2(__uint_as_float(v[2 * c][t]), __uint_as_float(v[2 * c + 1][t]));
+            }
+            stg_v8(p.y + off, u);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
 static void dt_schedule(DwTcParams& p) {
@@ -499,8 +763,57 @@ int dwconv_tc_supported(int C, int K, int stride) {
   return !off && stride == 1 && (C % DT_CG) == 0 && K >= 3 && (K & 1) && K + 7 <= DT_MAX_KS;
 }
 
+static int dwconv_tc16_fwd(const void* x, const float* w, void* y, const void* addend, int N, int T, int C, int K,
+                           int flip, cudaStream_t stream) {
+  Dw16Params p{};
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.w = w;
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.addend = static_cast<const __nv_bfloat16*>(addend);
+  p.N = N;
+  p.T = T;
+  p.C = C;
+  p.K = K;
+  p.KS = cdiv(K + 15, 16) * 16;
+  p.flip = flip;
+  p.w_early = early_param_loads() ? 1 : 0;
+  p.SL = (D16_SLOTF - p.KS) / 16 * 16;
+  p.rows_valid = p.SL / 16;
+  p.t_chunks = cdiv(T, p.SL);
+  p.slots_per_cg = N * p.t_chunks;
+  p.items_per_cg = cdiv(p.slots_per_cg, 2);
+  p.num_cg = cdiv(C, DT_CG);
+  int per = kNumSMs / p.num_cg;
+  if (per < 1) per = 1;
+  if (per > p.items_per_cg) per = p.items_per_cg;
+  const int rounds = cdiv(p.items_per_cg, per);
+  p.ctas_per_cg = cdiv(p.items_per_cg, rounds);
+  const int toep = DT_CG * p.KS * 32;
+  int stages = (232448 - 1024 - 256 - toep) / D16_STAGE;
+  if (stages > 3) stages = 3;
+  if (stages < 2) return LASR_ERR_UNSUPPORTED;
+  p.stages = stages;
+  const int smem = 1024 + stages * D16_STAGE + toep + 256;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_tc16_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e != cudaSuccess) {
+      lasr_set_cuda_error(e);
+      return LASR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  LASR_CHECK_PDL(launch_pdl(2, dwconv_tc16_fwd_kernel, dim3(p.num_cg * p.ctas_per_cg), dim3(DT_THREADS), smem, stream, p));
+  return LASR_OK;
+}
+
 int dwconv_tc_fwd(const void* x, const float* w, void* y, const void* addend, int N, int T, int C, int K, int flip,
                   cudaStream_t stream) {
+  static const int dw16 = getenv("LASR_DW16") ? atoi(getenv("LASR_DW16")) : 0;
+  if (dw16 && K + 15 <= 112) {
+    const int rc16 = dwconv_tc16_fwd(x, w, y, addend, N, T, C, K, flip, stream);
+    if (rc16 != LASR_ERR_UNSUPPORTED) return rc16;
+  }
   DwTcParams p{};
   p.x = static_cast<const __nv_bfloat16*>(x);
   p.w = w;
