@@ -314,6 +314,16 @@ class InferEngine:
         self.copy_stream = torch.cuda.Stream()
         self._staged_evt = self._consumed_evt = None
         self.use_graph, self.graph = graph, None
+        # weights do not change during inference: ONE bf16 shadow cast here instead of one per layer and pass
+        self.bank = runtime.ParamBank(module)
+        runtime.install(self.bank)
+        self.refresh_weights()
+
+    def refresh_weights(self):
+        """Re-cast the bf16 weight shadows (call after load_state_dict / any parameter update)."""
+        b = self.bank
+        _lib.call("lasr_cast_weight", b.master, b.shadow, 1, b.numel, 0, _lib.LASR_BF16)
+        b.shadow_fresh = True
 
     def _run(self):
         fe, ops = self.frontend, self.ops
