@@ -236,7 +236,7 @@ def cpu_training_throughput(model_name, seconds, labels, sample_n, steps, warmup
     import torch
     from lightning_asr_b200.quartznet import build_model
     from lightning_asr_b200.trainer import synthetic_batch
-    from oracle import train_oracle
+    from oracle import optim_oracle, train_oracle
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -245,18 +245,22 @@ def cpu_training_throughput(model_name, seconds, labels, sample_n, steps, warmup
     params = [v.requires_grad_(True) for k, v in sd.items() if v.is_floating_point() and "running" not in k]
     batch = synthetic_batch(sample_n, seconds, len(labels), seed=1234, ragged=False)
     times = []
+    opt_state = [{} for _ in params]
     for i in range(warmup + steps):
         for p in params:
             p.grad = None
         t0 = time.perf_counter()
         loss, _, _ = train_oracle.training_step(sd, batch, labels, mask=True, training=True, update_buffers=True)
         loss.backward()
+        with torch.no_grad():  # the reference's optimizer step (scheduler/novograd.py, train.py:46), like the GPU arm
+            optim_oracle.novograd_step([p.data for p in params], [p.grad for p in params], opt_state, 1e-4,
+                                       betas=(0.8, 0.5), weight_decay=1e-4)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     med = statistics.median(times)
     return {"value": sample_n * seconds / med, "unit": "audio-s/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{sample_n} x {seconds:g} s utterances of the workload, fp32 fwd+bwd+CTC, median of {steps} "
+            "sample": f"{sample_n} x {seconds:g} s utterances of the workload, fp32 fwd+bwd+CTC+Novograd, median of {steps} "
                       f"steps ({med * 1e3:.0f} ms/step)", "ms_per_step": med * 1e3}
 
 
@@ -275,8 +279,12 @@ def run_reference(args):
         "unit": "audio-s/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": cb["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "model_name": model_name, "per_gpu_batch": n, "seconds": seconds,
-                   "note": "reference algorithm (oracle port of models/QuartNet.py + torch CTCLoss) on the host cores; "
-                           "each step is a bounded sample of the workload"},
+                   "frames": 1 + (int(seconds * 16000) + 64) // 160,
+                   "encoder_steps": (1 + (int(seconds * 16000) + 64) // 160 - 1) // 2 + 1, "vocab": len(labels) + 1,
+                   "mask": True, "step": "forward + CTC + backward + Novograd update",
+                   "note": "reference algorithm (oracle port of models/QuartNet.py + torch CTCLoss + "
+                           "scheduler/novograd.py) on the host cores; each step is a bounded sample of the workload "
+                           f"({sample_n} of the {n} utterances)"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
