@@ -107,6 +107,14 @@ int lasr_dwconv1d_wgrad(const void* x, const void* dy, float* dw, int N, int T_i
 int lasr_pwconv_fwd(const void* x, const void* w, void* y, const float* bias, const int32_t* lengths, int T,
                     double* stats, int M, int Cin, int Cout, int ldx, int ldw, int ldy, int dtype,
                     lasr_stream_t stream);
+/* Inference (eval-mode) block epilogue, SURVEY.md 8f-4: with BatchNorm's running statistics folded into the weight
+ * rows and a bias (w' = diag(gamma / sqrt(var + eps)) w, bias = beta - mean * scale), the chain
+ *   conv1x1 -> MaskCNN -> BatchNorm -> (+ residual branch) -> ReLU      models/QuartNet.py:31-37,71-78,145-148
+ * is ONE GEMM:  y = act( mask(x w'^T) + bias [+ residual] ),  masked rows keep bias + residual (BN of a zeroed row).
+ * residual [M, ld_res] dtype nullable, relu 0/1.  bf16 only (LASR_ERR_UNSUPPORTED otherwise); Cout % 32 == 0. */
+int lasr_pwconv_fwd_fused(const void* x, const void* w, void* y, const float* bias, const void* residual,
+                          const int32_t* lengths, int T, int relu, int M, int Cin, int Cout, int ldx, int ldw, int ldy,
+                          int ld_res, int dtype, lasr_stream_t stream);
 int lasr_pwconv_dgrad(const void* dy, const void* w, void* dx, int M, int Cin, int Cout, int lddy, int ldw, int lddx,
                       int dtype, lasr_stream_t stream);
 int lasr_pwconv_wgrad(const void* dy, const void* x, float* dw, int M, int Cin, int Cout, int lddy, int ldx, int lddw,

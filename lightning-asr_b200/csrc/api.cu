@@ -24,6 +24,9 @@ int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const
                int M, int N, int K, int lda, int ldb, int ldc, int out_f32, cudaStream_t stream);
 int gemm_tc_nn(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldc, int out_f32,
                cudaStream_t stream);
+int gemm_tc_nt_fused(const void* a, const void* b, void* out, const float* bias, const void* residual, int ld_res,
+                     const int32_t* lengths, int T, int relu, int M, int N, int K, int lda, int ldb, int ldc,
+                     cudaStream_t stream);
 int gemm_simt_nn(const float* a, const float* b, float* c, int M, int N, int K, int lda, int ldb, int ldc,
                  cudaStream_t stream);
 int gemm_tc_tn_accum(const void* dy, const void* x, float* dw, int R, int Cout, int Cin, int lddy, int ldx, int lddw,
@@ -184,6 +187,14 @@ int lasr_pwconv_fwd(const void* x, const void* w, void* y, const float* bias, co
     return LASR_OK;
   }
   return LASR_ERR_BAD_DTYPE;
+}
+
+int lasr_pwconv_fwd_fused(const void* x, const void* w, void* y, const float* bias, const void* residual,
+                          const int32_t* lengths, int T, int relu, int M, int Cin, int Cout, int ldx, int ldw, int ldy,
+                          int ld_res, int dtype, lasr_stream_t stream) {
+  if (lengths != nullptr && T <= 0) return LASR_ERR_BAD_SHAPE;
+  if (dtype != LASR_BF16) return LASR_ERR_UNSUPPORTED;  // the fp32 exact-parity mode keeps the unfused passes
+  return gemm_tc_nt_fused(x, w, y, bias, residual, ld_res, lengths, T, relu, M, Cout, Cin, ldx, ldw, ldy, stream);
 }
 
 int lasr_pwconv_dgrad(const void* dy, const void* w, void* dx, int M, int Cin, int Cout, int lddy, int ldw, int lddx,

@@ -407,6 +407,11 @@ struct GemmWsParams {
   int stages;
   int cluster;  // CTAs per cluster = num_n_blocks when the activation tiles are multicast, else 1
   int w_early;  // weight slice may be fetched before griddepcontrol.wait (lasr_set_early_param_loads)
+  // fused inference epilogue (lasr_pwconv_fwd_fused): y = act(mask(acc) + bias + residual)
+  const __nv_bfloat16* residual;  // [M, ld_res] or NULL
+  int ld_res;
+  int relu;
+  int bias_after_mask;  // 1: masked rows keep bias (+ residual): BatchNorm folded into w / bias sees mask(pw) = 0
   const float* bias;
   const int32_t* lengths;
   int T;
@@ -611,20 +616,47 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * WS_BN;
 #pragma unroll
       for (int ch = 0; ch < WS_BN / 32; ++ch) {
+        const int col0 = n_blk * WS_BN + ch * 32;
+        // residual row segment of the fused inference epilogue: requested before the accumulator load so that its
+        // latency hides under tcgen05.ld
+        uint4 rr[4];
+        const bool use_res = p.residual != nullptr && row < p.M && col0 + 32 <= p.N;
+        if (use_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.ld_res + col0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rr[q] = __ldg(rp + q);
+        }
         uint32_t v[32];
         tmem_ld_32x32(taddr0 + ch * 32, v);
         tmem_ld_wait();
-        const int col0 = n_blk * WS_BN + ch * 32;
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias_after_mask && !keep) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = 0.f;
+        }
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] += (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
         }
-        if (!keep) {
+        if (!p.bias_after_mask && !keep) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = 0.f;
+        }
+        if (use_res) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 u = rr[q];
+            const float2 a0 = bf16x2_to_f32x2(u.x), a1 = bf16x2_to_f32x2(u.y), a2 = bf16x2_to_f32x2(u.z),
+                         a3 = bf16x2_to_f32x2(u.w);
+            f[8 * q + 0] += a0.x; f[8 * q + 1] += a0.y; f[8 * q + 2] += a1.x; f[8 * q + 3] += a1.y;
+            f[8 * q + 4] += a2.x; f[8 * q + 5] += a2.y; f[8 * q + 6] += a3.x; f[8 * q + 7] += a3.y;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
         uint8_t* sub = s_stg + (ch >> 1) * (WS_BM * 128) + r * 128;
 #pragma unroll
@@ -863,20 +895,45 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * 256 + h * WS_BN;
 #pragma unroll
         for (int ch = 0; ch < WS_BN / 32; ++ch) {
+          const int col0 = n0 + h * WS_BN + ch * 32;
+          uint4 rr[4];
+          const bool use_res = p.residual != nullptr && row < p.M && col0 + 32 <= p.N;
+          if (use_res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.ld_res + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) rr[q] = __ldg(rp + q);
+          }
           uint32_t v[32];
           tmem_ld_32x32(taddr0 + ch * 32, v);
           tmem_ld_wait();
-          const int col0 = n0 + h * WS_BN + ch * 32;
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias_after_mask && !keep) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          }
           if (p.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] += (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
           }
-          if (!keep) {
+          if (!p.bias_after_mask && !keep) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          }
+          if (use_res) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 u = rr[q];
+              const float2 a0 = bf16x2_to_f32x2(u.x), a1 = bf16x2_to_f32x2(u.y), a2 = bf16x2_to_f32x2(u.z),
+                           a3 = bf16x2_to_f32x2(u.w);
+              f[8 * q + 0] += a0.x; f[8 * q + 1] += a0.y; f[8 * q + 2] += a1.x; f[8 * q + 3] += a1.y;
+              f[8 * q + 4] += a2.x; f[8 * q + 5] += a2.y; f[8 * q + 6] += a3.x; f[8 * q + 7] += a3.y;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
           }
           uint8_t* sub = s_stg + (ch >> 1) * (WS_BM * 128) + r * 128;
 #pragma unroll
@@ -1230,9 +1287,17 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmT
 static unsigned long long* g_ws_trace = nullptr;
 extern "C" void lasr_debug_set_gemm_trace(unsigned long long* buf) { g_ws_trace = buf; }
 
+struct WsFused {
+  const void* residual = nullptr;
+  int ld_res = 0;
+  int relu = 0;
+  int bias_after_mask = 0;
+};
+
 // weight-stationary launch; returns LASR_ERR_UNSUPPORTED when the shape does not qualify (caller falls back)
 static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const float* bias, const int32_t* lengths, int T,
-                     double* stats, int M, int N, int K, int lda, int ldb, int ldc, cudaStream_t stream) {
+                     double* stats, int M, int N, int K, int lda, int ldb, int ldc, cudaStream_t stream,
+                     const WsFused& fu = WsFused()) {
   const int kbs = cdiv(K, WS_BK);
   static const bool disabled = getenv("LASR_GEMM_STREAMED") != nullptr;  // A/B switch for profiling
   if (disabled) return LASR_ERR_UNSUPPORTED;
@@ -1275,6 +1340,10 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
   p.lengths = lengths;
   p.T = T;
   p.stats = stats;
+  p.residual = static_cast<const __nv_bfloat16*>(fu.residual);
+  p.ld_res = fu.ld_res;
+  p.relu = fu.relu;
+  p.bias_after_mask = fu.bias_after_mask;
   p.trace = g_ws_trace;
   p.w_early = early_param_loads() ? 1 : 0;
   const int smem = 1024 + 512 + kbs * WS_WKB_BYTES + stages * WS_A_BYTES + WS_STG_BYTES;
@@ -1335,7 +1404,8 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
 
 // CTA-pair launch (gemm_ws2_kernel); LASR_ERR_UNSUPPORTED when the shape does not qualify
 static int launch_ws2(bool b_mn, const void* a, const void* b, void* out, const float* bias, const int32_t* lengths,
-                      int T, double* stats, int M, int N, int K, int lda, int ldb, int ldc, cudaStream_t stream) {
+                      int T, double* stats, int M, int N, int K, int lda, int ldb, int ldc, cudaStream_t stream,
+                      const WsFused& fu = WsFused()) {
   // Measured (tools/bench_kernels.py, M = 25 632): the pair wins where the activation tile is large, K >= 512
   // (512->512 fwd+stats 29.5 -> 25.4 us, 512->1024 48 -> 33.7 us, dgrad of 256->512 21.2 -> 19.3 us) and loses at K = 256
   // (256->256 16.4 -> 21.5 us: 101 pair tiles over 74 pairs is two full rounds).  LASR_GEMM_PAIR=0 disables it,
@@ -1380,6 +1450,10 @@ static int launch_ws2(bool b_mn, const void* a, const void* b, void* out, const 
   p.lengths = lengths;
   p.T = T;
   p.stats = stats;
+  p.residual = static_cast<const __nv_bfloat16*>(fu.residual);
+  p.ld_res = fu.ld_res;
+  p.relu = fu.relu;
+  p.bias_after_mask = fu.bias_after_mask;
   p.trace = nullptr;
   p.w_early = early_param_loads() ? 1 : 0;
   const int smem = 1024 + 512 + kbs * WS_WKB_BYTES + stages * WS_A_BYTES + WS_STG_BYTES;
@@ -1462,6 +1536,23 @@ int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const
     case 128: return launch_inst<128, false, false, 0>(ta, tb, p, grid, stream);
     default: return launch_inst<256, false, false, 0>(ta, tb, p, grid, stream);
   }
+}
+
+// inference epilogue: y = act(mask(x w^T) + bias + residual), bf16; weight-stationary kernels only
+int gemm_tc_nt_fused(const void* a, const void* b, void* out, const float* bias, const void* residual, int ld_res,
+                     const int32_t* lengths, int T, int relu, int M, int N, int K, int lda, int ldb, int ldc,
+                     cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return LASR_ERR_BAD_SHAPE;
+  if ((lda % 8) || (ldb % 8) || (ld_res % 8) || (N % 32)) return LASR_ERR_ALIGNMENT;
+  if (residual != nullptr && (reinterpret_cast<uintptr_t>(residual) & 15)) return LASR_ERR_ALIGNMENT;
+  WsFused fu;
+  fu.residual = residual;
+  fu.ld_res = ld_res;
+  fu.relu = relu;
+  fu.bias_after_mask = 1;
+  const int rc2 = launch_ws2(false, a, b, out, bias, lengths, T, nullptr, M, N, K, lda, ldb, ldc, stream, fu);
+  if (rc2 != LASR_ERR_UNSUPPORTED) return rc2;
+  return launch_ws(false, a, b, out, bias, lengths, T, nullptr, M, N, K, lda, ldb, ldc, stream, fu);
 }
 
 // y[M, N] = a[M, K] b[K, N]: the data gradient dx = dy * W with W in its native [Cout = K, Cin = N] layout, i.e. an

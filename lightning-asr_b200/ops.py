@@ -92,6 +92,23 @@ def pwconv_fwd(x2d, w, bias=None, lengths=None, T=0, stats=None, out=None, ldy=N
     return y
 
 
+def pwconv_fwd_fused(x2d, w, bias, residual=None, lengths=None, T=0, relu=True):
+    """y = act(mask(x w^T) + bias [+ residual]) -- the eval-mode conv1x1 -> MaskCNN -> BN(folded) -> [+res] -> ReLU chain
+    as one GEMM (bf16 only)."""
+    _chk(x2d, "x"), _chk(w, "w")
+    Cin = x2d.shape[-1]
+    M = x2d.numel() // Cin
+    Cout = w.shape[0]
+    if w.shape[1] != Cin or w.dtype != x2d.dtype:
+        raise _lib.LasrError(f"pwconv weight {tuple(w.shape)}/{w.dtype} does not match input Cin={Cin}/{x2d.dtype}")
+    y = torch.empty(x2d.shape[:-1] + (Cout,), device=x2d.device, dtype=x2d.dtype)
+    if residual is not None:
+        _chk(residual, "residual")
+    call("lasr_pwconv_fwd_fused", x2d, w, y, bias, residual, lengths, T, 1 if relu else 0, M, Cin, Cout, Cin, Cin, Cout,
+         Cout, dtype_code(x2d.dtype))
+    return y
+
+
 def pwconv_dgrad(dy, w, lddy=None):
     """dx[M, Cin] = dy[M, Cout] w[Cout, Cin]   (w in its native layout; dy row pitch lddy >= Cout)."""
     _chk(dy, "dy"), _chk(w, "w")

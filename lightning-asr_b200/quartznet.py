@@ -40,6 +40,39 @@ def _bn_buffers(bn):
     return (bn.running_mean, bn.running_var, bn.num_batches_tracked)
 
 
+_FOLD = {"enabled": False}
+
+
+def set_eval_folding(on):
+    """Inference fast path: fold eval-mode BatchNorm into the 1x1 conv and run conv -> mask -> BN ->
+    (+ residual) -> ReLU as one GEMM epilogue (bf16, no-grad, non-SE blocks).  OPT-IN: validated against the unfused
+    kernels and the oracle (tests/test_model_gpu.py), but measured slower on B200 (config 5: 11.6 -> 12.7 ms): the
+    per-thread residual row reads of the GEMM epilogue cost more than the BatchNorm pass they replace."""
+    _FOLD["enabled"] = bool(on)
+
+
+def _fold_ok(module, x):
+    return (_FOLD["enabled"] and not module.training and not torch.is_grad_enabled() and x.dtype == torch.bfloat16)
+
+
+def _folded(conv, bn, cache_owner, tag):
+    """(w' [Cout, Cin] bf16, bias [Cout] fp32) with eval-mode BatchNorm folded into the 1x1 conv; cached on the module
+    and rebuilt when any of the tensors involved changed (in-place updates bump torch's version counters)."""
+    key = (conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version,
+           bn.running_var._version, conv.weight.data_ptr())
+    cache = cache_owner.__dict__.setdefault("_fold_cache", {})
+    hit = cache.get(tag)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    with torch.no_grad():
+        scale = bn.weight.double() / torch.sqrt(bn.running_var.double() + bn.eps)
+        shift = bn.bias.double() - bn.running_mean.double() * scale
+        w = (conv.weight.double().view(conv.weight.shape[0], -1) * scale[:, None]).to(torch.bfloat16).contiguous()
+        b = shift.float().contiguous()
+    cache[tag] = (key, w, b)
+    return w, b
+
+
 class SELayer(nn.Module):
     """Parameter container for models/QuartNetContextSE.py:8-23 (fc.0: C->C/r, fc.2: C/r->C, no biases)."""
 
@@ -82,6 +115,17 @@ class SeprationConv(nn.Module):
         applied after the add, models/QuartNet.py:75-77)."""
         lens = lengths if self.mask else None
         se1, se2 = self._se_weights()
+        if self.se is None and _fold_ok(self, x):
+            # eval fast path: dw conv -> [residual GEMM + bias] -> ONE GEMM with the whole block epilogue
+            d = ops.dwconv_fwd(x, self.depthwise_conv.weight.detach(), stride=self.stride)
+            w1, b1 = _folded(self.pointwise_conv, self.bn, self, "pw")
+            r = None
+            if residual is not None:
+                rconv, rbn = residual
+                w2, b2 = _folded(rconv, rbn, self, "res")
+                r = ops.pwconv_fwd(x if res_x is None else res_x, w2, bias=b2)
+            relu = True if residual is not None else (not self.last)
+            return ops.pwconv_fwd_fused(d, w1, b1, residual=r, lengths=lens, T=d.shape[1], relu=relu)
         if residual is not None:
             rconv, rbn = residual
             return SepConvBNFn.apply(x, res_x, lens, self.depthwise_conv.weight, self.pointwise_conv.weight,
@@ -204,8 +248,12 @@ class QuartNet12(nn.Module):
                 # stays on the device (the reference's `.cpu()` sync is gone)
                 c, _ = self.context_rnn(x, lengths)
                 x = torch.cat((x, c), dim=2).contiguous()
-        x = Conv1x1BNReLUFn.apply(x, self.last_cnn2[0].weight, self.last_cnn2[1].weight, self.last_cnn2[1].bias,
-                                  _bn_buffers(self.last_cnn2[1]), self.training, True)
+        if _fold_ok(self, x):
+            w, b = _folded(self.last_cnn2[0], self.last_cnn2[1], self, "last_cnn2")
+            x = ops.pwconv_fwd_fused(x, w, b, relu=True)
+        else:
+            x = Conv1x1BNReLUFn.apply(x, self.last_cnn2[0].weight, self.last_cnn2[1].weight, self.last_cnn2[1].bias,
+                                      _bn_buffers(self.last_cnn2[1]), self.training, True)
         if self.drop_rate > 0.0 and self.training:
             x = torch.nn.functional.dropout(x, p=self.drop_rate, training=True)
         return x

@@ -251,3 +251,31 @@ def test_infer_engine_matches_module_eval_path():
     assert got == ref
     assert [len(s) for s in got] == [int(c) for c in cnts]
     assert sum(len(s) for s in got) > 0
+
+
+@pytest.mark.parametrize("variant", ["base", "context"])
+def test_eval_folded_fast_path_matches_unfused_and_oracle(lasr, labels28, variant):
+    """Inference fast path (BatchNorm folded into the 1x1 convs, block epilogue in the GEMM): same log-probs as the
+    unfused eval kernels and as the oracle's eval forward, bf16 tolerance; greedy tokens identical to the unfused path."""
+    from oracle import quartznet_oracle as qo
+    cls = {"base": lasr.MyModel2, "context": lasr.MyModel2Context}[variant]
+    torch.manual_seed(1)
+    model = cls(labels28, mask=True, precision="bf16")
+    with torch.no_grad():  # non-trivial running statistics
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.normal_(0, 0.2)
+                m.running_var.uniform_(0.5, 1.5)
+    sd0 = copy.deepcopy(model.state_dict())
+    model = model.cuda().eval()
+    x, p = _inputs(4, 301)
+    with torch.no_grad():
+        lasr.set_eval_folding(True)
+        out_f = model(x.cuda(), p.cuda())
+        lasr.set_eval_folding(False)
+        out_u = model(x.cuda(), p.cuda())
+    ref = qo.model(x, p, _sd_to(sd0), mask=True, training=False)
+    assert rel_err(out_f, ref) < 2e-2
+    assert rel_err(out_f, out_u) < 2e-2
+    # the folded path keeps fp32 through the block epilogue, so it is at least as close to the oracle as the unfused one
+    assert rel_err(out_f, ref) < 1.5 * rel_err(out_u, ref) + 1e-3
