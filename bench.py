@@ -495,18 +495,35 @@ def run_b200(args):
     total_ms = sum(d["ms"] for d in fam.values())
     top = max(fam.items(), key=lambda kv: kv[1]["ms"])
     tname, t = top
+    # Per-call CUDA events in the eager replay also contain each call's launch latency (an empty kernel reads ~6 us
+    # this way, tools/bench_kernels.py "calibration"), which the timed region does not pay: there the same kernels
+    # run back to back from the CUDA graph.  The per-call overhead is calibrated so that the families add up to the
+    # measured graph step:  o = (sum of event times - ms_per_step) / calls,  t_family = events - calls_family * o.
+    # The raw eager figure is reported next to it; shares agree with the ncu launch list (profiles/README.md).
+    ncalls = sum(d["calls"] for d in fam.values())
+    over = max(0.0, (total_ms - ms_per_step) / ncalls) if ncalls else 0.0
+
+    def in_step(d):
+        return max(d["ms"] - d["calls"] * over, 0.25 * d["ms"])
+    t_ms = in_step(t)
     if tname == "pwconv_gemm":
         peak = peaks["bf16_tflops_sustained"]
-        ach = t["flops"] / (t["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
+        ach = t["flops"] / (t_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "achieved_eager_events": t["flops"] / (t["ms"] * 1e-3) / 1e12}
     else:
         peak = peaks["hbm_gbs"]
-        ach = t["bytes"] / (t["ms"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+        ach = t["bytes"] / (t_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "achieved_eager_events": t["bytes"] / (t["ms"] * 1e-3) / 1e9}
     roof.update({"traffic": load_traffic(tname), "kernel": tname, "peak_source": peaks["source"] + " (sustained)",
-                 "share_of_step": t["ms"] / total_ms if total_ms else None,
-                 "families": {k: {"ms": round(v["ms"], 4), "GB/s": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1),
-                                  "TFLOP/s": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 1), "calls": v["calls"]}
+                 "share_of_step": t_ms / ms_per_step, "ms_in_step": t_ms, "launches_per_step": t["calls"],
+                 "eager_launch_overhead_us": over * 1e3,
+                 "timing": "CUDA events around every C-ABI call (eager replay, launching stream) minus the calibrated "
+                           "per-call launch latency, so that the families sum to the measured graph step",
+                 "families": {k: {"ms": round(v["ms"], 4), "ms_in_step": round(in_step(v), 4),
+                                  "GB/s": round(v["bytes"] / max(in_step(v), 1e-9) / 1e6, 1),
+                                  "TFLOP/s": round(v["flops"] / max(in_step(v), 1e-9) / 1e9, 1), "calls": v["calls"]}
                               for k, v in fam.items()}})
     # schedule-L bytes of the whole step: asr13x1 V'=29: 159 726 elements per encoder step
     T = 1 + (int(seconds * 16000) + 64) // 160
