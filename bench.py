@@ -470,7 +470,9 @@ def run_b200(args):
     loss_val = 0.0
     engine.prefetch()  # H2D of step 0's batch; every later step's H2D is issued inside the loop (one per step)
     for i in range(args.steps):
-        loss_val = engine.step_host(prefetch_next=(i + 1 < args.steps))
+        # one H2D of the batch and one D2H of the loss per step; the host reads step i-1's loss while step i runs
+        engine.step_host(prefetch_next=(i + 1 < args.steps), defer_loss=True)
+    loss_val = engine.flush_loss()
     f1.record()
     barrier()
     e2e_ms = max_over_ranks(max(f0.elapsed_time(f1), (time.perf_counter() - t0) * 1e3))

@@ -163,6 +163,9 @@ class TrainEngine:
         self.static = [t.to(self.dev, non_blocking=True) if torch.is_tensor(t) else t for t in self.host]
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host if torch.is_tensor(t))
         self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
+        self._loss_ring = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._loss_evt = [None, None]
+        self._host_steps = 0
         self.loss_dev = torch.zeros((), device=self.dev, dtype=torch.float32)
         self.graph = None
         self.use_graph = graph
@@ -243,11 +246,14 @@ class TrainEngine:
             self._staged_evt = torch.cuda.Event()
             self._staged_evt.record(self.copy_stream)
 
-    def step_host(self, batch=None, prefetch_next=False):
+    def step_host(self, batch=None, prefetch_next=False, defer_loss=False):
         """End-to-end step: H2D of the batch from pinned memory, the step, D2H of the loss.  Returns a float.
         If prefetch() staged this batch earlier, the inputs are taken over with a device-to-device copy instead of
         waiting for PCIe; `prefetch_next` (True: the pinned example batch, or a batch tuple) starts the next batch's
-        H2D before this step's loss is awaited, so the copy hides under the step."""
+        H2D before this step's loss is awaited, so the copy hides under the step.
+        defer_loss=True keeps the host one step ahead of the device: the call enqueues this step (and its loss D2H)
+        and returns the PREVIOUS step's loss (None on the first call; flush_loss() returns the last one), so the next
+        graph launch is already queued when the device finishes -- what a training loop that logs the loss does."""
         cur = torch.cuda.current_stream()
         if batch is None and self._staged_evt is not None:
             cur.wait_event(self._staged_evt)
@@ -266,10 +272,28 @@ class TrainEngine:
         self.step_device()
         if prefetch_next is not False and prefetch_next is not None:
             self.prefetch(None if prefetch_next is True else prefetch_next)
-        self.loss_host.copy_(self.loss_dev, non_blocking=True)
-        cur.synchronize()
-        return float(self.loss_host)
+        if not defer_loss:
+            self.loss_host.copy_(self.loss_dev, non_blocking=True)
+            cur.synchronize()
+            return float(self.loss_host)
+        slot = self._host_steps & 1
+        self._loss_ring[slot].copy_(self.loss_dev, non_blocking=True)
+        self._loss_evt[slot] = torch.cuda.Event()
+        self._loss_evt[slot].record(cur)
+        self._host_steps += 1
+        prev = slot ^ 1
+        if self._loss_evt[prev] is None:
+            return None
+        self._loss_evt[prev].synchronize()
+        return float(self._loss_ring[prev])
 
+    def flush_loss(self):
+        """Loss of the most recent deferred step (waits for it)."""
+        slot = (self._host_steps - 1) & 1
+        if self._host_steps == 0 or self._loss_evt[slot] is None:
+            return None
+        self._loss_evt[slot].synchronize()
+        return float(self._loss_ring[slot])
 
 class InferEngine:
     """Validation / inference path on one GPU (BASELINE config 5; predict.py:43-62, train.py:88-116 without the loss):
