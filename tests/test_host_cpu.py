@@ -145,3 +145,26 @@ def test_grad_sync_gloo_world2(tmp_path):
         for a0, a1, l0, l1 in zip(avg0, avg1, loc0, loc1):
             assert torch.allclose(a0, a1)  # every rank ends the step with the same gradient ...
             assert torch.allclose(a0, (l0 + l1) / 2, atol=1e-7)  # ... the average of the per-rank gradients
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the reference's CPU algorithm on the host cores) prints ONE JSON line with the
+    contract's keys; runs on any machine (no GPU)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload",
+                          "asr13x1_b4_10s_fp32", "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                         timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "audio-s/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("train audio-seconds/sec") and d["value"] > 0 and d["ms_per_step"] > 0
+    assert d["config"]["workload"] == "asr13x1_b4_10s_fp32" and d["config"]["encoder_steps"] == 501
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
