@@ -119,6 +119,10 @@ int lasr_pwconv_dgrad(const void* dy, const void* w, void* dx, int M, int Cin, i
                       int dtype, lasr_stream_t stream);
 int lasr_pwconv_wgrad(const void* dy, const void* x, float* dw, int M, int Cin, int Cout, int lddy, int ldx, int lddw,
                       int dtype, lasr_stream_t stream);
+/* two weight gradients of identical shape in one launch (a block's pointwise conv, models/QuartNet.py:31, and its
+ * residual conv, :62-63,75): dw1 += dy1^T x1, dw2 += dy2^T x2 */
+int lasr_pwconv_wgrad2(const void* dy1, const void* x1, float* dw1, const void* dy2, const void* x2, float* dw2, int M,
+                       int Cin, int Cout, int lddy, int ldx, int lddw, int dtype, lasr_stream_t stream);
 /* out[c] += sum_m x[m, c], c < C (fp32, caller zeroes): the decoder bias gradient (models/QuartNet.py:275) */
 int lasr_colsum(const void* x, float* out, int M, int C, int ld, int dtype, lasr_stream_t stream);
 

@@ -31,6 +31,8 @@ int gemm_simt_nn(const float* a, const float* b, float* c, int M, int N, int K, 
                  cudaStream_t stream);
 int gemm_tc_tn_accum(const void* dy, const void* x, float* dw, int R, int Cout, int Cin, int lddy, int ldx, int lddw,
                      cudaStream_t stream);
+int gemm_tc_tn_accum2(const void* dy1, const void* x1, float* dw1, const void* dy2, const void* x2, float* dw2, int R,
+                      int Cout, int Cin, int lddy, int ldx, int lddw, cudaStream_t stream);
 int gemm_simt_nt(const float* a, const float* b, float* c, const float* bias, const int32_t* lengths, int T, int M,
                  int N, int K, int lda, int ldb, int ldc, cudaStream_t stream);
 int gemm_simt_tn_accum(const float* dy, const float* x, float* dw, int R, int Cout, int Cin, int lddy, int ldx,
@@ -204,6 +206,17 @@ int lasr_pwconv_dgrad(const void* dy, const void* w, void* dx, int M, int Cin, i
     return gemm_simt_nn(static_cast<const float*>(dy), static_cast<const float*>(w), static_cast<float*>(dx), M, Cin,
                         Cout, lddy, ldw, lddx, stream);
   return LASR_ERR_BAD_DTYPE;
+}
+
+int lasr_pwconv_wgrad2(const void* dy1, const void* x1, float* dw1, const void* dy2, const void* x2, float* dw2, int M,
+                       int Cin, int Cout, int lddy, int ldx, int lddw, int dtype, lasr_stream_t stream) {
+  if (dtype == LASR_BF16) {
+    const int rc = gemm_tc_tn_accum2(dy1, x1, dw1, dy2, x2, dw2, M, Cout, Cin, lddy, ldx, lddw, stream);
+    if (rc != LASR_ERR_UNSUPPORTED) return rc;
+  }
+  const int rc1 = lasr_pwconv_wgrad(dy1, x1, dw1, M, Cin, Cout, lddy, ldx, lddw, dtype, stream);
+  if (rc1) return rc1;
+  return lasr_pwconv_wgrad(dy2, x2, dw2, M, Cin, Cout, lddy, ldx, lddw, dtype, stream);
 }
 
 int lasr_pwconv_wgrad(const void* dy, const void* x, float* dw, int M, int Cin, int Cout, int lddy, int ldx, int lddw,

@@ -38,6 +38,7 @@ struct GemmTcParams {
   const int32_t* lengths;
   int T;
   double* stats;  // [2, N] column sum / sum of squares, accumulated with RED.f64 (caller zeroes)
+  int groups;     // 1, or 2: two independent problems of identical shape share one launch (second set of tensor maps)
 };
 
 template <int BN>
@@ -116,7 +117,9 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ CUtensorMap tma_c, const GemmTcParams p) {
+               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_a2,
+               const __grid_constant__ CUtensorMap tma_b2, const __grid_constant__ CUtensorMap tma_c2,
+               const GemmTcParams p) {
   using Cfg = GemmTcCfg<BN>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
   constexpr int A_BYTES = Cfg::A_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
@@ -141,6 +144,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     if (EPI == 1) tma_prefetch_desc(&tma_c);
+    if (p.groups > 1) {
+      tma_prefetch_desc(&tma_a2);
+      tma_prefetch_desc(&tma_b2);
+      tma_prefetch_desc(&tma_c2);
+    }
   }
   if (warp_idx == 1 && lane == 0) {
 #pragma unroll
@@ -165,7 +173,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   pdl_wait();  // prologue above overlapped the previous kernel; operands and outputs are touched only from here on
 
   const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
-  const int num_tiles = tiles_mn * p.k_splits;
+  const int group_tiles = tiles_mn * p.k_splits;       // tiles of one problem
+  const int num_tiles = group_tiles * (p.groups > 1 ? 2 : 1);
 
   if (warp_idx == 0) {
     // ===================== TMA producer (converged warp, elected lane issues) =====================
@@ -174,8 +183,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int split = tile / tiles_mn;
-        const int mn = tile - split * tiles_mn;
+        const int grp = tile >= group_tiles ? 1 : 0;
+        const int tg = tile - grp * group_tiles;
+        const CUtensorMap* ma = grp ? &tma_a2 : &tma_a;
+        const CUtensorMap* mb = grp ? &tma_b2 : &tma_b;
+        const int split = tg / tiles_mn;
+        const int mn = tg - split * tiles_mn;
         const int m_blk = mn / p.num_n_blocks;
         const int n_blk = mn - m_blk * p.num_n_blocks;
         const int kb0 = split * p.kb_per_split;
@@ -187,18 +200,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (leader) {
             mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
             if constexpr (!A_MN) {
-              tma_load_2d(sa, &tma_a, &full_bar[stage], kb * BK, m_blk * BM);
+              tma_load_2d(sa, ma, &full_bar[stage], kb * BK, m_blk * BM);
             } else {
 #pragma unroll
               for (int c = 0; c < BM / 64; ++c)
-                tma_load_2d(sa + c * (64 * BK * 2), &tma_a, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
+                tma_load_2d(sa + c * (64 * BK * 2), ma, &full_bar[stage], m_blk * BM + c * 64, kb * BK);
             }
             if constexpr (!B_MN) {
-              tma_load_2d(sb, &tma_b, &full_bar[stage], kb * BK, n_blk * BN);
+              tma_load_2d(sb, mb, &full_bar[stage], kb * BK, n_blk * BN);
             } else {
 #pragma unroll
               for (int c = 0; c < BN / 64; ++c)
-                tma_load_2d(sb + c * (64 * BK * 2), &tma_b, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
+                tma_load_2d(sb + c * (64 * BK * 2), mb, &full_bar[stage], n_blk * BN + c * 64, kb * BK);
             }
           }
           __syncwarp();
@@ -219,7 +232,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       uint32_t phase = 0;
       int local_tile = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
-        const int split = tile / tiles_mn;
+        const int tg = tile >= group_tiles ? tile - group_tiles : tile;
+        const int split = tg / tiles_mn;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
         const int acc = local_tile & 1;
@@ -260,8 +274,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int local_tile = 0;
     int nred = 0;  // staging tiles this warp has handed to the TMA reduce unit (EPI == 1)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local_tile) {
-      const int split = tile / tiles_mn;
-      const int mn = tile - split * tiles_mn;
+      const int grp = tile >= group_tiles ? 1 : 0;
+      const int tg = tile - grp * group_tiles;
+      const CUtensorMap* mc = grp ? &tma_c2 : &tma_c;
+      const int split = tg / tiles_mn;
+      const int mn = tg - split * tiles_mn;
       const int m_blk = mn / p.num_n_blocks;
       const int n_blk = mn - m_blk * p.num_n_blocks;
       const int acc = local_tile & 1;
@@ -358,7 +375,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_reduce_add_2d(&tma_c, buf, col0, m_blk * BM + ew * 32);
+              tma_reduce_add_2d(mc, buf, col0, m_blk * BM + ew * 32);
               tma_store_commit();
             }
             ++nred;
@@ -1266,7 +1283,8 @@ int make_tmap_nd_bf16(CUtensorMap* out, const void* base, int rank, const uint64
 
 template <int BN, bool A_MN, bool B_MN, int EPI>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmTcParams& p, int grid,
-                       cudaStream_t stream, const CUtensorMap* tc = nullptr) {
+                       cudaStream_t stream, const CUtensorMap* tc = nullptr, const CUtensorMap* ta2 = nullptr,
+                       const CUtensorMap* tb2 = nullptr, const CUtensorMap* tc2 = nullptr) {
   using Cfg = GemmTcCfg<BN>;
   constexpr int kSmem = EPI == 1 ? Cfg::SMEM_BYTES_RED : Cfg::SMEM_BYTES;
   static bool configured = false;
@@ -1280,7 +1298,8 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmT
     configured = true;
   }
   LASR_CHECK_PDL(launch_pdl(1, gemm_tc_kernel<BN, A_MN, B_MN, EPI>, dim3(grid), dim3(256), kSmem, stream, ta, tb,
-                            tc != nullptr ? *tc : ta, p));
+                            tc != nullptr ? *tc : ta, ta2 != nullptr ? *ta2 : ta, tb2 != nullptr ? *tb2 : tb,
+                            tc2 != nullptr ? *tc2 : ta, p));
   return LASR_OK;
 }
 
@@ -1593,6 +1612,54 @@ int gemm_tc_nn(const void* a, const void* b, void* out, int M, int N, int K, int
     case 64: return launch_inst<64, false, true, 0>(ta, tb, p, grid, stream);
     case 128: return launch_inst<128, false, true, 0>(ta, tb, p, grid, stream);
     default: return launch_inst<256, false, true, 0>(ta, tb, p, grid, stream);
+  }
+}
+
+// Two weight gradients of identical shape (the block's pointwise conv and its residual conv) in ONE launch: every CTA
+// still owns one output tile, with a twice longer slice of the frame axis -- launch, prologue and the split-K reduction
+// epilogue are paid once instead of twice.  LASR_ERR_UNSUPPORTED: caller issues two single launches.
+int gemm_tc_tn_accum2(const void* dy1, const void* x1, float* dw1, const void* dy2, const void* x2, float* dw2, int R,
+                      int Cout, int Cin, int lddy, int ldx, int lddw, cudaStream_t stream) {
+  static const bool off = getenv("LASR_WGRAD_GROUPED") != nullptr && atoi(getenv("LASR_WGRAD_GROUPED")) == 0;
+  if (off) return LASR_ERR_UNSUPPORTED;
+  if (R <= 0 || Cout <= 0 || Cin < 32) return LASR_ERR_UNSUPPORTED;
+  if ((lddy % 8) || (ldx % 8)) return LASR_ERR_UNSUPPORTED;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(dw1) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dw2) & 15) == 0) &&
+                       ((static_cast<size_t>(lddw) * 4) % 16 == 0);
+  if (!aligned) return LASR_ERR_UNSUPPORTED;
+  const int BN = Cin <= 64 ? 64 : (Cin <= 128 ? 128 : 256);
+  CUtensorMap ta, tb, tc, ta2, tb2, tc2;
+  int rc = make_tmap_2d_bf16(&ta, dy1, Cout, R, static_cast<uint64_t>(lddy) * 2, 64, 64, true);
+  if (!rc) rc = make_tmap_2d_bf16(&tb, x1, Cin, R, static_cast<uint64_t>(ldx) * 2, 64, 64, true);
+  if (!rc) rc = make_tmap_2d_f32(&tc, dw1, Cin, Cout, static_cast<uint64_t>(lddw) * 4, 32, 32, true);
+  if (!rc) rc = make_tmap_2d_bf16(&ta2, dy2, Cout, R, static_cast<uint64_t>(lddy) * 2, 64, 64, true);
+  if (!rc) rc = make_tmap_2d_bf16(&tb2, x2, Cin, R, static_cast<uint64_t>(ldx) * 2, 64, 64, true);
+  if (!rc) rc = make_tmap_2d_f32(&tc2, dw2, Cin, Cout, static_cast<uint64_t>(lddw) * 4, 32, 32, true);
+  if (rc) return rc;
+  GemmTcParams p{};
+  p.M = Cout;
+  p.N = Cin;
+  p.K = R;
+  p.num_m_blocks = cdiv(Cout, 128);
+  p.num_n_blocks = cdiv(Cin, BN);
+  p.num_k_blocks = cdiv(R, 64);
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  int splits = kNumSMs / (2 * tiles);
+  if (splits < 1) return LASR_ERR_UNSUPPORTED;
+  if (splits > p.num_k_blocks) splits = p.num_k_blocks;
+  p.kb_per_split = cdiv(p.num_k_blocks, splits);
+  p.k_splits = cdiv(p.num_k_blocks, p.kb_per_split);
+  p.out = dw1;
+  p.ldc = lddw;
+  p.out_f32 = 1;
+  p.vec_ok = 1;
+  p.groups = 2;
+  const int total = 2 * tiles * p.k_splits;
+  const int grid = total < kNumSMs ? total : kNumSMs;
+  switch (BN) {
+    case 64: return launch_inst<64, true, true, 1>(ta, tb, p, grid, stream, &tc, &ta2, &tb2, &tc2);
+    case 128: return launch_inst<128, true, true, 1>(ta, tb, p, grid, stream, &tc, &ta2, &tb2, &tc2);
+    default: return launch_inst<256, true, true, 1>(ta, tb, p, grid, stream, &tc, &ta2, &tb2, &tc2);
   }
 }
 

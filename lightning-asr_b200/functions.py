@@ -119,24 +119,32 @@ class SepConvBNFn(torch.autograd.Function):
 
         # pointwise conv: weight gradient (split-K tcgen05 MN-major GEMM) and data gradient (W as MN-major B operand)
         g_pw, ret_pw = runtime.grad_sink(pw_w)
-
-        def _pw_wgrad():
-            ops.pwconv_wgrad(dy, d, out=g_pw)
-            runtime.grad_ready(pw_w)
-        runtime.defer(_pw_wgrad, dy, d)
-        dd = ops.pwconv_dgrad(dy, pw_s)
         ret_res = None
         dxr = None
         d_res_x = None
         need_dx = ctx.needs_input_grad[0]
+        rin = g_res = None
         if has_res:
             rin = x if res_x is None else res_x
             g_res, ret_res = runtime.grad_sink(res_w)
-
-            def _res_wgrad():
-                ops.pwconv_wgrad(dr, rin, out=g_res)
-                runtime.grad_ready(res_w)
-            runtime.defer(_res_wgrad, dr, rin)
+        if has_res and rin.shape == d.shape:
+            # the block's two weight gradients have the same shape: one grouped launch
+            def _wgrads():
+                ops.pwconv_wgrad2(dy, d, g_pw.view(Cout, Cin), dr, rin, g_res.view(Cout, Cin))
+                runtime.grad_ready(pw_w, res_w)
+            runtime.defer(_wgrads, dy, d, dr, rin)
+        else:
+            def _pw_wgrad():
+                ops.pwconv_wgrad(dy, d, out=g_pw)
+                runtime.grad_ready(pw_w)
+            runtime.defer(_pw_wgrad, dy, d)
+            if has_res:
+                def _res_wgrad():
+                    ops.pwconv_wgrad(dr, rin, out=g_res)
+                    runtime.grad_ready(res_w)
+                runtime.defer(_res_wgrad, dr, rin)
+        dd = ops.pwconv_dgrad(dy, pw_s)
+        if has_res:
             if (res_x is None and need_dx) or (res_x is not None and ctx.needs_input_grad[1]):
                 dxr = ops.pwconv_dgrad(dr, res_s)
                 if res_x is not None:

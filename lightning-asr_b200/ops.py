@@ -131,6 +131,17 @@ def pwconv_wgrad(dy, x, out=None, Cout=None):
     return dw
 
 
+def pwconv_wgrad2(dy1, x1, out1, dy2, x2, out2):
+    """out1 += dy1^T x1 and out2 += dy2^T x2 (same shapes) in one launch."""
+    for t in (dy1, x1, dy2, x2):
+        _chk(t, "operand")
+    lddy, Cin = dy1.shape[-1], x1.shape[-1]
+    if dy2.shape != dy1.shape or x2.shape != x1.shape or out1.shape != out2.shape:
+        raise _lib.LasrError("pwconv_wgrad2: the two problems must have identical shapes")
+    M = x1.numel() // Cin
+    call("lasr_pwconv_wgrad2", dy1, x1, out1, dy2, x2, out2, M, Cin, lddy, lddy, Cin, Cin, dtype_code(x1.dtype))
+
+
 def colsum(x, C, out=None):
     """out[c] += sum over rows of x[..., c], c < C."""
     ld = x.shape[-1]
