@@ -119,6 +119,15 @@ int lasr_pwconv_dgrad(const void* dy, const void* w, void* dx, int M, int Cin, i
                       int dtype, lasr_stream_t stream);
 int lasr_pwconv_wgrad(const void* dy, const void* x, float* dw, int M, int Cin, int Cout, int lddy, int ldx, int lddw,
                       int dtype, lasr_stream_t stream);
+/* Grouped launches for a QuartNetBlock's two 1x1 convs of identical shape (the pointwise conv of its last
+ * SeprationConv and the residual conv, models/QuartNet.py:31 and :62-63,75): dense operands (row pitch = channel
+ * count), no bias; problem 1 / 2 carry their own MaskCNN lengths and BatchNorm statistics buffers (nullable).
+ *   fwd2:   y1 = mask1(x1 w1^T), y2 = mask2(x2 w2^T)        dgrad2: dx1 = dy1 w1, dx2 = dy2 w2 */
+int lasr_pwconv_fwd2(const void* x1, const void* w1, void* y1, const int32_t* lengths1, double* stats1, const void* x2,
+                     const void* w2, void* y2, const int32_t* lengths2, double* stats2, int T, int M, int Cin, int Cout,
+                     int dtype, lasr_stream_t stream);
+int lasr_pwconv_dgrad2(const void* dy1, const void* w1, void* dx1, const void* dy2, const void* w2, void* dx2, int M,
+                       int Cin, int Cout, int dtype, lasr_stream_t stream);
 /* two weight gradients of identical shape in one launch (a block's pointwise conv, models/QuartNet.py:31, and its
  * residual conv, :62-63,75): dw1 += dy1^T x1, dw2 += dy2^T x2 */
 int lasr_pwconv_wgrad2(const void* dy1, const void* x1, float* dw1, const void* dy2, const void* x2, float* dw2, int M,

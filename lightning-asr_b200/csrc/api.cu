@@ -24,6 +24,9 @@ int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const
                int M, int N, int K, int lda, int ldb, int ldc, int out_f32, cudaStream_t stream);
 int gemm_tc_nn(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldc, int out_f32,
                cudaStream_t stream);
+int gemm_tc_grouped2(bool b_mn, const void* a1, const void* b1, void* out1, const int32_t* lengths1, double* stats1,
+                     const void* a2, const void* b2, void* out2, const int32_t* lengths2, double* stats2, int T, int M,
+                     int N, int K, int lda, int ldb, int ldc, cudaStream_t stream);
 int gemm_tc_nt_fused(const void* a, const void* b, void* out, const float* bias, const void* residual, int ld_res,
                      const int32_t* lengths, int T, int relu, int M, int N, int K, int lda, int ldb, int ldc,
                      cudaStream_t stream);
@@ -189,6 +192,31 @@ int lasr_pwconv_fwd(const void* x, const void* w, void* y, const float* bias, co
     return LASR_OK;
   }
   return LASR_ERR_BAD_DTYPE;
+}
+
+int lasr_pwconv_fwd2(const void* x1, const void* w1, void* y1, const int32_t* lengths1, double* stats1, const void* x2,
+                     const void* w2, void* y2, const int32_t* lengths2, double* stats2, int T, int M, int Cin, int Cout,
+                     int dtype, lasr_stream_t stream) {
+  if (dtype == LASR_BF16) {
+    const int rc = gemm_tc_grouped2(false, x1, w1, y1, lengths1, stats1, x2, w2, y2, lengths2, stats2, T, M, Cout, Cin,
+                                    Cin, Cin, Cout, stream);
+    if (rc != LASR_ERR_UNSUPPORTED) return rc;
+  }
+  const int rc1 = lasr_pwconv_fwd(x1, w1, y1, nullptr, lengths1, T, stats1, M, Cin, Cout, Cin, Cin, Cout, dtype, stream);
+  if (rc1) return rc1;
+  return lasr_pwconv_fwd(x2, w2, y2, nullptr, lengths2, T, stats2, M, Cin, Cout, Cin, Cin, Cout, dtype, stream);
+}
+
+int lasr_pwconv_dgrad2(const void* dy1, const void* w1, void* dx1, const void* dy2, const void* w2, void* dx2, int M,
+                       int Cin, int Cout, int dtype, lasr_stream_t stream) {
+  if (dtype == LASR_BF16) {
+    const int rc = gemm_tc_grouped2(true, dy1, w1, dx1, nullptr, nullptr, dy2, w2, dx2, nullptr, nullptr, 0, M, Cin, Cout,
+                                    Cout, Cin, Cin, stream);
+    if (rc != LASR_ERR_UNSUPPORTED) return rc;
+  }
+  const int rc1 = lasr_pwconv_dgrad(dy1, w1, dx1, M, Cin, Cout, Cout, Cin, Cin, dtype, stream);
+  if (rc1) return rc1;
+  return lasr_pwconv_dgrad(dy2, w2, dx2, M, Cin, Cout, Cout, Cin, Cin, dtype, stream);
 }
 
 int lasr_pwconv_fwd_fused(const void* x, const void* w, void* y, const float* bias, const void* residual,

@@ -429,6 +429,12 @@ struct GemmWsParams {
   int ld_res;
   int relu;
   int bias_after_mask;  // 1: masked rows keep bias (+ residual): BatchNorm folded into w / bias sees mask(pw) = 0
+  // grouped launch: two problems of identical shape (a block's pointwise and residual conv); CTAs >= group_ctas work
+  // on problem 2 with the second set of tensor maps and its own mask / statistics pointers
+  int groups;
+  int group_ctas;
+  const int32_t* lengths2;
+  double* stats2;
   const float* bias;
   const int32_t* lengths;
   int T;
@@ -459,7 +465,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <bool B_MN>
 __global__ void __launch_bounds__(384, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               const __grid_constant__ CUtensorMap tma_c, const GemmWsParams p) {
+               const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_a2,
+                const __grid_constant__ CUtensorMap tma_b2, const __grid_constant__ CUtensorMap tma_c2,
+                const GemmWsParams p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -476,14 +484,21 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_blk = blockIdx.x % p.num_n_blocks;
-  const int m_first = blockIdx.x / p.num_n_blocks;
+  const int grp = (p.groups > 1 && static_cast<int>(blockIdx.x) >= p.group_ctas) ? 1 : 0;
+  const int bid = static_cast<int>(blockIdx.x) - grp * p.group_ctas;
+  const CUtensorMap* ma = grp ? &tma_a2 : &tma_a;
+  const CUtensorMap* mb = grp ? &tma_b2 : &tma_b;
+  const CUtensorMap* mc = grp ? &tma_c2 : &tma_c;
+  const int32_t* lengths_g = grp ? p.lengths2 : p.lengths;
+  double* stats_g = grp ? p.stats2 : p.stats;
+  const int n_blk = bid % p.num_n_blocks;
+  const int m_first = bid / p.num_n_blocks;
   if (threadIdx.x == 0) WS_TRACE(0, 0);
 
   if (warp_idx == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_b);
-    tma_prefetch_desc(&tma_c);
+    tma_prefetch_desc(ma);
+    tma_prefetch_desc(mb);
+    tma_prefetch_desc(mc);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -526,11 +541,11 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         uint8_t* dst = s_w + kb * WS_WKB_BYTES;
         if (leader) {
           if constexpr (!B_MN) {
-            tma_load_2d(dst, &tma_b, w_bar, kb * WS_BK, n_blk * WS_BN);
+            tma_load_2d(dst, mb, w_bar, kb * WS_BK, n_blk * WS_BN);
           } else {
 #pragma unroll
             for (int c = 0; c < WS_BN / 64; ++c)
-              tma_load_2d(dst + c * (64 * WS_BK * 2), &tma_b, w_bar, n_blk * WS_BN + c * 64, kb * WS_BK);
+              tma_load_2d(dst + c * (64 * WS_BK * 2), mb, w_bar, n_blk * WS_BN + c * 64, kb * WS_BK);
           }
         }
       }
@@ -544,10 +559,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (leader) {
             mbar_arrive_expect_tx(&full_bar[stage], WS_A_BYTES);
             if (p.cluster == 1) {
-              tma_load_2d(s_a + stage * WS_A_BYTES, &tma_a, &full_bar[stage], kb * WS_BK, m_blk * WS_BM);
+              tma_load_2d(s_a + stage * WS_A_BYTES, ma, &full_bar[stage], kb * WS_BK, m_blk * WS_BM);
             } else {
               // this CTA fetches its slice of rows and multicasts it; the peers deliver the other slices
-              tma_load_2d_mc(s_a + stage * WS_A_BYTES + crank * slice_rows * 128, &tma_a, &full_bar[stage],
+              tma_load_2d_mc(s_a + stage * WS_A_BYTES + crank * slice_rows * 128, ma, &full_bar[stage],
                              kb * WS_BK, m_blk * WS_BM + crank * slice_rows, mc_mask);
             }
           }
@@ -619,9 +634,9 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t acc_phase = (local_tile >> 1) & 1;
       const int row = m_blk * WS_BM + r;
       bool keep = row < p.M;
-      if (keep && p.lengths != nullptr) {
+      if (keep && lengths_g != nullptr) {
         const int n = row / p.T;
-        keep = (row - n * p.T) < p.lengths[n];
+        keep = (row - n * p.T) < lengths_g[n];
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
@@ -696,7 +711,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if (threadIdx.x == 128) {
 #pragma unroll
         for (int j = 0; j < WS_BN / 64; ++j)
-          tma_store_2d(&tma_c, s_stg + j * (WS_BM * 128), n_blk * WS_BN + j * 64, m_blk * WS_BM);
+          tma_store_2d(mc, s_stg + j * (WS_BM * 128), n_blk * WS_BN + j * 64, m_blk * WS_BM);
         tma_store_commit();
       }
     }
@@ -708,7 +723,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int sub = sw & 1;          // 64-column sub-tile
     const int r0 = (sw >> 1) * 64;   // row half
     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-    const bool want = p.stats != nullptr;
+    const bool want = stats_g != nullptr;
     for (int m_blk = m_first; m_blk < p.num_m_blocks; m_blk += p.ctas_per_n) {
       named_bar_sync(1, 256);
       named_bar_sync(2, 256);
@@ -730,12 +745,12 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (want) {
       const int col = n_blk * WS_BN + sub * 64 + 2 * lane;
       if (col < p.N) {
-        red_add_f64(p.stats + col, static_cast<double>(s0));
-        red_add_f64(p.stats + p.N + col, static_cast<double>(q0));
+        red_add_f64(stats_g + col, static_cast<double>(s0));
+        red_add_f64(stats_g + p.N + col, static_cast<double>(q0));
       }
       if (col + 1 < p.N) {
-        red_add_f64(p.stats + col + 1, static_cast<double>(s1));
-        red_add_f64(p.stats + p.N + col + 1, static_cast<double>(q1));
+        red_add_f64(stats_g + col + 1, static_cast<double>(s1));
+        red_add_f64(stats_g + p.N + col + 1, static_cast<double>(q1));
       }
     }
   }
@@ -761,7 +776,9 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 template <bool B_MN>
 __global__ void __launch_bounds__(384, 1)
 gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-                const __grid_constant__ CUtensorMap tma_c, const GemmWsParams p) {
+                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_a2,
+                const __grid_constant__ CUtensorMap tma_b2, const __grid_constant__ CUtensorMap tma_c2,
+                const GemmWsParams p) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -780,16 +797,22 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int crank = static_cast<int>(cluster_ctarank());
   const bool is_leader = crank == 0;
-  const int pair = blockIdx.x >> 1;
+  const int grp = (p.groups > 1 && static_cast<int>(blockIdx.x) >= p.group_ctas) ? 1 : 0;
+  const CUtensorMap* ma = grp ? &tma_a2 : &tma_a;
+  const CUtensorMap* mb = grp ? &tma_b2 : &tma_b;
+  const CUtensorMap* mc = grp ? &tma_c2 : &tma_c;
+  const int32_t* lengths_g = grp ? p.lengths2 : p.lengths;
+  double* stats_g = grp ? p.stats2 : p.stats;
+  const int pair = (static_cast<int>(blockIdx.x) - grp * p.group_ctas) >> 1;
   const int n_blk2 = pair % p.num_n_blocks;     // 256-column slice of the pair
   const int m_first = pair / p.num_n_blocks;    // 256-row tiles m_first, m_first + ctas_per_n, ...
   const int n0 = n_blk2 * 256;                  // first output column of the pair
   const int nw0 = n0 + crank * WS_BN;           // first weight row (output column) this CTA keeps
 
   if (warp_idx == 0 && lane == 0) {
-    tma_prefetch_desc(&tma_a);
-    tma_prefetch_desc(&tma_b);
-    tma_prefetch_desc(&tma_c);
+    tma_prefetch_desc(ma);
+    tma_prefetch_desc(mb);
+    tma_prefetch_desc(mc);
   }
   if (warp_idx == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -823,11 +846,11 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       uint8_t* dst = s_w + kb * WS_WKB_BYTES;
       if (leader_lane) {
         if constexpr (!B_MN) {
-          tma_load_2d_2sm(dst, &tma_b, w_bar, kb * WS_BK, nw0);
+          tma_load_2d_2sm(dst, mb, w_bar, kb * WS_BK, nw0);
         } else {
 #pragma unroll
           for (int c = 0; c < WS_BN / 64; ++c)
-            tma_load_2d_2sm(dst + c * (64 * WS_BK * 2), &tma_b, w_bar, nw0 + c * 64, kb * WS_BK);
+            tma_load_2d_2sm(dst + c * (64 * WS_BK * 2), mb, w_bar, nw0 + c * 64, kb * WS_BK);
         }
       }
     }
@@ -841,7 +864,7 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         if (leader_lane) {
           if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * WS_A_BYTES);
-          tma_load_2d_2sm(s_a + stage * WS_A_BYTES, &tma_a, &full_bar[stage], kb * WS_BK, row0);
+          tma_load_2d_2sm(s_a + stage * WS_A_BYTES, ma, &full_bar[stage], kb * WS_BK, row0);
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -899,9 +922,9 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       const uint32_t acc_phase = (local_tile >> 1) & 1;
       const int row = m2 * 256 + crank * WS_BM + r;
       bool keep = row < p.M;
-      if (keep && p.lengths != nullptr) {
+      if (keep && lengths_g != nullptr) {
         const int n = row / p.T;
-        keep = (row - n * p.T) < p.lengths[n];
+        keep = (row - n * p.T) < lengths_g[n];
       }
       mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc_fence_after();
@@ -974,7 +997,7 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         if (threadIdx.x == 128) {
 #pragma unroll
           for (int j = 0; j < WS_BN / 64; ++j)
-            tma_store_2d(&tma_c, s_stg + j * (WS_BM * 128), n0 + h * WS_BN + j * 64, m2 * 256 + crank * WS_BM);
+            tma_store_2d(mc, s_stg + j * (WS_BM * 128), n0 + h * WS_BN + j * 64, m2 * 256 + crank * WS_BM);
           tma_store_commit();
         }
       }
@@ -986,7 +1009,7 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     const int sub = sw & 1;
     const int r0 = (sw >> 1) * 64;
     float s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, q0[2] = {0.f, 0.f}, q1[2] = {0.f, 0.f};
-    const bool want = p.stats != nullptr;
+    const bool want = stats_g != nullptr;
     for (int m2 = m_first; m2 < p.num_m_blocks; m2 += p.ctas_per_n) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -1013,12 +1036,12 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
       for (int h = 0; h < 2; ++h) {
         const int col = n0 + h * WS_BN + sub * 64 + 2 * lane;
         if (col < p.N) {
-          red_add_f64(p.stats + col, static_cast<double>(s0[h]));
-          red_add_f64(p.stats + p.N + col, static_cast<double>(q0[h]));
+          red_add_f64(stats_g + col, static_cast<double>(s0[h]));
+          red_add_f64(stats_g + p.N + col, static_cast<double>(q0[h]));
         }
         if (col + 1 < p.N) {
-          red_add_f64(p.stats + col + 1, static_cast<double>(s1[h]));
-          red_add_f64(p.stats + p.N + col + 1, static_cast<double>(q1[h]));
+          red_add_f64(stats_g + col + 1, static_cast<double>(s1[h]));
+          red_add_f64(stats_g + p.N + col + 1, static_cast<double>(q1[h]));
         }
       }
     }
@@ -1311,6 +1334,13 @@ struct WsFused {
   int ld_res = 0;
   int relu = 0;
   int bias_after_mask = 0;
+  // second problem of a grouped launch (same M, N, K and leading dimensions): activations, weights, output and its
+  // own MaskCNN lengths / BatchNorm statistics
+  const void* a2 = nullptr;
+  const void* b2 = nullptr;
+  void* out2 = nullptr;
+  const int32_t* lengths2 = nullptr;
+  double* stats2 = nullptr;
 };
 
 // weight-stationary launch; returns LASR_ERR_UNSUPPORTED when the shape does not qualify (caller falls back)
@@ -1338,6 +1368,21 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tc, out, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
   if (rc) return rc;
+  const bool grouped = fu.a2 != nullptr;
+  if (grouped && (cluster > 1 || (reinterpret_cast<uintptr_t>(fu.out2) & 15))) return LASR_ERR_UNSUPPORTED;
+  CUtensorMap ta2 = ta, tb2 = tb, tc2 = tc;
+  if (grouped) {
+    rc = make_tmap_2d_bf16(&ta2, fu.a2, K, M, static_cast<uint64_t>(lda) * 2, 64, 128, true);
+    if (rc) return rc;
+    if (!b_mn)
+      rc = make_tmap_2d_bf16(&tb2, fu.b2, K, N, static_cast<uint64_t>(ldb) * 2, 64, WS_BN, true);
+    else
+      rc = make_tmap_2d_bf16(&tb2, fu.b2, N, K, static_cast<uint64_t>(ldb) * 2, 64, 64, true);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tc2, fu.out2, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
+    if (rc) return rc;
+  }
+  const int sms = grouped ? kNumSMs / 2 : kNumSMs;  // CTAs available to ONE problem
   GemmWsParams p{};
   p.M = M;
   p.N = N;
@@ -1345,8 +1390,8 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
   p.num_m_blocks = cdiv(M, WS_BM);
   p.num_n_blocks = cdiv(N, WS_BN);
   p.num_k_blocks = kbs;
-  if (p.num_n_blocks > kNumSMs) return LASR_ERR_UNSUPPORTED;
-  int per_n = kNumSMs / p.num_n_blocks;
+  if (p.num_n_blocks > sms) return LASR_ERR_UNSUPPORTED;
+  int per_n = sms / p.num_n_blocks;
   if (per_n > p.num_m_blocks) per_n = p.num_m_blocks;
   // equalise: the same number of rounds with as few CTAs as needed keeps every CTA's tile count within one
   p.cluster = cluster;
@@ -1411,9 +1456,13 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
   const int rounds = cdiv(p.num_m_blocks, per_n);
   per_n = cdiv(p.num_m_blocks, rounds);
   p.ctas_per_n = per_n;
-  cfg.gridDim = dim3(p.num_n_blocks * per_n);
-  cudaError_t le = b_mn ? cudaLaunchKernelEx(&cfg, gemm_ws_kernel<true>, ta, tb, tc, p)
-                        : cudaLaunchKernelEx(&cfg, gemm_ws_kernel<false>, ta, tb, tc, p);
+  p.groups = grouped ? 2 : 1;
+  p.group_ctas = p.num_n_blocks * per_n;
+  p.lengths2 = fu.lengths2;
+  p.stats2 = fu.stats2;
+  cfg.gridDim = dim3(p.group_ctas * p.groups);
+  cudaError_t le = b_mn ? cudaLaunchKernelEx(&cfg, gemm_ws_kernel<true>, ta, tb, tc, ta2, tb2, tc2, p)
+                        : cudaLaunchKernelEx(&cfg, gemm_ws_kernel<false>, ta, tb, tc, ta2, tb2, tc2, p);
   if (le != cudaSuccess) {
     lasr_set_cuda_error(le);
     return LASR_ERR_CUDA;
@@ -1445,6 +1494,20 @@ static int launch_ws2(bool b_mn, const void* a, const void* b, void* out, const 
   if (rc) return rc;
   rc = make_tmap_2d_bf16(&tc, out, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
   if (rc) return rc;
+  const bool grouped = fu.a2 != nullptr;
+  if (grouped && (reinterpret_cast<uintptr_t>(fu.out2) & 15)) return LASR_ERR_UNSUPPORTED;
+  CUtensorMap ta2 = ta, tb2 = tb, tc2 = tc;
+  if (grouped) {
+    rc = make_tmap_2d_bf16(&ta2, fu.a2, K, M, static_cast<uint64_t>(lda) * 2, 64, 128, true);
+    if (rc) return rc;
+    if (!b_mn)
+      rc = make_tmap_2d_bf16(&tb2, fu.b2, K, N, static_cast<uint64_t>(ldb) * 2, 64, WS_BN, true);
+    else
+      rc = make_tmap_2d_bf16(&tb2, fu.b2, N, K, static_cast<uint64_t>(ldb) * 2, 64, 64, true);
+    if (rc) return rc;
+    rc = make_tmap_2d_bf16(&tc2, fu.out2, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
+    if (rc) return rc;
+  }
   GemmWsParams p{};
   p.M = M;
   p.N = N;
@@ -1452,7 +1515,7 @@ static int launch_ws2(bool b_mn, const void* a, const void* b, void* out, const 
   p.num_m_blocks = cdiv(M, 256);   // 256-row pair tiles
   p.num_n_blocks = cdiv(N, 256);   // 256-column pair slices
   p.num_k_blocks = kbs;
-  const int pairs = kNumSMs / 2;
+  const int pairs = (kNumSMs / 2) / (grouped ? 2 : 1);  // pairs available to ONE problem
   if (p.num_n_blocks > pairs) return LASR_ERR_UNSUPPORTED;
   int per_n = pairs / p.num_n_blocks;
   if (per_n > p.num_m_blocks) per_n = p.num_m_blocks;
@@ -1488,7 +1551,11 @@ static int launch_ws2(bool b_mn, const void* a, const void* b, void* out, const 
     configured = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(2 * p.num_n_blocks * per_n);
+  p.groups = grouped ? 2 : 1;
+  p.group_ctas = 2 * p.num_n_blocks * per_n;
+  p.lengths2 = fu.lengths2;
+  p.stats2 = fu.stats2;
+  cfg.gridDim = dim3(p.group_ctas * p.groups);
   cfg.blockDim = dim3(384);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -1501,8 +1568,8 @@ static int launch_ws2(bool b_mn, const void* a, const void* b, void* out, const 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled(1) ? 2 : 1;
-  cudaError_t le = b_mn ? cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<true>, ta, tb, tc, p)
-                        : cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<false>, ta, tb, tc, p);
+  cudaError_t le = b_mn ? cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<true>, ta, tb, tc, ta2, tb2, tc2, p)
+                        : cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<false>, ta, tb, tc, ta2, tb2, tc2, p);
   if (le != cudaSuccess) {
     lasr_set_cuda_error(le);
     return LASR_ERR_CUDA;
@@ -1555,6 +1622,26 @@ int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const
     case 128: return launch_inst<128, false, false, 0>(ta, tb, p, grid, stream);
     default: return launch_inst<256, false, false, 0>(ta, tb, p, grid, stream);
   }
+}
+
+// Two forward (b_mn = false: y = x w^T with mask / statistics) or data-gradient (b_mn = true: dx = dy w) GEMMs of
+// identical shape in ONE launch: the CTAs are split between the problems, each CTA walks twice as many tiles, and the
+// launch, prologue and weight-slice load are paid once.  LASR_ERR_UNSUPPORTED: caller issues two launches.
+int gemm_tc_grouped2(bool b_mn, const void* a1, const void* b1, void* out1, const int32_t* lengths1, double* stats1,
+                     const void* a2, const void* b2, void* out2, const int32_t* lengths2, double* stats2, int T, int M,
+                     int N, int K, int lda, int ldb, int ldc, cudaStream_t stream) {
+  static const bool off = getenv("LASR_GEMM_GROUPED") != nullptr && atoi(getenv("LASR_GEMM_GROUPED")) == 0;
+  if (off || M <= 0 || N <= 64 || K <= 0) return LASR_ERR_UNSUPPORTED;
+  if ((lda % 8) || (ldb % 8)) return LASR_ERR_UNSUPPORTED;
+  WsFused fu;
+  fu.a2 = a2;
+  fu.b2 = b2;
+  fu.out2 = out2;
+  fu.lengths2 = lengths2;
+  fu.stats2 = stats2;
+  const int rc2 = launch_ws2(b_mn, a1, b1, out1, nullptr, lengths1, T, stats1, M, N, K, lda, ldb, ldc, stream, fu);
+  if (rc2 != LASR_ERR_UNSUPPORTED) return rc2;
+  return launch_ws(b_mn, a1, b1, out1, nullptr, lengths1, T, stats1, M, N, K, lda, ldb, ldc, stream, fu);
 }
 
 // inference epilogue: y = act(mask(x w^T) + bias + residual), bf16; weight-stationary kernels only

@@ -53,15 +53,20 @@ class SepConvBNFn(torch.autograd.Function):
         T = d.shape[1]
         pw_s = runtime.weight(pw_w, dt).view(Cout, Cin)
         sums1 = _stats(Cout, dev) if training else None
-        y = ops.pwconv_fwd(d, pw_s, lengths=lengths, T=T, stats=sums1)
         has_res = res_w is not None
         r = res_s = bn2 = None
         if has_res:
             rin = x if res_x is None else res_x
             res_s = runtime.weight(res_w, dt).view(Cout, rin.shape[-1])
             sums2 = _stats(Cout, dev) if training else None
-            r = ops.pwconv_fwd(rin, res_s, stats=sums2)
+            if rin.shape == d.shape:  # the block's two 1x1 convs have the same shape: one grouped launch
+                y, r = ops.pwconv_fwd2(d, pw_s, lengths, sums1, rin, res_s, None, sums2, T)
+            else:
+                y = ops.pwconv_fwd(d, pw_s, lengths=lengths, T=T, stats=sums1)
+                r = ops.pwconv_fwd(rin, res_s, stats=sums2)
             bn2 = ops.BNForward(rbn_w.detach(), rbn_b.detach(), rbn_buffers[0], rbn_buffers[1], rbn_buffers[2], sums2)
+        else:
+            y = ops.pwconv_fwd(d, pw_s, lengths=lengths, T=T, stats=sums1)
         bn1 = ops.BNForward(bn_w.detach(), bn_b.detach(), bn_buffers[0], bn_buffers[1], bn_buffers[2], sums1)
         gate = s = hidden = sums_y = scale1 = shift1 = None
         se_side = True
@@ -143,12 +148,15 @@ class SepConvBNFn(torch.autograd.Function):
                     ops.pwconv_wgrad(dr, rin, out=g_res)
                     runtime.grad_ready(res_w)
                 runtime.defer(_res_wgrad, dr, rin)
-        dd = ops.pwconv_dgrad(dy, pw_s)
-        if has_res:
-            if (res_x is None and need_dx) or (res_x is not None and ctx.needs_input_grad[1]):
+        want_dxr = has_res and ((res_x is None and need_dx) or (res_x is not None and ctx.needs_input_grad[1]))
+        if want_dxr and res_s.shape == pw_s.shape:
+            dd, dxr = ops.pwconv_dgrad2(dy, pw_s, dr, res_s)  # both data gradients in one grouped launch
+        else:
+            dd = ops.pwconv_dgrad(dy, pw_s)
+            if want_dxr:
                 dxr = ops.pwconv_dgrad(dr, res_s)
-                if res_x is not None:
-                    d_res_x, dxr = dxr, None
+        if want_dxr and res_x is not None:
+            d_res_x, dxr = dxr, None
         # depthwise conv
         g_dw, ret_dw = runtime.grad_sink(dw_w)
 

@@ -131,6 +131,35 @@ def pwconv_wgrad(dy, x, out=None, Cout=None):
     return dw
 
 
+def pwconv_fwd2(x1, w1, lengths1, stats1, x2, w2, lengths2, stats2, T):
+    """Two 1x1 convs of identical shape in one launch: y1 = mask1(x1 w1^T), y2 = mask2(x2 w2^T) (+ BN statistics)."""
+    for t in (x1, w1, x2, w2):
+        _chk(t, "operand")
+    Cin, Cout = x1.shape[-1], w1.shape[0]
+    if x2.shape != x1.shape or w2.shape != w1.shape or w1.shape[1] != Cin or w1.dtype != x1.dtype or x2.dtype != x1.dtype:
+        raise _lib.LasrError("pwconv_fwd2: the two problems must have identical shapes and dtypes")
+    M = x1.numel() // Cin
+    y1 = torch.empty(x1.shape[:-1] + (Cout,), device=x1.device, dtype=x1.dtype)
+    y2 = torch.empty_like(y1)
+    call("lasr_pwconv_fwd2", x1, w1, y1, lengths1, stats1, x2, w2, y2, lengths2, stats2, T, M, Cin, Cout,
+         dtype_code(x1.dtype))
+    return y1, y2
+
+
+def pwconv_dgrad2(dy1, w1, dy2, w2):
+    """dx1 = dy1 w1 and dx2 = dy2 w2 (identical shapes, dense operands) in one launch."""
+    for t in (dy1, w1, dy2, w2):
+        _chk(t, "operand")
+    Cout, Cin = w1.shape[0], w1.shape[1]
+    if dy2.shape != dy1.shape or w2.shape != w1.shape or dy1.shape[-1] != Cout:
+        raise _lib.LasrError("pwconv_dgrad2: the two problems must have identical dense shapes")
+    M = dy1.numel() // Cout
+    dx1 = torch.empty(dy1.shape[:-1] + (Cin,), device=dy1.device, dtype=dy1.dtype)
+    dx2 = torch.empty_like(dx1)
+    call("lasr_pwconv_dgrad2", dy1, w1, dx1, dy2, w2, dx2, M, Cin, Cout, dtype_code(dy1.dtype))
+    return dx1, dx2
+
+
 def pwconv_wgrad2(dy1, x1, out1, dy2, x2, out2):
     """out1 += dy1^T x1 and out2 += dy2^T x2 (same shapes) in one launch."""
     for t in (dy1, x1, dy2, x2):
