@@ -90,6 +90,11 @@ int lasr_dwconv1d_fwd(const void* x, const float* w, void* y, const void* addend
  * (caller zeroes).  Deterministic only up to fp32 atomic ordering. */
 int lasr_dwconv1d_wgrad(const void* x, const void* dy, float* dw, int N, int T_in, int T_out, int C, int K, int stride,
                         int dtype, lasr_stream_t stream);
+/* stride-1 backward of one layer in ONE launch: dx [N, T, C] = correlation of dy with the flipped taps (+ addend, the
+ * residual-branch gradient, nullable) and dw [C, 1, K] += sum over frames of dy * shifted x  (autograd of
+ * models/QuartNet.py:30) */
+int lasr_dwconv1d_bwd(const void* x, const void* dy, const float* w, const void* addend, void* dx, float* dw, int N,
+                      int T, int C, int K, int dtype, lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pointwise (1x1) Conv1d as a GEMM over frames (replaces nn.Conv1d(Cin, Cout, 1), models/QuartNet.py:22-23,31,

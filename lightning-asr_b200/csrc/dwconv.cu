@@ -385,6 +385,8 @@ int dwconv_tc_supported(int C, int K, int stride);
 int dwconv_tc_fwd(const void* x, const float* w, void* y, const void* addend, int N, int T, int C, int K, int flip,
                   cudaStream_t stream);
 int dwconv_tc_wgrad(const void* x, const void* dy, float* dw, int N, int T, int C, int K, cudaStream_t stream);
+int dwconv_tc_bwd(const void* x, const void* dy, const float* w, const void* addend, void* dx, float* dw, int N, int T,
+                  int C, int K, cudaStream_t stream);
 }  // namespace lasr
 
 using namespace lasr;
@@ -402,6 +404,18 @@ int lasr_dwconv1d_fwd(const void* x, const float* wt, void* y, const void* adden
   if (dtype == LASR_BF16)
     return fwd_t<__nv_bfloat16>(x, wt, y, addend, N, T_in, T_out, C, K, stride, flip, dtype, stream);
   return LASR_ERR_BAD_DTYPE;
+}
+
+int lasr_dwconv1d_bwd(const void* x, const void* dy, const float* wt, const void* addend, void* dx, float* dwt, int N,
+                      int T, int C, int K, int dtype, lasr_stream_t stream) {
+  if (N <= 0 || T <= 0 || C <= 0 || (C & 1)) return LASR_ERR_BAD_SHAPE;
+  if (dtype == LASR_BF16 && dwconv_tc_supported(C, K, 1)) {
+    const int rc = dwconv_tc_bwd(x, dy, wt, addend, dx, dwt, N, T, C, K, stream);
+    if (rc != LASR_ERR_UNSUPPORTED) return rc;
+  }
+  const int rc1 = lasr_dwconv1d_wgrad(x, dy, dwt, N, T, T, C, K, 1, dtype, stream);
+  if (rc1) return rc1;
+  return lasr_dwconv1d_fwd(dy, wt, dx, addend, N, T, T, C, K, 1, 1, dtype, stream);
 }
 
 int lasr_dwconv1d_wgrad(const void* x, const void* dy, float* dwt, int N, int T_in, int T_out, int C, int K,

@@ -155,7 +155,7 @@ __device__ __forceinline__ void load_series(const __nv_bfloat16* __restrict__ sr
   }
 }
 
-__global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_fwd_kernel(const DwTcParams p) {
+__device__ __forceinline__ void dwconv_tc_fwd_body(const DwTcParams& p, const int bid) {
   pdl_launch_dependents();  // the Toeplitz build / TMEM allocation below overlap the previous kernel's tail; taps are
                             // parameters (written behind a full stream barrier), see common.cuh
   extern __shared__ uint8_t smem_raw[];
@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_fwd_kernel(const DwTc
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int cg = blockIdx.x % p.num_cg;
-  const int first = blockIdx.x / p.num_cg;
+  const int cg = bid % p.num_cg;
+  const int first = bid / p.num_cg;
   const int c0 = cg * DT_CG;
   const int P = p.K / 2;
 
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_fwd_kernel(const DwTc
 // ------------------------------------------------------------------------------------------------
 // weight gradient
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_wgrad_kernel(const DwTcParams p) {
+__device__ __forceinline__ void dwconv_tc_wgrad_body(const DwTcParams& p, const int bid) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -366,8 +366,8 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_wgrad_kernel(const Dw
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int cg = blockIdx.x % p.num_cg;
-  const int first = blockIdx.x / p.num_cg;
+  const int cg = bid % p.num_cg;
+  const int first = bid / p.num_cg;
   const int c0 = cg * DT_CG;
   const int P = p.K / 2;
 
@@ -478,6 +478,23 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_wgrad_kernel(const Dw
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
+}
+
+__global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_fwd_kernel(const DwTcParams p) {
+  dwconv_tc_fwd_body(p, static_cast<int>(blockIdx.x));
+}
+__global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc_wgrad_kernel(const DwTcParams p) {
+  dwconv_tc_wgrad_body(p, static_cast<int>(blockIdx.x));
+}
+// Backward of one depthwise layer in ONE launch: CTAs [0, split) compute the data gradient (flipped taps + residual
+// addend), the rest the weight gradient.  Both read the same upstream gradient; each half walks twice as many items per
+// CTA as a full-grid launch would, which amortises the load -> MMA -> store pipeline fill that dominates these kernels.
+__global__ void __launch_bounds__(DT_THREADS, 1)
+dwconv_tc_bwd_kernel(const DwTcParams pd, const DwTcParams pw, const int split) {
+  if (static_cast<int>(blockIdx.x) < split)
+    dwconv_tc_fwd_body(pd, static_cast<int>(blockIdx.x));
+  else
+    dwconv_tc_wgrad_body(pw, static_cast<int>(blockIdx.x) - split);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -747,11 +764,11 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc16_fwd_kernel(const Dw
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
-static void dt_schedule(DwTcParams& p) {
+static void dt_schedule(DwTcParams& p, int sms = kNumSMs) {
   p.num_cg = cdiv(p.C, DT_CG);
   p.t_chunks = cdiv(p.T, DT_CHUNK);
   p.items_per_cg = p.N * p.t_chunks;
-  int per = kNumSMs / p.num_cg;
+  int per = sms / p.num_cg;
   if (per < 1) per = 1;
   if (per > p.items_per_cg) per = p.items_per_cg;
   const int rounds = cdiv(p.items_per_cg, per);
@@ -870,6 +887,57 @@ int dwconv_tc_wgrad(const void* x, const void* dy, float* dw, int N, int T, int 
     configured = true;
   }
   LASR_CHECK_PDL(launch_pdl(2, dwconv_tc_wgrad_kernel, dim3(p.num_cg * p.ctas_per_cg), dim3(DT_THREADS), smem, stream, p));
+  return LASR_OK;
+}
+
+
+// dx = corr(dy, flipped taps) + addend   and   dw += sum dy * shifted x   in one launch (dwconv_tc_bwd_kernel)
+int dwconv_tc_bwd(const void* x, const void* dy, const float* w, const void* addend, void* dx, float* dw, int N, int T,
+                  int C, int K, cudaStream_t stream) {
+  static const bool off = getenv("LASR_DW_GROUPED") != nullptr && atoi(getenv("LASR_DW_GROUPED")) == 0;
+  if (off || g_dt_trace != nullptr) return LASR_ERR_UNSUPPORTED;
+  DwTcParams pd{};
+  pd.x = static_cast<const __nv_bfloat16*>(dy);
+  pd.w = w;
+  pd.y = static_cast<__nv_bfloat16*>(dx);
+  pd.addend = static_cast<const __nv_bfloat16*>(addend);
+  pd.N = N;
+  pd.T = T;
+  pd.C = C;
+  pd.K = K;
+  pd.KS = cdiv(K + 7, 16) * 16;
+  pd.flip = 1;
+  pd.w_early = early_param_loads() ? 1 : 0;
+  pd.ZL = DT_CHUNK + pd.KS - 8;
+  dt_schedule(pd, kNumSMs / 2);
+  DwTcParams pw{};
+  pw.x = static_cast<const __nv_bfloat16*>(x);
+  pw.dy = static_cast<const __nv_bfloat16*>(dy);
+  pw.dw = dw;
+  pw.N = N;
+  pw.T = T;
+  pw.C = C;
+  pw.K = K;
+  pw.KS = 0;
+  pw.ZL = DT_CHUNK + 128;
+  dt_schedule(pw, kNumSMs / 2);
+  int smem_d = 128 + DT_CG * (pd.KS / 8) * 128 + DT_STAGES * DT_CG * pd.ZL * 2 + 128;
+  const int smem_w = 128 + 2 * (DT_CG * pw.ZL * 2 + DT_CG * DT_CHUNK * 2) + 128;
+  int smem = smem_d > smem_w ? smem_d : smem_w;
+  if (smem < 116 * 1024) smem = 116 * 1024;  // one CTA per SM (the data-gradient half allocates all 512 TMEM columns)
+  if (smem > 200 * 1024) return LASR_ERR_UNSUPPORTED;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      lasr_set_cuda_error(e);
+      return LASR_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int split = pd.num_cg * pd.ctas_per_cg;
+  const int grid = split + pw.num_cg * pw.ctas_per_cg;
+  LASR_CHECK_PDL(launch_pdl(2, dwconv_tc_bwd_kernel, dim3(grid), dim3(DT_THREADS), smem, stream, pd, pw, split));
   return LASR_OK;
 }
 

@@ -159,16 +159,18 @@ class SepConvBNFn(torch.autograd.Function):
             d_res_x, dxr = dxr, None
         # depthwise conv
         g_dw, ret_dw = runtime.grad_sink(dw_w)
-
-        def _dw_wgrad():
-            ops.dwconv_wgrad(x, dd, K, stride=stride, out=g_dw)
-            runtime.grad_ready(dw_w)
-        runtime.defer(_dw_wgrad, x, dd)
         dx = None
-        if need_dx:
-            if stride != 1:
+        if need_dx and stride == 1:
+            # data gradient (+ the residual branch's gradient as addend) and weight gradient in one launch
+            dx, _ = ops.dwconv_bwd(x, dd, dw_w.detach(), addend=dxr, out_dw=g_dw)
+            runtime.grad_ready(dw_w)
+        else:
+            def _dw_wgrad():
+                ops.dwconv_wgrad(x, dd, K, stride=stride, out=g_dw)
+                runtime.grad_ready(dw_w)
+            runtime.defer(_dw_wgrad, x, dd)
+            if need_dx:
                 raise RuntimeError("lightning_asr_b200: data gradient of the stride-2 first conv is not needed/implemented")
-            dx = ops.dwconv_fwd(dd, dw_w.detach(), stride=1, flip=True, addend=dxr)
         return (dx, d_res_x, None, ret_dw, ret_pw, ret_bn_w, ret_bn_b, ret_res, ret_rbn_w, ret_rbn_b, ret_se1, ret_se2,
                 None, None, None, None, None)
 

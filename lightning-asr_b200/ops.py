@@ -77,6 +77,19 @@ def dwconv_wgrad(x, dy, K, stride=1, out=None):
     return dw
 
 
+def dwconv_bwd(x, dy, w, addend=None, out_dw=None):
+    """Stride-1 backward in one launch: -> (dx [N, T, C], dw [C, 1, K] fp32 accumulated into out_dw if given)."""
+    _chk(x, "x"), _chk(dy, "dy"), _chk(w, "w")
+    N, T, C = x.shape
+    K = w.shape[-1]
+    if dy.shape != x.shape:
+        raise _lib.LasrError("dwconv_bwd: stride-1 layers only (dy and x must have the same shape)")
+    dx = torch.empty_like(dy)
+    dw = out_dw if out_dw is not None else torch.zeros((C, 1, K), device=x.device, dtype=torch.float32)
+    call("lasr_dwconv1d_bwd", x, dy, w, addend, dx, dw, N, T, C, K, dtype_code(x.dtype))
+    return dx, dw
+
+
 def pwconv_fwd(x2d, w, bias=None, lengths=None, T=0, stats=None, out=None, ldy=None):
     """y[M, Cout] = x[M, Cin] w[Cout, Cin]^T (+bias), MaskCNN row mask; `stats` (double [2, Cout], zeroed) receives the
     BatchNorm batch sums.  x2d may be [N, T, Cin]; w [Cout, Cin(, 1)] in x's dtype.  Output row pitch ldy >= Cout."""
