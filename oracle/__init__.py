@@ -4,7 +4,7 @@ This package is a CPU restatement (plain PyTorch fp32/fp64 + numpy) of the refer
 algorithm for the path BASELINE.json's north_star names: log-mel frontend -> QuartzNet-style
 encoder (3 variants) -> log-softmax -> CTC loss / greedy CTC decode.
 
-Rules (enforced by tests/test_layout_rules.py):
+Rules (enforced by tests/test_host_cpu.py::test_no_cpu_fallback_and_no_oracle_in_product):
   * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
     legs may import anything from here;
   * the product package (lightning_asr_b200) never imports it and has no CPU fallback.
