@@ -100,19 +100,35 @@ se_bn_bwd_finalize_kernel(const float* __restrict__ partials, int N, int chunks,
                           const float* __restrict__ sums_y, const float* __restrict__ gamma,
                           const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ dgamma,
                           float* __restrict__ dbeta, float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  // blockDim = (32 channels, 8 utterance lanes): the per-utterance terms are independent, so 8 lanes walk the batch in
+  // parallel (a single thread per channel chained 5 dependent-latency loads x N utterances: ~60 us at N = 64) and a
+  // shared-memory reduction folds them
+  __shared__ double red_a[8][33], red_b[8][33];
+  const int cl = threadIdx.x & 31, nl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
   double a = 0.0, b = 0.0;
-  for (int n = 0; n < N; ++n) {
-    double sg = 0.0, sgy = 0.0;
-    for (int k = 0; k < chunks; ++k) {
-      const float* p = partials + static_cast<size_t>(n * chunks + k) * 3 * C;
-      sg += p[c];
-      sgy += p[C + c];
+  if (c < C) {
+#pragma unroll 2
+    for (int n = nl; n < N; n += 8) {
+      double sg = 0.0, sgy = 0.0;
+      for (int k = 0; k < chunks; ++k) {
+        const float* p = partials + static_cast<size_t>(n * chunks + k) * 3 * C;
+        sg += p[c];
+        sgy += p[C + c];
+      }
+      const double gt = gate[static_cast<size_t>(n) * C + c], ex = extra[static_cast<size_t>(n) * C + c];
+      a += gt * sg + ex * T_len;
+      b += gt * sgy + ex * sums_y[static_cast<size_t>(n) * C + c];
     }
-    const double gt = gate[static_cast<size_t>(n) * C + c], ex = extra[static_cast<size_t>(n) * C + c];
-    a += gt * sg + ex * T_len;
-    b += gt * sgy + ex * sums_y[static_cast<size_t>(n) * C + c];
+  }
+  red_a[nl][cl] = a;
+  red_b[nl][cl] = b;
+  __syncthreads();
+  if (nl != 0 || c >= C) return;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) {
+    a += red_a[i][cl];
+    b += red_b[i][cl];
   }
   const double mu = mean[c], is = invstd[c], ga = gamma[c];
   const double dga = is * (b - mu * a);
@@ -158,7 +174,7 @@ int lasr_se_bn_bwd_finalize(const float* partials, int N, int chunks, int C, int
                             const float* extra, const float* sums_y, const float* gamma, const float* mean,
                             const float* invstd, float* dgamma, float* dbeta, float* coef, lasr_stream_t stream) {
   if (N <= 0 || C <= 0 || T <= 0 || chunks <= 0) return LASR_ERR_BAD_SHAPE;
-  se_bn_bwd_finalize_kernel<<<cdiv(C, 128), 128, 0, stream>>>(partials, N, chunks, C, T,
+  se_bn_bwd_finalize_kernel<<<cdiv(C, 32), 256, 0, stream>>>(partials, N, chunks, C, T,
                                                               static_cast<double>(N) * T, gate, extra, sums_y, gamma,
                                                               mean, invstd, dgamma, dbeta, coef);
   LASR_CHECK_LAUNCH();
