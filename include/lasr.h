@@ -165,6 +165,21 @@ typedef struct lasr_bn_bwd {
   float* dbeta;        /* [C] += (nullable) */
 } lasr_bn_bwd_t;
 
+/* nn.Dropout(p) (models/QuartNet.py:27,38,149) fused into the BatchNorm passes.  HOST struct.  The keep mask is one byte
+ * per element of the [M, C] activation (1 = keep); kept elements are scaled by 1/(1-p).  mode 0: no dropout (or pass
+ * NULL); mode 1: the forward READS `mask` (a mask supplied by the caller: the parity hook, torch's Philox stream cannot
+ * be reproduced); mode 2: the forward GENERATES the mask with Philox4x32-10 keyed by (seed, element index / 8) and
+ * WRITES it to `mask`.  The backward passes always read `mask`.  Dropout acts on the normalised branch
+ * BN1(y) [* gate] before the residual add and the final ReLU, exactly where SeprationConv.forward applies it. */
+typedef struct lasr_dropout {
+  uint8_t* mask; /* [M, C] bytes */
+  int mode;
+  float p;
+  uint64_t seed;
+  const uint64_t* seed_dev; /* nullable DEVICE pointer: a per-step counter added to `seed` inside the kernel, so that a
+                               replayed CUDA graph (whose kernel arguments are frozen) draws a fresh mask every step */
+} lasr_dropout_t;
+
 /* scale = gamma*invstd, shift = beta - mean*scale ([C] each) from the descriptor; side_effects != 0 also performs the
  * training side effects (save_mean/save_invstd, running statistics, num_batches_tracked).  count = N*T rows. */
 int lasr_bn_coeffs(const lasr_bn_t* bn, int C, int count, float eps, float momentum, float* scale, float* shift,
@@ -172,23 +187,25 @@ int lasr_bn_coeffs(const lasr_bn_t* bn, int C, int count, float eps, float momen
 /* sums[n, c] = sum_t y[n, t, c] over ALL T frames (SE squeeze numerator, models/QuartNetContextSE.py:11,21) */
 int lasr_sum_over_time(const void* y, float* sums, int N, int T, int C, int dtype, lasr_stream_t stream);
 
-/* out = act( BN1(y) [* gate[n,c]] [+ BN2(r)] );  y, r, out [M, C]; gate [M/T, C] nullable; r / bn2 nullable together.
- * One pass; side_effects != 0 performs the training side effects of bn1 and bn2 exactly once. */
+/* out = act( BN1(y) [* gate[n,c]] [* dropout] [+ BN2(r)] );  y, r, out [M, C]; gate [M/T, C] nullable; r / bn2 nullable
+ * together; drop nullable.  One pass; side_effects != 0 performs the training side effects of bn1 and bn2 exactly once. */
 int lasr_bn_apply_act_fwd(const void* y, const lasr_bn_t* bn1, const void* r, const lasr_bn_t* bn2, const float* gate,
                           void* out, int M, int C, int T, int count, float eps, float momentum, int act,
-                          int side_effects, int dtype, lasr_stream_t stream);
+                          int side_effects, const lasr_dropout_t* drop, int dtype, lasr_stream_t stream);
 
-/* backward pass 1.  With g = dout * (act == RELU ? out > 0 : 1):
- *   totals[0][c] += sum g, totals[1][c] += sum g*y, totals[2][c] += sum g*r      double [3, C], caller zeroes
- *   per_n[n][0][c] += sum_t g, per_n[n][1][c] += sum_t g*y                        float [N, 3, C], nullable (SE) */
+/* backward pass 1.  With g = dout * (act == RELU ? out > 0 : 1) and g1 = g * dropout factor (= g without dropout):
+ *   totals[0][c] += sum g, totals[1][c] += sum g1*y, totals[2][c] += sum g*r     double [3, C], caller zeroes
+ *   totals[3][c] += sum g1                                                        (only with dropout: double [4, C])
+ *   per_n[n][0][c] += sum_t g1, per_n[n][1][c] += sum_t g1*y                      float [N, 3, C], nullable (SE) */
 int lasr_bn_bwd_chunks(int N, int T);
 int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, const void* r, double* totals,
-                           float* per_n, int N, int T, int C, int act, int dtype, lasr_stream_t stream);
+                           float* per_n, int N, int T, int C, int act, const lasr_dropout_t* drop, int dtype,
+                           lasr_stream_t stream);
 /* standalone: coef [3, C] with d(BN input) = coef[0]*g + coef[1]*x + coef[2], from totals slots (0, slot_gx);
  * dgamma / dbeta += (nullable) */
 int lasr_bn_bwd_coef(const double* totals, int C, int count, int slot_gx, const float* gamma, const float* mean,
                      const float* invstd, float* dgamma, float* dbeta, float* coef, lasr_stream_t stream);
-/* pass 2: dy = mask_t<len( c1[0]*(g*gate[n,c] + extra[n,c]) + c1[1]*y + c1[2] ),  dr = c2[0]*g + c2[1]*r + c2[2]
+/* pass 2: dy = mask_t<len( c1[0]*(g1*gate[n,c] + extra[n,c]) + c1[1]*y + c1[2] ),  dr = c2[0]*g + c2[1]*r + c2[2]
  * c1 / c2 are folded from `totals` and bn1 / bn2 in the prologue (dgamma / dbeta accumulated once), unless coef1 is
  * given (the gated SE branch).  gate/extra nullable together; r/dr/bn2 nullable together; lengths nullable = no
  * MaskCNN.  The mask zeroes the gradient that reaches the pointwise conv at padded frames exactly like
@@ -196,7 +213,7 @@ int lasr_bn_bwd_coef(const double* totals, int C, int count, int slot_gx, const 
 int lasr_bn_act_bwd_apply(const void* dout, const void* out, const void* y, const void* r, const float* gate,
                           const float* extra, const double* totals, const float* coef1, const lasr_bn_bwd_t* bn1,
                           const lasr_bn_bwd_t* bn2, int count, const int32_t* lengths, int T, void* dy, void* dr,
-                          int M, int C, int act, int dtype, lasr_stream_t stream);
+                          int M, int C, int act, const lasr_dropout_t* drop, int dtype, lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Squeeze-excitation (models/QuartNetContextSE.py:8-23): gate[n,:] = sigmoid(W2 * relu(W1 * s[n,:])),

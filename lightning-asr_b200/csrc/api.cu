@@ -117,7 +117,7 @@ const char* lasr_strerror(int code) {
   }
 }
 
-int lasr_abi_version(void) { return 1; }
+int lasr_abi_version(void) { return 2; }
 
 int lasr_set_early_param_loads(int on) { return g_early_params.exchange(on != 0 ? 1 : 0); }
 

@@ -61,6 +61,51 @@ __device__ __forceinline__ void load8f(const float* p, float (&v)[8]) { Vec8<flo
 __device__ __forceinline__ void lds8(const float* p, float (&v)[8]) { Vec8<float>::load(p, v); }
 
 // ------------------------------------------------------------------------------------------------
+// Dropout (nn.Dropout(p=drop_rate), models/QuartNet.py:27,38,149) fused into the passes.  The keep mask is one byte per
+// element ([M, C], 1 = keep); the forward pass either READS it (mode 1: a mask supplied by the caller, the parity hook of
+// SURVEY.md 7.2-8) or GENERATES it with Philox4x32-10 keyed by (seed, vector index) and WRITES it (mode 2) for the
+// backward passes.  Kept elements are scaled by 1/(1-p) like torch.
+// ------------------------------------------------------------------------------------------------
+struct DropArgs {
+  uint8_t* mask;
+  int mode;  // 0 off, 1 read, 2 generate + write
+  float scale;
+  uint32_t thresh;  // keep iff 16-bit uniform >= thresh  (thresh = round(p * 65536))
+  unsigned long long seed;
+  const unsigned long long* seed_dev;  // nullable: a device-resident step counter added to the seed (CUDA-graph replays
+                                       // must not repeat the mask, and kernel arguments are frozen at capture)
+};
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+// the 8 keep bytes of vector v (8 consecutive channels of one row)
+__device__ __forceinline__ uint2 drop_generate(const DropArgs& d, long long v) {
+  const unsigned long long seed = d.seed + (d.seed_dev != nullptr ? __ldg(d.seed_dev) : 0ull);
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(v), static_cast<uint32_t>(v >> 32), 0u, 0u),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t k[2] = {0u, 0u};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t u16 = (w[i >> 1] >> (16 * (i & 1))) & 0xffffu;
+    k[i >> 2] |= (u16 >= d.thresh ? 1u : 0u) << (8 * (i & 3));
+  }
+  return make_uint2(k[0], k[1]);
+}
+__device__ __forceinline__ void drop_factors(const uint2 m, float scale, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] = (((i < 4 ? m.x : m.y) >> (8 * (i & 3))) & 0xffu) ? scale : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
 // BatchNorm coefficients.  The pointwise-GEMM epilogue leaves the batch sum / sum of squares of every channel in a
 // double [2, C] buffer (RED.f64); there is NO separate finalize launch: every CTA of the apply pass folds them into
 // scale = gamma * invstd, shift = beta - mean * scale in its prologue (C <= 1024 channels, a few hundred ns), and
@@ -142,11 +187,11 @@ __global__ void bn_coeffs_kernel(const lasr_bn_t bn, int C, double count, float 
 // forward apply: out = act( (scale1*y + shift1) [* gate[n,c]] [+ scale2*r + shift2] )
 // persistent CTAs of 512 threads; smem: scale1, shift1, scale2, shift2 [C] each
 // ------------------------------------------------------------------------------------------------
-template <typename T, bool HAS_R, bool HAS_GATE>
+template <typename T, bool HAS_R, bool HAS_GATE, bool HAS_DROP>
 __global__ void __launch_bounds__(512, 2)
 bn_apply_fwd_kernel(const T* __restrict__ y, const lasr_bn_t bn1, const T* __restrict__ r, const lasr_bn_t bn2,
                     const float* __restrict__ gate, T* __restrict__ out, long long total_vec, int CV, int C, int T_len,
-                    double count, float eps, float momentum, int act, int side_effects) {
+                    double count, float eps, float momentum, int act, int side_effects, const DropArgs drop) {
   pdl_launch_dependents();
   pdl_wait();  // the statistics come from the GEMM right before this pass
   extern __shared__ float coef_s[];  // [4][C]
@@ -178,12 +223,16 @@ bn_apply_fwd_kernel(const T* __restrict__ y, const lasr_bn_t bn1, const T* __res
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long v0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v0 < total_vec; v0 += U * stride) {
     Raw ya[U], ra[U];
+    uint2 ma[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long v = v0 + u * stride;
       if (v < total_vec) {
         ya[u] = Vec8<T>::ldraw(y + v * 8);  // element offset row*C + c == 8*v
         if constexpr (HAS_R) ra[u] = Vec8<T>::ldraw(r + v * 8);
+        if constexpr (HAS_DROP) {
+          if (drop.mode == 1) ma[u] = *reinterpret_cast<const uint2*>(drop.mask + v * 8);
+        }
       }
     }
 #pragma unroll
@@ -207,6 +256,18 @@ bn_apply_fwd_kernel(const T* __restrict__ y, const lasr_bn_t bn1, const T* __res
         load8f(gate + static_cast<size_t>(n) * C + c, g);
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] *= g[i];
+      }
+      if constexpr (HAS_DROP) {
+        // dropout sits after BN [/ SE / ReLU] and BEFORE the residual add (models/QuartNet.py:38,76); without a
+        // residual relu(x)*m == relu(x*m) because m >= 0
+        if (drop.mode == 2) {
+          ma[u] = drop_generate(drop, v);
+          *reinterpret_cast<uint2*>(drop.mask + v * 8) = ma[u];
+        }
+        float f[8];
+        drop_factors(ma[u], drop.scale, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] *= f[i];
       }
       if constexpr (HAS_R) {
         float rr[8], sc[8], sh[8];
@@ -261,23 +322,24 @@ __device__ __forceinline__ void red_add_f64(double* addr, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
 
-template <typename T, bool HAS_R>
+template <typename T, bool HAS_R, bool HAS_DROP>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, const T* __restrict__ y,
                      const T* __restrict__ r, double* __restrict__ totals, float* __restrict__ per_n, int T_len, int C,
-                     int chunks, int rows_per_chunk, int act) {
+                     int chunks, int rows_per_chunk, int act, const uint8_t* __restrict__ drop_mask, float drop_scale) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ float red[];  // [rows_par][3][C]
+  constexpr int NS = HAS_DROP ? 4 : 3;  // slots: sum g, sum g1*y, sum g*r [, sum g1]; g1 = g * dropout factor
+  extern __shared__ float red[];  // [rows_par][NS][C]
   const int n = blockIdx.x / chunks, k = blockIdx.x - n * chunks;
   const int CV = C / 8;
   const int rows_par = 256 / CV;
   const int tr = threadIdx.x / CV, cv = threadIdx.x - tr * CV;
   const int t0 = k * rows_per_chunk;
   const int t1 = min(T_len, t0 + rows_per_chunk);
-  float sg[8], sgy[8], sgr[8];
+  float sg[8], sgy[8], sgr[8], sg1[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) sg[i] = sgy[i] = sgr[i] = 0.f;
+  for (int i = 0; i < 8; ++i) sg[i] = sgy[i] = sgr[i] = sg1[i] = 0.f;
   if (tr < rows_par) {
     using Raw = typename Vec8<T>::Raw;
     constexpr int U = sizeof(T) == 2 ? 2 : 1;  // rows per trip: up to 8 independent 16-byte loads in flight per thread
@@ -285,9 +347,11 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
     const T* base_y = y + static_cast<size_t>(n) * T_len * C + cv * 8;
     const T* base_o = out + static_cast<size_t>(n) * T_len * C + cv * 8;
     const T* base_r = HAS_R ? r + static_cast<size_t>(n) * T_len * C + cv * 8 : nullptr;
+    const uint8_t* base_m = HAS_DROP ? drop_mask + static_cast<size_t>(n) * T_len * C + cv * 8 : nullptr;
     const bool relu = act == LASR_ACT_RELU;
     for (int tt = t0 + tr; tt < t1; tt += U * rows_par) {
       Raw gr[U], yr[U], orr[U], rrr[U];
+      uint2 mr[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int t = tt + u * rows_par;
@@ -297,6 +361,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
           yr[u] = Vec8<T>::ldraw(base_y + off);
           if (relu) orr[u] = Vec8<T>::ldraw(base_o + off);
           if constexpr (HAS_R) rrr[u] = Vec8<T>::ldraw(base_r + off);
+          if constexpr (HAS_DROP) mr[u] = *reinterpret_cast<const uint2*>(base_m + off);
         }
       }
 #pragma unroll
@@ -311,10 +376,23 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
 #pragma unroll
           for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
         }
+        if constexpr (HAS_DROP) {
+          // the gated / normalised branch sees g1 = g * m / (1-p); the residual branch sees g
+          float f[8];
+          drop_factors(mr[u], drop_scale, f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          sg[i] += g[i];
-          sgy[i] = fmaf(g[i], yy[i], sgy[i]);
+          for (int i = 0; i < 8; ++i) {
+            const float g1 = g[i] * f[i];
+            sg[i] += g[i];
+            sg1[i] += g1;
+            sgy[i] = fmaf(g1, yy[i], sgy[i]);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            sg[i] += g[i];
+            sgy[i] = fmaf(g[i], yy[i], sgy[i]);
+          }
         }
         if constexpr (HAS_R) {
           Vec8<T>::unpack(rrr[u], rr);
@@ -323,21 +401,30 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
         }
       }
     }
-    float* dst = red + static_cast<size_t>(tr) * 3 * C + cv * 8;
+    float* dst = red + static_cast<size_t>(tr) * NS * C + cv * 8;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       dst[i] = sg[i];
       dst[C + i] = sgy[i];
       dst[2 * C + i] = sgr[i];
+      if constexpr (HAS_DROP) dst[3 * C + i] = sg1[i];
     }
   }
   __syncthreads();
-  const int nred = HAS_R ? 3 * C : 2 * C;
+  const int nred = HAS_DROP ? 4 * C : (HAS_R ? 3 * C : 2 * C);
   for (int i = threadIdx.x; i < nred; i += 256) {
     float s = 0.f;
-    for (int j = 0; j < rows_par; ++j) s += red[static_cast<size_t>(j) * 3 * C + i];
+    for (int j = 0; j < rows_par; ++j) s += red[static_cast<size_t>(j) * NS * C + i];
     red_add_f64(totals + i, static_cast<double>(s));
-    if (per_n != nullptr && i < 2 * C) atomicAdd(per_n + static_cast<size_t>(n) * 3 * C + i, s);
+    if (per_n != nullptr) {
+      // the SE branch's per-utterance sums are those of its own upstream gradient g1: slot 0 <- sum g1, slot 1 <- sum g1*y
+      if constexpr (HAS_DROP) {
+        if (i >= 3 * C) atomicAdd(per_n + static_cast<size_t>(n) * 3 * C + (i - 3 * C), s);
+        else if (i >= C && i < 2 * C) atomicAdd(per_n + static_cast<size_t>(n) * 3 * C + i, s);
+      } else {
+        if (i < 2 * C) atomicAdd(per_n + static_cast<size_t>(n) * 3 * C + i, s);
+      }
+    }
   }
 }
 
@@ -384,13 +471,14 @@ struct BnBwdSide {
   float* dbeta;
 };
 
-template <typename T, bool HAS_R, bool HAS_GATE>
+template <typename T, bool HAS_R, bool HAS_GATE, bool HAS_DROP>
 __global__ void __launch_bounds__(512, 2)
 bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const T* __restrict__ y,
                     const T* __restrict__ r, const float* __restrict__ gate, const float* __restrict__ extra,
                     const double* __restrict__ totals, const float* __restrict__ coef1_in, const BnBwdSide bn1,
                     const BnBwdSide bn2, double count, const int32_t* __restrict__ lengths, int T_len,
-                    T* __restrict__ dy, T* __restrict__ dr, long long total_vec, int CV, int C, int act) {
+                    T* __restrict__ dy, T* __restrict__ dr, long long total_vec, int CV, int C, int act,
+                    const uint8_t* __restrict__ drop_mask, float drop_scale) {
   pdl_launch_dependents();
   pdl_wait();  // totals come from the reduce pass right before
   extern __shared__ float coef_s[];  // coef1 [3][C], coef2 [3][C]
@@ -399,9 +487,12 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float c0, c1, c2, dg, db;
     // all global loads of this channel first: one round trip instead of one per BatchNorm
-    double t_a = 0.0, t_b1 = 0.0, t_b2 = 0.0;
+    double t_a = 0.0, t_a1 = 0.0, t_b1 = 0.0, t_b2 = 0.0;
     float g1 = 0.f, m1 = 0.f, i1 = 0.f, g2 = 0.f, m2 = 0.f, i2 = 0.f;
-    if (totals != nullptr) t_a = totals[c];
+    if (totals != nullptr) {
+      t_a = totals[c];
+      t_a1 = HAS_DROP ? totals[3 * C + c] : t_a;  // sum of the normalised branch's own upstream gradient
+    }
     if (coef1_in == nullptr) {
       t_b1 = totals[C + c];
       g1 = bn1.gamma[c];
@@ -419,7 +510,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
       k1[C + c] = coef1_in[C + c];
       k1[2 * C + c] = coef1_in[2 * C + c];
     } else {
-      bn_bwd_coef(t_a, t_b1, count, g1, m1, i1, c0, c1, c2, dg, db);
+      bn_bwd_coef(t_a1, t_b1, count, g1, m1, i1, c0, c1, c2, dg, db);
       k1[c] = c0;
       k1[C + c] = c1;
       k1[2 * C + c] = c2;
@@ -446,6 +537,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long v0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v0 < total_vec; v0 += U * stride) {
     Raw gr[U], orr[U], yr[U], rrr[U];
+    uint2 mr[U];
     bool keep_u[U];
     int n_u[U], c_u[U];
 #pragma unroll
@@ -462,6 +554,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
         if (relu) orr[u] = Vec8<T>::ldraw(out + v * 8);
         if constexpr (HAS_R) rrr[u] = Vec8<T>::ldraw(r + v * 8);
         if (keep_u[u]) yr[u] = Vec8<T>::ldraw(y + v * 8);
+        if constexpr (HAS_DROP) mr[u] = *reinterpret_cast<const uint2*>(drop_mask + v * 8);
       }
     }
 #pragma unroll
@@ -492,6 +585,12 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
       if (keep) {
         float yy[8];
         Vec8<T>::unpack(yr[u], yy);
+        if constexpr (HAS_DROP) {
+          float f[8];
+          drop_factors(mr[u], drop_scale, f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] *= f[i];
+        }
         if constexpr (HAS_GATE) {
           float gt[8], ex[8];
           load8f(gate + static_cast<size_t>(n) * C + c, gt);
@@ -523,22 +622,28 @@ static inline int persistent_grid(long long total_vec, int threads) {
 template <typename TT>
 static int bn_fwd_launch(const void* y, const lasr_bn_t& b1, const void* r, const lasr_bn_t& b2, const float* gate,
                          void* out, long long total, int CV, int C, int T, double count, float eps, float momentum,
-                         int act, int side_effects, cudaStream_t stream) {
+                         int act, int side_effects, const DropArgs& drop, cudaStream_t stream) {
   const int grid = persistent_grid(total, 512);
   const int smem = 4 * C * static_cast<int>(sizeof(float));
   const TT* yy = static_cast<const TT*>(y);
   const TT* rr = static_cast<const TT*>(r);
   TT* oo = static_cast<TT*>(out);
-#define LASR_BN_FWD_ARGS yy, b1, rr, b2, gate, oo, total, CV, C, T, count, eps, momentum, act, side_effects
   cudaError_t le;
-  if (r != nullptr && gate != nullptr)
-    le = launch_pdl(4, bn_apply_fwd_kernel<TT, true, true>, dim3(grid), dim3(512), smem, stream, LASR_BN_FWD_ARGS);
-  else if (r != nullptr)
-    le = launch_pdl(4, bn_apply_fwd_kernel<TT, true, false>, dim3(grid), dim3(512), smem, stream, LASR_BN_FWD_ARGS);
-  else if (gate != nullptr)
-    le = launch_pdl(4, bn_apply_fwd_kernel<TT, false, true>, dim3(grid), dim3(512), smem, stream, LASR_BN_FWD_ARGS);
-  else
-    le = launch_pdl(4, bn_apply_fwd_kernel<TT, false, false>, dim3(grid), dim3(512), smem, stream, LASR_BN_FWD_ARGS);
+#define LASR_BN_FWD(R, G, D)                                                                                      \
+  le = launch_pdl(4, bn_apply_fwd_kernel<TT, R, G, D>, dim3(grid), dim3(512), smem, stream, yy, b1, rr, b2, gate, oo, \
+                  total, CV, C, T, count, eps, momentum, act, side_effects, drop)
+  const int sel = (r != nullptr ? 4 : 0) | (gate != nullptr ? 2 : 0) | (drop.mode != 0 ? 1 : 0);
+  switch (sel) {
+    case 0: LASR_BN_FWD(false, false, false); break;
+    case 1: LASR_BN_FWD(false, false, true); break;
+    case 2: LASR_BN_FWD(false, true, false); break;
+    case 3: LASR_BN_FWD(false, true, true); break;
+    case 4: LASR_BN_FWD(true, false, false); break;
+    case 5: LASR_BN_FWD(true, false, true); break;
+    case 6: LASR_BN_FWD(true, true, false); break;
+    default: LASR_BN_FWD(true, true, true); break;
+  }
+#undef LASR_BN_FWD
   LASR_CHECK_PDL(le);
   return LASR_OK;
 }
@@ -547,7 +652,8 @@ template <typename TT>
 static int bn_bwd_launch(const void* dout, const void* out, const void* y, const void* r, const float* gate,
                          const float* extra, const double* totals, const float* coef1, const BnBwdSide& s1,
                          const BnBwdSide& s2, double count, const int32_t* lengths, int T, void* dy, void* dr,
-                         long long total, int CV, int C, int act, cudaStream_t stream) {
+                         long long total, int CV, int C, int act, const uint8_t* drop_mask, float drop_scale,
+                         cudaStream_t stream) {
   const int grid = persistent_grid(total, 512);
   const int smem = 6 * C * static_cast<int>(sizeof(float));
   const TT* a0 = static_cast<const TT*>(dout);
@@ -556,17 +662,37 @@ static int bn_bwd_launch(const void* dout, const void* out, const void* y, const
   const TT* a3 = static_cast<const TT*>(r);
   TT* o0 = static_cast<TT*>(dy);
   TT* o1 = static_cast<TT*>(dr);
-#define LASR_BN_BWD_ARGS a0, a1, a2, a3, gate, extra, totals, coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, act
   cudaError_t le;
-  if (r != nullptr && gate != nullptr)
-    le = launch_pdl(4, bn_bwd_apply_kernel<TT, true, true>, dim3(grid), dim3(512), smem, stream, LASR_BN_BWD_ARGS);
-  else if (r != nullptr)
-    le = launch_pdl(4, bn_bwd_apply_kernel<TT, true, false>, dim3(grid), dim3(512), smem, stream, LASR_BN_BWD_ARGS);
-  else if (gate != nullptr)
-    le = launch_pdl(4, bn_bwd_apply_kernel<TT, false, true>, dim3(grid), dim3(512), smem, stream, LASR_BN_BWD_ARGS);
-  else
-    le = launch_pdl(4, bn_bwd_apply_kernel<TT, false, false>, dim3(grid), dim3(512), smem, stream, LASR_BN_BWD_ARGS);
+#define LASR_BN_BWD(R, G, D)                                                                                       \
+  le = launch_pdl(4, bn_bwd_apply_kernel<TT, R, G, D>, dim3(grid), dim3(512), smem, stream, a0, a1, a2, a3, gate,   \
+                  extra, totals, coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, act, drop_mask, drop_scale)
+  const int sel = (r != nullptr ? 4 : 0) | (gate != nullptr ? 2 : 0) | (drop_mask != nullptr ? 1 : 0);
+  switch (sel) {
+    case 0: LASR_BN_BWD(false, false, false); break;
+    case 1: LASR_BN_BWD(false, false, true); break;
+    case 2: LASR_BN_BWD(false, true, false); break;
+    case 3: LASR_BN_BWD(false, true, true); break;
+    case 4: LASR_BN_BWD(true, false, false); break;
+    case 5: LASR_BN_BWD(true, false, true); break;
+    case 6: LASR_BN_BWD(true, true, false); break;
+    default: LASR_BN_BWD(true, true, true); break;
+  }
+#undef LASR_BN_BWD
   LASR_CHECK_PDL(le);
+  return LASR_OK;
+}
+
+// host view of lasr_dropout_t
+static int drop_args(const lasr_dropout_t* d, DropArgs& a) {
+  a = DropArgs{};
+  if (d == nullptr || d->mode == 0 || d->p <= 0.f) return LASR_OK;
+  if (d->mask == nullptr || d->p >= 1.f || d->mode < 0 || d->mode > 2) return LASR_ERR_BAD_SHAPE;
+  a.mask = d->mask;
+  a.mode = d->mode;
+  a.scale = 1.f / (1.f - d->p);
+  a.thresh = static_cast<uint32_t>(d->p * 65536.f + 0.5f);
+  a.seed = d->seed;
+  a.seed_dev = reinterpret_cast<const unsigned long long*>(d->seed_dev);
   return LASR_OK;
 }
 
@@ -610,8 +736,10 @@ int lasr_sum_over_time(const void* y, float* sums, int N, int T, int C, int dtyp
 
 int lasr_bn_apply_act_fwd(const void* y, const lasr_bn_t* bn1, const void* r, const lasr_bn_t* bn2, const float* gate,
                           void* out, int M, int C, int T, int count, float eps, float momentum, int act,
-                          int side_effects, int dtype, lasr_stream_t stream) {
+                          int side_effects, const lasr_dropout_t* drop, int dtype, lasr_stream_t stream) {
   if (M <= 0 || C <= 0 || (C % 8) || C > 2048 || count <= 0 || bn1 == nullptr) return LASR_ERR_BAD_SHAPE;
+  DropArgs da;
+  if (int rc = drop_args(drop, da)) return rc;
   if ((r != nullptr) != (bn2 != nullptr)) return LASR_ERR_BAD_SHAPE;
   if (gate != nullptr && T <= 0) return LASR_ERR_BAD_SHAPE;
   const int CV = C / 8;
@@ -620,10 +748,10 @@ int lasr_bn_apply_act_fwd(const void* y, const lasr_bn_t* bn1, const void* r, co
   const lasr_bn_t& b2 = bn2 ? *bn2 : none;
   if (dtype == LASR_F32)
     return bn_fwd_launch<float>(y, *bn1, r, b2, gate, out, total, CV, C, T, count, eps, momentum, act, side_effects,
-                                stream);
+                                da, stream);
   if (dtype == LASR_BF16)
     return bn_fwd_launch<__nv_bfloat16>(y, *bn1, r, b2, gate, out, total, CV, C, T, count, eps, momentum, act,
-                                        side_effects, stream);
+                                        side_effects, da, stream);
   return LASR_ERR_BAD_DTYPE;
 }
 
@@ -637,8 +765,13 @@ int lasr_bn_bwd_chunks(int N, int T) {
 }
 
 int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, const void* r, double* totals,
-                           float* per_n, int N, int T, int C, int act, int dtype, lasr_stream_t stream) {
+                           float* per_n, int N, int T, int C, int act, const lasr_dropout_t* drop, int dtype,
+                           lasr_stream_t stream) {
   if (N <= 0 || T <= 0 || C <= 0 || (C % 8) || C > 2048 || totals == nullptr) return LASR_ERR_BAD_SHAPE;
+  DropArgs da;
+  if (int rc = drop_args(drop, da)) return rc;
+  const uint8_t* dmask = da.mode ? da.mask : nullptr;
+  const float dscale = da.scale;
   // Without per-utterance sums (no SE) the rows are one flat [N*T, C] matrix: two fat CTAs per SM instead of 4 thin
   // ones per SM and utterance halve the fp64 REDs that all land on the same 3*C addresses.
   if (per_n == nullptr) {
@@ -658,19 +791,19 @@ int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, con
   const int rows_per_chunk = cdiv(T, chunks);
   const int CV = C / 8;
   const int rows_par = 256 / CV;
-  const int smem = rows_par * 3 * C * static_cast<int>(sizeof(float));
+  const int smem = rows_par * (dmask ? 4 : 3) * C * static_cast<int>(sizeof(float));
   const int grid = N * chunks;
   cudaError_t le = cudaSuccess;
+#define LASR_BN_RED_ONE(TT, R, D)                                                                                  \
+  le = launch_pdl(4, bn_bwd_reduce_kernel<TT, R, D>, dim3(grid), dim3(256), smem, stream,                          \
+                  static_cast<const TT*>(dout), static_cast<const TT*>(out), static_cast<const TT*>(y),            \
+                  static_cast<const TT*>(r), totals, per_n, T, C, chunks, rows_per_chunk, act, dmask, dscale)
 #define LASR_BN_RED_LAUNCH(TT)                                                                                     \
   do {                                                                                                             \
-    if (r != nullptr)                                                                                              \
-      le = launch_pdl(4, bn_bwd_reduce_kernel<TT, true>, dim3(grid), dim3(256), smem, stream,                         \
-                      static_cast<const TT*>(dout), static_cast<const TT*>(out), static_cast<const TT*>(y),        \
-                      static_cast<const TT*>(r), totals, per_n, T, C, chunks, rows_per_chunk, act);                \
-    else                                                                                                           \
-      le = launch_pdl(4, bn_bwd_reduce_kernel<TT, false>, dim3(grid), dim3(256), smem, stream,                        \
-                      static_cast<const TT*>(dout), static_cast<const TT*>(out), static_cast<const TT*>(y),        \
-                      static_cast<const TT*>(r), totals, per_n, T, C, chunks, rows_per_chunk, act);                \
+    if (r != nullptr && dmask != nullptr) LASR_BN_RED_ONE(TT, true, true);                                         \
+    else if (r != nullptr) LASR_BN_RED_ONE(TT, true, false);                                                       \
+    else if (dmask != nullptr) LASR_BN_RED_ONE(TT, false, true);                                                   \
+    else LASR_BN_RED_ONE(TT, false, false);                                                                        \
   } while (0)
   if (dtype == LASR_F32)
     LASR_BN_RED_LAUNCH(float);
@@ -694,8 +827,11 @@ int lasr_bn_bwd_coef(const double* totals, int C, int count, int slot_gx, const 
 int lasr_bn_act_bwd_apply(const void* dout, const void* out, const void* y, const void* r, const float* gate,
                           const float* extra, const double* totals, const float* coef1, const lasr_bn_bwd_t* bn1,
                           const lasr_bn_bwd_t* bn2, int count, const int32_t* lengths, int T, void* dy, void* dr,
-                          int M, int C, int act, int dtype, lasr_stream_t stream) {
+                          int M, int C, int act, const lasr_dropout_t* drop, int dtype, lasr_stream_t stream) {
   if (M <= 0 || C <= 0 || (C % 8) || C > 2048 || T <= 0 || count <= 0) return LASR_ERR_BAD_SHAPE;
+  DropArgs da;
+  if (int rc = drop_args(drop, da)) return rc;
+  const uint8_t* dmask = da.mode ? da.mask : nullptr;
   if ((r != nullptr) != (dr != nullptr) || (r != nullptr) != (bn2 != nullptr)) return LASR_ERR_BAD_SHAPE;
   if ((gate != nullptr) != (extra != nullptr)) return LASR_ERR_BAD_SHAPE;
   if (coef1 == nullptr && (bn1 == nullptr || totals == nullptr)) return LASR_ERR_BAD_SHAPE;
@@ -707,10 +843,10 @@ int lasr_bn_act_bwd_apply(const void* dout, const void* out, const void* y, cons
   if (bn2) s2 = BnBwdSide{bn2->gamma, bn2->mean, bn2->invstd, bn2->dgamma, bn2->dbeta};
   if (dtype == LASR_F32)
     return bn_bwd_launch<float>(dout, out, y, r, gate, extra, totals, coef1, s1, s2, count, lengths, T, dy, dr, total,
-                                CV, C, act, stream);
+                                CV, C, act, dmask, da.scale, stream);
   if (dtype == LASR_BF16)
     return bn_bwd_launch<__nv_bfloat16>(dout, out, y, r, gate, extra, totals, coef1, s1, s2, count, lengths, T, dy,
-                                        dr, total, CV, C, act, stream);
+                                        dr, total, CV, C, act, dmask, da.scale, stream);
   return LASR_ERR_BAD_DTYPE;
 }
 

@@ -321,11 +321,13 @@ ctc_grad_kernel(const T* __restrict__ x, const float* __restrict__ lse, const in
   const int t = static_cast<int>(row - static_cast<long long>(n) * T_len);
   GT* gr = grad + static_cast<size_t>(row) * ldg;
   const int Tn = in_len[n];
-  if (t >= Tn) {
+  const int Sn = tgt_len[n];
+  // frames past the utterance, and utterances whose lattice was never built (bad lengths: the lattice kernel returns
+  // early and leaves alpha / beta unwritten), get a zero gradient row
+  if (t >= Tn || Sn < 0 || Sn > S_max) {
     for (int c = lane; c < ldg; c += 32) gr[c] = from_f32<GT>(0.f);
     return;
   }
-  const int Sn = tgt_len[n];
   const int Lp = 2 * Sn + 1;
   const int Lp_max = 2 * S_max + 1;
   const T* xr = x + static_cast<size_t>(row) * ldx;

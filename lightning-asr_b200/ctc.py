@@ -1,4 +1,6 @@
 """torch.nn.CTCLoss-compatible callable backed by the CTC kernels (train.py:196 call contract)."""
+import os
+
 import torch
 
 from .functions import CTCLossFn
@@ -24,7 +26,14 @@ class CTCLoss(torch.nn.Module):
         targets = targets.to(dev).long().contiguous()
         il = torch.as_tensor(input_lengths).to(dev).int().contiguous()
         tl = torch.as_tensor(target_lengths).to(dev).int().contiguous()
-        nll = CTCLossFn.apply(log_probs, targets, il, tl, self.blank)
+        if os.environ.get("LASR_DEBUG", "0") == "1":  # host-side validation costs a device sync: debug runs only
+            bad = (targets < 0) | (targets >= log_probs.shape[-1])
+            valid = torch.arange(targets.shape[1], device=dev)[None, :] < tl[:, None]
+            if bool((bad & valid).any()):
+                raise ValueError("CTCLoss: a target label is outside [0, C)")
+            if bool((tl > targets.shape[1]).any()) or bool((il > log_probs.shape[0]).any()):
+                raise ValueError("CTCLoss: a length exceeds its tensor")
+        nll = CTCLossFn.apply(log_probs, targets, il, tl, self.blank, self.zero_infinity)
         if self.zero_infinity:
             nll = torch.where(torch.isinf(nll), torch.zeros_like(nll), nll)
         if self.reduction == "none":

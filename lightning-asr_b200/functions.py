@@ -24,6 +24,18 @@ def _stats(C, device):
     return runtime.zeros((2, C), torch.float64, device)
 
 
+def _make_drop(drop, shape, device, training):
+    """drop = None | (p, mask_or_None): -> ops.Dropout for the forward pass (None when inactive).
+    A supplied uint8 keep-mask [N, T, C] is applied as is (parity hook); otherwise the forward kernel draws one."""
+    if drop is None or not training or drop[0] <= 0.0:
+        return None
+    p, mask = drop[0], drop[1]
+    if mask is not None:
+        return ops.Dropout(mask.contiguous(), p, "read")
+    seed, seed_dev = runtime.next_dropout_stream()
+    return ops.Dropout(torch.empty(shape, device=device, dtype=torch.uint8), p, "generate", seed, seed_dev)
+
+
 class SepConvBNFn(torch.autograd.Function):
     """y = act( [gate *] BN1(mask(pw(dw(x)))) [+ BN2(res(x))] ).
 
@@ -35,6 +47,8 @@ class SepConvBNFn(torch.autograd.Function):
       se_w1 [Cout/8, Cout], se_w2 [Cout, Cout/8] or None (SELayer.fc.0 / fc.2)
       bn_buffers = (running_mean, running_var, num_batches_tracked) for bn; rbn_buffers likewise
       stride, relu (bool), training (bool)
+      drop = None | (p, keep_mask uint8 [N, T, Cout] or None): nn.Dropout(p) on the normalised branch, fused into the
+             apply pass (before the residual add, models/QuartNet.py:38,76); a supplied mask is the parity hook
     Kernel sequence (training): dwconv -> pw GEMM (+mask, +BN sums) [-> residual GEMM (+BN sums)] [-> SE squeeze /
     excite] -> ONE apply pass.  Backward: reduce -> apply -> pw wgrad, pw dgrad [-> res wgrad, res dgrad] -> dw wgrad,
     dw dgrad (+ residual dgrad fused as addend).
@@ -42,7 +56,7 @@ class SepConvBNFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, res_x, lengths, dw_w, pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2, bn_buffers,
-                rbn_buffers, stride, relu, training):
+                rbn_buffers, stride, relu, training, drop=None):
         dt = x.dtype
         dev = x.device
         N, T_in, Cin = x.shape
@@ -75,24 +89,26 @@ class SepConvBNFn(torch.autograd.Function):
             scale1, shift1 = ops.bn_coeffs(bn1, N * T, BN_EPS, BN_MOMENTUM, side_effects=False)
             sums_y = ops.sum_over_time(y)
             s, hidden, gate = ops.se_excite_fwd(sums_y, scale1, shift1, T, se_w1.detach(), se_w2.detach())
-        out = ops.bn_apply_act(y, bn1, r, bn2, gate, act, BN_EPS, BN_MOMENTUM, side_effects=se_side)
+        dr_ = _make_drop(drop, (N, T, Cout), dev, training)
+        out = ops.bn_apply_act(y, bn1, r, bn2, gate, act, BN_EPS, BN_MOMENTUM, side_effects=se_side, drop=dr_)
 
         # save_for_backward (not attributes): holding `out` on ctx directly would create an uncollectable
         # node <-> tensor cycle and leak every step's activations
         ctx.save_for_backward(x, res_x, lengths, d, y, r, out, bn1.save, bn2.save if bn2 is not None else None, gate, s,
                               hidden, sums_y, scale1, shift1, pw_s, res_s, dw_w, pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b,
-                              se_w1, se_w2)
-        ctx.cfg = (stride, act, training, K, Cin, Cout)
+                              se_w1, se_w2, dr_.mask if dr_ is not None else None)
+        ctx.cfg = (stride, act, training, K, Cin, Cout, dr_.p if dr_ is not None else 0.0)
         ctx.set_materialize_grads(False)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         if dout is None:
-            return (None,) * 17
+            return (None,) * 18
         (x, res_x, lengths, d, y, r, out, save1, save2, gate, s, hidden, sums_y, scale1, shift1, pw_s, res_s, dw_w,
-         pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2) = ctx.saved_tensors
-        stride, act, training, K, Cin, Cout = ctx.cfg
+         pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2, drop_mask) = ctx.saved_tensors
+        stride, act, training, K, Cin, Cout, drop_p = ctx.cfg
+        drop = ops.Dropout(drop_mask, drop_p, "read") if drop_mask is not None else None
         if not training:
             raise RuntimeError("lightning_asr_b200: backward through eval-mode BatchNorm is not implemented")
         dev = x.device
@@ -105,9 +121,9 @@ class SepConvBNFn(torch.autograd.Function):
         if has_res:
             g_rbn_w, ret_rbn_w = runtime.grad_sink(rbn_w)
             g_rbn_b, ret_rbn_b = runtime.grad_sink(rbn_b)
-        totals = runtime.zeros((3, Cout), torch.float64, dev)
+        totals = runtime.zeros((4 if drop is not None else 3, Cout), torch.float64, dev)
         per_n = runtime.zeros((N, 3, Cout), torch.float32, dev) if gate is not None else None
-        ops.bn_act_bwd_reduce(dout, out, y, r, act, totals, per_n)
+        ops.bn_act_bwd_reduce(dout, out, y, r, act, totals, per_n, drop=drop)
         extra = coef1 = None
         ret_se1 = ret_se2 = None
         bn1_side = (bn_w.detach(), save1, g_bn_w, g_bn_b)
@@ -119,7 +135,8 @@ class SepConvBNFn(torch.autograd.Function):
             coef1 = ops.se_bn_bwd_finalize(per_n, N, T, gate, extra, sums_y, bn_w.detach(), save1, g_bn_w, g_bn_b)
             bn1_side = None
         bn2_side = (rbn_w.detach(), save2, g_rbn_w, g_rbn_b) if has_res else None
-        dy, dr = ops.bn_act_bwd_apply(dout, out, y, r, gate, extra, totals, coef1, bn1_side, bn2_side, lengths, act)
+        dy, dr = ops.bn_act_bwd_apply(dout, out, y, r, gate, extra, totals, coef1, bn1_side, bn2_side, lengths, act,
+                                      drop=drop)
         runtime.grad_ready(bn_w, bn_b, rbn_w, rbn_b, se_w1, se_w2)
 
         # pointwise conv: weight gradient (split-K tcgen05 MN-major GEMM) and data gradient (W as MN-major B operand)
@@ -172,7 +189,7 @@ class SepConvBNFn(torch.autograd.Function):
             if need_dx:
                 raise RuntimeError("lightning_asr_b200: data gradient of the stride-2 first conv is not needed/implemented")
         return (dx, d_res_x, None, ret_dw, ret_pw, ret_bn_w, ret_bn_b, ret_res, ret_rbn_w, ret_rbn_b, ret_se1, ret_se2,
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 class Conv1x1BNReLUFn(torch.autograd.Function):
@@ -180,7 +197,7 @@ class Conv1x1BNReLUFn(torch.autograd.Function):
     residual branch conv1x1 -> BN (models/QuartNet.py:62-65) used by the unfused dropout path."""
 
     @staticmethod
-    def forward(ctx, x, w, bn_w, bn_b, bn_buffers, training, relu=True):
+    def forward(ctx, x, w, bn_w, bn_b, bn_buffers, training, relu=True, drop=None):
         dt = x.dtype
         N, T, Cin = x.shape
         Cout = w.shape[0]
@@ -189,27 +206,30 @@ class Conv1x1BNReLUFn(torch.autograd.Function):
         y = ops.pwconv_fwd(x, w_s, stats=sums)
         bn = ops.BNForward(bn_w.detach(), bn_b.detach(), bn_buffers[0], bn_buffers[1], bn_buffers[2], sums)
         act = ACT_RELU if relu else ACT_NONE
-        out = ops.bn_apply_act(y, bn, act=act, eps=BN_EPS, momentum=BN_MOMENTUM)
-        ctx.save_for_backward(x, y, out, bn.save, w_s, w, bn_w, bn_b)
+        dr_ = _make_drop(drop, (N, T, Cout), x.device, training)  # nn.Dropout after the ReLU (models/QuartNet.py:149)
+        out = ops.bn_apply_act(y, bn, act=act, eps=BN_EPS, momentum=BN_MOMENTUM, drop=dr_)
+        ctx.save_for_backward(x, y, out, bn.save, w_s, w, bn_w, bn_b, dr_.mask if dr_ is not None else None)
         ctx.training = training
         ctx.act = act
+        ctx.drop_p = dr_.p if dr_ is not None else 0.0
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        x, y, out, save, w_s, w, bn_w, bn_b = ctx.saved_tensors
+        x, y, out, save, w_s, w, bn_w, bn_b, drop_mask = ctx.saved_tensors
         if not ctx.training:
             raise RuntimeError("lightning_asr_b200: backward through eval-mode BatchNorm is not implemented")
         dout = dout.contiguous()
         N, T, Cin = x.shape
         Cout = w.shape[0]
         act = ctx.act
-        totals = runtime.zeros((3, Cout), torch.float64, x.device)
-        ops.bn_act_bwd_reduce(dout, out, y, None, act, totals)
+        drop = ops.Dropout(drop_mask, ctx.drop_p, "read") if drop_mask is not None else None
+        totals = runtime.zeros((4 if drop is not None else 3, Cout), torch.float64, x.device)
+        ops.bn_act_bwd_reduce(dout, out, y, None, act, totals, drop=drop)
         g_w, ret_w = runtime.grad_sink(bn_w)
         g_b, ret_b = runtime.grad_sink(bn_b)
         dy, _ = ops.bn_act_bwd_apply(dout, out, y, None, None, None, totals, None, (bn_w.detach(), save, g_w, g_b),
-                                     None, None, act)
+                                     None, None, act, drop=drop)
         runtime.grad_ready(bn_w, bn_b)
         g_cw, ret_cw = runtime.grad_sink(w)
 
@@ -218,7 +238,7 @@ class Conv1x1BNReLUFn(torch.autograd.Function):
             runtime.grad_ready(w)
         runtime.defer(_wgrad, dy, x)
         dx = ops.pwconv_dgrad(dy, w_s) if ctx.needs_input_grad[0] else None
-        return dx, ret_cw, ret_w, ret_b, None, None, None
+        return dx, ret_cw, ret_w, ret_b, None, None, None, None
 
 
 def _pad8(v):
@@ -283,7 +303,7 @@ class CTCLossFn(torch.autograd.Function):
     """torch.nn.CTCLoss(blank, reduction='none', zero_infinity=False) on [T, N, V] log-probs -> nll [N]."""
 
     @staticmethod
-    def forward(ctx, log_probs, targets, input_lengths, target_lengths, blank):
+    def forward(ctx, log_probs, targets, input_lengths, target_lengths, blank, zero_infinity=False):
         x = _as_ntv(log_probs)
         if x.dtype not in (torch.float32, torch.bfloat16):
             x = x.float()
@@ -293,6 +313,7 @@ class CTCLossFn(torch.autograd.Function):
         ctx.save_for_backward(x, targets, input_lengths, target_lengths, alpha, beta, nll)
         ctx.blank = blank
         ctx.in_dtype = log_probs.dtype
+        ctx.zero_infinity = zero_infinity
         return nll
 
     @staticmethod
@@ -301,7 +322,11 @@ class CTCLossFn(torch.autograd.Function):
         V = x.shape[-1]
         grad = ops.ctc_bwd(x, None, targets, il, tl, alpha, beta, nll, gout.contiguous().float(), V, ctx.blank, V,
                            torch.float32)
-        return grad.transpose(0, 1).to(ctx.in_dtype), None, None, None, None
+        if ctx.zero_infinity:
+            # torch.nn.CTCLoss(zero_infinity=True) zeroes the gradient of infeasible utterances (their lattice terms
+            # are inf / NaN); the reference's own setting is zero_infinity=False (train.py:196)
+            grad = torch.where(torch.isfinite(nll)[:, None, None], grad, torch.zeros_like(grad))
+        return grad.transpose(0, 1).to(ctx.in_dtype), None, None, None, None, None
 
 
 class FusedDecoderCTCFn(torch.autograd.Function):

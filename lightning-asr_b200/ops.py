@@ -206,6 +206,35 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+class _Drop(ctypes.Structure):
+    _fields_ = [("mask", ctypes.c_void_p), ("mode", ctypes.c_int), ("p", ctypes.c_float), ("seed", ctypes.c_uint64),
+                ("seed_dev", ctypes.c_void_p)]
+
+
+class Dropout:
+    """lasr_dropout_t: nn.Dropout(p) fused into the BatchNorm passes (models/QuartNet.py:27,38,149).
+    mask: uint8 [N, T, C] keep mask (1 = keep).  mode 'read' applies a caller-supplied mask (parity hook); mode
+    'generate' draws it on the device (Philox4x32-10 keyed by `seed`) in the forward pass and stores it in `mask`."""
+
+    def __init__(self, mask, p, mode="read", seed=0, seed_dev=None):
+        if mask.dtype != torch.uint8 or not mask.is_cuda or not mask.is_contiguous():
+            raise _lib.LasrError("dropout mask must be a contiguous CUDA uint8 tensor")
+        if not (0.0 < p < 1.0):
+            raise _lib.LasrError("dropout p must be in (0, 1)")
+        self.mask, self.p = mask, float(p)
+        self.seed_dev = seed_dev  # int64 device scalar (kept alive here)
+        self.c = _Drop(mask.data_ptr(), {"read": 1, "generate": 2}[mode], float(p), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                       _p(seed_dev))
+
+    @property
+    def ptr(self):
+        return ctypes.addressof(self.c)
+
+    def backward_view(self):
+        """The same mask, read-only mode (what the backward passes use)."""
+        return Dropout(self.mask, self.p, "read")
+
+
 class BNForward:
     """lasr_bn_t for one BatchNorm call.  training: `sums` = double [2, C] batch statistics (from the GEMM epilogue),
     save [2, C] receives mean / invstd.  eval: sums None, running statistics are read."""
@@ -239,12 +268,16 @@ def sum_over_time(y):
     return sums
 
 
-def bn_apply_act(y, bn1, r=None, bn2=None, gate=None, act=ACT_RELU, eps=1e-3, momentum=0.1, side_effects=True):
-    """out = act(BN1(y) [* gate] [+ BN2(r)]) in one pass; performs the training side effects of both BNs."""
+def bn_apply_act(y, bn1, r=None, bn2=None, gate=None, act=ACT_RELU, eps=1e-3, momentum=0.1, side_effects=True,
+                 drop=None):
+    """out = act(BN1(y) [* gate] [* dropout] [+ BN2(r)]) in one pass; performs the training side effects of both BNs."""
     N, T, C = y.shape
     out = torch.empty_like(y)
+    if drop is not None and drop.mask.numel() != y.numel():
+        raise _lib.LasrError("dropout mask must have one byte per activation element")
     call("lasr_bn_apply_act_fwd", y, bn1.ptr, r, bn2.ptr if bn2 is not None else None, gate, out, N * T, C, T, N * T,
-         eps, momentum, act, 1 if (side_effects and bn1.training) else 0, dtype_code(y.dtype))
+         eps, momentum, act, 1 if (side_effects and bn1.training) else 0, drop.ptr if drop is not None else None,
+         dtype_code(y.dtype))
     return out
 
 
@@ -252,9 +285,13 @@ def bn_bwd_chunks(N, T):
     return _lib.load().lasr_bn_bwd_chunks(N, T)
 
 
-def bn_act_bwd_reduce(dout, out, y, r, act, totals, per_n=None):
+def bn_act_bwd_reduce(dout, out, y, r, act, totals, per_n=None, drop=None):
+    """totals: double [3, C] (zeroed); [4, C] with dropout."""
     N, T, C = y.shape
-    call("lasr_bn_act_bwd_reduce", dout, out, y, r, totals, per_n, N, T, C, act, dtype_code(y.dtype))
+    if totals.shape[0] < (4 if drop is not None else 3):
+        raise _lib.LasrError("bn_act_bwd_reduce: totals needs 4 slots with dropout, 3 without")
+    call("lasr_bn_act_bwd_reduce", dout, out, y, r, totals, per_n, N, T, C, act,
+         drop.ptr if drop is not None else None, dtype_code(y.dtype))
     return totals
 
 
@@ -265,7 +302,7 @@ def bn_bwd_coef(totals, count, slot_gx, gamma, save, dgamma, dbeta):
     return coef
 
 
-def bn_act_bwd_apply(dout, out, y, r, gate, extra, totals, coef1, bn1, bn2, lengths, act):
+def bn_act_bwd_apply(dout, out, y, r, gate, extra, totals, coef1, bn1, bn2, lengths, act, drop=None):
     """bn1 / bn2: (gamma, save [2,C], dgamma, dbeta) tuples or None."""
     N, T, C = y.shape
     dy = torch.empty_like(y)
@@ -274,7 +311,7 @@ def bn_act_bwd_apply(dout, out, y, r, gate, extra, totals, coef1, bn1, bn2, leng
     s2 = _BNBwd(_p(bn2[0]), _p(bn2[1][0]), _p(bn2[1][1]), _p(bn2[2]), _p(bn2[3])) if bn2 is not None else None
     call("lasr_bn_act_bwd_apply", dout, out, y, r, gate, extra, totals, coef1,
          ctypes.addressof(s1) if s1 is not None else None, ctypes.addressof(s2) if s2 is not None else None, N * T,
-         lengths, T, dy, dr, N * T, C, act, dtype_code(y.dtype))
+         lengths, T, dy, dr, N * T, C, act, drop.ptr if drop is not None else None, dtype_code(y.dtype))
     return dy, dr
 
 

@@ -115,6 +115,49 @@ class Novograd(Optimizer):
         """The learning rate the most recent step() applied (synchronises)."""
         return float(self._lr_use.item())
 
+    # -- checkpoint / resume -----------------------------------------------------------------------------------
+    def state_dict(self):
+        """torch.optim layout (state[i] = {step, exp_avg, exp_avg_sq} like scheduler/novograd.py) plus the device-side
+        pieces the fused step really reads: the LR-schedule struct and the step count."""
+        sd = super().state_dict()
+        sd["lasr"] = {"steps": self._steps,
+                      "sched": None if self._sched_dev is None else self._sched_dev.detach().cpu().clone(),
+                      "lr_use": self._lr_use.detach().cpu().clone()}
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        """Resume: the inherited loader replaces self.state with fresh tensors, but the fused kernel only reads the flat
+        buffers -- copy the loaded moments into them, re-create the views, restore the schedule struct and step count."""
+        state_dict = dict(state_dict)
+        extra = state_dict.pop("lasr", None)
+        super().load_state_dict(state_dict)
+        bank = self.bank
+        steps = 0
+        for i, p in enumerate(self._plist):
+            st = self.state.get(p)
+            o = bank.offsets[id(p)]
+            if st is not None and "exp_avg" in st:
+                self._exp_avg[o:o + p.numel()].copy_(st["exp_avg"].reshape(-1).to(self._exp_avg.dtype))
+                self._exp_avg_sq[i].copy_(torch.as_tensor(st["exp_avg_sq"]).reshape(()).to(self._exp_avg_sq.dtype))
+                steps = max(steps, int(st.get("step", 0)))
+            else:
+                self._exp_avg[o:o + p.numel()].zero_()
+                self._exp_avg_sq[i].zero_()
+            self.state[p] = {"step": int(st.get("step", 0)) if st else 0,
+                             "exp_avg": self._exp_avg[o:o + p.numel()].view_as(p), "exp_avg_sq": self._exp_avg_sq[i]}
+        self._steps = steps
+        if extra is not None:
+            self._steps = int(extra.get("steps", steps))
+            if extra.get("sched") is not None:
+                if self._sched_dev is not None and self._sched_dev.numel() == extra["sched"].numel():
+                    self._sched_dev.copy_(extra["sched"].to(bank.device))  # in place: a captured graph keeps the pointer
+                else:
+                    self._sched_dev = extra["sched"].to(bank.device).clone()
+            if extra.get("lr_use") is not None:
+                self._lr_use.copy_(extra["lr_use"].to(bank.device))
+        bank.invalidate_shadow()  # the caller usually reloads the model too: force a fresh bf16 cast
+
     # -- the step ----------------------------------------------------------------------------------------------
     @torch.no_grad()
     def step(self, closure=None):

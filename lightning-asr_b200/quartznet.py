@@ -110,10 +110,12 @@ class SeprationConv(nn.Module):
             return None, None
         return self.se.fc[0].weight, self.se.fc[2].weight
 
-    def forward(self, x, lengths, residual=None, res_x=None):
+    def forward(self, x, lengths, residual=None, res_x=None, drop_mask=None):
         """x [N, T, Cin] channels-last.  `residual` = (conv1x1, bn) of the enclosing block to fuse (then ReLU is
-        applied after the add, models/QuartNet.py:75-77)."""
+        applied after the add, models/QuartNet.py:75-77).  nn.Dropout(drop_rate) (:27,38) is fused into the apply pass;
+        `drop_mask` (uint8 keep mask [N, T, Cout]) replaces the device-drawn mask (parity hook)."""
         lens = lengths if self.mask else None
+        drop = (self.drop_rate, drop_mask) if (self.drop_rate > 0.0 and self.training) else None
         se1, se2 = self._se_weights()
         if self.se is None and _fold_ok(self, x):
             # eval fast path: dw conv -> [residual GEMM + bias] -> ONE GEMM with the whole block epilogue
@@ -130,13 +132,10 @@ class SeprationConv(nn.Module):
             rconv, rbn = residual
             return SepConvBNFn.apply(x, res_x, lens, self.depthwise_conv.weight, self.pointwise_conv.weight,
                                      self.bn.weight, self.bn.bias, rconv.weight, rbn.weight, rbn.bias, se1, se2,
-                                     _bn_buffers(self.bn), _bn_buffers(rbn), self.stride, True, self.training)
-        out = SepConvBNFn.apply(x, None, lens, self.depthwise_conv.weight, self.pointwise_conv.weight, self.bn.weight,
-                                self.bn.bias, None, None, None, se1, se2, _bn_buffers(self.bn), None, self.stride,
-                                not self.last, self.training)
-        if self.drop_rate > 0.0 and self.training:
-            out = torch.nn.functional.dropout(out, p=self.drop_rate, training=True)
-        return out
+                                     _bn_buffers(self.bn), _bn_buffers(rbn), self.stride, True, self.training, drop)
+        return SepConvBNFn.apply(x, None, lens, self.depthwise_conv.weight, self.pointwise_conv.weight, self.bn.weight,
+                                 self.bn.bias, None, None, None, se1, se2, _bn_buffers(self.bn), None, self.stride,
+                                 not self.last, self.training, drop)
 
 
 class QuartNetBlock(nn.Module):
@@ -155,18 +154,15 @@ class QuartNetBlock(nn.Module):
         self.seq = nn.ModuleList(seq)
         self.drop_rate = drop_rate
 
-    def forward(self, x, lengths):
+    def forward(self, x, lengths, drop_masks=None):
+        """drop_masks: optional list of uint8 keep masks, one per SeprationConv of `seq` (parity hook)."""
         start = x
-        for m in self.seq[:-1]:
-            x = m(x, lengths)
+        for i, m in enumerate(self.seq[:-1]):
+            x = m(x, lengths, drop_mask=None if drop_masks is None else drop_masks[i])
         last = self.seq[-1]
-        if self.drop_rate > 0.0 and self.training:
-            # dropout sits between BN and the residual add (models/QuartNet.py:38,76): unfused path
-            y = last(x, lengths)
-            r = Conv1x1BNReLUFn.apply(start, self.reside[0].weight, self.reside[1].weight, self.reside[1].bias,
-                                      _bn_buffers(self.reside[1]), self.training, False)
-            return torch.relu(y + r)
-        return last(x, lengths, residual=(self.reside[0], self.reside[1]), res_x=None if x is start else start)
+        # dropout sits between BN and the residual add (models/QuartNet.py:38,76): the apply pass does both
+        return last(x, lengths, residual=(self.reside[0], self.reside[1]), res_x=None if x is start else start,
+                    drop_mask=None if drop_masks is None else drop_masks[-1])
 
 
 class BatchLSTM(nn.Module):
@@ -236,13 +232,16 @@ class QuartNet12(nn.Module):
             self.context_rnn = BatchLSTM(in_ch=256, out_ch=40, batch_first=True, bidirection=True)
         self.drop_rate = drop_rate
 
-    def forward_ntc(self, x, percents):
-        """x [N, T, F] channels-last features -> [N, T', 1024] channels-last."""
+    def forward_ntc(self, x, percents, drop_masks=None):
+        """x [N, T, F] channels-last features -> [N, T', 1024] channels-last.
+        drop_masks: optional dict module name -> uint8 keep mask [N, T', C] ('first_cnn', block names, 'last_cnn2'):
+        the parity hook for drop_rate > 0 (torch's Philox stream cannot be reproduced)."""
         T_out = (x.shape[1] - 1) // 2 + 1
         lengths = ops.out_lengths(T_out, percents.to(x.device))
-        x = self.first_cnn(x, lengths)
+        dm = drop_masks or {}
+        x = self.first_cnn(x, lengths, drop_mask=dm.get("first_cnn"))
         for name in self.block_names:
-            x = getattr(self, name)(x, lengths)
+            x = getattr(self, name)(x, lengths, drop_masks=[dm[name]] if name in dm else None)
             if name == "block23" and self.variant != "base":
                 # models/QuartNetContext.py:171-173: length = (T' * percents).int() is the same `lengths` tensor; it
                 # stays on the device (the reference's `.cpu()` sync is gone)
@@ -252,18 +251,17 @@ class QuartNet12(nn.Module):
             w, b = _folded(self.last_cnn2[0], self.last_cnn2[1], self, "last_cnn2")
             x = ops.pwconv_fwd_fused(x, w, b, relu=True)
         else:
+            drop = (self.drop_rate, dm.get("last_cnn2")) if (self.drop_rate > 0.0 and self.training) else None
             x = Conv1x1BNReLUFn.apply(x, self.last_cnn2[0].weight, self.last_cnn2[1].weight, self.last_cnn2[1].bias,
-                                      _bn_buffers(self.last_cnn2[1]), self.training, True)
-        if self.drop_rate > 0.0 and self.training:
-            x = torch.nn.functional.dropout(x, p=self.drop_rate, training=True)
+                                      _bn_buffers(self.last_cnn2[1]), self.training, True, drop)
         return x
 
-    def forward(self, input, percents, precision=None):
+    def forward(self, input, percents, precision=None, drop_masks=None):
         """input [N, 1, F, T] fp32 (reference layout) -> [N, T', 1024] channels-last (internal layout)."""
         _lib.require_device()
         dt = resolve_dtype(precision)
         feats = input.squeeze(dim=1).contiguous().float()
-        return self.forward_ntc(ops.nct_to_ntc(feats, dt), percents)
+        return self.forward_ntc(ops.nct_to_ntc(feats, dt), percents, drop_masks=drop_masks)
 
 
 class MyModel2(nn.Module):
@@ -281,11 +279,11 @@ class MyModel2(nn.Module):
         self.encoder = QuartNet12(drop_rate=drop_rate, mask=mask, in_c=in_c, variant=self.variant)
         self.decoder = nn.Conv1d(1024, len(self.labels) + 1, kernel_size=(1,))
 
-    def encode(self, input, percents):
-        return self.encoder(input, percents, precision=self.precision)
+    def encode(self, input, percents, drop_masks=None):
+        return self.encoder(input, percents, precision=self.precision, drop_masks=drop_masks)
 
-    def forward(self, input, percents):
-        x = self.encode(input, percents)
+    def forward(self, input, percents, drop_masks=None):
+        x = self.encode(input, percents, drop_masks=drop_masks)
         return DecoderLogSoftmaxFn.apply(x, self.decoder.weight, self.decoder.bias)
 
     def forward_fused_ctc(self, input, percents, targets, target_lengths):

@@ -28,6 +28,12 @@ class ParamBank:
         params = [p for p in (module.parameters() if hasattr(module, "parameters") else module)]
         if not params or not params[0].is_cuda:
             raise _lib.LasrError("ParamBank needs a module that already lives on the GPU")
+        cur = _BANK["bank"]
+        if cur is not None and any(id(p) in cur.offsets for p in params):
+            raise _lib.LasrError(
+                "these parameters already live in the installed ParamBank: a second bank would re-home them and "
+                "silently detach the first one's master / shadow / gradient buffers (captured CUDA graphs and the "
+                "fused optimizer keep using those).  Share runtime.current(), or runtime.uninstall() first.")
         self.device = params[0].device
         self.params = params
         self.offsets = {}
@@ -49,6 +55,11 @@ class ParamBank:
         self.shadow_fresh = False
         self.shadow_synced = False  # set by optim.Novograd: its update pass already rewrote the bf16 shadows
         self.on_grad_ready = None  # callable(param) installed by ddp.GradSync
+        # device-resident step counter: added to the dropout seeds inside the kernels, so that a replayed CUDA graph
+        # (frozen kernel arguments) still draws fresh masks; only advanced when some module actually drops
+        self.step_counter = torch.zeros((), device=self.device, dtype=torch.int64)
+        self.count_steps = any(getattr(m, "drop_rate", 0.0) > 0.0 for m in module.modules()) \
+            if hasattr(module, "modules") else False
         # weight-gradient kernels are off the critical path of backward (nothing reads them before the step ends):
         # defer() launches them on a lower-priority side stream so they fill the SMs that the main chain leaves idle
         # at kernel boundaries and tails.  Their inputs are kept alive until join_side().  OPT-IN (LASR_SIDE_WGRAD=1):
@@ -70,6 +81,8 @@ class ParamBank:
         previous step already refreshed them)."""
         self._zeroed.zero_()
         self._arena_off = 0
+        if self.count_steps:
+            self.step_counter.add_(1)
         if not self.shadow_synced:
             _lib.call("lasr_cast_weight", self.master, self.shadow, 1, self.numel, 0, _lib.LASR_BF16)
         self.shadow_synced = False
@@ -164,6 +177,26 @@ def weight(p, dtype):
     out = torch.empty(p.shape, device=p.device, dtype=dtype)
     _lib.call("lasr_cast_weight", p.detach().contiguous(), out, 1, p.numel(), 0, _lib.dtype_code(dtype))
     return out
+
+
+_DROP = {"base": 0x5DEECE66D, "calls": 0}
+
+
+def set_dropout_seed(seed):
+    """Seed of the fused dropout masks (the reference uses torch's global Philox stream; ours is independent of it)."""
+    _DROP["base"] = int(seed)
+    _DROP["calls"] = 0
+
+
+def next_dropout_stream():
+    """-> (seed, seed_dev) for one dropout call site.  Every call gets its own seed; inside an armed step the bank's
+    device step counter is added in the kernel, so a CUDA-graph replay draws new masks although `seed` is frozen."""
+    _DROP["calls"] += 1
+    seed = (_DROP["base"] + 0x9E3779B97F4A7C15 * _DROP["calls"]) & 0xFFFFFFFFFFFFFFFF
+    b = _BANK["bank"]
+    if b is not None and b.armed and b.count_steps:
+        return seed, b.step_counter
+    return seed, None
 
 
 def grad_sink(p):

@@ -159,7 +159,13 @@ class TrainEngine:
             self.grad_sync = ddp.GradSync(module, group=world_sync[0], bucket_mb=world_sync[1], overlap=True,
                                           bank=self.bank)
         self.fused = fused
-        self.host = [t.pin_memory() if torch.is_tensor(t) else t for t in example_batch[:4]]
+        # TWO pinned host staging sets: the H2D copies are asynchronous, so the host may only overwrite a set once the
+        # copy that last read it has completed (event per set); with two sets the host can stage batch i+1 while the
+        # H2D of batch i is still in flight (the two-deep pipeline of step_host(prefetch_next=..., defer_loss=True))
+        self._host_sets = [[t.clone().pin_memory() if torch.is_tensor(t) else t for t in example_batch[:4]]
+                           for _ in range(2)]
+        self._host_idx = 0
+        self._h2d_evt = [None, None]
         self.static = [t.to(self.dev, non_blocking=True) if torch.is_tensor(t) else t for t in self.host]
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host if torch.is_tensor(t))
         self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
@@ -174,6 +180,32 @@ class TrainEngine:
         self.staging = [torch.empty_like(t) if torch.is_tensor(t) else t for t in self.static]
         self._staged_evt = None
         self._consumed_evt = None
+
+    @property
+    def host(self):
+        """The pinned staging set holding the most recently staged batch."""
+        return self._host_sets[self._host_idx]
+
+    def _stage_host(self, batch):
+        """Copy a new batch into the OTHER pinned set (waiting until the H2D that last read it has finished)."""
+        i = self._host_idx ^ 1
+        if self._h2d_evt[i] is not None:
+            self._h2d_evt[i].synchronize()
+        for h, src in zip(self._host_sets[i], batch[:4]):
+            if torch.is_tensor(src):
+                if src.shape != h.shape:
+                    raise ValueError(f"TrainEngine batches must keep their shape: {tuple(src.shape)} vs {tuple(h.shape)}")
+                h.copy_(src)
+        self._host_idx = i
+
+    def _h2d(self, dst, stream):
+        """Queue the H2D of the current pinned set into `dst` on `stream` and remember when it completes."""
+        for h, d in zip(self.host, dst):
+            if torch.is_tensor(h):
+                d.copy_(h, non_blocking=True)
+        evt = torch.cuda.Event()
+        evt.record(stream)
+        self._h2d_evt[self._host_idx] = evt
 
     def _step_eager(self):
         m = self.module
@@ -221,30 +253,19 @@ class TrainEngine:
 
     def load_batch(self, batch):
         """Pinned-host staging + async H2D of a new batch of the SAME shapes."""
-        for h, d, src in zip(self.host, self.static, batch[:4]):
-            if torch.is_tensor(src):
-                if src.shape != h.shape:
-                    raise ValueError(f"TrainEngine batches must keep their shape: {tuple(src.shape)} vs {tuple(h.shape)}")
-                h.copy_(src)
-                d.copy_(h, non_blocking=True)
+        self._stage_host(batch)
+        self._h2d(self.static, torch.cuda.current_stream())
 
     def prefetch(self, batch=None):
         """Start the H2D of the NEXT batch (pinned host -> device staging buffers) on the copy stream; it overlaps
         whatever the compute stream is doing.  `batch=None` re-sends the pinned example batch (bench.py)."""
         if batch is not None:
-            for h, src in zip(self.host, batch[:4]):
-                if torch.is_tensor(src):
-                    if src.shape != h.shape:
-                        raise ValueError(f"TrainEngine batches must keep their shape: {tuple(src.shape)} vs {tuple(h.shape)}")
-                    h.copy_(src)
+            self._stage_host(batch)
         if self._consumed_evt is not None:
             self.copy_stream.wait_event(self._consumed_evt)  # the previous staging contents have been taken over
         with torch.cuda.stream(self.copy_stream):
-            for h, d in zip(self.host, self.staging):
-                if torch.is_tensor(h):
-                    d.copy_(h, non_blocking=True)
-            self._staged_evt = torch.cuda.Event()
-            self._staged_evt.record(self.copy_stream)
+            self._h2d(self.staging, self.copy_stream)
+            self._staged_evt = self._h2d_evt[self._host_idx]
 
     def step_host(self, batch=None, prefetch_next=False, defer_loss=False):
         """End-to-end step: H2D of the batch from pinned memory, the step, D2H of the loss.  Returns a float.
@@ -266,9 +287,7 @@ class TrainEngine:
         elif batch is not None:
             self.load_batch(batch)
         else:
-            for h, d in zip(self.host, self.static):
-                if torch.is_tensor(h):
-                    d.copy_(h, non_blocking=True)
+            self._h2d(self.static, cur)
         self.step_device()
         if prefetch_next is not False and prefetch_next is not None:
             self.prefetch(None if prefetch_next is True else prefetch_next)
@@ -286,6 +305,11 @@ class TrainEngine:
             return None
         self._loss_evt[prev].synchronize()
         return float(self._loss_ring[prev])
+
+    def close(self):
+        """Release the step runtime (the parameters stay valid views of this engine's flat master buffer)."""
+        if runtime.current() is self.bank:
+            runtime.uninstall()
 
     def flush_loss(self):
         """Loss of the most recent deferred step (waits for it)."""
@@ -338,16 +362,30 @@ class InferEngine:
         self.copy_stream = torch.cuda.Stream()
         self._staged_evt = self._consumed_evt = None
         self.use_graph, self.graph = graph, None
-        # weights do not change during inference: ONE bf16 shadow cast here instead of one per layer and pass
-        self.bank = runtime.ParamBank(module)
-        runtime.install(self.bank)
+        # weights do not change during inference: ONE bf16 shadow cast here instead of one per layer and pass.
+        # If the module is already owned by the installed bank (validation during training: the TrainEngine's graph and
+        # the fused optimizer keep writing THAT bank's masters / shadows) the engine shares it -- re-homing the
+        # parameters into a second bank would silently freeze both state_dict() and this engine's weights.
+        cur = runtime.current()
+        params = list(module.parameters())
+        if cur is not None and all(id(p) in cur.offsets for p in params):
+            self.bank, self._owns_bank = cur, False
+        else:
+            self.bank, self._owns_bank = runtime.ParamBank(module), True  # raises if another installed bank owns them
+            runtime.install(self.bank)
         self.refresh_weights()
 
     def refresh_weights(self):
-        """Re-cast the bf16 weight shadows (call after load_state_dict / any parameter update)."""
+        """Re-cast the bf16 weight shadows (call after load_state_dict / any parameter update; with a bank shared with a
+        TrainEngine, call it before validating so the shadows reflect the latest optimizer step)."""
         b = self.bank
         _lib.call("lasr_cast_weight", b.master, b.shadow, 1, b.numel, 0, _lib.LASR_BF16)
         b.shadow_fresh = True
+
+    def close(self):
+        """Release the step runtime if this engine installed it."""
+        if self._owns_bank and runtime.current() is self.bank:
+            runtime.uninstall()
 
     def _run(self):
         fe, ops = self.frontend, self.ops

@@ -89,19 +89,22 @@ def sep_conv(x, percents, sd, prefix, last, mask, stride, training, update_buffe
     return x
 
 
-def block(x, percents, sd, prefix, mask, training, update_buffers, relu_mask=None):
-    """models/QuartNet.py:71-78 for repeat == 1 (+ the repeat > 1 quirk of :60 is exercised by its own test).
+def block(x, percents, sd, prefix, mask, training, update_buffers, relu_mask=None, drop_masks=None):
+    """models/QuartNet.py:71-78, any `repeat` (the :60 quirk -- `mask` lands in the inner seps' `last` slot -- is
+    pinned by tests/test_oracle_golden.py::test_block_repeat_quirk_matches_reference and exercised on the GPU by
+    tests/test_parity_gpu.py).
     relu_mask (parity hook, like drop_mask): replaces the final ReLU's own gate by a supplied 0/1 tensor so a
-    reduced-precision implementation can be checked on an identical gating pattern."""
+    reduced-precision implementation can be checked on an identical gating pattern.
+    drop_masks: optional list (one per SeprationConv of the block) of dropout factors [N, C, T] (0 or 1/(1-p))."""
     start = x
     i = 0
     while (prefix + f".seq.{i + 1}.depthwise_conv.weight") in sd:
         # inner seps: constructed as SeprationConv(in, in, k, mask, ...) -> last=mask, mask=True (:60)
         x = sep_conv(x, percents, sd, prefix + f".seq.{i}", last=bool(mask), mask=True, stride=1, training=training,
-                     update_buffers=update_buffers)
+                     update_buffers=update_buffers, drop_mask=None if drop_masks is None else drop_masks[i])
         i += 1
     x = sep_conv(x, percents, sd, prefix + f".seq.{i}", last=True, mask=mask, stride=1, training=training,
-                 update_buffers=update_buffers)
+                 update_buffers=update_buffers, drop_mask=None if drop_masks is None else drop_masks[i])
     r = F.conv1d(start, sd[prefix + ".reside.0.weight"])
     r = batch_norm(r, sd, prefix + ".reside.1", training, update_buffers)
     if relu_mask is not None:
@@ -126,12 +129,16 @@ def context_lstm(x, percents, sd, prefix):
     return torch.cat((x, c.transpose(1, 2)), dim=1)
 
 
-def encoder(x, percents, sd, prefix="encoder", mask=False, training=True, update_buffers=False, taps=None):
+def encoder(x, percents, sd, prefix="encoder", mask=False, training=True, update_buffers=False, taps=None,
+            drop_masks=None):
     """QuartNet12.forward (models/QuartNet.py:152-173; Context variants models/QuartNetContext.py:163-184).
-    x [N, 1, F, T] -> [N, 1024, T'].  `taps` (dict) collects intermediate activations by module name."""
+    x [N, 1, F, T] -> [N, 1024, T'].  `taps` (dict) collects intermediate activations by module name.
+    drop_masks: dict module name ('first_cnn', block names, 'last_cnn2') -> dropout factors [N, C, T'] standing in
+    for nn.Dropout(drop_rate) at models/QuartNet.py:38 and :149 (torch's random stream is not reproducible)."""
+    dm = drop_masks or {}
     x = x.squeeze(dim=1)
     x = sep_conv(x, percents, sd, prefix + ".first_cnn", last=False, mask=mask, stride=2, training=training,
-                 update_buffers=update_buffers)
+                 update_buffers=update_buffers, drop_mask=dm.get("first_cnn"))
     if taps is not None:
         taps["first_cnn"] = x
     names = [n for n, _ in ASR13X1_BLOCKS]
@@ -139,7 +146,8 @@ def encoder(x, percents, sd, prefix="encoder", mask=False, training=True, update
     if has_ctx:
         names.append("block6")
     for name in names:
-        x = block(x, percents, sd, prefix + "." + name, mask, training, update_buffers)
+        x = block(x, percents, sd, prefix + "." + name, mask, training, update_buffers,
+                  drop_masks=[dm[name]] if name in dm else None)
         if taps is not None:
             taps[name] = x
         if name == "block23" and has_ctx:
@@ -147,13 +155,15 @@ def encoder(x, percents, sd, prefix="encoder", mask=False, training=True, update
     x = F.conv1d(x, sd[prefix + ".last_cnn2.0.weight"])
     x = batch_norm(x, sd, prefix + ".last_cnn2.1", training, update_buffers)
     x = torch.relu(x)
+    if "last_cnn2" in dm:
+        x = x * dm["last_cnn2"]
     if taps is not None:
         taps["last_cnn2"] = x
     return x
 
 
-def model(x, percents, sd, mask=False, training=True, update_buffers=False, taps=None):
+def model(x, percents, sd, mask=False, training=True, update_buffers=False, taps=None, drop_masks=None):
     """MyModel2.forward (models/QuartNet.py:280-291): encoder -> decoder conv (bias) -> [N,T',V'] -> log_softmax."""
-    h = encoder(x, percents, sd, "encoder", mask, training, update_buffers, taps)
+    h = encoder(x, percents, sd, "encoder", mask, training, update_buffers, taps, drop_masks)
     logits = F.conv1d(h, sd["decoder.weight"], sd["decoder.bias"])
     return F.log_softmax(logits.transpose(1, 2), dim=-1)

@@ -90,3 +90,25 @@ class optim_case:
     def grads(step):
         return [torch.randn(s, generator=_gen(f"optim.g{i}.{step}")) * (0.01 + 0.003 * i)
                 for i, s in enumerate(optim_case.SHAPES)]
+
+
+def aishell_labels():
+    """A 4333-symbol vocabulary the size of data/aishell1-vocab.txt (only the SIZE matters: V' = 4334)."""
+    return [chr(0x4E00 + i) for i in range(4333)]
+
+
+def drop_factor(call_index, shape, p):
+    """Dropout factor tensor (0 or 1/(1-p)) of the call_index-th nn.Dropout call of a forward pass, reference layout
+    [N, C, T]: seeded per call, so make_golden_variants.py (which patches nn.Dropout.forward with it) and the tests
+    (which feed the same masks to the oracle / the CUDA kernels) agree without storing the masks."""
+    keep = torch.rand(tuple(shape), generator=_gen(f"drop/{call_index}")) >= p
+    return keep.float() / (1.0 - p)
+
+
+def block_inputs(cin, cout, n=3, frames=75):
+    """Seeded input / percents / upstream gradient for a single QuartNetBlock, reference layout [N, C, T]."""
+    g = _gen(f"block/{cin}/{cout}")
+    x = torch.randn(n, cin, frames, generator=g)
+    percents = torch.tensor([1.0, 0.83, 0.52][:n])
+    dout = torch.randn(n, cout, frames, generator=g)
+    return x, percents, dout

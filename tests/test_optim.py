@@ -105,3 +105,48 @@ def test_fused_novograd_large_tensor_and_odd_sizes_vs_oracle():
         optim_oracle.novograd_step(ref, grads, state, 3e-3, betas=(0.8, 0.5), weight_decay=1e-4)
     for a, b in zip(params, ref):
         assert torch.allclose(a.detach().cpu(), b, rtol=5e-6, atol=1e-8)
+
+
+@pytest.mark.gpu
+def test_novograd_checkpoint_resume_matches_uninterrupted_run():
+    """save -> load -> continue must equal the uninterrupted run: the moments live in flat device buffers and
+    the LR schedule in a device struct, neither of which the inherited load_state_dict touches."""
+    import copy
+
+    from lightning_asr_b200.optim import CosineAnnealingWarmupRestarts, Novograd
+
+    hyper, sched, steps = optim_case.CASES["train_py"]
+
+    def make():
+        params = [torch.nn.Parameter(p.cuda()) for p in optim_case.params()]
+        opt = Novograd(params, **hyper)
+        opt.attach_schedule(CosineAnnealingWarmupRestarts(opt, **sched))
+        return params, opt
+
+    def run(params, opt, lo, hi):
+        for k in range(lo, hi):
+            for p, g in zip(params, optim_case.grads(k)):
+                p.grad = g.cuda()
+            opt.step()
+
+    pa, oa = make()
+    run(pa, oa, 0, 12)
+    pb, ob = make()
+    run(pb, ob, 0, 5)
+    ckpt = copy.deepcopy({"opt": ob.state_dict(), "params": [p.detach().clone() for p in pb]})
+    assert ckpt["opt"]["state"][0]["exp_avg"].abs().sum() > 0 and ckpt["opt"]["lasr"]["steps"] == 5
+    pc, oc = make()  # a fresh process: new parameters, new optimizer, then resume
+    with torch.no_grad():
+        for p, q in zip(pc, ckpt["params"]):
+            p.copy_(q)
+    oc.load_state_dict(ckpt["opt"])
+    assert oc.state[pc[0]]["exp_avg"].data_ptr() == oc._exp_avg.data_ptr() + 4 * oc.bank.offsets[id(pc[0])]
+    assert oc.schedule_state() == ob.schedule_state()
+    run(pc, oc, 5, 12)
+    assert oc.last_lr() == oa.last_lr()
+    for a, c in zip(pa, pc):
+        assert torch.equal(a.detach(), c.detach())
+    for a, c in zip(pa, pc):
+        assert torch.equal(oa.state[a]["exp_avg"], oc.state[c]["exp_avg"])
+        assert torch.equal(oa.state[a]["exp_avg_sq"], oc.state[c]["exp_avg_sq"])
+        assert oc.state[c]["step"] == 12

@@ -157,3 +157,94 @@ def test_augment_oracle_matches_reference():
         # the product's host-side draw (no oracle import there) follows the same arithmetic
         from lightning_asr_b200 import frontend
         assert frontend.draw_augment(d["samples"], random.Random(d["rng_seed"])) == (start, kept, bands)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# variants.pt (tests/golden/make_golden_variants.py): mask=False, QuartNetBlock(repeat=2), drop_rate > 0, AISHELL vocab
+# ---------------------------------------------------------------------------------------------------------------
+from golden_common import aishell_labels, block_inputs, drop_factor  # noqa: E402
+
+DROP_NAMES = ["first_cnn", "block1", "block12", "block13", "block2", "block22", "block23", "block3", "block32",
+              "block33", "block4", "block42", "block43", "block5"]
+
+
+def drop_masks_for(fx, with_block6):
+    """The keep factors make_golden_variants.py fed the reference's nn.Dropout calls, keyed by module name (the call
+    order of the reference's forward: first_cnn, the blocks in order, last_cnn2)."""
+    names = DROP_NAMES + (["block6"] if with_block6 else []) + ["last_cnn2"]
+    assert len(names) == len(fx["calls"])
+    return {n: drop_factor(i, fx["calls"][i], fx["p"]) for i, n in enumerate(names)}
+
+
+def _train_grads(sd, x, percents, targets, tgt_len, labels, mask, drop_masks=None):
+    """fp64 oracle step (the variants fixture is the reference's own fp64 run, stored as fp32)."""
+    for k in list(sd):
+        if sd[k].is_floating_point():
+            sd[k] = sd[k].double()
+            if "running" not in k:
+                sd[k].requires_grad_(True)
+    if drop_masks is not None:
+        drop_masks = {k: v.double() for k, v in drop_masks.items()}
+    out = quartznet_oracle.model(x.double(), percents, sd, mask=mask, training=True, drop_masks=drop_masks)
+    t_len = torch.mul(out.size(1), percents).int()
+    nll = torch.nn.functional.ctc_loss(out.transpose(0, 1), targets, t_len, tgt_len, blank=len(labels), reduction="none")
+    nll.mean().backward()
+    return out.detach(), nll.detach()
+
+
+def _check_grads(sd, fx, norm_tol=1e-5, tol=1e-5):
+    for k, ref in fx["grad_norm"].items():
+        got = float(sd[k].grad.double().norm())
+        assert abs(got - ref) <= norm_tol * max(ref, 1e-12), (k, got, ref)
+    for k, ref in fx["grad"].items():
+        assert rel_err(sd[k].grad, ref) < tol, k
+
+
+def test_oracle_mask_false_matches_reference():
+    fx = _load("variants.pt")["mask_false"]
+    sd = golden_weights(fx["schema"])
+    out, nll = _train_grads(sd, *model_inputs(), LABELS28, mask=False)
+    assert rel_err(out, fx["train_out"]) < 2e-6
+    assert rel_err(nll, fx["train_nll"]) < 2e-6
+    _check_grads(sd, fx)
+
+
+@pytest.mark.parametrize("mask", [True, False])
+def test_block_repeat_quirk_matches_reference(mask):
+    """QuartNetBlock(repeat=2): `mask` lands in the inner SeprationConv's `last` slot (models/QuartNet.py:60)."""
+    fx = _load("variants.pt")["repeat2_mask" if mask else "repeat2_nomask"]
+    assert fx["inner_last"] == mask and fx["inner_mask"] is True
+    sd = {"b." + k: v.requires_grad_(v.is_floating_point() and "running" not in k)
+          for k, v in golden_weights(fx["schema"]).items()}
+    x, percents, dout = block_inputs(64, 96)
+    x = x.clone().requires_grad_(True)
+    out = quartznet_oracle.block(x, percents, sd, "b", mask=mask, training=True, update_buffers=False)
+    out.backward(dout)
+    assert rel_err(out, fx["out"]) < 2e-6
+    assert rel_err(x.grad, fx["dx"]) < 1e-5
+    for k, ref in fx["grad"].items():
+        assert rel_err(sd["b." + k].grad, ref) < 1e-5, k
+
+
+@pytest.mark.parametrize("variant", ["base", "contextse"])
+def test_oracle_dropout_placement_matches_reference(variant):
+    fx = _load("variants.pt")["dropout_" + variant]
+    sd = golden_weights(fx["schema"])
+    dm = drop_masks_for(fx, with_block6=(variant != "base"))
+    out, nll = _train_grads(sd, *model_inputs(), LABELS28, mask=True, drop_masks=dm)
+    assert rel_err(out, fx["train_out"]) < 2e-6
+    assert rel_err(nll, fx["train_nll"]) < 2e-6
+    _check_grads(sd, fx)
+
+
+def test_oracle_aishell_vocab_matches_reference():
+    fx = _load("variants.pt")["aishell"]
+    labels = aishell_labels()
+    sd = golden_weights(fx["schema"])
+    x, percents, targets, tgt_len = model_inputs(n_labels=len(labels))
+    out, nll = _train_grads(sd, x, percents, targets, tgt_len, labels, mask=True)
+    assert out.shape[-1] == 4334
+    assert rel_err(out[:, :, fx["cols"]], fx["train_out_cols"]) < 2e-6
+    assert torch.equal(out.argmax(dim=-1), fx["train_out_argmax"])
+    assert rel_err(nll, fx["train_nll"]) < 2e-6
+    _check_grads(sd, fx)
