@@ -64,6 +64,8 @@ _lib = None
 # Optional instrumentation (bench.py / tools only): when PROFILE is a list, every call() appends
 # (name, int/float args, pointer-non-null flags, start_event, end_event) recorded on the launching stream; CALLS counts entry-point calls.
 PROFILE = None
+PROFILE_EXTERNAL = False  # True: the events become event-record NODES of a CUDA graph being captured (timed per replay)
+PROFILE_ONLY = None  # optional callable(name) -> bool: only these entry points get events (the rest are listed untimed)
 CALLS = {"n": 0}
 
 
@@ -122,8 +124,13 @@ def call(name, *args):
             conv.append(int(a))
     conv.append(stream_ptr())
     CALLS["n"] += 1
-    if PROFILE is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if PROFILE is not None and PROFILE_ONLY is not None and not PROFILE_ONLY(name):
+        rc = getattr(lib, name)(*conv)
+        PROFILE.append((name, tuple(a for c, a in zip(codes, conv) if c in "if"),
+                        tuple(a is not None for c, a in zip(codes, conv) if c == "p"), None, None))
+    elif PROFILE is not None:
+        e0 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
+        e1 = torch.cuda.Event(enable_timing=True, external=PROFILE_EXTERNAL)
         e0.record()
         rc = getattr(lib, name)(*conv)
         e1.record()

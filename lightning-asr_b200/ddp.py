@@ -62,6 +62,7 @@ class GradSync:
                     items.append((p, off, p.numel()))
                     off += p.numel()
             self.buckets.append((flat, items))
+        self.enabled = True  # False: skip the collective itself (bench.py measures how much of it is exposed)
         self.overlap = overlap and self.world > 1
         self.comm_stream = None
         if self.overlap and self.params and self.params[0].is_cuda:
@@ -105,7 +106,7 @@ class GradSync:
                     flat[off:off + n].zero_()
                 else:
                     flat[off:off + n].copy_(p.grad.reshape(-1))
-        if self.world > 1:
+        if self.world > 1 and self.enabled:
             if flat.is_cuda:
                 dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
             else:

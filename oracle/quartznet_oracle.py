@@ -70,8 +70,8 @@ def se_layer(x, sd, prefix):
     return x * y[:, :, None]
 
 
-def sep_conv(x, percents, sd, prefix, last, mask, stride, training, update_buffers, drop_mask=None):
-    """models/QuartNet.py:29-39 (+ models/QuartNetContextSE.py:55)."""
+def sep_conv(x, percents, sd, prefix, last, mask, stride, training, update_buffers, drop_mask=None, relu_mask=None):
+    """models/QuartNet.py:29-39 (+ models/QuartNetContextSE.py:55).  relu_mask: parity hook, see block()."""
     dw = sd[prefix + ".depthwise_conv.weight"]
     k = dw.shape[-1]
     x = F.conv1d(x, dw, stride=stride, padding=k // 2, groups=dw.shape[0])
@@ -83,25 +83,28 @@ def sep_conv(x, percents, sd, prefix, last, mask, stride, training, update_buffe
     if (prefix + ".se.fc.0.weight") in sd:
         x = se_layer(x, sd, prefix + ".se")
     if not last:
-        x = torch.relu(x)
+        x = torch.relu(x) if relu_mask is None else x * relu_mask
     if drop_mask is not None:  # dropout with an externally supplied keep-mask / (1-p) scale (parity hook)
         x = x * drop_mask
     return x
 
 
-def block(x, percents, sd, prefix, mask, training, update_buffers, relu_mask=None, drop_masks=None):
+def block(x, percents, sd, prefix, mask, training, update_buffers, relu_mask=None, drop_masks=None,
+          inner_relu_masks=None):
     """models/QuartNet.py:71-78, any `repeat` (the :60 quirk -- `mask` lands in the inner seps' `last` slot -- is
     pinned by tests/test_oracle_golden.py::test_block_repeat_quirk_matches_reference and exercised on the GPU by
     tests/test_parity_gpu.py).
     relu_mask (parity hook, like drop_mask): replaces the final ReLU's own gate by a supplied 0/1 tensor so a
     reduced-precision implementation can be checked on an identical gating pattern.
+    inner_relu_masks: the same hook for the ReLUs of the inner SeprationConvs (repeat > 1, present iff not mask).
     drop_masks: optional list (one per SeprationConv of the block) of dropout factors [N, C, T] (0 or 1/(1-p))."""
     start = x
     i = 0
     while (prefix + f".seq.{i + 1}.depthwise_conv.weight") in sd:
         # inner seps: constructed as SeprationConv(in, in, k, mask, ...) -> last=mask, mask=True (:60)
         x = sep_conv(x, percents, sd, prefix + f".seq.{i}", last=bool(mask), mask=True, stride=1, training=training,
-                     update_buffers=update_buffers, drop_mask=None if drop_masks is None else drop_masks[i])
+                     update_buffers=update_buffers, drop_mask=None if drop_masks is None else drop_masks[i],
+                     relu_mask=None if inner_relu_masks is None else inner_relu_masks[i])
         i += 1
     x = sep_conv(x, percents, sd, prefix + f".seq.{i}", last=True, mask=mask, stride=1, training=training,
                  update_buffers=update_buffers, drop_mask=None if drop_masks is None else drop_masks[i])

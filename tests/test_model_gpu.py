@@ -91,7 +91,10 @@ def test_model_fp32_train_parity(lasr, labels28, variant):
     model = cls(labels28, mask=True, precision="fp32")
     sd0 = copy.deepcopy(model.state_dict())
     model = model.cuda().train()
-    N, T = 4, 301
+    # BASELINE config 1 shape (batch 4 of 10 s utterances, T = 1001): whole-network gradient noise is dominated by
+    # individual ReLU gates that flip between two fp32 runs; at this size both runs see many of them, so the comparison
+    # of ours against the fp32 oracle's own deviation (measured at this very shape) is stable
+    N, T = 4, 1001
     x, p = _inputs(N, T)
     Tp = (T - 1) // 2 + 1
     t_len = torch.mul(Tp, p).int()

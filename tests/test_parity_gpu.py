@@ -115,7 +115,10 @@ def test_block_repeat2_matches_reference_fixture(lasr, mask, precision, tol):
     dt = torch.bfloat16 if precision == "bf16" else torch.float32
     xg = x.to(dt).cuda().transpose(1, 2).contiguous().requires_grad_(True)
     lengths = torch.mul(x.shape[2], percents).int().cuda()
+    inner = []
+    hook = blk.seq[0].register_forward_hook(lambda m, a, o: inner.append(o.detach()))
     out = blk(xg, lengths)
+    hook.remove()
     out.backward(dout.to(dt).cuda().transpose(1, 2).contiguous())
     if precision == "fp32":
         assert rel_err(out.transpose(1, 2), fx["out"]) < tol
@@ -123,16 +126,18 @@ def test_block_repeat2_matches_reference_fixture(lasr, mask, precision, tol):
         for k, ref in fx["grad"].items():
             assert rel_err(dict(blk.named_parameters())[k].grad, ref) < tol, k
         return
-    # bf16: identical (rounded) inputs, gradients judged on the gating pattern of our forward; the
-    # inner sep's ReLU (present iff not mask) gates on its own bf16 forward, so allow the documented 3x on gradients
+    # bf16: identical (rounded) inputs, gradients judged on the gating pattern of our forward: the
+    # block's final ReLU and the inner sep's ReLU (present iff not mask) both take their gates from our forward
     sd = {"b." + k: v.double().requires_grad_(v.is_floating_point() and "running" not in k)
           for k, v in golden_weights(fx["schema"]).items()}
     xr = x.to(dt).double().requires_grad_(True)
     gate = (out.detach().float().transpose(1, 2) > 0).double().cpu()
-    ref = qo.block(xr, percents, sd, "b", mask=mask, training=True, update_buffers=False, relu_mask=gate)
+    inner_gate = [(inner[0].float().transpose(1, 2) > 0).double().cpu()]
+    ref = qo.block(xr, percents, sd, "b", mask=mask, training=True, update_buffers=False, relu_mask=gate,
+                   inner_relu_masks=inner_gate)
     ref.backward(dout.to(dt).double())
     assert rel_err(out.float().transpose(1, 2), ref) < tol
-    gtol = 3 * tol if mask else 10 * tol  # mask=False: the inner ReLU's own gate flips are not pinned by relu_mask
+    gtol = 3 * tol
     assert rel_err(xg.grad.float().transpose(1, 2), xr.grad) < gtol
     for k, prm in blk.named_parameters():
         assert rel_err(prm.grad, sd["b." + k].grad) < gtol, k
