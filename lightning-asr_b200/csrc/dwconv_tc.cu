@@ -567,6 +567,7 @@ struct Dw16Params {
   int N, T, C, K, KS, flip;
   int SL, rows_valid, t_chunks, slots_per_cg, items_per_cg, num_cg, ctas_per_cg, stages;
   int w_early;
+  unsigned long long* trace;  // debug timeline (tools/trace_dw.py), normally NULL
 };
 
 __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc16_fwd_kernel(const Dw16Params p) {
@@ -762,6 +763,419 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc16_fwd_kernel(const Dw
 }
 
 // ------------------------------------------------------------------------------------------------
+// 16-frame rows, second generation (default for stride-1 bf16 layers): same operands and MMAs as dwconv_tc16_fwd_kernel,
+// restructured around what the timeline (tools/trace_dw.py) and tools/tma_probe.cu showed:
+//   * the kernel is bound by how fast ONE SM can move 32-byte column slices of a channels-last matrix: ~16-20 B/clk/SM
+//     through LDG, TMA loads and STG alike (one L2 request per 32 useful bytes), i.e. ~1.3 us per (16 channels x 801
+//     frames) slot for its read + write, against ~0.7 us of MMA time -- so everything else has to hide behind the slices;
+//   * FOUR producer groups of 4 warps, one per (stage, slot): the gathers of all four utterance slots a CTA can hold
+//     (2 stages x 2 slots) are in flight at once (the round-1 kernels loaded one slot per group and item: 2-8 exposed
+//     gather latencies per CTA);
+//   * the Toeplitz cores are built from a shared-memory copy of the taps, one 16-byte chunk per thread and trip (the
+//     round-1 loop built them element by element with an integer division and a 2-byte store each: 3.5-5.5 us of
+//     exposed prologue per launch, measured);
+//   * the epilogue moves 2 frames x 16 channels per trip (32 + 16 live registers), which is what lets 22 warps
+//     (704 threads) share the register file; the residual-gradient addend (data-gradient launches only: template
+//     parameter) is requested one trip ahead.
+// ------------------------------------------------------------------------------------------------
+constexpr int D2_GROUPS = 4;
+constexpr int D2_THREADS = 32 * (6 + 4 * D2_GROUPS);  // 704
+
+__device__ __forceinline__ void tmem_ld_32x32_x2(uint32_t taddr, uint32_t (&v)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
+}
+
+template <bool HAS_ADDEND>
+__global__ void __launch_bounds__(D2_THREADS, 1) dwconv_tc16v2_fwd_kernel(const Dw16Params p) {
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) DT_TRACE(7, 0);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int toep_bytes_c = p.KS * 32;                       // per channel: KS/8 x 2 cores of 128 B
+  uint8_t* s_ser = smem;                                    // [2 stages][16][2 slots x 1024 frames] bf16, swizzled
+  uint8_t* s_toep = s_ser + 2 * D16_STAGE;                  // [16][KS/8][2][128 B]
+  float* s_w = reinterpret_cast<float*>(s_toep + DT_CG * toep_bytes_c);  // [16][DT_MAX_KS] fp32 taps of this channel group
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_w + DT_CG * DT_MAX_KS);
+  uint64_t* full_bar = bars;          // [2] producers (8 warps) -> MMA
+  uint64_t* empty_bar = bars + 2;     // [2] MMA -> producers
+  uint64_t* tmem_full_bar = bars + 4;
+  uint64_t* tmem_empty_bar = bars + 6;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cg = blockIdx.x % p.num_cg;
+  const int first = blockIdx.x / p.num_cg;
+  const int c0 = cg * DT_CG;
+  const int P = p.K / 2;
+
+  if (!p.w_early) pdl_wait();
+  for (int i = threadIdx.x; i < DT_CG * p.K; i += D2_THREADS) {
+    const int c = i / p.K, j = i - c * p.K;
+    s_w[c * DT_MAX_KS + j] = c0 + c < p.C ? p.w[static_cast<size_t>(c0 + c) * p.K + (p.flip ? p.K - 1 - j : j)] : 0.f;
+  }
+  if (warp_idx == 4 && lane == 0) {
+    for (int st = 0; st < 2; ++st) {
+      mbar_init(&full_bar[st], 8);
+      mbar_init(&empty_bar[st], 1);
+      mbar_init(&tmem_full_bar[st], 1);
+      mbar_init(&tmem_empty_bar[st], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp_idx == 5) {
+    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_relinquish();
+  }
+  __syncthreads();
+  // Toeplitz factor B[t, s] = w[s - t], t < 16 output frames of a row, s < KS series frames: K-major no-swizzle cores
+  // [s / 8][t / 8], element (t % 8, s % 8).  One 16-byte chunk = the 8 elements of (channel, core, row).
+  {
+    const int chunks_c = 2 * p.KS;  // per channel: KS/8 x 2 cores x 8 rows
+    for (int q = threadIdx.x; q < DT_CG * chunks_c; q += D2_THREADS) {
+      const int c = q / chunks_c;
+      const int rem = q - c * chunks_c;
+      const int core = rem >> 3, r = rem & 7;
+      const int j0 = 8 * (core >> 1) - (8 * (core & 1) + r);
+      const float* wc = s_w + c * DT_MAX_KS;
+      uint32_t o[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const int j = j0 + 2 * m;
+        const float a = (j >= 0 && j < p.K) ? wc[j] : 0.f;
+        const float b = (j + 1 >= 0 && j + 1 < p.K) ? wc[j + 1] : 0.f;
+        o[m] = f32x2_to_bf16x2(a, b);
+      }
+      *reinterpret_cast<uint4*>(s_toep + static_cast<size_t>(q) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) DT_TRACE(7, 1);
+  pdl_wait();
+
+  if (warp_idx >= 6) {
+    // ===================== producers: group g owns (stage g / 2, slot g % 2) =====================
+    const int pw = (warp_idx - 6) & 3;
+    const int grp = (warp_idx - 6) >> 2;
+    const int stage = grp >> 1, sl = grp & 1;
+    int it = stage;
+    for (int idx = first + stage * p.ctas_per_cg; idx < p.items_per_cg; idx += 2 * p.ctas_per_cg, it += 2) {
+      const uint32_t phase = (it >> 1) & 1;
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      if (pw == 0 && lane == 0) DT_TRACE(0, 2 * it + sl);
+      const int slot = 2 * idx + sl;
+      const __nv_bfloat16* src = nullptr;
+      int f_base = 0;
+      if (slot < p.slots_per_cg) {
+        const int n = slot / p.t_chunks, tc = slot - n * p.t_chunks;
+        src = p.x + static_cast<size_t>(n) * p.T * p.C + c0;
+        f_base = tc * p.SL - P;
+      }
+      load_slot_sw32(src, p.C, p.T, f_base, s_ser + stage * D16_STAGE + sl * (D16_SLOTF * 2), pw, lane);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (pw == 0 && lane == 0) DT_TRACE(1, 2 * it + sl);
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+    }
+  } else if (warp_idx == 4) {
+    // ===================== MMA issuer =====================
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(DT_ROWS, 16, 0, 0);
+    const int ksteps = p.KS / 16;
+    int it = 0;
+    for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
+      const int stage = it & 1;
+      const uint32_t phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[stage], phase ^ 1u);
+      if (leader) DT_TRACE(2, it);
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (leader) DT_TRACE(3, it);
+      uint64_t da_c = umma_desc_sw32(smem_u32(s_ser + stage * D16_STAGE), 256);
+      uint64_t db_c = umma_desc_none(smem_u32(s_toep), 256, 128);
+      uint32_t tmem_d = tmem_base + stage * 256;
+      const uint64_t da_step = static_cast<uint64_t>(D16_ROWB >> 4), db_step = static_cast<uint64_t>(toep_bytes_c >> 4);
+#pragma unroll 1
+      for (int c = 0; c < DT_CG; ++c) {
+        uint64_t da = da_c, db = db_c;
+        if (leader) umma_bf16_first(tmem_d, da, db, idesc);
+#pragma unroll 1
+        for (int kc = 1; kc < ksteps; ++kc) {
+          da += 2;    // 32 B: the series 16 frames later
+          db += 32;   // 512 B: two K-cores (x 2 N-cores)
+          if (leader) umma_bf16_acc(tmem_d, da, db, idesc);
+        }
+        da_c += da_step;
+        db_c += db_step;
+        tmem_d += 16;
+      }
+      if (leader) {
+        umma_commit(&empty_bar[stage]);
+        umma_commit(&tmem_full_bar[stage]);
+        DT_TRACE(4, it);
+      }
+      __syncwarp();
+    }
+  } else if (warp_idx < 4) {
+    // ===================== epilogue: row = 16 output frames x 16 channels, 2 frames per trip =====================
+    const int row = warp_idx * 32 + lane;
+    const int sl = row >> 6, mr = row & 63;
+    int it = 0;
+    for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
+      const int acc = it & 1;
+      const uint32_t phase = (it >> 1) & 1;
+      const int slot = 2 * idx + sl;
+      int n = 0, tc = 0;
+      bool live = slot < p.slots_per_cg && mr < p.rows_valid;
+      if (live) {
+        n = slot / p.t_chunks;
+        tc = slot - n * p.t_chunks;
+      }
+      const int f0 = tc * p.SL + 16 * mr;
+      live = live && f0 < p.T;
+      const size_t off0 = (static_cast<size_t>(n) * p.T + f0) * p.C + c0;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16) + acc * 256;
+      uint32_t nxt[2][8];  // HAS_ADDEND: the residual-branch gradient rows of the next trip
+      if constexpr (HAS_ADDEND) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) nxt[t][c] = 0u;
+          if (live && f0 + t < p.T) ldg_v8(p.addend + off0 + static_cast<size_t>(t) * p.C, nxt[t]);
+        }
+      }
+      mbar_wait(&tmem_full_bar[acc], phase);
+      tc_fence_after();
+      if (threadIdx.x == 0) DT_TRACE(5, it);
+#pragma unroll 1
+      for (int th = 0; th < 8; ++th) {
+        uint32_t v[DT_CG][2];
+#pragma unroll
+        for (int c = 0; c < DT_CG; ++c) tmem_ld_32x32_x2(taddr + c * 16 + 2 * th, v[c]);
+        uint32_t add[2][8];
+        if constexpr (HAS_ADDEND) {
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) add[t][c] = nxt[t][c];
+          if (th + 1 < 8) {
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) nxt[t][c] = 0u;
+              if (live && f0 + 2 * th + 2 + t < p.T)
+                ldg_v8(p.addend + off0 + static_cast<size_t>(2 * th + 2 + t) * p.C, nxt[t]);
+            }
+          }
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int f = f0 + 2 * th + t;
+          if (live && f < p.T) {
+            const size_t off = off0 + static_cast<size_t>(2 * th + t) * p.C;
+            uint32_t u[8];
+            if constexpr (HAS_ADDEND) {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const float2 av = bf16x2_to_f32x2(add[t][c]);
+                u[c] = f32x2_to_bf16x2(__uint_as_float(v[2 * c][t]) + av.x, __uint_as_float(v[2 * c + 1][t]) + av.y);
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 8; ++c)
+                u[c] = f32x2_to_bf16x2(__uint_as_float(v[2 * c][t]), __uint_as_float(v[2 * c + 1][t]));
+            }
+            stg_v8(p.y + off, u);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (threadIdx.x == 0) DT_TRACE(6, it);
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+  if (threadIdx.x == 0) DT_TRACE(7, 3);
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient, second generation: the MMAs of dwconv_tc_wgrad_body, FOUR producer groups -- group g fills
+// (stage g / 2, operand g % 2: the x series with its halo / the dy series), so both operands of both stages are gathered
+// concurrently instead of one after the other by the same group.  One 128-frame block per warp and trip (32 registers).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_series_block(const __nv_bfloat16* __restrict__ src, int C, int T, int f_base, int ZL,
+                                                  uint8_t* series, int blk, int lane) {
+  const int h = lane >> 4;
+  const int b = lane & 15;
+  const int sigma = blk * 128 + 8 * b;
+  if (sigma >= ZL) return;
+  uint4 r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = f_base + sigma + i;
+    r[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (f >= 0 && f < T) r[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(f) * C + 8 * h));
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint32_t o[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const uint32_t a = (&r[2 * m].x)[q >> 1], bb = (&r[2 * m + 1].x)[q >> 1];
+      o[m] = __byte_perm(a, bb, (q & 1) ? 0x7632 : 0x5410);
+    }
+    *reinterpret_cast<uint4*>(series + (static_cast<size_t>(8 * h + q) * ZL + sigma) * 2) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void __launch_bounds__(D2_THREADS, 1) dwconv_tc_wgrad2_kernel(const DwTcParams p) {
+  pdl_launch_dependents();
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((128u - (raw_addr & 127u)) & 127u);
+  const int xs_bytes = DT_CG * p.ZL * 2;
+  const int dys_bytes = DT_CG * DT_CHUNK * 2;
+  const int stage_bytes = xs_bytes + dys_bytes;
+  uint8_t* s_ser = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ser + 2 * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + 2;
+  uint64_t* done_bar = bars + 4;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cg = blockIdx.x % p.num_cg;
+  const int first = blockIdx.x / p.num_cg;
+  const int c0 = cg * DT_CG;
+  const int P = p.K / 2;
+
+  if (warp_idx == 4 && lane == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&full_bar[s], 8);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp_idx == 5) {
+    tmem_alloc(tmem_ptr_smem, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  const bool has_items = first < p.items_per_cg;
+
+  if (warp_idx >= 6) {
+    const int pw = (warp_idx - 6) & 3;
+    const int grp = (warp_idx - 6) >> 2;
+    const int stage = grp >> 1, which = grp & 1;
+    int it = stage;
+    for (int idx = first + stage * p.ctas_per_cg; idx < p.items_per_cg; idx += 2 * p.ctas_per_cg, it += 2) {
+      const uint32_t phase = (it >> 1) & 1;
+      const int n = idx / p.t_chunks, tc = idx - n * p.t_chunks;
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      uint8_t* base = s_ser + stage * stage_bytes;
+      const size_t uoff = static_cast<size_t>(n) * p.T * p.C + c0;
+      if (which == 0) {
+#pragma unroll 1
+        for (int blk = pw; blk * 128 < p.ZL; blk += 4)
+          load_series_block(p.x + uoff, p.C, p.T, tc * DT_CHUNK - P, p.ZL, base, blk, lane);
+      } else {
+#pragma unroll 1
+        for (int blk = pw; blk * 128 < DT_CHUNK; blk += 4)
+          load_series_block(p.dy + uoff, p.C, p.T, tc * DT_CHUNK, DT_CHUNK, base + xs_bytes, blk, lane);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[stage]);
+    }
+  } else if (warp_idx == 4) {
+    // D[t' (M = 128), t (N = 16)] += sum_w z[8w + t'] dy[8w + t]: A and B both MN-major
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc_bf16(DT_ROWS, 16, 1, 1);
+    int it = 0;
+    for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
+      const int stage = it & 1;
+      const uint32_t phase = (it >> 1) & 1;
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t xs = smem_u32(s_ser + stage * stage_bytes);
+      uint64_t da_c = umma_desc_none(xs, 128, 16);
+      uint64_t db_c = umma_desc_none(xs + xs_bytes, 128, 16);
+      uint32_t tmem_d = tmem_base;
+      const uint64_t da_step = static_cast<uint64_t>(p.ZL * 2 >> 4);
+#pragma unroll 1
+      for (int c = 0; c < DT_CG; ++c) {
+        uint64_t da = da_c, db = db_c;
+        if (leader) {
+          if (it == 0)
+            umma_bf16_first(tmem_d, da, db, idesc);
+          else
+            umma_bf16_acc(tmem_d, da, db, idesc);
+        }
+#pragma unroll
+        for (int kc = 1; kc < DT_CHUNK / 128; ++kc) {
+          da += 16;
+          db += 16;
+          if (leader) umma_bf16_acc(tmem_d, da, db, idesc);
+        }
+        da_c += da_step;
+        db_c += DT_CHUNK * 2 >> 4;
+        tmem_d += 16;
+      }
+      if (leader) umma_commit(&empty_bar[stage]);
+      __syncwarp();
+    }
+    if (leader) umma_commit(done_bar);
+  } else if (warp_idx < 4) {
+    if (has_items) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+      const int tp = warp_idx * 32 + lane;  // t'
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < DT_CG; ++c) {
+        uint32_t v[8];
+        tmem_ld_32x32_x8(taddr + c * 16, v);
+        tmem_ld_wait();
+        if (c0 + c < p.C) {
+          float* dst = p.dw + static_cast<size_t>(c0 + c) * p.K;
+#pragma unroll
+          for (int t = 0; t < 8; ++t) {
+            const int j = tp - t;
+            if (j >= 0 && j < p.K) atomicAdd(dst + j, __uint_as_float(v[t]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
 static void dt_schedule(DwTcParams& p, int sms = kNumSMs) {
@@ -794,6 +1208,7 @@ static int dwconv_tc16_fwd(const void* x, const float* w, void* y, const void* a
   p.KS = cdiv(K + 15, 16) * 16;
   p.flip = flip;
   p.w_early = early_param_loads() ? 1 : 0;
+  p.trace = g_dt_trace;
   p.SL = (D16_SLOTF - p.KS) / 16 * 16;
   p.rows_valid = p.SL / 16;
   p.t_chunks = cdiv(T, p.SL);
@@ -806,6 +1221,29 @@ static int dwconv_tc16_fwd(const void* x, const float* w, void* y, const void* a
   const int rounds = cdiv(p.items_per_cg, per);
   p.ctas_per_cg = cdiv(p.items_per_cg, rounds);
   const int toep = DT_CG * p.KS * 32;
+  static const int v2 = getenv("LASR_DW16_V2") ? atoi(getenv("LASR_DW16_V2")) : 1;
+  if (v2) {
+    p.stages = 2;
+    const int smem2 = 1024 + 2 * D16_STAGE + toep + DT_CG * DT_MAX_KS * 4 + 256;
+    static bool configured2 = false;
+    if (!configured2) {
+      cudaError_t e = cudaFuncSetAttribute(dwconv_tc16v2_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           232448);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(dwconv_tc16v2_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      if (e != cudaSuccess) {
+        lasr_set_cuda_error(e);
+        return LASR_ERR_CUDA;
+      }
+      configured2 = true;
+    }
+    const dim3 grid(p.num_cg * p.ctas_per_cg);
+    if (addend != nullptr)
+      LASR_CHECK_PDL(launch_pdl(2, dwconv_tc16v2_fwd_kernel<true>, grid, dim3(D2_THREADS), smem2, stream, p));
+    else
+      LASR_CHECK_PDL(launch_pdl(2, dwconv_tc16v2_fwd_kernel<false>, grid, dim3(D2_THREADS), smem2, stream, p));
+    return LASR_OK;
+  }
   int stages = (232448 - 1024 - 256 - toep) / D16_STAGE;
   if (stages > 3) stages = 3;
   if (stages < 2) return LASR_ERR_UNSUPPORTED;
@@ -826,7 +1264,7 @@ static int dwconv_tc16_fwd(const void* x, const float* w, void* y, const void* a
 
 int dwconv_tc_fwd(const void* x, const float* w, void* y, const void* addend, int N, int T, int C, int K, int flip,
                   cudaStream_t stream) {
-  static const int dw16 = getenv("LASR_DW16") ? atoi(getenv("LASR_DW16")) : 0;
+  static const int dw16 = getenv("LASR_DW16") ? atoi(getenv("LASR_DW16")) : 1;
   if (dw16 && K + 15 <= 112) {
     const int rc16 = dwconv_tc16_fwd(x, w, y, addend, N, T, C, K, flip, stream);
     if (rc16 != LASR_ERR_UNSUPPORTED) return rc16;
@@ -876,6 +1314,22 @@ int dwconv_tc_wgrad(const void* x, const void* dy, float* dw, int N, int T, int 
   p.ZL = DT_CHUNK + 128;
   dt_schedule(p);
   const int smem = 128 + 2 * (DT_CG * p.ZL * 2 + DT_CG * DT_CHUNK * 2) + 128;
+  static const int wg2 = getenv("LASR_DW_WGRAD2") ? atoi(getenv("LASR_DW_WGRAD2")) : 1;
+  if (wg2) {
+    static bool configured2 = false;
+    if (!configured2) {
+      cudaError_t e =
+          cudaFuncSetAttribute(dwconv_tc_wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      if (e != cudaSuccess) {
+        lasr_set_cuda_error(e);
+        return LASR_ERR_CUDA;
+      }
+      configured2 = true;
+    }
+    LASR_CHECK_PDL(
+        launch_pdl(2, dwconv_tc_wgrad2_kernel, dim3(p.num_cg * p.ctas_per_cg), dim3(D2_THREADS), smem, stream, p));
+    return LASR_OK;
+  }
   static bool configured = false;
   if (!configured) {
     cudaError_t e =
@@ -894,8 +1348,11 @@ int dwconv_tc_wgrad(const void* x, const void* dy, float* dw, int N, int T, int 
 // dx = corr(dy, flipped taps) + addend   and   dw += sum dy * shifted x   in one launch (dwconv_tc_bwd_kernel)
 int dwconv_tc_bwd(const void* x, const void* dy, const float* w, const void* addend, void* dx, float* dw, int N, int T,
                   int C, int K, cudaStream_t stream) {
-  static const bool off = getenv("LASR_DW_GROUPED") != nullptr && atoi(getenv("LASR_DW_GROUPED")) == 0;
-  if (off || g_dt_trace != nullptr) return LASR_ERR_UNSUPPORTED;
+  // one launch for both gradients (8-frame-row bodies) only when asked for: the default data-gradient kernel is the
+  // 16-frame-row one (dwconv_tc16v2_fwd_kernel), launched on its own next to the weight-gradient kernel
+  static const bool dw16 = getenv("LASR_DW16") ? atoi(getenv("LASR_DW16")) != 0 : true;
+  static const bool grouped = getenv("LASR_DW_GROUPED") ? atoi(getenv("LASR_DW_GROUPED")) != 0 : !dw16;
+  if (!grouped || g_dt_trace != nullptr) return LASR_ERR_UNSUPPORTED;
   DwTcParams pd{};
   pd.x = static_cast<const __nv_bfloat16*>(dy);
   pd.w = w;

@@ -9,7 +9,8 @@ lib = _lib.load()
 lib.lasr_debug_set_dw_trace.argtypes = [ctypes.c_void_p]
 lib.lasr_debug_set_dw_trace.restype = None
 N, T = 32, 801
-names = ["prod:start", "prod:stored", "mma:acc_free", "mma:series_full", "mma:issued", "epi:tmem_full", "epi:done"]
+names = ["prod:start", "prod:stored", "mma:acc_free", "mma:series_full", "mma:issued", "epi:tmem_full", "epi:done",
+         "cta:entry/prologue_done/pdl_wait_done/roles_done"]
 for c, k in [(512, 63), (256, 33)]:
     x = torch.randn(N, T, c, device="cuda").bfloat16()
     w = torch.randn(c, 1, k, device="cuda") / k ** 0.5
@@ -21,8 +22,9 @@ for c, k in [(512, 63), (256, 33)]:
     torch.cuda.synchronize()
     lib.lasr_debug_set_dw_trace(None)
     tr = trace.cpu().view(148, 8, 16)
-    t0 = int(tr[:, 0, 0][tr[:, 0, 0] > 0].min())
+    t0 = int(tr[:, 7, 0][tr[:, 7, 0] > 0].min()) if int(tr[:, 7, 0].max()) > 0 else int(tr[:, 0, 0][tr[:, 0, 0] > 0].min())
     print(f"=== C={c} k={k}: last epilogue end {int(tr[:, 6].max()) - t0} ns")
+    print("   CTA entry spread (ns):", int(tr[:, 7, 0][tr[:, 7, 0] > 0].max()) - t0 if int(tr[:, 7, 0].max()) > 0 else None)
     for cta in (0, 77):
         print(f"-- CTA {cta}")
         for slot, nm in enumerate(names):
