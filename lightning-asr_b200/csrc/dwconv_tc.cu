@@ -559,6 +559,34 @@ __device__ __forceinline__ void load_slot_sw32(const __nv_bfloat16* __restrict__
   }
 }
 
+// one 128-frame block of a slot (8 warps cover the slot's 1024 series frames in one trip, 32 registers of loads in flight)
+__device__ __forceinline__ void load_slot_sw32_blk(const __nv_bfloat16* __restrict__ src, int C, int T, int f_base,
+                                                   uint8_t* rows, int blk, int lane) {
+  const int h = lane >> 4;
+  const int b = lane & 15;
+  const int sigma = blk * 128 + 8 * b;
+  uint4 r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int f = f_base + sigma + i;
+    r[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (src != nullptr && f >= 0 && f < T)
+      r[i] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(f) * C + 8 * h));
+  }
+  const uint32_t L = static_cast<uint32_t>(sigma) * 2u;
+  const uint32_t Ls = L ^ (((L >> 7) & 1u) << 4);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint32_t o[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const uint32_t a = (&r[2 * m].x)[q >> 1], bb = (&r[2 * m + 1].x)[q >> 1];
+      o[m] = __byte_perm(a, bb, (q & 1) ? 0x7632 : 0x5410);
+    }
+    *reinterpret_cast<uint4*>(rows + static_cast<size_t>(8 * h + q) * D16_ROWB + Ls) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 struct Dw16Params {
   const __nv_bfloat16* x;
   const float* w;
@@ -786,7 +814,7 @@ __device__ __forceinline__ void tmem_ld_32x32_x2(uint32_t taddr, uint32_t (&v)[2
 }
 
 template <bool HAS_ADDEND>
-__global__ void __launch_bounds__(D2_THREADS, 1) dwconv_tc16v2_fwd_kernel(const Dw16Params p) {
+__device__ __forceinline__ void dwconv_tc16v2_fwd_body(const Dw16Params& p, const int bid) {
   pdl_launch_dependents();
   if (threadIdx.x == 0) DT_TRACE(7, 0);
   extern __shared__ uint8_t smem_raw[];
@@ -805,8 +833,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dwconv_tc16v2_fwd_kernel(const 
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int cg = blockIdx.x % p.num_cg;
-  const int first = blockIdx.x / p.num_cg;
+  const int cg = bid % p.num_cg;
+  const int first = bid / p.num_cg;
   const int c0 = cg * DT_CG;
   const int P = p.K / 2;
 
@@ -817,7 +845,7 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dwconv_tc16v2_fwd_kernel(const 
   }
   if (warp_idx == 4 && lane == 0) {
     for (int st = 0; st < 2; ++st) {
-      mbar_init(&full_bar[st], 8);
+      mbar_init(&full_bar[st], 16);
       mbar_init(&empty_bar[st], 1);
       mbar_init(&tmem_full_bar[st], 1);
       mbar_init(&tmem_empty_bar[st], 4);
@@ -859,15 +887,17 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dwconv_tc16v2_fwd_kernel(const 
   pdl_wait();
 
   if (warp_idx >= 6) {
-    // ===================== producers: group g owns (stage g / 2, slot g % 2) =====================
-    const int pw = (warp_idx - 6) & 3;
-    const int grp = (warp_idx - 6) >> 2;
-    const int stage = grp >> 1, sl = grp & 1;
-    int it = stage;
-    for (int idx = first + stage * p.ctas_per_cg; idx < p.items_per_cg; idx += 2 * p.ctas_per_cg, it += 2) {
+    // ===================== producers: 8 warps per slot, ALL 16 on the same item =====================
+    // (the first item of a CTA is complete after one gather of 51 KB instead of after the gathers of everything the CTA
+    // owns; the next item's gather then overlaps the MMAs and the epilogue of this one)
+    const int blk = (warp_idx - 6) & 7;
+    const int sl = (warp_idx - 6) >> 3;
+    int it = 0;
+    for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
+      const int stage = it & 1;
       const uint32_t phase = (it >> 1) & 1;
       mbar_wait(&empty_bar[stage], phase ^ 1u);
-      if (pw == 0 && lane == 0) DT_TRACE(0, 2 * it + sl);
+      if (blk == 0 && lane == 0) DT_TRACE(0, 2 * it + sl);
       const int slot = 2 * idx + sl;
       const __nv_bfloat16* src = nullptr;
       int f_base = 0;
@@ -876,10 +906,10 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dwconv_tc16v2_fwd_kernel(const 
         src = p.x + static_cast<size_t>(n) * p.T * p.C + c0;
         f_base = tc * p.SL - P;
       }
-      load_slot_sw32(src, p.C, p.T, f_base, s_ser + stage * D16_STAGE + sl * (D16_SLOTF * 2), pw, lane);
+      load_slot_sw32_blk(src, p.C, p.T, f_base, s_ser + stage * D16_STAGE + sl * (D16_SLOTF * 2), blk, lane);
       fence_proxy_async_smem();
       __syncwarp();
-      if (pw == 0 && lane == 0) DT_TRACE(1, 2 * it + sl);
+      if (blk == 0 && lane == 0) DT_TRACE(1, 2 * it + sl);
       if (lane == 0) mbar_arrive(&full_bar[stage]);
     }
   } else if (warp_idx == 4) {
@@ -1041,7 +1071,7 @@ __device__ __forceinline__ void load_series_block(const __nv_bfloat16* __restric
   }
 }
 
-__global__ void __launch_bounds__(D2_THREADS, 1) dwconv_tc_wgrad2_kernel(const DwTcParams p) {
+__device__ __forceinline__ void dwconv_tc_wgrad2_body(const DwTcParams& p, const int bid) {
   pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -1058,8 +1088,8 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dwconv_tc_wgrad2_kernel(const D
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int cg = blockIdx.x % p.num_cg;
-  const int first = blockIdx.x / p.num_cg;
+  const int cg = bid % p.num_cg;
+  const int first = bid / p.num_cg;
   const int c0 = cg * DT_CG;
   const int P = p.K / 2;
 
@@ -1175,6 +1205,26 @@ __global__ void __launch_bounds__(D2_THREADS, 1) dwconv_tc_wgrad2_kernel(const D
   }
 }
 
+template <bool HAS_ADDEND>
+__global__ void __launch_bounds__(D2_THREADS, 1) dwconv_tc16v2_fwd_kernel(const Dw16Params p) {
+  dwconv_tc16v2_fwd_body<HAS_ADDEND>(p, static_cast<int>(blockIdx.x));
+}
+__global__ void __launch_bounds__(D2_THREADS, 1) dwconv_tc_wgrad2_kernel(const DwTcParams p) {
+  dwconv_tc_wgrad2_body(p, static_cast<int>(blockIdx.x));
+}
+// Backward of one depthwise layer in ONE launch (second generation bodies): CTAs [0, split) compute the data gradient
+// (flipped taps + residual addend, 16-frame rows), the rest the weight gradient.  Each half walks twice as many items per
+// CTA as a launch of its own would, so the fixed cost of a launch (ramp, prologue, tail: ~4 us) is paid once per layer
+// and the two halves' slice traffic interleaves on every SM pair.
+template <bool HAS_ADDEND>
+__global__ void __launch_bounds__(D2_THREADS, 1)
+dwconv_tc_bwd2_kernel(const Dw16Params pd, const DwTcParams pw, const int split) {
+  if (static_cast<int>(blockIdx.x) < split)
+    dwconv_tc16v2_fwd_body<HAS_ADDEND>(pd, static_cast<int>(blockIdx.x));
+  else
+    dwconv_tc_wgrad2_body(pw, static_cast<int>(blockIdx.x) - split);
+}
+
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
@@ -1192,6 +1242,34 @@ static void dt_schedule(DwTcParams& p, int sms = kNumSMs) {
 int dwconv_tc_supported(int C, int K, int stride) {
   static const bool off = getenv("LASR_DWCONV_FFMA") != nullptr;  // A/B switch: force the fp32-pipe kernels
   return !off && stride == 1 && (C % DT_CG) == 0 && K >= 3 && (K & 1) && K + 7 <= DT_MAX_KS;
+}
+
+static void dw16_params(Dw16Params& p, const void* x, const float* w, void* y, const void* addend, int N, int T, int C,
+                        int K, int flip, int sms) {
+  p.x = static_cast<const __nv_bfloat16*>(x);
+  p.w = w;
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.addend = static_cast<const __nv_bfloat16*>(addend);
+  p.N = N;
+  p.T = T;
+  p.C = C;
+  p.K = K;
+  p.KS = cdiv(K + 15, 16) * 16;
+  p.flip = flip;
+  p.w_early = early_param_loads() ? 1 : 0;
+  p.trace = g_dt_trace;
+  p.SL = (D16_SLOTF - p.KS) / 16 * 16;
+  p.rows_valid = p.SL / 16;
+  p.t_chunks = cdiv(T, p.SL);
+  p.slots_per_cg = N * p.t_chunks;
+  p.items_per_cg = cdiv(p.slots_per_cg, 2);
+  p.num_cg = cdiv(C, DT_CG);
+  int per = sms / p.num_cg;
+  if (per < 1) per = 1;
+  if (per > p.items_per_cg) per = p.items_per_cg;
+  const int rounds = cdiv(p.items_per_cg, per);
+  p.ctas_per_cg = cdiv(p.items_per_cg, rounds);
+  p.stages = 2;
 }
 
 static int dwconv_tc16_fwd(const void* x, const float* w, void* y, const void* addend, int N, int T, int C, int K,
@@ -1351,8 +1429,46 @@ int dwconv_tc_bwd(const void* x, const void* dy, const float* w, const void* add
   // one launch for both gradients (8-frame-row bodies) only when asked for: the default data-gradient kernel is the
   // 16-frame-row one (dwconv_tc16v2_fwd_kernel), launched on its own next to the weight-gradient kernel
   static const bool dw16 = getenv("LASR_DW16") ? atoi(getenv("LASR_DW16")) != 0 : true;
-  static const bool grouped = getenv("LASR_DW_GROUPED") ? atoi(getenv("LASR_DW_GROUPED")) != 0 : !dw16;
+  static const bool grouped = getenv("LASR_DW_GROUPED") ? atoi(getenv("LASR_DW_GROUPED")) != 0 : true;
   if (!grouped || g_dt_trace != nullptr) return LASR_ERR_UNSUPPORTED;
+  if (dw16 && K + 15 <= 112) {
+    // second-generation bodies: 16-frame-row data gradient + 4-group weight gradient behind one blockIdx split
+    Dw16Params pd{};
+    dw16_params(pd, dy, w, dx, addend, N, T, C, K, 1, kNumSMs / 2);
+    DwTcParams pw{};
+    pw.x = static_cast<const __nv_bfloat16*>(x);
+    pw.dy = static_cast<const __nv_bfloat16*>(dy);
+    pw.dw = dw;
+    pw.N = N;
+    pw.T = T;
+    pw.C = C;
+    pw.K = K;
+    pw.KS = 0;
+    pw.ZL = DT_CHUNK + 128;
+    dt_schedule(pw, kNumSMs / 2);
+    const int smem_d = 1024 + 2 * D16_STAGE + DT_CG * pd.KS * 32 + DT_CG * DT_MAX_KS * 4 + 256;
+    const int smem_w = 128 + 2 * (DT_CG * pw.ZL * 2 + DT_CG * DT_CHUNK * 2) + 128;
+    const int smem = smem_d > smem_w ? smem_d : smem_w;
+    static bool configured2 = false;
+    if (!configured2) {
+      cudaError_t e =
+          cudaFuncSetAttribute(dwconv_tc_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(dwconv_tc_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+      if (e != cudaSuccess) {
+        lasr_set_cuda_error(e);
+        return LASR_ERR_CUDA;
+      }
+      configured2 = true;
+    }
+    const int split = pd.num_cg * pd.ctas_per_cg;
+    const dim3 grid(split + pw.num_cg * pw.ctas_per_cg);
+    if (addend != nullptr)
+      LASR_CHECK_PDL(launch_pdl(2, dwconv_tc_bwd2_kernel<true>, grid, dim3(D2_THREADS), smem, stream, pd, pw, split));
+    else
+      LASR_CHECK_PDL(launch_pdl(2, dwconv_tc_bwd2_kernel<false>, grid, dim3(D2_THREADS), smem, stream, pd, pw, split));
+    return LASR_OK;
+  }
   DwTcParams pd{};
   pd.x = static_cast<const __nv_bfloat16*>(dy);
   pd.w = w;
