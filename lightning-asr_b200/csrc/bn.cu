@@ -188,7 +188,7 @@ __global__ void bn_coeffs_kernel(const lasr_bn_t bn, int C, double count, float 
 // persistent CTAs of 512 threads; smem: scale1, shift1, scale2, shift2 [C] each
 // ------------------------------------------------------------------------------------------------
 template <typename T, bool HAS_R, bool HAS_GATE, bool HAS_DROP>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(256, 2)
 bn_apply_fwd_kernel(const T* __restrict__ y, const lasr_bn_t bn1, const T* __restrict__ r, const lasr_bn_t bn2,
                     const float* __restrict__ gate, T* __restrict__ out, long long total_vec, int CV, int C, int T_len,
                     double count, float eps, float momentum, int act, int side_effects, const DropArgs drop) {
@@ -218,16 +218,33 @@ bn_apply_fwd_kernel(const T* __restrict__ y, const lasr_bn_t bn1, const T* __res
     }
   }
   __syncthreads();
+  // Every thread owns ONE 8-channel vector position (cv) for its whole life and walks rows: its coefficients live in
+  // registers.  (Round 1 re-read them from shared memory for every vector -- 2-6 LDS.128 per 16 bytes of activation, which
+  // made the pass L1TEX-bound at 85 % while HBM idled at ~50 %, ncu r1f -- and paid a 64-bit division per vector.)
   using Raw = typename Vec8<T>::Raw;
-  constexpr int U = sizeof(T) == 2 ? 4 : 2;  // vectors per thread and trip, all loads issued before the first use
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long v0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v0 < total_vec; v0 += U * stride) {
+  constexpr int U = sizeof(T) == 2 ? 4 : 2;  // rows per thread and trip, all loads issued before the first use
+  const int rpb = static_cast<int>(blockDim.x) / CV;  // rows per CTA and trip
+  const int r_in = static_cast<int>(threadIdx.x) / CV;
+  const int cv = static_cast<int>(threadIdx.x) - r_in * CV;
+  if (r_in >= rpb) return;
+  const int c = cv * 8;
+  const int rows = static_cast<int>(total_vec / CV);
+  float sc1[8], sh1[8], sc2[8], sh2[8];
+  lds8(s_scale1 + c, sc1);
+  lds8(s_shift1 + c, sh1);
+  if constexpr (HAS_R) {
+    lds8(s_scale2 + c, sc2);
+    lds8(s_shift2 + c, sh2);
+  }
+  const int row_stride = static_cast<int>(gridDim.x) * rpb;
+  for (int row0 = static_cast<int>(blockIdx.x) * rpb + r_in; row0 < rows; row0 += U * row_stride) {
     Raw ya[U], ra[U];
     uint2 ma[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long v = v0 + u * stride;
-      if (v < total_vec) {
+      const int row = row0 + u * row_stride;
+      if (row < rows) {
+        const long long v = static_cast<long long>(row) * CV + cv;
         ya[u] = Vec8<T>::ldraw(y + v * 8);  // element offset row*C + c == 8*v
         if constexpr (HAS_R) ra[u] = Vec8<T>::ldraw(r + v * 8);
         if constexpr (HAS_DROP) {
@@ -237,21 +254,15 @@ bn_apply_fwd_kernel(const T* __restrict__ y, const lasr_bn_t bn1, const T* __res
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long v = v0 + u * stride;
-      if (v >= total_vec) break;
-      const long long row = v / CV;
-      const int c = static_cast<int>(v - row * CV) * 8;
+      const int row = row0 + u * row_stride;
+      if (row >= rows) break;
+      const long long v = static_cast<long long>(row) * CV + cv;
       float a[8], o[8];
       Vec8<T>::unpack(ya[u], a);
-      {
-        float sc[8], sh[8];
-        lds8(s_scale1 + c, sc);
-        lds8(s_shift1 + c, sh);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = fmaf(a[i], sc[i], sh[i]);
-      }
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(a[i], sc1[i], sh1[i]);
       if constexpr (HAS_GATE) {
-        const int n = static_cast<int>(row / T_len);
+        const int n = row / T_len;
         float g[8];
         load8f(gate + static_cast<size_t>(n) * C + c, g);
 #pragma unroll
@@ -270,12 +281,10 @@ bn_apply_fwd_kernel(const T* __restrict__ y, const lasr_bn_t bn1, const T* __res
         for (int i = 0; i < 8; ++i) o[i] *= f[i];
       }
       if constexpr (HAS_R) {
-        float rr[8], sc[8], sh[8];
+        float rr[8];
         Vec8<T>::unpack(ra[u], rr);
-        lds8(s_scale2 + c, sc);
-        lds8(s_shift2 + c, sh);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] += fmaf(rr[i], sc[i], sh[i]);
+        for (int i = 0; i < 8; ++i) o[i] += fmaf(rr[i], sc2[i], sh2[i]);
       }
       if (act == LASR_ACT_RELU) {
 #pragma unroll
@@ -342,7 +351,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
   for (int i = 0; i < 8; ++i) sg[i] = sgy[i] = sgr[i] = sg1[i] = 0.f;
   if (tr < rows_par) {
     using Raw = typename Vec8<T>::Raw;
-    constexpr int U = sizeof(T) == 2 ? 2 : 1;  // rows per trip: up to 8 independent 16-byte loads in flight per thread
+    constexpr int U = sizeof(T) == 2 ? 4 : 2;  // rows per trip: up to 16 independent 16-byte loads in flight per thread
     const T* base_g = dout + static_cast<size_t>(n) * T_len * C + cv * 8;
     const T* base_y = y + static_cast<size_t>(n) * T_len * C + cv * 8;
     const T* base_o = out + static_cast<size_t>(n) * T_len * C + cv * 8;
@@ -472,7 +481,7 @@ struct BnBwdSide {
 };
 
 template <typename T, bool HAS_R, bool HAS_GATE, bool HAS_DROP>
-__global__ void __launch_bounds__(512, 2)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const T* __restrict__ y,
                     const T* __restrict__ r, const float* __restrict__ gate, const float* __restrict__ extra,
                     const double* __restrict__ totals, const float* __restrict__ coef1_in, const BnBwdSide bn1,
@@ -531,24 +540,39 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
     }
   }
   __syncthreads();
+  // one 8-channel vector position per thread for its whole life, coefficients in registers (see bn_apply_fwd_kernel)
   using Raw = typename Vec8<T>::Raw;
   constexpr int U = sizeof(T) == 2 ? 2 : 1;
   const bool relu = act == LASR_ACT_RELU;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long v0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; v0 < total_vec; v0 += U * stride) {
+  const int rpb = static_cast<int>(blockDim.x) / CV;
+  const int r_in = static_cast<int>(threadIdx.x) / CV;
+  const int cv = static_cast<int>(threadIdx.x) - r_in * CV;
+  if (r_in >= rpb) return;
+  const int c = cv * 8;
+  const int rows = static_cast<int>(total_vec / CV);
+  float a0[8], a1[8], a2[8], b0[8], b1[8], b2[8];
+  lds8(k1 + c, a0);
+  lds8(k1 + C + c, a1);
+  lds8(k1 + 2 * C + c, a2);
+  if constexpr (HAS_R) {
+    lds8(k2 + c, b0);
+    lds8(k2 + C + c, b1);
+    lds8(k2 + 2 * C + c, b2);
+  }
+  const int row_stride = static_cast<int>(gridDim.x) * rpb;
+  for (int row0 = static_cast<int>(blockIdx.x) * rpb + r_in; row0 < rows; row0 += U * row_stride) {
     Raw gr[U], orr[U], yr[U], rrr[U];
     uint2 mr[U];
     bool keep_u[U];
-    int n_u[U], c_u[U];
+    int n_u[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long v = v0 + u * stride;
+      const int row = row0 + u * row_stride;
       keep_u[u] = false;
-      if (v < total_vec) {
-        const long long row = v / CV;
-        c_u[u] = static_cast<int>(v - row * CV) * 8;
-        n_u[u] = static_cast<int>(row / T_len);
-        const int t = static_cast<int>(row - static_cast<long long>(n_u[u]) * T_len);
+      if (row < rows) {
+        const long long v = static_cast<long long>(row) * CV + cv;
+        n_u[u] = row / T_len;
+        const int t = row - n_u[u] * T_len;
         keep_u[u] = lengths == nullptr || t < lengths[n_u[u]];
         gr[u] = Vec8<T>::ldraw(dout + v * 8);
         if (relu) orr[u] = Vec8<T>::ldraw(out + v * 8);
@@ -559,9 +583,10 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long v = v0 + u * stride;
-      if (v >= total_vec) break;
-      const int c = c_u[u], n = n_u[u];
+      const int row = row0 + u * row_stride;
+      if (row >= rows) break;
+      const long long v = static_cast<long long>(row) * CV + cv;
+      const int n = n_u[u];
       const bool keep = keep_u[u];
       float g[8];
       Vec8<T>::unpack(gr[u], g);
@@ -572,13 +597,10 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
         for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
       }
       if constexpr (HAS_R) {
-        float rr[8], a0[8], a1[8], a2[8], d[8];
+        float rr[8], d[8];
         Vec8<T>::unpack(rrr[u], rr);
-        lds8(k2 + c, a0);
-        lds8(k2 + C + c, a1);
-        lds8(k2 + 2 * C + c, a2);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] = fmaf(a0[i], g[i], fmaf(a1[i], rr[i], a2[i]));
+        for (int i = 0; i < 8; ++i) d[i] = fmaf(b0[i], g[i], fmaf(b1[i], rr[i], b2[i]));
         Vec8<T>::store(dr + v * 8, d);
       }
       float d[8];
@@ -598,10 +620,6 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
 #pragma unroll
           for (int i = 0; i < 8; ++i) g[i] = fmaf(g[i], gt[i], ex[i]);
         }
-        float a0[8], a1[8], a2[8];
-        lds8(k1 + c, a0);
-        lds8(k1 + C + c, a1);
-        lds8(k1 + 2 * C + c, a2);
 #pragma unroll
         for (int i = 0; i < 8; ++i) d[i] = fmaf(a0[i], g[i], fmaf(a1[i], yy[i], a2[i]));
       } else {
@@ -613,6 +631,8 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
   }
 }
 
+constexpr int BN_THREADS = 256;  // 2 CTAs / SM x 256 threads x <= 128 registers: coefficients + 8 vectors in flight per thread
+static inline int bn_block(int CV) { return CV >= BN_THREADS ? CV : BN_THREADS / CV * CV; }
 static inline int persistent_grid(long long total_vec, int threads) {
   long long b = (total_vec + threads - 1) / threads;
   const long long cap = 2LL * kNumSMs;
@@ -623,14 +643,15 @@ template <typename TT>
 static int bn_fwd_launch(const void* y, const lasr_bn_t& b1, const void* r, const lasr_bn_t& b2, const float* gate,
                          void* out, long long total, int CV, int C, int T, double count, float eps, float momentum,
                          int act, int side_effects, const DropArgs& drop, cudaStream_t stream) {
-  const int grid = persistent_grid(total, 512);
+  const int threads = bn_block(CV);
+  const int grid = persistent_grid(total, threads);
   const int smem = 4 * C * static_cast<int>(sizeof(float));
   const TT* yy = static_cast<const TT*>(y);
   const TT* rr = static_cast<const TT*>(r);
   TT* oo = static_cast<TT*>(out);
   cudaError_t le;
 #define LASR_BN_FWD(R, G, D)                                                                                      \
-  le = launch_pdl(4, bn_apply_fwd_kernel<TT, R, G, D>, dim3(grid), dim3(512), smem, stream, yy, b1, rr, b2, gate, oo, \
+  le = launch_pdl(4, bn_apply_fwd_kernel<TT, R, G, D>, dim3(grid), dim3(threads), smem, stream, yy, b1, rr, b2, gate, oo, \
                   total, CV, C, T, count, eps, momentum, act, side_effects, drop)
   const int sel = (r != nullptr ? 4 : 0) | (gate != nullptr ? 2 : 0) | (drop.mode != 0 ? 1 : 0);
   switch (sel) {
@@ -654,7 +675,8 @@ static int bn_bwd_launch(const void* dout, const void* out, const void* y, const
                          const BnBwdSide& s2, double count, const int32_t* lengths, int T, void* dy, void* dr,
                          long long total, int CV, int C, int act, const uint8_t* drop_mask, float drop_scale,
                          cudaStream_t stream) {
-  const int grid = persistent_grid(total, 512);
+  const int threads = bn_block(CV);
+  const int grid = persistent_grid(total, threads);
   const int smem = 6 * C * static_cast<int>(sizeof(float));
   const TT* a0 = static_cast<const TT*>(dout);
   const TT* a1 = static_cast<const TT*>(out);
@@ -664,7 +686,7 @@ static int bn_bwd_launch(const void* dout, const void* out, const void* y, const
   TT* o1 = static_cast<TT*>(dr);
   cudaError_t le;
 #define LASR_BN_BWD(R, G, D)                                                                                       \
-  le = launch_pdl(4, bn_bwd_apply_kernel<TT, R, G, D>, dim3(grid), dim3(512), smem, stream, a0, a1, a2, a3, gate,   \
+  le = launch_pdl(4, bn_bwd_apply_kernel<TT, R, G, D>, dim3(grid), dim3(threads), smem, stream, a0, a1, a2, a3, gate,   \
                   extra, totals, coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, act, drop_mask, drop_scale)
   const int sel = (r != nullptr ? 4 : 0) | (gate != nullptr ? 2 : 0) | (drop_mask != nullptr ? 1 : 0);
   switch (sel) {
