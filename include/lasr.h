@@ -267,6 +267,24 @@ int lasr_logmel_prepare_crop(const float* wave, const float* dither, const int32
                              lasr_stream_t stream);
 int lasr_spec_augment(float* db, double* stats, const int32_t* num_samples, const int32_t* bands, int N, int T_max,
                       lasr_stream_t stream);
+/* prepare with the waveform taken as it travels: wave_dtype LASR_WAVE_F32 ([-1, 1] floats) or LASR_WAVE_I16 (16-bit PCM,
+ * x / 32768 like torchaudio.load(normalize=True), data_module.py:153 -- half the H2D bytes of fp32 samples).
+ * Dither (data_module.py:155): `dither` [N, S_max] supplied by the caller, or drawn in the kernel (standard normal from
+ * Philox keyed by dither_seed + *seed_dev, utterance, sample) when dither == NULL and dither_seed != 0.  seed_dev: a
+ * device step counter, so a replayed CUDA graph draws fresh noise.  starts NULL = no crop. */
+enum { LASR_WAVE_F32 = 0, LASR_WAVE_I16 = 1 };
+int lasr_logmel_prepare_wave(const void* wave, int wave_dtype, const float* dither, uint64_t dither_seed,
+                             const uint64_t* seed_dev, const int32_t* starts, const int32_t* num_samples, void* parts,
+                             int N, int S_max, int T_max, lasr_stream_t stream);
+/* The random draws of parse_audio(mask=True) on the device, in the reference's order and arithmetic (sub_secquence
+ * data_module.py:138-148, spec_augment :97-122): num_samples [N] = whole-utterance sample counts ->
+ * starts / kept [N] (the arguments of prepare_crop / prepare_wave), bands [N, 4] (the argument of lasr_spec_augment),
+ * percents [N] = T_n / T_max (nullable; data_module.py:244 with the batch padded to T_max frames).
+ * uniforms [N, 6] double (nullable) = the six random() values per utterance (parity hook); otherwise Philox keyed by
+ * seed + *seed_dev.  crop / spec switch the two augmentations off individually (kept = num_samples, empty bands). */
+int lasr_augment_draw(const int32_t* num_samples, const double* uniforms, uint64_t seed, const uint64_t* seed_dev,
+                      int32_t* starts, int32_t* kept, int32_t* bands, float* percents, int N, int T_max, int crop,
+                      int spec, lasr_stream_t stream);
 int lasr_logmel_fwd(const void* parts, const void* basis, const int32_t* mel_idx, const float* mel_w,
                     const int32_t* num_samples, float* db, double* stats, int N, int T_max, int products,
                     lasr_stream_t stream);

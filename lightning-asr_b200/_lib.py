@@ -2,7 +2,7 @@
 
 There is deliberately NO fallback: if the shared library is missing, or the device is not an
 sm_100 part, every op raises.  Signatures are spelled with one character per argument:
-  p = device pointer (torch.Tensor / int / None), i = int, f = float, z = size_t, s = cudaStream_t
+  p = device pointer (torch.Tensor / int / None), i = int, f = float, z = size_t, q = uint64_t, s = cudaStream_t
 """
 import ctypes
 import os
@@ -37,6 +37,8 @@ def _parse_header(path):
                     codes += "p"
                 elif a.startswith("size_t"):
                     codes += "z"
+                elif a.startswith("uint64_t"):
+                    codes += "q"
                 elif a.startswith("float"):
                     codes += "f"
                 elif a.startswith("int") or a.startswith("int32_t"):
@@ -56,6 +58,7 @@ _CODES = {
     "i": ctypes.c_int,
     "f": ctypes.c_float,
     "z": ctypes.c_size_t,
+    "q": ctypes.c_uint64,
     "s": ctypes.c_void_p,
 }
 
@@ -120,6 +123,8 @@ def call(name, *args):
             conv.append(_ptr(a))
         elif c == "f":
             conv.append(float(a))
+        elif c == "q":
+            conv.append(int(a) & 0xFFFFFFFFFFFFFFFF)
         else:
             conv.append(int(a))
     conv.append(stream_ptr())

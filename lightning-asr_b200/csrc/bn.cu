@@ -75,17 +75,6 @@ struct DropArgs {
   const unsigned long long* seed_dev;  // nullable: a device-resident step counter added to the seed (CUDA-graph replays
                                        // must not repeat the mask, and kernel arguments are frozen at capture)
 };
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += 0x9E3779B9u;
-    key.y += 0xBB67AE85u;
-  }
-  return ctr;
-}
 // the 8 keep bytes of vector v (8 consecutive channels of one row)
 __device__ __forceinline__ uint2 drop_generate(const DropArgs& d, long long v) {
   const unsigned long long seed = d.seed + (d.seed_dev != nullptr ? __ldg(d.seed_dev) : 0ull);

@@ -39,7 +39,29 @@ __device__ __forceinline__ int lm_frames(int num_samples) { return 1 + (num_samp
 // ------------------------------------------------------------------------------------------------
 // prepare: parts[p][n][k] = bf16 term p of e_n[k], k < Lp
 // ------------------------------------------------------------------------------------------------
-__global__ void logmel_prepare_kernel(const float* __restrict__ wave, const float* __restrict__ dither,
+template <typename W>
+__device__ __forceinline__ float lm_sample_f32(W v);
+template <>
+__device__ __forceinline__ float lm_sample_f32<float>(float v) { return v; }
+// 16-bit PCM -> [-1, 1): torchaudio.load(normalize=True) divides by 32768 (data_module.py:153)
+template <>
+__device__ __forceinline__ float lm_sample_f32<int16_t>(int16_t v) { return static_cast<float>(v) * (1.0f / 32768.0f); }
+
+// standard normal deviate of (seed, utterance, sample): the device-side dither `torch.randn_like(y)` of data_module.py:155
+// (the reference's stream is unseeded; this one is a pure function of its key, so sample(s) and sample(s-1) agree
+// between neighbouring threads)
+__device__ __forceinline__ float lm_dither_normal(unsigned long long seed, int n, int i) {
+  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(i), static_cast<uint32_t>(n), 0x6d656cu, 0u),
+                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+  const float u1 = (static_cast<float>(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = (static_cast<float>(r.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+template <typename W>
+__global__ void logmel_prepare_kernel(const W* __restrict__ wave, const float* __restrict__ dither,
+                                      const unsigned long long dither_seed,
+                                      const unsigned long long* __restrict__ seed_dev,
                                       const int32_t* __restrict__ starts, const int32_t* __restrict__ num_samples,
                                       __nv_bfloat16* __restrict__ parts, int N, int S_max, int Lp) {
   const int n = blockIdx.y;
@@ -49,8 +71,10 @@ __global__ void logmel_prepare_kernel(const float* __restrict__ wave, const floa
   // utterance: the cropped stream starts at sample `st` of the pre-emphasised signal, so its first sample still sees
   // its predecessor
   const int st = starts != nullptr ? starts[n] : 0;
-  const float* w = wave + static_cast<size_t>(n) * S_max + st;
+  const W* w = wave + static_cast<size_t>(n) * S_max + st;
   const float* dth = dither ? dither + static_cast<size_t>(n) * S_max + st : nullptr;
+  const bool gen = dither == nullptr && dither_seed != 0ull;
+  const unsigned long long seed = dither_seed + (seed_dev != nullptr ? __ldg(seed_dev) : 0ull);
   const size_t plane = static_cast<size_t>(N) * Lp;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < Lp; k += gridDim.x * blockDim.x) {
     // k + 96 indexes the reflect-padded stream; j indexes the zero-padded one
@@ -62,8 +86,9 @@ __global__ void logmel_prepare_kernel(const float* __restrict__ wave, const floa
       const int s = j - LM_PAD;
       if (s >= 0 && s < S) {
         auto sample = [&](int i) {
-          float x = w[i];
+          float x = lm_sample_f32<W>(w[i]);
           if (dth) x = __fadd_rn(x, __fmul_rn(1e-5f, dth[i]));  // y += 1e-5 * randn  (data_module.py:155)
+          if (gen) x = __fadd_rn(x, __fmul_rn(1e-5f, lm_dither_normal(seed, n, st + i)));
           return x;
         };
         v = sample(s);
@@ -349,6 +374,67 @@ spec_augment_kernel(float* __restrict__ db, double* __restrict__ stats, const in
 }
 
 // ------------------------------------------------------------------------------------------------
+// The random draws of parse_audio(mask=True) for one utterance, on the device: restates the arithmetic
+// of sub_secquence(weight=0.98) (data_module.py:138-148) and spec_augment(freq_mask=27, time_mask=0.07) (:97-122) in
+// the reference's draw order, random.uniform(a, b) = a + (b - a) * random() in double precision:
+//   target_length = int(S * U(0.98, 1));  location = int(U(0, S - target_length));  kept = max(target_length - location, 0)
+//   T = 1 + (kept + 64) / 160;  w_x = int(U(0, 27));  w_y = int(U(0, int(T * 0.07)));
+//   rect_x = int(U(0, 64 - w_x));  rect_y = int(U(0, T - w_y))
+// `uniforms` [N, 6] double (nullable): the six random() values per utterance supplied by the caller (parity hook: feed
+// the reference's own seeded random.Random() stream); otherwise Philox keyed by (seed + *seed_dev, utterance).
+// crop == 0 keeps the whole utterance, spec == 0 writes empty bands.  percents[n] = T_n / T_max (data_module.py:244).
+// ------------------------------------------------------------------------------------------------
+__global__ void augment_draw_kernel(const int32_t* __restrict__ num_samples, const double* __restrict__ uniforms,
+                                    unsigned long long seed, const unsigned long long* __restrict__ seed_dev,
+                                    int32_t* __restrict__ starts, int32_t* __restrict__ kept, int32_t* __restrict__ bands,
+                                    float* __restrict__ percents, int N, int T_max, int crop, int spec) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double u[6];
+  if (uniforms != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) u[i] = uniforms[6 * n + i];
+  } else {
+    const unsigned long long sd = seed + (seed_dev != nullptr ? __ldg(seed_dev) : 0ull);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(n), static_cast<uint32_t>(h), 0x617567u, 0u),
+                                    make_uint2(static_cast<uint32_t>(sd), static_cast<uint32_t>(sd >> 32)));
+      // 53-bit uniforms in [0, 1) like Python's random(): (a >> 5) * 2^26 + (b >> 6), / 2^53 -- three per Philox call
+      // would need 6 words; use 2 x (27 + 26 bits) from (x, y), (z, w) and a third from a second lane of the counter
+      u[3 * h + 0] = (static_cast<double>(r.x >> 5) * 67108864.0 + static_cast<double>(r.y >> 6)) * (1.0 / 9007199254740992.0);
+      u[3 * h + 1] = (static_cast<double>(r.z >> 5) * 67108864.0 + static_cast<double>(r.w >> 6)) * (1.0 / 9007199254740992.0);
+      const uint4 q = philox4x32_10(make_uint4(static_cast<uint32_t>(n), static_cast<uint32_t>(h), 0x617567u, 1u),
+                                    make_uint2(static_cast<uint32_t>(sd), static_cast<uint32_t>(sd >> 32)));
+      u[3 * h + 2] = (static_cast<double>(q.x >> 5) * 67108864.0 + static_cast<double>(q.y >> 6)) * (1.0 / 9007199254740992.0);
+    }
+  }
+  const int S = num_samples[n];
+  int loc = 0, k = S;
+  if (crop) {
+    const int target_length = static_cast<int>(static_cast<double>(S) * (0.98 + (1.0 - 0.98) * u[0]));
+    loc = static_cast<int>(0.0 + (static_cast<double>(S - target_length) - 0.0) * u[1]);
+    k = target_length - loc;
+    if (k < 0) k = 0;
+  }
+  const int T = lm_frames(k);
+  int w_x = 0, w_y = 0, rect_x = 0, rect_y = 0;
+  if (spec) {
+    w_x = static_cast<int>(27.0 * u[2]);
+    w_y = static_cast<int>(static_cast<double>(static_cast<int>(static_cast<double>(T) * 0.07)) * u[3]);
+    rect_x = static_cast<int>(static_cast<double>(LM_MELS - w_x) * u[4]);
+    rect_y = static_cast<int>(static_cast<double>(T - w_y) * u[5]);
+  }
+  starts[n] = loc;
+  kept[n] = k;
+  bands[4 * n + 0] = rect_x;
+  bands[4 * n + 1] = w_x;
+  bands[4 * n + 2] = rect_y;
+  bands[4 * n + 3] = w_y;
+  if (percents != nullptr) percents[n] = static_cast<float>(static_cast<double>(T) / static_cast<double>(T_max));
+}
+
+// ------------------------------------------------------------------------------------------------
 template <typename OutT>
 __global__ void logmel_normalize_kernel(const float* __restrict__ db, const double* __restrict__ stats,
                                         const int32_t* __restrict__ num_samples, float* __restrict__ out_nct,
@@ -393,10 +479,38 @@ int lasr_logmel_prepare_crop(const float* wave, const float* dither, const int32
                              const int32_t* num_samples, void* parts, int N, int S_max, int T_max,
                              lasr_stream_t stream) {
   if (N <= 0 || S_max <= 0 || T_max <= 0) return LASR_ERR_BAD_SHAPE;
+  return lasr_logmel_prepare_wave(wave, LASR_WAVE_F32, dither, 0ull, nullptr, starts, num_samples, parts, N, S_max, T_max,
+                                 stream);
+}
+
+int lasr_logmel_prepare_wave(const void* wave, int wave_dtype, const float* dither, uint64_t dither_seed,
+                             const uint64_t* seed_dev, const int32_t* starts, const int32_t* num_samples, void* parts,
+                             int N, int S_max, int T_max, lasr_stream_t stream) {
+  if (N <= 0 || S_max <= 0 || T_max <= 0 || wave == nullptr) return LASR_ERR_BAD_SHAPE;
   const int Lp = lasr_logmel_padded_len(T_max);
   dim3 grid(cdiv(Lp, 256 * 4) < 1 ? 1 : cdiv(Lp, 256 * 4), N);
-  logmel_prepare_kernel<<<grid, 256, 0, stream>>>(wave, dither, starts, num_samples,
-                                                  static_cast<__nv_bfloat16*>(parts), N, S_max, Lp);
+  const unsigned long long* sd = reinterpret_cast<const unsigned long long*>(seed_dev);
+  if (wave_dtype == LASR_WAVE_F32)
+    logmel_prepare_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(wave), dither, dither_seed, sd, starts,
+                                                           num_samples, static_cast<__nv_bfloat16*>(parts), N, S_max, Lp);
+  else if (wave_dtype == LASR_WAVE_I16)
+    logmel_prepare_kernel<int16_t><<<grid, 256, 0, stream>>>(static_cast<const int16_t*>(wave), dither, dither_seed, sd,
+                                                             starts, num_samples, static_cast<__nv_bfloat16*>(parts), N,
+                                                             S_max, Lp);
+  else
+    return LASR_ERR_BAD_DTYPE;
+  LASR_CHECK_LAUNCH();
+  return LASR_OK;
+}
+
+int lasr_augment_draw(const int32_t* num_samples, const double* uniforms, uint64_t seed, const uint64_t* seed_dev,
+                      int32_t* starts, int32_t* kept, int32_t* bands, float* percents, int N, int T_max, int crop,
+                      int spec, lasr_stream_t stream) {
+  if (N <= 0 || T_max <= 0 || num_samples == nullptr || starts == nullptr || kept == nullptr || bands == nullptr)
+    return LASR_ERR_BAD_SHAPE;
+  augment_draw_kernel<<<cdiv(N, 128), 128, 0, stream>>>(num_samples, uniforms, seed,
+                                                        reinterpret_cast<const unsigned long long*>(seed_dev), starts,
+                                                        kept, bands, percents, N, T_max, crop, spec);
   LASR_CHECK_LAUNCH();
   return LASR_OK;
 }

@@ -8,7 +8,10 @@ All arithmetic runs in csrc/logmel.cu (tcgen05 windowed-DFT GEMM, error-compensa
 constant tables (window x DFT basis split in three bf16 terms, sparse HTK mel filterbank) once per device.
 The reference runs this per utterance on CPU DataLoader workers; here it is batched on the GPU and can emit the
 encoder's channels-last input directly (out_ntc).  Random train-time augmentation (crop :158-159, SpecAugment
-:163-165) uses an unseeded host RNG in the reference and is not part of the parity contract.
+:163-165) runs on the device too: the draws restate the reference's arithmetic (draw_augment on the host with any
+random.Random, lasr_augment_draw on the device with Philox or caller-supplied uniforms) and are pinned to the
+reference's own parse_audio(mask=True) by tests/golden/augment.pt.  DeviceFrontend is the static-buffer, CUDA-graph
+capturable pipeline TrainEngine runs inside its step: int16 PCM on the wire, features never leave the device.
 """
 import math
 
@@ -150,6 +153,60 @@ def logmel_batch(waves, num_samples, dither=None, out_dtype=None, want_nct=True,
             "db": db}
 
 
+class DeviceFrontend:
+    """waveforms resident on the device -> channels-last log-mel features, all buffers static (CUDA-graph capturable):
+
+        feats [N, T_max, 64] out_dtype, percents [N] fp32 = DeviceFrontend(...)(waves [N, S_max], num_samples [N] int32)
+
+    waves: int16 PCM (x / 32768, what torchaudio.load(normalize=True) yields, data_module.py:153) or fp32 in [-1, 1].
+    T_max = frames of S_max samples: the batch is padded to the bucket length, percents[n] = T_n / T_max (:244).
+    augment=True: train-time crop + SpecAugment drawn on the device (lasr_augment_draw: the reference's arithmetic, Philox
+    keyed by seed + the bank's step counter, or `uniforms` [N, 6] fp64 supplied per call = the parity hook);
+    dither=True: y += 1e-5 * N(0, 1) drawn in the prepare kernel (:155)."""
+
+    def __init__(self, N, S_max, device, out_dtype, augment=False, dither=False, seed=0x6C617372, seed_dev=None):
+        self.N, self.S_max, self.dev, self.out_dtype = N, S_max, torch.device(device), out_dtype
+        self.augment, self.dither, self.seed, self.seed_dev = augment, dither, int(seed), seed_dev
+        self.T_max = num_frames(S_max)
+        self.basis, self.mel_idx, self.mel_w = constants(self.dev)
+        Lp = _lib.load().lasr_logmel_padded_len(self.T_max)
+        dev = self.dev
+        self.parts = torch.empty((3, N, Lp), device=dev, dtype=torch.bfloat16)
+        self.db = torch.empty((N, self.T_max, N_MELS), device=dev, dtype=torch.float32)
+        self.stats = torch.zeros((N, 2), device=dev, dtype=torch.float64)
+        self.feats = torch.empty((N, self.T_max, N_MELS), device=dev, dtype=out_dtype)
+        self.starts = torch.zeros((N,), device=dev, dtype=torch.int32)
+        self.kept = torch.zeros((N,), device=dev, dtype=torch.int32)
+        self.bands = torch.zeros((N, 4), device=dev, dtype=torch.int32)
+        self.percents = torch.zeros((N,), device=dev, dtype=torch.float32)
+
+    def __call__(self, waves, num_samples, uniforms=None):
+        if waves.dtype not in (torch.int16, torch.float32) or tuple(waves.shape) != (self.N, self.S_max):
+            raise _lib.LasrError("DeviceFrontend: waves must be int16 or float32 [N, S_max] on the device")
+        if not waves.is_cuda or not waves.is_contiguous() or num_samples.dtype != torch.int32:
+            raise _lib.LasrError("DeviceFrontend: contiguous CUDA waves and int32 num_samples expected")
+        N, T = self.N, self.T_max
+        aug = 1 if self.augment else 0
+        _lib.call("lasr_augment_draw", num_samples, uniforms, self.seed, self.seed_dev if uniforms is None else None,
+                  self.starts, self.kept, self.bands, self.percents, N, T, aug, aug)
+        self.stats.zero_()
+        wave_code = 1 if waves.dtype == torch.int16 else 0
+        _lib.call("lasr_logmel_prepare_wave", waves, wave_code, None, (self.seed ^ 0x5DEECE66D) if self.dither else 0,
+                  self.seed_dev, self.starts if self.augment else None, self.kept, self.parts, N, self.S_max, T)
+        _lib.call("lasr_logmel_fwd", self.parts, self.basis, self.mel_idx, self.mel_w, self.kept, self.db, self.stats, N, T,
+                  6)
+        if self.augment:
+            _lib.call("lasr_spec_augment", self.db, self.stats, self.kept, self.bands, N, T)
+        _lib.call("lasr_logmel_normalize", self.db, self.stats, self.kept, None, self.feats, N, T,
+                  _lib.dtype_code(self.out_dtype))
+        return self.feats, self.percents
+
+
+def pcm16(waves):
+    """float waveform in [-1, 1] -> 16-bit PCM (the wire format: x * 32768 rounded, saturated)."""
+    return (waves.float() * 32768.0).round().clamp_(-32768, 32767).to(torch.int16)
+
+
 def _load_wav(path_or_file):
     """PCM wav -> float32 [1, S] in [-1, 1) and its sample rate (torchaudio.load(..., normalize=True) contract,
     data_module.py:153).  Decoding is I/O, outside the hot path: stdlib `wave` covers the 16-bit PCM files that
@@ -170,17 +227,19 @@ def _load_wav(path_or_file):
 class AudioParser:
     """data_module.py:58-174.  parse_audio(audio_path, mask=False) -> [1, 64, T] fp32 (on the GPU).
     `audio_path` may be a path / file-like (as in the reference) or an already decoded waveform tensor [S] / [1, S].
-    mask=True (train-time crop + SpecAugment, unseeded host RNG in the reference) is not reproduced: it raises."""
+    mask=True applies the train-time crop (:158-159) and SpecAugment (:163-165) with draws from `self.random`, an
+    unseeded random.Random() exactly like the reference's (:65); assign a seeded one for reproducible runs."""
 
     def __init__(self, win_len=0.02, sr=16000, device="cuda", dither=True):
+        import random
+
         self.sr = sr
         self.win_len = win_len  # kept for signature parity; the reference hard-codes 320/160 too (:68-70)
         self.device = torch.device(device)
         self.dither = dither
+        self.random = random.Random()  # :65
 
     def parse_audio(self, audio_path, mask=False):
-        if mask:
-            raise _lib.LasrError("train-time augmentation (crop / SpecAugment) is host-side and out of the hot path")
         if isinstance(audio_path, torch.Tensor):
             y = audio_path.reshape(1, -1)
         else:
@@ -192,7 +251,11 @@ class AudioParser:
             y = y[:1]
         y = y.to(self.device, torch.float32)
         d = torch.randn_like(y) if self.dither else None  # :155
-        out = logmel_batch(y, [y.shape[1]], dither=d, sr=self.sr)
+        if mask:
+            start, kept, bands = draw_augment(y.shape[1], self.random)
+            out = logmel_batch(y, [kept], dither=d, sr=self.sr, starts=[start], bands=[list(bands)])
+        else:
+            out = logmel_batch(y, [y.shape[1]], dither=d, sr=self.sr)
         return out["inputs"][0]
 
 

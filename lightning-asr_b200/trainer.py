@@ -182,7 +182,14 @@ class TrainEngine:
     and one cast launch per step) and, with graph=True, captures the whole step -- memset, cast, forward, CTC,
     backward, gradient all-reduce, optimizer -- into ONE CUDA graph that is replayed every step."""
 
-    def __init__(self, module, example_batch, graph=True, optimizer=None, grad_sync=None, fused=True, world_sync=None):
+    def __init__(self, module, example_batch, graph=True, optimizer=None, grad_sync=None, fused=True, world_sync=None,
+                 augment=False, dither=False, wave_dtype=torch.int16):
+        """example_batch: the reference's training tuple (inputs [N,1,64,T] fp32 features, targets, percents,
+        target_sizes, ...) -- or, for the step that starts from WAVEFORMS (the log-mel frontend on the training path,
+        data_module.py:150-174 moved onto the device), ((waves [N, S_max], num_samples [N]), targets, _,
+        target_sizes, ...): the waveforms travel as 16-bit PCM (wave_dtype=torch.float32 keeps fp32 samples, used by the
+        parity tests), the frontend runs inside the step graph, `augment` / `dither` switch the train-time crop +
+        SpecAugment and the dither on (drawn on the device, re-keyed every step by the bank's step counter)."""
         _lib.require_device()
         self.module = module
         self.dev = torch.device("cuda", torch.cuda.current_device())
@@ -199,6 +206,19 @@ class TrainEngine:
             self.grad_sync = ddp.GradSync(module, group=world_sync[0], bucket_mb=world_sync[1], overlap=True,
                                           bank=self.bank)
         self.fused = fused
+        self.waveform = isinstance(example_batch[0], (tuple, list))
+        self.frontend = None
+        if self.waveform:
+            from . import frontend as fe
+            waves, ns = example_batch[0]
+            self._wave_dtype = wave_dtype
+            w = fe.pcm16(waves) if (wave_dtype == torch.int16 and waves.dtype != torch.int16) else waves.to(wave_dtype)
+            example_batch = (w.contiguous(), example_batch[1], torch.as_tensor(ns).int(), example_batch[3])
+            from .quartznet import resolve_dtype
+            self.bank.count_steps = self.bank.count_steps or augment or dither
+            self.frontend = fe.DeviceFrontend(w.shape[0], w.shape[1], self.dev, resolve_dtype(module.encoder.precision),
+                                              augment=augment, dither=dither, seed_dev=self.bank.step_counter)
+            self.uniforms = None  # optional [N, 6] fp64 device tensor: the augmentation parity hook
         # TWO pinned host staging sets: the H2D copies are asynchronous, so the host may only overwrite a set once the
         # copy that last read it has completed (event per set); with two sets the host can stage batch i+1 while the
         # H2D of batch i is still in flight (the two-deep pipeline of step_host(prefetch_next=..., defer_loss=True))
@@ -231,6 +251,11 @@ class TrainEngine:
         i = self._host_idx ^ 1
         if self._h2d_evt[i] is not None:
             self._h2d_evt[i].synchronize()
+        if self.waveform and isinstance(batch[0], (tuple, list)):  # ((waves, num_samples), targets, _, target_sizes)
+            from . import frontend as fe
+            w = batch[0][0]
+            w = fe.pcm16(w) if (self._wave_dtype == torch.int16 and w.dtype != torch.int16) else w.to(self._wave_dtype)
+            batch = (w, batch[1], torch.as_tensor(batch[0][1]).int(), batch[3])
         for h, src in zip(self._host_sets[i], batch[:4]):
             if torch.is_tensor(src):
                 if src.shape != h.shape:
@@ -252,7 +277,13 @@ class TrainEngine:
         self.bank.begin_step()
         if self.grad_sync is not None:
             self.grad_sync.zero_and_attach()
-        if self.fused:
+        if self.waveform:
+            # static = [waves, targets, num_samples, target_sizes]: frontend -> encoder -> fused decoder + CTC
+            feats, percents = self.frontend(self.static[0], self.static[2], self.uniforms)
+            x = m.encoder.encoder.forward_ntc(feats, percents)
+            nll, _, _ = m.encoder.fused_ctc_from_encoded(x, percents, self.static[1], self.static[3])
+            loss = torch.mean(nll)
+        elif self.fused:
             loss, _, _ = m.training_step_fused(self.static)
         else:
             loss, _, _ = m.training_step_tensors(self.static)

@@ -131,3 +131,83 @@ def test_device_augmentation_matches_reference_fixture(frontend):
         if fw > 0:
             band = got[0, f0:f0 + fw, :]
             assert float(band.max() - band.min()) == 0.0
+
+
+def test_augment_draw_on_device_matches_reference_arithmetic(frontend):
+    """lasr_augment_draw fed the six random() values of a seeded random.Random gives exactly the (start, kept, bands) of
+    the host restatement frontend.draw_augment (pinned to the reference's parse_audio(mask=True) by the fixture test
+    above) -- i.e. the device kernel restates data_module.py:138-148,97-122 in the reference's draw order."""
+    import random
+
+    from lightning_asr_b200 import _lib
+    sizes = [20000, 48000, 256000, 16000 * 7 + 13, 4000, 300000, 65537]
+    seeds = [3, 904, 905, 17, 99, 1234, 5]
+    want, unif = [], []
+    for S, sd in zip(sizes, seeds):
+        want.append(frontend.draw_augment(S, random.Random(sd)))
+        r = random.Random(sd)
+        unif.append([r.random() for _ in range(6)])
+    N = len(sizes)
+    T_max = frontend.num_frames(max(sizes))
+    ns = torch.tensor(sizes, device="cuda", dtype=torch.int32)
+    u = torch.tensor(unif, device="cuda", dtype=torch.float64)
+    starts = torch.zeros(N, device="cuda", dtype=torch.int32)
+    kept = torch.zeros_like(starts)
+    bands = torch.zeros(N, 4, device="cuda", dtype=torch.int32)
+    perc = torch.zeros(N, device="cuda")
+    _lib.call("lasr_augment_draw", ns, u, 0, None, starts, kept, bands, perc, N, T_max, 1, 1)
+    for i, (st, kp, bd) in enumerate(want):
+        assert (int(starts[i]), int(kept[i]), tuple(bands[i].tolist())) == (st, kp, tuple(bd)), i
+        assert float(perc[i]) == pytest.approx(frontend.num_frames(kp) / T_max, rel=1e-7)
+    # augmentation switched off: the whole utterance, empty bands
+    _lib.call("lasr_augment_draw", ns, u, 0, None, starts, kept, bands, perc, N, T_max, 0, 0)
+    assert torch.equal(kept, ns) and int(starts.abs().sum()) == 0 and int(bands.abs().sum()) == 0
+    # Philox draws: inside the reference's ranges, different per utterance, per seed and per device step counter
+    ns2 = torch.full((64,), 160000, device="cuda", dtype=torch.int32)
+    outs = []
+    for seed, ctr in ((7, None), (8, None), (7, torch.tensor(3, device="cuda", dtype=torch.int64))):
+        st2, kp2 = torch.zeros(64, device="cuda", dtype=torch.int32), torch.zeros(64, device="cuda", dtype=torch.int32)
+        bd2 = torch.zeros(64, 4, device="cuda", dtype=torch.int32)
+        _lib.call("lasr_augment_draw", ns2, None, seed, ctr, st2, kp2, bd2, None, 64, 1001, 1, 1)
+        assert int(kp2.min()) > 0.96 * 160000 - 3200 and int((st2 + kp2).max()) <= 160000
+        assert int(st2.max()) <= 3200 and int(bd2[:, 1].max()) < 27 and int((bd2[:, 0] + bd2[:, 1]).max()) <= 64
+        assert int((bd2[:, 2] + bd2[:, 3]).max()) <= 1001 and len(set(kp2.tolist())) > 32
+        outs.append(kp2.clone())
+    assert not torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("wire", ["fp32", "int16"])
+def test_device_frontend_matches_reference_fixture(frontend, wire):
+    """DeviceFrontend (static buffers, draws on the device, what TrainEngine captures in its step graph) against the
+    reference's own parse_audio(mask=True) output; the int16 wire format against the same utterances quantised to
+    16-bit PCM first (the reference decodes 16-bit wav files, data_module.py:153)."""
+    import os
+    import random
+
+    from oracle import frontend_oracle
+    fx = torch.load(os.path.join(GOLDEN, "augment.pt"), weights_only=False)
+    names = sorted(fx)
+    waves = [seeded_wave(fx[k]["samples"], fx[k]["seed"]) for k in names]
+    unif = []
+    for k in names:
+        r = random.Random(fx[k]["rng_seed"])
+        unif.append([r.random() for _ in range(6)])
+    S = max(len(w) for w in waves)
+    x = torch.zeros(len(waves), S)
+    for i, w in enumerate(waves):
+        x[i, :len(w)] = w
+    ns = torch.tensor([len(w) for w in waves], device="cuda", dtype=torch.int32)
+    xd = x.cuda() if wire == "fp32" else frontend.pcm16(x).cuda()
+    fe = frontend.DeviceFrontend(len(waves), S, "cuda", torch.float32, augment=True)
+    feats, perc = fe(xd.contiguous(), ns, torch.tensor(unif, device="cuda", dtype=torch.float64))
+    for i, k in enumerate(names):
+        start, kept, bands = frontend.draw_augment(fx[k]["samples"], random.Random(fx[k]["rng_seed"]))
+        if wire == "fp32":
+            ref = fx[k]["features"]
+        else:  # the oracle (pinned to the same fixture) on the quantised samples
+            ref = frontend_oracle.logmel(frontend.pcm16(waves[i]).float() / 32768.0, crop=(start, kept), bands=bands)
+        T = ref.shape[-1]
+        assert float(perc[i]) == pytest.approx(T / fe.T_max, rel=1e-7)
+        got = feats[i, :T].t().cpu()
+        assert rel_err(got, ref[0]) < 1e-4, k
+        assert float(feats[i, T:].abs().max()) == 0.0 if T < fe.T_max else True  # collate's zero padding

@@ -385,3 +385,52 @@ def test_ctc_zero_infinity_gradients_are_finite(lasr):
     ref = torch.nn.functional.ctc_loss(lpr, targets, il, tl, blank=28, reduction="none", zero_infinity=True)
     ref.sum().backward()
     assert rel_err(nll, ref) < 1e-5 and rel_err(lp.grad, lpr.grad) < 5e-4
+
+
+def test_train_engine_from_waveforms_matches_oracle(lasr, labels28):
+    """The training step that starts from WAVEFORMS (frontend inside the step graph): loss against the
+    oracle's frontend (data_module.py:155-172 restated) + collate (:222-248) + model + CTC on the same utterances, fp32;
+    then the int16 wire format, dither and on-device augmentation inside the CUDA graph."""
+    from lightning_asr_b200 import frontend, runtime
+    from lightning_asr_b200.trainer import LightingModule, TrainEngine, synthetic_batch
+    from oracle import frontend_oracle, train_oracle
+    batch = synthetic_batch(3, 2.0, 28, seed=6, ragged=True, features=False)
+    (waves, lens), targets, _, tgt_len, _ = batch
+    torch.manual_seed(4)
+    mod = LightingModule(labels=labels28, mask=True, precision="fp32").cuda().train()
+    sd0 = {k: v.detach().clone().cpu() for k, v in mod.encoder.state_dict().items()}
+    feats = [frontend_oracle.logmel(waves[i, : int(lens[i])]) for i in range(3)]
+    inputs, _, percents, _, _ = frontend_oracle.collate([(f, [0], "") for f in feats])
+    ref_loss, _, _ = train_oracle.training_step(sd0, (inputs, targets, percents, tgt_len), labels28, mask=True, training=True)
+    try:
+        eng = TrainEngine(mod, batch, graph=True, optimizer=None, wave_dtype=torch.float32)
+        loss = eng.step_host()
+        loss2 = eng.step_host(batch)  # restaged through the pinned sets
+    finally:
+        runtime.uninstall()
+    assert abs(loss - float(ref_loss)) <= 1e-4 * abs(float(ref_loss)), (loss, float(ref_loss))
+    assert abs(loss2 - loss) <= 1e-6 * abs(loss)
+    # int16 on the wire: the oracle on the quantised samples
+    wq = frontend.pcm16(waves).float() / 32768.0
+    feats = [frontend_oracle.logmel(wq[i, : int(lens[i])]) for i in range(3)]
+    inputs, _, percents, _, _ = frontend_oracle.collate([(f, [0], "") for f in feats])
+    ref_q, _, _ = train_oracle.training_step(sd0, (inputs, targets, percents, tgt_len), labels28, mask=True, training=True)
+    mod2 = LightingModule(labels=labels28, mask=True, precision="fp32").cuda().train()
+    mod2.encoder.load_state_dict(sd0)
+    try:
+        eng2 = TrainEngine(mod2, batch, graph=True, optimizer=None)
+        assert eng2.h2d_bytes == waves.numel() * 2 + targets.numel() * 8 + 3 * 4 + 3 * 4
+        loss_q = eng2.step_host()
+    finally:
+        runtime.uninstall()
+    assert abs(loss_q - float(ref_q)) <= 1e-4 * abs(float(ref_q))
+    # augmentation + dither drawn on the device inside the graph: every replay sees different crops / bands / noise
+    mod3 = LightingModule(labels=labels28, mask=True, precision="bf16").cuda().train()
+    try:
+        eng3 = TrainEngine(mod3, batch, graph=True, optimizer=None, augment=True, dither=True)
+        ls = [eng3.step_host() for _ in range(4)]
+        kept = eng3.frontend.kept.clone()
+    finally:
+        runtime.uninstall()
+    assert len({round(v, 5) for v in ls}) == 4 and all(v == v and v > 0 for v in ls), ls
+    assert bool((kept <= lens.cuda()).all()) and bool((kept >= (0.96 * lens.float()).int().cuda() - 1).all())
