@@ -587,7 +587,9 @@ def measure_train(workload, steps, warmup, graph, world, rank, local, peaks, opt
     # the step starts from WAVEFORMS (16-bit PCM on the wire): log-mel frontend -> encoder -> CTC -> backward -> optimizer
     batch = synthetic_batch(n, seconds, len(labels), seed=1234 + rank, ragged=False, features=False)
     engine = TrainEngine(module, batch, graph=graph, fused=True,
-                         world_sync=(None, float(os.environ.get("LASR_BUCKET_MB", "8"))) if world > 1 else None,
+                         world_sync=(None, float(os.environ.get("LASR_BUCKET_MB", "8")),
+                                     tuple(float(v) for v in os.environ.get("LASR_TAIL_MB", "0.75,2.5,4").split(",") if v))
+                         if world > 1 else None,
                          optimizer="novograd" if optimizer else None)
     graph_note = graph
     try:
@@ -694,6 +696,10 @@ def run_b200(args):
     torch.cuda.set_device(local)
     _lib.require_device()
     if world > 1:
+        # the gradient exchange is 20-40 MB per step in <= 8 MB buckets: latency-, not bandwidth-bound.  Fewer NCCL CTAs
+        # leave the SMs to the persistent compute kernels the all-reduce overlaps with (measured at N = 2: exposed
+        # all-reduce 115 us with NCCL's default, 96 us with 4 CTAs, 310 us with 2)
+        os.environ.setdefault("NCCL_MAX_CTAS", "4")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = load_peaks()
     infer = args.workload.startswith("infer_")

@@ -32,15 +32,21 @@ class GradSync:
     reporting.  Call the object after backward to drain: it reduces whatever has not fired and joins the side stream.
     """
 
-    def __init__(self, module, group=None, bucket_mb=8.0, overlap=True, bank=None):
+    def __init__(self, module, group=None, bucket_mb=8.0, overlap=True, bank=None, tail_mb=(0.75, 2.5, 4.0)):
+        """bucket_mb: size of the buckets that complete early in backward (decoder side).  tail_mb: sizes of the LAST
+        buckets to complete, innermost first -- the final bucket (first_cnn + the first block) finishes with the very last
+        weight-gradient kernel and nothing but the optimizer is left to hide its all-reduce behind, so it is kept small
+        (latency-bound, ~25 us) and the ones before it grow geometrically; () restores uniform buckets."""
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bank = bank
         self.params = [p for p in module.parameters() if p.requires_grad]
-        order = list(reversed(self.params))  # ~ backward completion order (decoder / last layers first)
-        cap = int(bucket_mb * 1024 * 1024 / 4)
+        # walk the parameters in FORWARD order (= reverse completion order): the tail buckets first, then uniform ones
+        cap_rest = int(bucket_mb * 1024 * 1024 / 4)
+        caps = [min(int(mb * 1024 * 1024 / 4), cap_rest) for mb in tail_mb]
         groups, cur, cur_n = [], [], 0
-        for p in order:
+        for p in self.params:
+            cap = caps[len(groups)] if len(groups) < len(caps) else cap_rest
             if cur and cur_n + p.numel() > cap:
                 groups.append(cur)
                 cur, cur_n = [], 0
@@ -48,6 +54,8 @@ class GradSync:
             cur_n += p.numel()
         if cur:
             groups.append(cur)
+        # buckets in backward completion order (decoder / last layers first), parameters inside likewise
+        groups = [list(reversed(g)) for g in reversed(groups)]
         self.buckets = []  # (flat fp32 tensor, [(param, offset, numel)])
         for g in groups:
             if bank is not None:

@@ -203,8 +203,9 @@ class TrainEngine:
         self.grad_sync = grad_sync
         if world_sync is not None:  # (group, bucket_mb): build the gradient exchange over the bank's flat buffer
             from . import ddp
+            tail = world_sync[2] if len(world_sync) > 2 else (0.75, 2.5, 4.0)
             self.grad_sync = ddp.GradSync(module, group=world_sync[0], bucket_mb=world_sync[1], overlap=True,
-                                          bank=self.bank)
+                                          bank=self.bank, tail_mb=tail)
         self.fused = fused
         self.waveform = isinstance(example_batch[0], (tuple, list))
         self.frontend = None
