@@ -193,6 +193,24 @@ int lasr_bn_apply_act_fwd(const void* y, const lasr_bn_t* bn1, const void* r, co
                           void* out, int M, int C, int T, int count, float eps, float momentum, int act,
                           int side_effects, const lasr_dropout_t* drop, int dtype, lasr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Channel-major series: the operand format of the TMA-fed depthwise kernels (bf16 only).
+ *   xT [C][N][S]: frame t of utterance n, channel c at position off + t of row (c, n); zeros before and after;
+ *   off = lasr_cm_offset(K) = K/2 rounded up to 8 (the conv's left padding), S = lasr_cm_pitch(T, K) (a multiple of 128);
+ *   16-byte groups of 8 positions are stored at group index g ^ ((g >> 3) & 1) (the tensor cores' 32-byte swizzle
+ *   applied in global memory).  K is the kernel size of the depthwise conv that will CONSUME the tensor.
+ * lasr_bn_apply_act_fwd_cm = lasr_bn_apply_act_fwd (bf16, no dropout, C % 64 == 0) that also writes the series
+ * companion outT of its output: the block that follows reads its depthwise input from it (models/QuartNet.py:30). */
+int lasr_cm_offset(int K);
+int lasr_cm_pitch(int T, int K);
+int lasr_bn_apply_act_fwd_cm(const void* y, const lasr_bn_t* bn1, const void* r, const lasr_bn_t* bn2, const float* gate,
+                             void* out, void* outT, int N, int T, int C, int S, int off, float eps, float momentum,
+                             int act, int side_effects, lasr_stream_t stream);
+/* y [N, T, C] channels-last = depthwise conv of the series xT (flip = 1: reversed taps = the data gradient, + addend
+ * [N, T, C] nullable); same arithmetic as lasr_dwconv1d_fwd(stride 1, bf16) */
+int lasr_dwconv1d_fwd_cm(const void* xT, const float* w, void* y, const void* addend, int N, int T, int C, int K, int S,
+                         int flip, lasr_stream_t stream);
+
 /* backward pass 1.  With g = dout * (act == RELU ? out > 0 : 1) and g1 = g * dropout factor (= g without dropout):
  *   totals[0][c] += sum g, totals[1][c] += sum g1*y, totals[2][c] += sum g*r     double [3, C], caller zeroes
  *   totals[3][c] += sum g1                                                        (only with dropout: double [4, C])

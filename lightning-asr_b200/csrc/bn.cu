@@ -285,6 +285,140 @@ bn_apply_fwd_kernel(const T* __restrict__ y, const lasr_bn_t bn1, const T* __res
 }
 
 // ------------------------------------------------------------------------------------------------
+// forward apply that ALSO writes the channel-major "series" companion of its output (bf16 only): the operand format of
+// the TMA-fed depthwise kernels (dwconv_cm.cu; layout contract in include/lasr.h, "channel-major series").
+//   out  [N*T, C]  channels-last, as bn_apply_fwd_kernel
+//   outT [C][N][S] frame t of utterance n at position off + t of row (c, n); positions [0, off) and [off + T, S) zero;
+//                  16-byte groups of 8 positions stored at group index g ^ ((g >> 3) & 1): the tensor cores' 32-byte
+//                  swizzle applied in GLOBAL memory, so that an unswizzled TMA copy of 128-position-aligned blocks lands
+//                  as a SWIZZLE_32B operand.
+// A depthwise conv consumes per-channel time series; in a channels-last tensor they do not exist, and gathering them
+// inside the conv kernel (one L2 request per 32 useful bytes, a transposition on the critical path of a 4-item pipeline)
+// is what kept that kernel at 20 % of its HBM bound in round 1.  This pass is a pure stream with every thread owning an
+// 8-frame x 8-channel block: 8 row loads of 16 B per operand (a quarter-warp covers a full 128-byte line), the
+// arithmetic, 8 row stores, then the 8x8 transposition with byte permutes and 8 more 16-byte stores, one per channel
+// row of outT (four neighbouring lanes fill a 64-byte run).  The extra cost is one more write stream in a pass that
+// already moves three.
+// ------------------------------------------------------------------------------------------------
+template <bool HAS_R, bool HAS_GATE>
+__global__ void __launch_bounds__(256, 2)
+bn_apply_fwd_cm_kernel(const __nv_bfloat16* __restrict__ y, const lasr_bn_t bn1, const __nv_bfloat16* __restrict__ r,
+                       const lasr_bn_t bn2, const float* __restrict__ gate, __nv_bfloat16* __restrict__ out,
+                       __nv_bfloat16* __restrict__ outT, int N, int T_len, int C, int S, int off, double count, float eps,
+                       float momentum, int act, int side_effects) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float coef_s[];  // [4][C]
+  float* s_scale1 = coef_s;
+  float* s_shift1 = coef_s + C;
+  float* s_scale2 = coef_s + 2 * C;
+  float* s_shift2 = coef_s + 3 * C;
+  const double inv_count = 1.0 / count;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const BnRaw r1 = bn_load_raw(bn1, c, C);
+    BnRaw r2{};
+    if constexpr (HAS_R) r2 = bn_load_raw(bn2, c, C);
+    float sc, sh, mf, isf;
+    double var;
+    bn_coeffs_raw(r1, bn1.sums != nullptr, inv_count, eps, sc, sh, mf, isf, var);
+    s_scale1[c] = sc;
+    s_shift1[c] = sh;
+    if (blockIdx.x == 0 && side_effects) bn_side_effects(bn1, c, count, momentum, mf, isf, var);
+    if constexpr (HAS_R) {
+      bn_coeffs_raw(r2, bn2.sums != nullptr, inv_count, eps, sc, sh, mf, isf, var);
+      s_scale2[c] = sc;
+      s_shift2[c] = sh;
+      if (blockIdx.x == 0 && side_effects) bn_side_effects(bn2, c, count, momentum, mf, isf, var);
+    }
+  }
+  __syncthreads();
+  // warp unit = 4 position groups (32 positions) x 8 channel vectors (64 channels); lane = (group, vector)
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & 3, cvl = lane >> 2;
+  const int CVO = C / 64;         // channel octets
+  const int quads = S / 32;       // per utterance row
+  const long long units = static_cast<long long>(N) * quads * CVO;
+  const long long warp0 = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long wstride = static_cast<long long>(gridDim.x) * (blockDim.x >> 5);
+  const bool relu = act == LASR_ACT_RELU;
+  for (long long u = warp0; u < units; u += wstride) {
+    const int cvo = static_cast<int>(u % CVO);
+    const long long rest = u / CVO;
+    const int quad = static_cast<int>(rest % quads);
+    const int n = static_cast<int>(rest / quads);
+    const int c = (cvo * 8 + cvl) * 8;
+    const int g = quad * 4 + gl;         // position group of this lane
+    const int f0 = g * 8 - off;          // first frame of the group (off % 8 == 0: all 8 frames share validity but the last)
+    const size_t row0 = static_cast<size_t>(n) * T_len;
+    uint4 ya[8], ra[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = f0 + i;
+      ya[i] = make_uint4(0u, 0u, 0u, 0u);
+      if constexpr (HAS_R) ra[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (f >= 0 && f < T_len) {
+        const size_t e = (row0 + f) * C + c;
+        ya[i] = *reinterpret_cast<const uint4*>(y + e);
+        if constexpr (HAS_R) ra[i] = *reinterpret_cast<const uint4*>(r + e);
+      }
+    }
+    float sc1[8], sh1[8], sc2[8], sh2[8], gt[8];
+    lds8(s_scale1 + c, sc1);
+    lds8(s_shift1 + c, sh1);
+    if constexpr (HAS_R) {
+      lds8(s_scale2 + c, sc2);
+      lds8(s_shift2 + c, sh2);
+    }
+    if constexpr (HAS_GATE) load8f(gate + static_cast<size_t>(n) * C + c, gt);
+    uint4 o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int f = f0 + i;
+      float a[8], v[8];
+      Vec8<__nv_bfloat16>::unpack(ya[i], a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = fmaf(a[k], sc1[k], sh1[k]);
+      if constexpr (HAS_GATE) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] *= gt[k];
+      }
+      if constexpr (HAS_R) {
+        float rr[8];
+        Vec8<__nv_bfloat16>::unpack(ra[i], rr);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] += fmaf(rr[k], sc2[k], sh2[k]);
+      }
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+      }
+      o[i].x = f32x2_to_bf16x2(v[0], v[1]);
+      o[i].y = f32x2_to_bf16x2(v[2], v[3]);
+      o[i].z = f32x2_to_bf16x2(v[4], v[5]);
+      o[i].w = f32x2_to_bf16x2(v[6], v[7]);
+      if (f >= 0 && f < T_len)
+        *reinterpret_cast<uint4*>(out + (row0 + f) * C + c) = o[i];
+      else
+        o[i] = make_uint4(0u, 0u, 0u, 0u);  // the conv's zero padding
+    }
+    // 8 frames x 8 channels -> 8 channels x 8 frames; group g is stored at its swizzled index
+    const int gs = g ^ ((g >> 3) & 1);
+    __nv_bfloat16* dst = outT + (static_cast<size_t>(c) * N + n) * S + static_cast<size_t>(gs) * 8;
+    const size_t cstride = static_cast<size_t>(N) * S;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint32_t w[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const uint32_t lo = (&o[2 * m].x)[q >> 1], hi = (&o[2 * m + 1].x)[q >> 1];
+        w[m] = __byte_perm(lo, hi, (q & 1) ? 0x7632 : 0x5410);
+      }
+      *reinterpret_cast<uint4*>(dst + q * cstride) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-(utterance, channel) sum over time (SE squeeze): sums[n, c] = sum_t y[n, t, c]
 // grid (N, chunks); atomics into a zeroed buffer
 // ------------------------------------------------------------------------------------------------
@@ -764,6 +898,36 @@ int lasr_bn_apply_act_fwd(const void* y, const lasr_bn_t* bn1, const void* r, co
     return bn_fwd_launch<__nv_bfloat16>(y, *bn1, r, b2, gate, out, total, CV, C, T, count, eps, momentum, act,
                                         side_effects, da, stream);
   return LASR_ERR_BAD_DTYPE;
+}
+
+int lasr_bn_apply_act_fwd_cm(const void* y, const lasr_bn_t* bn1, const void* r, const lasr_bn_t* bn2, const float* gate,
+                             void* out, void* outT, int N, int T, int C, int S, int off, float eps, float momentum,
+                             int act, int side_effects, lasr_stream_t stream) {
+  if (N <= 0 || T <= 0 || C <= 0 || (C % 64) || C > 2048 || bn1 == nullptr || outT == nullptr) return LASR_ERR_BAD_SHAPE;
+  if ((r != nullptr) != (bn2 != nullptr)) return LASR_ERR_BAD_SHAPE;
+  if (S <= 0 || (S % 128) || off < 0 || (off % 8) || off + T > S) return LASR_ERR_BAD_SHAPE;
+  const lasr_bn_t none{};
+  const lasr_bn_t& b2 = bn2 ? *bn2 : none;
+  const long long units = static_cast<long long>(N) * (S / 32) * (C / 64);
+  long long ctas = (units + 7) / 8;
+  if (ctas > 2 * kNumSMs) ctas = 2 * kNumSMs;
+  const int smem = 4 * C * static_cast<int>(sizeof(float));
+  const double count = static_cast<double>(N) * T;
+  const __nv_bfloat16* yy = static_cast<const __nv_bfloat16*>(y);
+  const __nv_bfloat16* rr = static_cast<const __nv_bfloat16*>(r);
+  __nv_bfloat16* oo = static_cast<__nv_bfloat16*>(out);
+  __nv_bfloat16* ot = static_cast<__nv_bfloat16*>(outT);
+  cudaError_t le;
+#define LASR_BN_CM(R, G)                                                                                           \
+  le = launch_pdl(4, bn_apply_fwd_cm_kernel<R, G>, dim3(static_cast<unsigned>(ctas)), dim3(256), smem, stream, yy, *bn1, \
+                  rr, b2, gate, oo, ot, N, T, C, S, off, count, eps, momentum, act, side_effects)
+  if (r != nullptr && gate != nullptr) LASR_BN_CM(true, true);
+  else if (r != nullptr) LASR_BN_CM(true, false);
+  else if (gate != nullptr) LASR_BN_CM(false, true);
+  else LASR_BN_CM(false, false);
+#undef LASR_BN_CM
+  LASR_CHECK_PDL(le);
+  return LASR_OK;
 }
 
 int lasr_bn_bwd_chunks(int N, int T) {

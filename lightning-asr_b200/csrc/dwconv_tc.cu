@@ -28,18 +28,15 @@
 // plain series: A[t', w] = z_c[8 w + t'] and B[w, t] = dy_c[8 w + t] are MN-major no-swizzle operands (LBO = 128 B
 // between groups of 8 windows, SBO = 16 B between groups of 8 t'), D[t', t] += sum_w z_c[8w + t'] dy_c[8w + t] and
 // dw_c[j] = sum_{t<8} D[t + j, t].  The accumulator stays in TMEM over all items of the CTA; one RED pass at the end.
-#include "common.cuh"
+#include "dw_common.cuh"
 
 #include <cstdlib>
 
 namespace lasr {
 
-constexpr int DT_CG = 16;        // channels per CTA
-constexpr int DT_ROWS = 128;     // MMA M: windows of 8 frames
 constexpr int DT_CHUNK = 1024;   // output frames per item
 constexpr int DT_PROD_WARPS = 8;  // two groups of 4: group g fills series stage g
 constexpr int DT_THREADS = 32 * (6 + DT_PROD_WARPS);
-constexpr int DT_MAX_KS = 112;
 constexpr int DT_STAGES = 4;     // series buffers of the forward kernel
 
 struct DwTcParams {
@@ -69,52 +66,7 @@ __device__ __forceinline__ unsigned long long dt_gtimer() {
 static unsigned long long* g_dt_trace = nullptr;
 extern "C" void lasr_debug_set_dw_trace(unsigned long long* buf) { g_dt_trace = buf; }
 
-__device__ __forceinline__ uint64_t umma_desc_none(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;  // descriptor version (Blackwell); layout type 0 = no swizzle
-  return d;
-}
 
-__device__ __forceinline__ void umma_bf16_first(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 0, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16_acc(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.eq.b32 p, 0, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32_x8(uint32_t taddr, uint32_t (&v)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-               : "r"(taddr)
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_32x32_x4(uint32_t taddr, uint32_t (&v)[4]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void ldg_v8(const void* p, uint32_t (&a)[8]) {
-  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7])
-               : "l"(p));
-}
-__device__ __forceinline__ void stg_v8(void* p, const uint32_t (&a)[8]) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]),
-               "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7])
-               : "memory");
-}
 
 // global [frames, C] -> per-channel series in shared memory.  series[c][sigma] (bf16, pitch ZL) for sigma in
 // [0, ZL): frame f = f_base + sigma of utterance rows `src` (out of [0, T): zero).  Called by the 4 warps of a producer
@@ -514,15 +466,6 @@ constexpr int D16_SLOTF = 1024;                 // series frames per slot
 constexpr int D16_ROWB = 2 * D16_SLOTF * 2;     // bytes of one channel's series in a stage (2 slots)
 constexpr int D16_STAGE = DT_CG * D16_ROWB;     // 64 KB
 
-__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>(1) << 16;  // LBO unused: one K-step is exactly the 32-byte swizzle span
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(6) << 61;  // SWIZZLE_32B
-  return d;
-}
 
 // one slot: global [frames, C] -> series[c][slot frames 0..1023] swizzled; out of [0, T) frames are zero
 __device__ __forceinline__ void load_slot_sw32(const __nv_bfloat16* __restrict__ src, int C, int T, int f_base,
@@ -809,9 +752,6 @@ __global__ void __launch_bounds__(DT_THREADS, 1) dwconv_tc16_fwd_kernel(const Dw
 constexpr int D2_GROUPS = 4;
 constexpr int D2_THREADS = 32 * (6 + 4 * D2_GROUPS);  // 704
 
-__device__ __forceinline__ void tmem_ld_32x32_x2(uint32_t taddr, uint32_t (&v)[2]) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];\n" : "=r"(v[0]), "=r"(v[1]) : "r"(taddr) : "memory");
-}
 
 template <bool HAS_ADDEND>
 __device__ __forceinline__ void dwconv_tc16v2_fwd_body(const Dw16Params& p, const int bid) {

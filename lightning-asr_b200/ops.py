@@ -90,6 +90,61 @@ def dwconv_bwd(x, dy, w, addend=None, out_dw=None):
     return dx, dw
 
 
+class Series:
+    """Channel-major companion of a channels-last activation (include/lasr.h, "channel-major series"): the operand of
+    the TMA-fed depthwise kernels.  t: bf16 [C, N, S]; built for a depthwise conv of kernel size K over T frames."""
+    __slots__ = ("t", "N", "T", "C", "K", "S", "off")
+
+    def __init__(self, t, N, T, C, K):
+        self.t, self.N, self.T, self.C, self.K = t, N, T, C, K
+        self.S, self.off = cm_pitch(T, K), cm_offset(K)
+
+
+def cm_offset(K):
+    return _lib.load().lasr_cm_offset(K)
+
+
+def cm_pitch(T, K):
+    return _lib.load().lasr_cm_pitch(T, K)
+
+
+def cm_supported(C, K, dtype, stride=1):
+    """a depthwise layer (C channels, kernel K) can read its input as a Series"""
+    return dtype == torch.bfloat16 and stride == 1 and C % 64 == 0 and K % 2 == 1 and 3 <= K <= 89
+
+
+def series_from_ntc(x, K):
+    """Reference construction of a Series from a channels-last tensor with torch ops (tests / the layers whose input is
+    not produced by a BatchNorm pass)."""
+    N, T, C = x.shape
+    S, off = cm_pitch(T, K), cm_offset(K)
+    buf = torch.zeros((C, N, S), device=x.device, dtype=x.dtype)
+    buf[:, :, off:off + T] = x.permute(2, 0, 1)
+    g = torch.arange(S // 8, device=x.device)
+    perm = g ^ ((g >> 3) & 1)
+    t = buf.view(C, N, S // 8, 8)[:, :, perm, :].reshape(C, N, S).contiguous()
+    return Series(t, N, T, C, K)
+
+
+def series_to_ntc(s):
+    """inverse of series_from_ntc (tests)"""
+    g = torch.arange(s.S // 8, device=s.t.device)
+    perm = g ^ ((g >> 3) & 1)
+    buf = s.t.view(s.C, s.N, s.S // 8, 8)[:, :, perm, :].reshape(s.C, s.N, s.S)
+    return buf[:, :, s.off:s.off + s.T].permute(1, 2, 0).contiguous(), buf
+
+
+def dwconv_fwd_cm(xs, w, flip=False, addend=None):
+    """depthwise conv (stride 1, bf16) reading its input from a Series -> y [N, T, C] channels-last"""
+    _chk(w, "w")
+    K = w.shape[-1]
+    if K != xs.K:
+        raise _lib.LasrError(f"dwconv_fwd_cm: the series was laid out for K={xs.K}, the conv has K={K}")
+    y = torch.empty((xs.N, xs.T, xs.C), device=xs.t.device, dtype=torch.bfloat16)
+    call("lasr_dwconv1d_fwd_cm", xs.t, w, y, addend, xs.N, xs.T, xs.C, K, xs.S, 1 if flip else 0)
+    return y
+
+
 def pwconv_fwd(x2d, w, bias=None, lengths=None, T=0, stats=None, out=None, ldy=None):
     """y[M, Cout] = x[M, Cin] w[Cout, Cin]^T (+bias), MaskCNN row mask; `stats` (double [2, Cout], zeroed) receives the
     BatchNorm batch sums.  x2d may be [N, T, Cin]; w [Cout, Cin(, 1)] in x's dtype.  Output row pitch ldy >= Cout."""
@@ -269,12 +324,22 @@ def sum_over_time(y):
 
 
 def bn_apply_act(y, bn1, r=None, bn2=None, gate=None, act=ACT_RELU, eps=1e-3, momentum=0.1, side_effects=True,
-                 drop=None):
-    """out = act(BN1(y) [* gate] [* dropout] [+ BN2(r)]) in one pass; performs the training side effects of both BNs."""
+                 drop=None, cm_k=None):
+    """out = act(BN1(y) [* gate] [* dropout] [+ BN2(r)]) in one pass; performs the training side effects of both BNs.
+    cm_k = kernel size of the depthwise conv that consumes the result: also writes the channel-major Series companion
+    and returns (out, series)."""
     N, T, C = y.shape
     out = torch.empty_like(y)
     if drop is not None and drop.mask.numel() != y.numel():
         raise _lib.LasrError("dropout mask must have one byte per activation element")
+    if cm_k is not None:
+        if drop is not None or not cm_supported(C, cm_k, y.dtype):
+            raise _lib.LasrError("bn_apply_act: no channel-major companion for this configuration")
+        xs = Series(None, N, T, C, cm_k)
+        xs.t = torch.empty((C, N, xs.S), device=y.device, dtype=y.dtype)
+        call("lasr_bn_apply_act_fwd_cm", y, bn1.ptr, r, bn2.ptr if bn2 is not None else None, gate, out, xs.t, N, T, C,
+             xs.S, xs.off, eps, momentum, act, 1 if (side_effects and bn1.training) else 0)
+        return out, xs
     call("lasr_bn_apply_act_fwd", y, bn1.ptr, r, bn2.ptr if bn2 is not None else None, gate, out, N * T, C, T, N * T,
          eps, momentum, act, 1 if (side_effects and bn1.training) else 0, drop.ptr if drop is not None else None,
          dtype_code(y.dtype))

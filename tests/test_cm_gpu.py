@@ -1,0 +1,94 @@
+"""Channel-major series path (include/lasr.h "channel-major series"): the BatchNorm apply pass that writes the series
+companion, and the TMA-fed depthwise kernels that read it.  Yardsticks: fp64 torch ops on the same bf16 inputs
+(models/QuartNet.py:14-21,24,30,35-37)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from lightning_asr_b200 import _lib, ops
+    _lib.require_device()
+    return ops
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def _dw_ref(x, w, flip=False):
+    """x [N, T, C] -> fp64 depthwise conv, channels-last"""
+    K = w.shape[-1]
+    ww = w.double().flip(-1) if flip else w.double()
+    return F.conv1d(x.double().transpose(1, 2), ww, padding=K // 2, groups=x.shape[-1]).transpose(1, 2)
+
+
+@pytest.mark.parametrize("T", [801, 157, 896, 897, 2000])
+@pytest.mark.parametrize("K", [33, 39, 75])
+def test_series_layout_round_trip(ops, T, K):
+    x = torch.randn(3, T, 64, device="cuda").bfloat16()
+    s = ops.series_from_ntc(x, K)
+    assert s.S % 128 == 0 and s.off % 8 == 0 and s.off >= K // 2 and s.S >= s.off + T + 48
+    back, buf = ops.series_to_ntc(s)
+    assert torch.equal(back, x)
+    assert buf[:, :, :s.off].abs().max().item() == 0 and buf[:, :, s.off + T:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("N,T,C,K", [(4, 157, 256, 33), (32, 801, 256, 33), (32, 801, 256, 39), (32, 801, 512, 51),
+                                     (32, 801, 512, 63), (32, 801, 512, 75), (8, 801, 512, 87), (3, 801, 64, 33),
+                                     (5, 2001, 256, 51), (2, 3000, 128, 75), (1, 40, 64, 33), (7, 896, 64, 39),
+                                     (6, 897, 64, 39)])
+@pytest.mark.parametrize("flip", [False, True])
+def test_dwconv_fwd_cm_matches_fp64(ops, N, T, C, K, flip):
+    torch.manual_seed(N * 1000 + T + C + K)
+    x = torch.randn(N, T, C, device="cuda").bfloat16()
+    w = (torch.randn(C, 1, K, device="cuda") / K ** 0.5)
+    xs = ops.series_from_ntc(x, K)
+    y = ops.dwconv_fwd_cm(xs, w, flip=flip)
+    # the kernel multiplies bf16-rounded taps
+    ref = _dw_ref(x, w.bfloat16().float(), flip)
+    assert rel_err(y, ref) < 6e-3  # bf16 output rounding
+    # and agrees with the gather kernel on the same inputs
+    y_old = ops.dwconv_fwd(x, w, flip=flip)
+    assert rel_err(y, y_old.float()) < 6e-3
+    addend = torch.randn_like(x)
+    y2 = ops.dwconv_fwd_cm(xs, w, flip=flip, addend=addend)
+    assert rel_err(y2, ref + addend.double()) < 6e-3
+
+
+@pytest.mark.parametrize("N,T,C,K,has_r,has_gate", [(4, 157, 256, 33, True, False), (32, 801, 512, 75, True, False),
+                                                    (3, 801, 64, 39, False, False), (5, 301, 128, 51, True, True),
+                                                    (2, 897, 64, 33, False, True)])
+def test_bn_apply_cm_matches_plain_pass_and_layout(ops, N, T, C, K, has_r, has_gate):
+    torch.manual_seed(T + C)
+    dev = "cuda"
+    y = torch.randn(N, T, C, device=dev).bfloat16()
+    r = torch.randn(N, T, C, device=dev).bfloat16() if has_r else None
+    gate = torch.rand(N, C, device=dev) if has_gate else None
+
+    def bn(src):
+        sums = torch.stack((src.double().sum((0, 1)), (src.double() ** 2).sum((0, 1)))).contiguous()
+        return ops.BNForward(torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev), torch.zeros(C, device=dev),
+                             torch.ones(C, device=dev), torch.zeros((), device=dev, dtype=torch.int64), sums)
+
+    torch.manual_seed(1)
+    b1, b2 = bn(y), (bn(r) if has_r else None)
+    out_ref = ops.bn_apply_act(y, b1, r, b2, gate)
+    rm_ref, rv_ref = b1.running_mean.clone(), b1.running_var.clone()
+    torch.manual_seed(1)
+    b1c, b2c = bn(y), (bn(r) if has_r else None)
+    out, xs = ops.bn_apply_act(y, b1c, r, b2c, gate, cm_k=K)
+    assert torch.equal(out, out_ref)
+    assert torch.equal(b1c.running_mean, rm_ref) and torch.equal(b1c.running_var, rv_ref)
+    assert torch.equal(b1c.save, b1.save)
+    back, buf = ops.series_to_ntc(xs)
+    assert torch.equal(back, out)
+    assert buf[:, :, :xs.off].abs().max().item() == 0 and buf[:, :, xs.off + T:].abs().max().item() == 0
+    # and the depthwise conv reads it
+    w = torch.randn(C, 1, K, device=dev) / K ** 0.5
+    d = ops.dwconv_fwd_cm(xs, w)
+    assert rel_err(d, _dw_ref(out, w.bfloat16().float())) < 6e-3

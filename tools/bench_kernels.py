@@ -1,6 +1,6 @@
 """Per-kernel timings at the asr13x1 config-2 shapes (N=32, T'=801, bf16): CUDA events on the launching stream, an
 L2-sized scratch write between iterations (cold L2), median of `iters`.  Prints us, achieved GB/s (algorithmic bytes)
-and TFLOP/s per kernel.   python tools/bench_kernels.py [gemm|dw|bn|ctc|all]"""
+and TFLOP/s per kernel.   python tools/bench_kernels.py [gemm|dw|dwcm|bn|ctc|all]"""
 import statistics
 import sys
 
@@ -76,6 +76,32 @@ def bench_dw():
         report(f"dwconv_wgrad C={c} k={k}", timeit(lambda: ops.dwconv_wgrad(x, add, k, out=dw)), by, fl)
 
 
+def bench_dwcm():
+    """TMA-fed depthwise kernels reading channel-major series, and the BatchNorm pass that writes them"""
+    for c, k in [(256, 33), (256, 39), (256, 51), (512, 51), (512, 63), (512, 75)]:
+        x = torch.randn(N, T, c, device=dev).bfloat16()
+        w = torch.randn(c, 1, k, device=dev) / k ** 0.5
+        xs = ops.series_from_ntc(x, k)
+        by, fl = 2 * M * c * 2, 2.0 * M * c * k
+        report(f"dwconv_fwd_cm   C={c} k={k}", timeit(lambda: ops.dwconv_fwd_cm(xs, w)), by, fl)
+        add = torch.randn(N, T, c, device=dev).bfloat16()
+        report(f"dwconv_dgrad_cm+addend C={c} k={k}", timeit(lambda: ops.dwconv_fwd_cm(xs, w, flip=True, addend=add)), by + 2 * M * c, fl)
+    for c in (256, 512):
+        y = torch.randn(N, T, c, device=dev).bfloat16()
+        r = torch.randn(N, T, c, device=dev).bfloat16()
+        g = torch.ones(c, device=dev)
+        b = torch.zeros(c, device=dev)
+        rm, rv, nbt = torch.zeros(c, device=dev), torch.ones(c, device=dev), torch.zeros((), device=dev, dtype=torch.long)
+
+        def sums(t):
+            t2 = t.double().reshape(-1, c)
+            return torch.stack([t2.sum(0), (t2 * t2).sum(0)])
+        bn1 = ops.BNForward(g, b, rm, rv, nbt, sums(y))
+        bn2 = ops.BNForward(g, b, rm.clone(), rv.clone(), nbt.clone(), sums(r))
+        report(f"bn_apply_act_fwd (res) C={c}", timeit(lambda: ops.bn_apply_act(y, bn1, r, bn2)), 2 * M * c * 3, 0)
+        report(f"bn_apply_act_fwd_cm (res) C={c}", timeit(lambda: ops.bn_apply_act(y, bn1, r, bn2, cm_k=51)), 2 * M * c * 4, 0)
+
+
 def bench_bn():
     for c in (256, 512):
         y = torch.randn(N, T, c, device=dev).bfloat16()
@@ -132,6 +158,6 @@ def bench_frontend():
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
-for name, fn in [("calib", bench_calib), ("gemm", bench_gemm), ("dw", bench_dw), ("bn", bench_bn), ("ctc", bench_ctc), ("frontend", bench_frontend)]:
+for name, fn in [("calib", bench_calib), ("gemm", bench_gemm), ("dw", bench_dw), ("dwcm", bench_dwcm), ("bn", bench_bn), ("ctc", bench_ctc), ("frontend", bench_frontend)]:
     if which in ("all", name):
         fn()
