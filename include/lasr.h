@@ -206,10 +206,24 @@ int lasr_cm_pitch(int T, int K);
 int lasr_bn_apply_act_fwd_cm(const void* y, const lasr_bn_t* bn1, const void* r, const lasr_bn_t* bn2, const float* gate,
                              void* out, void* outT, int N, int T, int C, int S, int off, float eps, float momentum,
                              int act, int side_effects, lasr_stream_t stream);
-/* y [N, T, C] channels-last = depthwise conv of the series xT (flip = 1: reversed taps = the data gradient, + addend
- * [N, T, C] nullable); same arithmetic as lasr_dwconv1d_fwd(stride 1, bf16) */
-int lasr_dwconv1d_fwd_cm(const void* xT, const float* w, void* y, const void* addend, int N, int T, int C, int K, int S,
-                         int flip, lasr_stream_t stream);
+/* y [N, T, C] channels-last = depthwise conv of the series xT (flip = 1: reversed taps = the data gradient) + an
+ * optional addend, given EITHER channels-last (addend [N, T, C]) OR as a series laid out like xT (addendT); same
+ * arithmetic as lasr_dwconv1d_fwd(stride 1, bf16) */
+int lasr_dwconv1d_fwd_cm(const void* xT, const float* w, void* y, const void* addend, const void* addendT, int N, int T,
+                         int C, int K, int S, int flip, lasr_stream_t stream);
+/* dw [C, 1, K] fp32 += sum_{n,t} dy[n,t,c] x[n, t + j - K/2, c] from the series of x and of dy (same K, same layout) */
+int lasr_dwconv1d_wgrad_cm(const void* xT, const void* dyT, float* dw, int N, int T, int C, int K, int S,
+                           lasr_stream_t stream);
+/* stride-1 backward of one layer in ONE launch from series operands: dx [N, T, C] channels-last = correlation of dy with
+ * the flipped taps (+ addend / addendT) and dw += (autograd of models/QuartNet.py:30) */
+int lasr_dwconv1d_bwd_cm(const void* xT, const void* dyT, const float* w, const void* addend, const void* addendT,
+                         void* dx, float* dw, int N, int T, int C, int K, int S, lasr_stream_t stream);
+/* data gradient(s) of 1x1 convs written as channel-major series (bf16): dxT[c][n][off + t] = sum_k dy[n, t, k] w[k, c],
+ * dy [N*T, Cout] channels-last, w [Cout, Cin]; the pads of dxT are written as zeros.  (dy2, w2, dxT2): optional second
+ * problem of the same shape in the same launch (the block's residual conv), nullable together.  Returns
+ * LASR_ERR_UNSUPPORTED for shapes the weight-stationary tensor-core kernels do not take (Cin % 128 != 0). */
+int lasr_pwconv_dgrad_cm(const void* dy1, const void* w1, void* dxT1, const void* dy2, const void* w2, void* dxT2, int N,
+                         int T, int Cin, int Cout, int S, int off, lasr_stream_t stream);
 
 /* backward pass 1.  With g = dout * (act == RELU ? out > 0 : 1) and g1 = g * dropout factor (= g without dropout):
  *   totals[0][c] += sum g, totals[1][c] += sum g1*y, totals[2][c] += sum g*r     double [3, C], caller zeroes

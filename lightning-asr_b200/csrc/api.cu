@@ -22,6 +22,8 @@ bool pdl_enabled(int family) {
 }
 int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const int32_t* lengths, int T, double* stats,
                int M, int N, int K, int lda, int ldb, int ldc, int out_f32, cudaStream_t stream);
+int gemm_tc_nn_series(const void* dy1, const void* w1, void* outT1, const void* dy2, const void* w2, void* outT2,
+                      int n_utt, int T, int N, int K, int lda, int ldb, int S, int off, cudaStream_t stream);
 int gemm_tc_nn(const void* a, const void* b, void* out, int M, int N, int K, int lda, int ldb, int ldc, int out_f32,
                cudaStream_t stream);
 int gemm_tc_grouped2(bool b_mn, const void* a1, const void* b1, void* out1, const int32_t* lengths1, double* stats1,
@@ -217,6 +219,15 @@ int lasr_pwconv_dgrad2(const void* dy1, const void* w1, void* dx1, const void* d
   const int rc1 = lasr_pwconv_dgrad(dy1, w1, dx1, M, Cin, Cout, Cout, Cin, Cin, dtype, stream);
   if (rc1) return rc1;
   return lasr_pwconv_dgrad(dy2, w2, dx2, M, Cin, Cout, Cout, Cin, Cin, dtype, stream);
+}
+
+int lasr_pwconv_dgrad_cm(const void* dy1, const void* w1, void* dxT1, const void* dy2, const void* w2, void* dxT2, int N,
+                         int T, int Cin, int Cout, int S, int off, lasr_stream_t stream) {
+  if (N <= 0 || T <= 0 || Cin <= 0 || Cout <= 0 || dy1 == nullptr || w1 == nullptr || dxT1 == nullptr)
+    return LASR_ERR_BAD_SHAPE;
+  if ((dy2 != nullptr) != (dxT2 != nullptr) || (dy2 != nullptr) != (w2 != nullptr)) return LASR_ERR_BAD_SHAPE;
+  if (S <= 0 || (S % 128) || off < 0 || (off % 8) || off + T > S) return LASR_ERR_BAD_SHAPE;
+  return gemm_tc_nn_series(dy1, w1, dxT1, dy2, w2, dxT2, N, T, Cin, Cout, Cout, Cin, S, off, stream);
 }
 
 int lasr_pwconv_fwd_fused(const void* x, const void* w, void* y, const float* bias, const void* residual,

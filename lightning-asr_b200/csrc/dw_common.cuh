@@ -95,4 +95,16 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// debug timeline (tools/trace_dw.py): [CTA][8 slots][16 stamps] of %globaltimer, normally NULL
+unsigned long long* dw_trace_buffer();
+__device__ __forceinline__ unsigned long long dw_gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define DW_TRACE(buf, slot, idx)                                                                  \
+  do {                                                                                            \
+    if ((buf) != nullptr && (idx) < 16) (buf)[(blockIdx.x * 8 + (slot)) * 16 + (idx)] = dw_gtimer(); \
+  } while (0)
+
 }  // namespace lasr

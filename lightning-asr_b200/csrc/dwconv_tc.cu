@@ -65,6 +65,7 @@ __device__ __forceinline__ unsigned long long dt_gtimer() {
   } while (0)
 static unsigned long long* g_dt_trace = nullptr;
 extern "C" void lasr_debug_set_dw_trace(unsigned long long* buf) { g_dt_trace = buf; }
+unsigned long long* dw_trace_buffer() { return g_dt_trace; }
 
 
 

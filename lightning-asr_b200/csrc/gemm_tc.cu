@@ -440,6 +440,10 @@ struct GemmWsParams {
   int T;
   double* stats;
   unsigned long long* trace;  // debug timeline (tools/trace_gemm.py), normally NULL
+  // TR (series output, data gradients only): tiles are 128-POSITION blocks of the channel-major series layout
+  // (include/lasr.h): block b = (utterance b / tr_bpu, block b % tr_bpu) covers frames [128 j - tr_off, +128) of the
+  // utterance (rows outside [0, T) are zero-filled by TMA), and the result is written transposed, [channel][position]
+  int tr_bpu, tr_off, tr_S, tr_blocks;
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -462,7 +466,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <bool B_MN>
+template <bool B_MN, bool TR = false>
 __global__ void __launch_bounds__(384, 1)
 gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_a2,
@@ -558,7 +562,10 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           if (leader) {
             mbar_arrive_expect_tx(&full_bar[stage], WS_A_BYTES);
-            if (p.cluster == 1) {
+            if constexpr (TR) {
+              const int un = m_blk / p.tr_bpu, uj = m_blk - un * p.tr_bpu;
+              tma_load_3d(s_a + stage * WS_A_BYTES, ma, &full_bar[stage], kb * WS_BK, uj * WS_BM - p.tr_off, un);
+            } else if (p.cluster == 1) {
               tma_load_2d(s_a + stage * WS_A_BYTES, ma, &full_bar[stage], kb * WS_BK, m_blk * WS_BM);
             } else {
               // this CTA fetches its slice of rows and multicasts it; the peers deliver the other slices
@@ -578,7 +585,8 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ===================== MMA issuer (converged warp, elected lane) =====================
     {
       const bool leader = elect_one();
-      constexpr uint32_t idesc = umma_idesc_bf16(WS_BM, WS_BN, 0, B_MN ? 1 : 0);
+      // TR: operands swapped -- A = the weight slice (MN-major), B = the activation tile (K-major): D[channel, frame]
+      constexpr uint32_t idesc = TR ? umma_idesc_bf16(WS_BN, WS_BM, 1, 0) : umma_idesc_bf16(WS_BM, WS_BN, 0, B_MN ? 1 : 0);
       mbar_wait(w_bar, 0);
       tc_fence_after();
       if (leader) WS_TRACE(0, 2);
@@ -603,7 +611,12 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, 64 * WS_BK * 2, 1024)
                                      : umma_desc_sw128(sb + k * 32, 16, 1024);
-            if (leader) umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (leader) {
+              if constexpr (TR)
+                umma_bf16(tmem_d, db, da, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else
+                umma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
           if (leader) {
             if (p.cluster == 1)
@@ -646,6 +659,28 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       named_bar_sync(1, 256);
       if (threadIdx.x == 128) WS_TRACE(5, local_tile);
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * WS_BN;
+      if constexpr (TR) {
+        // lane = channel, columns = the tile's 128 positions: 8 consecutive positions are one 16-byte group, stored at its
+        // pre-swizzled group index (g ^ ((g >> 3) & 1), include/lasr.h) inside the 128-byte-swizzled staging tile
+#pragma unroll
+        for (int ch = 0; ch < WS_BM / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr0 + ch * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = f32x2_to_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+            u.y = f32x2_to_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+            u.z = f32x2_to_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+            u.w = f32x2_to_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+            const int gl = ch * 4 + q;                 // group inside the 128-position block
+            const int glp = gl ^ ((gl >> 3) & 1);
+            uint8_t* sub = s_stg + (glp >> 3) * (WS_BM * 128) + r * 128;
+            *reinterpret_cast<uint4*>(sub + (((glp & 7) ^ (r & 7)) << 4)) = u;
+          }
+        }
+      } else {
 #pragma unroll
       for (int ch = 0; ch < WS_BN / 32; ++ch) {
         const int col0 = n_blk * WS_BN + ch * 32;
@@ -702,6 +737,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           *reinterpret_cast<uint4*>(sub + ((c16 ^ (r & 7)) << 4)) = u;
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -709,9 +745,16 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       named_bar_sync(2, 256);  // staging tile complete
       if (threadIdx.x == 128) WS_TRACE(6, local_tile);
       if (threadIdx.x == 128) {
+        if constexpr (TR) {
+          const int un = m_blk / p.tr_bpu, uj = m_blk - un * p.tr_bpu;
 #pragma unroll
-        for (int j = 0; j < WS_BN / 64; ++j)
-          tma_store_2d(mc, s_stg + j * (WS_BM * 128), n_blk * WS_BN + j * 64, m_blk * WS_BM);
+          for (int j = 0; j < 2; ++j)
+            tma_store_2d(mc, s_stg + j * (WS_BM * 128), un * p.tr_S + uj * WS_BM + j * 64, n_blk * WS_BN);
+        } else {
+#pragma unroll
+          for (int j = 0; j < WS_BN / 64; ++j)
+            tma_store_2d(mc, s_stg + j * (WS_BM * 128), n_blk * WS_BN + j * 64, m_blk * WS_BM);
+        }
         tma_store_commit();
       }
     }
@@ -773,7 +816,7 @@ gemm_ws_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 // multicast to both CTAs' empty and accumulator-full barriers; both CTAs' epilogue warps arrive on the leader's
 // accumulator-empty barrier.  Per CTA: 128 rows x 256 fp32 columns x 2 buffers = all 512 TMEM columns.
 // ------------------------------------------------------------------------------------------------
-template <bool B_MN>
+template <bool B_MN, bool TR = false>
 __global__ void __launch_bounds__(384, 1)
 gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                 const __grid_constant__ CUtensorMap tma_c, const __grid_constant__ CUtensorMap tma_a2,
@@ -864,7 +907,15 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         mbar_wait(&empty_bar[stage], phase ^ 1u);
         if (leader_lane) {
           if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2u * WS_A_BYTES);
-          tma_load_2d_2sm(s_a + stage * WS_A_BYTES, ma, &full_bar[stage], kb * WS_BK, row0);
+          if constexpr (TR) {
+            // this CTA's 128-position block of the pair tile (a block past the end: utterance index out of range, the
+            // whole box is zero-filled)
+            const int ub = 2 * m2 + crank;
+            const int un = ub / p.tr_bpu, uj = ub - un * p.tr_bpu;
+            tma_load_3d_2sm(s_a + stage * WS_A_BYTES, ma, &full_bar[stage], kb * WS_BK, uj * WS_BM - p.tr_off, un);
+          } else {
+            tma_load_2d_2sm(s_a + stage * WS_A_BYTES, ma, &full_bar[stage], kb * WS_BK, row0);
+          }
         }
         __syncwarp();
         if (++stage == p.stages) {
@@ -877,7 +928,8 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
     // ===================== MMA issuer: leader CTA only =====================
     if (is_leader) {
       const bool leader_lane = elect_one();
-      constexpr uint32_t idesc = umma_idesc_bf16(256, 256, 0, B_MN ? 1 : 0);
+      // TR: operands swapped -- A = the pair's 256 weight rows (MN-major), B = its 256 positions (K-major)
+      constexpr uint32_t idesc = TR ? umma_idesc_bf16(256, 256, 1, 0) : umma_idesc_bf16(256, 256, 0, B_MN ? 1 : 0);
       mbar_wait(w_bar, 0);
       tc_fence_after();
       int stage = 0;
@@ -899,7 +951,12 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             const uint64_t da = umma_desc_sw128(sa + k * 32, 16, 1024);
             const uint64_t db = B_MN ? umma_desc_sw128(sb + k * 2048, 64 * WS_BK * 2, 1024)
                                      : umma_desc_sw128(sb + k * 32, 16, 1024);
-            if (leader_lane) umma_bf16_2sm(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (leader_lane) {
+              if constexpr (TR)
+                umma_bf16_2sm(tmem_d, db, da, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              else
+                umma_bf16_2sm(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
           if (leader_lane) umma_commit_2sm(&empty_bar[stage]);
           __syncwarp();
@@ -933,6 +990,27 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         if (threadIdx.x == 128) tma_store_wait_read<0>();
         named_bar_sync(1, 256);
         const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * 256 + h * WS_BN;
+        if constexpr (TR) {
+          // lanes = this CTA's 128 channels (weight rows nw0 ..), columns [128 h, +128) = the positions of block 2 m2 + h
+#pragma unroll
+          for (int ch = 0; ch < WS_BM / 32; ++ch) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr0 + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 u;
+              u.x = f32x2_to_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+              u.y = f32x2_to_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+              u.z = f32x2_to_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+              u.w = f32x2_to_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+              const int gl = ch * 4 + q;
+              const int glp = gl ^ ((gl >> 3) & 1);
+              uint8_t* sub = s_stg + (glp >> 3) * (WS_BM * 128) + r * 128;
+              *reinterpret_cast<uint4*>(sub + (((glp & 7) ^ (r & 7)) << 4)) = u;
+            }
+          }
+        } else {
 #pragma unroll
         for (int ch = 0; ch < WS_BN / 32; ++ch) {
           const int col0 = n0 + h * WS_BN + ch * 32;
@@ -987,6 +1065,7 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
             *reinterpret_cast<uint4*>(sub + ((c16 ^ (r & 7)) << 4)) = u;
           }
         }
+        }
         if (h == 1) {
           tc_fence_before();
           __syncwarp();
@@ -995,9 +1074,19 @@ gemm_ws2_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant
         fence_proxy_async_smem();
         named_bar_sync(2, 256);
         if (threadIdx.x == 128) {
+          if constexpr (TR) {
+            const int ub = 2 * m2 + h;
+            if (ub < p.tr_blocks) {
+              const int un = ub / p.tr_bpu, uj = ub - un * p.tr_bpu;
 #pragma unroll
-          for (int j = 0; j < WS_BN / 64; ++j)
-            tma_store_2d(mc, s_stg + j * (WS_BM * 128), n0 + h * WS_BN + j * 64, m2 * 256 + crank * WS_BM);
+              for (int j = 0; j < 2; ++j)
+                tma_store_2d(mc, s_stg + j * (WS_BM * 128), un * p.tr_S + uj * WS_BM + j * 64, nw0);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < WS_BN / 64; ++j)
+              tma_store_2d(mc, s_stg + j * (WS_BM * 128), n0 + h * WS_BN + j * 64, m2 * 256 + crank * WS_BM);
+          }
           tma_store_commit();
         }
       }
@@ -1341,7 +1430,23 @@ struct WsFused {
   void* out2 = nullptr;
   const int32_t* lengths2 = nullptr;
   double* stats2 = nullptr;
+  // series output (data gradients, b_mn = true): a = dy [sr_n utterances x sr_T frames, K], out(2) = channel-major
+  // series tensors [N][sr_n][sr_S] with frame offset sr_off (include/lasr.h)
+  int sr_n = 0, sr_T = 0, sr_S = 0, sr_off = 0;
 };
+
+// tensor maps of the series mode: activations as {K, T, utterance} (rows outside [0, T) zero-filled), output as
+// {sr_n * sr_S positions, N channels}
+static int series_maps(CUtensorMap* ta, CUtensorMap* tc, const void* a, void* out, const WsFused& fu, int N, int K,
+                       int lda) {
+  const uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(fu.sr_T), static_cast<uint64_t>(fu.sr_n)};
+  const uint64_t strides[2] = {static_cast<uint64_t>(lda) * 2, static_cast<uint64_t>(lda) * 2 * fu.sr_T};
+  const uint32_t box[3] = {64, 128, 1};
+  int rc = make_tmap_nd_bf16(ta, a, 3, dims, strides, box, true);
+  if (rc) return rc;
+  const uint64_t pos = static_cast<uint64_t>(fu.sr_n) * fu.sr_S;
+  return make_tmap_2d_bf16(tc, out, pos, N, pos * 2, 64, 128, true);
+}
 
 // weight-stationary launch; returns LASR_ERR_UNSUPPORTED when the shape does not qualify (caller falls back)
 static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const float* bias, const int32_t* lengths, int T,
@@ -1358,28 +1463,32 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
   // concurrent readers of a tile) and co-residency of clusters costs CTAs.  LASR_GEMM_MULTICAST=1 enables it.
   static const bool use_mc = getenv("LASR_GEMM_MULTICAST") != nullptr;
   const int cluster = (use_mc && (nblk == 2 || nblk == 4 || nblk == 8)) ? nblk : 1;
+  const bool series = fu.sr_n > 0;
+  if (series && (!b_mn || cluster > 1 || (N % WS_BN) || (fu.sr_S % 128))) return LASR_ERR_UNSUPPORTED;
   CUtensorMap ta, tb, tc;
-  int rc = make_tmap_2d_bf16(&ta, a, K, M, static_cast<uint64_t>(lda) * 2, 64, 128 / cluster, true);
+  int rc = series ? series_maps(&ta, &tc, a, out, fu, N, K, lda)
+                  : make_tmap_2d_bf16(&ta, a, K, M, static_cast<uint64_t>(lda) * 2, 64, 128 / cluster, true);
   if (rc) return rc;
   if (!b_mn)
     rc = make_tmap_2d_bf16(&tb, b, K, N, static_cast<uint64_t>(ldb) * 2, 64, WS_BN, true);
   else
     rc = make_tmap_2d_bf16(&tb, b, N, K, static_cast<uint64_t>(ldb) * 2, 64, 64, true);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tc, out, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
+  if (!series) rc = make_tmap_2d_bf16(&tc, out, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
   if (rc) return rc;
   const bool grouped = fu.a2 != nullptr;
   if (grouped && (cluster > 1 || (reinterpret_cast<uintptr_t>(fu.out2) & 15))) return LASR_ERR_UNSUPPORTED;
   CUtensorMap ta2 = ta, tb2 = tb, tc2 = tc;
   if (grouped) {
-    rc = make_tmap_2d_bf16(&ta2, fu.a2, K, M, static_cast<uint64_t>(lda) * 2, 64, 128, true);
+    rc = series ? series_maps(&ta2, &tc2, fu.a2, fu.out2, fu, N, K, lda)
+                : make_tmap_2d_bf16(&ta2, fu.a2, K, M, static_cast<uint64_t>(lda) * 2, 64, 128, true);
     if (rc) return rc;
     if (!b_mn)
       rc = make_tmap_2d_bf16(&tb2, fu.b2, K, N, static_cast<uint64_t>(ldb) * 2, 64, WS_BN, true);
     else
       rc = make_tmap_2d_bf16(&tb2, fu.b2, N, K, static_cast<uint64_t>(ldb) * 2, 64, 64, true);
     if (rc) return rc;
-    rc = make_tmap_2d_bf16(&tc2, fu.out2, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
+    if (!series) rc = make_tmap_2d_bf16(&tc2, fu.out2, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
     if (rc) return rc;
   }
   const int sms = grouped ? kNumSMs / 2 : kNumSMs;  // CTAs available to ONE problem
@@ -1388,6 +1497,13 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
   p.N = N;
   p.K = K;
   p.num_m_blocks = cdiv(M, WS_BM);
+  if (series) {
+    p.tr_bpu = fu.sr_S / 128;
+    p.tr_off = fu.sr_off;
+    p.tr_S = fu.sr_S;
+    p.tr_blocks = fu.sr_n * p.tr_bpu;
+    p.num_m_blocks = p.tr_blocks;
+  }
   p.num_n_blocks = cdiv(N, WS_BN);
   p.num_k_blocks = kbs;
   if (p.num_n_blocks > sms) return LASR_ERR_UNSUPPORTED;
@@ -1416,6 +1532,8 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
     cudaError_t e = cudaFuncSetAttribute(gemm_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(gemm_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_ws_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) {
       lasr_set_cuda_error(e);
       return LASR_ERR_CUDA;
@@ -1461,8 +1579,9 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
   p.lengths2 = fu.lengths2;
   p.stats2 = fu.stats2;
   cfg.gridDim = dim3(p.group_ctas * p.groups);
-  cudaError_t le = b_mn ? cudaLaunchKernelEx(&cfg, gemm_ws_kernel<true>, ta, tb, tc, ta2, tb2, tc2, p)
-                        : cudaLaunchKernelEx(&cfg, gemm_ws_kernel<false>, ta, tb, tc, ta2, tb2, tc2, p);
+  cudaError_t le = series ? cudaLaunchKernelEx(&cfg, gemm_ws_kernel<true, true>, ta, tb, tc, ta2, tb2, tc2, p)
+                   : b_mn ? cudaLaunchKernelEx(&cfg, gemm_ws_kernel<true>, ta, tb, tc, ta2, tb2, tc2, p)
+                          : cudaLaunchKernelEx(&cfg, gemm_ws_kernel<false>, ta, tb, tc, ta2, tb2, tc2, p);
   if (le != cudaSuccess) {
     lasr_set_cuda_error(le);
     return LASR_ERR_CUDA;
@@ -1484,28 +1603,32 @@ static int launch_ws2(bool b_mn, const void* a, const void* b, void* out, const 
   if (mode == 1 && K < 512) return LASR_ERR_UNSUPPORTED;
   if (N < 256 || kbs * WS_WKB_BYTES > 131072) return LASR_ERR_UNSUPPORTED;
   if ((ldc % 8) || (reinterpret_cast<uintptr_t>(out) & 15)) return LASR_ERR_UNSUPPORTED;
+  const bool series = fu.sr_n > 0;
+  if (series && (!b_mn || (N % 256) || (fu.sr_S % 128))) return LASR_ERR_UNSUPPORTED;
   CUtensorMap ta, tb, tc;
-  int rc = make_tmap_2d_bf16(&ta, a, K, M, static_cast<uint64_t>(lda) * 2, 64, 128, true);
+  int rc = series ? series_maps(&ta, &tc, a, out, fu, N, K, lda)
+                  : make_tmap_2d_bf16(&ta, a, K, M, static_cast<uint64_t>(lda) * 2, 64, 128, true);
   if (rc) return rc;
   if (!b_mn)
     rc = make_tmap_2d_bf16(&tb, b, K, N, static_cast<uint64_t>(ldb) * 2, 64, WS_BN, true);
   else
     rc = make_tmap_2d_bf16(&tb, b, N, K, static_cast<uint64_t>(ldb) * 2, 64, 64, true);
   if (rc) return rc;
-  rc = make_tmap_2d_bf16(&tc, out, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
+  if (!series) rc = make_tmap_2d_bf16(&tc, out, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
   if (rc) return rc;
   const bool grouped = fu.a2 != nullptr;
   if (grouped && (reinterpret_cast<uintptr_t>(fu.out2) & 15)) return LASR_ERR_UNSUPPORTED;
   CUtensorMap ta2 = ta, tb2 = tb, tc2 = tc;
   if (grouped) {
-    rc = make_tmap_2d_bf16(&ta2, fu.a2, K, M, static_cast<uint64_t>(lda) * 2, 64, 128, true);
+    rc = series ? series_maps(&ta2, &tc2, fu.a2, fu.out2, fu, N, K, lda)
+                : make_tmap_2d_bf16(&ta2, fu.a2, K, M, static_cast<uint64_t>(lda) * 2, 64, 128, true);
     if (rc) return rc;
     if (!b_mn)
       rc = make_tmap_2d_bf16(&tb2, fu.b2, K, N, static_cast<uint64_t>(ldb) * 2, 64, WS_BN, true);
     else
       rc = make_tmap_2d_bf16(&tb2, fu.b2, N, K, static_cast<uint64_t>(ldb) * 2, 64, 64, true);
     if (rc) return rc;
-    rc = make_tmap_2d_bf16(&tc2, fu.out2, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
+    if (!series) rc = make_tmap_2d_bf16(&tc2, fu.out2, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
     if (rc) return rc;
   }
   GemmWsParams p{};
@@ -1513,6 +1636,13 @@ static int launch_ws2(bool b_mn, const void* a, const void* b, void* out, const 
   p.N = N;
   p.K = K;
   p.num_m_blocks = cdiv(M, 256);   // 256-row pair tiles
+  if (series) {
+    p.tr_bpu = fu.sr_S / 128;
+    p.tr_off = fu.sr_off;
+    p.tr_S = fu.sr_S;
+    p.tr_blocks = fu.sr_n * p.tr_bpu;
+    p.num_m_blocks = cdiv(p.tr_blocks, 2);
+  }
   p.num_n_blocks = cdiv(N, 256);   // 256-column pair slices
   p.num_k_blocks = kbs;
   const int pairs = (kNumSMs / 2) / (grouped ? 2 : 1);  // pairs available to ONE problem
@@ -1544,6 +1674,8 @@ static int launch_ws2(bool b_mn, const void* a, const void* b, void* out, const 
     cudaError_t e = cudaFuncSetAttribute(gemm_ws2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(gemm_ws2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gemm_ws2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
     if (e != cudaSuccess) {
       lasr_set_cuda_error(e);
       return LASR_ERR_CUDA;
@@ -1568,8 +1700,9 @@ static int launch_ws2(bool b_mn, const void* a, const void* b, void* out, const 
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled(1) ? 2 : 1;
-  cudaError_t le = b_mn ? cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<true>, ta, tb, tc, ta2, tb2, tc2, p)
-                        : cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<false>, ta, tb, tc, ta2, tb2, tc2, p);
+  cudaError_t le = series ? cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<true, true>, ta, tb, tc, ta2, tb2, tc2, p)
+                   : b_mn ? cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<true>, ta, tb, tc, ta2, tb2, tc2, p)
+                          : cudaLaunchKernelEx(&cfg, gemm_ws2_kernel<false>, ta, tb, tc, ta2, tb2, tc2, p);
   if (le != cudaSuccess) {
     lasr_set_cuda_error(le);
     return LASR_ERR_CUDA;
@@ -1700,6 +1833,28 @@ int gemm_tc_nn(const void* a, const void* b, void* out, int M, int N, int K, int
     case 128: return launch_inst<128, false, true, 0>(ta, tb, p, grid, stream);
     default: return launch_inst<256, false, true, 0>(ta, tb, p, grid, stream);
   }
+}
+
+// Data gradient(s) written as channel-major series: outT[c][n][off + t] = sum_k dy[n, t, k] w[k, c] (and the same for a
+// second problem of identical shape: the block's residual conv), the operand format of the TMA-fed depthwise kernels.
+// Weight-stationary kernels with swapped operands; LASR_ERR_UNSUPPORTED when the shape does not qualify.
+int gemm_tc_nn_series(const void* dy1, const void* w1, void* outT1, const void* dy2, const void* w2, void* outT2,
+                      int n_utt, int T, int N, int K, int lda, int ldb, int S, int off, cudaStream_t stream) {
+  if (n_utt <= 0 || T <= 0 || N <= 64 || K <= 0 || (lda % 8) || (ldb % 8)) return LASR_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(outT1) & 255) || (dy2 != nullptr && (reinterpret_cast<uintptr_t>(outT2) & 255)))
+    return LASR_ERR_UNSUPPORTED;
+  WsFused fu;
+  fu.sr_n = n_utt;
+  fu.sr_T = T;
+  fu.sr_S = S;
+  fu.sr_off = off;
+  fu.a2 = dy2;
+  fu.b2 = w2;
+  fu.out2 = outT2;
+  const int M = n_utt * T;
+  const int rc2 = launch_ws2(true, dy1, w1, outT1, nullptr, nullptr, 0, nullptr, M, N, K, lda, ldb, 8, stream, fu);
+  if (rc2 != LASR_ERR_UNSUPPORTED) return rc2;
+  return launch_ws(true, dy1, w1, outT1, nullptr, nullptr, 0, nullptr, M, N, K, lda, ldb, 8, stream, fu);
 }
 
 // Two weight gradients of identical shape (the block's pointwise conv and its residual conv) in ONE launch: every CTA

@@ -56,14 +56,22 @@ class SepConvBNFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, res_x, lengths, dw_w, pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2, bn_buffers,
-                rbn_buffers, stride, relu, training, drop=None):
+                rbn_buffers, stride, relu, training, drop=None, xs=None, cm_out=None):
+        """xs: ops.Series companion of x (channel-major, written by the pass that produced x) or None;
+        cm_out: None | [K_next]: ask the apply pass for the Series companion of the OUTPUT, laid out for a depthwise conv
+        of kernel size K_next; it replaces the list's content (autograd Functions return tensors only)."""
         dt = x.dtype
         dev = x.device
         N, T_in, Cin = x.shape
         K = dw_w.shape[-1]
         Cout = pw_w.shape[0]
         act = ACT_RELU if relu else ACT_NONE
-        d = ops.dwconv_fwd(x, dw_w.detach(), stride=stride)
+        if xs is not None and (stride != 1 or xs.K != K or (xs.N, xs.T, xs.C) != (N, T_in, Cin)):
+            xs = None
+        if xs is not None:
+            d = ops.dwconv_fwd_cm(xs, dw_w.detach())  # TMA-fed: the series already exist in memory
+        else:
+            d = ops.dwconv_fwd(x, dw_w.detach(), stride=stride)
         T = d.shape[1]
         pw_s = runtime.weight(pw_w, dt).view(Cout, Cin)
         sums1 = _stats(Cout, dev) if training else None
@@ -90,7 +98,14 @@ class SepConvBNFn(torch.autograd.Function):
             sums_y = ops.sum_over_time(y)
             s, hidden, gate = ops.se_excite_fwd(sums_y, scale1, shift1, T, se_w1.detach(), se_w2.detach())
         dr_ = _make_drop(drop, (N, T, Cout), dev, training)
-        out = ops.bn_apply_act(y, bn1, r, bn2, gate, act, BN_EPS, BN_MOMENTUM, side_effects=se_side, drop=dr_)
+        cm_k = cm_out[0] if cm_out else None
+        if cm_k is not None and dr_ is None and ops.cm_supported(Cout, cm_k, dt):
+            out, cm_out[0] = ops.bn_apply_act(y, bn1, r, bn2, gate, act, BN_EPS, BN_MOMENTUM, side_effects=se_side,
+                                              cm_k=cm_k)
+        else:
+            if cm_out:
+                cm_out[0] = None
+            out = ops.bn_apply_act(y, bn1, r, bn2, gate, act, BN_EPS, BN_MOMENTUM, side_effects=se_side, drop=dr_)
 
         # save_for_backward (not attributes): holding `out` on ctx directly would create an uncollectable
         # node <-> tensor cycle and leak every step's activations
@@ -104,7 +119,7 @@ class SepConvBNFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         if dout is None:
-            return (None,) * 18
+            return (None,) * 20
         (x, res_x, lengths, d, y, r, out, save1, save2, gate, s, hidden, sums_y, scale1, shift1, pw_s, res_s, dw_w,
          pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2, drop_mask) = ctx.saved_tensors
         stride, act, training, K, Cin, Cout, drop_p = ctx.cfg
@@ -189,7 +204,7 @@ class SepConvBNFn(torch.autograd.Function):
             if need_dx:
                 raise RuntimeError("lightning_asr_b200: data gradient of the stride-2 first conv is not needed/implemented")
         return (dx, d_res_x, None, ret_dw, ret_pw, ret_bn_w, ret_bn_b, ret_res, ret_rbn_w, ret_rbn_b, ret_se1, ret_se2,
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None)
 
 
 class Conv1x1BNReLUFn(torch.autograd.Function):

@@ -134,15 +134,64 @@ def series_to_ntc(s):
     return buf[:, :, s.off:s.off + s.T].permute(1, 2, 0).contiguous(), buf
 
 
+def _addends(addend):
+    """addend: None | channels-last tensor | Series -> (channels-last ptr arg, series ptr arg)"""
+    if addend is None:
+        return None, None
+    if isinstance(addend, Series):
+        return None, addend.t
+    return _chk(addend, "addend"), None
+
+
 def dwconv_fwd_cm(xs, w, flip=False, addend=None):
-    """depthwise conv (stride 1, bf16) reading its input from a Series -> y [N, T, C] channels-last"""
+    """depthwise conv (stride 1, bf16) reading its input from a Series -> y [N, T, C] channels-last.
+    addend: channels-last [N, T, C] tensor or a Series laid out like xs."""
     _chk(w, "w")
     K = w.shape[-1]
     if K != xs.K:
         raise _lib.LasrError(f"dwconv_fwd_cm: the series was laid out for K={xs.K}, the conv has K={K}")
     y = torch.empty((xs.N, xs.T, xs.C), device=xs.t.device, dtype=torch.bfloat16)
-    call("lasr_dwconv1d_fwd_cm", xs.t, w, y, addend, xs.N, xs.T, xs.C, K, xs.S, 1 if flip else 0)
+    a_cl, a_cm = _addends(addend)
+    call("lasr_dwconv1d_fwd_cm", xs.t, w, y, a_cl, a_cm, xs.N, xs.T, xs.C, K, xs.S, 1 if flip else 0)
     return y
+
+
+def dwconv_wgrad_cm(xs, dys, K, out=None):
+    """dw [C, 1, K] fp32 += sum dy * shifted x from the Series of x and dy."""
+    dw = out if out is not None else torch.zeros((xs.C, 1, K), device=xs.t.device, dtype=torch.float32)
+    call("lasr_dwconv1d_wgrad_cm", xs.t, dys.t, dw, xs.N, xs.T, xs.C, K, xs.S)
+    return dw
+
+
+def dwconv_bwd_cm(xs, dys, w, addend=None, out_dw=None):
+    """Stride-1 backward in one launch from Series operands -> (dx [N, T, C] channels-last, dw [C, 1, K] fp32)."""
+    _chk(w, "w")
+    K = w.shape[-1]
+    if K != xs.K or K != dys.K or (xs.N, xs.T, xs.C) != (dys.N, dys.T, dys.C):
+        raise _lib.LasrError("dwconv_bwd_cm: the series of x and dy must share the conv's layout")
+    dx = torch.empty((xs.N, xs.T, xs.C), device=xs.t.device, dtype=torch.bfloat16)
+    dw = out_dw if out_dw is not None else torch.zeros((xs.C, 1, K), device=xs.t.device, dtype=torch.float32)
+    a_cl, a_cm = _addends(addend)
+    call("lasr_dwconv1d_bwd_cm", xs.t, dys.t, w, a_cl, a_cm, dx, dw, xs.N, xs.T, xs.C, K, xs.S)
+    return dx, dw
+
+
+def pwconv_dgrad_cm(dy, w, K, dy2=None, w2=None):
+    """Data gradient of a 1x1 conv written as the channel-major Series a depthwise conv of kernel size K consumes:
+    dy [N, T, Cout], w [Cout, Cin] -> Series of dx [N, T, Cin]; (dy2, w2): the block's residual conv in the same launch
+    -> (series1, series2).  Raises LasrError(UNSUPPORTED) for shapes the kernels do not take."""
+    _chk(dy, "dy"), _chk(w, "w")
+    N, T, Cout = dy.shape
+    Cin = w.shape[1]
+    s1 = Series(None, N, T, Cin, K)
+    s1.t = torch.empty((Cin, N, s1.S), device=dy.device, dtype=dy.dtype)
+    s2 = None
+    if dy2 is not None:
+        _chk(dy2, "dy2"), _chk(w2, "w2")
+        s2 = Series(None, N, T, Cin, K)
+        s2.t = torch.empty((Cin, N, s2.S), device=dy.device, dtype=dy.dtype)
+    call("lasr_pwconv_dgrad_cm", dy, w, s1.t, dy2, w2, s2.t if s2 is not None else None, N, T, Cin, Cout, s1.S, s1.off)
+    return (s1, s2) if dy2 is not None else s1
 
 
 def pwconv_fwd(x2d, w, bias=None, lengths=None, T=0, stats=None, out=None, ldy=None):

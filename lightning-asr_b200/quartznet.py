@@ -11,6 +11,8 @@ initialisation under a given torch seed is identical.  Their forward() is never 
 hand-written sm_100a kernels in functions.py, on channels-last activations.  Only MyModel2 is a layout boundary:
 it takes the reference's [N, 1, F, T] fp32 features and returns [N, T', V+1] fp32 log-probs.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -41,6 +43,8 @@ def _bn_buffers(bn):
 
 
 _FOLD = {"enabled": False}
+# channel-major series companions between blocks (csrc/dwconv_cm.cu); LASR_CM=0 is the A/B switch back to the gather kernels
+_CM = {"enabled": os.environ.get("LASR_CM", "1") != "0"}
 
 
 def set_eval_folding(on):
@@ -110,13 +114,19 @@ class SeprationConv(nn.Module):
             return None, None
         return self.se.fc[0].weight, self.se.fc[2].weight
 
-    def forward(self, x, lengths, residual=None, res_x=None, drop_mask=None):
+    def forward(self, x, lengths, residual=None, res_x=None, drop_mask=None, next_k=None):
         """x [N, T, Cin] channels-last.  `residual` = (conv1x1, bn) of the enclosing block to fuse (then ReLU is
         applied after the add, models/QuartNet.py:75-77).  nn.Dropout(drop_rate) (:27,38) is fused into the apply pass;
-        `drop_mask` (uint8 keep mask [N, T, Cout]) replaces the device-drawn mask (parity hook)."""
+        `drop_mask` (uint8 keep mask [N, T, Cout]) replaces the device-drawn mask (parity hook).
+        next_k: kernel size of the depthwise conv that consumes the result (None: unknown / not a depthwise conv).
+        When given (bf16), the apply pass also writes the channel-major series companion of the output and attaches it
+        as `out._lasr_series`; a depthwise conv whose input carries a matching companion reads it through TMA
+        (csrc/dwconv_cm.cu) instead of gathering the series from the channels-last tensor."""
         lens = lengths if self.mask else None
         drop = (self.drop_rate, drop_mask) if (self.drop_rate > 0.0 and self.training) else None
         se1, se2 = self._se_weights()
+        xs = getattr(x, "_lasr_series", None) if _CM["enabled"] else None
+        cm_out = [next_k] if (next_k is not None and _CM["enabled"]) else None
         if self.se is None and _fold_ok(self, x):
             # eval fast path: dw conv -> [residual GEMM + bias] -> ONE GEMM with the whole block epilogue
             d = ops.dwconv_fwd(x, self.depthwise_conv.weight.detach(), stride=self.stride)
@@ -130,12 +140,17 @@ class SeprationConv(nn.Module):
             return ops.pwconv_fwd_fused(d, w1, b1, residual=r, lengths=lens, T=d.shape[1], relu=relu)
         if residual is not None:
             rconv, rbn = residual
-            return SepConvBNFn.apply(x, res_x, lens, self.depthwise_conv.weight, self.pointwise_conv.weight,
-                                     self.bn.weight, self.bn.bias, rconv.weight, rbn.weight, rbn.bias, se1, se2,
-                                     _bn_buffers(self.bn), _bn_buffers(rbn), self.stride, True, self.training, drop)
-        return SepConvBNFn.apply(x, None, lens, self.depthwise_conv.weight, self.pointwise_conv.weight, self.bn.weight,
-                                 self.bn.bias, None, None, None, se1, se2, _bn_buffers(self.bn), None, self.stride,
-                                 not self.last, self.training, drop)
+            out = SepConvBNFn.apply(x, res_x, lens, self.depthwise_conv.weight, self.pointwise_conv.weight,
+                                    self.bn.weight, self.bn.bias, rconv.weight, rbn.weight, rbn.bias, se1, se2,
+                                    _bn_buffers(self.bn), _bn_buffers(rbn), self.stride, True, self.training, drop, xs,
+                                    cm_out)
+        else:
+            out = SepConvBNFn.apply(x, None, lens, self.depthwise_conv.weight, self.pointwise_conv.weight,
+                                    self.bn.weight, self.bn.bias, None, None, None, se1, se2, _bn_buffers(self.bn), None,
+                                    self.stride, not self.last, self.training, drop, xs, cm_out)
+        if cm_out and cm_out[0] is not None:
+            out._lasr_series = cm_out[0]
+        return out
 
 
 class QuartNetBlock(nn.Module):
@@ -154,15 +169,16 @@ class QuartNetBlock(nn.Module):
         self.seq = nn.ModuleList(seq)
         self.drop_rate = drop_rate
 
-    def forward(self, x, lengths, drop_masks=None):
-        """drop_masks: optional list of uint8 keep masks, one per SeprationConv of `seq` (parity hook)."""
+    def forward(self, x, lengths, drop_masks=None, next_k=None):
+        """drop_masks: optional list of uint8 keep masks, one per SeprationConv of `seq` (parity hook).
+        next_k: kernel size of the depthwise conv that follows the block (see SeprationConv.forward)."""
         start = x
         for i, m in enumerate(self.seq[:-1]):
-            x = m(x, lengths, drop_mask=None if drop_masks is None else drop_masks[i])
+            x = m(x, lengths, drop_mask=None if drop_masks is None else drop_masks[i], next_k=self.seq[i + 1].k)
         last = self.seq[-1]
         # dropout sits between BN and the residual add (models/QuartNet.py:38,76): the apply pass does both
         return last(x, lengths, residual=(self.reside[0], self.reside[1]), res_x=None if x is start else start,
-                    drop_mask=None if drop_masks is None else drop_masks[-1])
+                    drop_mask=None if drop_masks is None else drop_masks[-1], next_k=next_k)
 
 
 class BatchLSTM(nn.Module):
@@ -239,9 +255,13 @@ class QuartNet12(nn.Module):
         T_out = (x.shape[1] - 1) // 2 + 1
         lengths = ops.out_lengths(T_out, percents.to(x.device))
         dm = drop_masks or {}
-        x = self.first_cnn(x, lengths, drop_mask=dm.get("first_cnn"))
-        for name in self.block_names:
-            x = getattr(self, name)(x, lengths, drop_masks=[dm[name]] if name in dm else None)
+        blocks = [getattr(self, name) for name in self.block_names]
+        x = self.first_cnn(x, lengths, drop_mask=dm.get("first_cnn"), next_k=blocks[0].seq[0].k)
+        for i, name in enumerate(self.block_names):
+            # the next depthwise conv reads this block's output, unless the BiLSTM splice comes in between
+            spliced = name == "block23" and self.variant != "base"
+            next_k = blocks[i + 1].seq[0].k if (i + 1 < len(blocks) and not spliced) else None
+            x = blocks[i](x, lengths, drop_masks=[dm[name]] if name in dm else None, next_k=next_k)
             if name == "block23" and self.variant != "base":
                 # models/QuartNetContext.py:171-173: length = (T' * percents).int() is the same `lengths` tensor; it
                 # stays on the device (the reference's `.cpu()` sync is gone)

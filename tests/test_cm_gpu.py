@@ -92,3 +92,57 @@ def test_bn_apply_cm_matches_plain_pass_and_layout(ops, N, T, C, K, has_r, has_g
     w = torch.randn(C, 1, K, device=dev) / K ** 0.5
     d = ops.dwconv_fwd_cm(xs, w)
     assert rel_err(d, _dw_ref(out, w.bfloat16().float())) < 6e-3
+
+
+@pytest.mark.parametrize("N,T,Cin,Cout,K", [(32, 801, 256, 256, 33), (32, 801, 256, 512, 51), (32, 801, 512, 512, 63),
+                                            (5, 157, 512, 512, 75), (3, 2001, 256, 256, 39), (1, 40, 128, 256, 33),
+                                            (7, 897, 512, 512, 87)])
+@pytest.mark.parametrize("grouped", [False, True])
+def test_pwconv_dgrad_cm_writes_the_series_of_the_plain_dgrad(ops, N, T, Cin, Cout, K, grouped):
+    torch.manual_seed(T + Cin + Cout)
+    dy = torch.randn(N, T, Cout, device="cuda").bfloat16()
+    w = (torch.randn(Cout, Cin, device="cuda") / Cout ** 0.5).bfloat16()
+    ref = ops.pwconv_dgrad(dy, w)
+    if grouped:
+        dy2 = torch.randn(N, T, Cout, device="cuda").bfloat16()
+        w2 = (torch.randn(Cout, Cin, device="cuda") / Cout ** 0.5).bfloat16()
+        s1, s2 = ops.pwconv_dgrad_cm(dy, w, K, dy2, w2)
+        back2, buf2 = ops.series_to_ntc(s2)
+        assert rel_err(back2, ops.pwconv_dgrad(dy2, w2)) < 1e-2
+        assert buf2[:, :, :s2.off].abs().max().item() == 0 and buf2[:, :, s2.off + T:].abs().max().item() == 0
+    else:
+        s1 = ops.pwconv_dgrad_cm(dy, w, K)
+    back, buf = ops.series_to_ntc(s1)
+    assert rel_err(back, ref) < 1e-2
+    assert rel_err(back, (dy.double().reshape(-1, Cout) @ w.double()).reshape(N, T, Cin)) < 1e-2
+    assert buf[:, :, :s1.off].abs().max().item() == 0 and buf[:, :, s1.off + T:].abs().max().item() == 0
+    assert torch.isfinite(buf.float()).all()
+
+
+@pytest.mark.parametrize("N,T,C,K", [(32, 801, 256, 33), (32, 801, 256, 39), (32, 801, 512, 51), (32, 801, 512, 75),
+                                     (8, 801, 512, 87), (3, 157, 64, 33), (5, 2001, 256, 51), (1, 40, 64, 33),
+                                     (6, 897, 64, 39), (2, 3000, 128, 63)])
+@pytest.mark.parametrize("addend", ["none", "ntc", "series"])
+def test_dwconv_bwd_cm_matches_fp64(ops, N, T, C, K, addend):
+    torch.manual_seed(N + T + C + K)
+    x = torch.randn(N, T, C, device="cuda").bfloat16()
+    dy = torch.randn(N, T, C, device="cuda").bfloat16()
+    w = torch.randn(C, 1, K, device="cuda") / K ** 0.5
+    xs, dys = ops.series_from_ntc(x, K), ops.series_from_ntc(dy, K)
+    add = torch.randn(N, T, C, device="cuda").bfloat16() if addend != "none" else None
+    add_arg = ops.series_from_ntc(add, K) if addend == "series" else add
+    # yardstick: fp64 autograd of the conv on the same bf16 operands (taps rounded to bf16 in the data gradient)
+    xr = x.double().transpose(1, 2).requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    F.conv1d(xr, wr, padding=K // 2, groups=C).backward(dy.double().transpose(1, 2))
+    dx_ref = _dw_ref(dy, w.bfloat16().float(), flip=True)
+    if add is not None:
+        dx_ref = dx_ref + add.double()
+    dx, dw = ops.dwconv_bwd_cm(xs, dys, w, addend=add_arg)
+    assert rel_err(dx, dx_ref) < 6e-3
+    assert rel_err(dw, wr.grad) < 2e-3
+    # separate launches agree
+    dw2 = ops.dwconv_wgrad_cm(xs, dys, K)
+    assert rel_err(dw2, wr.grad) < 2e-3
+    dx2 = ops.dwconv_fwd_cm(dys, w, flip=True, addend=add_arg)
+    assert torch.equal(dx2, dx)
