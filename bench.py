@@ -102,6 +102,19 @@ def algorithmic(name, a, has):
     if name == "lasr_dwconv1d_wgrad":  # N, T_in, T_out, C, K, stride, dtype
         N, Ti, To, C, K, s, dt = a
         return "dwconv", es(dt) * N * C * (Ti + To), 2.0 * N * To * C * K
+    if name == "lasr_dwconv1d_fwd_cm":  # N, T, C, K, S, flip; ptrs xT, w, y, addend, addendT (series operands, bf16)
+        N, T, C, K = a[0], a[1], a[2], a[3]
+        return "dwconv", 2 * N * C * T * (2 + (1 if (has[3] or has[4]) else 0)) + 4 * C * K, 2.0 * N * T * C * K
+    if name == "lasr_dwconv1d_bwd_cm":  # N, T, C, K, S; ptrs xT, dyT, w, addend, addendT, dx, dw
+        N, T, C, K = a[0], a[1], a[2], a[3]
+        return "dwconv", 2 * N * C * T * (3 + (1 if (has[3] or has[4]) else 0)) + 4 * C * K, 4.0 * N * T * C * K
+    if name == "lasr_pwconv_dgrad_cm":  # N, T, Cin, Cout, S, off; ptrs dy1, w1, dxT1, dy2, w2, dxT2 (one or two problems)
+        N, T, Cin, Cout = a[0], a[1], a[2], a[3]
+        k = 2 if has[3] else 1
+        return "pwconv_gemm", k * 2 * N * T * (Cin + Cout), k * 2.0 * N * T * Cin * Cout
+    if name == "lasr_bn_apply_act_fwd_cm":  # N, T, C, S, off, ...; ptrs y, bn1, r, bn2, gate, out, outT: + the series write
+        N, T, C = a[0], a[1], a[2]
+        return "bn_pass", 2 * N * T * C * ((3 if has[2] else 2) + 1), 4.0 * N * T * C
     if name == "lasr_bn_apply_act_fwd":  # M, C, T, count, eps, momentum, act, side_effects, dtype; ptrs y,bn1,r,bn2,gate,out
         M, C, dt = a[0], a[1], a[8]
         return "bn_pass", es(dt) * M * C * (3 if has[2] else 2), 4.0 * M * C
@@ -121,7 +134,7 @@ def algorithmic_family(name):
         return "pwconv_gemm"
     if name.startswith("lasr_dwconv"):
         return "dwconv"
-    if name in ("lasr_bn_apply_act_fwd", "lasr_bn_act_bwd_reduce", "lasr_bn_act_bwd_apply"):
+    if name in ("lasr_bn_apply_act_fwd", "lasr_bn_apply_act_fwd_cm", "lasr_bn_act_bwd_reduce", "lasr_bn_act_bwd_apply"):
         return "bn_pass"
     if name == "lasr_novograd_step":
         return "novograd"

@@ -357,6 +357,7 @@ constexpr int WG_STAGE = WG_XB + WG_DB;              // 72 KB
 struct DwCmWgParams {
   float* dw;
   int N, C, K, sh, chunks, items_per_cg, num_cg, ctas_per_cg, stages;
+  unsigned long long* trace;
 };
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
@@ -380,7 +381,7 @@ __device__ __forceinline__ void dwconv_cm_wgrad_body(const CUtensorMap* __restri
   uint64_t* empty_bar = bars + 4;  // [4]
   uint64_t* done_bar = bars + 8;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 9);
-  float* s_dw = reinterpret_cast<float*>(s_ser);  // [16][K] diagonal sums: re-uses stage 0 after the last MMA
+  float* s_dw = reinterpret_cast<float*>(s_ser);  // [16][128][17] accumulator copy: re-uses the stages after the last MMA
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -410,6 +411,10 @@ __device__ __forceinline__ void dwconv_cm_wgrad_body(const CUtensorMap* __restri
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();
   const bool has_items = first < p.items_per_cg;
+  if (threadIdx.x == 0) {
+    DW_TRACE(p.trace, 7, 0);
+    DW_TRACE(p.trace, 7, 1);
+  }
 
   if (warp_idx == W_TMA) {
     if (lane == 0) {
@@ -418,6 +423,7 @@ __device__ __forceinline__ void dwconv_cm_wgrad_body(const CUtensorMap* __restri
         const int stage = it % p.stages;
         const uint32_t phase = (it / p.stages) & 1;
         mbar_wait(&empty_bar[stage], phase ^ 1u);
+        DW_TRACE(p.trace, 0, it);
         mbar_arrive_expect_tx(&full_bar[stage], WG_STAGE);
         const int n = idx / p.chunks, q = idx - n * p.chunks;
         uint8_t* base = s_ser + stage * WG_STAGE;
@@ -434,6 +440,7 @@ __device__ __forceinline__ void dwconv_cm_wgrad_body(const CUtensorMap* __restri
       const uint32_t phase = (it / p.stages) & 1;
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
+      if (leader) DW_TRACE(p.trace, 3, it);
       const uint32_t xs = smem_u32(s_ser + stage * WG_STAGE);
       // A starts sh positions before the chunk (the X box starts one 128-position block before it)
       uint64_t da_c = umma_desc_sw32_mn(xs + (128 - p.sh) * 2, 32, 256);
@@ -458,45 +465,52 @@ __device__ __forceinline__ void dwconv_cm_wgrad_body(const CUtensorMap* __restri
         db_c += WG_CHUNK * 2 >> 4;
         tmem_d += 16;
       }
-      if (leader) umma_commit(&empty_bar[stage]);
+      if (leader) {
+        umma_commit(&empty_bar[stage]);
+        DW_TRACE(p.trace, 4, it);
+      }
       __syncwarp();
     }
     if (leader) umma_commit(done_bar);
   }
-  // ===================== epilogue: all 11 warps zero the tap sums, warps 0-3 fold the diagonals =====================
+  // ===================== epilogue: accumulators -> shared memory (warps 0-7, two per TMEM lane quadrant), then every
+  // thread folds the diagonals dw[c][j] = sum_t D_c[t + j - e, t] and adds them to the gradient =====================
   if (has_items) {
-    if (warp_idx < 4 || warp_idx == W_MMA) {
-      // nothing: the MMA warp falls through after its last commit, warps 0-3 wait below
-    }
     mbar_wait(done_bar, 0);  // every MMA has retired: the series buffers are free
     tc_fence_after();
-    for (int i = threadIdx.x; i < DT_CG * p.K; i += CM_THREADS) s_dw[i] = 0.f;
-  }
-  __syncthreads();
-  if (has_items && warp_idx < 4) {
-    const int tp = warp_idx * 32 + lane;  // t'
-    const int e = p.K / 2 - p.sh;         // j = t' - t + e
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16);
+    if (threadIdx.x == 0) DW_TRACE(p.trace, 5, 0);
+    if (warp_idx < 8) {
+      const int quad = warp_idx & 3, chalf = warp_idx >> 2;
+      const int tp = quad * 32 + lane;  // t'
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < DT_CG; ++c) {
-      uint32_t v[16];
-      tmem_ld_32x32_x16(taddr + c * 16, v);
-      tmem_ld_wait();
+      for (int c = chalf * 8; c < chalf * 8 + 8; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32_x16(taddr + c * 16, v);
+        tmem_ld_wait();
+        float* dst = s_dw + (c * 128 + tp) * 17;
 #pragma unroll
-      for (int t = 0; t < 16; ++t) {
-        const int j = tp - t + e;
-        if (j >= 0 && j < p.K) atomicAdd(s_dw + c * p.K + j, __uint_as_float(v[t]));
+        for (int t = 0; t < 16; ++t) dst[t] = __uint_as_float(v[t]);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (has_items) {
+    const int e = p.K / 2 - p.sh;  // j = t' - t + e
     for (int i = threadIdx.x; i < DT_CG * p.K; i += CM_THREADS) {
-      const int c = i / p.K;
-      if (c0 + c < p.C) atomicAdd(p.dw + static_cast<size_t>(c0) * p.K + i, s_dw[i]);
+      const int c = i / p.K, j = i - c * p.K;
+      const float* src = s_dw + c * 128 * 17;
+      float acc = 0.f;
+#pragma unroll
+      for (int t = 0; t < 16; ++t) {
+        const int tp = j - e + t;
+        if (tp >= 0 && tp < 128) acc += src[tp * 17 + t];
+      }
+      if (c0 + c < p.C) atomicAdd(p.dw + static_cast<size_t>(c0) * p.K + i, acc);
     }
   }
+  if (threadIdx.x == 0) DW_TRACE(p.trace, 7, 2);
   if (warp_idx == W_TMA) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
@@ -640,6 +654,7 @@ static void cm_wg_params(DwCmWgParams& p, float* dw, int N, int C, int K, int S,
   const int rounds = cdiv(p.items_per_cg, per);
   p.ctas_per_cg = cdiv(p.items_per_cg, rounds);
   p.stages = rounds < 3 ? (rounds < 2 ? 2 : rounds) : 3;
+  p.trace = dw_trace_buffer();
 }
 
 static int cm_wg_smem(const DwCmWgParams& p) { return 1024 + p.stages * WG_STAGE + 256; }

@@ -111,7 +111,7 @@ class SepConvBNFn(torch.autograd.Function):
         # node <-> tensor cycle and leak every step's activations
         ctx.save_for_backward(x, res_x, lengths, d, y, r, out, bn1.save, bn2.save if bn2 is not None else None, gate, s,
                               hidden, sums_y, scale1, shift1, pw_s, res_s, dw_w, pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b,
-                              se_w1, se_w2, dr_.mask if dr_ is not None else None)
+                              se_w1, se_w2, dr_.mask if dr_ is not None else None, xs.t if xs is not None else None)
         ctx.cfg = (stride, act, training, K, Cin, Cout, dr_.p if dr_ is not None else 0.0)
         ctx.set_materialize_grads(False)
         return out
@@ -121,7 +121,7 @@ class SepConvBNFn(torch.autograd.Function):
         if dout is None:
             return (None,) * 20
         (x, res_x, lengths, d, y, r, out, save1, save2, gate, s, hidden, sums_y, scale1, shift1, pw_s, res_s, dw_w,
-         pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2, drop_mask) = ctx.saved_tensors
+         pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2, drop_mask, xs_t) = ctx.saved_tensors
         stride, act, training, K, Cin, Cout, drop_p = ctx.cfg
         drop = ops.Dropout(drop_mask, drop_p, "read") if drop_mask is not None else None
         if not training:
@@ -181,6 +181,21 @@ class SepConvBNFn(torch.autograd.Function):
                     runtime.grad_ready(res_w)
                 runtime.defer(_res_wgrad, dr, rin)
         want_dxr = has_res and ((res_x is None and need_dx) or (res_x is not None and ctx.needs_input_grad[1]))
+        # series path (csrc/dwconv_cm.cu): the forward read x as a channel-major series; the data-gradient GEMMs write the
+        # depthwise conv's upstream gradient (and the residual branch's gradient, its addend) in the same format
+        series = (xs_t is not None and need_dx and stride == 1 and Cin % 128 == 0 and Cout <= 512 and Cout % 64 == 0
+                  and (not want_dxr or (res_x is None and res_s.shape == pw_s.shape)))
+        if series:
+            xs = ops.Series(xs_t, x.shape[0], x.shape[1], Cin, K)
+            if want_dxr:
+                dd_s, dxr_s = ops.pwconv_dgrad_cm(dy, pw_s, K, dr, res_s)
+            else:
+                dd_s, dxr_s = ops.pwconv_dgrad_cm(dy, pw_s, K), None
+            g_dw, ret_dw = runtime.grad_sink(dw_w)
+            dx, _ = ops.dwconv_bwd_cm(xs, dd_s, dw_w.detach(), addend=dxr_s, out_dw=g_dw)
+            runtime.grad_ready(dw_w)
+            return (dx, d_res_x, None, ret_dw, ret_pw, ret_bn_w, ret_bn_b, ret_res, ret_rbn_w, ret_rbn_b, ret_se1,
+                    ret_se2, None, None, None, None, None, None, None, None)
         if want_dxr and res_s.shape == pw_s.shape:
             dd, dxr = ops.pwconv_dgrad2(dy, pw_s, dr, res_s)  # both data gradients in one grouped launch
         else:

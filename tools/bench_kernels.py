@@ -86,6 +86,18 @@ def bench_dwcm():
         report(f"dwconv_fwd_cm   C={c} k={k}", timeit(lambda: ops.dwconv_fwd_cm(xs, w)), by, fl)
         add = torch.randn(N, T, c, device=dev).bfloat16()
         report(f"dwconv_dgrad_cm+addend C={c} k={k}", timeit(lambda: ops.dwconv_fwd_cm(xs, w, flip=True, addend=add)), by + 2 * M * c, fl)
+        adds = ops.series_from_ntc(add, k)
+        report(f"dwconv_dgrad_cm+series addend C={c} k={k}", timeit(lambda: ops.dwconv_fwd_cm(xs, w, flip=True, addend=adds)), by + 2 * M * c, fl)
+        dw = torch.zeros(c, 1, k, device=dev)
+        report(f"dwconv_wgrad_cm C={c} k={k}", timeit(lambda: ops.dwconv_wgrad_cm(xs, adds, k, out=dw)), by, fl)
+        report(f"dwconv_bwd_cm (dgrad+series addend, wgrad) C={c} k={k}", timeit(lambda: ops.dwconv_bwd_cm(xs, adds, w, addend=adds, out_dw=dw)), 2 * M * c * 4, 2 * fl)
+    for cin, cout, k in [(256, 256, 33), (256, 512, 51), (512, 512, 63)]:
+        dy = torch.randn(N, T, cout, device=dev).bfloat16()
+        dr = torch.randn(N, T, cout, device=dev).bfloat16()
+        w = (torch.randn(cout, cin, device=dev) / cin ** 0.5).bfloat16()
+        by, fl = 2 * M * (cin + cout), 2.0 * M * cin * cout
+        report(f"pwconv_dgrad2 (grouped) {cin}<-{cout}", timeit(lambda: ops.pwconv_dgrad2(dy, w, dr, w)), 2 * by, 2 * fl)
+        report(f"pwconv_dgrad_cm (grouped, series out) {cin}<-{cout}", timeit(lambda: ops.pwconv_dgrad_cm(dy, w, k, dr, w)), 2 * by, 2 * fl)
     for c in (256, 512):
         y = torch.randn(N, T, c, device=dev).bfloat16()
         r = torch.randn(N, T, c, device=dev).bfloat16()

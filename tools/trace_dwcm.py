@@ -16,8 +16,15 @@ for c, k in [(512, 63), (256, 33)]:
     x = torch.randn(N, T, c, device="cuda").bfloat16()
     w = torch.randn(c, 1, k, device="cuda") / k ** 0.5
     xs = ops.series_from_ntc(x, k)
-    add = torch.randn_like(x) if which == "dgrad" else None
-    run = lambda: ops.dwconv_fwd_cm(xs, w, flip=which == "dgrad", addend=add)
+    add = ops.series_from_ntc(torch.randn_like(x), k) if which in ("dgrad", "bwd") else None
+    dwb = torch.zeros(c, 1, k, device="cuda")
+    if which == "bwd":
+        run = lambda: ops.dwconv_bwd_cm(xs, add, w, addend=add, out_dw=dwb)
+    elif which == "wgrad":
+        add = ops.series_from_ntc(torch.randn_like(x), k)
+        run = lambda: ops.dwconv_wgrad_cm(xs, add, k, out=dwb)
+    else:
+        run = lambda: ops.dwconv_fwd_cm(xs, w, flip=which == "dgrad", addend=add)
     run()
     trace = torch.zeros(148 * 8 * 16, device="cuda", dtype=torch.int64)
     torch.cuda.synchronize()
