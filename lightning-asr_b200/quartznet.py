@@ -44,7 +44,7 @@ def _bn_buffers(bn):
 
 _FOLD = {"enabled": False}
 # channel-major series companions between blocks (csrc/dwconv_cm.cu); LASR_CM=0 is the A/B switch back to the gather kernels
-_CM = {"enabled": os.environ.get("LASR_CM", "1") != "0"}
+_CM = {"enabled": os.environ.get("LASR_CM", "1") != "0", "max_bytes": int(os.environ.get("LASR_CM_MAX_MB", "96")) << 20}
 
 
 def set_eval_folding(on):
@@ -126,7 +126,10 @@ class SeprationConv(nn.Module):
         drop = (self.drop_rate, drop_mask) if (self.drop_rate > 0.0 and self.training) else None
         se1, se2 = self._se_weights()
         xs = getattr(x, "_lasr_series", None) if _CM["enabled"] else None
-        cm_out = [next_k] if (next_k is not None and _CM["enabled"]) else None
+        # the companion pays (one more write stream in the apply pass) while the depthwise conv can read it back from
+        # L2; at inference batch sizes (hundreds of MB per activation) everything streams through HBM and it loses
+        small = x.shape[0] * x.shape[1] * self.pointwise_conv.out_channels * 2 <= _CM["max_bytes"]
+        cm_out = [next_k] if (next_k is not None and _CM["enabled"] and small) else None
         if self.se is None and _fold_ok(self, x):
             # eval fast path: dw conv -> [residual GEMM + bias] -> ONE GEMM with the whole block epilogue
             d = ops.dwconv_fwd(x, self.depthwise_conv.weight.detach(), stride=self.stride)

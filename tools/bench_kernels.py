@@ -112,6 +112,17 @@ def bench_dwcm():
         bn2 = ops.BNForward(g, b, rm.clone(), rv.clone(), nbt.clone(), sums(r))
         report(f"bn_apply_act_fwd (res) C={c}", timeit(lambda: ops.bn_apply_act(y, bn1, r, bn2)), 2 * M * c * 3, 0)
         report(f"bn_apply_act_fwd_cm (res) C={c}", timeit(lambda: ops.bn_apply_act(y, bn1, r, bn2, cm_k=51)), 2 * M * c * 4, 0)
+    for c in (256, 512):  # inference shape (config 5): everything streams through DRAM
+        Nb, Tb = 256, 1501
+        y = torch.randn(Nb, Tb, c, device=dev).bfloat16()
+        r = torch.randn(Nb, Tb, c, device=dev).bfloat16()
+        g = torch.ones(c, device=dev)
+        b = torch.zeros(c, device=dev)
+        rm, rv, nbt = torch.zeros(c, device=dev), torch.ones(c, device=dev), torch.zeros((), device=dev, dtype=torch.long)
+        bn1 = ops.BNForward(g, b, rm, rv, nbt, None)
+        bn2 = ops.BNForward(g, b, rm.clone(), rv.clone(), nbt.clone(), None)
+        report(f"bn_apply_act_fwd eval b256x30s C={c}", timeit(lambda: ops.bn_apply_act(y, bn1, r, bn2)), 2 * Nb * Tb * c * 3, 0)
+        report(f"bn_apply_act_fwd_cm eval b256x30s C={c}", timeit(lambda: ops.bn_apply_act(y, bn1, r, bn2, cm_k=51)), 2 * Nb * Tb * c * 4, 0)
 
 
 def bench_bn():
