@@ -120,10 +120,13 @@ def algorithmic(name, a, has):
         return "bn_pass", es(dt) * M * C * (3 if has[2] else 2), 4.0 * M * C
     if name == "lasr_bn_act_bwd_reduce":  # N, T, C, act, dtype; ptrs dout,out,y,r,totals,per_n
         N, T, C, act, dt = a
-        return "bn_pass", es(dt) * N * T * C * ((3 if act else 2) + (1 if has[3] else 0)), 6.0 * N * T * C
+        # the ReLU gate is read from `out` (has[1]) or from its sign bits (1 byte per 8 channels)
+        gate_b = (es(dt) if has[1] else 0.125) if act else 0
+        return "bn_pass", N * T * C * (2 * es(dt) + gate_b + (es(dt) if has[3] else 0)), 6.0 * N * T * C
     if name == "lasr_bn_act_bwd_apply":  # count, T, M, C, act, dtype; ptrs dout,out,y,r,...
         _, T, M, C, act, dt = a
-        return "bn_pass", es(dt) * M * C * ((4 if act else 3) + (2 if has[3] else 0)), 6.0 * M * C
+        gate_b = (es(dt) if has[1] else 0.125) if act else 0
+        return "bn_pass", M * C * (3 * es(dt) + gate_b + (2 * es(dt) if has[3] else 0)), 6.0 * M * C
     if name == "lasr_novograd_step":  # reads p, g, m; writes p, m (+ bf16 shadow): 22 B per parameter element
         return "novograd", 0, 0.0
     return algorithmic_family(name), 0, 0.0

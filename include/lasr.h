@@ -189,9 +189,13 @@ int lasr_sum_over_time(const void* y, float* sums, int N, int T, int C, int dtyp
 
 /* out = act( BN1(y) [* gate[n,c]] [* dropout] [+ BN2(r)] );  y, r, out [M, C]; gate [M/T, C] nullable; r / bn2 nullable
  * together; drop nullable.  One pass; side_effects != 0 performs the training side effects of bn1 and bn2 exactly once. */
+/* relu_bits (nullable, every pass below): the sign of the forward output as one byte per (frame, 8 channels), bit i =
+ * out[n, t, 8 cv + i] > 0, laid out [N][ceil(T / 8)][C / 8][8] (needs M == N * T).  The forward passes write it, the
+ * backward passes then read it INSTEAD of the whole `out` tensor (which may be NULL there). */
 int lasr_bn_apply_act_fwd(const void* y, const lasr_bn_t* bn1, const void* r, const lasr_bn_t* bn2, const float* gate,
                           void* out, int M, int C, int T, int count, float eps, float momentum, int act,
-                          int side_effects, const lasr_dropout_t* drop, int dtype, lasr_stream_t stream);
+                          int side_effects, const lasr_dropout_t* drop, int dtype, uint8_t* relu_bits,
+                          lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Channel-major series: the operand format of the TMA-fed depthwise kernels (bf16 only).
@@ -205,7 +209,7 @@ int lasr_cm_offset(int K);
 int lasr_cm_pitch(int T, int K);
 int lasr_bn_apply_act_fwd_cm(const void* y, const lasr_bn_t* bn1, const void* r, const lasr_bn_t* bn2, const float* gate,
                              void* out, void* outT, int N, int T, int C, int S, int off, float eps, float momentum,
-                             int act, int side_effects, lasr_stream_t stream);
+                             int act, int side_effects, uint8_t* relu_bits, lasr_stream_t stream);
 /* y [N, T, C] channels-last = depthwise conv of the series xT (flip = 1: reversed taps = the data gradient) + an
  * optional addend, given EITHER channels-last (addend [N, T, C]) OR as a series laid out like xT (addendT); same
  * arithmetic as lasr_dwconv1d_fwd(stride 1, bf16) */
@@ -232,7 +236,7 @@ int lasr_pwconv_dgrad_cm(const void* dy1, const void* w1, void* dxT1, const void
 int lasr_bn_bwd_chunks(int N, int T);
 int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, const void* r, double* totals,
                            float* per_n, int N, int T, int C, int act, const lasr_dropout_t* drop, int dtype,
-                           lasr_stream_t stream);
+                           const uint8_t* relu_bits, lasr_stream_t stream);
 /* standalone: coef [3, C] with d(BN input) = coef[0]*g + coef[1]*x + coef[2], from totals slots (0, slot_gx);
  * dgamma / dbeta += (nullable) */
 int lasr_bn_bwd_coef(const double* totals, int C, int count, int slot_gx, const float* gamma, const float* mean,
@@ -245,7 +249,8 @@ int lasr_bn_bwd_coef(const double* totals, int C, int count, int slot_gx, const 
 int lasr_bn_act_bwd_apply(const void* dout, const void* out, const void* y, const void* r, const float* gate,
                           const float* extra, const double* totals, const float* coef1, const lasr_bn_bwd_t* bn1,
                           const lasr_bn_bwd_t* bn2, int count, const int32_t* lengths, int T, void* dy, void* dr,
-                          int M, int C, int act, const lasr_dropout_t* drop, int dtype, lasr_stream_t stream);
+                          int M, int C, int act, const lasr_dropout_t* drop, int dtype, const uint8_t* relu_bits,
+                          lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Squeeze-excitation (models/QuartNetContextSE.py:8-23): gate[n,:] = sigmoid(W2 * relu(W1 * s[n,:])),

@@ -95,6 +95,22 @@ __device__ __forceinline__ void drop_factors(const uint2 m, float scale, float (
 }
 
 // ------------------------------------------------------------------------------------------------
+// ReLU gate bits.  The backward passes only need the SIGN of the forward output (g = dout * [out > 0]); reading the
+// whole bf16 tensor for it is 2 of the 10 streams of the two backward passes.  The forward pass can leave one byte per
+// (frame, 8 channels) instead -- bit i = out[n, t, 8 cv + i] > 0 -- laid out [N][ceil(T / 8)][C / 8][8 frames] so that a
+// thread that owns 8 consecutive frames of a channel vector writes one 8-byte word.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ size_t relu_bits_index(int n, int t, int cv, int Tb, int CV) {
+  return ((static_cast<size_t>(n) * Tb + (t >> 3)) * CV + cv) * 8 + (t & 7);
+}
+__device__ __forceinline__ uint32_t relu_byte(const float (&o)[8]) {
+  uint32_t b = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b |= (o[i] > 0.f ? 1u : 0u) << i;
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------------
 // BatchNorm coefficients.  The pointwise-GEMM epilogue leaves the batch sum / sum of squares of every channel in a
 // double [2, C] buffer (RED.f64); there is NO separate finalize launch: every CTA of the apply pass folds them into
 // scale = gamma * invstd, shift = beta - mean * scale in its prologue (C <= 1024 channels, a few hundred ns), and
@@ -180,7 +196,8 @@ template <typename T, bool HAS_R, bool HAS_GATE, bool HAS_DROP>
 __global__ void __launch_bounds__(256, 2)
 bn_apply_fwd_kernel(const T* __restrict__ y, const lasr_bn_t bn1, const T* __restrict__ r, const lasr_bn_t bn2,
                     const float* __restrict__ gate, T* __restrict__ out, long long total_vec, int CV, int C, int T_len,
-                    double count, float eps, float momentum, int act, int side_effects, const DropArgs drop) {
+                    double count, float eps, float momentum, int act, int side_effects, const DropArgs drop,
+                    uint8_t* __restrict__ relu_bits) {
   pdl_launch_dependents();
   pdl_wait();  // the statistics come from the GEMM right before this pass
   extern __shared__ float coef_s[];  // [4][C]
@@ -280,6 +297,10 @@ bn_apply_fwd_kernel(const T* __restrict__ y, const lasr_bn_t bn1, const T* __res
         for (int i = 0; i < 8; ++i) o[i] = fmaxf(o[i], 0.f);
       }
       Vec8<T>::store(out + v * 8, o);
+      if (relu_bits != nullptr) {
+        const int n = row / T_len;
+        relu_bits[relu_bits_index(n, row - n * T_len, cv, (T_len + 7) >> 3, CV)] = static_cast<uint8_t>(relu_byte(o));
+      }
     }
   }
 }
@@ -305,7 +326,7 @@ __global__ void __launch_bounds__(256, 2)
 bn_apply_fwd_cm_kernel(const __nv_bfloat16* __restrict__ y, const lasr_bn_t bn1, const __nv_bfloat16* __restrict__ r,
                        const lasr_bn_t bn2, const float* __restrict__ gate, __nv_bfloat16* __restrict__ out,
                        __nv_bfloat16* __restrict__ outT, int N, int T_len, int C, int S, int off, double count, float eps,
-                       float momentum, int act, int side_effects) {
+                       float momentum, int act, int side_effects, uint8_t* __restrict__ relu_bits) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float coef_s[];  // [4][C]
@@ -371,6 +392,7 @@ bn_apply_fwd_cm_kernel(const __nv_bfloat16* __restrict__ y, const lasr_bn_t bn1,
     }
     if constexpr (HAS_GATE) load8f(gate + static_cast<size_t>(n) * C + c, gt);
     uint4 o[8];
+    uint32_t rb[2] = {0u, 0u};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int f = f0 + i;
@@ -396,11 +418,15 @@ bn_apply_fwd_cm_kernel(const __nv_bfloat16* __restrict__ y, const lasr_bn_t bn1,
       o[i].y = f32x2_to_bf16x2(v[2], v[3]);
       o[i].z = f32x2_to_bf16x2(v[4], v[5]);
       o[i].w = f32x2_to_bf16x2(v[6], v[7]);
-      if (f >= 0 && f < T_len)
+      if (f >= 0 && f < T_len) {
         *reinterpret_cast<uint4*>(out + (row0 + f) * C + c) = o[i];
-      else
+        rb[i >> 2] |= relu_byte(v) << (8 * (i & 3));
+      } else {
         o[i] = make_uint4(0u, 0u, 0u, 0u);  // the conv's zero padding
+      }
     }
+    if (relu_bits != nullptr && f0 >= 0 && f0 < T_len)
+      *reinterpret_cast<uint2*>(relu_bits + relu_bits_index(n, f0, c >> 3, (T_len + 7) >> 3, C >> 3)) = make_uint2(rb[0], rb[1]);
     // 8 frames x 8 channels -> 8 channels x 8 frames; group g is stored at its swizzled index
     const int gs = g ^ ((g >> 3) & 1);
     __nv_bfloat16* dst = outT + (static_cast<size_t>(c) * N + n) * S + static_cast<size_t>(gs) * 8;
@@ -458,7 +484,8 @@ template <typename T, bool HAS_R, bool HAS_DROP>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, const T* __restrict__ y,
                      const T* __restrict__ r, double* __restrict__ totals, float* __restrict__ per_n, int T_len, int C,
-                     int chunks, int rows_per_chunk, int act, const uint8_t* __restrict__ drop_mask, float drop_scale) {
+                     int chunks, int rows_per_chunk, int act, const uint8_t* __restrict__ drop_mask, float drop_scale,
+                     const uint8_t* __restrict__ relu_bits, int T_true) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int NS = HAS_DROP ? 4 : 3;  // slots: sum g, sum g1*y, sum g*r [, sum g1]; g1 = g * dropout factor
@@ -481,9 +508,11 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
     const T* base_r = HAS_R ? r + static_cast<size_t>(n) * T_len * C + cv * 8 : nullptr;
     const uint8_t* base_m = HAS_DROP ? drop_mask + static_cast<size_t>(n) * T_len * C + cv * 8 : nullptr;
     const bool relu = act == LASR_ACT_RELU;
+    const int Tb = (T_true + 7) >> 3;
     for (int tt = t0 + tr; tt < t1; tt += U * rows_par) {
       Raw gr[U], yr[U], orr[U], rrr[U];
       uint2 mr[U];
+      uint32_t ob[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int t = tt + u * rows_par;
@@ -491,7 +520,15 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
           const size_t off = static_cast<size_t>(t) * C;
           gr[u] = Vec8<T>::ldraw(base_g + off);
           yr[u] = Vec8<T>::ldraw(base_y + off);
-          if (relu) orr[u] = Vec8<T>::ldraw(base_o + off);
+          if (relu) {
+            if (relu_bits != nullptr) {
+              const int rowg = n * T_len + t;  // (the rows may have been flattened into one "utterance")
+              const int nn = rowg / T_true;
+              ob[u] = relu_bits[relu_bits_index(nn, rowg - nn * T_true, cv, Tb, CV)];
+            } else {
+              orr[u] = Vec8<T>::ldraw(base_o + off);
+            }
+          }
           if constexpr (HAS_R) rrr[u] = Vec8<T>::ldraw(base_r + off);
           if constexpr (HAS_DROP) mr[u] = *reinterpret_cast<const uint2*>(base_m + off);
         }
@@ -504,9 +541,14 @@ bn_bwd_reduce_kernel(const T* __restrict__ dout, const T* __restrict__ out, cons
         Vec8<T>::unpack(gr[u], g);
         Vec8<T>::unpack(yr[u], yy);
         if (relu) {
-          Vec8<T>::unpack(orr[u], o);
+          if (relu_bits != nullptr) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+            for (int i = 0; i < 8; ++i) g[i] = ((ob[u] >> i) & 1u) ? g[i] : 0.f;
+          } else {
+            Vec8<T>::unpack(orr[u], o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+          }
         }
         if constexpr (HAS_DROP) {
           // the gated / normalised branch sees g1 = g * m / (1-p); the residual branch sees g
@@ -610,7 +652,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
                     const double* __restrict__ totals, const float* __restrict__ coef1_in, const BnBwdSide bn1,
                     const BnBwdSide bn2, double count, const int32_t* __restrict__ lengths, int T_len,
                     T* __restrict__ dy, T* __restrict__ dr, long long total_vec, int CV, int C, int act,
-                    const uint8_t* __restrict__ drop_mask, float drop_scale) {
+                    const uint8_t* __restrict__ drop_mask, float drop_scale, const uint8_t* __restrict__ relu_bits) {
   pdl_launch_dependents();
   pdl_wait();  // totals come from the reduce pass right before
   extern __shared__ float coef_s[];  // coef1 [3][C], coef2 [3][C]
@@ -686,6 +728,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
   for (int row0 = static_cast<int>(blockIdx.x) * rpb + r_in; row0 < rows; row0 += U * row_stride) {
     Raw gr[U], orr[U], yr[U], rrr[U];
     uint2 mr[U];
+    uint32_t ob[U];
     bool keep_u[U];
     int n_u[U];
 #pragma unroll
@@ -698,7 +741,12 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
         const int t = row - n_u[u] * T_len;
         keep_u[u] = lengths == nullptr || t < lengths[n_u[u]];
         gr[u] = Vec8<T>::ldraw(dout + v * 8);
-        if (relu) orr[u] = Vec8<T>::ldraw(out + v * 8);
+        if (relu) {
+          if (relu_bits != nullptr)
+            ob[u] = relu_bits[relu_bits_index(n_u[u], t, cv, (T_len + 7) >> 3, CV)];
+          else
+            orr[u] = Vec8<T>::ldraw(out + v * 8);
+        }
         if constexpr (HAS_R) rrr[u] = Vec8<T>::ldraw(r + v * 8);
         if (keep_u[u]) yr[u] = Vec8<T>::ldraw(y + v * 8);
         if constexpr (HAS_DROP) mr[u] = *reinterpret_cast<const uint2*>(drop_mask + v * 8);
@@ -714,10 +762,15 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
       float g[8];
       Vec8<T>::unpack(gr[u], g);
       if (relu) {
-        float o[8];
-        Vec8<T>::unpack(orr[u], o);
+        if (relu_bits != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+          for (int i = 0; i < 8; ++i) g[i] = ((ob[u] >> i) & 1u) ? g[i] : 0.f;
+        } else {
+          float o[8];
+          Vec8<T>::unpack(orr[u], o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) g[i] = o[i] > 0.f ? g[i] : 0.f;
+        }
       }
       if constexpr (HAS_R) {
         float rr[8], d[8];
@@ -765,7 +818,7 @@ static inline int persistent_grid(long long total_vec, int threads) {
 template <typename TT>
 static int bn_fwd_launch(const void* y, const lasr_bn_t& b1, const void* r, const lasr_bn_t& b2, const float* gate,
                          void* out, long long total, int CV, int C, int T, double count, float eps, float momentum,
-                         int act, int side_effects, const DropArgs& drop, cudaStream_t stream) {
+                         int act, int side_effects, const DropArgs& drop, uint8_t* relu_bits, cudaStream_t stream) {
   const int threads = bn_block(CV);
   const int grid = persistent_grid(total, threads);
   const int smem = 4 * C * static_cast<int>(sizeof(float));
@@ -775,7 +828,7 @@ static int bn_fwd_launch(const void* y, const lasr_bn_t& b1, const void* r, cons
   cudaError_t le;
 #define LASR_BN_FWD(R, G, D)                                                                                      \
   le = launch_pdl(4, bn_apply_fwd_kernel<TT, R, G, D>, dim3(grid), dim3(threads), smem, stream, yy, b1, rr, b2, gate, oo, \
-                  total, CV, C, T, count, eps, momentum, act, side_effects, drop)
+                  total, CV, C, T, count, eps, momentum, act, side_effects, drop, relu_bits)
   const int sel = (r != nullptr ? 4 : 0) | (gate != nullptr ? 2 : 0) | (drop.mode != 0 ? 1 : 0);
   switch (sel) {
     case 0: LASR_BN_FWD(false, false, false); break;
@@ -797,7 +850,7 @@ static int bn_bwd_launch(const void* dout, const void* out, const void* y, const
                          const float* extra, const double* totals, const float* coef1, const BnBwdSide& s1,
                          const BnBwdSide& s2, double count, const int32_t* lengths, int T, void* dy, void* dr,
                          long long total, int CV, int C, int act, const uint8_t* drop_mask, float drop_scale,
-                         cudaStream_t stream) {
+                         const uint8_t* relu_bits, cudaStream_t stream) {
   const int threads = bn_block(CV);
   const int grid = persistent_grid(total, threads);
   const int smem = 6 * C * static_cast<int>(sizeof(float));
@@ -810,7 +863,8 @@ static int bn_bwd_launch(const void* dout, const void* out, const void* y, const
   cudaError_t le;
 #define LASR_BN_BWD(R, G, D)                                                                                       \
   le = launch_pdl(4, bn_bwd_apply_kernel<TT, R, G, D>, dim3(grid), dim3(threads), smem, stream, a0, a1, a2, a3, gate,   \
-                  extra, totals, coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, act, drop_mask, drop_scale)
+                  extra, totals, coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, act, drop_mask, drop_scale,   \
+                  relu_bits)
   const int sel = (r != nullptr ? 4 : 0) | (gate != nullptr ? 2 : 0) | (drop_mask != nullptr ? 1 : 0);
   switch (sel) {
     case 0: LASR_BN_BWD(false, false, false); break;
@@ -881,8 +935,10 @@ int lasr_sum_over_time(const void* y, float* sums, int N, int T, int C, int dtyp
 
 int lasr_bn_apply_act_fwd(const void* y, const lasr_bn_t* bn1, const void* r, const lasr_bn_t* bn2, const float* gate,
                           void* out, int M, int C, int T, int count, float eps, float momentum, int act,
-                          int side_effects, const lasr_dropout_t* drop, int dtype, lasr_stream_t stream) {
+                          int side_effects, const lasr_dropout_t* drop, int dtype, uint8_t* relu_bits,
+                          lasr_stream_t stream) {
   if (M <= 0 || C <= 0 || (C % 8) || C > 2048 || count <= 0 || bn1 == nullptr) return LASR_ERR_BAD_SHAPE;
+  if (relu_bits != nullptr && (T <= 0 || (M % T) != 0)) return LASR_ERR_BAD_SHAPE;
   DropArgs da;
   if (int rc = drop_args(drop, da)) return rc;
   if ((r != nullptr) != (bn2 != nullptr)) return LASR_ERR_BAD_SHAPE;
@@ -893,16 +949,16 @@ int lasr_bn_apply_act_fwd(const void* y, const lasr_bn_t* bn1, const void* r, co
   const lasr_bn_t& b2 = bn2 ? *bn2 : none;
   if (dtype == LASR_F32)
     return bn_fwd_launch<float>(y, *bn1, r, b2, gate, out, total, CV, C, T, count, eps, momentum, act, side_effects,
-                                da, stream);
+                                da, relu_bits, stream);
   if (dtype == LASR_BF16)
     return bn_fwd_launch<__nv_bfloat16>(y, *bn1, r, b2, gate, out, total, CV, C, T, count, eps, momentum, act,
-                                        side_effects, da, stream);
+                                        side_effects, da, relu_bits, stream);
   return LASR_ERR_BAD_DTYPE;
 }
 
 int lasr_bn_apply_act_fwd_cm(const void* y, const lasr_bn_t* bn1, const void* r, const lasr_bn_t* bn2, const float* gate,
                              void* out, void* outT, int N, int T, int C, int S, int off, float eps, float momentum,
-                             int act, int side_effects, lasr_stream_t stream) {
+                             int act, int side_effects, uint8_t* relu_bits, lasr_stream_t stream) {
   if (N <= 0 || T <= 0 || C <= 0 || (C % 64) || C > 2048 || bn1 == nullptr || outT == nullptr) return LASR_ERR_BAD_SHAPE;
   if ((r != nullptr) != (bn2 != nullptr)) return LASR_ERR_BAD_SHAPE;
   if (S <= 0 || (S % 128) || off < 0 || (off % 8) || off + T > S) return LASR_ERR_BAD_SHAPE;
@@ -920,7 +976,7 @@ int lasr_bn_apply_act_fwd_cm(const void* y, const lasr_bn_t* bn1, const void* r,
   cudaError_t le;
 #define LASR_BN_CM(R, G)                                                                                           \
   le = launch_pdl(4, bn_apply_fwd_cm_kernel<R, G>, dim3(static_cast<unsigned>(ctas)), dim3(256), smem, stream, yy, *bn1, \
-                  rr, b2, gate, oo, ot, N, T, C, S, off, count, eps, momentum, act, side_effects)
+                  rr, b2, gate, oo, ot, N, T, C, S, off, count, eps, momentum, act, side_effects, relu_bits)
   if (r != nullptr && gate != nullptr) LASR_BN_CM(true, true);
   else if (r != nullptr) LASR_BN_CM(true, false);
   else if (gate != nullptr) LASR_BN_CM(false, true);
@@ -941,8 +997,10 @@ int lasr_bn_bwd_chunks(int N, int T) {
 
 int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, const void* r, double* totals,
                            float* per_n, int N, int T, int C, int act, const lasr_dropout_t* drop, int dtype,
-                           lasr_stream_t stream) {
+                           const uint8_t* relu_bits, lasr_stream_t stream) {
   if (N <= 0 || T <= 0 || C <= 0 || (C % 8) || C > 2048 || totals == nullptr) return LASR_ERR_BAD_SHAPE;
+  if (act == LASR_ACT_RELU && out == nullptr && relu_bits == nullptr) return LASR_ERR_BAD_SHAPE;
+  const int T_true = T;
   DropArgs da;
   if (int rc = drop_args(drop, da)) return rc;
   const uint8_t* dmask = da.mode ? da.mask : nullptr;
@@ -972,7 +1030,8 @@ int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, con
 #define LASR_BN_RED_ONE(TT, R, D)                                                                                  \
   le = launch_pdl(4, bn_bwd_reduce_kernel<TT, R, D>, dim3(grid), dim3(256), smem, stream,                          \
                   static_cast<const TT*>(dout), static_cast<const TT*>(out), static_cast<const TT*>(y),            \
-                  static_cast<const TT*>(r), totals, per_n, T, C, chunks, rows_per_chunk, act, dmask, dscale)
+                  static_cast<const TT*>(r), totals, per_n, T, C, chunks, rows_per_chunk, act, dmask, dscale,      \
+                  relu_bits, T_true)
 #define LASR_BN_RED_LAUNCH(TT)                                                                                     \
   do {                                                                                                             \
     if (r != nullptr && dmask != nullptr) LASR_BN_RED_ONE(TT, true, true);                                         \
@@ -1002,8 +1061,11 @@ int lasr_bn_bwd_coef(const double* totals, int C, int count, int slot_gx, const 
 int lasr_bn_act_bwd_apply(const void* dout, const void* out, const void* y, const void* r, const float* gate,
                           const float* extra, const double* totals, const float* coef1, const lasr_bn_bwd_t* bn1,
                           const lasr_bn_bwd_t* bn2, int count, const int32_t* lengths, int T, void* dy, void* dr,
-                          int M, int C, int act, const lasr_dropout_t* drop, int dtype, lasr_stream_t stream) {
+                          int M, int C, int act, const lasr_dropout_t* drop, int dtype, const uint8_t* relu_bits,
+                          lasr_stream_t stream) {
   if (M <= 0 || C <= 0 || (C % 8) || C > 2048 || T <= 0 || count <= 0) return LASR_ERR_BAD_SHAPE;
+  if (act == LASR_ACT_RELU && out == nullptr && relu_bits == nullptr) return LASR_ERR_BAD_SHAPE;
+  if (relu_bits != nullptr && (M % T) != 0) return LASR_ERR_BAD_SHAPE;
   DropArgs da;
   if (int rc = drop_args(drop, da)) return rc;
   const uint8_t* dmask = da.mode ? da.mask : nullptr;
@@ -1018,10 +1080,10 @@ int lasr_bn_act_bwd_apply(const void* dout, const void* out, const void* y, cons
   if (bn2) s2 = BnBwdSide{bn2->gamma, bn2->mean, bn2->invstd, bn2->dgamma, bn2->dbeta};
   if (dtype == LASR_F32)
     return bn_bwd_launch<float>(dout, out, y, r, gate, extra, totals, coef1, s1, s2, count, lengths, T, dy, dr, total,
-                                CV, C, act, dmask, da.scale, stream);
+                                CV, C, act, dmask, da.scale, relu_bits, stream);
   if (dtype == LASR_BF16)
     return bn_bwd_launch<__nv_bfloat16>(dout, out, y, r, gate, extra, totals, coef1, s1, s2, count, lengths, T, dy,
-                                        dr, total, CV, C, act, dmask, da.scale, stream);
+                                        dr, total, CV, C, act, dmask, da.scale, relu_bits, stream);
   return LASR_ERR_BAD_DTYPE;
 }
 

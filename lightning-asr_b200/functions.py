@@ -11,6 +11,8 @@
 All activations inside are channels-last [N, T, C]; parameters keep the reference's shapes (state_dict schema).
 Backward passes are hand-scheduled kernel sequences, not autograd graphs.
 """
+import os
+
 import torch
 
 from . import ops, runtime
@@ -18,6 +20,7 @@ from .ops import ACT_NONE, ACT_RELU
 
 BN_EPS = 1e-3  # nn.BatchNorm1d(out_ch, eps=1e-3)  models/QuartNet.py:24,64,147
 BN_MOMENTUM = 0.1
+RELU_BITS = os.environ.get("LASR_RELU_BITS", "1") != "0"  # A/B switch: backward passes read `out` again
 
 
 def _stats(C, device):
@@ -99,19 +102,23 @@ class SepConvBNFn(torch.autograd.Function):
             s, hidden, gate = ops.se_excite_fwd(sums_y, scale1, shift1, T, se_w1.detach(), se_w2.detach())
         dr_ = _make_drop(drop, (N, T, Cout), dev, training)
         cm_k = cm_out[0] if cm_out else None
+        # the backward passes read the ReLU gate as one byte per 8 channels instead of the whole output tensor
+        bits = ops.relu_bits_alloc(N, T, Cout, dev) if (training and relu and dr_ is None and RELU_BITS) else None
         if cm_k is not None and dr_ is None and ops.cm_supported(Cout, cm_k, dt):
             out, cm_out[0] = ops.bn_apply_act(y, bn1, r, bn2, gate, act, BN_EPS, BN_MOMENTUM, side_effects=se_side,
-                                              cm_k=cm_k)
+                                              cm_k=cm_k, relu_bits=bits)
         else:
             if cm_out:
                 cm_out[0] = None
-            out = ops.bn_apply_act(y, bn1, r, bn2, gate, act, BN_EPS, BN_MOMENTUM, side_effects=se_side, drop=dr_)
+            out = ops.bn_apply_act(y, bn1, r, bn2, gate, act, BN_EPS, BN_MOMENTUM, side_effects=se_side, drop=dr_,
+                                   relu_bits=bits)
 
         # save_for_backward (not attributes): holding `out` on ctx directly would create an uncollectable
         # node <-> tensor cycle and leak every step's activations
         ctx.save_for_backward(x, res_x, lengths, d, y, r, out, bn1.save, bn2.save if bn2 is not None else None, gate, s,
                               hidden, sums_y, scale1, shift1, pw_s, res_s, dw_w, pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b,
-                              se_w1, se_w2, dr_.mask if dr_ is not None else None, xs.t if xs is not None else None)
+                              se_w1, se_w2, dr_.mask if dr_ is not None else None, xs.t if xs is not None else None,
+                              bits)
         ctx.cfg = (stride, act, training, K, Cin, Cout, dr_.p if dr_ is not None else 0.0)
         ctx.set_materialize_grads(False)
         return out
@@ -121,7 +128,7 @@ class SepConvBNFn(torch.autograd.Function):
         if dout is None:
             return (None,) * 20
         (x, res_x, lengths, d, y, r, out, save1, save2, gate, s, hidden, sums_y, scale1, shift1, pw_s, res_s, dw_w,
-         pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2, drop_mask, xs_t) = ctx.saved_tensors
+         pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2, drop_mask, xs_t, bits) = ctx.saved_tensors
         stride, act, training, K, Cin, Cout, drop_p = ctx.cfg
         drop = ops.Dropout(drop_mask, drop_p, "read") if drop_mask is not None else None
         if not training:
@@ -138,7 +145,7 @@ class SepConvBNFn(torch.autograd.Function):
             g_rbn_b, ret_rbn_b = runtime.grad_sink(rbn_b)
         totals = runtime.zeros((4 if drop is not None else 3, Cout), torch.float64, dev)
         per_n = runtime.zeros((N, 3, Cout), torch.float32, dev) if gate is not None else None
-        ops.bn_act_bwd_reduce(dout, out, y, r, act, totals, per_n, drop=drop)
+        ops.bn_act_bwd_reduce(dout, out, y, r, act, totals, per_n, drop=drop, relu_bits=bits)
         extra = coef1 = None
         ret_se1 = ret_se2 = None
         bn1_side = (bn_w.detach(), save1, g_bn_w, g_bn_b)
@@ -151,7 +158,7 @@ class SepConvBNFn(torch.autograd.Function):
             bn1_side = None
         bn2_side = (rbn_w.detach(), save2, g_rbn_w, g_rbn_b) if has_res else None
         dy, dr = ops.bn_act_bwd_apply(dout, out, y, r, gate, extra, totals, coef1, bn1_side, bn2_side, lengths, act,
-                                      drop=drop)
+                                      drop=drop, relu_bits=bits)
         runtime.grad_ready(bn_w, bn_b, rbn_w, rbn_b, se_w1, se_w2)
 
         # pointwise conv: weight gradient (split-K tcgen05 MN-major GEMM) and data gradient (W as MN-major B operand)
@@ -237,8 +244,9 @@ class Conv1x1BNReLUFn(torch.autograd.Function):
         bn = ops.BNForward(bn_w.detach(), bn_b.detach(), bn_buffers[0], bn_buffers[1], bn_buffers[2], sums)
         act = ACT_RELU if relu else ACT_NONE
         dr_ = _make_drop(drop, (N, T, Cout), x.device, training)  # nn.Dropout after the ReLU (models/QuartNet.py:149)
-        out = ops.bn_apply_act(y, bn, act=act, eps=BN_EPS, momentum=BN_MOMENTUM, drop=dr_)
-        ctx.save_for_backward(x, y, out, bn.save, w_s, w, bn_w, bn_b, dr_.mask if dr_ is not None else None)
+        bits = ops.relu_bits_alloc(N, T, Cout, x.device) if (training and relu and dr_ is None and RELU_BITS) else None
+        out = ops.bn_apply_act(y, bn, act=act, eps=BN_EPS, momentum=BN_MOMENTUM, drop=dr_, relu_bits=bits)
+        ctx.save_for_backward(x, y, out, bn.save, w_s, w, bn_w, bn_b, dr_.mask if dr_ is not None else None, bits)
         ctx.training = training
         ctx.act = act
         ctx.drop_p = dr_.p if dr_ is not None else 0.0
@@ -246,7 +254,7 @@ class Conv1x1BNReLUFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        x, y, out, save, w_s, w, bn_w, bn_b, drop_mask = ctx.saved_tensors
+        x, y, out, save, w_s, w, bn_w, bn_b, drop_mask, bits = ctx.saved_tensors
         if not ctx.training:
             raise RuntimeError("lightning_asr_b200: backward through eval-mode BatchNorm is not implemented")
         dout = dout.contiguous()
@@ -255,11 +263,11 @@ class Conv1x1BNReLUFn(torch.autograd.Function):
         act = ctx.act
         drop = ops.Dropout(drop_mask, ctx.drop_p, "read") if drop_mask is not None else None
         totals = runtime.zeros((4 if drop is not None else 3, Cout), torch.float64, x.device)
-        ops.bn_act_bwd_reduce(dout, out, y, None, act, totals, drop=drop)
+        ops.bn_act_bwd_reduce(dout, out, y, None, act, totals, drop=drop, relu_bits=bits)
         g_w, ret_w = runtime.grad_sink(bn_w)
         g_b, ret_b = runtime.grad_sink(bn_b)
         dy, _ = ops.bn_act_bwd_apply(dout, out, y, None, None, None, totals, None, (bn_w.detach(), save, g_w, g_b),
-                                     None, None, act, drop=drop)
+                                     None, None, act, drop=drop, relu_bits=bits)
         runtime.grad_ready(bn_w, bn_b)
         g_cw, ret_cw = runtime.grad_sink(w)
 

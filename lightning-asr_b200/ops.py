@@ -372,11 +372,17 @@ def sum_over_time(y):
     return sums
 
 
+def relu_bits_alloc(N, T, C, device):
+    """storage of the ReLU gate bits of an [N, T, C] activation (include/lasr.h: one byte per frame and 8 channels)"""
+    return torch.empty((N, (T + 7) // 8, C // 8, 8), device=device, dtype=torch.uint8)
+
+
 def bn_apply_act(y, bn1, r=None, bn2=None, gate=None, act=ACT_RELU, eps=1e-3, momentum=0.1, side_effects=True,
-                 drop=None, cm_k=None):
+                 drop=None, cm_k=None, relu_bits=None):
     """out = act(BN1(y) [* gate] [* dropout] [+ BN2(r)]) in one pass; performs the training side effects of both BNs.
     cm_k = kernel size of the depthwise conv that consumes the result: also writes the channel-major Series companion
-    and returns (out, series)."""
+    and returns (out, series).  relu_bits (relu_bits_alloc): receives the sign bits the backward passes read instead of
+    `out`."""
     N, T, C = y.shape
     out = torch.empty_like(y)
     if drop is not None and drop.mask.numel() != y.numel():
@@ -387,11 +393,11 @@ def bn_apply_act(y, bn1, r=None, bn2=None, gate=None, act=ACT_RELU, eps=1e-3, mo
         xs = Series(None, N, T, C, cm_k)
         xs.t = torch.empty((C, N, xs.S), device=y.device, dtype=y.dtype)
         call("lasr_bn_apply_act_fwd_cm", y, bn1.ptr, r, bn2.ptr if bn2 is not None else None, gate, out, xs.t, N, T, C,
-             xs.S, xs.off, eps, momentum, act, 1 if (side_effects and bn1.training) else 0)
+             xs.S, xs.off, eps, momentum, act, 1 if (side_effects and bn1.training) else 0, relu_bits)
         return out, xs
     call("lasr_bn_apply_act_fwd", y, bn1.ptr, r, bn2.ptr if bn2 is not None else None, gate, out, N * T, C, T, N * T,
          eps, momentum, act, 1 if (side_effects and bn1.training) else 0, drop.ptr if drop is not None else None,
-         dtype_code(y.dtype))
+         dtype_code(y.dtype), relu_bits)
     return out
 
 
@@ -399,13 +405,14 @@ def bn_bwd_chunks(N, T):
     return _lib.load().lasr_bn_bwd_chunks(N, T)
 
 
-def bn_act_bwd_reduce(dout, out, y, r, act, totals, per_n=None, drop=None):
-    """totals: double [3, C] (zeroed); [4, C] with dropout."""
+def bn_act_bwd_reduce(dout, out, y, r, act, totals, per_n=None, drop=None, relu_bits=None):
+    """totals: double [3, C] (zeroed); [4, C] with dropout.  relu_bits: the forward's sign bits (then `out` is not read
+    and may be None)."""
     N, T, C = y.shape
     if totals.shape[0] < (4 if drop is not None else 3):
         raise _lib.LasrError("bn_act_bwd_reduce: totals needs 4 slots with dropout, 3 without")
-    call("lasr_bn_act_bwd_reduce", dout, out, y, r, totals, per_n, N, T, C, act,
-         drop.ptr if drop is not None else None, dtype_code(y.dtype))
+    call("lasr_bn_act_bwd_reduce", dout, out if relu_bits is None else None, y, r, totals, per_n, N, T, C, act,
+         drop.ptr if drop is not None else None, dtype_code(y.dtype), relu_bits)
     return totals
 
 
@@ -416,16 +423,16 @@ def bn_bwd_coef(totals, count, slot_gx, gamma, save, dgamma, dbeta):
     return coef
 
 
-def bn_act_bwd_apply(dout, out, y, r, gate, extra, totals, coef1, bn1, bn2, lengths, act, drop=None):
+def bn_act_bwd_apply(dout, out, y, r, gate, extra, totals, coef1, bn1, bn2, lengths, act, drop=None, relu_bits=None):
     """bn1 / bn2: (gamma, save [2,C], dgamma, dbeta) tuples or None."""
     N, T, C = y.shape
     dy = torch.empty_like(y)
     dr = torch.empty_like(y) if r is not None else None
     s1 = _BNBwd(_p(bn1[0]), _p(bn1[1][0]), _p(bn1[1][1]), _p(bn1[2]), _p(bn1[3])) if bn1 is not None else None
     s2 = _BNBwd(_p(bn2[0]), _p(bn2[1][0]), _p(bn2[1][1]), _p(bn2[2]), _p(bn2[3])) if bn2 is not None else None
-    call("lasr_bn_act_bwd_apply", dout, out, y, r, gate, extra, totals, coef1,
+    call("lasr_bn_act_bwd_apply", dout, out if relu_bits is None else None, y, r, gate, extra, totals, coef1,
          ctypes.addressof(s1) if s1 is not None else None, ctypes.addressof(s2) if s2 is not None else None, N * T,
-         lengths, T, dy, dr, N * T, C, act, drop.ptr if drop is not None else None, dtype_code(y.dtype))
+         lengths, T, dy, dr, N * T, C, act, drop.ptr if drop is not None else None, dtype_code(y.dtype), relu_bits)
     return dy, dr
 
 

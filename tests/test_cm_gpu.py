@@ -146,3 +146,49 @@ def test_dwconv_bwd_cm_matches_fp64(ops, N, T, C, K, addend):
     assert rel_err(dw2, wr.grad) < 2e-3
     dx2 = ops.dwconv_fwd_cm(dys, w, flip=True, addend=add_arg)
     assert torch.equal(dx2, dx)
+
+
+@pytest.mark.parametrize("N,T,C,cm", [(4, 157, 256, True), (4, 157, 256, False), (32, 801, 512, True), (3, 40, 64, False),
+                                      (2, 808, 1024, False)])
+def test_relu_bits_replace_the_output_tensor_in_the_backward_passes(ops, N, T, C, cm):
+    """forward passes write one byte per (frame, 8 channels); the backward passes driven by the bits must produce the
+    same totals / gradients, bit for bit, as when they read the output tensor"""
+    torch.manual_seed(C + T)
+    dev = "cuda"
+    y = torch.randn(N, T, C, device=dev).bfloat16()
+    r = torch.randn(N, T, C, device=dev).bfloat16()
+
+    def bn(src):
+        sums = torch.stack((src.double().sum((0, 1)), (src.double() ** 2).sum((0, 1)))).contiguous()
+        return ops.BNForward(torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev), torch.zeros(C, device=dev),
+                             torch.ones(C, device=dev), torch.zeros((), device=dev, dtype=torch.int64), sums)
+
+    torch.manual_seed(2)
+    b1, b2 = bn(y), bn(r)
+    bits = ops.relu_bits_alloc(N, T, C, dev)
+    bits.fill_(0xAA)
+    if cm:
+        out, _ = ops.bn_apply_act(y, b1, r, b2, cm_k=33, relu_bits=bits)
+    else:
+        out = ops.bn_apply_act(y, b1, r, b2, relu_bits=bits)
+    # the bits are the sign of the stored output
+    Tb = (T + 7) // 8
+    ref = torch.zeros(N, Tb * 8, C // 8, device=dev, dtype=torch.int32)
+    pos = (out.float() > 0).view(N, T, C // 8, 8).int()
+    ref[:, :T] = (pos << torch.arange(8, device=dev, dtype=torch.int32)).sum(-1)
+    got = bits.view(N, Tb, C // 8, 8).permute(0, 1, 3, 2).reshape(N, Tb * 8, C // 8).int()
+    assert torch.equal(got[:, :T], ref[:, :T])
+    dout = torch.randn(N, T, C, device=dev).bfloat16()
+    lengths = torch.randint(T // 2, T + 1, (N,), device=dev, dtype=torch.int32)
+    res = []
+    for use_bits in (False, True):
+        totals = torch.zeros(3, C, device=dev, dtype=torch.float64)
+        ops.bn_act_bwd_reduce(dout, out, y, r, ops.ACT_RELU, totals, relu_bits=bits if use_bits else None)
+        dg = torch.zeros(4, C, device=dev)
+        dy, dr = ops.bn_act_bwd_apply(dout, out, y, r, None, None, totals, None, (b1.gamma, b1.save, dg[0], dg[1]),
+                                      (b2.gamma, b2.save, dg[2], dg[3]), lengths, ops.ACT_RELU,
+                                      relu_bits=bits if use_bits else None)
+        res.append((totals, dy, dr, dg))
+    assert rel_err(res[1][0], res[0][0]) < 1e-6  # fp32 partial sums, different CTA order
+    assert rel_err(res[1][1], res[0][1]) < 1e-2 and rel_err(res[1][2], res[0][2]) < 1e-2
+    assert rel_err(res[1][3], res[0][3]) < 1e-5

@@ -144,11 +144,17 @@ def bench_bn():
         dout = torch.randn(N, T, c, device=dev).bfloat16()
         totals = torch.zeros(3, c, device=dev, dtype=torch.float64)
         report(f"bn_act_bwd_reduce (res) C={c}", timeit(lambda: ops.bn_act_bwd_reduce(dout, out, y, r, ops.ACT_RELU, totals)), 2 * M * c * 4, 0)
+        bits = ops.relu_bits_alloc(N, T, c, dev)
+        ops.bn_apply_act(y, bn1, r, bn2, relu_bits=bits)
+        report(f"bn_act_bwd_reduce (res, relu bits) C={c}", timeit(lambda: ops.bn_act_bwd_reduce(dout, None, y, r, ops.ACT_RELU, totals, relu_bits=bits)), 2 * M * c * 3, 0)
         lengths = torch.full((N,), T, device=dev, dtype=torch.int32)
         dg = torch.zeros(4, c, device=dev)
         report(f"bn_act_bwd_apply (res) C={c}",
                timeit(lambda: ops.bn_act_bwd_apply(dout, out, y, r, None, None, totals, None, (g, bn1.save, dg[0], dg[1]),
                                                    (g, bn2.save, dg[2], dg[3]), lengths, ops.ACT_RELU)), 2 * M * c * 6, 0)
+        report(f"bn_act_bwd_apply (res, relu bits) C={c}",
+               timeit(lambda: ops.bn_act_bwd_apply(dout, None, y, r, None, None, totals, None, (g, bn1.save, dg[0], dg[1]),
+                                                   (g, bn2.save, dg[2], dg[3]), lengths, ops.ACT_RELU, relu_bits=bits)), 2 * M * c * 5, 0)
 
 
 def bench_ctc():
