@@ -347,16 +347,26 @@ int lasr_log_softmax_bwd(const float* dlp, const float* lp, void* dlogits, int M
  *   beta     same shape, nullable: when given, the beta lattice is computed CONCURRENTLY with alpha
  *            (separate CTAs) so the backward is just the parallel combine pass
  *   nll      [N] fp32 out: -log p(target | x); +inf when no alignment exists
+ *   scales / emis  workspaces of lasr_ctc_scales_bytes / lasr_ctc_emis_bytes bytes, nullable TOGETHER:
+ *            given     -> scaled lattices: 8 warps per (utterance, direction), probabilities kept linear with an exact
+ *                         power-of-two rescaling every 4th frame; alpha[n,t,s] = the stored value * 2^scales[0][n][t],
+ *                         `beta` holds beta WITHOUT the frame's emission * 2^scales[1][n][t]; scales[2*N*T + 2n, +1] =
+ *                         (float bits of P's mantissa part, its exponent).  emis [N, T, pad4(S_max+2)] fp32 receives
+ *                         the emission probabilities the lattice reads (labels 0..S_n-1, blank at S_max).
+ *            NULL      -> log-space lattices (round-1 kernels: one state per thread), alpha / beta are logarithms.
+ *            The same `scales` (or NULL) must be passed to lasr_ctc_bwd.
  * bwd: grad [N, T, ldg] grad_dtype = (softmax - occupancy) * grad_out[n] for t < input_lengths[n], 0 after
  *      (this is also torch's "gradient w.r.t. log-probs").
  * ---------------------------------------------------------------------------------------------- */
+size_t lasr_ctc_scales_bytes(int N, int T);
+size_t lasr_ctc_emis_bytes(int N, int T, int S_max);
 int lasr_ctc_fwd(const void* x, const float* lse, const int64_t* targets, const int32_t* input_lengths,
-                 const int32_t* target_lengths, float* alpha, float* beta, float* nll, int N, int T, int V, int ldx,
-                 int S_max, int blank, int dtype, lasr_stream_t stream);
+                 const int32_t* target_lengths, float* alpha, float* beta, float* nll, int32_t* scales, float* emis,
+                 int N, int T, int V, int ldx, int S_max, int blank, int dtype, lasr_stream_t stream);
 int lasr_ctc_bwd(const void* x, const float* lse, const int64_t* targets, const int32_t* input_lengths,
                  const int32_t* target_lengths, const float* alpha, const float* beta, const float* nll,
-                 const float* grad_out, void* grad, int N, int T, int V, int ldx, int ldg, int S_max, int blank,
-                 int dtype, int grad_dtype, lasr_stream_t stream);
+                 const int32_t* scales, const float* grad_out, void* grad, int N, int T, int V, int ldx, int ldg,
+                 int S_max, int blank, int dtype, int grad_dtype, lasr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Greedy CTC decode (replaces out.argmax(-1) train.py:80 + the collapse loop utils/asr_metrics.py:153-171).

@@ -308,8 +308,8 @@ __global__ void __launch_bounds__(256)
 ctc_grad_kernel(const T* __restrict__ x, const float* __restrict__ lse, const int64_t* __restrict__ targets,
                 const int32_t* __restrict__ in_len, const int32_t* __restrict__ tgt_len,
                 const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ nll,
-                const float* __restrict__ grad_out, GT* __restrict__ grad, int N, int T_len, int V, int ldx, int ldg,
-                int S_max, int blank, int warps) {
+                const int32_t* __restrict__ scales, const float* __restrict__ grad_out, GT* __restrict__ grad, int N,
+                int T_len, int V, int ldx, int ldg, int S_max, int blank, int warps) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float occ_all[];  // [warps][V]
@@ -339,10 +339,25 @@ ctc_grad_kernel(const T* __restrict__ x, const float* __restrict__ lse, const in
   const float* ar = alpha + static_cast<size_t>(row) * Lp_max;
   const float* br = beta + static_cast<size_t>(row) * Lp_max;
   const int64_t* tg = targets + static_cast<size_t>(n) * S_max;
-  for (int s = lane; s < Lp; s += 32) {
-    const int label = (s & 1) ? static_cast<int>(tg[s >> 1]) : blank;
-    const float lpv = to_f32<T>(xr[label]) - l;
-    atomicAdd(&occ[label], expf(ar[s] + br[s] + nl - lpv));
+  if (scales != nullptr) {
+    // scaled lattices (ctc_lattice2_kernel): alpha = a * 2^EA, beta~ = b * 2^EB, P = Pm * 2^EP -> occupancy without any
+    // logarithm, exponential or division per state
+    const size_t NT = static_cast<size_t>(N) * T_len;
+    const int ea = scales[static_cast<size_t>(n) * T_len + t];
+    const int eb = scales[NT + static_cast<size_t>(n) * T_len + t];
+    const float Pm = __uint_as_float(static_cast<uint32_t>(scales[2 * NT + 2 * n]));
+    const int ep = scales[2 * NT + 2 * n + 1];
+    const float w = scalbnf(1.0f / Pm, ea + eb - ep);
+    for (int s = lane; s < Lp; s += 32) {
+      const int label = (s & 1) ? static_cast<int>(tg[s >> 1]) : blank;
+      atomicAdd(&occ[label], ar[s] * br[s] * w);
+    }
+  } else {
+    for (int s = lane; s < Lp; s += 32) {
+      const int label = (s & 1) ? static_cast<int>(tg[s >> 1]) : blank;
+      const float lpv = to_f32<T>(xr[label]) - l;
+      atomicAdd(&occ[label], expf(ar[s] + br[s] + nl - lpv));
+    }
   }
   __syncwarp();
   for (int c = lane; c < ldg; c += 32) {
@@ -350,6 +365,253 @@ ctc_grad_kernel(const T* __restrict__ x, const float* __restrict__ lse, const in
     if (c < V) g = (expf(to_f32<T>(xr[c]) - l) - occ[c]) * go;
     gr[c] = from_f32<GT>(g);
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// CTC lattices, second generation: ONE WARP per (utterance, direction), no block barrier in the recursion.
+//
+// The recursion is a chain of T' dependent steps; with one state per thread (ctc_lattice_kernel) every step pays a
+// block barrier over 13-19 warps plus a shared-memory round trip and a 3-way log-sum-exp (two ex2 + one lg2 on the MUFU
+// pipe): ~630 cycles per frame, 266 us for T' = 801 however few states there are.  Here a lane owns K CONSECUTIVE
+// states in registers, the two neighbours it needs from the previous lane come by warp shuffle, and the arithmetic is
+// the classic SCALED forward-backward instead of per-state logarithms: probabilities stay linear and every 4th frame the
+// whole column is multiplied by an exact power of two (so the scaling itself adds no rounding); the running exponent is
+// an INTEGER per frame.  Log space is kept where it matters -- alpha_t[s] = a[t][s] * 2^E[t] with E the shared exponent --
+// and a step is two adds and one multiply per state: ~150 issue cycles per frame for the whole lattice.
+//   stage 1  ctc_emit_kernel      e[n, t, j] = exp(x[n, t, label_j] - lse[n, t]), j < S_n; e[n, t, S_max] = blank
+//                                 (one pass over the score matrix, any vocabulary size; the lattice reads rows of it)
+//   stage 2  ctc_lattice2_kernel  alpha (with the frame's emission) and beta~ (WITHOUT it: what the gradient needs, so
+//                                 nothing is divided by an emission later), int32 exponents per frame, P = sum of the
+//                                 two final states as (mantissa, exponent), nll = -ln P
+//   stage 3  ctc_grad_kernel      occupancy[c] += alpha * beta~ * 2^(EA + EB - EP) / P_mantissa, fused softmax gradient
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+ctc_emit_kernel(const T* __restrict__ x, const float* __restrict__ lse, const int64_t* __restrict__ targets,
+                const int32_t* __restrict__ in_len, const int32_t* __restrict__ tgt_len, float* __restrict__ emis, int N,
+                int T_len, int ldx, int S_max, int E_pad, int blank) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= static_cast<long long>(N) * T_len) return;
+  const int n = static_cast<int>(row / T_len);
+  const int t = static_cast<int>(row - static_cast<long long>(n) * T_len);
+  const int Sn = tgt_len[n];
+  if (t >= in_len[n] || Sn < 0 || Sn > S_max) return;
+  const T* xr = x + static_cast<size_t>(row) * ldx;
+  const float l = lse != nullptr ? lse[row] : 0.f;
+  const int64_t* tg = targets + static_cast<size_t>(n) * S_max;
+  float* er = emis + static_cast<size_t>(row) * E_pad;
+  for (int j = lane; j < E_pad; j += 32) {
+    float v = 0.f;
+    if (j < Sn)
+      v = __expf(to_f32<T>(xr[static_cast<int>(tg[j])]) - l);
+    else if (j == S_max)
+      v = __expf(to_f32<T>(xr[blank]) - l);
+    er[j] = v;
+  }
+}
+
+constexpr int CTC2_DEPTH = 8;  // emission rows in flight (cp.async ring)
+
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+
+constexpr int CTC2_WARPS = 8;
+constexpr int CTC2_THREADS = 32 * CTC2_WARPS;
+
+// One CTA of 8 warps per (utterance, direction); thread tid owns the K consecutive states q = tid * K + j in registers
+// (alpha: s = q; beta: s = Lp - 1 - q, so that both directions read predecessors q - 1 and q - 2).  Per frame:
+// neighbours by warp shuffle (the first lane(s) of a warp read the previous warp's last two states from a double-buffered
+// shared slot), K x (2 adds, 1 multiply), the column staged in shared memory in global state order, ONE block barrier,
+// then coalesced global stores that overlap the next frame.
+template <int K, int DIR>
+__device__ __forceinline__ void ctc_lattice2_body(const float* __restrict__ emis, const int64_t* __restrict__ targets,
+                                                  const int32_t* __restrict__ in_len,
+                                                  const int32_t* __restrict__ tgt_len, float* __restrict__ lat_out,
+                                                  float* __restrict__ nll, int32_t* __restrict__ scales, int N, int T_len,
+                                                  int S_max, int E_pad) {
+  extern __shared__ __align__(16) float sm2[];
+  // sm2: ring [CTC2_DEPTH][E_pad], rowbuf [2][CTC2_THREADS * K], bslot [2][CTC2_WARPS][2], mslot [CTC2_WARPS]
+  const int n = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int Tn = in_len[n];
+  const int Sn = tgt_len[n];
+  const int Lp = 2 * Sn + 1;
+  const int Lp_max = 2 * S_max + 1;
+  const size_t NT = static_cast<size_t>(N) * T_len;
+  int32_t* exps = scales + (static_cast<size_t>(DIR) * N + n) * T_len;  // exponent of the stored column of every frame
+  if (Tn <= 0 || Sn < 0 || Sn > S_max || Tn > T_len) {
+    if (DIR == 0 && tid == 0) {
+      nll[n] = (Tn == 0 && Sn == 0) ? 0.f : CUDART_INF_F;
+      scales[2 * NT + 2 * n] = 0;
+      scales[2 * NT + 2 * n + 1] = 0;
+    }
+    return;
+  }
+  const int64_t* tg = targets + static_cast<size_t>(n) * S_max;
+  constexpr int ROWF = CTC2_THREADS * K;
+  const uint32_t ring_s = smem_u32(sm2);
+  const uint32_t row_s = ring_s + 4u * CTC2_DEPTH * E_pad;
+  const uint32_t bsl_s = row_s + 4u * 2 * ROWF;
+  const uint32_t msl_s = bsl_s + 4u * 2 * CTC2_WARPS * 2;
+  // per-state constants; invalid states (q >= Lp) read the always-zero emission cell and write a slot nobody reads
+  uint32_t eoff[K], soff[K];
+  uint32_t skip = 0u;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const int q = tid * K + j;
+    eoff[j] = 4u * (S_max + 1);
+    soff[j] = 4u * q;
+    if (q < Lp) {
+      const int s = DIR ? Lp - 1 - q : q;
+      eoff[j] = 4u * ((s & 1) ? (s >> 1) : S_max);
+      soff[j] = 4u * s;
+      if ((s & 1) && q >= 2) {
+        const int s2 = DIR ? s + 2 : s - 2;
+        if (tg[s >> 1] != tg[s2 >> 1]) skip |= 1u << j;
+      }
+    }
+  }
+  const int chunks = E_pad / 4;  // 16-byte pieces of an emission row (<= CTC2_THREADS, checked by the host)
+  const long long estep = DIR ? -static_cast<long long>(E_pad) : static_cast<long long>(E_pad);
+  const float* esrc = emis + (static_cast<size_t>(n) * T_len + (DIR ? Tn - 1 : 0)) * E_pad + 4 * tid;
+  int pf = 0;  // local index of the next frame to prefetch
+  auto prefetch = [&]() {
+    if (pf < Tn && tid < chunks)
+      cp_async_16(ring_s + 4u * static_cast<uint32_t>((pf & (CTC2_DEPTH - 1)) * E_pad) + 16u * tid, esrc);
+    cp_async_commit();
+    esrc += estep;
+    ++pf;
+  };
+#pragma unroll 1
+  for (int i = 0; i < CTC2_DEPTH - 1; ++i) prefetch();
+  cp_async_wait<CTC2_DEPTH - 2>();  // frame 0 has landed
+  __syncthreads();
+  float a[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) a[j] = 0.f;
+  int E = 0;
+  const long long ostep = DIR ? -static_cast<long long>(Lp_max) : static_cast<long long>(Lp_max);
+  float* orow = lat_out + (static_cast<size_t>(n) * T_len + (DIR ? Tn - 1 : 0)) * Lp_max + tid;
+  int32_t* ep = exps + (DIR ? Tn - 1 : 0);
+#pragma unroll 1
+  for (int i = 0; i < Tn; ++i) {
+    const uint32_t par = static_cast<uint32_t>(i & 1);
+    const uint32_t er = ring_s + 4u * static_cast<uint32_t>((i & (CTC2_DEPTH - 1)) * E_pad);
+    float e[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) e[j] = lds_f32(er + eoff[j]);
+    // pending rescale (the warps' maxima of frame i - 1): an exact power of two, identical in every thread
+    float sc = 1.f;
+    if ((i & 3) == 0 && i > 0) {
+      float m = lds_f32(msl_s);
+#pragma unroll
+      for (int w = 1; w < CTC2_WARPS; ++w) m = fmaxf(m, lds_f32(msl_s + 4u * w));
+      if (m > 0.f) {
+        int k = static_cast<int>((__float_as_uint(m) >> 23) & 0xffu) - 127;
+        k = max(-100, min(100, k));
+        sc = __uint_as_float(static_cast<uint32_t>(127 - k) << 23);
+#pragma unroll
+        for (int j = 0; j < K; ++j) a[j] *= sc;
+        E += k;
+      }
+    }
+    float st[K];  // what is stored for this frame: alpha (with the emission) / beta~ (without)
+    if (i == 0) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const int q = tid * K + j;
+        const float one = (q < 2 && q < Lp) ? 1.f : 0.f;
+        st[j] = one;
+        a[j] = one * e[j];
+      }
+    } else {
+      // predecessors of this thread's first state: q - 1 and q - 2 live in the previous thread(s)
+      float in1 = __shfl_up_sync(0xffffffffu, a[K - 1], 1);
+      float in2 = K >= 2 ? __shfl_up_sync(0xffffffffu, a[K >= 2 ? K - 2 : 0], 1) : __shfl_up_sync(0xffffffffu, a[0], 2);
+      if (lane == 0 || (K == 1 && lane == 1)) {
+        float b1 = 0.f, b2 = 0.f;
+        if (warp > 0) {
+          const uint32_t bs = bsl_s + 4u * (((par ^ 1u) * CTC2_WARPS + (warp - 1)) * 2);
+          b1 = lds_f32(bs) * sc;       // the previous warp's last state, stored before this frame's rescale
+          b2 = lds_f32(bs + 4u) * sc;  // and its second to last
+        }
+        if (lane == 0) {
+          in1 = b1;
+          in2 = b2;
+        } else {
+          in2 = b1;  // K == 1, lane 1: q - 2 is the previous warp's last state
+        }
+      }
+#pragma unroll
+      for (int j = K - 1; j >= 0; --j) {
+        const float p1 = j >= 1 ? a[j - 1] : in1;
+        const float p2 = j >= 2 ? a[j - 2] : (j == 1 ? in1 : in2);
+        const float sum = a[j] + p1 + (((skip >> j) & 1u) ? p2 : 0.f);
+        st[j] = sum;
+        a[j] = sum * e[j];
+      }
+    }
+    // the last two states of the warp, for the next warp's first lane(s) at the next frame
+    if (K >= 2) {
+      if (lane == 31) {
+        const uint32_t bs = bsl_s + 4u * ((par * CTC2_WARPS + warp) * 2);
+        sts_f32(bs, a[K - 1]);
+        sts_f32(bs + 4u, a[K >= 2 ? K - 2 : 0]);
+      }
+    } else {
+      if (lane >= 30) sts_f32(bsl_s + 4u * ((par * CTC2_WARPS + warp) * 2 + (31 - lane)), a[0]);
+    }
+    if ((i & 3) == 3) {
+      float m = a[0];
+#pragma unroll
+      for (int j = 1; j < K; ++j) m = fmaxf(m, a[j]);
+      m = warp_max(m);
+      if (lane == 0) sts_f32(msl_s + 4u * warp, m);
+    }
+    const uint32_t rb = row_s + 4u * par * ROWF;
+#pragma unroll
+    for (int j = 0; j < K; ++j) sts_f32(rb + soff[j], DIR ? st[j] : a[j]);
+    prefetch();
+    cp_async_wait<CTC2_DEPTH - 2>();  // the emissions of frame i + 1 have landed (this thread's share)
+    __syncthreads();
+    float v[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) v[j] = lds_f32(rb + 4u * (tid + CTC2_THREADS * j));
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+      if (tid + CTC2_THREADS * j < Lp) orow[CTC2_THREADS * j] = v[j];
+    if (tid == 0) *ep = E;
+    orow += ostep;
+    ep += DIR ? -1 : 1;
+  }
+  if (DIR == 0 && tid == 0) {
+    const uint32_t rb = row_s + 4u * static_cast<uint32_t>((Tn - 1) & 1) * ROWF;
+    const float P = lds_f32(rb + 4u * (Lp - 1)) + (Lp >= 2 ? lds_f32(rb + 4u * (Lp - 2)) : 0.f);
+    scales[2 * NT + 2 * n] = static_cast<int32_t>(__float_as_uint(P));
+    scales[2 * NT + 2 * n + 1] = E;
+    nll[n] = P > 0.f ? static_cast<float>(-(log(static_cast<double>(P)) + static_cast<double>(E) * 0.6931471805599453))
+                     : CUDART_INF_F;
+  }
+}
+
+// grid (N, 2): blockIdx.y = 0 the alpha lattice, 1 the beta~ lattice (beta == NULL: grid (N, 1)); they run concurrently
+template <int K>
+__global__ void __launch_bounds__(CTC2_THREADS)
+ctc_lattice2_kernel(const float* __restrict__ emis, const int64_t* __restrict__ targets, const int32_t* __restrict__ in_len,
+                    const int32_t* __restrict__ tgt_len, float* __restrict__ alpha, float* __restrict__ beta,
+                    float* __restrict__ nll, int32_t* __restrict__ scales, int N, int T_len, int S_max, int E_pad) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (blockIdx.y == 0)
+    ctc_lattice2_body<K, 0>(emis, targets, in_len, tgt_len, alpha, nll, scales, N, T_len, S_max, E_pad);
+  else
+    ctc_lattice2_body<K, 1>(emis, targets, in_len, tgt_len, beta, nll, scales, N, T_len, S_max, E_pad);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -436,8 +698,8 @@ colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long M, int
 template <typename T, typename GT>
 static int ctc_grad_launch(const void* x, const float* lse, const int64_t* targets, const int32_t* il,
                            const int32_t* tl, const float* alpha, const float* beta, const float* nll,
-                           const float* grad_out, void* grad, int N, int Tn, int V, int ldx, int ldg, int S_max,
-                           int blank, cudaStream_t stream) {
+                           const int32_t* scales, const float* grad_out, void* grad, int N, int Tn, int V, int ldx,
+                           int ldg, int S_max, int blank, cudaStream_t stream) {
   int warps = (96 * 1024) / (V * 4);
   if (warps > 8) warps = 8;
   if (warps < 1) warps = 1;
@@ -456,9 +718,45 @@ static int ctc_grad_launch(const void* x, const float* lse, const int64_t* targe
   const long long rows = static_cast<long long>(N) * Tn;
   const int grid = static_cast<int>((rows + warps - 1) / warps);
   LASR_CHECK_PDL(launch_pdl(8, ctc_grad_kernel<T, GT>, dim3(grid), dim3(256), smem, stream, static_cast<const T*>(x), lse,
-                            targets, il, tl, alpha, beta, nll, grad_out, static_cast<GT*>(grad), N, Tn, V, ldx, ldg,
-                            S_max, blank, warps));
+                            targets, il, tl, alpha, beta, nll, scales, grad_out, static_cast<GT*>(grad), N, Tn, V, ldx,
+                            ldg, S_max, blank, warps));
   return LASR_OK;
+}
+
+// second-generation lattices: emission gather + one 8-warp CTA per (utterance, direction)
+template <int K>
+static int ctc_lattice2_launch(const float* emis, const int64_t* targets, const int32_t* il, const int32_t* tl,
+                               float* alpha, float* beta, float* nll, int32_t* scales, int N, int T_len, int S_max,
+                               int E_pad, cudaStream_t stream) {
+  const int smem = (CTC2_DEPTH * E_pad + 2 * CTC2_THREADS * K + 2 * CTC2_WARPS * 2 + CTC2_WARPS) *
+                   static_cast<int>(sizeof(float));
+  if (smem > 48 * 1024) return LASR_ERR_UNSUPPORTED;
+  LASR_CHECK_PDL(launch_pdl(8, ctc_lattice2_kernel<K>, dim3(N, beta != nullptr ? 2 : 1), dim3(CTC2_THREADS), smem, stream,
+                            emis, targets, il, tl, alpha, beta, nll, scales, N, T_len, S_max, E_pad));
+  return LASR_OK;
+}
+
+template <typename T>
+static int ctc_fwd2(const void* x, const float* lse, const int64_t* targets, const int32_t* il, const int32_t* tl,
+                    float* alpha, float* beta, float* nll, int32_t* scales, float* emis, int N, int T_len, int ldx,
+                    int S_max, int blank, cudaStream_t stream) {
+  const int E_pad = (S_max + 2 + 3) / 4 * 4;  // labels, blank at S_max, an always-zero cell at S_max + 1
+  if (E_pad / 4 > CTC2_THREADS) return LASR_ERR_UNSUPPORTED;
+  const long long rows = static_cast<long long>(N) * T_len;
+  LASR_CHECK_PDL(launch_pdl(8, ctc_emit_kernel<T>, dim3(static_cast<unsigned>((rows + 7) / 8)), dim3(256), 0, stream,
+                            static_cast<const T*>(x), lse, targets, il, tl, emis, N, T_len, ldx, S_max, E_pad, blank));
+  const int Lp_max = 2 * S_max + 1;
+  const int k = (Lp_max + CTC2_THREADS - 1) / CTC2_THREADS;
+#define LASR_CTC2(KK) \
+  return ctc_lattice2_launch<KK>(emis, targets, il, tl, alpha, beta, nll, scales, N, T_len, S_max, E_pad, stream)
+  if (k <= 1) LASR_CTC2(1);
+  if (k <= 2) LASR_CTC2(2);
+  if (k <= 3) LASR_CTC2(3);
+  if (k <= 4) LASR_CTC2(4);
+  if (k <= 6) LASR_CTC2(6);
+  if (k <= 8) LASR_CTC2(8);
+#undef LASR_CTC2
+  return LASR_ERR_UNSUPPORTED;
 }
 
 template <typename T, int SPT, int CTC_THREADS>
@@ -538,11 +836,29 @@ int lasr_log_softmax_bwd(const float* dlp, const float* lp, void* dlogits, int M
   return LASR_OK;
 }
 
+size_t lasr_ctc_scales_bytes(int N, int T) {
+  return (2 * static_cast<size_t>(N) * T + 2 * static_cast<size_t>(N)) * sizeof(int32_t);
+}
+size_t lasr_ctc_emis_bytes(int N, int T, int S_max) {
+  return static_cast<size_t>(N) * T * ((S_max + 2 + 3) / 4 * 4) * sizeof(float);
+}
+
 int lasr_ctc_fwd(const void* x, const float* lse, const int64_t* targets, const int32_t* input_lengths,
-                 const int32_t* target_lengths, float* alpha, float* beta, float* nll, int N, int T, int V, int ldx,
-                 int S_max, int blank, int dtype, lasr_stream_t stream) {
+                 const int32_t* target_lengths, float* alpha, float* beta, float* nll, int32_t* scales, float* emis,
+                 int N, int T, int V, int ldx, int S_max, int blank, int dtype, lasr_stream_t stream) {
   if (N <= 0 || T <= 0 || V <= 0 || ldx < V || S_max < 0 || blank < 0 || blank >= V) return LASR_ERR_BAD_SHAPE;
   if ((reinterpret_cast<uintptr_t>(x) & 3) != 0) return LASR_ERR_ALIGNMENT;
+  if ((scales != nullptr) != (emis != nullptr)) return LASR_ERR_BAD_SHAPE;
+  if (scales != nullptr && 2 * S_max + 1 <= 32 * 33) {
+    if (dtype == LASR_F32)
+      return ctc_fwd2<float>(x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, scales, emis, N, T, ldx,
+                             S_max, blank, stream);
+    if (dtype == LASR_BF16)
+      return ctc_fwd2<__nv_bfloat16>(x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, scales, emis, N,
+                                     T, ldx, S_max, blank, stream);
+    return LASR_ERR_BAD_DTYPE;
+  }
+  if (scales != nullptr) return LASR_ERR_UNSUPPORTED;
   if (dtype == LASR_F32)
     return ctc_lattice_dispatch<float>(x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, N, T, ldx,
                                        S_max, blank, stream);
@@ -556,12 +872,13 @@ int lasr_ctc_fwd(const void* x, const float* lse, const int64_t* targets, const 
 
 int lasr_ctc_bwd(const void* x, const float* lse, const int64_t* targets, const int32_t* input_lengths,
                  const int32_t* target_lengths, const float* alpha, const float* beta, const float* nll,
-                 const float* grad_out, void* grad, int N, int T, int V, int ldx, int ldg, int S_max, int blank,
-                 int dtype, int grad_dtype, lasr_stream_t stream) {
+                 const int32_t* scales, const float* grad_out, void* grad, int N, int T, int V, int ldx, int ldg,
+                 int S_max, int blank, int dtype, int grad_dtype, lasr_stream_t stream) {
   if (N <= 0 || T <= 0 || V <= 0 || ldx < V || ldg < V || S_max < 0) return LASR_ERR_BAD_SHAPE;
   if (alpha == nullptr || beta == nullptr) return LASR_ERR_BAD_SHAPE;
-#define LASR_CTC_ARGS \
-  x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, grad_out, grad, N, T, V, ldx, ldg, S_max, blank, stream
+#define LASR_CTC_ARGS                                                                                                \
+  x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, scales, grad_out, grad, N, T, V, ldx, ldg, S_max, \
+      blank, stream
   if (dtype == LASR_F32 && grad_dtype == LASR_F32) return ctc_grad_launch<float, float>(LASR_CTC_ARGS);
   if (dtype == LASR_BF16 && grad_dtype == LASR_BF16)
     return ctc_grad_launch<__nv_bfloat16, __nv_bfloat16>(LASR_CTC_ARGS);

@@ -347,8 +347,9 @@ class CTCLossFn(torch.autograd.Function):
             x = x.float()
         V = x.shape[-1]
         need_grad = log_probs.requires_grad
-        nll, alpha, beta = ops.ctc_fwd(x, None, targets, input_lengths, target_lengths, V, blank, want_beta=need_grad)
-        ctx.save_for_backward(x, targets, input_lengths, target_lengths, alpha, beta, nll)
+        nll, alpha, beta, scales = ops.ctc_fwd(x, None, targets, input_lengths, target_lengths, V, blank,
+                                               want_beta=need_grad)
+        ctx.save_for_backward(x, targets, input_lengths, target_lengths, alpha, beta, nll, scales)
         ctx.blank = blank
         ctx.in_dtype = log_probs.dtype
         ctx.zero_infinity = zero_infinity
@@ -356,10 +357,10 @@ class CTCLossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gout):
-        x, targets, il, tl, alpha, beta, nll = ctx.saved_tensors
+        x, targets, il, tl, alpha, beta, nll, scales = ctx.saved_tensors
         V = x.shape[-1]
         grad = ops.ctc_bwd(x, None, targets, il, tl, alpha, beta, nll, gout.contiguous().float(), V, ctx.blank, V,
-                           torch.float32)
+                           torch.float32, scales=scales)
         if ctx.zero_infinity:
             # torch.nn.CTCLoss(zero_infinity=True) zeroes the gradient of infeasible utterances (their lattice terms
             # are inf / NaN); the reference's own setting is zero_infinity=False (train.py:196)
@@ -376,19 +377,20 @@ class FusedDecoderCTCFn(torch.autograd.Function):
         V = w.shape[0]
         logits, w_s = _decoder_logits(x, w, b)
         lse, _ = ops.log_softmax_fwd(logits, V, want_lp=False)
-        nll, alpha, beta = ops.ctc_fwd(logits, lse, targets, input_lengths, target_lengths, V, blank, want_beta=True)
-        ctx.save_for_backward(x, logits, lse, targets, input_lengths, target_lengths, alpha, beta, nll, w_s, w, b)
+        nll, alpha, beta, scales = ops.ctc_fwd(logits, lse, targets, input_lengths, target_lengths, V, blank,
+                                               want_beta=True)
+        ctx.save_for_backward(x, logits, lse, targets, input_lengths, target_lengths, alpha, beta, nll, w_s, w, b, scales)
         ctx.blank = blank
         ctx.mark_non_differentiable(logits)
         return nll, logits
 
     @staticmethod
     def backward(ctx, gout, _glogits):
-        x, logits, lse, targets, il, tl, alpha, beta, nll, w_s, w, b = ctx.saved_tensors
+        x, logits, lse, targets, il, tl, alpha, beta, nll, w_s, w, b, scales = ctx.saved_tensors
         V = w.shape[0]
         ld = logits.shape[-1]
         dlogits = ops.ctc_bwd(logits, lse, targets, il, tl, alpha, beta, nll, gout.contiguous().float(), V, ctx.blank,
-                              ld, x.dtype)
+                              ld, x.dtype, scales=scales)
         dx, d_w, d_b = _decoder_backward(x, w, b, w_s, dlogits, ctx.needs_input_grad[0])
         return dx, d_w, d_b, None, None, None, None
 

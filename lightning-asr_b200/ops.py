@@ -6,6 +6,7 @@ eager / CPU fallback: inputs must be CUDA tensors and the shared library must be
 Activations are channels-last: [N, T, C] contiguous (C fastest).
 """
 import ctypes
+import os
 
 import torch
 
@@ -502,25 +503,36 @@ def log_softmax_bwd(dlp, lp, ld, dtype):
     return dlogits
 
 
+CTC_SCALED = os.environ.get("LASR_CTC_SCALED", "1") != "0"  # 0: the round-1 log-space lattice kernels (A/B switch)
+
+
 def ctc_fwd(x, lse, targets, input_lengths, target_lengths, V, blank, want_beta):
-    """x [N, T, ld] log-probs (lse None) or logits (+lse [N,T]).  -> nll [N], alpha, beta|None."""
+    """x [N, T, ld] log-probs (lse None) or logits (+lse [N,T]).  -> nll [N], alpha, beta|None, scales|None.
+    scales (int32 workspace) is not None when the scaled single-warp lattices ran (include/lasr.h): pass it on to
+    ctc_bwd together with alpha / beta."""
     N, T, ld = x.shape
     S_max = max(int(targets.shape[1]), 1) if targets.dim() == 2 else 1
     Lp = 2 * S_max + 1
     alpha = torch.empty((N, T, Lp), device=x.device, dtype=torch.float32)
     beta = torch.empty((N, T, Lp), device=x.device, dtype=torch.float32) if want_beta else None
     nll = torch.empty((N,), device=x.device, dtype=torch.float32)
-    call("lasr_ctc_fwd", x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, N, T, V, ld, S_max, blank,
-         dtype_code(x.dtype))
-    return nll, alpha, beta
+    scales = emis = None
+    if CTC_SCALED and Lp <= 32 * 33:
+        lib = _lib.load()
+        scales = torch.empty((lib.lasr_ctc_scales_bytes(N, T) // 4,), device=x.device, dtype=torch.int32)
+        emis = torch.empty((lib.lasr_ctc_emis_bytes(N, T, S_max) // 4,), device=x.device, dtype=torch.float32)
+    call("lasr_ctc_fwd", x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, scales, emis, N, T, V, ld,
+         S_max, blank, dtype_code(x.dtype))
+    return nll, alpha, beta, scales
 
 
-def ctc_bwd(x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, grad_out, V, blank, ldg, grad_dtype):
+def ctc_bwd(x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, grad_out, V, blank, ldg, grad_dtype,
+            scales=None):
     N, T, ld = x.shape
     S_max = max(int(targets.shape[1]), 1)
     grad = torch.empty((N, T, ldg), device=x.device, dtype=grad_dtype)
-    call("lasr_ctc_bwd", x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, grad_out, grad, N, T, V, ld,
-         ldg, S_max, blank, dtype_code(x.dtype), dtype_code(grad_dtype))
+    call("lasr_ctc_bwd", x, lse, targets, input_lengths, target_lengths, alpha, beta, nll, scales, grad_out, grad, N, T, V,
+         ld, ldg, S_max, blank, dtype_code(x.dtype), dtype_code(grad_dtype))
     return grad
 
 

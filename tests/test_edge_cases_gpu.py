@@ -30,11 +30,11 @@ def test_ctc_empty_targets_and_single_frame(ops):
     nll_ref = F.ctc_loss(lp_ref.transpose(0, 1), targets, in_len.long(), tgt_len.long(), blank=V - 1, reduction="none")
     nll_ref.sum().backward()
     lse, _ = ops.log_softmax_fwd(logits, V, want_lp=False)
-    nll, alpha, beta = ops.ctc_fwd(logits, lse, targets, in_len, tgt_len, V, V - 1, want_beta=True)
+    nll, alpha, beta, scales = ops.ctc_fwd(logits, lse, targets, in_len, tgt_len, V, V - 1, want_beta=True)
     assert rel_err(nll, nll_ref) < 1e-5
     assert rel_err(nll[0], -lp_ref[0, :, V - 1].sum()) < 1e-5  # empty target = all blanks
     grad = ops.ctc_bwd(logits, lse, targets, in_len, tgt_len, alpha, beta, nll, torch.ones(N, device="cuda"), V, V - 1,
-                       ld, torch.float32)
+                       ld, torch.float32, scales=scales)
     assert rel_err(grad[..., :V], lp_ref.grad) < 5e-4
     assert torch.isfinite(grad).all()
 

@@ -169,11 +169,11 @@ def test_ctc_matches_torch(ops, V, dtype):
     gout = torch.rand(N, device="cuda") + 0.5
     (nll_ref[:4] * gout[:4].double()).sum().backward()
     for x, l in ((lp, None), (logits, lse)):
-        nll, alpha, beta = ops.ctc_fwd(x, l, targets, in_len, tgt_len, V, blank, want_beta=True)
+        nll, alpha, beta, scales = ops.ctc_fwd(x, l, targets, in_len, tgt_len, V, blank, want_beta=True)
         assert torch.isinf(nll[4]) and nll[4] > 0
         assert rel_err(nll[:4], nll_ref[:4]) < 1e-4
         grad = ops.ctc_bwd(x, l, targets, in_len, tgt_len, alpha, beta, nll, gout, V, blank, x.shape[-1],
-                           torch.float32)
+                           torch.float32, scales=scales)
         # torch's own fp32 CTC gradient is only ~2e-4 accurate; compare against the fp64 run
         assert rel_err(grad[:4, :, :V], lpd.grad[:4]) < 5e-4
         assert grad[:4, :, V:].abs().max().item() == 0 if x.shape[-1] > V else True

@@ -166,11 +166,11 @@ def bench_ctc():
     tl = torch.full((N,), S, device=dev, dtype=torch.int32)
     lse, _ = ops.log_softmax_fwd(logits, V, want_lp=False)
     report("log_softmax_fwd (lse only) V=29", timeit(lambda: ops.log_softmax_fwd(logits, V, want_lp=False)), 2 * M * ld, 0)
-    nll, alpha, beta = ops.ctc_fwd(logits, lse, targets, il, tl, V, 28, want_beta=True)
+    nll, alpha, beta, scales = ops.ctc_fwd(logits, lse, targets, il, tl, V, 28, want_beta=True)
     report("ctc_fwd (alpha+beta lattices)", timeit(lambda: ops.ctc_fwd(logits, lse, targets, il, tl, V, 28, want_beta=True)),
            8 * M * (2 * S + 1), 0)
     go = torch.full((N,), 1.0 / N, device=dev)
-    report("ctc_bwd (fused softmax grad)", timeit(lambda: ops.ctc_bwd(logits, lse, targets, il, tl, alpha, beta, nll, go, V, 28, ld, torch.bfloat16)),
+    report("ctc_bwd (fused softmax grad)", timeit(lambda: ops.ctc_bwd(logits, lse, targets, il, tl, alpha, beta, nll, go, V, 28, ld, torch.bfloat16, scales=scales)),
            8 * M * (2 * S + 1) + 4 * M * ld, 0)
 
 
