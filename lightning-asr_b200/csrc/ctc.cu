@@ -348,16 +348,33 @@ ctc_grad_kernel(const T* __restrict__ x, const float* __restrict__ lse, const in
     const float Pm = __uint_as_float(static_cast<uint32_t>(scales[2 * NT + 2 * n]));
     const int ep = scales[2 * NT + 2 * n + 1];
     const float w = scalbnf(1.0f / Pm, ea + eb - ep);
+    // every other state is the blank: its occupancy is summed in registers (even lanes own even states) and reduced with
+    // shuffles -- 16 lanes adding to the same shared-memory word per instruction was a large part of this kernel's time
+    float bsum = 0.f;
     for (int s = lane; s < Lp; s += 32) {
-      const int label = (s & 1) ? static_cast<int>(tg[s >> 1]) : blank;
-      atomicAdd(&occ[label], ar[s] * br[s] * w);
+      const float v = ar[s] * br[s] * w;
+      if (s & 1)
+        atomicAdd(&occ[static_cast<int>(tg[s >> 1])], v);
+      else
+        bsum += v;
     }
+    bsum = warp_sum(bsum);
+    __syncwarp();
+    if (lane == 0) occ[blank] += bsum;
   } else {
+    float bsum = 0.f;
     for (int s = lane; s < Lp; s += 32) {
       const int label = (s & 1) ? static_cast<int>(tg[s >> 1]) : blank;
       const float lpv = to_f32<T>(xr[label]) - l;
-      atomicAdd(&occ[label], expf(ar[s] + br[s] + nl - lpv));
+      const float v = expf(ar[s] + br[s] + nl - lpv);
+      if (s & 1)
+        atomicAdd(&occ[label], v);
+      else
+        bsum += v;
     }
+    bsum = warp_sum(bsum);
+    __syncwarp();
+    if (lane == 0) occ[blank] += bsum;
   }
   __syncwarp();
   for (int c = lane; c < ldg; c += 32) {
@@ -369,16 +386,19 @@ ctc_grad_kernel(const T* __restrict__ x, const float* __restrict__ lse, const in
 
 
 // ------------------------------------------------------------------------------------------------
-// CTC lattices, second generation: ONE WARP per (utterance, direction), no block barrier in the recursion.
+// CTC lattices, second generation: linear-domain ("scaled") forward-backward, 8 warps per (utterance, direction).
 //
-// The recursion is a chain of T' dependent steps; with one state per thread (ctc_lattice_kernel) every step pays a
-// block barrier over 13-19 warps plus a shared-memory round trip and a 3-way log-sum-exp (two ex2 + one lg2 on the MUFU
-// pipe): ~630 cycles per frame, 266 us for T' = 801 however few states there are.  Here a lane owns K CONSECUTIVE
-// states in registers, the two neighbours it needs from the previous lane come by warp shuffle, and the arithmetic is
-// the classic SCALED forward-backward instead of per-state logarithms: probabilities stay linear and every 4th frame the
-// whole column is multiplied by an exact power of two (so the scaling itself adds no rounding); the running exponent is
-// an INTEGER per frame.  Log space is kept where it matters -- alpha_t[s] = a[t][s] * 2^E[t] with E the shared exponent --
-// and a step is two adds and one multiply per state: ~150 issue cycles per frame for the whole lattice.
+// The recursion is a chain of T' dependent steps.  The round-1 kernel (ctc_lattice_kernel: one state per thread, log
+// space) pays per step a block barrier over 13-19 warps, a shared-memory round trip and a 3-way log-sum-exp (two ex2 + one
+// lg2 on the MUFU pipe): ~630 cycles per frame, 266 us for T' = 801 however few states there are.  Here a thread owns K
+// CONSECUTIVE states in registers, the two predecessors of its first state come by warp shuffle (from the previous warp:
+// through a double-buffered shared-memory slot), and the arithmetic is the classic SCALED forward-backward: probabilities
+// stay linear and every 4th frame the whole column is multiplied by an exact power of two (so the scaling itself adds no
+// rounding); the running exponent is an INTEGER per frame, alpha_t[s] = a[t][s] * 2^E[t].  A step is two adds and one
+// multiply per state and ONE barrier over 8 warps: ~460 cycles per frame, 198 us.  (Measured and rejected: more states per
+// thread on fewer warps (K = 4: 255 us), deferring the column's global store by a frame (212 us), and a barrier-free
+// skewed pipeline of warps with per-warp exponents and progress counters in shared memory (388 us: the fences of the
+// hand-off cost more than the barrier).)
 //   stage 1  ctc_emit_kernel      e[n, t, j] = exp(x[n, t, label_j] - lse[n, t]), j < S_n; e[n, t, S_max] = blank
 //                                 (one pass over the score matrix, any vocabulary size; the lattice reads rows of it)
 //   stage 2  ctc_lattice2_kernel  alpha (with the frame's emission) and beta~ (WITHOUT it: what the gradient needs, so
