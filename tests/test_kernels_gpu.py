@@ -231,3 +231,33 @@ def test_bilstm_matches_torch_packed_lstm(dtype, tol):
             ref.weight_hh_l0_reverse, ref.bias_ih_l0_reverse, ref.bias_hh_l0_reverse)
     for p, r in zip(params, refs):
         assert rel_err(p.grad.cpu(), r.grad) < tol
+
+
+@pytest.mark.parametrize("N,T,S,scale,gtol", [(8, 801, 200, 1.0, 3e-3), (8, 801, 100, 3.0, 3e-3),
+                                              (4, 1501, 60, 2.0, 1e-2)])
+def test_ctc_long_lattices_keep_the_mass_near_the_diagonal(ops, N, T, S, scale, gtol):
+    """long lattices with short / ragged targets and peaky emissions: the forward mass near the alignment diagonal sits
+    hundreds of octaves below the column maximum (this is what ruled out linear-domain lattices with a shared exponent per
+    frame as the default); loss and gradient against torch's fp64 CTC"""
+    torch.manual_seed(T + S)
+    V, ld = 29, 32
+    logits = (torch.randn(N, T, ld, device="cuda") * scale).bfloat16()
+    targets = torch.randint(0, V - 1, (N, S), device="cuda")
+    il = torch.full((N,), T, device="cuda", dtype=torch.int32)
+    il[1] = T - 37
+    tl = torch.full((N,), S, device="cuda", dtype=torch.int32)
+    tl[2] = S // 2
+    tl[3] = 1
+    lpd = torch.log_softmax(logits[..., :V].double(), -1).requires_grad_(True)
+    ref = F.ctc_loss(lpd.transpose(0, 1), targets, il.long(), tl.long(), blank=V - 1, reduction="none")
+    ref.sum().backward()
+    lse, _ = ops.log_softmax_fwd(logits, V, want_lp=False)
+    nll, alpha, beta, scales = ops.ctc_fwd(logits, lse, targets, il, tl, V, V - 1, want_beta=True)
+    assert torch.isfinite(nll).all()
+    assert rel_err(nll, ref) < 1e-4
+    grad = ops.ctc_bwd(logits, lse, targets, il, tl, alpha, beta, nll, torch.ones(N, device="cuda"), V, V - 1, ld,
+                       torch.float32, scales=scales)
+    # (softmax - occupancy): what torch returns as the gradient w.r.t. the log-probs (SURVEY.md a16).  The occupancy is
+    # exp(alpha + beta - log P - lp) with fp32 lattices whose entries reach |log alpha| ~ 2000 .. 8000 here: one ulp there
+    # is 2.4e-4 .. 1e-3, which bounds the relative accuracy of any fp32 log-space CTC gradient (torch's own included)
+    assert rel_err(grad[..., :V], lpd.grad) < gtol
