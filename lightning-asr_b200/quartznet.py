@@ -42,7 +42,7 @@ def _bn_buffers(bn):
     return (bn.running_mean, bn.running_var, bn.num_batches_tracked)
 
 
-_FOLD = {"enabled": False}
+_FOLD = {"enabled": os.environ.get("LASR_EVAL_FOLD", "0") == "1"}
 # channel-major series companions between blocks (csrc/dwconv_cm.cu); LASR_CM=0 is the A/B switch back to the gather kernels
 _CM = {"enabled": os.environ.get("LASR_CM", "1") != "0", "max_bytes": int(os.environ.get("LASR_CM_MAX_MB", "96")) << 20}
 
