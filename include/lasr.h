@@ -207,21 +207,29 @@ int lasr_bn_apply_act_fwd(const void* y, const lasr_bn_t* bn1, const void* r, co
  * companion outT of its output: the block that follows reads its depthwise input from it (models/QuartNet.py:30). */
 int lasr_cm_offset(int K);
 int lasr_cm_pitch(int T, int K);
+/* Toeplitz factors (nullable extras of the three calls below): the depthwise kernels multiply the series with a banded
+ * Toeplitz factor per channel built from the taps; (dw_w [C, 1, dw_K] fp32, toep, toep_flip) make the pass that writes
+ * the series also build the factors of the conv that will read it -- toep for its forward, toep_flip (reversed taps) for
+ * its data gradient, bf16 [C][lasr_cm_ks(K) * 16] each -- and lasr_dwconv1d_fwd_cm / _bwd_cm then fetch them with one
+ * bulk copy instead of rebuilding them in every launch's prologue.  Valid as long as the taps are unchanged. */
+int lasr_cm_ks(int K);
 int lasr_bn_apply_act_fwd_cm(const void* y, const lasr_bn_t* bn1, const void* r, const lasr_bn_t* bn2, const float* gate,
                              void* out, void* outT, int N, int T, int C, int S, int off, float eps, float momentum,
-                             int act, int side_effects, uint8_t* relu_bits, lasr_stream_t stream);
+                             int act, int side_effects, uint8_t* relu_bits, const float* dw_w, void* toep,
+                             void* toep_flip, int dw_K, lasr_stream_t stream);
 /* y [N, T, C] channels-last = depthwise conv of the series xT (flip = 1: reversed taps = the data gradient) + an
  * optional addend, given EITHER channels-last (addend [N, T, C]) OR as a series laid out like xT (addendT); same
  * arithmetic as lasr_dwconv1d_fwd(stride 1, bf16) */
-int lasr_dwconv1d_fwd_cm(const void* xT, const float* w, void* y, const void* addend, const void* addendT, int N, int T,
-                         int C, int K, int S, int flip, lasr_stream_t stream);
+int lasr_dwconv1d_fwd_cm(const void* xT, const float* w, void* y, const void* addend, const void* addendT,
+                         const void* toep, int N, int T, int C, int K, int S, int flip, lasr_stream_t stream);
 /* dw [C, 1, K] fp32 += sum_{n,t} dy[n,t,c] x[n, t + j - K/2, c] from the series of x and of dy (same K, same layout) */
 int lasr_dwconv1d_wgrad_cm(const void* xT, const void* dyT, float* dw, int N, int T, int C, int K, int S,
                            lasr_stream_t stream);
 /* stride-1 backward of one layer in ONE launch from series operands: dx [N, T, C] channels-last = correlation of dy with
  * the flipped taps (+ addend / addendT) and dw += (autograd of models/QuartNet.py:30) */
 int lasr_dwconv1d_bwd_cm(const void* xT, const void* dyT, const float* w, const void* addend, const void* addendT,
-                         void* dx, float* dw, int N, int T, int C, int K, int S, lasr_stream_t stream);
+                         const void* toep_flip, void* dx, float* dw, int N, int T, int C, int K, int S,
+                         lasr_stream_t stream);
 /* data gradient(s) of 1x1 convs written as channel-major series (bf16): dxT[c][n][off + t] = sum_k dy[n, t, k] w[k, c],
  * dy [N*T, Cout] channels-last, w [Cout, Cin]; the pads of dxT are written as zeros.  (dy2, w2, dxT2): optional second
  * problem of the same shape in the same launch (the block's residual conv), nullable together.  Returns

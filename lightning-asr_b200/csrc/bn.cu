@@ -8,7 +8,7 @@
 // Backward: bn_act_bwd_reduce (one pass: sum g, sum g*y, sum g*r per utterance chunk), bn_bwd_finalize (per-channel
 //   coefficients + dgamma/dbeta), bn_act_bwd_apply (one pass: dy, dr with the MaskCNN gradient mask).
 // Every thread moves 8 channels (16 B of bf16 / 32 B of fp32) per row.
-#include "common.cuh"
+#include "dw_common.cuh"
 
 #include <cstdlib>
 
@@ -326,7 +326,9 @@ __global__ void __launch_bounds__(256, 2)
 bn_apply_fwd_cm_kernel(const __nv_bfloat16* __restrict__ y, const lasr_bn_t bn1, const __nv_bfloat16* __restrict__ r,
                        const lasr_bn_t bn2, const float* __restrict__ gate, __nv_bfloat16* __restrict__ out,
                        __nv_bfloat16* __restrict__ outT, int N, int T_len, int C, int S, int off, double count, float eps,
-                       float momentum, int act, int side_effects, uint8_t* __restrict__ relu_bits) {
+                       float momentum, int act, int side_effects, uint8_t* __restrict__ relu_bits,
+                       const float* __restrict__ dw_w, __nv_bfloat16* __restrict__ toep,
+                       __nv_bfloat16* __restrict__ toep_flip, int dwK, int dwKS, int dw_delta) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float coef_s[];  // [4][C]
@@ -353,6 +355,20 @@ bn_apply_fwd_cm_kernel(const __nv_bfloat16* __restrict__ y, const lasr_bn_t bn1,
     }
   }
   __syncthreads();
+  // Toeplitz factors of the depthwise conv that will read outT (forward taps, and reversed: its data gradient), one
+  // 16-byte chunk per thread and trip: built here, once, instead of in the prologue of every depthwise launch
+  if (toep != nullptr) {
+    const int chunks_c = 2 * dwKS;
+    const long long total = 2ll * C * chunks_c;
+    for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < total;
+         q += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const int flip = q >= static_cast<long long>(C) * chunks_c ? 1 : 0;
+      const long long qq = q - (flip ? static_cast<long long>(C) * chunks_c : 0);
+      const int c = static_cast<int>(qq / chunks_c);
+      const uint4 v = toeplitz_chunk(dw_w + static_cast<size_t>(c) * dwK, dwK, dw_delta, flip, static_cast<int>(qq - static_cast<long long>(c) * chunks_c));
+      *reinterpret_cast<uint4*>((flip ? toep_flip : toep) + qq * 8) = v;
+    }
+  }
   // warp unit = 4 position groups (32 positions) x 8 channel vectors (64 channels); lane = (group, vector)
   const int lane = threadIdx.x & 31;
   const int gl = lane & 3, cvl = lane >> 2;
@@ -958,10 +974,16 @@ int lasr_bn_apply_act_fwd(const void* y, const lasr_bn_t* bn1, const void* r, co
 
 int lasr_bn_apply_act_fwd_cm(const void* y, const lasr_bn_t* bn1, const void* r, const lasr_bn_t* bn2, const float* gate,
                              void* out, void* outT, int N, int T, int C, int S, int off, float eps, float momentum,
-                             int act, int side_effects, uint8_t* relu_bits, lasr_stream_t stream) {
+                             int act, int side_effects, uint8_t* relu_bits, const float* dw_w, void* toep,
+                             void* toep_flip, int dw_K, lasr_stream_t stream) {
   if (N <= 0 || T <= 0 || C <= 0 || (C % 64) || C > 2048 || bn1 == nullptr || outT == nullptr) return LASR_ERR_BAD_SHAPE;
   if ((r != nullptr) != (bn2 != nullptr)) return LASR_ERR_BAD_SHAPE;
   if (S <= 0 || (S % 128) || off < 0 || (off % 8) || off + T > S) return LASR_ERR_BAD_SHAPE;
+  if ((toep != nullptr) != (toep_flip != nullptr) || (toep != nullptr && (dw_w == nullptr || dw_K < 3))) return LASR_ERR_BAD_SHAPE;
+  const int dwKS = toep != nullptr ? lasr_cm_ks_host(dw_K) : 0;
+  const int dw_delta = toep != nullptr ? off - dw_K / 2 : 0;
+  __nv_bfloat16* tp = static_cast<__nv_bfloat16*>(toep);
+  __nv_bfloat16* tpf = static_cast<__nv_bfloat16*>(toep_flip);
   const lasr_bn_t none{};
   const lasr_bn_t& b2 = bn2 ? *bn2 : none;
   const long long units = static_cast<long long>(N) * (S / 32) * (C / 64);
@@ -976,7 +998,8 @@ int lasr_bn_apply_act_fwd_cm(const void* y, const lasr_bn_t* bn1, const void* r,
   cudaError_t le;
 #define LASR_BN_CM(R, G)                                                                                           \
   le = launch_pdl(4, bn_apply_fwd_cm_kernel<R, G>, dim3(static_cast<unsigned>(ctas)), dim3(256), smem, stream, yy, *bn1, \
-                  rr, b2, gate, oo, ot, N, T, C, S, off, count, eps, momentum, act, side_effects, relu_bits)
+                  rr, b2, gate, oo, ot, N, T, C, S, off, count, eps, momentum, act, side_effects, relu_bits, dw_w, tp, tpf, \
+                  dw_K, dwKS, dw_delta)
   if (r != nullptr && gate != nullptr) LASR_BN_CM(true, true);
   else if (r != nullptr) LASR_BN_CM(true, false);
   else if (gate != nullptr) LASR_BN_CM(false, true);

@@ -95,6 +95,31 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// One 16-byte chunk of a channel's Toeplitz factor B[t, s] = w[s - t - delta] (t < 16 output frames of a row, s < KS series
+// positions) in the K-major no-swizzle core-matrix order [s / 8][t / 8], element (t % 8, s % 8): chunk `rem` of the
+// channel = (core = rem >> 3, row r = rem & 7); taps given un-flipped, `flip` reads them reversed (the data gradient).
+__device__ __forceinline__ uint4 toeplitz_chunk(const float* __restrict__ wc, int K, int delta, int flip, int rem) {
+  const int core = rem >> 3, r = rem & 7;
+  const int j0 = 8 * (core >> 1) - (8 * (core & 1) + r) - delta;
+  uint32_t o[4];
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    const int j = j0 + 2 * m;
+    const float a = (j >= 0 && j < K) ? wc[flip ? K - 1 - j : j] : 0.f;
+    const float b = (j + 1 >= 0 && j + 1 < K) ? wc[flip ? K - 2 - j : j + 1] : 0.f;
+    o[m] = f32x2_to_bf16x2(a, b);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+// plain (non-tensor) bulk copy global -> shared, completion counted on an mbarrier; size % 16 == 0
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+int lasr_cm_ks_host(int K);
+
 // debug timeline (tools/trace_dw.py): [CTA][8 slots][16 stamps] of %globaltimer, normally NULL
 unsigned long long* dw_trace_buffer();
 __device__ __forceinline__ unsigned long long dw_gtimer() {

@@ -42,10 +42,13 @@ struct DwCmParams {
   int t_chunks, pair_utt, pairs_per_utt;
   int items_per_cg, num_cg, ctas_per_cg, stages, w_early;
   int issuers;                // MMA issuer warps (1 or 2: 8 channels each)
+  const __nv_bfloat16* toep;  // nullable: the Toeplitz factors of all channels, prebuilt by the pass that wrote the series
+                              // ([C][2 KS chunks of 16 B], lasr_bn_apply_act_fwd_cm): one bulk copy instead of the build
   unsigned long long* trace;  // debug timeline (tools/trace_dw.py), normally NULL
 };
 
 int lasr_cm_offset_host(int K) { return (K / 2 + 7) / 8 * 8; }
+int lasr_cm_ks_host(int K) { return cdiv(K + 15 + lasr_cm_offset_host(K) - K / 2, 16) * 16; }
 int lasr_cm_pitch_host(int T, int K) {
   const int off = lasr_cm_offset_host(K);
   const int t_chunks = cdiv(T, CM_SL);
@@ -69,7 +72,8 @@ __device__ __forceinline__ void dwconv_cm_fwd_body(const CUtensorMap* __restrict
   uint64_t* empty_bar = bars + 4;     // [4] MMA -> TMA
   uint64_t* tmem_full_bar = bars + 8;   // [2]
   uint64_t* tmem_empty_bar = bars + 10; // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* toep_bar = bars + 12;       // prebuilt Toeplitz factors landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -89,9 +93,14 @@ __device__ __forceinline__ void dwconv_cm_fwd_body(const CUtensorMap* __restrict
       mbar_init(&tmem_full_bar[st], p.issuers);
       mbar_init(&tmem_empty_bar[st], 8);
     }
+    mbar_init(toep_bar, 1);
     mbar_fence_init();
     // the series of the first items are requested NOW: they land while the other warps build the Toeplitz factor
     pdl_wait();
+    if (p.toep != nullptr) {
+      mbar_arrive_expect_tx(toep_bar, static_cast<uint32_t>(DT_CG * toep_bytes_c));
+      bulk_load(s_toep, p.toep + static_cast<size_t>(c0) * p.KS * 16, static_cast<uint32_t>(DT_CG * toep_bytes_c), toep_bar);
+    }
     int it = 0;
     for (int idx = first; idx < p.items_per_cg && it < p.stages; idx += p.ctas_per_cg, ++it) {
       mbar_arrive_expect_tx(&full_bar[it], CM_STAGE);
@@ -111,31 +120,19 @@ __device__ __forceinline__ void dwconv_cm_fwd_body(const CUtensorMap* __restrict
     tmem_alloc(tmem_ptr_smem, 512);
     tmem_relinquish();
   }
-  if (!p.w_early) pdl_wait();
-  for (int i = threadIdx.x; i < DT_CG * p.K; i += CM_THREADS) {
-    const int c = i / p.K, j = i - c * p.K;
-    s_w[c * DT_MAX_KS + j] = c0 + c < p.C ? p.w[static_cast<size_t>(c0 + c) * p.K + (p.flip ? p.K - 1 - j : j)] : 0.f;
-  }
-  __syncthreads();
-  // Toeplitz factor B[t, s] = w[s - t - delta], t < 16 output frames of a row, s < KS series positions: K-major
-  // no-swizzle cores [s / 8][t / 8], element (t % 8, s % 8).  One 16-byte chunk = the 8 elements of (channel, core, row).
-  {
+  if (p.toep == nullptr) {
+    if (!p.w_early) pdl_wait();
+    for (int i = threadIdx.x; i < DT_CG * p.K; i += CM_THREADS) {
+      const int c = i / p.K, j = i - c * p.K;
+      s_w[c * DT_MAX_KS + j] = c0 + c < p.C ? p.w[static_cast<size_t>(c0 + c) * p.K + j] : 0.f;
+    }
+    __syncthreads();
+    // Toeplitz factor B[t, s] = w[s - t - delta] (dw_common.cuh), one 16-byte chunk per thread and trip
     const int chunks_c = 2 * p.KS;  // per channel: KS/8 x 2 cores x 8 rows
     for (int q = threadIdx.x; q < DT_CG * chunks_c; q += CM_THREADS) {
       const int c = q / chunks_c;
-      const int rem = q - c * chunks_c;
-      const int core = rem >> 3, r = rem & 7;
-      const int j0 = 8 * (core >> 1) - (8 * (core & 1) + r) - p.delta;
-      const float* wc = s_w + c * DT_MAX_KS;
-      uint32_t o[4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        const int j = j0 + 2 * m;
-        const float a = (j >= 0 && j < p.K) ? wc[j] : 0.f;
-        const float b = (j + 1 >= 0 && j + 1 < p.K) ? wc[j + 1] : 0.f;
-        o[m] = f32x2_to_bf16x2(a, b);
-      }
-      *reinterpret_cast<uint4*>(s_toep + static_cast<size_t>(q) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(s_toep + static_cast<size_t>(q) * 16) =
+          toeplitz_chunk(s_w + c * DT_MAX_KS, p.K, p.delta, p.flip, q - c * chunks_c);
     }
   }
   fence_proxy_async_smem();
@@ -178,6 +175,7 @@ __device__ __forceinline__ void dwconv_cm_fwd_body(const CUtensorMap* __restrict
       constexpr uint32_t idesc = umma_idesc_bf16(DT_ROWS, 16, 0, 0);
       const int ksteps = p.KS / 16;
       const int cpi = DT_CG / p.issuers;
+      if (p.toep != nullptr) mbar_wait(toep_bar, 0);
       int it = 0;
       for (int idx = first; idx < p.items_per_cg; idx += p.ctas_per_cg, ++it) {
         const int stage = it % p.stages;
@@ -554,8 +552,9 @@ static int cm_item_tmap(CUtensorMap* tm, const void* xT, int N, int C, int S, in
 }
 
 static void cm_params(DwCmParams& p, const float* w, void* y, const void* addend, int N, int T, int C, int K, int flip,
-                      int sms) {
+                      int sms, const void* toep = nullptr) {
   p.w = w;
+  p.toep = static_cast<const __nv_bfloat16*>(toep);
   p.y = static_cast<__nv_bfloat16*>(y);
   p.addend = static_cast<const __nv_bfloat16*>(addend);
   p.N = N;
@@ -564,7 +563,7 @@ static void cm_params(DwCmParams& p, const float* w, void* y, const void* addend
   p.K = K;
   p.flip = flip;
   p.delta = lasr_cm_offset_host(K) - K / 2;
-  p.KS = cdiv(K + 15 + p.delta, 16) * 16;
+  p.KS = lasr_cm_ks_host(K);
   p.w_early = early_param_loads() ? 1 : 0;
   static const int issuers = getenv("LASR_CM_ISSUERS") ? atoi(getenv("LASR_CM_ISSUERS")) : 2;
   p.issuers = issuers == 1 ? 1 : 2;
@@ -609,12 +608,12 @@ static int cm_fwd_smem(const DwCmParams& p) {
 }
 
 // addend: channels-last [N, T, C]; addendT: a series tensor laid out like xT (at most one of them)
-int dwconv_cm_fwd(const void* xT, const float* w, void* y, const void* addend, const void* addendT, int N, int T, int C,
-                  int K, int S, int flip, cudaStream_t stream) {
+int dwconv_cm_fwd(const void* xT, const float* w, void* y, const void* addend, const void* addendT, const void* toep,
+                  int N, int T, int C, int K, int S, int flip, cudaStream_t stream) {
   if (!dwconv_cm_supported(C, K) || S != lasr_cm_pitch_host(T, K) || (addend != nullptr && addendT != nullptr))
     return LASR_ERR_BAD_SHAPE;
   DwCmParams p{};
-  cm_params(p, w, y, addendT != nullptr ? addendT : addend, N, T, C, K, flip, kNumSMs);
+  cm_params(p, w, y, addendT != nullptr ? addendT : addend, N, T, C, K, flip, kNumSMs, toep);
   p.S = S;
   p.off = lasr_cm_offset_host(K);
   CUtensorMap tm;
@@ -673,13 +672,16 @@ int dwconv_cm_wgrad(const void* xT, const void* dyT, float* dw, int N, int T, in
 }
 
 // dx = corr(dy, flipped taps) + addend   and   dw += sum dy * shifted x   in one launch
-int dwconv_cm_bwd(const void* xT, const void* dyT, const float* w, const void* addend, const void* addendT, void* dx,
-                  float* dw, int N, int T, int C, int K, int S, cudaStream_t stream) {
+int dwconv_cm_bwd(const void* xT, const void* dyT, const float* w, const void* addend, const void* addendT,
+                  const void* toep_flip, void* dx, float* dw, int N, int T, int C, int K, int S, cudaStream_t stream) {
   if (!dwconv_cm_supported(C, K) || S != lasr_cm_pitch_host(T, K) || (addend != nullptr && addendT != nullptr))
     return LASR_ERR_BAD_SHAPE;
+  // SMs of the data-gradient half.  Half and half is the measured optimum at the config-2 shapes: the data gradient is
+  // paced by its epilogue (addend + 32-byte stores), the weight gradient by its MMAs, and a split by MMA counts (tried:
+  // 2 + 7 CTAs per channel group at C = 256) made the launch 40 % slower
   static const int share = getenv("LASR_CM_DGRAD_SMS") ? atoi(getenv("LASR_CM_DGRAD_SMS")) : kNumSMs / 2;
   DwCmParams pd{};
-  cm_params(pd, w, dx, addendT != nullptr ? addendT : addend, N, T, C, K, 1, share);
+  cm_params(pd, w, dx, addendT != nullptr ? addendT : addend, N, T, C, K, 1, share, toep_flip);
   pd.S = S;
   pd.off = lasr_cm_offset_host(K);
   DwCmWgParams pw{};
@@ -711,10 +713,12 @@ extern "C" {
 int lasr_cm_offset(int K) { return lasr_cm_offset_host(K); }
 int lasr_cm_pitch(int T, int K) { return lasr_cm_pitch_host(T, K); }
 
-int lasr_dwconv1d_fwd_cm(const void* xT, const float* w, void* y, const void* addend, const void* addendT, int N, int T,
-                         int C, int K, int S, int flip, lasr_stream_t stream) {
+int lasr_cm_ks(int K) { return lasr_cm_ks_host(K); }
+
+int lasr_dwconv1d_fwd_cm(const void* xT, const float* w, void* y, const void* addend, const void* addendT,
+                         const void* toep, int N, int T, int C, int K, int S, int flip, lasr_stream_t stream) {
   if (N <= 0 || T <= 0 || C <= 0 || xT == nullptr || y == nullptr || w == nullptr) return LASR_ERR_BAD_SHAPE;
-  return dwconv_cm_fwd(xT, w, y, addend, addendT, N, T, C, K, S, flip, stream);
+  return dwconv_cm_fwd(xT, w, y, addend, addendT, toep, N, T, C, K, S, flip, stream);
 }
 
 int lasr_dwconv1d_wgrad_cm(const void* xT, const void* dyT, float* dw, int N, int T, int C, int K, int S,
@@ -724,10 +728,11 @@ int lasr_dwconv1d_wgrad_cm(const void* xT, const void* dyT, float* dw, int N, in
 }
 
 int lasr_dwconv1d_bwd_cm(const void* xT, const void* dyT, const float* w, const void* addend, const void* addendT,
-                         void* dx, float* dw, int N, int T, int C, int K, int S, lasr_stream_t stream) {
+                         const void* toep_flip, void* dx, float* dw, int N, int T, int C, int K, int S,
+                         lasr_stream_t stream) {
   if (N <= 0 || T <= 0 || C <= 0 || xT == nullptr || dyT == nullptr || w == nullptr || dx == nullptr || dw == nullptr)
     return LASR_ERR_BAD_SHAPE;
-  return dwconv_cm_bwd(xT, dyT, w, addend, addendT, dx, dw, N, T, C, K, S, stream);
+  return dwconv_cm_bwd(xT, dyT, w, addend, addendT, toep_flip, dx, dw, N, T, C, K, S, stream);
 }
 
 }  // extern "C"

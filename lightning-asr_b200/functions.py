@@ -61,8 +61,9 @@ class SepConvBNFn(torch.autograd.Function):
     def forward(ctx, x, res_x, lengths, dw_w, pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2, bn_buffers,
                 rbn_buffers, stride, relu, training, drop=None, xs=None, cm_out=None):
         """xs: ops.Series companion of x (channel-major, written by the pass that produced x) or None;
-        cm_out: None | [K_next]: ask the apply pass for the Series companion of the OUTPUT, laid out for a depthwise conv
-        of kernel size K_next; it replaces the list's content (autograd Functions return tensors only)."""
+        cm_out: None | [K_next, taps_next]: ask the apply pass for the Series companion of the OUTPUT, laid out for a
+        depthwise conv of kernel size K_next (taps given: its Toeplitz factors are built too); the Series replaces the
+        list's first element (autograd Functions return tensors only)."""
         dt = x.dtype
         dev = x.device
         N, T_in, Cin = x.shape
@@ -102,11 +103,12 @@ class SepConvBNFn(torch.autograd.Function):
             s, hidden, gate = ops.se_excite_fwd(sums_y, scale1, shift1, T, se_w1.detach(), se_w2.detach())
         dr_ = _make_drop(drop, (N, T, Cout), dev, training)
         cm_k = cm_out[0] if cm_out else None
+        cm_w = cm_out[1].detach() if (cm_out and len(cm_out) > 1 and cm_out[1] is not None) else None
         # the backward passes read the ReLU gate as one byte per 8 channels instead of the whole output tensor
         bits = ops.relu_bits_alloc(N, T, Cout, dev) if (training and relu and dr_ is None and RELU_BITS) else None
         if cm_k is not None and dr_ is None and ops.cm_supported(Cout, cm_k, dt):
             out, cm_out[0] = ops.bn_apply_act(y, bn1, r, bn2, gate, act, BN_EPS, BN_MOMENTUM, side_effects=se_side,
-                                              cm_k=cm_k, relu_bits=bits)
+                                              cm_k=cm_k, relu_bits=bits, cm_w=cm_w)
         else:
             if cm_out:
                 cm_out[0] = None
@@ -118,7 +120,7 @@ class SepConvBNFn(torch.autograd.Function):
         ctx.save_for_backward(x, res_x, lengths, d, y, r, out, bn1.save, bn2.save if bn2 is not None else None, gate, s,
                               hidden, sums_y, scale1, shift1, pw_s, res_s, dw_w, pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b,
                               se_w1, se_w2, dr_.mask if dr_ is not None else None, xs.t if xs is not None else None,
-                              bits)
+                              bits, xs.toep_flip if xs is not None else None)
         ctx.cfg = (stride, act, training, K, Cin, Cout, dr_.p if dr_ is not None else 0.0)
         ctx.set_materialize_grads(False)
         return out
@@ -128,7 +130,7 @@ class SepConvBNFn(torch.autograd.Function):
         if dout is None:
             return (None,) * 20
         (x, res_x, lengths, d, y, r, out, save1, save2, gate, s, hidden, sums_y, scale1, shift1, pw_s, res_s, dw_w,
-         pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2, drop_mask, xs_t, bits) = ctx.saved_tensors
+         pw_w, bn_w, bn_b, res_w, rbn_w, rbn_b, se_w1, se_w2, drop_mask, xs_t, bits, toep_flip) = ctx.saved_tensors
         stride, act, training, K, Cin, Cout, drop_p = ctx.cfg
         drop = ops.Dropout(drop_mask, drop_p, "read") if drop_mask is not None else None
         if not training:
@@ -199,7 +201,7 @@ class SepConvBNFn(torch.autograd.Function):
             else:
                 dd_s, dxr_s = ops.pwconv_dgrad_cm(dy, pw_s, K), None
             g_dw, ret_dw = runtime.grad_sink(dw_w)
-            dx, _ = ops.dwconv_bwd_cm(xs, dd_s, dw_w.detach(), addend=dxr_s, out_dw=g_dw)
+            dx, _ = ops.dwconv_bwd_cm(xs, dd_s, dw_w.detach(), addend=dxr_s, out_dw=g_dw, toep_flip=toep_flip)
             runtime.grad_ready(dw_w)
             return (dx, d_res_x, None, ret_dw, ret_pw, ret_bn_w, ret_bn_b, ret_res, ret_rbn_w, ret_rbn_b, ret_se1,
                     ret_se2, None, None, None, None, None, None, None, None)

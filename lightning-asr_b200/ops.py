@@ -94,11 +94,13 @@ def dwconv_bwd(x, dy, w, addend=None, out_dw=None):
 class Series:
     """Channel-major companion of a channels-last activation (include/lasr.h, "channel-major series"): the operand of
     the TMA-fed depthwise kernels.  t: bf16 [C, N, S]; built for a depthwise conv of kernel size K over T frames."""
-    __slots__ = ("t", "N", "T", "C", "K", "S", "off")
+    __slots__ = ("t", "N", "T", "C", "K", "S", "off", "toep", "toep_flip")
 
     def __init__(self, t, N, T, C, K):
         self.t, self.N, self.T, self.C, self.K = t, N, T, C, K
         self.S, self.off = cm_pitch(T, K), cm_offset(K)
+        # Toeplitz factors of the conv that reads the series (forward / reversed taps), built by the pass that wrote it
+        self.toep = self.toep_flip = None
 
 
 def cm_offset(K):
@@ -153,7 +155,8 @@ def dwconv_fwd_cm(xs, w, flip=False, addend=None):
         raise _lib.LasrError(f"dwconv_fwd_cm: the series was laid out for K={xs.K}, the conv has K={K}")
     y = torch.empty((xs.N, xs.T, xs.C), device=xs.t.device, dtype=torch.bfloat16)
     a_cl, a_cm = _addends(addend)
-    call("lasr_dwconv1d_fwd_cm", xs.t, w, y, a_cl, a_cm, xs.N, xs.T, xs.C, K, xs.S, 1 if flip else 0)
+    call("lasr_dwconv1d_fwd_cm", xs.t, w, y, a_cl, a_cm, xs.toep_flip if flip else xs.toep, xs.N, xs.T, xs.C, K, xs.S,
+         1 if flip else 0)
     return y
 
 
@@ -164,8 +167,9 @@ def dwconv_wgrad_cm(xs, dys, K, out=None):
     return dw
 
 
-def dwconv_bwd_cm(xs, dys, w, addend=None, out_dw=None):
-    """Stride-1 backward in one launch from Series operands -> (dx [N, T, C] channels-last, dw [C, 1, K] fp32)."""
+def dwconv_bwd_cm(xs, dys, w, addend=None, out_dw=None, toep_flip=None):
+    """Stride-1 backward in one launch from Series operands -> (dx [N, T, C] channels-last, dw [C, 1, K] fp32).
+    toep_flip: the prebuilt Toeplitz factors of the reversed taps (Series.toep_flip of the forward's input)."""
     _chk(w, "w")
     K = w.shape[-1]
     if K != xs.K or K != dys.K or (xs.N, xs.T, xs.C) != (dys.N, dys.T, dys.C):
@@ -173,7 +177,7 @@ def dwconv_bwd_cm(xs, dys, w, addend=None, out_dw=None):
     dx = torch.empty((xs.N, xs.T, xs.C), device=xs.t.device, dtype=torch.bfloat16)
     dw = out_dw if out_dw is not None else torch.zeros((xs.C, 1, K), device=xs.t.device, dtype=torch.float32)
     a_cl, a_cm = _addends(addend)
-    call("lasr_dwconv1d_bwd_cm", xs.t, dys.t, w, a_cl, a_cm, dx, dw, xs.N, xs.T, xs.C, K, xs.S)
+    call("lasr_dwconv1d_bwd_cm", xs.t, dys.t, w, a_cl, a_cm, toep_flip, dx, dw, xs.N, xs.T, xs.C, K, xs.S)
     return dx, dw
 
 
@@ -379,10 +383,11 @@ def relu_bits_alloc(N, T, C, device):
 
 
 def bn_apply_act(y, bn1, r=None, bn2=None, gate=None, act=ACT_RELU, eps=1e-3, momentum=0.1, side_effects=True,
-                 drop=None, cm_k=None, relu_bits=None):
+                 drop=None, cm_k=None, relu_bits=None, cm_w=None):
     """out = act(BN1(y) [* gate] [* dropout] [+ BN2(r)]) in one pass; performs the training side effects of both BNs.
     cm_k = kernel size of the depthwise conv that consumes the result: also writes the channel-major Series companion
-    and returns (out, series).  relu_bits (relu_bits_alloc): receives the sign bits the backward passes read instead of
+    and returns (out, series); cm_w = that conv's taps [C, 1, cm_k]: the pass also builds its Toeplitz factors
+    (series.toep / .toep_flip).  relu_bits (relu_bits_alloc): receives the sign bits the backward passes read instead of
     `out`."""
     N, T, C = y.shape
     out = torch.empty_like(y)
@@ -393,8 +398,13 @@ def bn_apply_act(y, bn1, r=None, bn2=None, gate=None, act=ACT_RELU, eps=1e-3, mo
             raise _lib.LasrError("bn_apply_act: no channel-major companion for this configuration")
         xs = Series(None, N, T, C, cm_k)
         xs.t = torch.empty((C, N, xs.S), device=y.device, dtype=y.dtype)
+        if cm_w is not None:
+            ks16 = _lib.load().lasr_cm_ks(cm_k) * 16
+            xs.toep = torch.empty((C, ks16), device=y.device, dtype=y.dtype)
+            xs.toep_flip = torch.empty((C, ks16), device=y.device, dtype=y.dtype)
         call("lasr_bn_apply_act_fwd_cm", y, bn1.ptr, r, bn2.ptr if bn2 is not None else None, gate, out, xs.t, N, T, C,
-             xs.S, xs.off, eps, momentum, act, 1 if (side_effects and bn1.training) else 0, relu_bits)
+             xs.S, xs.off, eps, momentum, act, 1 if (side_effects and bn1.training) else 0, relu_bits, cm_w, xs.toep,
+             xs.toep_flip, cm_k)
         return out, xs
     call("lasr_bn_apply_act_fwd", y, bn1.ptr, r, bn2.ptr if bn2 is not None else None, gate, out, N * T, C, T, N * T,
          eps, momentum, act, 1 if (side_effects and bn1.training) else 0, drop.ptr if drop is not None else None,

@@ -114,11 +114,12 @@ class SeprationConv(nn.Module):
             return None, None
         return self.se.fc[0].weight, self.se.fc[2].weight
 
-    def forward(self, x, lengths, residual=None, res_x=None, drop_mask=None, next_k=None):
+    def forward(self, x, lengths, residual=None, res_x=None, drop_mask=None, next_k=None, next_w=None):
         """x [N, T, Cin] channels-last.  `residual` = (conv1x1, bn) of the enclosing block to fuse (then ReLU is
         applied after the add, models/QuartNet.py:75-77).  nn.Dropout(drop_rate) (:27,38) is fused into the apply pass;
         `drop_mask` (uint8 keep mask [N, T, Cout]) replaces the device-drawn mask (parity hook).
-        next_k: kernel size of the depthwise conv that consumes the result (None: unknown / not a depthwise conv).
+        next_k, next_w: kernel size and taps of the depthwise conv that consumes the result (None: unknown / not a
+        depthwise conv).
         When given (bf16), the apply pass also writes the channel-major series companion of the output and attaches it
         as `out._lasr_series`; a depthwise conv whose input carries a matching companion reads it through TMA
         (csrc/dwconv_cm.cu) instead of gathering the series from the channels-last tensor."""
@@ -129,7 +130,7 @@ class SeprationConv(nn.Module):
         # the companion pays (one more write stream in the apply pass) while the depthwise conv can read it back from
         # L2; at inference batch sizes (hundreds of MB per activation) everything streams through HBM and it loses
         small = x.shape[0] * x.shape[1] * self.pointwise_conv.out_channels * 2 <= _CM["max_bytes"]
-        cm_out = [next_k] if (next_k is not None and _CM["enabled"] and small) else None
+        cm_out = [next_k, next_w] if (next_k is not None and _CM["enabled"] and small) else None
         if self.se is None and _fold_ok(self, x):
             # eval fast path: dw conv -> [residual GEMM + bias] -> ONE GEMM with the whole block epilogue
             d = ops.dwconv_fwd(x, self.depthwise_conv.weight.detach(), stride=self.stride)
@@ -172,16 +173,17 @@ class QuartNetBlock(nn.Module):
         self.seq = nn.ModuleList(seq)
         self.drop_rate = drop_rate
 
-    def forward(self, x, lengths, drop_masks=None, next_k=None):
+    def forward(self, x, lengths, drop_masks=None, next_k=None, next_w=None):
         """drop_masks: optional list of uint8 keep masks, one per SeprationConv of `seq` (parity hook).
         next_k: kernel size of the depthwise conv that follows the block (see SeprationConv.forward)."""
         start = x
         for i, m in enumerate(self.seq[:-1]):
-            x = m(x, lengths, drop_mask=None if drop_masks is None else drop_masks[i], next_k=self.seq[i + 1].k)
+            x = m(x, lengths, drop_mask=None if drop_masks is None else drop_masks[i], next_k=self.seq[i + 1].k,
+                  next_w=self.seq[i + 1].depthwise_conv.weight)
         last = self.seq[-1]
         # dropout sits between BN and the residual add (models/QuartNet.py:38,76): the apply pass does both
         return last(x, lengths, residual=(self.reside[0], self.reside[1]), res_x=None if x is start else start,
-                    drop_mask=None if drop_masks is None else drop_masks[-1], next_k=next_k)
+                    drop_mask=None if drop_masks is None else drop_masks[-1], next_k=next_k, next_w=next_w)
 
 
 class BatchLSTM(nn.Module):
@@ -259,12 +261,15 @@ class QuartNet12(nn.Module):
         lengths = ops.out_lengths(T_out, percents.to(x.device))
         dm = drop_masks or {}
         blocks = [getattr(self, name) for name in self.block_names]
-        x = self.first_cnn(x, lengths, drop_mask=dm.get("first_cnn"), next_k=blocks[0].seq[0].k)
+        x = self.first_cnn(x, lengths, drop_mask=dm.get("first_cnn"), next_k=blocks[0].seq[0].k,
+                           next_w=blocks[0].seq[0].depthwise_conv.weight)
         for i, name in enumerate(self.block_names):
             # the next depthwise conv reads this block's output, unless the BiLSTM splice comes in between
             spliced = name == "block23" and self.variant != "base"
-            next_k = blocks[i + 1].seq[0].k if (i + 1 < len(blocks) and not spliced) else None
-            x = blocks[i](x, lengths, drop_masks=[dm[name]] if name in dm else None, next_k=next_k)
+            nxt = blocks[i + 1].seq[0] if (i + 1 < len(blocks) and not spliced) else None
+            x = blocks[i](x, lengths, drop_masks=[dm[name]] if name in dm else None,
+                          next_k=None if nxt is None else nxt.k,
+                          next_w=None if nxt is None else nxt.depthwise_conv.weight)
             if name == "block23" and self.variant != "base":
                 # models/QuartNetContext.py:171-173: length = (T' * percents).int() is the same `lengths` tensor; it
                 # stays on the device (the reference's `.cpu()` sync is gone)

@@ -192,3 +192,28 @@ def test_relu_bits_replace_the_output_tensor_in_the_backward_passes(ops, N, T, C
     assert rel_err(res[1][0], res[0][0]) < 1e-6  # fp32 partial sums, different CTA order
     assert rel_err(res[1][1], res[0][1]) < 1e-2 and rel_err(res[1][2], res[0][2]) < 1e-2
     assert rel_err(res[1][3], res[0][3]) < 1e-5
+
+
+@pytest.mark.parametrize("N,T,C,K", [(32, 801, 256, 33), (8, 801, 512, 75), (3, 157, 64, 39), (4, 2001, 128, 87)])
+def test_prebuilt_toeplitz_factors_give_the_same_results(ops, N, T, C, K):
+    """the BatchNorm pass builds the Toeplitz factors of the conv that reads its series; forward and backward launches
+    that fetch them must reproduce the launches that build them in their own prologue bit for bit"""
+    torch.manual_seed(K + C)
+    dev = "cuda"
+    y = torch.randn(N, T, C, device=dev).bfloat16()
+    sums = torch.stack((y.double().sum((0, 1)), (y.double() ** 2).sum((0, 1)))).contiguous()
+    bn = ops.BNForward(torch.rand(C, device=dev) + 0.5, torch.randn(C, device=dev), torch.zeros(C, device=dev),
+                       torch.ones(C, device=dev), torch.zeros((), device=dev, dtype=torch.int64), sums)
+    w = torch.randn(C, 1, K, device=dev) / K ** 0.5
+    out, xs = ops.bn_apply_act(y, bn, cm_k=K, cm_w=w)
+    assert xs.toep is not None and xs.toep_flip is not None
+    d = ops.dwconv_fwd_cm(xs, w)
+    toep, toep_flip = xs.toep, xs.toep_flip
+    xs.toep = xs.toep_flip = None
+    assert torch.equal(d, ops.dwconv_fwd_cm(xs, w))
+    dy = ops.series_from_ntc(torch.randn(N, T, C, device=dev).bfloat16(), K)
+    dx1, dw1 = ops.dwconv_bwd_cm(xs, dy, w, toep_flip=toep_flip)
+    dx2, dw2 = ops.dwconv_bwd_cm(xs, dy, w)
+    assert torch.equal(dx1, dx2)
+    assert rel_err(dw1, dw2) < 1e-5  # fp32 atomics in a different CTA split order
+    assert rel_err(d, _dw_ref(out, w.bfloat16().float())) < 6e-3
