@@ -119,7 +119,7 @@ const char* lasr_strerror(int code) {
   }
 }
 
-int lasr_abi_version(void) { return 2; }
+int lasr_abi_version(void) { return 3; }  // 3: series entry points, relu_bits / Toeplitz arguments, CTC scales
 
 int lasr_set_early_param_loads(int on) { return g_early_params.exchange(on != 0 ? 1 : 0); }
 

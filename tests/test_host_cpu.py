@@ -190,3 +190,27 @@ def test_bench_reference_arm_under_torchrun_world2():
     assert len(lines) == 1, out.stdout[-2000:]
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+
+
+def test_series_layout_helpers_hold_their_invariants():
+    """lasr_cm_offset / lasr_cm_pitch / lasr_cm_ks are host functions (no GPU): the invariants the TMA-fed depthwise
+    kernels and the pre-swizzled global layout rely on (include/lasr.h, "channel-major series")"""
+    from lightning_asr_b200 import _lib
+    lib = _lib.load()
+    for K in range(3, 91, 2):
+        off = lib.lasr_cm_offset(K)
+        ks = lib.lasr_cm_ks(K)
+        assert off % 8 == 0 and K // 2 <= off < K // 2 + 8          # left padding rounded up to one 16-byte group
+        assert ks % 16 == 0 and K + 15 + (off - K // 2) <= ks <= 112  # Toeplitz factor covers taps + 15 + the remainder
+        for T in (1, 7, 40, 157, 801, 895, 896, 897, 1501, 1792, 1793, 3000, 12000):
+            S = lib.lasr_cm_pitch(T, K)
+            assert S % 128 == 0                       # 256-byte rows: the swizzle phase of a block is its own
+            assert S >= off + T + 48                  # zero tail >= the weight gradient's backward reach
+            chunks = -(-T // 896)
+            if chunks > 1:                            # every 1024-position slot of every 896-output chunk lies in the row
+                assert S >= 896 * (chunks - 1) + 1024
+    # one group index permutation for the whole layout: an involution that only swaps neighbours in the upper half of a
+    # 128-position block
+    for g in range(64):
+        gs = g ^ ((g >> 3) & 1)
+        assert (gs ^ ((gs >> 3) & 1)) == g and gs // 2 == g // 2
