@@ -712,10 +712,12 @@ def run_b200(args):
     torch.cuda.set_device(local)
     _lib.require_device()
     if world > 1:
-        # the gradient exchange is 20-40 MB per step in <= 8 MB buckets: latency-, not bandwidth-bound.  Fewer NCCL CTAs
-        # leave the SMs to the persistent compute kernels the all-reduce overlaps with (measured at N = 2: exposed
-        # all-reduce 115 us with NCCL's default, 96 us with 4 CTAs, 310 us with 2)
-        os.environ.setdefault("NCCL_MAX_CTAS", "4")
+        # the gradient exchange is 20-40 MB per step in <= 8 MB buckets: latency-, not bandwidth-bound.  NCCL's CTAs get
+        # their own SMs: TrainEngine sizes every persistent kernel for 148 - NCCL_MAX_CTAS SMs (lasr_set_sm_budget), so the
+        # compute kernels no longer run a second wave on the SMs the all-reduce occupies.  Measured at N = 2 (exposed
+        # all-reduce per step, r3q/r3r sweeps): 2 CTAs 350 us, 4 CTAs 136 us, 8 CTAs 28 us, 12 CTAs 55 us, 16 CTAs 54 us;
+        # without the SM budget (round-1 behaviour) 4 CTAs were the optimum at 187 us
+        os.environ.setdefault("NCCL_MAX_CTAS", "8")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     peaks = load_peaks()
     infer = args.workload.startswith("infer_")

@@ -63,6 +63,10 @@ int lasr_check_device(void);
  * kernel is still draining.  Default 0: parameters are read only after the previous kernel has completed, like every
  * other operand.  Returns the previous setting.  (The reference has no counterpart: torch's stream order covers it.) */
 int lasr_set_early_param_loads(int on);
+/* SMs the persistent kernels (GEMMs, depthwise, BatchNorm passes) size their grids for: default all 148.  A caller that
+ * overlaps a collective with the compute stream (the gradient all-reduce, conf/conf.yaml:30) passes 148 minus the
+ * collective's CTAs: a one-CTA-per-SM grid that finds SMs taken runs its last CTAs as a second wave. */
+int lasr_set_sm_budget(int sms);
 
 /* ------------------------------------------------------------------------------------------------
  * Layout conversion at the module boundary.

@@ -98,6 +98,10 @@ __global__ void cast_weight_kernel(const float* __restrict__ w, OutT* __restrict
 
 using namespace lasr;
 
+namespace lasr {
+int g_sm_budget = kNumSMs;
+}
+
 extern "C" {
 
 const char* lasr_strerror(int code) {
@@ -119,6 +123,11 @@ const char* lasr_strerror(int code) {
   }
 }
 
+int lasr_set_sm_budget(int sms) {
+  if (sms < 16 || sms > lasr::kNumSMs) return LASR_ERR_BAD_SHAPE;
+  lasr::g_sm_budget = sms;
+  return LASR_OK;
+}
 int lasr_abi_version(void) { return 3; }  // 3: series entry points, relu_bits / Toeplitz arguments, CTC scales
 
 int lasr_set_early_param_loads(int on) { return g_early_params.exchange(on != 0 ? 1 : 0); }

@@ -827,7 +827,7 @@ constexpr int BN_THREADS = 256;  // 2 CTAs / SM x 256 threads x <= 128 registers
 static inline int bn_block(int CV) { return CV >= BN_THREADS ? CV : BN_THREADS / CV * CV; }
 static inline int persistent_grid(long long total_vec, int threads) {
   long long b = (total_vec + threads - 1) / threads;
-  const long long cap = 2LL * kNumSMs;
+  const long long cap = 2LL * sm_budget();
   return static_cast<int>(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
@@ -933,7 +933,7 @@ int lasr_sum_over_time(const void* y, float* sums, int N, int T, int C, int dtyp
     lasr_set_cuda_error(e);
     return LASR_ERR_CUDA;
   }
-  int chunks = cdiv(4 * kNumSMs, N);
+  int chunks = cdiv(4 * sm_budget(), N);
   if (chunks > cdiv(T, 16)) chunks = cdiv(T, 16);
   const int rows_per_chunk = cdiv(T, chunks);
   chunks = cdiv(T, rows_per_chunk);
@@ -988,7 +988,7 @@ int lasr_bn_apply_act_fwd_cm(const void* y, const lasr_bn_t* bn1, const void* r,
   const lasr_bn_t& b2 = bn2 ? *bn2 : none;
   const long long units = static_cast<long long>(N) * (S / 32) * (C / 64);
   long long ctas = (units + 7) / 8;
-  if (ctas > 2 * kNumSMs) ctas = 2 * kNumSMs;
+  if (ctas > 2 * sm_budget()) ctas = 2 * sm_budget();
   const int smem = 4 * C * static_cast<int>(sizeof(float));
   const double count = static_cast<double>(N) * T;
   const __nv_bfloat16* yy = static_cast<const __nv_bfloat16*>(y);
@@ -1010,7 +1010,7 @@ int lasr_bn_apply_act_fwd_cm(const void* y, const lasr_bn_t* bn1, const void* r,
 }
 
 int lasr_bn_bwd_chunks(int N, int T) {
-  int chunks = cdiv(4 * kNumSMs, N);
+  int chunks = cdiv(4 * sm_budget(), N);
   const int max_chunks = cdiv(T, 8);
   if (chunks > max_chunks) chunks = max_chunks;
   if (chunks < 1) chunks = 1;
@@ -1040,7 +1040,7 @@ int lasr_bn_act_bwd_reduce(const void* dout, const void* out, const void* y, con
   int chunks = lasr_bn_bwd_chunks(N, T);
   if (N == 1) {
     static const int mult = getenv("LASR_BN_RED_CTAS") ? atoi(getenv("LASR_BN_RED_CTAS")) : 2;
-    chunks = mult * kNumSMs;
+    chunks = mult * sm_budget();
     if (chunks > cdiv(T, 8)) chunks = cdiv(T, 8);
     chunks = cdiv(T, cdiv(T, chunks));
   }

@@ -58,6 +58,11 @@ inline cudaError_t launch_pdl(int family, void (*kernel)(KArgs...), dim3 grid, d
   } while (0)
 
 static constexpr int kNumSMs = 148;
+// SMs the persistent kernels size their grids for (lasr_set_sm_budget): all of them, unless the caller keeps some free
+// for a concurrently running collective (NCCL's CTAs during the overlapped gradient all-reduce) -- a one-CTA-per-SM grid
+// that finds 4 SMs taken runs its last 4 CTAs as a second wave, i.e. takes twice as long
+extern int g_sm_budget;
+inline int sm_budget() { return g_sm_budget; }
 
 __host__ __device__ __forceinline__ int cdiv(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ __forceinline__ long long cdivll(long long a, long long b) { return (a + b - 1) / b; }

@@ -613,7 +613,7 @@ int dwconv_cm_fwd(const void* xT, const float* w, void* y, const void* addend, c
   if (!dwconv_cm_supported(C, K) || S != lasr_cm_pitch_host(T, K) || (addend != nullptr && addendT != nullptr))
     return LASR_ERR_BAD_SHAPE;
   DwCmParams p{};
-  cm_params(p, w, y, addendT != nullptr ? addendT : addend, N, T, C, K, flip, kNumSMs, toep);
+  cm_params(p, w, y, addendT != nullptr ? addendT : addend, N, T, C, K, flip, sm_budget(), toep);
   p.S = S;
   p.off = lasr_cm_offset_host(K);
   CUtensorMap tm;
@@ -661,7 +661,7 @@ static int cm_wg_smem(const DwCmWgParams& p) { return 1024 + p.stages * WG_STAGE
 int dwconv_cm_wgrad(const void* xT, const void* dyT, float* dw, int N, int T, int C, int K, int S, cudaStream_t stream) {
   if (!dwconv_cm_supported(C, K) || S != lasr_cm_pitch_host(T, K)) return LASR_ERR_BAD_SHAPE;
   DwCmWgParams p{};
-  cm_wg_params(p, dw, N, C, K, S, kNumSMs);
+  cm_wg_params(p, dw, N, C, K, S, sm_budget());
   CUtensorMap tx, td;
   if (int rc = cm_row_tmap(&tx, xT, N, C, S, WG_XPOS / 128)) return rc;
   if (int rc = cm_row_tmap(&td, dyT, N, C, S, WG_CHUNK / 128)) return rc;
@@ -679,13 +679,14 @@ int dwconv_cm_bwd(const void* xT, const void* dyT, const float* w, const void* a
   // SMs of the data-gradient half.  Half and half is the measured optimum at the config-2 shapes: the data gradient is
   // paced by its epilogue (addend + 32-byte stores), the weight gradient by its MMAs, and a split by MMA counts (tried:
   // 2 + 7 CTAs per channel group at C = 256) made the launch 40 % slower
-  static const int share = getenv("LASR_CM_DGRAD_SMS") ? atoi(getenv("LASR_CM_DGRAD_SMS")) : kNumSMs / 2;
+  static const int forced_share = getenv("LASR_CM_DGRAD_SMS") ? atoi(getenv("LASR_CM_DGRAD_SMS")) : 0;
+  const int share = forced_share > 0 ? forced_share : sm_budget() / 2;
   DwCmParams pd{};
   cm_params(pd, w, dx, addendT != nullptr ? addendT : addend, N, T, C, K, 1, share, toep_flip);
   pd.S = S;
   pd.off = lasr_cm_offset_host(K);
   DwCmWgParams pw{};
-  cm_wg_params(pw, dw, N, C, K, S, kNumSMs - share);
+  cm_wg_params(pw, dw, N, C, K, S, sm_budget() - share);
   CUtensorMap ti, tx, td;
   if (int rc = cm_item_tmap(&ti, dyT, N, C, S, pd.t_chunks, pd.pair_utt)) return rc;
   if (int rc = cm_row_tmap(&tx, xT, N, C, S, WG_XPOS / 128)) return rc;

@@ -1169,7 +1169,8 @@ dwconv_tc_bwd2_kernel(const Dw16Params pd, const DwTcParams pw, const int split)
 // ------------------------------------------------------------------------------------------------
 // host
 // ------------------------------------------------------------------------------------------------
-static void dt_schedule(DwTcParams& p, int sms = kNumSMs) {
+static void dt_schedule(DwTcParams& p, int sms = 0) {
+  if (sms <= 0) sms = sm_budget();
   p.num_cg = cdiv(p.C, DT_CG);
   p.t_chunks = cdiv(p.T, DT_CHUNK);
   p.items_per_cg = p.N * p.t_chunks;
@@ -1234,7 +1235,7 @@ static int dwconv_tc16_fwd(const void* x, const float* w, void* y, const void* a
   p.slots_per_cg = N * p.t_chunks;
   p.items_per_cg = cdiv(p.slots_per_cg, 2);
   p.num_cg = cdiv(C, DT_CG);
-  int per = kNumSMs / p.num_cg;
+  int per = sm_budget() / p.num_cg;
   if (per < 1) per = 1;
   if (per > p.items_per_cg) per = p.items_per_cg;
   const int rounds = cdiv(p.items_per_cg, per);
@@ -1375,7 +1376,7 @@ int dwconv_tc_bwd(const void* x, const void* dy, const float* w, const void* add
   if (dw16 && K + 15 <= 112) {
     // second-generation bodies: 16-frame-row data gradient + 4-group weight gradient behind one blockIdx split
     Dw16Params pd{};
-    dw16_params(pd, dy, w, dx, addend, N, T, C, K, 1, kNumSMs / 2);
+    dw16_params(pd, dy, w, dx, addend, N, T, C, K, 1, sm_budget() / 2);
     DwTcParams pw{};
     pw.x = static_cast<const __nv_bfloat16*>(x);
     pw.dy = static_cast<const __nv_bfloat16*>(dy);
@@ -1386,7 +1387,7 @@ int dwconv_tc_bwd(const void* x, const void* dy, const float* w, const void* add
     pw.K = K;
     pw.KS = 0;
     pw.ZL = DT_CHUNK + 128;
-    dt_schedule(pw, kNumSMs / 2);
+    dt_schedule(pw, sm_budget() / 2);
     const int smem_d = 1024 + 2 * D16_STAGE + DT_CG * pd.KS * 32 + DT_CG * DT_MAX_KS * 4 + 256;
     const int smem_w = 128 + 2 * (DT_CG * pw.ZL * 2 + DT_CG * DT_CHUNK * 2) + 128;
     const int smem = smem_d > smem_w ? smem_d : smem_w;
@@ -1423,7 +1424,7 @@ int dwconv_tc_bwd(const void* x, const void* dy, const float* w, const void* add
   pd.flip = 1;
   pd.w_early = early_param_loads() ? 1 : 0;
   pd.ZL = DT_CHUNK + pd.KS - 8;
-  dt_schedule(pd, kNumSMs / 2);
+  dt_schedule(pd, sm_budget() / 2);
   DwTcParams pw{};
   pw.x = static_cast<const __nv_bfloat16*>(x);
   pw.dy = static_cast<const __nv_bfloat16*>(dy);
@@ -1434,7 +1435,7 @@ int dwconv_tc_bwd(const void* x, const void* dy, const float* w, const void* add
   pw.K = K;
   pw.KS = 0;
   pw.ZL = DT_CHUNK + 128;
-  dt_schedule(pw, kNumSMs / 2);
+  dt_schedule(pw, sm_budget() / 2);
   int smem_d = 128 + DT_CG * (pd.KS / 8) * 128 + DT_STAGES * DT_CG * pd.ZL * 2 + 128;
   const int smem_w = 128 + 2 * (DT_CG * pw.ZL * 2 + DT_CG * DT_CHUNK * 2) + 128;
   int smem = smem_d > smem_w ? smem_d : smem_w;

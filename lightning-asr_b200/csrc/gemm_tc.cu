@@ -1491,7 +1491,7 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
     if (!series) rc = make_tmap_2d_bf16(&tc2, fu.out2, N, M, static_cast<uint64_t>(ldc) * 2, 64, 128, true);
     if (rc) return rc;
   }
-  const int sms = grouped ? kNumSMs / 2 : kNumSMs;  // CTAs available to ONE problem
+  const int sms = grouped ? sm_budget() / 2 : sm_budget();  // CTAs available to ONE problem
   GemmWsParams p{};
   p.M = M;
   p.N = N;
@@ -1564,7 +1564,7 @@ static int launch_ws(bool b_mn, const void* a, const void* b, void* out, const f
                            : cudaOccupancyMaxActiveClusters(&n, gemm_ws_kernel<false>, &cfg);
       if (e != cudaSuccess || n <= 0) {
         (void)cudaGetLastError();
-        n = (kNumSMs / cluster) * 3 / 4;
+        n = (sm_budget() / cluster) * 3 / 4;
       }
       max_clusters[cluster] = n;
       cfg.dynamicSmemBytes = smem;
@@ -1645,7 +1645,7 @@ static int launch_ws2(bool b_mn, const void* a, const void* b, void* out, const 
   }
   p.num_n_blocks = cdiv(N, 256);   // 256-column pair slices
   p.num_k_blocks = kbs;
-  const int pairs = (kNumSMs / 2) / (grouped ? 2 : 1);  // pairs available to ONE problem
+  const int pairs = (sm_budget() / 2) / (grouped ? 2 : 1);  // pairs available to ONE problem
   if (p.num_n_blocks > pairs) return LASR_ERR_UNSUPPORTED;
   int per_n = pairs / p.num_n_blocks;
   if (per_n > p.num_m_blocks) per_n = p.num_m_blocks;
@@ -1748,7 +1748,7 @@ int gemm_tc_nt(const void* a, const void* b, void* out, const float* bias, const
   p.T = T;
   p.stats = stats;
   const int tiles = p.num_m_blocks * p.num_n_blocks;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  const int grid = tiles < sm_budget() ? tiles : sm_budget();
   switch (BN) {
     case 32: return launch_inst<32, false, false, 0>(ta, tb, p, grid, stream);
     case 64: return launch_inst<64, false, false, 0>(ta, tb, p, grid, stream);
@@ -1827,7 +1827,7 @@ int gemm_tc_nn(const void* a, const void* b, void* out, int M, int N, int K, int
   const int esz = out_f32 ? 4 : 2;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((static_cast<size_t>(ldc) * esz) % 16 == 0);
   const int tiles = p.num_m_blocks * p.num_n_blocks;
-  const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+  const int grid = tiles < sm_budget() ? tiles : sm_budget();
   switch (BN) {
     case 64: return launch_inst<64, false, true, 0>(ta, tb, p, grid, stream);
     case 128: return launch_inst<128, false, true, 0>(ta, tb, p, grid, stream);
@@ -1886,7 +1886,7 @@ int gemm_tc_tn_accum2(const void* dy1, const void* x1, float* dw1, const void* d
   p.num_n_blocks = cdiv(Cin, BN);
   p.num_k_blocks = cdiv(R, 64);
   const int tiles = p.num_m_blocks * p.num_n_blocks;
-  int splits = kNumSMs / (2 * tiles);
+  int splits = sm_budget() / (2 * tiles);
   if (splits < 1) return LASR_ERR_UNSUPPORTED;
   if (splits > p.num_k_blocks) splits = p.num_k_blocks;
   p.kb_per_split = cdiv(p.num_k_blocks, splits);
@@ -1897,7 +1897,7 @@ int gemm_tc_tn_accum2(const void* dy1, const void* x1, float* dw1, const void* d
   p.vec_ok = 1;
   p.groups = 2;
   const int total = 2 * tiles * p.k_splits;
-  const int grid = total < kNumSMs ? total : kNumSMs;
+  const int grid = total < sm_budget() ? total : sm_budget();
   switch (BN) {
     case 64: return launch_inst<64, true, true, 1>(ta, tb, p, grid, stream, &tc, &ta2, &tb2, &tc2);
     case 128: return launch_inst<128, true, true, 1>(ta, tb, p, grid, stream, &tc, &ta2, &tb2, &tc2);
@@ -1932,7 +1932,7 @@ int gemm_tc_tn_accum(const void* dy, const void* x, float* dw, int R, int Cout, 
       p.num_n_blocks = cdiv(Cin, 256);
       p.num_k_blocks = cdiv(R, 64);
       const int tiles = p.num_m_blocks * p.num_n_blocks;
-      const int pairs = kNumSMs / 2;
+      const int pairs = sm_budget() / 2;
       int splits = pairs / tiles;
       if (splits < 1) splits = 1;
       if (splits > p.num_k_blocks) splits = p.num_k_blocks;
@@ -1987,7 +1987,7 @@ int gemm_tc_tn_accum(const void* dy, const void* x, float* dw, int R, int Cout, 
   const int tiles = p.num_m_blocks * p.num_n_blocks;
   // one tile per CTA: every extra split adds a full Cout x Cin pass of L2 reductions
   static const int split_mult = getenv("LASR_WGRAD_SPLIT_MULT") ? atoi(getenv("LASR_WGRAD_SPLIT_MULT")) : 1;
-  int splits = (split_mult * kNumSMs) / tiles;
+  int splits = (split_mult * sm_budget()) / tiles;
   if (splits < 1) splits = 1;
   if (splits > p.num_k_blocks) splits = p.num_k_blocks;
   p.kb_per_split = cdiv(p.num_k_blocks, splits);
@@ -2004,7 +2004,7 @@ int gemm_tc_tn_accum(const void* dy, const void* x, float* dw, int R, int Cout, 
     if (rc) return rc;
   }
   const int total = tiles * p.k_splits;
-  const int grid = total < kNumSMs ? total : kNumSMs;
+  const int grid = total < sm_budget() ? total : sm_budget();
   switch (BN) {
     case 64: return launch_inst<64, true, true, 1>(ta, tb, p, grid, stream, &tc);
     case 128: return launch_inst<128, true, true, 1>(ta, tb, p, grid, stream, &tc);

@@ -9,6 +9,8 @@ on one GPU, optionally replayed from a CUDA graph.
 pytorch_lightning / hydra / comet are the reference's control plane and are out of scope (SURVEY.md section 2);
 `self.log` becomes a plain dict (`self.logged`).
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -202,6 +204,10 @@ class TrainEngine:
         self.optimizer = optimizer
         self.grad_sync = grad_sync
         if world_sync is not None:  # (group, bucket_mb): build the gradient exchange over the bank's flat buffer
+            if torch.distributed.is_initialized() and torch.distributed.get_world_size(world_sync[0]) > 1:
+                # leave NCCL's CTAs their SMs: the persistent kernels size their grids for the rest (include/lasr.h)
+                nccl_ctas = int(os.environ.get("NCCL_MAX_CTAS", "8"))
+                _lib.load().lasr_set_sm_budget(max(64, 148 - int(os.environ.get("LASR_SM_RESERVE", str(nccl_ctas)))))
             from . import ddp
             tail = world_sync[2] if len(world_sync) > 2 else (0.75, 2.5, 4.0)
             self.grad_sync = ddp.GradSync(module, group=world_sync[0], bucket_mb=world_sync[1], overlap=True,
