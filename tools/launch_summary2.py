@@ -52,7 +52,7 @@ def main():
               f"mean DRAM {a[2] / a[0] / 1e6:7.2f} MB/launch")
     if "--traffic" in sys.argv:
         out = {f: {"dram_bytes_per_launch": a[2] / a[0], "us_per_launch_under_ncu": a[1] / a[0], "launches": a[0],
-                   "share_of_kernel_time": a[1] / total, "source": "profiles/" + path.split("/")[-1].replace("launches_", "").replace(".csv", "") + "_launches.csv",
+                   "share_of_kernel_time": a[1] / total, "source": "profiles/" + path.split("/")[-1],
                    "how": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
                           "--clock-control none over `python bench.py --steps 2 --warmup 1 --no-cpu-baseline`"}
                for f, a in fam.items()}
