@@ -12,6 +12,7 @@
 #include "common.cuh"
 
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace lasr {
 
@@ -297,6 +298,228 @@ ctc_lattice_kernel(const T* __restrict__ x, const float* __restrict__ lse, const
   if (!backward && threadIdx.x == 0) {
     const float a = lds_f32(last + 4u * (Lp - 1 + 2));
     const float b = Lp >= 2 ? lds_f32(last + 4u * (Lp - 2 + 2)) : -CUDART_INF_F;
+    const float m = fmaxf(a, b);
+    nll[n] = (m == -CUDART_INF_F) ? CUDART_INF_F : -(m + logf(expf(a - m) + expf(b - m)));
+  }
+}
+
+constexpr uint32_t kCtcSentinel = 0x7fc0deadu;  // a NaN payload no arithmetic produces: "slot empty"
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-pipelined lattices (round 2, the default).  ncu on the kernels above: a warp spends a frame issuing its own
+// dependent instruction stream, then waits at the CTA barrier for the slowest warp, then pays the STS -> barrier -> LDS
+// round trip before the next frame can start.  Here a frame has NO CTA barrier and no shared-memory column: lane l of
+// warp w owns state 32w + l and keeps it in a register, the neighbours s-1 / s-2 (alpha; s+1 / s+2 for beta) come from
+// two warp shuffles, and only the two states across a warp boundary travel through shared memory: after frame f the
+// edge lane of warp w stores (its value, its neighbour's value) as ONE 8-byte word into slot f mod 16 of the next
+// warp's inbox; that warp reads the slot a frame EARLY (the load is issued at the top of frame f for use in frame f+1),
+// falls back to spinning only if it still holds the sentinel (a NaN payload no arithmetic produces -- value and flag
+// are the same word, so no fence), and puts the sentinel back.  Warp 0 depends on nobody, warp w settles a hand-over
+// latency behind warp w-1: the warps form a skewed pipeline, 13 warps deep for a 401-state lattice, each running at
+// the speed of its own shuffle -> log-sum-exp chain.  Flow control: a producer looks once every 8 frames whether the
+// slot 8 frames ahead has been emptied.  Emissions (and lse) are gathered 8 frames ahead into a register ring.
+// The arithmetic per state is that of ctc_lattice_kernel (same lse3_bf on the same operands): bit-identical results.
+// ------------------------------------------------------------------------------------------------
+constexpr int CTCW_SLOTS = 16;
+__device__ __forceinline__ uint2 lds_v2_volatile(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_v2_volatile(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+
+// one direction of one utterance's lattice; returns the lane's state at the last frame
+template <typename T, bool LSE, bool BWD>
+__device__ __forceinline__ float ctc_warp_lattice(const T* __restrict__ x, const float* __restrict__ lse,
+                                                  const int64_t* __restrict__ targets, float* __restrict__ lat, int n,
+                                                  int Tn, int Lp, int T_len, int ldx, int S_max, int blank,
+                                                  uint32_t inbox0) {
+  constexpr bool kHalf = sizeof(T) == 2;
+  constexpr uint32_t kNegInfWord = kHalf ? 0xff80u : 0xff800000u;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int Lp_max = 2 * S_max + 1;
+  float v = -CUDART_INF_F;
+  {
+    const int64_t* tg = targets + static_cast<size_t>(n) * S_max;
+    const size_t row0 = static_cast<size_t>(n) * T_len;
+    const int t_first = BWD ? Tn - 1 : 0;
+    const int dt = BWD ? -1 : 1;
+    const int st = tid;
+    const bool act = st < Lp;
+    int lab = blank;
+    bool skip_ok = false;  // may take the s-2 (alpha) / s+2 (beta) transition
+    if (act && (st & 1)) {
+      lab = static_cast<int>(tg[st >> 1]);
+      if (!BWD)
+        skip_ok = (st >= 2) && lab != static_cast<int>(tg[(st >> 1) - 1]);
+      else
+        skip_ok = (st + 2 < Lp) && lab != static_cast<int>(tg[(st >> 1) + 1]);
+    }
+    const char* srcb = reinterpret_cast<const char*>(x) +
+                       ((row0 + t_first) * static_cast<size_t>(ldx) + lab) * sizeof(T);
+    const ptrdiff_t src_step = static_cast<ptrdiff_t>(dt) * ldx * static_cast<ptrdiff_t>(sizeof(T));
+    const char* lseb = LSE ? reinterpret_cast<const char*>(lse + row0 + t_first) : nullptr;
+    const ptrdiff_t lse_step = static_cast<ptrdiff_t>(dt) * 4;
+    char* latb = reinterpret_cast<char*>(lat + (row0 + t_first) * Lp_max + (act ? st : 0));
+    const ptrdiff_t lat_step = static_cast<ptrdiff_t>(dt) * Lp_max * 4;
+    // the pipeline: alpha flows from warp w to w+1 (edge lanes 31 -> 0), beta from w+1 to w (edge lanes 0 -> 31)
+    const bool more_above = 32 * (warp + 1) < Lp;
+    const bool takes = BWD ? more_above : warp > 0;
+    const bool posts = BWD ? warp > 0 : more_above;
+    const int edge = BWD ? 31 : 0;          // the lane next to the producer warp
+    const int edge2 = BWD ? 30 : 1;
+    const bool is_edge = lane == edge, is_edge2 = lane == edge2;
+    const bool post_lane = posts && lane == (BWD ? 0 : 31);
+    const uint32_t inbox = inbox0 + 8u * CTCW_SLOTS * warp;
+    const uint32_t outbox = inbox0 + 8u * CTCW_SLOTS * (BWD ? warp - 1 : warp + 1);
+
+    uint32_t wv[CTC_RING];
+    float lr[CTC_RING];
+    auto fetch = [&](uint32_t& w, float& l) {  // the next frame not yet requested (idle lanes keep their -inf)
+      if (act) {
+        if constexpr (kHalf)
+          w = *reinterpret_cast<const unsigned short*>(srcb);
+        else
+          w = *reinterpret_cast<const uint32_t*>(srcb);
+      }
+      if constexpr (LSE) l = *reinterpret_cast<const float*>(lseb);
+      srcb += src_step;
+      if constexpr (LSE) lseb += lse_step;
+    };
+    auto emission = [&](uint32_t w, float l) {
+      const float em = __uint_as_float(kHalf ? (w << 16) : w);
+      return LSE ? em - l : em;
+    };
+    auto neighbours = [&](float val, float& n1, float& n2) {
+      if (BWD) {
+        n1 = __shfl_down_sync(0xffffffffu, val, 1);
+        n2 = __shfl_down_sync(0xffffffffu, val, 2);
+        if (lane >= 31) n1 = -CUDART_INF_F;  // no producer above: states past the lattice
+        if (lane >= 30) n2 = -CUDART_INF_F;
+      } else {
+        n1 = __shfl_up_sync(0xffffffffu, val, 1);
+        n2 = __shfl_up_sync(0xffffffffu, val, 2);
+        if (lane < 1) n1 = -CUDART_INF_F;
+        if (lane < 2) n2 = -CUDART_INF_F;
+      }
+    };
+
+#pragma unroll
+    for (int f = 0; f < CTC_RING; ++f) {
+      wv[f] = kNegInfWord;
+      lr[f] = 0.f;
+      if (f < Tn) fetch(wv[f], lr[f]);
+    }
+    float n1, n2;
+    {  // frame 0
+      const bool start = act && (BWD ? (st == Lp - 1 || st == Lp - 2) : (st == 0 || st == 1));
+      if (start) v = emission(wv[0], lr[0]);
+      if (CTC_RING < Tn) fetch(wv[0], lr[0]);
+      if (act) *reinterpret_cast<float*>(latb) = v;
+      neighbours(v, n1, n2);
+      if (post_lane) sts_v2_volatile(outbox, __float_as_uint(v), __float_as_uint(n1));
+    }
+    uint2 early = make_uint2(kCtcSentinel, kCtcSentinel);  // the producer's word for the coming frame, read a frame early
+    if (takes) early = lds_v2_volatile(inbox);
+    // frame f: `slot` = (f - 1) mod 16 holds the producer's frame f-1; the frame's own result goes to slot f mod 16
+    auto frame = [&](uint32_t& w, float& l, uint32_t slot, bool refill, bool more_frames) {
+      if (takes) {
+        uint2 m = early;
+        while (m.x == kCtcSentinel) m = lds_v2_volatile(inbox + 8u * slot);
+        if (is_edge) sts_v2_volatile(inbox + 8u * slot, kCtcSentinel, kCtcSentinel);  // slot free again
+        if (more_frames) early = lds_v2_volatile(inbox + 8u * ((slot + 1) & (CTCW_SLOTS - 1)));
+        n1 = is_edge ? __uint_as_float(m.x) : n1;
+        n2 = is_edge ? __uint_as_float(m.y) : (is_edge2 ? __uint_as_float(m.x) : n2);
+      }
+      const float c2 = skip_ok ? n2 : -CUDART_INF_F;
+      v = lse3_bf(v, n1, c2) + emission(w, l);
+      if (refill) fetch(w, l);
+      latb += lat_step;
+      if (act) *reinterpret_cast<float*>(latb) = v;
+      neighbours(v, n1, n2);
+      if (post_lane) {
+        const uint32_t bits = __float_as_uint(v);
+        sts_v2_volatile(outbox + 8u * ((slot + 1) & (CTCW_SLOTS - 1)), bits == kCtcSentinel ? 0x7fffffffu : bits,
+                        __float_as_uint(n1));
+      }
+    };
+    // a producer may run at most 16 frames ahead: before posting frames f .. f+7 it makes sure the slot of frame f+7 (last
+    // used by frame f-9) has been emptied -- the consumer empties slots in order
+    auto wait_room = [&](uint32_t slot_last) {
+      if (posts) {
+        while (lds_v2_volatile(outbox + 8u * slot_last).x != kCtcSentinel) {
+        }
+      }
+    };
+    int step = 1;
+    // steady state, 16 frames per trip (slot numbers and ring registers are immediates); all refills exist
+#pragma unroll 1
+    for (; step + 16 + CTC_RING <= Tn; step += 16) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        if ((u & 7) == 0) wait_room((u + 1 + 7) & (CTCW_SLOTS - 1));
+        frame(wv[(1 + u) & (CTC_RING - 1)], lr[(1 + u) & (CTC_RING - 1)], u, true, true);
+      }
+    }
+#pragma unroll 1
+    for (; step < Tn; step += 16) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        if (step + u < Tn) {
+          if ((u & 7) == 0) wait_room((u + 1 + 7) & (CTCW_SLOTS - 1));
+          frame(wv[(1 + u) & (CTC_RING - 1)], lr[(1 + u) & (CTC_RING - 1)], u, step + u + CTC_RING < Tn,
+                step + u + 1 < Tn);
+        }
+      }
+    }
+  }
+  return v;
+}
+
+template <typename T, bool LSE>
+__global__ void __launch_bounds__(1024)
+ctc_lattice_warp_kernel(const T* __restrict__ x, const float* __restrict__ lse, const int64_t* __restrict__ targets,
+                        const int32_t* __restrict__ in_len, const int32_t* __restrict__ tgt_len,
+                        float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll, int T_len, int ldx,
+                        int S_max, int blank) {
+  pdl_launch_dependents();
+  extern __shared__ float sm[];
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int warp = tid >> 5, nwarps = nthreads >> 5;
+  const int n = blockIdx.x;
+  const bool backward = blockIdx.y == 1;
+  // sm: inbox [nwarps][CTCW_SLOTS] 8-byte words, last column [nthreads]
+  const uint32_t inbox0 = smem_u32(sm);
+  const uint32_t fin = inbox0 + 8u * CTCW_SLOTS * nwarps;
+  for (int i = tid; i < 2 * CTCW_SLOTS * nwarps; i += nthreads) sts_u32(inbox0 + 4u * i, kCtcSentinel);
+  __syncthreads();
+  pdl_wait();
+  const int Tn = in_len[n];
+  const int Sn = tgt_len[n];
+  const int Lp = 2 * Sn + 1;
+  // infeasible / degenerate cases (torch: loss = inf when the target does not fit)
+  if (Tn <= 0 || Sn > S_max || Tn > T_len) {
+    if (!backward && tid == 0) nll[n] = (Tn == 0 && Sn == 0) ? 0.f : CUDART_INF_F;
+    return;
+  }
+  float v = -CUDART_INF_F;
+  if (32 * warp < Lp) {
+    if (backward)
+      v = ctc_warp_lattice<T, LSE, true>(x, lse, targets, beta, n, Tn, Lp, T_len, ldx, S_max, blank, inbox0);
+    else
+      v = ctc_warp_lattice<T, LSE, false>(x, lse, targets, alpha, n, Tn, Lp, T_len, ldx, S_max, blank, inbox0);
+  }
+  sts_f32(fin + 4u * tid, v);
+  __syncthreads();
+  if (!backward && tid == 0) {
+    const float a = lds_f32(fin + 4u * (Lp - 1));
+    const float b = Lp >= 2 ? lds_f32(fin + 4u * (Lp - 2)) : -CUDART_INF_F;
     const float m = fmaxf(a, b);
     nll[n] = (m == -CUDART_INF_F) ? CUDART_INF_F : -(m + logf(expf(a - m) + expf(b - m)));
   }
@@ -805,11 +1028,39 @@ static int ctc_lattice_launch(const void* x, const float* lse, const int64_t* ta
   return LASR_OK;
 }
 
+// LASR_CTC_WARP=0 selects the round-1 barrier kernel (A/B runs, the bit-identity test); lattices wider than 1024 states
+// always take it
+template <typename T>
+static int ctc_warp_dispatch(const void* x, const float* lse, const int64_t* targets, const int32_t* il,
+                             const int32_t* tl, float* alpha, float* beta, float* nll, int N, int T_len, int ldx,
+                             int S_max, int blank, cudaStream_t stream) {
+  const int Lp_max = 2 * S_max + 1;
+  const char* env = getenv("LASR_CTC_WARP");
+  if (env != nullptr && atoi(env) == 0) return LASR_ERR_UNSUPPORTED;
+  const int threads = cdiv(Lp_max, 32) * 32;
+  if (threads > 1024) return LASR_ERR_UNSUPPORTED;
+  const size_t smem = 8u * CTCW_SLOTS * (threads / 32) + 4u * threads;
+  const dim3 grid(N, beta != nullptr ? 2 : 1);
+  if (lse != nullptr)
+    LASR_CHECK_PDL(launch_pdl(8, ctc_lattice_warp_kernel<T, true>, grid, dim3(threads), smem, stream,
+                              static_cast<const T*>(x), lse, targets, il, tl, alpha, beta, nll, T_len, ldx, S_max,
+                              blank));
+  else
+    LASR_CHECK_PDL(launch_pdl(8, ctc_lattice_warp_kernel<T, false>, grid, dim3(threads), smem, stream,
+                              static_cast<const T*>(x), lse, targets, il, tl, alpha, beta, nll, T_len, ldx, S_max,
+                              blank));
+  return LASR_OK;
+}
+
 template <typename T>
 static int ctc_lattice_dispatch(const void* x, const float* lse, const int64_t* targets, const int32_t* il,
                                 const int32_t* tl, float* alpha, float* beta, float* nll, int N, int T_len, int ldx,
                                 int S_max, int blank, cudaStream_t stream) {
   const int Lp_max = 2 * S_max + 1;
+  {
+    const int rc = ctc_warp_dispatch<T>(x, lse, targets, il, tl, alpha, beta, nll, N, T_len, ldx, S_max, blank, stream);
+    if (rc != LASR_ERR_UNSUPPORTED) return rc;
+  }
 #define LASR_CTC_LAT(SPT, TH) \
   return ctc_lattice_launch<T, SPT, TH>(x, lse, targets, il, tl, alpha, beta, nll, N, T_len, ldx, S_max, blank, stream)
   if (Lp_max <= 128) LASR_CTC_LAT(1, 128);

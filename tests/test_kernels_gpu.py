@@ -261,3 +261,63 @@ def test_ctc_long_lattices_keep_the_mass_near_the_diagonal(ops, N, T, S, scale, 
     # exp(alpha + beta - log P - lp) with fp32 lattices whose entries reach |log alpha| ~ 2000 .. 8000 here: one ulp there
     # is 2.4e-4 .. 1e-3, which bounds the relative accuracy of any fp32 log-space CTC gradient (torch's own included)
     assert rel_err(grad[..., :V], lpd.grad) < gtol
+
+
+@pytest.mark.parametrize("N,T,S,dtype", [(5, 120, 30, torch.float32), (32, 801, 200, torch.bfloat16),
+                                         (16, 401, 100, torch.bfloat16), (3, 257, 300, torch.float32),
+                                         (2, 64, 1, torch.bfloat16), (4, 40, 15, torch.float32),
+                                         (3, 500, 511, torch.bfloat16)])
+@pytest.mark.parametrize("use_lse", [True, False])
+def test_ctc_warp_pipelined_lattices_are_bit_identical(ops, N, T, S, dtype, use_lse):
+    """The default lattice kernel (csrc/ctc.cu ctc_lattice_warp_kernel: states in registers, neighbours by warp shuffle,
+    warp-boundary states through a shared-memory mailbox, no CTA barrier per frame) runs the arithmetic of the round-1
+    barrier kernel: alpha, beta, nll and the gradient must not differ in a single bit -- ragged lengths, lattices of 1 to
+    32 warps, empty / one-label / infeasible targets, log-prob and logit + lse inputs."""
+    import os
+    torch.manual_seed(N * T + S)
+    V, ld = 29, 32
+    logits = (torch.randn(N, T, ld, device="cuda") * 2).to(dtype)
+    targets = torch.randint(0, V - 1, (N, S), device="cuda")
+    targets[0, : min(S, 12)] = 5  # repeats: no skip transitions there
+    il = torch.full((N,), T, device="cuda", dtype=torch.int32)
+    tl = torch.full((N,), min(S, T // 2), device="cuda", dtype=torch.int32)
+    il[1] = T - 37 if T > 40 else T
+    tl[1] = max(int(tl[1]) // 2, 1)
+    if N > 2:
+        tl[2] = 1
+    if N > 3:
+        tl[3] = 0
+    if N > 4:
+        il[4] = 2  # infeasible unless S <= 2
+    lse, lp = ops.log_softmax_fwd(logits, V, want_lp=not use_lse)
+    x, l = (logits, lse) if use_lse else (lp, None)
+    gout = torch.rand(N, device="cuda") + 0.5
+    old = os.environ.get("LASR_CTC_WARP")
+    results = {}
+    try:
+        for mode in ("0", "1"):
+            os.environ["LASR_CTC_WARP"] = mode
+            nll, alpha, beta, scales = ops.ctc_fwd(x, l, targets, il, tl, V, V - 1, want_beta=True)
+            grad = ops.ctc_bwd(x, l, targets, il, tl, alpha, beta, nll, gout, V, V - 1, x.shape[-1], torch.float32,
+                               scales=scales)
+            torch.cuda.synchronize()
+            results[mode] = (nll.clone(), alpha.clone(), beta.clone(), grad.clone())
+    finally:
+        if old is None:
+            os.environ.pop("LASR_CTC_WARP", None)
+        else:
+            os.environ["LASR_CTC_WARP"] = old
+    nll0, a0, b0, g0 = results["0"]
+    nll, a, b, g = results["1"]
+    feasible = torch.isfinite(nll0)
+    assert feasible.sum() >= min(N, 2)
+    assert torch.equal(torch.isfinite(nll), feasible)
+    assert torch.equal(nll[feasible], nll0[feasible])
+    assert bool((nll[~feasible] > 0).all())
+    for n in range(N):
+        if not bool(feasible[n]):
+            continue
+        Tn, Lp = int(il[n]), 2 * int(tl[n]) + 1
+        assert torch.equal(a[n, :Tn, :Lp], a0[n, :Tn, :Lp]), n
+        assert torch.equal(b[n, :Tn, :Lp], b0[n, :Tn, :Lp]), n
+        assert torch.equal(g[n], g0[n]), n
