@@ -823,6 +823,198 @@ bn_bwd_apply_kernel(const T* __restrict__ dout, const T* __restrict__ out, const
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Ring variants (round 2).  ncu on the passes above: DRAM 41-45 %, issue slots 42-49 %, and of the ~8.5 cycles between
+// two issues of a warp 4 are `long_scoreboard` -- a thread loads a trip's vectors into registers, waits, computes,
+// stores, and only then asks for the next trip: the memory pipe drains once per trip, and the 124 registers that hold
+// the raw vectors + coefficients cap the SM at 16 warps, too few to cover it.  Here every thread streams ITS OWN vectors
+// through a private slot ring in shared memory with cp.async (16 B per request, 3 trips ahead): the requests of trips
+// i+1 .. i+3 are in flight while trip i is unpacked (no CTA barrier -- a thread only ever reads what it asked for
+// itself, `cp.async.wait_group` is enough), ~110-150 KB per SM permanently in flight instead of a burst per trip.
+// The hot bf16 training variant of the backward APPLY pass only (no SE gate, no dropout, ReLU from the gate bits);
+// everything else keeps the register kernels.  Same arithmetic in the same order: bit-identical outputs; LASR_BN_RING=0
+// turns it off.  Measured (cold L2, N = 32, T' = 801, minus the 6.2 us event overhead): C = 512 28.6 -> 25.5 us
+// (5.1 TB/s of algorithmic bytes), C = 256 16.3 -> 14.3 us.  The same ring under the backward REDUCE pass measured
+// equal-to-slower (22.5 us for 80 MB at C = 512 either way: that pass already keeps 16 loads per thread in flight and is
+// paced by its launch ramp and the fp64 reduction tail) and was dropped; the forward pass issues 16 loads per thread
+// per unit as well.
+// ------------------------------------------------------------------------------------------------
+constexpr int RING_D = 4;  // trips in the ring (3 in flight + the one being consumed)
+constexpr int RING_U = 2;  // rows per trip and thread
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds_u4(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+static bool bn_ring_enabled() {
+  static const bool on = !(getenv("LASR_BN_RING") != nullptr && atoi(getenv("LASR_BN_RING")) == 0);
+  return on;
+}
+
+template <bool HAS_R>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_ring_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ y,
+                         const __nv_bfloat16* __restrict__ r, const double* __restrict__ totals,
+                         const float* __restrict__ coef1_in, const BnBwdSide bn1, const BnBwdSide bn2, double count,
+                         const int32_t* __restrict__ lengths, int T_len, __nv_bfloat16* __restrict__ dy,
+                         __nv_bfloat16* __restrict__ dr, long long total_vec, int CV, int C,
+                         const uint8_t* __restrict__ relu_bits) {
+  using T = __nv_bfloat16;
+  pdl_launch_dependents();
+  pdl_wait();  // totals come from the reduce pass right before
+  extern __shared__ float coef_s[];  // coef1 [3][C], coef2 [3][C], then the slot ring
+  float* k1 = coef_s;
+  float* k2 = coef_s + 3 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float c0, c1, c2, dg, db;
+    double t_a = totals[c], t_b1 = 0.0, t_b2 = 0.0;
+    float g1 = 0.f, m1 = 0.f, i1 = 0.f, g2 = 0.f, m2 = 0.f, i2 = 0.f;
+    if (coef1_in == nullptr) {
+      t_b1 = totals[C + c];
+      g1 = bn1.gamma[c];
+      m1 = bn1.mean[c];
+      i1 = bn1.invstd[c];
+    }
+    if constexpr (HAS_R) {
+      t_b2 = totals[2 * C + c];
+      g2 = bn2.gamma[c];
+      m2 = bn2.mean[c];
+      i2 = bn2.invstd[c];
+    }
+    if (coef1_in != nullptr) {
+      k1[c] = coef1_in[c];
+      k1[C + c] = coef1_in[C + c];
+      k1[2 * C + c] = coef1_in[2 * C + c];
+    } else {
+      bn_bwd_coef(t_a, t_b1, count, g1, m1, i1, c0, c1, c2, dg, db);
+      k1[c] = c0;
+      k1[C + c] = c1;
+      k1[2 * C + c] = c2;
+      if (blockIdx.x == 0) {
+        if (bn1.dgamma != nullptr) bn1.dgamma[c] += dg;
+        if (bn1.dbeta != nullptr) bn1.dbeta[c] += db;
+      }
+    }
+    if constexpr (HAS_R) {
+      bn_bwd_coef(t_a, t_b2, count, g2, m2, i2, c0, c1, c2, dg, db);
+      k2[c] = c0;
+      k2[C + c] = c1;
+      k2[2 * C + c] = c2;
+      if (blockIdx.x == 0) {
+        if (bn2.dgamma != nullptr) bn2.dgamma[c] += dg;
+        if (bn2.dbeta != nullptr) bn2.dbeta[c] += db;
+      }
+    }
+  }
+  __syncthreads();
+  const int rpb = static_cast<int>(blockDim.x) / CV;
+  const int r_in = static_cast<int>(threadIdx.x) / CV;
+  const int cv = static_cast<int>(threadIdx.x) - r_in * CV;
+  if (r_in >= rpb) return;
+  const int c = cv * 8;
+  const int rows = static_cast<int>(total_vec / CV);
+  float a0[8], a1[8], a2[8], b0[8], b1[8], b2[8];
+  lds8(k1 + c, a0);
+  lds8(k1 + C + c, a1);
+  lds8(k1 + 2 * C + c, a2);
+  if constexpr (HAS_R) {
+    lds8(k2 + c, b0);
+    lds8(k2 + C + c, b1);
+    lds8(k2 + 2 * C + c, b2);
+  }
+  constexpr int K = HAS_R ? 3 : 2;  // vectors per row: dout, y [, r]
+  // slot (stage, u, k) of this thread: consecutive threads 16 B apart (conflict-free 128-bit accesses)
+  const uint32_t ring = smem_u32(coef_s + 6 * C) + 16u * threadIdx.x;
+  auto slot = [&](int st, int u, int k) { return ring + 16u * 256u * static_cast<uint32_t>((st * RING_U + u) * K + k); };
+  const int row_stride = static_cast<int>(gridDim.x) * rpb;
+  const int first = static_cast<int>(blockIdx.x) * rpb + r_in;
+  const int Tb = (T_len + 7) >> 3;
+  // per-stage bookkeeping in registers (the loop below is unrolled over the ring: compile-time indices)
+  uint32_t ob[RING_D][RING_U];
+  int len_n[RING_D][RING_U], t_of[RING_D][RING_U];
+  auto issue = [&](int trip, int st) {
+#pragma unroll
+    for (int u = 0; u < RING_U; ++u) {
+      const int row = first + (trip * RING_U + u) * row_stride;
+      if (row < rows) {
+        const long long v = static_cast<long long>(row) * CV + cv;
+        const int n = row / T_len;
+        const int t = row - n * T_len;
+        cp_async_16(slot(st, u, 0), dout + v * 8);
+        cp_async_16(slot(st, u, 1), y + v * 8);  // also for padded frames: `keep` is only known when the length lands
+        if constexpr (HAS_R) cp_async_16(slot(st, u, 2), r + v * 8);
+        ob[st][u] = relu_bits != nullptr ? relu_bits[relu_bits_index(n, t, cv, Tb, CV)] : 0xffu;
+        len_n[st][u] = lengths != nullptr ? lengths[n] : T_len;
+        t_of[st][u] = t;
+      }
+    }
+    cp_async_commit_group();
+  };
+  auto consume = [&](int trip, int st) {
+#pragma unroll
+    for (int u = 0; u < RING_U; ++u) {
+      const int row = first + (trip * RING_U + u) * row_stride;
+      if (row >= rows) break;
+      const long long v = static_cast<long long>(row) * CV + cv;
+      float g[8];
+      Vec8<T>::unpack(lds_u4(slot(st, u, 0)), g);
+      const uint32_t bits = ob[st][u];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = ((bits >> i) & 1u) ? g[i] : 0.f;
+      if constexpr (HAS_R) {
+        float rr[8], d[8];
+        Vec8<T>::unpack(lds_u4(slot(st, u, 2)), rr);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = fmaf(b0[i], g[i], fmaf(b1[i], rr[i], b2[i]));
+        Vec8<T>::store(dr + v * 8, d);
+      }
+      float d[8];
+      if (t_of[st][u] < len_n[st][u]) {
+        float yy[8];
+        Vec8<T>::unpack(lds_u4(slot(st, u, 1)), yy);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = fmaf(a0[i], g[i], fmaf(a1[i], yy[i], a2[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] = 0.f;
+      }
+      Vec8<T>::store(dy + v * 8, d);
+    }
+  };
+  const int per_trip = RING_U * row_stride;
+  const int ntrips = first < rows ? (rows - first + per_trip - 1) / per_trip : 0;
+#pragma unroll
+  for (int s = 0; s < RING_D - 1; ++s) {
+    if (s < ntrips)
+      issue(s, s);
+    else
+      cp_async_commit_group();
+  }
+#pragma unroll 1
+  for (int i = 0; i < ntrips; i += RING_D) {
+#pragma unroll
+    for (int d = 0; d < RING_D; ++d) {
+      const int trip = i + d;
+      if (trip < ntrips) {
+        if (trip + RING_D - 1 < ntrips)
+          issue(trip + RING_D - 1, (d + RING_D - 1) % RING_D);
+        else
+          cp_async_commit_group();
+        cp_async_wait_group<RING_D - 1>();
+        consume(trip, d);
+      }
+    }
+  }
+}
+
 constexpr int BN_THREADS = 256;  // 2 CTAs / SM x 256 threads x <= 128 registers: coefficients + 8 vectors in flight per thread
 static inline int bn_block(int CV) { return CV >= BN_THREADS ? CV : BN_THREADS / CV * CV; }
 static inline int persistent_grid(long long total_vec, int threads) {
@@ -877,6 +1069,29 @@ static int bn_bwd_launch(const void* dout, const void* out, const void* y, const
   TT* o0 = static_cast<TT*>(dy);
   TT* o1 = static_cast<TT*>(dr);
   cudaError_t le;
+  if constexpr (sizeof(TT) == 2) {
+    // the hot training variant streams through a per-thread cp.async ring (bn_bwd_apply_ring_kernel)
+    const bool relu_ok = act == LASR_ACT_RELU ? relu_bits != nullptr : true;
+    const int ring_smem = smem + RING_D * RING_U * (r != nullptr ? 3 : 2) * 256 * 16;
+    if (bn_ring_enabled() && gate == nullptr && drop_mask == nullptr && relu_ok && totals != nullptr && threads <= 256 &&
+        ring_smem <= 113 * 1024) {
+      const uint8_t* bits = act == LASR_ACT_RELU ? relu_bits : nullptr;
+      static bool configured = false;
+      if (!configured) {
+        cudaFuncSetAttribute(bn_bwd_apply_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        cudaFuncSetAttribute(bn_bwd_apply_ring_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
+        configured = true;
+      }
+      if (r != nullptr)
+        le = launch_pdl(4, bn_bwd_apply_ring_kernel<true>, dim3(grid), dim3(threads), ring_smem, stream, a0, a2, a3, totals,
+                        coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, bits);
+      else
+        le = launch_pdl(4, bn_bwd_apply_ring_kernel<false>, dim3(grid), dim3(threads), ring_smem, stream, a0, a2, a3,
+                        totals, coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, bits);
+      LASR_CHECK_PDL(le);
+      return LASR_OK;
+    }
+  }
 #define LASR_BN_BWD(R, G, D)                                                                                       \
   le = launch_pdl(4, bn_bwd_apply_kernel<TT, R, G, D>, dim3(grid), dim3(threads), smem, stream, a0, a1, a2, a3, gate,   \
                   extra, totals, coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, act, drop_mask, drop_scale,   \

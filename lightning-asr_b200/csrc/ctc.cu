@@ -309,20 +309,42 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Warp-pipelined lattices (round 2, the default).  ncu on the kernels above: a warp spends a frame issuing its own
-// dependent instruction stream, then waits at the CTA barrier for the slowest warp, then pays the STS -> barrier -> LDS
-// round trip before the next frame can start.  Here a frame has NO CTA barrier and no shared-memory column: lane l of
-// warp w owns state 32w + l and keeps it in a register, the neighbours s-1 / s-2 (alpha; s+1 / s+2 for beta) come from
-// two warp shuffles, and only the two states across a warp boundary travel through shared memory: after frame f the
-// edge lane of warp w stores (its value, its neighbour's value) as ONE 8-byte word into slot f mod 16 of the next
-// warp's inbox; that warp reads the slot a frame EARLY (the load is issued at the top of frame f for use in frame f+1),
-// falls back to spinning only if it still holds the sentinel (a NaN payload no arithmetic produces -- value and flag
-// are the same word, so no fence), and puts the sentinel back.  Warp 0 depends on nobody, warp w settles a hand-over
-// latency behind warp w-1: the warps form a skewed pipeline, 13 warps deep for a 401-state lattice, each running at
-// the speed of its own shuffle -> log-sum-exp chain.  Flow control: a producer looks once every 8 frames whether the
-// slot 8 frames ahead has been emptied.  Emissions (and lse) are gathered 8 frames ahead into a register ring.
-// The arithmetic per state is that of ctc_lattice_kernel (same lse3_bf on the same operands): bit-identical results.
+// Warp-pipelined lattices (round 2, the default).  ncu on the kernel above: a warp spends a frame issuing its own
+// dependent instruction stream (~90 instructions), then waits at the CTA barrier for the slowest warp, then pays the
+// STS -> barrier -> LDS round trip before the next frame can start.  Here a frame has NO CTA barrier and no
+// shared-memory column.  Lane l of warp w owns the even state s0 = 64w + 2l (a blank) and the odd state s0 + 1 (label
+// 32w + l) in registers: half the warps of a one-state-per-thread layout issue per SM (7 instead of 13 for 401 states),
+// every lane has two independent log-sum-exp chains in flight, and the neighbourhood shrinks -- a blank has no skip
+// transition and the label's s-1 is the lane's own blank, so alpha needs ONE value from the lane below (its label
+// state: one shuffle), beta two from the lane above.  Only the pair across a WARP boundary travels through shared
+// memory: after frame f the edge lane of warp w stores its pair as ONE 8-byte word into slot f mod 16 of the next warp's
+// inbox; that warp reads the slot a frame EARLY (the load is issued at the top of frame f for use in frame f+1), falls
+// back to spinning only if it still holds the sentinel (a NaN payload no arithmetic produces -- value and flag are the
+// same word, so no fence), and puts the sentinel back.  Warp 0 depends on nobody, warp w settles a hand-over latency
+// behind warp w-1: the warps form a skewed pipeline, each running at the speed of its own shuffle -> log-sum-exp chain.
+// Flow control: a producer looks once every 8 frames whether the slot 8 frames ahead has been emptied.  Emissions (and
+// lse) are gathered 8 frames ahead with plain 16-bit / 32-bit loads into a REGISTER ring (the frame loop is unrolled
+// over it, so ring slots and mailbox slots are immediates; no cp.async groups, no shared-memory ring).
+// log(e^a + e^b) is evaluated as lse3_bf(a, b, -inf) term by term (its third exponential is exactly 0), every state sees
+// the operands of ctc_lattice_kernel in the same order: results are bit-identical
+// (tests/test_kernels_gpu.py::test_ctc_warp_pipelined_lattices_are_bit_identical).
+// Measured (N = 32, T' = 801, S = 200, bf16 logits + lse, stand-alone incl. ~8 us of event overhead): round-1 kernel
+// 266 us; the same barrier kernel with the register ring and an unrolled loop 173 us; a lattice cut over a 2- / 4-CTA
+// cluster with the boundary states posted into the neighbour's shared memory (st.shared::cluster) 184 / 182 us (the
+// spinning consumer costs more than the second SM brings); one state per lane + shuffles 147 us; this kernel 141 us.
+// What is left is the length of one warp's instruction stream per frame (~80 instructions for 64 states, most of them
+// dependent) against a floor of ~130 cycles for shuffle + log-sum-exp.
 // ------------------------------------------------------------------------------------------------
+// keep a running pointer / shared address in its register: without this the compiler re-derives it from the loop
+// counter (or re-reads the shared window base) inside the frame loop, several instructions per use
+template <typename P>
+__device__ __forceinline__ void keep_ptr(P*& p) {
+  asm volatile("" : "+l"(p));
+}
+__device__ __forceinline__ void keep_u32(uint32_t& a) {
+  asm volatile("" : "+r"(a));
+}
+
 constexpr int CTCW_SLOTS = 16;
 __device__ __forceinline__ uint2 lds_v2_volatile(uint32_t addr) {
   uint2 v;
@@ -333,168 +355,203 @@ __device__ __forceinline__ void sts_v2_volatile(uint32_t addr, uint32_t a, uint3
   asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 
-// one direction of one utterance's lattice; returns the lane's state at the last frame
+__device__ __forceinline__ float lse2_bf(float a, float b) {
+  const float m = fmaxf(a, b), lo = fminf(a, b);
+  const float mc = fmaxf(m, -3.0e38f);
+  const float e2 = ex2_approx((lo - mc) * 1.4426950408889634f);
+  const float r = fmaf(lg2_approx(1.f + e2), 0.6931471805599453f, mc);
+  return m == -CUDART_INF_F ? -CUDART_INF_F : r;
+}
+
 template <typename T, bool LSE, bool BWD>
-__device__ __forceinline__ float ctc_warp_lattice(const T* __restrict__ x, const float* __restrict__ lse,
+__device__ __forceinline__ void ctc_warp2_lattice(const T* __restrict__ x, const float* __restrict__ lse,
                                                   const int64_t* __restrict__ targets, float* __restrict__ lat, int n,
                                                   int Tn, int Lp, int T_len, int ldx, int S_max, int blank,
-                                                  uint32_t inbox0) {
+                                                  uint32_t inbox0, float& v0, float& v1) {
   constexpr bool kHalf = sizeof(T) == 2;
   constexpr uint32_t kNegInfWord = kHalf ? 0xff80u : 0xff800000u;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int Lp_max = 2 * S_max + 1;
-  float v = -CUDART_INF_F;
-  {
-    const int64_t* tg = targets + static_cast<size_t>(n) * S_max;
-    const size_t row0 = static_cast<size_t>(n) * T_len;
-    const int t_first = BWD ? Tn - 1 : 0;
-    const int dt = BWD ? -1 : 1;
-    const int st = tid;
-    const bool act = st < Lp;
-    int lab = blank;
-    bool skip_ok = false;  // may take the s-2 (alpha) / s+2 (beta) transition
-    if (act && (st & 1)) {
-      lab = static_cast<int>(tg[st >> 1]);
-      if (!BWD)
-        skip_ok = (st >= 2) && lab != static_cast<int>(tg[(st >> 1) - 1]);
+  const int64_t* tg = targets + static_cast<size_t>(n) * S_max;
+  const size_t row0 = static_cast<size_t>(n) * T_len;
+  const int t_first = BWD ? Tn - 1 : 0;
+  const int dt = BWD ? -1 : 1;
+  const int s0 = 2 * tid, s1 = s0 + 1;
+  const bool act0 = s0 < Lp, act1 = s1 < Lp;
+  int lab = blank;
+  bool skip_ok = false;  // the label state may take the s-2 (alpha) / s+2 (beta) transition
+  if (act1) {
+    lab = static_cast<int>(tg[tid]);
+    if (!BWD)
+      skip_ok = (tid >= 1) && lab != static_cast<int>(tg[tid - 1]);
+    else
+      skip_ok = (s1 + 2 < Lp) && lab != static_cast<int>(tg[tid + 1]);
+  }
+  const size_t rowe = (row0 + t_first) * static_cast<size_t>(ldx);
+  const char* pB = reinterpret_cast<const char*>(x) + (rowe + blank) * sizeof(T);
+  const char* pL = reinterpret_cast<const char*>(x) + (rowe + lab) * sizeof(T);
+  const ptrdiff_t src_step = static_cast<ptrdiff_t>(dt) * ldx * static_cast<ptrdiff_t>(sizeof(T));
+  const char* lseb = LSE ? reinterpret_cast<const char*>(lse + row0 + t_first) : nullptr;
+  const ptrdiff_t lse_step = static_cast<ptrdiff_t>(dt) * 4;
+  char* latb = reinterpret_cast<char*>(lat + (row0 + t_first) * Lp_max + (act0 ? s0 : 0));
+  const ptrdiff_t lat_step = static_cast<ptrdiff_t>(dt) * Lp_max * 4;
+  // the pipeline: alpha flows from warp w to w+1 (lane 31 -> lane 0), beta from w+1 to w (lane 0 -> lane 31)
+  const bool more_above = 64 * (warp + 1) < Lp;
+  const bool takes = BWD ? more_above : warp > 0;
+  const bool posts = BWD ? warp > 0 : more_above;
+  const bool is_edge = lane == (BWD ? 31 : 0);
+  const bool post_lane = posts && lane == (BWD ? 0 : 31);
+  uint32_t inbox = inbox0 + 8u * CTCW_SLOTS * warp;
+  uint32_t outbox = inbox0 + 8u * CTCW_SLOTS * (BWD ? warp - 1 : warp + 1);
+  keep_u32(inbox);
+  keep_u32(outbox);
+
+  uint32_t wB[CTC_RING], wL[CTC_RING];
+  float lr[CTC_RING];
+  auto fetch = [&](uint32_t& b, uint32_t& w, float& l) {  // the next frame not yet requested (idle states keep -inf)
+    if (act0) {
+      if constexpr (kHalf)
+        b = *reinterpret_cast<const unsigned short*>(pB);
       else
-        skip_ok = (st + 2 < Lp) && lab != static_cast<int>(tg[(st >> 1) + 1]);
+        b = *reinterpret_cast<const uint32_t*>(pB);
     }
-    const char* srcb = reinterpret_cast<const char*>(x) +
-                       ((row0 + t_first) * static_cast<size_t>(ldx) + lab) * sizeof(T);
-    const ptrdiff_t src_step = static_cast<ptrdiff_t>(dt) * ldx * static_cast<ptrdiff_t>(sizeof(T));
-    const char* lseb = LSE ? reinterpret_cast<const char*>(lse + row0 + t_first) : nullptr;
-    const ptrdiff_t lse_step = static_cast<ptrdiff_t>(dt) * 4;
-    char* latb = reinterpret_cast<char*>(lat + (row0 + t_first) * Lp_max + (act ? st : 0));
-    const ptrdiff_t lat_step = static_cast<ptrdiff_t>(dt) * Lp_max * 4;
-    // the pipeline: alpha flows from warp w to w+1 (edge lanes 31 -> 0), beta from w+1 to w (edge lanes 0 -> 31)
-    const bool more_above = 32 * (warp + 1) < Lp;
-    const bool takes = BWD ? more_above : warp > 0;
-    const bool posts = BWD ? warp > 0 : more_above;
-    const int edge = BWD ? 31 : 0;          // the lane next to the producer warp
-    const int edge2 = BWD ? 30 : 1;
-    const bool is_edge = lane == edge, is_edge2 = lane == edge2;
-    const bool post_lane = posts && lane == (BWD ? 0 : 31);
-    const uint32_t inbox = inbox0 + 8u * CTCW_SLOTS * warp;
-    const uint32_t outbox = inbox0 + 8u * CTCW_SLOTS * (BWD ? warp - 1 : warp + 1);
-
-    uint32_t wv[CTC_RING];
-    float lr[CTC_RING];
-    auto fetch = [&](uint32_t& w, float& l) {  // the next frame not yet requested (idle lanes keep their -inf)
-      if (act) {
-        if constexpr (kHalf)
-          w = *reinterpret_cast<const unsigned short*>(srcb);
-        else
-          w = *reinterpret_cast<const uint32_t*>(srcb);
-      }
-      if constexpr (LSE) l = *reinterpret_cast<const float*>(lseb);
-      srcb += src_step;
-      if constexpr (LSE) lseb += lse_step;
-    };
-    auto emission = [&](uint32_t w, float l) {
-      const float em = __uint_as_float(kHalf ? (w << 16) : w);
-      return LSE ? em - l : em;
-    };
-    auto neighbours = [&](float val, float& n1, float& n2) {
-      if (BWD) {
-        n1 = __shfl_down_sync(0xffffffffu, val, 1);
-        n2 = __shfl_down_sync(0xffffffffu, val, 2);
-        if (lane >= 31) n1 = -CUDART_INF_F;  // no producer above: states past the lattice
-        if (lane >= 30) n2 = -CUDART_INF_F;
-      } else {
-        n1 = __shfl_up_sync(0xffffffffu, val, 1);
-        n2 = __shfl_up_sync(0xffffffffu, val, 2);
-        if (lane < 1) n1 = -CUDART_INF_F;
-        if (lane < 2) n2 = -CUDART_INF_F;
-      }
-    };
+    if (act1) {
+      if constexpr (kHalf)
+        w = *reinterpret_cast<const unsigned short*>(pL);
+      else
+        w = *reinterpret_cast<const uint32_t*>(pL);
+    }
+    if constexpr (LSE) l = *reinterpret_cast<const float*>(lseb);
+    pB += src_step;
+    pL += src_step;
+    keep_ptr(pB);
+    keep_ptr(pL);
+    if constexpr (LSE) {
+      lseb += lse_step;
+      keep_ptr(lseb);
+    }
+  };
+  auto emission = [&](uint32_t w, float l) {
+    const float em = __uint_as_float(kHalf ? (w << 16) : w);
+    return LSE ? em - l : em;
+  };
+  // what the lane below (alpha) / above (beta) holds: alpha needs its label state, beta its blank and its label
+  float nb0 = -CUDART_INF_F, nb1 = -CUDART_INF_F;
+  auto neighbours = [&]() {
+    if (BWD) {
+      nb0 = __shfl_down_sync(0xffffffffu, v0, 1);
+      nb1 = __shfl_down_sync(0xffffffffu, v1, 1);
+    } else {
+      nb1 = __shfl_up_sync(0xffffffffu, v1, 1);
+    }
+  };
+  auto post = [&](uint32_t slot) {  // the edge lane's own pair: what the next warp's edge lane will want
+    if (post_lane) sts_v2_volatile(outbox + 8u * slot, __float_as_uint(v0), __float_as_uint(v1));
+  };
 
 #pragma unroll
-    for (int f = 0; f < CTC_RING; ++f) {
-      wv[f] = kNegInfWord;
-      lr[f] = 0.f;
-      if (f < Tn) fetch(wv[f], lr[f]);
+  for (int f = 0; f < CTC_RING; ++f) {
+    wB[f] = wL[f] = kNegInfWord;
+    lr[f] = 0.f;
+    if (f < Tn) fetch(wB[f], wL[f], lr[f]);
+  }
+  {  // frame 0
+    const bool start0 = act0 && (BWD ? s0 == Lp - 1 : s0 == 0);
+    const bool start1 = act1 && (BWD ? s1 == Lp - 2 : s1 == 1);
+    if (start0) v0 = emission(wB[0], lr[0]);
+    if (start1) v1 = emission(wL[0], lr[0]);
+    // the mailbox reads "empty" by value: keep an input's NaN payload from looking like it (only frame 0 can carry raw
+    // input bits; every later value is the result of an addition, and arithmetic returns the canonical NaN)
+    if (__float_as_uint(v0) == kCtcSentinel) v0 = __uint_as_float(0x7fffffffu);
+    if (__float_as_uint(v1) == kCtcSentinel) v1 = __uint_as_float(0x7fffffffu);
+    if (CTC_RING < Tn) fetch(wB[0], wL[0], lr[0]);
+    if (act0) *reinterpret_cast<float*>(latb) = v0;
+    if (act1) *reinterpret_cast<float*>(latb + 4) = v1;
+    neighbours();
+    post(0);
+  }
+  uint2 early = make_uint2(kCtcSentinel, kCtcSentinel);  // the producer's word for the coming frame, read a frame early
+  if (takes) early = lds_v2_volatile(inbox);
+  // frame f: `slot` = (f - 1) mod 16 holds the producer's frame f-1; the frame's own result goes to slot f mod 16
+  auto frame = [&](uint32_t& b, uint32_t& w, float& l, uint32_t slot, bool refill, bool more_frames) {
+    if (takes) {
+      uint2 m = early;
+      while (m.x == kCtcSentinel) m = lds_v2_volatile(inbox + 8u * slot);
+      if (is_edge) sts_v2_volatile(inbox + 8u * slot, kCtcSentinel, kCtcSentinel);  // slot free again
+      if (more_frames) early = lds_v2_volatile(inbox + 8u * ((slot + 1) & (CTCW_SLOTS - 1)));
+      if (BWD) nb0 = is_edge ? __uint_as_float(m.x) : nb0;
+      nb1 = is_edge ? __uint_as_float(m.y) : nb1;
+    } else {
+      if (BWD) nb0 = is_edge ? -CUDART_INF_F : nb0;
+      nb1 = is_edge ? -CUDART_INF_F : nb1;
     }
-    float n1, n2;
-    {  // frame 0
-      const bool start = act && (BWD ? (st == Lp - 1 || st == Lp - 2) : (st == 0 || st == 1));
-      if (start) v = emission(wv[0], lr[0]);
-      if (CTC_RING < Tn) fetch(wv[0], lr[0]);
-      if (act) *reinterpret_cast<float*>(latb) = v;
-      neighbours(v, n1, n2);
-      if (post_lane) sts_v2_volatile(outbox, __float_as_uint(v), __float_as_uint(n1));
+    const float eb = emission(b, l), el = emission(w, l);
+    float u0, u1;
+    if (BWD) {
+      // blank s0: stays or moves to the lane's own label s0+1; label s1: stays, s1+1 = next blank, s1+2 = next label
+      u0 = lse2_bf(v0, v1) + eb;
+      u1 = lse3_bf(v1, nb0, skip_ok ? nb1 : -CUDART_INF_F) + el;
+    } else {
+      // blank s0: from itself or the label below; label s1: from itself, the lane's own blank, the label below
+      u0 = lse2_bf(v0, nb1) + eb;
+      u1 = lse3_bf(v1, v0, skip_ok ? nb1 : -CUDART_INF_F) + el;
     }
-    uint2 early = make_uint2(kCtcSentinel, kCtcSentinel);  // the producer's word for the coming frame, read a frame early
-    if (takes) early = lds_v2_volatile(inbox);
-    // frame f: `slot` = (f - 1) mod 16 holds the producer's frame f-1; the frame's own result goes to slot f mod 16
-    auto frame = [&](uint32_t& w, float& l, uint32_t slot, bool refill, bool more_frames) {
-      if (takes) {
-        uint2 m = early;
-        while (m.x == kCtcSentinel) m = lds_v2_volatile(inbox + 8u * slot);
-        if (is_edge) sts_v2_volatile(inbox + 8u * slot, kCtcSentinel, kCtcSentinel);  // slot free again
-        if (more_frames) early = lds_v2_volatile(inbox + 8u * ((slot + 1) & (CTCW_SLOTS - 1)));
-        n1 = is_edge ? __uint_as_float(m.x) : n1;
-        n2 = is_edge ? __uint_as_float(m.y) : (is_edge2 ? __uint_as_float(m.x) : n2);
+    v0 = u0;
+    v1 = u1;
+    if (refill) fetch(b, w, l);
+    latb += lat_step;
+    keep_ptr(latb);
+    if (act0) *reinterpret_cast<float*>(latb) = v0;
+    if (act1) *reinterpret_cast<float*>(latb + 4) = v1;
+    neighbours();
+    post((slot + 1) & (CTCW_SLOTS - 1));
+  };
+  // a producer may run at most 16 frames ahead: before posting frames f .. f+7 it makes sure the slot of frame f+7 (last
+  // used by frame f-9) has been emptied -- the consumer empties slots in order
+  auto wait_room = [&](uint32_t slot_last) {
+    if (posts) {
+      while (lds_v2_volatile(outbox + 8u * slot_last).x != kCtcSentinel) {
       }
-      const float c2 = skip_ok ? n2 : -CUDART_INF_F;
-      v = lse3_bf(v, n1, c2) + emission(w, l);
-      if (refill) fetch(w, l);
-      latb += lat_step;
-      if (act) *reinterpret_cast<float*>(latb) = v;
-      neighbours(v, n1, n2);
-      if (post_lane) {
-        const uint32_t bits = __float_as_uint(v);
-        sts_v2_volatile(outbox + 8u * ((slot + 1) & (CTCW_SLOTS - 1)), bits == kCtcSentinel ? 0x7fffffffu : bits,
-                        __float_as_uint(n1));
-      }
-    };
-    // a producer may run at most 16 frames ahead: before posting frames f .. f+7 it makes sure the slot of frame f+7 (last
-    // used by frame f-9) has been emptied -- the consumer empties slots in order
-    auto wait_room = [&](uint32_t slot_last) {
-      if (posts) {
-        while (lds_v2_volatile(outbox + 8u * slot_last).x != kCtcSentinel) {
-        }
-      }
-    };
-    int step = 1;
-    // steady state, 16 frames per trip (slot numbers and ring registers are immediates); all refills exist
+    }
+  };
+  int step = 1;
+  // steady state, 16 frames per trip (slot numbers and ring registers are immediates); all refills exist
 #pragma unroll 1
-    for (; step + 16 + CTC_RING <= Tn; step += 16) {
+  for (; step + 16 + CTC_RING <= Tn; step += 16) {
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
+    for (int u = 0; u < 16; ++u) {
+      if ((u & 7) == 0) wait_room((u + 1 + 7) & (CTCW_SLOTS - 1));
+      constexpr int R = CTC_RING - 1;
+      frame(wB[(1 + u) & R], wL[(1 + u) & R], lr[(1 + u) & R], u, true, true);
+    }
+  }
+#pragma unroll 1
+  for (; step < Tn; step += 16) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      if (step + u < Tn) {
         if ((u & 7) == 0) wait_room((u + 1 + 7) & (CTCW_SLOTS - 1));
-        frame(wv[(1 + u) & (CTC_RING - 1)], lr[(1 + u) & (CTC_RING - 1)], u, true, true);
-      }
-    }
-#pragma unroll 1
-    for (; step < Tn; step += 16) {
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        if (step + u < Tn) {
-          if ((u & 7) == 0) wait_room((u + 1 + 7) & (CTCW_SLOTS - 1));
-          frame(wv[(1 + u) & (CTC_RING - 1)], lr[(1 + u) & (CTC_RING - 1)], u, step + u + CTC_RING < Tn,
-                step + u + 1 < Tn);
-        }
+        constexpr int R = CTC_RING - 1;
+        frame(wB[(1 + u) & R], wL[(1 + u) & R], lr[(1 + u) & R], u, step + u + CTC_RING < Tn, step + u + 1 < Tn);
       }
     }
   }
-  return v;
 }
 
-template <typename T, bool LSE>
-__global__ void __launch_bounds__(1024)
-ctc_lattice_warp_kernel(const T* __restrict__ x, const float* __restrict__ lse, const int64_t* __restrict__ targets,
-                        const int32_t* __restrict__ in_len, const int32_t* __restrict__ tgt_len,
-                        float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll, int T_len, int ldx,
-                        int S_max, int blank) {
+template <typename T, bool LSE, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+ctc_lattice_warp2_kernel(const T* __restrict__ x, const float* __restrict__ lse, const int64_t* __restrict__ targets,
+                         const int32_t* __restrict__ in_len, const int32_t* __restrict__ tgt_len,
+                         float* __restrict__ alpha, float* __restrict__ beta, float* __restrict__ nll, int T_len, int ldx,
+                         int S_max, int blank) {
   pdl_launch_dependents();
   extern __shared__ float sm[];
   const int tid = threadIdx.x, nthreads = blockDim.x;
   const int warp = tid >> 5, nwarps = nthreads >> 5;
   const int n = blockIdx.x;
   const bool backward = blockIdx.y == 1;
-  // sm: inbox [nwarps][CTCW_SLOTS] 8-byte words, last column [nthreads]
+  // sm: inbox [nwarps][CTCW_SLOTS] 8-byte words, last column [2 * nthreads]
   const uint32_t inbox0 = smem_u32(sm);
   const uint32_t fin = inbox0 + 8u * CTCW_SLOTS * nwarps;
   for (int i = tid; i < 2 * CTCW_SLOTS * nwarps; i += nthreads) sts_u32(inbox0 + 4u * i, kCtcSentinel);
@@ -508,20 +565,23 @@ ctc_lattice_warp_kernel(const T* __restrict__ x, const float* __restrict__ lse, 
     if (!backward && tid == 0) nll[n] = (Tn == 0 && Sn == 0) ? 0.f : CUDART_INF_F;
     return;
   }
-  float v = -CUDART_INF_F;
-  if (32 * warp < Lp) {
+  float v0 = -CUDART_INF_F, v1 = -CUDART_INF_F;
+  if (64 * warp < Lp) {
     if (backward)
-      v = ctc_warp_lattice<T, LSE, true>(x, lse, targets, beta, n, Tn, Lp, T_len, ldx, S_max, blank, inbox0);
+      ctc_warp2_lattice<T, LSE, true>(x, lse, targets, beta, n, Tn, Lp, T_len, ldx, S_max, blank, inbox0, v0, v1);
     else
-      v = ctc_warp_lattice<T, LSE, false>(x, lse, targets, alpha, n, Tn, Lp, T_len, ldx, S_max, blank, inbox0);
+      ctc_warp2_lattice<T, LSE, false>(x, lse, targets, alpha, n, Tn, Lp, T_len, ldx, S_max, blank, inbox0, v0, v1);
   }
-  sts_f32(fin + 4u * tid, v);
-  __syncthreads();
-  if (!backward && tid == 0) {
-    const float a = lds_f32(fin + 4u * (Lp - 1));
-    const float b = Lp >= 2 ? lds_f32(fin + 4u * (Lp - 2)) : -CUDART_INF_F;
-    const float m = fmaxf(a, b);
-    nll[n] = (m == -CUDART_INF_F) ? CUDART_INF_F : -(m + logf(expf(a - m) + expf(b - m)));
+  if (!backward) {
+    sts_f32(fin + 8u * tid, v0);
+    sts_f32(fin + 8u * tid + 4u, v1);
+    __syncthreads();
+    if (tid == 0) {
+      const float a = lds_f32(fin + 4u * (Lp - 1));
+      const float b = Lp >= 2 ? lds_f32(fin + 4u * (Lp - 2)) : -CUDART_INF_F;
+      const float m = fmaxf(a, b);
+      nll[n] = (m == -CUDART_INF_F) ? CUDART_INF_F : -(m + logf(expf(a - m) + expf(b - m)));
+    }
   }
 }
 
@@ -1028,28 +1088,35 @@ static int ctc_lattice_launch(const void* x, const float* lse, const int64_t* ta
   return LASR_OK;
 }
 
-// LASR_CTC_WARP=0 selects the round-1 barrier kernel (A/B runs, the bit-identity test); lattices wider than 1024 states
-// always take it
+// LASR_CTC_WARP=0 selects the round-1 barrier kernel (A/B runs, the bit-identity test)
+template <typename T, bool LSE>
+static int ctc_warp_launch(const void* x, const float* lse, const int64_t* targets, const int32_t* il, const int32_t* tl,
+                           float* alpha, float* beta, float* nll, int N, int T_len, int ldx, int S_max, int blank,
+                           cudaStream_t stream) {
+  const int Lp_max = 2 * S_max + 1;
+  const dim3 grid(N, beta != nullptr ? 2 : 1);
+  const T* xx = static_cast<const T*>(x);
+  const int threads = cdiv(Lp_max, 64) * 32;
+  if (threads > 1024) return LASR_ERR_UNSUPPORTED;
+  const size_t smem = 8u * CTCW_SLOTS * (threads / 32) + 8u * threads;
+  if (threads <= 512)
+    LASR_CHECK_PDL(launch_pdl(8, ctc_lattice_warp2_kernel<T, LSE, 512>, grid, dim3(threads), smem, stream, xx, lse,
+                              targets, il, tl, alpha, beta, nll, T_len, ldx, S_max, blank));
+  else
+    LASR_CHECK_PDL(launch_pdl(8, ctc_lattice_warp2_kernel<T, LSE, 1024>, grid, dim3(threads), smem, stream, xx, lse,
+                              targets, il, tl, alpha, beta, nll, T_len, ldx, S_max, blank));
+  return LASR_OK;
+}
+
 template <typename T>
 static int ctc_warp_dispatch(const void* x, const float* lse, const int64_t* targets, const int32_t* il,
                              const int32_t* tl, float* alpha, float* beta, float* nll, int N, int T_len, int ldx,
                              int S_max, int blank, cudaStream_t stream) {
-  const int Lp_max = 2 * S_max + 1;
   const char* env = getenv("LASR_CTC_WARP");
   if (env != nullptr && atoi(env) == 0) return LASR_ERR_UNSUPPORTED;
-  const int threads = cdiv(Lp_max, 32) * 32;
-  if (threads > 1024) return LASR_ERR_UNSUPPORTED;
-  const size_t smem = 8u * CTCW_SLOTS * (threads / 32) + 4u * threads;
-  const dim3 grid(N, beta != nullptr ? 2 : 1);
   if (lse != nullptr)
-    LASR_CHECK_PDL(launch_pdl(8, ctc_lattice_warp_kernel<T, true>, grid, dim3(threads), smem, stream,
-                              static_cast<const T*>(x), lse, targets, il, tl, alpha, beta, nll, T_len, ldx, S_max,
-                              blank));
-  else
-    LASR_CHECK_PDL(launch_pdl(8, ctc_lattice_warp_kernel<T, false>, grid, dim3(threads), smem, stream,
-                              static_cast<const T*>(x), lse, targets, il, tl, alpha, beta, nll, T_len, ldx, S_max,
-                              blank));
-  return LASR_OK;
+    return ctc_warp_launch<T, true>(x, lse, targets, il, tl, alpha, beta, nll, N, T_len, ldx, S_max, blank, stream);
+  return ctc_warp_launch<T, false>(x, lse, targets, il, tl, alpha, beta, nll, N, T_len, ldx, S_max, blank, stream);
 }
 
 template <typename T>

@@ -170,9 +170,10 @@ def bench_ctc():
     report("ctc_fwd (alpha+beta lattices)", timeit(lambda: ops.ctc_fwd(logits, lse, targets, il, tl, V, 28, want_beta=True)),
            8 * M * (2 * S + 1), 0)
     import os
-    os.environ["LASR_CTC_WARP"] = "0"
-    report("ctc_fwd round-1 barrier kernel (LASR_CTC_WARP=0)",
-           timeit(lambda: ops.ctc_fwd(logits, lse, targets, il, tl, V, 28, want_beta=True)), 8 * M * (2 * S + 1), 0)
+    for mode, what in (("0", "round-1 barrier kernel"), ("1", "warp pipeline, state pair per lane")):
+        os.environ["LASR_CTC_WARP"] = mode
+        report(f"ctc_fwd LASR_CTC_WARP={mode} {what}",
+               timeit(lambda: ops.ctc_fwd(logits, lse, targets, il, tl, V, 28, want_beta=True)), 8 * M * (2 * S + 1), 0)
     os.environ.pop("LASR_CTC_WARP")
     go = torch.full((N,), 1.0 / N, device=dev)
     report("ctc_bwd (fused softmax grad)", timeit(lambda: ops.ctc_bwd(logits, lse, targets, il, tl, alpha, beta, nll, go, V, 28, ld, torch.bfloat16, scales=scales)),
