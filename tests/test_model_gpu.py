@@ -419,7 +419,9 @@ def test_train_engine_from_waveforms_matches_oracle(lasr, labels28):
     mod2.encoder.load_state_dict(sd0)
     try:
         eng2 = TrainEngine(mod2, batch, graph=True, optimizer=None)
-        assert eng2.h2d_bytes == waves.numel() * 2 + targets.numel() * 8 + 3 * 4 + 3 * 4
+        # 16-bit samples on the wire: the batch crosses PCIe as ONE flat buffer (tensors at 256-byte boundaries)
+        payload = waves.numel() * 2 + targets.numel() * 8 + 3 * 4 + 3 * 4
+        assert payload <= eng2.h2d_bytes < payload + 4 * 256
         loss_q = eng2.step_host()
     finally:
         runtime.uninstall()
