@@ -844,6 +844,18 @@ constexpr int RING_U = 2;  // rows per trip and thread
 __device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
 }
+// L2 eviction hints: a stream that nobody reads again after this pass should not push the tensors the NEXT kernel needs
+// out of the 126 MB L2 (the backward apply pass reads dout, y, r for the last time and writes dy, dr for the two GEMMs
+// that follow)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void cp_async_16_hint(uint32_t smem_addr, const void* gsrc, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gsrc), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() {
@@ -866,7 +878,7 @@ bn_bwd_apply_ring_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bflo
                          const float* __restrict__ coef1_in, const BnBwdSide bn1, const BnBwdSide bn2, double count,
                          const int32_t* __restrict__ lengths, int T_len, __nv_bfloat16* __restrict__ dy,
                          __nv_bfloat16* __restrict__ dr, long long total_vec, int CV, int C,
-                         const uint8_t* __restrict__ relu_bits) {
+                         const uint8_t* __restrict__ relu_bits, int dead_hint) {
   using T = __nv_bfloat16;
   pdl_launch_dependents();
   pdl_wait();  // totals come from the reduce pass right before
@@ -940,6 +952,7 @@ bn_bwd_apply_ring_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bflo
   // per-stage bookkeeping in registers (the loop below is unrolled over the ring: compile-time indices)
   uint32_t ob[RING_D][RING_U];
   int len_n[RING_D][RING_U], t_of[RING_D][RING_U];
+  const uint64_t dead = l2_policy_evict_first();
   auto issue = [&](int trip, int st) {
 #pragma unroll
     for (int u = 0; u < RING_U; ++u) {
@@ -948,9 +961,15 @@ bn_bwd_apply_ring_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bflo
         const long long v = static_cast<long long>(row) * CV + cv;
         const int n = row / T_len;
         const int t = row - n * T_len;
-        cp_async_16(slot(st, u, 0), dout + v * 8);
-        cp_async_16(slot(st, u, 1), y + v * 8);  // also for padded frames: `keep` is only known when the length lands
-        if constexpr (HAS_R) cp_async_16(slot(st, u, 2), r + v * 8);
+        if (dead_hint) {
+          cp_async_16_hint(slot(st, u, 0), dout + v * 8, dead);
+          cp_async_16_hint(slot(st, u, 1), y + v * 8, dead);  // (also for padded frames: `keep` is known later)
+          if constexpr (HAS_R) cp_async_16_hint(slot(st, u, 2), r + v * 8, dead);
+        } else {
+          cp_async_16(slot(st, u, 0), dout + v * 8);
+          cp_async_16(slot(st, u, 1), y + v * 8);
+          if constexpr (HAS_R) cp_async_16(slot(st, u, 2), r + v * 8);
+        }
         ob[st][u] = relu_bits != nullptr ? relu_bits[relu_bits_index(n, t, cv, Tb, CV)] : 0xffu;
         len_n[st][u] = lengths != nullptr ? lengths[n] : T_len;
         t_of[st][u] = t;
@@ -1076,6 +1095,7 @@ static int bn_bwd_launch(const void* dout, const void* out, const void* y, const
     if (bn_ring_enabled() && gate == nullptr && drop_mask == nullptr && relu_ok && totals != nullptr && threads <= 256 &&
         ring_smem <= 113 * 1024) {
       const uint8_t* bits = act == LASR_ACT_RELU ? relu_bits : nullptr;
+      static const int hint = getenv("LASR_L2_HINTS") != nullptr ? atoi(getenv("LASR_L2_HINTS")) : 1;
       static bool configured = false;
       if (!configured) {
         cudaFuncSetAttribute(bn_bwd_apply_ring_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);
@@ -1084,10 +1104,10 @@ static int bn_bwd_launch(const void* dout, const void* out, const void* y, const
       }
       if (r != nullptr)
         le = launch_pdl(4, bn_bwd_apply_ring_kernel<true>, dim3(grid), dim3(threads), ring_smem, stream, a0, a2, a3, totals,
-                        coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, bits);
+                        coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, bits, hint);
       else
         le = launch_pdl(4, bn_bwd_apply_ring_kernel<false>, dim3(grid), dim3(threads), ring_smem, stream, a0, a2, a3,
-                        totals, coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, bits);
+                        totals, coef1, s1, s2, count, lengths, T, o0, o1, total, CV, C, bits, hint);
       LASR_CHECK_PDL(le);
       return LASR_OK;
     }

@@ -236,6 +236,24 @@ def test_infer_engine_matches_module_eval_path():
     assert got == ref
     assert [len(s) for s in got] == [int(c) for c in cnts]
     assert sum(len(s) for s in got) > 0
+    eng.close()
+    # 16-bit PCM on the wire (a quarter of the H2D bytes): the same tokens as fp32 samples holding the quantised values,
+    # through prefetch() with a float batch (converted once on the host) and with an int16 batch
+    wq = frontend.pcm16(waves)
+    eng_f = InferEngine(module, wq.float() / 32768.0, lens, graph=True)
+    toks_f, cnts_f = (t.clone() for t in eng_f.step_host())
+    eng_f.close()
+    eng_q = InferEngine(module, waves, lens, graph=True, wave_dtype=torch.int16)
+    assert eng_q.h2d_bytes == waves.numel() * 2 and eng_q.static.dtype == torch.int16
+    toks_q, cnts_q = (t.clone() for t in eng_q.step_host())
+    def same(ta, ca, tb, cb):
+        return torch.equal(ca, cb) and all(torch.equal(ta[i, :int(ca[i])], tb[i, :int(cb[i])]) for i in range(len(ca)))
+
+    assert same(toks_q, cnts_q, toks_f, cnts_f)
+    eng_q.prefetch(wq)
+    toks_q2, cnts_q2 = eng_q.step_host()
+    assert same(toks_q2, cnts_q2, toks_f, cnts_f)
+    eng_q.close()
 
 
 @pytest.mark.parametrize("variant", ["base", "context"])
