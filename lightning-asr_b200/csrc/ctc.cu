@@ -668,6 +668,91 @@ ctc_grad_kernel(const T* __restrict__ x, const float* __restrict__ lse, const in
 }
 
 
+// The same pass for small vocabularies (V <= 128: the character models), 8 frames of ONE utterance per CTA: the labels
+// are read once per CTA into shared memory as int32 (the kernel above re-reads the int64 targets from global memory for
+// every frame row), the row's log-probs once per warp, so a lattice state costs two coalesced global loads (alpha, beta),
+// two shared-memory reads and one exponential; four states per lane are requested before the first is used.  Same
+// arithmetic in the same order per row: bit-identical gradients.
+template <typename T, typename GT>
+__global__ void __launch_bounds__(256)
+ctc_grad_small_kernel(const T* __restrict__ x, const float* __restrict__ lse, const int64_t* __restrict__ targets,
+                      const int32_t* __restrict__ in_len, const int32_t* __restrict__ tgt_len,
+                      const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ nll,
+                      const float* __restrict__ grad_out, GT* __restrict__ grad, int T_len, int V, int ldx, int ldg,
+                      int S_max, int blank, int S_pad, int Vp) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float gsm[];  // labels [S_pad] int32, then per warp: lp [Vp], occ [Vp]
+  int* labels = reinterpret_cast<int*>(gsm);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* lpw = gsm + S_pad + static_cast<size_t>(w) * 2 * Vp;
+  float* occ = lpw + Vp;
+  const int n = blockIdx.y;
+  const int t = blockIdx.x * 8 + w;
+  const int Tn = in_len[n];
+  const int Sn = tgt_len[n];
+  const bool built = !(Sn < 0 || Sn > S_max);  // bad lengths: the lattice kernel left alpha / beta unwritten
+  const int64_t* tg = targets + static_cast<size_t>(n) * S_max;
+  if (built)
+    for (int i = threadIdx.x; i < Sn; i += 256) labels[i] = static_cast<int>(tg[i]);
+  __syncthreads();
+  if (t >= T_len) return;
+  const size_t row = static_cast<size_t>(n) * T_len + t;
+  GT* gr = grad + row * ldg;
+  if (t >= Tn || !built) {  // frames past the utterance get a zero gradient row
+    for (int c = lane; c < ldg; c += 32) gr[c] = from_f32<GT>(0.f);
+    return;
+  }
+  const int Lp = 2 * Sn + 1;
+  const int Lp_max = 2 * S_max + 1;
+  const T* xr = x + row * ldx;
+  const float l = lse ? lse[row] : 0.f;
+  const float nl = nll[n];
+  const float go = grad_out[n];
+  for (int c = lane; c < V; c += 32) {
+    lpw[c] = to_f32<T>(xr[c]) - l;
+    occ[c] = 0.f;
+  }
+  __syncwarp();
+  const float* ar = alpha + row * Lp_max;
+  const float* br = beta + row * Lp_max;
+  float bsum = 0.f;
+  for (int s0 = lane; s0 < Lp; s0 += 128) {
+    float a[4], b[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int st = s0 + 32 * k;
+      a[k] = b[k] = 0.f;
+      if (st < Lp) {
+        a[k] = ar[st];
+        b[k] = br[st];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int st = s0 + 32 * k;
+      if (st < Lp) {
+        const int label = (st & 1) ? labels[st >> 1] : blank;
+        const float v = expf(a[k] + b[k] + nl - lpw[label]);
+        if (st & 1)
+          atomicAdd(&occ[label], v);
+        else
+          bsum += v;
+      }
+    }
+  }
+  bsum = warp_sum(bsum);
+  __syncwarp();
+  if (lane == 0) occ[blank] += bsum;
+  __syncwarp();
+  for (int c = lane; c < ldg; c += 32) {
+    float g = 0.f;
+    if (c < V) g = (expf(lpw[c]) - occ[c]) * go;
+    gr[c] = from_f32<GT>(g);
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------------
 // CTC lattices, second generation: linear-domain ("scaled") forward-backward, 8 warps per (utterance, direction).
 //
@@ -1003,6 +1088,16 @@ static int ctc_grad_launch(const void* x, const float* lse, const int64_t* targe
                            const int32_t* tl, const float* alpha, const float* beta, const float* nll,
                            const int32_t* scales, const float* grad_out, void* grad, int N, int Tn, int V, int ldx,
                            int ldg, int S_max, int blank, cudaStream_t stream) {
+  if (scales == nullptr && V <= 128 && !(getenv("LASR_CTC_GRAD_SMALL") != nullptr && atoi(getenv("LASR_CTC_GRAD_SMALL")) == 0)) {
+    const int S_pad = (S_max + 3) / 4 * 4, Vp = (V + 31) / 32 * 32;
+    const int smem_small = (S_pad + 8 * 2 * Vp) * static_cast<int>(sizeof(float));
+    if (smem_small <= 48 * 1024) {
+      LASR_CHECK_PDL(launch_pdl(8, ctc_grad_small_kernel<T, GT>, dim3(cdiv(Tn, 8), N), dim3(256), smem_small, stream,
+                                static_cast<const T*>(x), lse, targets, il, tl, alpha, beta, nll, grad_out,
+                                static_cast<GT*>(grad), Tn, V, ldx, ldg, S_max, blank, S_pad, Vp));
+      return LASR_OK;
+    }
+  }
   int warps = (96 * 1024) / (V * 4);
   if (warps > 8) warps = 8;
   if (warps < 1) warps = 1;

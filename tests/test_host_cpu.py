@@ -214,3 +214,37 @@ def test_series_layout_helpers_hold_their_invariants():
     for g in range(64):
         gs = g ^ ((g >> 3) & 1)
         assert (gs ^ ((gs >> 3) & 1)) == g and gs // 2 == g // 2
+
+
+def test_flat_batch_views_alias_one_buffer():
+    """TrainEngine stages a batch as ONE flat buffer (one H2D copy per step): every tensor of the batch is a view at a
+    256-byte boundary with its own dtype and shape, writes through a view land in the flat buffer, non-tensor entries
+    pass through, and the wire formats keep their widths (16-bit PCM stays 2 bytes per sample)."""
+    from lightning_asr_b200.trainer import _flat_views
+
+    waves = torch.randint(-32768, 32767, (3, 1001), dtype=torch.int16)
+    targets = torch.randint(0, 28, (3, 7))
+    lens = torch.tensor([1001, 900, 77], dtype=torch.int32)
+    tsz = torch.tensor([7, 5, 1], dtype=torch.int32)
+    flat, views = _flat_views([waves, targets, None, lens, tsz], "cpu")
+    assert flat.dtype == torch.uint8 and views[2] is None
+    payload = waves.numel() * 2 + targets.numel() * 8 + 3 * 4 + 3 * 4
+    assert payload <= flat.numel() < payload + 4 * 256
+    base = flat.data_ptr()
+    last_end = 0
+    for v, t in zip(views, [waves, targets, None, lens, tsz]):
+        if t is None:
+            continue
+        assert v.dtype == t.dtype and v.shape == t.shape and v.is_contiguous()
+        off = v.data_ptr() - base
+        assert off % 256 == 0 and off >= last_end
+        last_end = off + v.numel() * v.element_size()
+        v.copy_(t)
+    assert last_end <= flat.numel()
+    # the views alias the flat buffer: a byte-level copy of it carries the whole batch
+    clone = flat.clone()
+    off_t = views[1].data_ptr() - base
+    again = clone[off_t:off_t + targets.numel() * 8].view(torch.int64).view(targets.shape)
+    assert torch.equal(again, targets)
+    off_w = views[0].data_ptr() - base
+    assert torch.equal(clone[off_w:off_w + waves.numel() * 2].view(torch.int16).view(waves.shape), waves)

@@ -322,3 +322,43 @@ def test_ctc_warp_pipelined_lattices_are_bit_identical(ops, N, T, S, dtype, use_
             assert torch.equal(a[n, :Tn, :Lp], a0[n, :Tn, :Lp]), (mode, n)
             assert torch.equal(b[n, :Tn, :Lp], b0[n, :Tn, :Lp]), (mode, n)
             assert torch.equal(g[n], g0[n]), (mode, n)
+
+
+@pytest.mark.parametrize("N,T,S,dtype,gdtype", [(5, 120, 30, torch.float32, torch.float32),
+                                                (8, 801, 200, torch.bfloat16, torch.bfloat16),
+                                                (3, 257, 100, torch.bfloat16, torch.float32)])
+def test_ctc_gradient_pass_for_small_vocabularies_is_bit_identical(ops, N, T, S, dtype, gdtype):
+    """ctc_grad_small_kernel (8 frames of one utterance per CTA, labels and the row's log-probs in shared memory) against
+    the general gradient pass on the same lattices: same bits, incl. zero rows past an utterance's end and for an
+    infeasible utterance."""
+    import os
+    torch.manual_seed(N + T + S)
+    V, ld = 29, 32
+    logits = (torch.randn(N, T, ld, device="cuda") * 2).to(dtype)
+    targets = torch.randint(0, V - 1, (N, S), device="cuda")
+    il = torch.full((N,), T, device="cuda", dtype=torch.int32)
+    tl = torch.full((N,), min(S, T // 2), device="cuda", dtype=torch.int32)
+    il[1] = T - 37
+    tl[1] = 3
+    tl[2] = 0
+    if N > 4:
+        il[4] = 2
+    lse, _ = ops.log_softmax_fwd(logits, V, want_lp=False)
+    gout = torch.rand(N, device="cuda") + 0.5
+    nll, alpha, beta, scales = ops.ctc_fwd(logits, lse, targets, il, tl, V, V - 1, want_beta=True)
+    old = os.environ.get("LASR_CTC_GRAD_SMALL")
+    grads = {}
+    try:
+        for mode in ("0", "1"):
+            os.environ["LASR_CTC_GRAD_SMALL"] = mode
+            grads[mode] = ops.ctc_bwd(logits, lse, targets, il, tl, alpha, beta, nll, gout, V, V - 1, ld, gdtype,
+                                      scales=scales).clone()
+            torch.cuda.synchronize()
+    finally:
+        if old is None:
+            os.environ.pop("LASR_CTC_GRAD_SMALL", None)
+        else:
+            os.environ["LASR_CTC_GRAD_SMALL"] = old
+    feasible = torch.isfinite(nll)
+    assert torch.equal(grads["0"][feasible], grads["1"][feasible])
+    assert grads["1"][1, T - 37:].abs().max().item() == 0

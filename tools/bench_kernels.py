@@ -176,6 +176,11 @@ def bench_ctc():
                timeit(lambda: ops.ctc_fwd(logits, lse, targets, il, tl, V, 28, want_beta=True)), 8 * M * (2 * S + 1), 0)
     os.environ.pop("LASR_CTC_WARP")
     go = torch.full((N,), 1.0 / N, device=dev)
+    for mode in ("0", "1"):
+        os.environ["LASR_CTC_GRAD_SMALL"] = mode
+        report(f"ctc_bwd LASR_CTC_GRAD_SMALL={mode}", timeit(lambda: ops.ctc_bwd(logits, lse, targets, il, tl, alpha, beta, nll, go, V, 28, ld, torch.bfloat16, scales=scales)),
+               8 * M * (2 * S + 1) + 4 * M * ld, 0)
+    os.environ.pop("LASR_CTC_GRAD_SMALL")
     report("ctc_bwd (fused softmax grad)", timeit(lambda: ops.ctc_bwd(logits, lse, targets, il, tl, alpha, beta, nll, go, V, 28, ld, torch.bfloat16, scales=scales)),
            8 * M * (2 * S + 1) + 4 * M * ld, 0)
 
