@@ -266,13 +266,14 @@ def test_ctc_long_lattices_keep_the_mass_near_the_diagonal(ops, N, T, S, scale, 
 @pytest.mark.parametrize("N,T,S,dtype", [(5, 120, 30, torch.float32), (32, 801, 200, torch.bfloat16),
                                          (16, 401, 100, torch.bfloat16), (3, 257, 300, torch.float32),
                                          (2, 64, 1, torch.bfloat16), (4, 40, 15, torch.float32),
-                                         (3, 500, 511, torch.bfloat16)])
+                                         (3, 500, 511, torch.bfloat16), (2, 1300, 600, torch.bfloat16)])
 @pytest.mark.parametrize("use_lse", [True, False])
 def test_ctc_warp_pipelined_lattices_are_bit_identical(ops, N, T, S, dtype, use_lse):
     """The default lattice kernel (csrc/ctc.cu ctc_lattice_warp2_kernel: a state pair per lane in registers, neighbours by
     warp shuffle, warp-boundary states through a shared-memory mailbox, no CTA barrier per frame) runs the arithmetic of
     the round-1 barrier kernel: alpha, beta, nll and the gradient must not differ in a single bit -- ragged lengths,
-    lattices of 1 to 16 warps, empty / one-label / infeasible targets, log-prob and logit + lse inputs."""
+    lattices of 1 to 19 warps (both launch-bound variants), empty / one-label / infeasible targets, log-prob and
+    logit + lse inputs."""
     import os
     torch.manual_seed(N * T + S)
     V, ld = 29, 32
