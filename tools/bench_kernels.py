@@ -185,6 +185,28 @@ def bench_ctc():
            8 * M * (2 * S + 1) + 4 * M * ld, 0)
 
 
+def bench_ctc_aishell():
+    """config 4: the 4334-class decoder -- CTC gradient pass and the decoder-bias column sum"""
+    import os
+    V, ld = 4334, 4336
+    S = T // 4
+    logits = torch.randn(N, T, ld, device=dev).bfloat16()
+    targets = torch.randint(0, V - 1, (N, S), device=dev)
+    il = torch.full((N,), T, device=dev, dtype=torch.int32)
+    tl = torch.full((N,), S, device=dev, dtype=torch.int32)
+    lse, _ = ops.log_softmax_fwd(logits, V, want_lp=False)
+    nll, alpha, beta, scales = ops.ctc_fwd(logits, lse, targets, il, tl, V, V - 1, want_beta=True)
+    go = torch.full((N,), 1.0 / N, device=dev)
+    for mode in ("0", "1"):
+        os.environ["LASR_CTC_GRAD_LARGE"] = mode
+        report(f"ctc_bwd V=4334 LASR_CTC_GRAD_LARGE={mode}",
+               timeit(lambda: ops.ctc_bwd(logits, lse, targets, il, tl, alpha, beta, nll, go, V, V - 1, ld, torch.bfloat16, scales=scales)),
+               8 * M * (2 * S + 1) + 4 * M * ld, 0)
+    os.environ.pop("LASR_CTC_GRAD_LARGE")
+    out = torch.zeros(V, device=dev)
+    report("colsum [M, 4336] bf16 (decoder bias gradient)", timeit(lambda: ops.colsum(logits.view(M, ld), V, out=out)), 2 * M * ld, 0)
+
+
 def bench_frontend():
     from lightning_asr_b200 import frontend
 
@@ -198,6 +220,6 @@ def bench_frontend():
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
-for name, fn in [("calib", bench_calib), ("gemm", bench_gemm), ("dw", bench_dw), ("dwcm", bench_dwcm), ("bn", bench_bn), ("ctc", bench_ctc), ("frontend", bench_frontend)]:
+for name, fn in [("calib", bench_calib), ("gemm", bench_gemm), ("dw", bench_dw), ("dwcm", bench_dwcm), ("bn", bench_bn), ("ctc", bench_ctc), ("aishell", bench_ctc_aishell), ("frontend", bench_frontend)]:
     if which in ("all", name):
         fn()
