@@ -17,6 +17,8 @@
 //     reduce dh_prev[k] = sum_j W_hh[j, k] dgate_j with two shuffles.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace lasr {
 
 constexpr int LS_H = 40;          // hidden units per direction
@@ -213,6 +215,189 @@ bilstm_bwd_kernel(const T_* __restrict__ dout, const T_* __restrict__ out, const
   for (int t = len; t < T; ++t) dpre[(static_cast<size_t>(n) * T + t) * (2 * LS_G) + d * LS_G + j] = from_f32<T_>(0.f);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Second generation (round 2): ONE barrier per frame.  The kernels above are paced by two CTA barriers per frame and, in
+// the backward, by a phase that only 40 of the 160 threads execute (the tanh / gate-gradient chain) while the others
+// wait: 0.54 / 1.05 us per frame.  Here thread j = 4 u + q owns gate q of unit u, so the four gates of a unit sit in
+// four adjacent lanes:
+//   forward   every thread computes its gate's pre-activation (the same 40-term dot product in the same order), the
+//             quad exchanges the four activations with shuffles and all four lanes update the unit's cell state
+//             redundantly (no g_s round trip, no second barrier); lane q = 0 publishes h for the next frame;
+//   backward  all four lanes of a quad run the unit's gate-gradient chain redundantly and keep their own gate's
+//             gradient; after the frame's one barrier every thread adds its row's outer-product term to dW_hh and the
+//             regrouped reduction of dh_prev (thread = (unit k, gate q), two xor-shuffles) leaves dh_prev[k] in all
+//             four lanes of unit k's quad -- exactly where the next frame's chain needs it, in registers.
+// The exchange buffers are double-buffered, which is what makes one barrier enough.  Same operations in the same order
+// per value: outputs, saved gates / cells and all gradients are bit-identical to the kernels above
+// (tests/test_kernels_gpu.py::test_bilstm_one_barrier_kernels_are_bit_identical); LASR_LSTM_V1=1 selects those.
+// ------------------------------------------------------------------------------------------------
+template <typename T_>
+__global__ void __launch_bounds__(LS_G)
+bilstm_fwd2_kernel(const T_* __restrict__ pre, const float* __restrict__ whh, const int32_t* __restrict__ lengths,
+                   T_* __restrict__ out, float4* __restrict__ gates, float* __restrict__ cells, int T) {
+  const int n = blockIdx.x, d = blockIdx.y, j = threadIdx.x;
+  const int u = j >> 2, q = j & 3;
+  const int row_j = q * LS_H + u;  // this thread's gate row in PyTorch's (i, f, g, o) order
+  __shared__ __align__(16) float h_s[2][LS_H];
+  float w[LS_H];
+#pragma unroll
+  for (int k = 0; k < LS_H; ++k) w[k] = whh[(static_cast<size_t>(d) * LS_G + row_j) * LS_H + k];
+  int len = lengths != nullptr ? lengths[n] : T;
+  len = max(0, min(len, T));
+  if (j < LS_H) h_s[0][j] = 0.f;
+  float c = 0.f;
+  const T_* pre_n = pre + static_cast<size_t>(n) * T * (2 * LS_G) + d * LS_G + row_j;
+  auto frame = [&](int s) { return d == 0 ? s : len - 1 - s; };
+  float pf[LS_PF];
+#pragma unroll
+  for (int i = 0; i < LS_PF; ++i) pf[i] = (i < len) ? to_f32<T_>(pre_n[static_cast<size_t>(frame(i)) * (2 * LS_G)]) : 0.f;
+  __syncthreads();
+  const int quad = (j & 31) & ~3;  // first lane of this unit's quad
+  int cur = 0;
+  for (int s0 = 0; s0 < len; s0 += LS_PF) {
+#pragma unroll
+    for (int i = 0; i < LS_PF; ++i) {
+      const int s = s0 + i;
+      if (s >= len) break;
+      float acc0 = pf[i], acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      if (s + LS_PF < len) pf[i] = to_f32<T_>(pre_n[static_cast<size_t>(frame(s + LS_PF)) * (2 * LS_G)]);
+      const float* hp = h_s[cur];
+#pragma unroll
+      for (int k = 0; k < LS_H; k += 4) {
+        const float4 hv = *reinterpret_cast<const float4*>(hp + k);
+        acc0 = fmaf(w[k], hv.x, acc0);
+        acc1 = fmaf(w[k + 1], hv.y, acc1);
+        acc2 = fmaf(w[k + 2], hv.z, acc2);
+        acc3 = fmaf(w[k + 3], hv.w, acc3);
+      }
+      const float a = (acc0 + acc1) + (acc2 + acc3);
+      const float act = q == 2 ? tanhf_(a) : sigmoidf_(a);
+      const float gi = __shfl_sync(0xffffffffu, act, quad);
+      const float gf = __shfl_sync(0xffffffffu, act, quad + 1);
+      const float gg = __shfl_sync(0xffffffffu, act, quad + 2);
+      const float go = __shfl_sync(0xffffffffu, act, quad + 3);
+      c = fmaf(gf, c, gi * gg);
+      const float h = go * tanhf_(c);
+      if (q == 0) {
+        h_s[cur ^ 1][u] = h;
+        const int t = frame(s);
+        const size_t row = static_cast<size_t>(n) * T + t;
+        out[row * (2 * LS_H) + d * LS_H + u] = from_f32<T_>(h);
+        gates[(row * 2 + d) * LS_H + u] = make_float4(gi, gf, gg, go);
+        cells[(row * 2 + d) * LS_H + u] = c;
+      }
+      __syncthreads();
+      cur ^= 1;
+    }
+  }
+  // pad_packed_sequence: zeros after the utterance's last frame
+  if (j < LS_H)
+    for (int t = len; t < T; ++t) out[(static_cast<size_t>(n) * T + t) * (2 * LS_H) + d * LS_H + j] = from_f32<T_>(0.f);
+}
+
+template <typename T_>
+__global__ void __launch_bounds__(LS_G)
+bilstm_bwd2_kernel(const T_* __restrict__ dout, const T_* __restrict__ out, const float4* __restrict__ gates,
+                   const float* __restrict__ cells, const float* __restrict__ whh, const int32_t* __restrict__ lengths,
+                   T_* __restrict__ dpre, float* __restrict__ dwhh, int T) {
+  const int n = blockIdx.x, d = blockIdx.y, j = threadIdx.x;
+  const int u = j >> 2, q = j & 3;     // phase 1 / dW view: gate q of unit u (row q*40 + u)
+  const int row_j = q * LS_H + u;
+  __shared__ __align__(16) float dg_s[2][LS_G];
+  __shared__ __align__(16) float hprev_s[2][LS_H];
+  // dh_prev view: thread = (unit k = u, gate q); it owns W_hh[q*40 + jj, u], jj < 40
+  float wt[LS_H];
+#pragma unroll
+  for (int jj = 0; jj < LS_H; ++jj) wt[jj] = whh[(static_cast<size_t>(d) * LS_G + q * LS_H + jj) * LS_H + u];
+  float acc[LS_H];
+#pragma unroll
+  for (int k = 0; k < LS_H; ++k) acc[k] = 0.f;
+  int len = lengths != nullptr ? lengths[n] : T;
+  len = max(0, min(len, T));
+  float dc_carry = 0.f, dh_rec = 0.f;
+  auto frame = [&](int s) { return d == 0 ? s : len - 1 - s; };
+  struct Ld {
+    float4 g4;
+    float ct, cp, hp, dh;
+  };
+  auto load = [&](int s) {  // the unit's saved state: the four lanes of a quad read the same addresses
+    Ld v;
+    const size_t row = static_cast<size_t>(n) * T + frame(s);
+    v.g4 = gates[(row * 2 + d) * LS_H + u];
+    v.ct = cells[(row * 2 + d) * LS_H + u];
+    v.dh = to_f32<T_>(dout[row * (2 * LS_H) + d * LS_H + u]);
+    v.cp = 0.f;
+    v.hp = 0.f;
+    if (s > 0) {
+      const size_t rowp = static_cast<size_t>(n) * T + frame(s - 1);
+      v.cp = cells[(rowp * 2 + d) * LS_H + u];
+      v.hp = to_f32<T_>(out[rowp * (2 * LS_H) + d * LS_H + u]);
+    }
+    return v;
+  };
+  constexpr int PF = 4;  // positions of prefetch distance
+  Ld ring[PF];
+#pragma unroll
+  for (int i = 0; i < PF; ++i)
+    if (len - 1 - i >= 0) ring[i] = load(len - 1 - i);
+  int cur = 0;
+  for (int s0 = len - 1; s0 >= 0; s0 -= PF) {
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int s = s0 - i;
+      if (s < 0) break;
+      const Ld v = ring[i];
+      if (s - PF >= 0) ring[i] = load(s - PF);
+      const float4 g4 = v.g4;
+      const float dh = v.dh + dh_rec;
+      const float tc = tanhf_(v.ct);
+      const float d_o = dh * tc;
+      const float dc = fmaf(dh * g4.w, 1.f - tc * tc, dc_carry);
+      const float d_i = dc * g4.z, d_g = dc * g4.x, d_f = dc * v.cp;
+      dc_carry = dc * g4.y;
+      const float pi = d_i * g4.x * (1.f - g4.x);
+      const float pf_ = d_f * g4.y * (1.f - g4.y);
+      const float pg = d_g * (1.f - g4.z * g4.z);
+      const float po = d_o * g4.w * (1.f - g4.w);
+      const float dgj = q == 0 ? pi : (q == 1 ? pf_ : (q == 2 ? pg : po));  // this thread's row
+      dg_s[cur][row_j] = dgj;
+      if (q == 0) hprev_s[cur][u] = v.hp;
+      dpre[(static_cast<size_t>(n) * T + frame(s)) * (2 * LS_G) + d * LS_G + row_j] = from_f32<T_>(dgj);
+      __syncthreads();
+      {
+        const float* hp = hprev_s[cur];
+#pragma unroll
+        for (int k = 0; k < LS_H; k += 4) {
+          const float4 hv = *reinterpret_cast<const float4*>(hp + k);
+          acc[k] = fmaf(dgj, hv.x, acc[k]);
+          acc[k + 1] = fmaf(dgj, hv.y, acc[k + 1]);
+          acc[k + 2] = fmaf(dgj, hv.z, acc[k + 2]);
+          acc[k + 3] = fmaf(dgj, hv.w, acc[k + 3]);
+        }
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+        const float* dq = dg_s[cur] + q * LS_H;
+#pragma unroll
+        for (int jj = 0; jj < LS_H; jj += 4) {
+          const float4 dv = *reinterpret_cast<const float4*>(dq + jj);
+          p0 = fmaf(wt[jj], dv.x, p0);
+          p1 = fmaf(wt[jj + 1], dv.y, p1);
+          p2 = fmaf(wt[jj + 2], dv.z, p2);
+          p3 = fmaf(wt[jj + 3], dv.w, p3);
+        }
+        float part = (p0 + p1) + (p2 + p3);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        dh_rec = part;  // dh_prev of unit u, in all four lanes of its quad
+      }
+      cur ^= 1;  // the next frame fills the other buffers: nobody can still be reading them (one barrier behind)
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < LS_H; ++k) atomicAdd(dwhh + (static_cast<size_t>(d) * LS_G + row_j) * LS_H + k, acc[k]);
+  // frames past the end: no gradient
+  for (int t = len; t < T; ++t) dpre[(static_cast<size_t>(n) * T + t) * (2 * LS_G) + d * LS_G + j] = from_f32<T_>(0.f);
+}
+
 }  // namespace lasr
 
 using namespace lasr;
@@ -226,16 +411,26 @@ int lasr_bilstm_fwd(const void* pre, const float* whh, const int32_t* lengths, v
   if (hidden != LS_H) return LASR_ERR_UNSUPPORTED;  // the reference's only configuration (QuartNetContext.py:157)
   if (reinterpret_cast<uintptr_t>(gates) & 15) return LASR_ERR_ALIGNMENT;
   dim3 grid(N, 2);
-  if (dtype == LASR_F32)
-    bilstm_fwd_kernel<float><<<grid, LS_G, 0, stream>>>(static_cast<const float*>(pre), whh, lengths,
-                                                        static_cast<float*>(out), reinterpret_cast<float4*>(gates),
-                                                        cells, T);
-  else if (dtype == LASR_BF16)
-    bilstm_fwd_kernel<__nv_bfloat16><<<grid, LS_G, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(pre), whh, lengths, static_cast<__nv_bfloat16*>(out),
-        reinterpret_cast<float4*>(gates), cells, T);
-  else
+  const bool v1 = getenv("LASR_LSTM_V1") != nullptr && atoi(getenv("LASR_LSTM_V1")) != 0;
+  if (dtype == LASR_F32) {
+    const float* p = static_cast<const float*>(pre);
+    float* o = static_cast<float*>(out);
+    if (v1)
+      bilstm_fwd_kernel<float><<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, reinterpret_cast<float4*>(gates), cells, T);
+    else
+      bilstm_fwd2_kernel<float><<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, reinterpret_cast<float4*>(gates), cells, T);
+  } else if (dtype == LASR_BF16) {
+    const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(pre);
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+    if (v1)
+      bilstm_fwd_kernel<__nv_bfloat16>
+          <<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, reinterpret_cast<float4*>(gates), cells, T);
+    else
+      bilstm_fwd2_kernel<__nv_bfloat16>
+          <<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, reinterpret_cast<float4*>(gates), cells, T);
+  } else {
     return LASR_ERR_BAD_DTYPE;
+  }
   LASR_CHECK_LAUNCH();
   return LASR_OK;
 }
@@ -249,16 +444,27 @@ int lasr_bilstm_bwd(const void* dout, const void* out, const float* gates, const
   if (hidden != LS_H) return LASR_ERR_UNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(gates) & 15) return LASR_ERR_ALIGNMENT;
   dim3 grid(N, 2);
-  if (dtype == LASR_F32)
-    bilstm_bwd_kernel<float><<<grid, LS_G, 0, stream>>>(
-        static_cast<const float*>(dout), static_cast<const float*>(out), reinterpret_cast<const float4*>(gates), cells,
-        whh, lengths, static_cast<float*>(dpre), dwhh, T);
-  else if (dtype == LASR_BF16)
-    bilstm_bwd_kernel<__nv_bfloat16><<<grid, LS_G, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(out),
-        reinterpret_cast<const float4*>(gates), cells, whh, lengths, static_cast<__nv_bfloat16*>(dpre), dwhh, T);
-  else
+  const bool v1 = getenv("LASR_LSTM_V1") != nullptr && atoi(getenv("LASR_LSTM_V1")) != 0;
+  const float4* g4 = reinterpret_cast<const float4*>(gates);
+  if (dtype == LASR_F32) {
+    const float* a = static_cast<const float*>(dout);
+    const float* b = static_cast<const float*>(out);
+    float* o = static_cast<float*>(dpre);
+    if (v1)
+      bilstm_bwd_kernel<float><<<grid, LS_G, 0, stream>>>(a, b, g4, cells, whh, lengths, o, dwhh, T);
+    else
+      bilstm_bwd2_kernel<float><<<grid, LS_G, 0, stream>>>(a, b, g4, cells, whh, lengths, o, dwhh, T);
+  } else if (dtype == LASR_BF16) {
+    const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(dout);
+    const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(out);
+    __nv_bfloat16* o = static_cast<__nv_bfloat16*>(dpre);
+    if (v1)
+      bilstm_bwd_kernel<__nv_bfloat16><<<grid, LS_G, 0, stream>>>(a, b, g4, cells, whh, lengths, o, dwhh, T);
+    else
+      bilstm_bwd2_kernel<__nv_bfloat16><<<grid, LS_G, 0, stream>>>(a, b, g4, cells, whh, lengths, o, dwhh, T);
+  } else {
     return LASR_ERR_BAD_DTYPE;
+  }
   LASR_CHECK_LAUNCH();
   return LASR_OK;
 }

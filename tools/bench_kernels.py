@@ -207,6 +207,24 @@ def bench_ctc_aishell():
     report("colsum [M, 4336] bf16 (decoder bias gradient)", timeit(lambda: ops.colsum(logits.view(M, ld), V, out=out)), 2 * M * ld, 0)
 
 
+def bench_lstm():
+    """the Context variants' BiLSTM recurrence (config 4: N = 32, T' = 801; config 3: N = 64, T' = 1001)"""
+    import os
+    H = 40
+    for nn, tt in ((32, 801), (64, 1001)):
+        pre = (torch.randn(nn, tt, 8 * H, device=dev) * 0.7).bfloat16()
+        whh = torch.randn(2, 4 * H, H, device=dev) * 0.2
+        lens = torch.full((nn,), tt, device=dev, dtype=torch.int32)
+        dout = torch.randn(nn, tt, 2 * H, device=dev).bfloat16()
+        for mode in ("1", "0"):
+            os.environ["LASR_LSTM_V1"] = mode
+            out, gates, cells = ops.bilstm_fwd(pre, whh, lens, H)
+            dwhh = torch.zeros_like(whh)
+            report(f"bilstm_fwd N={nn} T={tt} LASR_LSTM_V1={mode}", timeit(lambda: ops.bilstm_fwd(pre, whh, lens, H)), 0, 0)
+            report(f"bilstm_bwd N={nn} T={tt} LASR_LSTM_V1={mode}", timeit(lambda: ops.bilstm_bwd(dout, out, gates, cells, whh, lens, dwhh, H)), 0, 0)
+        os.environ.pop("LASR_LSTM_V1")
+
+
 def bench_frontend():
     from lightning_asr_b200 import frontend
 
@@ -220,6 +238,6 @@ def bench_frontend():
 
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
-for name, fn in [("calib", bench_calib), ("gemm", bench_gemm), ("dw", bench_dw), ("dwcm", bench_dwcm), ("bn", bench_bn), ("ctc", bench_ctc), ("aishell", bench_ctc_aishell), ("frontend", bench_frontend)]:
+for name, fn in [("calib", bench_calib), ("gemm", bench_gemm), ("dw", bench_dw), ("dwcm", bench_dwcm), ("bn", bench_bn), ("ctc", bench_ctc), ("aishell", bench_ctc_aishell), ("lstm", bench_lstm), ("frontend", bench_frontend)]:
     if which in ("all", name):
         fn()
