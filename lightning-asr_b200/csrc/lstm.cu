@@ -229,7 +229,7 @@ bilstm_bwd_kernel(const T_* __restrict__ dout, const T_* __restrict__ out, const
 //             four lanes of unit k's quad -- exactly where the next frame's chain needs it, in registers.
 // The exchange buffers are double-buffered, which is what makes one barrier enough.  Same operations in the same order
 // per value: outputs, saved gates / cells and all gradients are bit-identical to the kernels above
-// (tests/test_kernels_gpu.py::test_bilstm_one_barrier_kernels_are_bit_identical); LASR_LSTM_V1=1 selects those.
+// (tests/test_kernels_gpu.py::test_bilstm_one_barrier_kernels_are_bit_identical); LASR_LSTM_V1=1 selects those, 2 these.
 // ------------------------------------------------------------------------------------------------
 template <typename T_>
 __global__ void __launch_bounds__(LS_G)
@@ -398,6 +398,240 @@ bilstm_bwd2_kernel(const T_* __restrict__ dout, const T_* __restrict__ out, cons
   for (int t = len; t < T; ++t) dpre[(static_cast<size_t>(n) * T + t) * (2 * LS_G) + d * LS_G + j] = from_f32<T_>(0.f);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Third generation: the same thread layout and single barrier as above, with the per-frame instruction stream of a warp
+// cut in half.  A CTA is 5 warps on 4 schedulers and every frame is one dependent chain, so the frame time is the length
+// of a warp's instruction stream (measured: generation 1 and 2 both 0.74 / 1.15 us per frame at 185 / 245 instructions),
+// not the barrier count.  What went:
+//   * the dot products run as packed fma.rn.f32x2 (FFMA2: two IEEE fp32 FMAs per instruction, same values as the scalar
+//     chains: 20 instead of 40 issue slots per 40-term product);
+//   * FAST (the bf16 path): sigmoid = rcp(1 + ex2(-x log2 e)), tanh(x) = 2 sigmoid(2x) - 1, branch-free for all four
+//     gate types (5 instructions; abs. error ~2e-7, three decimal orders below the bf16 rounding of `pre` and `out`).
+//     libm's tanhf / IEEE division cost ~60 instructions per frame and diverge inside a quad.  fp32 keeps libm;
+//   * rows are addressed with 32-bit element indices advanced by +-1 per frame (the 64-bit (n T + t) * stride arithmetic
+//     of five streams was ~70 of the backward's instructions);
+//   * backward: the cell state of the previous position comes from the prefetch ring (it is the next entry's c_t), each
+//     lane derives only ITS gate's gradient -- dgate = A * (B * D) with B, D selected per lane off the critical chain,
+//     A = dc (i, f, g) or dh tanh(c) (o) -- instead of all four.
+// Forward pre-activations are bit-identical to the kernels above; the backward re-associates a few products (1 ulp).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+// sc = 1: sigmoid(x); sc = 2: tanh(x).  km = -sc log2(e), kb = 1 - sc
+__device__ __forceinline__ float act_fast(float x, float km, float sc, float kb) {
+  return fmaf(rcp_approx(1.f + ex2_approx(x * km)), sc, kb);
+}
+__device__ __forceinline__ float tanh_fast(float x) { return act_fast(x, -2.f * kLog2e, 2.f, -1.f); }
+
+// branch-free select on a lane constant (the compiler turns nested ?: on per-lane values into divergent branches)
+__device__ __forceinline__ float selp(float a, float b, int take_a) {
+  float r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f32 %0, %1, %2, p;\n\t}" : "=f"(r) : "f"(a), "f"(b), "r"(take_a));
+  return r;
+}
+
+template <typename T_, bool FAST>
+__global__ void __launch_bounds__(LS_G)
+bilstm_fwd3_kernel(const T_* __restrict__ pre, const float* __restrict__ whh, const int32_t* __restrict__ lengths,
+                   T_* __restrict__ out, float4* __restrict__ gates, float* __restrict__ cells, int T) {
+  static_assert(LS_PF % 2 == 0, "the exchange buffer index is the unrolled position's parity");
+  const int n = blockIdx.x, d = blockIdx.y, j = threadIdx.x;
+  const int u = j >> 2, q = j & 3;
+  const int row_j = q * LS_H + u;  // this thread's gate row in PyTorch's (i, f, g, o) order
+  __shared__ __align__(16) float h_s[2][LS_H];
+  float2 w2[LS_H / 2];
+#pragma unroll
+  for (int k = 0; k < LS_H / 2; ++k)
+    w2[k] = *reinterpret_cast<const float2*>(whh + (static_cast<size_t>(d) * LS_G + row_j) * LS_H + 2 * k);
+  int len = lengths != nullptr ? lengths[n] : T;
+  len = max(0, min(len, T));
+  if (j < LS_H) h_s[0][j] = 0.f;
+  float c = 0.f;
+  const float sc = q == 2 ? 2.f : 1.f, km = -sc * kLog2e, kb = 1.f - sc;
+  const int dir = d == 0 ? 1 : -1;
+  const int row0 = n * T + (d == 0 ? 0 : len - 1);  // row of the recurrence's first position; the host checked the range
+  // element indices, advanced by +-1 row per frame: the prefetch target in `pre`, the row in out / gates / cells
+  const int spre = dir * (2 * LS_G), s80 = dir * (2 * LS_H);
+  int ipre = row0 * (2 * LS_G) + d * LS_G + row_j;
+  int i80 = row0 * (2 * LS_H) + d * LS_H + u;
+  float pf[LS_PF];
+#pragma unroll
+  for (int i = 0; i < LS_PF; ++i) {
+    pf[i] = (i < len) ? to_f32<T_>(pre[ipre]) : 0.f;
+    ipre += spre;
+  }
+  __syncthreads();
+  const int quad = (j & 31) & ~3;  // first lane of this unit's quad
+  for (int s0 = 0; s0 < len; s0 += LS_PF) {
+#pragma unroll
+    for (int i = 0; i < LS_PF; ++i) {
+      const int s = s0 + i;  // s >= len (the last pass of the unrolled ring): a virtual frame, nothing is stored
+      float2 a01 = make_float2(pf[i], 0.f), a23 = make_float2(0.f, 0.f);
+      if (s + LS_PF < len) pf[i] = to_f32<T_>(pre[ipre]);
+      ipre += spre;
+      const float* hp = h_s[i & 1];
+#pragma unroll
+      for (int k = 0; k < LS_H; k += 4) {
+        const float4 hv = *reinterpret_cast<const float4*>(hp + k);
+        a01 = ffma2(w2[k / 2], make_float2(hv.x, hv.y), a01);
+        a23 = ffma2(w2[k / 2 + 1], make_float2(hv.z, hv.w), a23);
+      }
+      const float a = (a01.x + a01.y) + (a23.x + a23.y);
+      float act;
+      if (FAST)
+        act = act_fast(a, km, sc, kb);
+      else
+        act = q == 2 ? tanhf_(a) : sigmoidf_(a);
+      const float gi = __shfl_sync(0xffffffffu, act, quad);
+      const float gf = __shfl_sync(0xffffffffu, act, quad + 1);
+      const float gg = __shfl_sync(0xffffffffu, act, quad + 2);
+      const float go = __shfl_sync(0xffffffffu, act, quad + 3);
+      c = fmaf(gf, c, gi * gg);
+      if (q == 0 && s < len) {
+        const float h = go * (FAST ? tanh_fast(c) : tanhf_(c));
+        h_s[(i & 1) ^ 1][u] = h;
+        out[i80] = from_f32<T_>(h);
+        gates[i80] = make_float4(gi, gf, gg, go);
+        cells[i80] = c;
+      }
+      i80 += s80;
+      __syncthreads();
+    }
+  }
+  // pad_packed_sequence: zeros after the utterance's last frame
+  if (j < LS_H)
+    for (int t = len; t < T; ++t) out[(static_cast<size_t>(n) * T + t) * (2 * LS_H) + d * LS_H + j] = from_f32<T_>(0.f);
+}
+
+template <typename T_, bool FAST>
+__global__ void __launch_bounds__(LS_G, 1)
+bilstm_bwd3_kernel(const T_* __restrict__ dout, const T_* __restrict__ out, const float4* __restrict__ gates,
+                   const float* __restrict__ cells, const float* __restrict__ whh, const int32_t* __restrict__ lengths,
+                   T_* __restrict__ dpre, float* __restrict__ dwhh, int T) {
+  const int n = blockIdx.x, d = blockIdx.y, j = threadIdx.x;
+  const int u = j >> 2, q = j & 3;  // gate q of unit u (row q*40 + u); for the dh_prev reduction: (unit k = u, gate q)
+  const int row_j = q * LS_H + u;
+  __shared__ __align__(16) float dg_s[2][LS_G];
+  __shared__ __align__(16) float hprev_s[2][LS_H];
+  float2 wt2[LS_H / 2];  // W_hh[q*40 + jj, u], jj < 40
+#pragma unroll
+  for (int jj = 0; jj < LS_H / 2; ++jj) {
+    wt2[jj].x = whh[(static_cast<size_t>(d) * LS_G + q * LS_H + 2 * jj) * LS_H + u];
+    wt2[jj].y = whh[(static_cast<size_t>(d) * LS_G + q * LS_H + 2 * jj + 1) * LS_H + u];
+  }
+  float2 acc2[LS_H / 2];
+#pragma unroll
+  for (int k = 0; k < LS_H / 2; ++k) acc2[k] = make_float2(0.f, 0.f);
+  int len = lengths != nullptr ? lengths[n] : T;
+  len = max(0, min(len, T));
+  float dc_carry = 0.f, dh_rec = 0.f;
+  const int dir = d == 0 ? 1 : -1;
+  // row of recurrence position s: n T + (d == 0 ? s : len - 1 - s); the walk starts at s = len - 1 and moves by -dir
+  const int row0 = n * T + (d == 0 ? len - 1 : 0);
+  const int s80 = -dir * (2 * LS_H), spre = -dir * (2 * LS_G);
+  int i80 = row0 * (2 * LS_H) + d * LS_H + u;    // the row being LOADED (PF positions ahead of the walk) in gates / cells / dout
+  int ipre = row0 * (2 * LS_G) + d * LS_G + row_j;  // the row being processed, in dpre
+  const int is_q0 = q == 0, is_q1 = q == 1, is_q2 = q == 2, is_q3 = q == 3;
+  constexpr int PF = 4;  // positions of prefetch distance
+  static_assert(PF % 2 == 0, "the exchange buffer index is the unrolled position's parity");
+  float4 r_g4[PF];
+  float r_ct[PF], r_hp[PF], r_dh[PF];
+  // the unit's saved state at the row the loads have reached; the four lanes of a quad read the same addresses.
+  // hp: h of the position before, one row further along the walk
+#define LASR_LSTM_LOAD(i, has_prev)                                         \
+  {                                                                         \
+    r_g4[i] = gates[i80];                                                   \
+    r_ct[i] = cells[i80];                                                   \
+    r_dh[i] = to_f32<T_>(dout[i80]);                                        \
+    r_hp[i] = (has_prev) ? to_f32<T_>(out[i80 + s80]) : 0.f;                \
+    i80 += s80;                                                             \
+  }
+#pragma unroll
+  for (int i = 0; i < PF; ++i) {
+    r_ct[i] = 0.f;
+    if (len - 1 - i >= 0) LASR_LSTM_LOAD(i, len - 1 - i > 0)
+  }
+  for (int s0 = len - 1; s0 >= 0; s0 -= PF) {
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int s = s0 - i;  // s < 0 (the last pass of the unrolled ring): a virtual frame with a zero gate gradient
+      const float cp = s > 0 ? r_ct[(i + 1) % PF] : 0.f;  // c of position s - 1: the ring's next entry
+      const float4 g4 = r_g4[i];
+      // off the recurrent chain: this lane's gate value S, its partner factor B and the activation derivative D
+      const float S = selp(g4.x, selp(g4.y, selp(g4.z, g4.w, is_q2), is_q1), is_q0);
+      const float B = selp(g4.z, selp(cp, selp(g4.x, 1.f, is_q2), is_q1), is_q0);
+      const float D = fmaf(-S, S, selp(1.f, S, is_q2));  // 1 - g^2 (tanh) or s - s^2 (sigmoid)
+      const float BD = B * D;
+      const float tc = FAST ? tanh_fast(r_ct[i]) : tanhf_(r_ct[i]);
+      const float k1 = g4.w * fmaf(-tc, tc, 1.f);
+      // the chain
+      const float dh = r_dh[i] + dh_rec;
+      const float dc = fmaf(dh, k1, dc_carry);
+      dc_carry = dc * g4.y;
+      const float dgj = s >= 0 ? selp(dh * tc, dc, is_q3) * BD : 0.f;
+      dg_s[i & 1][row_j] = dgj;
+      if (q == 0) hprev_s[i & 1][u] = s >= 0 ? r_hp[i] : 0.f;
+      if (s >= 0) dpre[ipre] = from_f32<T_>(dgj);
+      ipre += spre;
+      // refill this slot for position s - PF (its old content is dead; r_ct[i] was read as cp one position ago)
+      if (s - PF >= 0) LASR_LSTM_LOAD(i, s - PF > 0)
+      __syncthreads();
+      {
+        const float* hp = hprev_s[i & 1];
+        const float2 dg2 = make_float2(dgj, dgj);
+#pragma unroll
+        for (int k = 0; k < LS_H; k += 4) {
+          const float4 hv = *reinterpret_cast<const float4*>(hp + k);
+          acc2[k / 2] = ffma2(dg2, make_float2(hv.x, hv.y), acc2[k / 2]);
+          acc2[k / 2 + 1] = ffma2(dg2, make_float2(hv.z, hv.w), acc2[k / 2 + 1]);
+        }
+        float2 p01 = make_float2(0.f, 0.f), p23 = make_float2(0.f, 0.f);
+        const float* dq = dg_s[i & 1] + q * LS_H;
+#pragma unroll
+        for (int jj = 0; jj < LS_H; jj += 4) {
+          const float4 dv = *reinterpret_cast<const float4*>(dq + jj);
+          p01 = ffma2(wt2[jj / 2], make_float2(dv.x, dv.y), p01);
+          p23 = ffma2(wt2[jj / 2 + 1], make_float2(dv.z, dv.w), p23);
+        }
+        float part = (p01.x + p01.y) + (p23.x + p23.y);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        dh_rec = part;  // dh_prev of unit u, in all four lanes of its quad
+      }
+      // the next frame fills the other pair of buffers: nobody can still be reading them (one barrier behind)
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < LS_H / 2; ++k) {
+    atomicAdd(dwhh + (static_cast<size_t>(d) * LS_G + row_j) * LS_H + 2 * k, acc2[k].x);
+    atomicAdd(dwhh + (static_cast<size_t>(d) * LS_G + row_j) * LS_H + 2 * k + 1, acc2[k].y);
+  }
+#undef LASR_LSTM_LOAD
+  // frames past the end: no gradient
+  for (int t = len; t < T; ++t) dpre[(static_cast<size_t>(n) * T + t) * (2 * LS_G) + d * LS_G + j] = from_f32<T_>(0.f);
+}
+
+// which generation runs: LASR_LSTM_V1 = 1 / 2 / 3 forces one (tests, A/B timing); default: bf16 -> 3 (fast activations),
+// fp32 -> 2 (the exact-parity mode keeps libm activations and the unre-associated backward).  Generation 3 indexes rows
+// with 32-bit element offsets: batches beyond 2^31 / 320 rows fall back to generation 2.
+static int lstm_generation(int dtype, int N, int T) {
+  const char* e = getenv("LASR_LSTM_V1");
+  int g = e != nullptr ? atoi(e) : 0;
+  if (g < 1 || g > 3) g = dtype == LASR_BF16 ? 3 : 2;
+  if (g == 3 && static_cast<long long>(N) * T * (2 * LS_G) >= (1LL << 31)) g = 2;
+  return g;
+}
+
 }  // namespace lasr
 
 using namespace lasr;
@@ -411,23 +645,26 @@ int lasr_bilstm_fwd(const void* pre, const float* whh, const int32_t* lengths, v
   if (hidden != LS_H) return LASR_ERR_UNSUPPORTED;  // the reference's only configuration (QuartNetContext.py:157)
   if (reinterpret_cast<uintptr_t>(gates) & 15) return LASR_ERR_ALIGNMENT;
   dim3 grid(N, 2);
-  const bool v1 = getenv("LASR_LSTM_V1") != nullptr && atoi(getenv("LASR_LSTM_V1")) != 0;
+  const int gen = lstm_generation(dtype, N, T);
+  float4* g4 = reinterpret_cast<float4*>(gates);
   if (dtype == LASR_F32) {
     const float* p = static_cast<const float*>(pre);
     float* o = static_cast<float*>(out);
-    if (v1)
-      bilstm_fwd_kernel<float><<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, reinterpret_cast<float4*>(gates), cells, T);
+    if (gen == 1)
+      bilstm_fwd_kernel<float><<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, g4, cells, T);
+    else if (gen == 2)
+      bilstm_fwd2_kernel<float><<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, g4, cells, T);
     else
-      bilstm_fwd2_kernel<float><<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, reinterpret_cast<float4*>(gates), cells, T);
+      bilstm_fwd3_kernel<float, false><<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, g4, cells, T);
   } else if (dtype == LASR_BF16) {
     const __nv_bfloat16* p = static_cast<const __nv_bfloat16*>(pre);
     __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
-    if (v1)
-      bilstm_fwd_kernel<__nv_bfloat16>
-          <<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, reinterpret_cast<float4*>(gates), cells, T);
+    if (gen == 1)
+      bilstm_fwd_kernel<__nv_bfloat16><<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, g4, cells, T);
+    else if (gen == 2)
+      bilstm_fwd2_kernel<__nv_bfloat16><<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, g4, cells, T);
     else
-      bilstm_fwd2_kernel<__nv_bfloat16>
-          <<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, reinterpret_cast<float4*>(gates), cells, T);
+      bilstm_fwd3_kernel<__nv_bfloat16, true><<<grid, LS_G, 0, stream>>>(p, whh, lengths, o, g4, cells, T);
   } else {
     return LASR_ERR_BAD_DTYPE;
   }
@@ -444,24 +681,28 @@ int lasr_bilstm_bwd(const void* dout, const void* out, const float* gates, const
   if (hidden != LS_H) return LASR_ERR_UNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(gates) & 15) return LASR_ERR_ALIGNMENT;
   dim3 grid(N, 2);
-  const bool v1 = getenv("LASR_LSTM_V1") != nullptr && atoi(getenv("LASR_LSTM_V1")) != 0;
+  const int gen = lstm_generation(dtype, N, T);
   const float4* g4 = reinterpret_cast<const float4*>(gates);
   if (dtype == LASR_F32) {
     const float* a = static_cast<const float*>(dout);
     const float* b = static_cast<const float*>(out);
     float* o = static_cast<float*>(dpre);
-    if (v1)
+    if (gen == 1)
       bilstm_bwd_kernel<float><<<grid, LS_G, 0, stream>>>(a, b, g4, cells, whh, lengths, o, dwhh, T);
-    else
+    else if (gen == 2)
       bilstm_bwd2_kernel<float><<<grid, LS_G, 0, stream>>>(a, b, g4, cells, whh, lengths, o, dwhh, T);
+    else
+      bilstm_bwd3_kernel<float, false><<<grid, LS_G, 0, stream>>>(a, b, g4, cells, whh, lengths, o, dwhh, T);
   } else if (dtype == LASR_BF16) {
     const __nv_bfloat16* a = static_cast<const __nv_bfloat16*>(dout);
     const __nv_bfloat16* b = static_cast<const __nv_bfloat16*>(out);
     __nv_bfloat16* o = static_cast<__nv_bfloat16*>(dpre);
-    if (v1)
+    if (gen == 1)
       bilstm_bwd_kernel<__nv_bfloat16><<<grid, LS_G, 0, stream>>>(a, b, g4, cells, whh, lengths, o, dwhh, T);
-    else
+    else if (gen == 2)
       bilstm_bwd2_kernel<__nv_bfloat16><<<grid, LS_G, 0, stream>>>(a, b, g4, cells, whh, lengths, o, dwhh, T);
+    else
+      bilstm_bwd3_kernel<__nv_bfloat16, true><<<grid, LS_G, 0, stream>>>(a, b, g4, cells, whh, lengths, o, dwhh, T);
   } else {
     return LASR_ERR_BAD_DTYPE;
   }

@@ -441,11 +441,8 @@ def test_ctc_gradient_pass_for_large_vocabularies_is_bit_identical(ops, N, T, S,
     assert rel_err(grads["1"][feasible][..., :V].float(), lpd.grad[feasible]) < tol
 
 
-@pytest.mark.parametrize("N,T,dtype", [(3, 57, torch.float32), (4, 401, torch.bfloat16), (2, 9, torch.float32)])
-def test_bilstm_one_barrier_kernels_are_bit_identical(ops, N, T, dtype):
-    """csrc/lstm.cu second generation (the four gates of a unit in four adjacent lanes: shuffles instead of a shared-memory
-    round trip, ONE barrier per frame, the backward's gate-gradient chain on all 160 threads) against the two-barrier
-    kernels: outputs, saved gates / cells, dpre and dW_hh must not differ in a bit -- ragged, zero and full lengths."""
+def _bilstm_generations(ops, N, T, dtype, modes):
+    """forward + backward of the BiLSTM recurrence under LASR_LSTM_V1 = each of `modes` on the same seeded inputs"""
     import os
     torch.manual_seed(N * T)
     H = 40
@@ -459,8 +456,11 @@ def test_bilstm_one_barrier_kernels_are_bit_identical(ops, N, T, dtype):
     res = {}
     old = os.environ.get("LASR_LSTM_V1")
     try:
-        for mode in ("1", "0"):
-            os.environ["LASR_LSTM_V1"] = mode
+        for mode in modes:
+            if mode == "default":
+                os.environ.pop("LASR_LSTM_V1", None)
+            else:
+                os.environ["LASR_LSTM_V1"] = mode
             out, gates, cells = ops.bilstm_fwd(pre, whh, lens, H)
             dwhh = torch.zeros_like(whh)
             dpre = ops.bilstm_bwd(dout, out, gates, cells, whh, lens, dwhh, H)
@@ -471,11 +471,58 @@ def test_bilstm_one_barrier_kernels_are_bit_identical(ops, N, T, dtype):
             os.environ.pop("LASR_LSTM_V1", None)
         else:
             os.environ["LASR_LSTM_V1"] = old
+    return res, lens
+
+
+@pytest.mark.parametrize("N,T,dtype", [(3, 57, torch.float32), (4, 401, torch.bfloat16), (2, 9, torch.float32)])
+def test_bilstm_one_barrier_kernels_are_bit_identical(ops, N, T, dtype):
+    """csrc/lstm.cu second generation (the four gates of a unit in four adjacent lanes: shuffles instead of a shared-memory
+    round trip, ONE barrier per frame, the backward's gate-gradient chain on all 160 threads) against the two-barrier
+    kernels: outputs, saved gates / cells, dpre and dW_hh must not differ in a bit -- ragged, zero and full lengths."""
+    res, lens = _bilstm_generations(ops, N, T, dtype, ("1", "2"))
     o1, g1, c1, p1, w1 = res["1"]
-    o2, g2, c2, p2, w2 = res["0"]
+    o2, g2, c2, p2, w2 = res["2"]
     assert torch.equal(o1, o2) and torch.equal(p1, p2)
     for n in range(N):  # gates / cells are only defined inside an utterance
         ln = int(lens[n])
         assert torch.equal(g1[n, :ln], g2[n, :ln]) and torch.equal(c1[n, :ln], c2[n, :ln])
     # dW_hh: per-CTA register sums added with atomics from 2N CTAs -- the order of those few additions is not fixed
     assert rel_err(w2, w1) < 1e-6
+
+
+@pytest.mark.parametrize("N,T", [(3, 57), (4, 401), (2, 9), (1, 1), (2, 4), (2, 5)])
+def test_bilstm_third_generation_fp32_structure(ops, N, T):
+    """third generation with libm activations (LASR_LSTM_V1=3 on fp32): packed FFMA2 dot products, 32-bit row indices, the
+    unrolled rings running virtual frames past the end, per-lane gate gradients.  The forward must reproduce generation 1
+    bit for bit (FFMA2 = two IEEE FMAs); the backward re-associates a few products: 1e-6.  Lengths around the ring sizes
+    (4 and 8) included."""
+    res, lens = _bilstm_generations(ops, N, T, torch.float32, ("1", "3"))
+    o1, g1, c1, p1, w1 = res["1"]
+    o3, g3, c3, p3, w3 = res["3"]
+    assert torch.equal(o1, o3)
+    for n in range(N):
+        ln = int(lens[n])
+        assert torch.equal(g1[n, :ln], g3[n, :ln]) and torch.equal(c1[n, :ln], c3[n, :ln])
+        assert p3[n, ln:].abs().max().item() == 0 if ln < T else True
+    assert rel_err(p3, p1) < 1e-6
+    assert rel_err(w3, w1) < 1e-6
+
+
+@pytest.mark.parametrize("N,T", [(4, 401), (3, 57), (2, 8)])
+def test_bilstm_third_generation_bf16_fast_activations(ops, N, T):
+    """the bf16 default (third generation, sigmoid / tanh through ex2.approx + rcp.approx, abs. error ~2e-7) against the
+    libm kernels: saved fp32 gates and cells within 2e-6 absolute, outputs and gradients within bf16 rounding noise (a
+    1e-7 difference flips a bf16 rounding now and then: norm-relative 2e-3, 2^-9 = 2e-3 per flipped element)."""
+    res, lens = _bilstm_generations(ops, N, T, torch.bfloat16, ("1", "default"))
+    o1, g1, c1, p1, w1 = res["1"]
+    o3, g3, c3, p3, w3 = res["default"]
+    for n in range(N):
+        ln = int(lens[n])
+        if ln == 0:
+            continue
+        assert (g1[n, :ln] - g3[n, :ln]).abs().max().item() < 5e-6
+        assert (c1[n, :ln] - c3[n, :ln]).abs().max().item() < 2e-5 * max(1.0, c1[n, :ln].abs().max().item())
+        assert o3[n, ln:].abs().max().item() == 0 if ln < T else True
+    assert rel_err(o3, o1) < 2e-3
+    assert rel_err(p3, p1) < 4e-3
+    assert rel_err(w3, w1) < 2e-3
