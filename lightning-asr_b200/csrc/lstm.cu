@@ -409,11 +409,16 @@ bilstm_bwd2_kernel(const T_* __restrict__ dout, const T_* __restrict__ out, cons
 //   * FAST (the bf16 path): sigmoid = rcp(1 + ex2(-x log2 e)), tanh(x) = 2 sigmoid(2x) - 1, branch-free for all four
 //     gate types (5 instructions; abs. error ~2e-7, three decimal orders below the bf16 rounding of `pre` and `out`).
 //     libm's tanhf / IEEE division cost ~60 instructions per frame and diverge inside a quad.  fp32 keeps libm;
-//   * rows are addressed with 32-bit element indices advanced by +-1 per frame (the 64-bit (n T + t) * stride arithmetic
-//     of five streams was ~70 of the backward's instructions);
-//   * backward: the cell state of the previous position comes from the prefetch ring (it is the next entry's c_t), each
-//     lane derives only ITS gate's gradient -- dgate = A * (B * D) with B, D selected per lane off the critical chain,
-//     A = dc (i, f, g) or dh tanh(c) (o) -- instead of all four.
+//   * no global load is consumed inside the recurrence: the operands of the next 16 positions (forward: the `pre` rows;
+//     backward: gates, cells, dout and the previous h, ~1 KB per position) are copied to shared memory with cp.async
+//     while the current 16 are walked.  Loads issued several frames ahead through registers share scoreboards, so
+//     every frame waited for the YOUNGEST load's full latency (probe with L1-resident rows: fwd 260 -> 188 us, bwd 659 ->
+//     258 us); rows are addressed with 32-bit element indices advanced by +-1 per frame;
+//   * backward: the cell state of the previous position is the next row of the staged chunk, each lane derives only ITS
+//     gate's gradient -- dgate = A * (B * D) with B, D selected per lane off the critical chain, A = dc (i, f, g) or
+//     dh tanh(c) (o) -- instead of all four; the operands of position p + 1 are fetched from the stage right behind
+//     position p's barrier.  Chunks are walked in pairs of positions (static exchange-buffer parity); an odd tail runs
+//     one virtual frame that stores nothing.
 // Forward pre-activations are bit-identical to the kernels above; the backward re-associates a few products (1 ulp).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -440,15 +445,25 @@ __device__ __forceinline__ float selp(float a, float b, int take_a) {
   return r;
 }
 
+constexpr int LS_CH = 16;  // positions of the recurrence per staged chunk (even: exchange buffers alternate by parity)
+__device__ __forceinline__ void ls_cp16(void* sdst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(sdst))),
+               "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void ls_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ls_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <typename T_, bool FAST>
 __global__ void __launch_bounds__(LS_G)
 bilstm_fwd3_kernel(const T_* __restrict__ pre, const float* __restrict__ whh, const int32_t* __restrict__ lengths,
                    T_* __restrict__ out, float4* __restrict__ gates, float* __restrict__ cells, int T) {
-  static_assert(LS_PF % 2 == 0, "the exchange buffer index is the unrolled position's parity");
+  static_assert(LS_CH % 2 == 0, "the exchange buffer index is the unrolled position's parity");
   const int n = blockIdx.x, d = blockIdx.y, j = threadIdx.x;
   const int u = j >> 2, q = j & 3;
   const int row_j = q * LS_H + u;  // this thread's gate row in PyTorch's (i, f, g, o) order
   __shared__ __align__(16) float h_s[2][LS_H];
+  __shared__ __align__(16) T_ pre_s[2][LS_CH][LS_G];  // two chunks of this direction's input projections
   float2 w2[LS_H / 2];
 #pragma unroll
   for (int k = 0; k < LS_H / 2; ++k)
@@ -460,58 +475,81 @@ bilstm_fwd3_kernel(const T_* __restrict__ pre, const float* __restrict__ whh, co
   const float sc = q == 2 ? 2.f : 1.f, km = -sc * kLog2e, kb = 1.f - sc;
   const int dir = d == 0 ? 1 : -1;
   const int row0 = n * T + (d == 0 ? 0 : len - 1);  // row of the recurrence's first position; the host checked the range
-  // element indices, advanced by +-1 row per frame: the prefetch target in `pre`, the row in out / gates / cells
-  const int spre = dir * (2 * LS_G), s80 = dir * (2 * LS_H);
-  int ipre = row0 * (2 * LS_G) + d * LS_G + row_j;
-  int i80 = row0 * (2 * LS_H) + d * LS_H + u;
-  float pf[LS_PF];
+  // chunk ch of the walk = positions ch*LS_CH ..: their `pre` rows (160 values of this direction each) go to shared
+  // memory with cp.async while the previous chunk is being walked -- a global load consumed inside the recurrence costs
+  // its full latency every frame (the loads of several frames share a scoreboard: measured 260 vs 188 us)
+  constexpr int V = LS_G * sizeof(T_) / 16;  // 16-byte vectors per position
+  auto issue = [&](int ch) {
+    const int cnt = min(LS_CH, len - ch * LS_CH);
+    char* dst = reinterpret_cast<char*>(&pre_s[ch & 1][0][0]);
+    for (int e = j; e < cnt * V; e += LS_G) {
+      const int p = e / V, v = e - p * V;
+      const int row = row0 + dir * (ch * LS_CH + p);
+      ls_cp16(dst + e * 16, reinterpret_cast<const char*>(pre + (static_cast<size_t>(row) * 2 + d) * LS_G) + v * 16);
+    }
+  };
+  const int nch = (len + LS_CH - 1) / LS_CH;
+  if (nch > 0) issue(0);
+  ls_cp_commit();
+  const int s80 = dir * (2 * LS_H);
+  int i80 = row0 * (2 * LS_H) + d * LS_H + u;  // element index of the current row in out / gates / cells
+  const int quad = (j & 31) & ~3;              // first lane of this unit's quad
+  for (int ch = 0; ch < nch; ++ch) {
+    ls_cp_wait_all();
+    __syncthreads();  // chunk ch has landed for everybody, and everybody is done with the stage chunk ch + 1 goes to
+    if (ch + 1 < nch) issue(ch + 1);
+    ls_cp_commit();
+    const int cnt = min(LS_CH, len - ch * LS_CH);
+    const T_* ps = &pre_s[ch & 1][0][row_j];
+#pragma unroll 1
+    for (int p0 = 0; p0 < cnt; p0 += 2) {
 #pragma unroll
-  for (int i = 0; i < LS_PF; ++i) {
-    pf[i] = (i < len) ? to_f32<T_>(pre[ipre]) : 0.f;
-    ipre += spre;
-  }
-  __syncthreads();
-  const int quad = (j & 31) & ~3;  // first lane of this unit's quad
-  for (int s0 = 0; s0 < len; s0 += LS_PF) {
+      for (int i = 0; i < 2; ++i) {
+        const bool valid = p0 + i < cnt;  // an odd chunk ends with a virtual frame: nothing is stored
+        float2 a01 = make_float2(to_f32<T_>(ps[(p0 + i) * LS_G]), 0.f), a23 = make_float2(0.f, 0.f);
+        const float* hp = h_s[i];
 #pragma unroll
-    for (int i = 0; i < LS_PF; ++i) {
-      const int s = s0 + i;  // s >= len (the last pass of the unrolled ring): a virtual frame, nothing is stored
-      float2 a01 = make_float2(pf[i], 0.f), a23 = make_float2(0.f, 0.f);
-      if (s + LS_PF < len) pf[i] = to_f32<T_>(pre[ipre]);
-      ipre += spre;
-      const float* hp = h_s[i & 1];
-#pragma unroll
-      for (int k = 0; k < LS_H; k += 4) {
-        const float4 hv = *reinterpret_cast<const float4*>(hp + k);
-        a01 = ffma2(w2[k / 2], make_float2(hv.x, hv.y), a01);
-        a23 = ffma2(w2[k / 2 + 1], make_float2(hv.z, hv.w), a23);
+        for (int k = 0; k < LS_H; k += 4) {
+          const float4 hv = *reinterpret_cast<const float4*>(hp + k);
+          a01 = ffma2(w2[k / 2], make_float2(hv.x, hv.y), a01);
+          a23 = ffma2(w2[k / 2 + 1], make_float2(hv.z, hv.w), a23);
+        }
+        const float a = (a01.x + a01.y) + (a23.x + a23.y);
+        float act;
+        if (FAST)
+          act = act_fast(a, km, sc, kb);
+        else
+          act = q == 2 ? tanhf_(a) : sigmoidf_(a);
+        const float gi = __shfl_sync(0xffffffffu, act, quad);
+        const float gf = __shfl_sync(0xffffffffu, act, quad + 1);
+        const float gg = __shfl_sync(0xffffffffu, act, quad + 2);
+        const float go = __shfl_sync(0xffffffffu, act, quad + 3);
+        c = fmaf(gf, c, gi * gg);
+        if (q == 0 && valid) {
+          const float h = go * (FAST ? tanh_fast(c) : tanhf_(c));
+          h_s[i ^ 1][u] = h;
+          out[i80] = from_f32<T_>(h);
+          gates[i80] = make_float4(gi, gf, gg, go);
+          cells[i80] = c;
+        }
+        i80 += s80;
+        __syncthreads();
       }
-      const float a = (a01.x + a01.y) + (a23.x + a23.y);
-      float act;
-      if (FAST)
-        act = act_fast(a, km, sc, kb);
-      else
-        act = q == 2 ? tanhf_(a) : sigmoidf_(a);
-      const float gi = __shfl_sync(0xffffffffu, act, quad);
-      const float gf = __shfl_sync(0xffffffffu, act, quad + 1);
-      const float gg = __shfl_sync(0xffffffffu, act, quad + 2);
-      const float go = __shfl_sync(0xffffffffu, act, quad + 3);
-      c = fmaf(gf, c, gi * gg);
-      if (q == 0 && s < len) {
-        const float h = go * (FAST ? tanh_fast(c) : tanhf_(c));
-        h_s[(i & 1) ^ 1][u] = h;
-        out[i80] = from_f32<T_>(h);
-        gates[i80] = make_float4(gi, gf, gg, go);
-        cells[i80] = c;
-      }
-      i80 += s80;
-      __syncthreads();
     }
   }
   // pad_packed_sequence: zeros after the utterance's last frame
   if (j < LS_H)
     for (int t = len; t < T; ++t) out[(static_cast<size_t>(n) * T + t) * (2 * LS_H) + d * LS_H + j] = from_f32<T_>(0.f);
 }
+
+// one staged chunk of the backward walk: the saved state of LS_CH positions of one (utterance, direction)
+template <typename T_>
+struct LstmBwdStage {
+  float4 g4[LS_CH][LS_H];     // gates after the non-linearities
+  float ct[LS_CH + 1][LS_H];  // cell states; row p + 1 = the position before p (its c feeds the forget gate's gradient)
+  T_ dh[LS_CH][LS_H];         // upstream gradient of h
+  T_ hp[LS_CH][LS_H];         // h of the position before (the recurrent input)
+};
 
 template <typename T_, bool FAST>
 __global__ void __launch_bounds__(LS_G, 1)
@@ -521,6 +559,7 @@ bilstm_bwd3_kernel(const T_* __restrict__ dout, const T_* __restrict__ out, cons
   const int n = blockIdx.x, d = blockIdx.y, j = threadIdx.x;
   const int u = j >> 2, q = j & 3;  // gate q of unit u (row q*40 + u); for the dh_prev reduction: (unit k = u, gate q)
   const int row_j = q * LS_H + u;
+  __shared__ __align__(16) LstmBwdStage<T_> st_s[2];
   __shared__ __align__(16) float dg_s[2][LS_G];
   __shared__ __align__(16) float hprev_s[2][LS_H];
   float2 wt2[LS_H / 2];  // W_hh[q*40 + jj, u], jj < 40
@@ -536,79 +575,109 @@ bilstm_bwd3_kernel(const T_* __restrict__ dout, const T_* __restrict__ out, cons
   len = max(0, min(len, T));
   float dc_carry = 0.f, dh_rec = 0.f;
   const int dir = d == 0 ? 1 : -1;
-  // row of recurrence position s: n T + (d == 0 ? s : len - 1 - s); the walk starts at s = len - 1 and moves by -dir
-  const int row0 = n * T + (d == 0 ? len - 1 : 0);
-  const int s80 = -dir * (2 * LS_H), spre = -dir * (2 * LS_G);
-  int i80 = row0 * (2 * LS_H) + d * LS_H + u;    // the row being LOADED (PF positions ahead of the walk) in gates / cells / dout
-  int ipre = row0 * (2 * LS_G) + d * LS_G + row_j;  // the row being processed, in dpre
-  const int is_q0 = q == 0, is_q1 = q == 1, is_q2 = q == 2, is_q3 = q == 3;
-  constexpr int PF = 4;  // positions of prefetch distance
-  static_assert(PF % 2 == 0, "the exchange buffer index is the unrolled position's parity");
-  float4 r_g4[PF];
-  float r_ct[PF], r_hp[PF], r_dh[PF];
-  // the unit's saved state at the row the loads have reached; the four lanes of a quad read the same addresses.
-  // hp: h of the position before, one row further along the walk
-#define LASR_LSTM_LOAD(i, has_prev)                                         \
-  {                                                                         \
-    r_g4[i] = gates[i80];                                                   \
-    r_ct[i] = cells[i80];                                                   \
-    r_dh[i] = to_f32<T_>(dout[i80]);                                        \
-    r_hp[i] = (has_prev) ? to_f32<T_>(out[i80 + s80]) : 0.f;                \
-    i80 += s80;                                                             \
-  }
-#pragma unroll
-  for (int i = 0; i < PF; ++i) {
-    r_ct[i] = 0.f;
-    if (len - 1 - i >= 0) LASR_LSTM_LOAD(i, len - 1 - i > 0)
-  }
-  for (int s0 = len - 1; s0 >= 0; s0 -= PF) {
-#pragma unroll
-    for (int i = 0; i < PF; ++i) {
-      const int s = s0 - i;  // s < 0 (the last pass of the unrolled ring): a virtual frame with a zero gate gradient
-      const float cp = s > 0 ? r_ct[(i + 1) % PF] : 0.f;  // c of position s - 1: the ring's next entry
-      const float4 g4 = r_g4[i];
-      // off the recurrent chain: this lane's gate value S, its partner factor B and the activation derivative D
-      const float S = selp(g4.x, selp(g4.y, selp(g4.z, g4.w, is_q2), is_q1), is_q0);
-      const float B = selp(g4.z, selp(cp, selp(g4.x, 1.f, is_q2), is_q1), is_q0);
-      const float D = fmaf(-S, S, selp(1.f, S, is_q2));  // 1 - g^2 (tanh) or s - s^2 (sigmoid)
-      const float BD = B * D;
-      const float tc = FAST ? tanh_fast(r_ct[i]) : tanhf_(r_ct[i]);
-      const float k1 = g4.w * fmaf(-tc, tc, 1.f);
-      // the chain
-      const float dh = r_dh[i] + dh_rec;
-      const float dc = fmaf(dh, k1, dc_carry);
-      dc_carry = dc * g4.y;
-      const float dgj = s >= 0 ? selp(dh * tc, dc, is_q3) * BD : 0.f;
-      dg_s[i & 1][row_j] = dgj;
-      if (q == 0) hprev_s[i & 1][u] = s >= 0 ? r_hp[i] : 0.f;
-      if (s >= 0) dpre[ipre] = from_f32<T_>(dgj);
-      ipre += spre;
-      // refill this slot for position s - PF (its old content is dead; r_ct[i] was read as cp one position ago)
-      if (s - PF >= 0) LASR_LSTM_LOAD(i, s - PF > 0)
-      __syncthreads();
-      {
-        const float* hp = hprev_s[i & 1];
-        const float2 dg2 = make_float2(dgj, dgj);
-#pragma unroll
-        for (int k = 0; k < LS_H; k += 4) {
-          const float4 hv = *reinterpret_cast<const float4*>(hp + k);
-          acc2[k / 2] = ffma2(dg2, make_float2(hv.x, hv.y), acc2[k / 2]);
-          acc2[k / 2 + 1] = ffma2(dg2, make_float2(hv.z, hv.w), acc2[k / 2 + 1]);
-        }
-        float2 p01 = make_float2(0.f, 0.f), p23 = make_float2(0.f, 0.f);
-        const float* dq = dg_s[i & 1] + q * LS_H;
-#pragma unroll
-        for (int jj = 0; jj < LS_H; jj += 4) {
-          const float4 dv = *reinterpret_cast<const float4*>(dq + jj);
-          p01 = ffma2(wt2[jj / 2], make_float2(dv.x, dv.y), p01);
-          p23 = ffma2(wt2[jj / 2 + 1], make_float2(dv.z, dv.w), p23);
-        }
-        float part = (p01.x + p01.y) + (p23.x + p23.y);
-        part += __shfl_xor_sync(0xffffffffu, part, 1);
-        part += __shfl_xor_sync(0xffffffffu, part, 2);
-        dh_rec = part;  // dh_prev of unit u, in all four lanes of its quad
+  const int base = n * T + (d == 0 ? 0 : len - 1);  // row of recurrence position s: base + dir * s
+  // chunk ch of the walk = positions s_hi = len - 1 - ch*LS_CH downwards.  Per position: 40 + 10 + VD + VD 16-byte vectors
+  // (gates, cells, dout, out of the position before), plus one more row of cells behind the chunk's last position
+  constexpr int VD = LS_H * sizeof(T_) / 16, OPS = LS_H + LS_H / 4 + 2 * VD;
+  auto issue = [&](int ch) {
+    LstmBwdStage<T_>& S = st_s[ch & 1];
+    const int s_hi = len - 1 - ch * LS_CH;
+    const int cnt = min(LS_CH, s_hi + 1);
+    for (int e = j; e < cnt * OPS; e += LS_G) {
+      const int p = e / OPS, o = e - p * OPS;
+      const int s = s_hi - p;
+      const size_t r80 = static_cast<size_t>(base + dir * s) * (2 * LS_H) + d * LS_H;  // the (row, direction) block
+      if (o < LS_H) {
+        ls_cp16(&S.g4[p][o], gates + r80 + o);
+      } else if (o < LS_H + LS_H / 4) {
+        ls_cp16(&S.ct[p][(o - LS_H) * 4], cells + r80 + (o - LS_H) * 4);
+      } else if (o < LS_H + LS_H / 4 + VD) {
+        const int v = o - (LS_H + LS_H / 4);
+        ls_cp16(reinterpret_cast<char*>(&S.dh[p][0]) + v * 16, reinterpret_cast<const char*>(dout + r80) + v * 16);
+      } else if (s > 0) {
+        const int v = o - (LS_H + LS_H / 4 + VD);
+        const size_t r80p = static_cast<size_t>(base + dir * (s - 1)) * (2 * LS_H) + d * LS_H;
+        ls_cp16(reinterpret_cast<char*>(&S.hp[p][0]) + v * 16, reinterpret_cast<const char*>(out + r80p) + v * 16);
       }
-      // the next frame fills the other pair of buffers: nobody can still be reading them (one barrier behind)
+    }
+    if (j < LS_H / 4 && s_hi - cnt >= 0) {
+      const size_t r80 = static_cast<size_t>(base + dir * (s_hi - cnt)) * (2 * LS_H) + d * LS_H;
+      ls_cp16(&S.ct[cnt][j * 4], cells + r80 + j * 4);
+    }
+  };
+  const int nch = (len + LS_CH - 1) / LS_CH;
+  if (nch > 0) issue(0);
+  ls_cp_commit();
+  const int spre = -dir * (2 * LS_G);
+  int ipre = (base + dir * (len - 1)) * (2 * LS_G) + d * LS_G + row_j;  // the row being processed, in dpre
+  const int is_q0 = q == 0, is_q1 = q == 1, is_q2 = q == 2, is_q3 = q == 3;
+  for (int ch = 0; ch < nch; ++ch) {
+    ls_cp_wait_all();
+    __syncthreads();  // chunk ch has landed for everybody, and everybody is done with the stage chunk ch + 1 goes to
+    if (ch + 1 < nch) issue(ch + 1);
+    ls_cp_commit();
+    const LstmBwdStage<T_>& S = st_s[ch & 1];
+    const int s_hi = len - 1 - ch * LS_CH;
+    const int cnt = min(LS_CH, s_hi + 1);
+    // operands of the next position, fetched from the stage one frame ahead (behind the previous frame's barrier)
+    float4 g4 = S.g4[0][u];
+    float ct = S.ct[0][u], cpn = S.ct[1][u], dhv = to_f32<T_>(S.dh[0][u]), hpv = to_f32<T_>(S.hp[0][u]);
+#pragma unroll 1
+    for (int p0 = 0; p0 < cnt; p0 += 2) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int p = p0 + i, s = s_hi - p;
+        const bool valid = p < cnt;  // an odd last chunk ends with a virtual frame (s = -1): zero gate gradient, no store
+        const float cp = s > 0 ? cpn : 0.f;  // c of position s - 1
+        // off the recurrent chain: this lane's gate value S, its partner factor B and the activation derivative D
+        const float Sg = selp(g4.x, selp(g4.y, selp(g4.z, g4.w, is_q2), is_q1), is_q0);
+        const float B = selp(g4.z, selp(cp, selp(g4.x, 1.f, is_q2), is_q1), is_q0);
+        const float D = fmaf(-Sg, Sg, selp(1.f, Sg, is_q2));  // 1 - g^2 (tanh) or s - s^2 (sigmoid)
+        const float BD = B * D;
+        const float tc = FAST ? tanh_fast(ct) : tanhf_(ct);
+        const float k1 = g4.w * fmaf(-tc, tc, 1.f);
+        // the chain
+        const float dh = dhv + dh_rec;
+        const float dc = fmaf(dh, k1, dc_carry);
+        dc_carry = dc * g4.y;
+        const float dgj = valid ? selp(dh * tc, dc, is_q3) * BD : 0.f;
+        dg_s[i][row_j] = dgj;
+        if (q == 0) hprev_s[i][u] = s > 0 ? hpv : 0.f;
+        if (valid) dpre[ipre] = from_f32<T_>(dgj);
+        ipre += spre;
+        __syncthreads();
+        {
+          const int pn = min(p + 1, LS_CH - 1);
+          g4 = S.g4[pn][u];
+          ct = S.ct[pn][u];
+          cpn = S.ct[pn + 1][u];
+          dhv = to_f32<T_>(S.dh[pn][u]);
+          hpv = to_f32<T_>(S.hp[pn][u]);
+        }
+        {
+          const float* hp = hprev_s[i];
+          const float2 dg2 = make_float2(dgj, dgj);
+#pragma unroll
+          for (int k = 0; k < LS_H; k += 4) {
+            const float4 hv = *reinterpret_cast<const float4*>(hp + k);
+            acc2[k / 2] = ffma2(dg2, make_float2(hv.x, hv.y), acc2[k / 2]);
+            acc2[k / 2 + 1] = ffma2(dg2, make_float2(hv.z, hv.w), acc2[k / 2 + 1]);
+          }
+          float2 p01 = make_float2(0.f, 0.f), p23 = make_float2(0.f, 0.f);
+          const float* dq = dg_s[i] + q * LS_H;
+#pragma unroll
+          for (int jj = 0; jj < LS_H; jj += 4) {
+            const float4 dv = *reinterpret_cast<const float4*>(dq + jj);
+            p01 = ffma2(wt2[jj / 2], make_float2(dv.x, dv.y), p01);
+            p23 = ffma2(wt2[jj / 2 + 1], make_float2(dv.z, dv.w), p23);
+          }
+          float part = (p01.x + p01.y) + (p23.x + p23.y);
+          part += __shfl_xor_sync(0xffffffffu, part, 1);
+          part += __shfl_xor_sync(0xffffffffu, part, 2);
+          dh_rec = part;  // dh_prev of unit u, in all four lanes of its quad
+        }
+        // the next frame fills the other pair of exchange buffers: nobody can still be reading them (one barrier behind)
+      }
     }
   }
 #pragma unroll
@@ -616,20 +685,24 @@ bilstm_bwd3_kernel(const T_* __restrict__ dout, const T_* __restrict__ out, cons
     atomicAdd(dwhh + (static_cast<size_t>(d) * LS_G + row_j) * LS_H + 2 * k, acc2[k].x);
     atomicAdd(dwhh + (static_cast<size_t>(d) * LS_G + row_j) * LS_H + 2 * k + 1, acc2[k].y);
   }
-#undef LASR_LSTM_LOAD
   // frames past the end: no gradient
   for (int t = len; t < T; ++t) dpre[(static_cast<size_t>(n) * T + t) * (2 * LS_G) + d * LS_G + j] = from_f32<T_>(0.f);
 }
 
 // which generation runs: LASR_LSTM_V1 = 1 / 2 / 3 forces one (tests, A/B timing); default: bf16 -> 3 (fast activations),
 // fp32 -> 2 (the exact-parity mode keeps libm activations and the unre-associated backward).  Generation 3 indexes rows
-// with 32-bit element offsets: batches beyond 2^31 / 320 rows fall back to generation 2.
-static int lstm_generation(int dtype, int N, int T) {
+// with 32-bit element offsets and copies 16-byte vectors: batches beyond 2^31 / 320 rows or operands that are not
+// 16-byte aligned fall back to generation 2.
+static int lstm_generation(int dtype, int N, int T, bool aligned16) {
   const char* e = getenv("LASR_LSTM_V1");
   int g = e != nullptr ? atoi(e) : 0;
   if (g < 1 || g > 3) g = dtype == LASR_BF16 ? 3 : 2;
-  if (g == 3 && static_cast<long long>(N) * T * (2 * LS_G) >= (1LL << 31)) g = 2;
+  if (g == 3 && (!aligned16 || static_cast<long long>(N) * T * (2 * LS_G) >= (1LL << 31))) g = 2;
   return g;
+}
+static bool aligned16(const void* a, const void* b = nullptr, const void* c = nullptr, const void* d = nullptr) {
+  return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c) |
+           reinterpret_cast<uintptr_t>(d)) & 15) == 0;
 }
 
 }  // namespace lasr
@@ -645,7 +718,7 @@ int lasr_bilstm_fwd(const void* pre, const float* whh, const int32_t* lengths, v
   if (hidden != LS_H) return LASR_ERR_UNSUPPORTED;  // the reference's only configuration (QuartNetContext.py:157)
   if (reinterpret_cast<uintptr_t>(gates) & 15) return LASR_ERR_ALIGNMENT;
   dim3 grid(N, 2);
-  const int gen = lstm_generation(dtype, N, T);
+  const int gen = lstm_generation(dtype, N, T, aligned16(pre));
   float4* g4 = reinterpret_cast<float4*>(gates);
   if (dtype == LASR_F32) {
     const float* p = static_cast<const float*>(pre);
@@ -681,7 +754,7 @@ int lasr_bilstm_bwd(const void* dout, const void* out, const float* gates, const
   if (hidden != LS_H) return LASR_ERR_UNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(gates) & 15) return LASR_ERR_ALIGNMENT;
   dim3 grid(N, 2);
-  const int gen = lstm_generation(dtype, N, T);
+  const int gen = lstm_generation(dtype, N, T, aligned16(dout, out, cells, gates));
   const float4* g4 = reinterpret_cast<const float4*>(gates);
   if (dtype == LASR_F32) {
     const float* a = static_cast<const float*>(dout);
