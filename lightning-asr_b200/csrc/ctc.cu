@@ -19,6 +19,12 @@ namespace lasr {
 // ------------------------------------------------------------------------------------------------
 // log-softmax: one warp per row
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 log_softmax_fwd_kernel(const T* __restrict__ x, float* __restrict__ lse_out, float* __restrict__ lp, int M, int V,
@@ -28,10 +34,42 @@ log_softmax_fwd_kernel(const T* __restrict__ x, float* __restrict__ lse_out, flo
   if (row >= M) return;
   const T* xr = x + static_cast<size_t>(row) * ld;
   float m = -CUDART_INF_F;
-  for (int c = lane; c < V; c += 32) m = fmaxf(m, to_f32<T>(xr[c]));
-  m = warp_max(m);
   float s = 0.f;
-  for (int c = lane; c < V; c += 32) s += expf(to_f32<T>(xr[c]) - m);
+  if (sizeof(T) == 2 && V > 256 && (ld & 7) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    // wide rows of bf16 scores (the 4334-class decoder): 16-byte loads, and exponentials as ONE ex2.approx of a fused
+    // multiply-add (libm's expf is ~8 instructions: the pass was issue-bound at 2.6x its HBM time).  ex2.approx is
+    // good to 2^-22, the scores themselves carry 2^-9.
+    const int Vr = (V + 7) & ~7;
+    for (int c0 = lane * 8; c0 < Vr; c0 += 256) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(xr + c0);
+      const uint32_t wv[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 xv = bf16x2_to_f32x2(wv[q]);
+        if (c0 + 2 * q < V) m = fmaxf(m, xv.x);
+        if (c0 + 2 * q + 1 < V) m = fmaxf(m, xv.y);
+      }
+    }
+    m = warp_max(m);
+    const float m2 = -m * 1.4426950408889634f;
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c0 = lane * 8; c0 < Vr; c0 += 256) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(xr + c0);  // second pass: the row is in L1 / L2
+      const uint32_t wv[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 xv = bf16x2_to_f32x2(wv[q]);
+        const float e0 = ex2_approx_ftz(fmaf(xv.x, 1.4426950408889634f, m2));
+        const float e1 = ex2_approx_ftz(fmaf(xv.y, 1.4426950408889634f, m2));
+        s4[q] += (c0 + 2 * q < V ? e0 : 0.f) + (c0 + 2 * q + 1 < V ? e1 : 0.f);
+      }
+    }
+    s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+  } else {
+    for (int c = lane; c < V; c += 32) m = fmaxf(m, to_f32<T>(xr[c]));
+    m = warp_max(m);
+    for (int c = lane; c < V; c += 32) s += expf(to_f32<T>(xr[c]) - m);
+  }
   s = warp_sum(s);
   const float lse = m + logf(s);
   if (lane == 0) lse_out[row] = lse;
@@ -761,7 +799,8 @@ ctc_grad_small_kernel(const T* __restrict__ x, const float* __restrict__ lse, co
 // first position that carries position j's label; a warp accumulates occupancy per POSITION (occ_pos[rep[j]], S floats),
 // and the class pass looks a class up through tab.  8 classes per lane and trip as 16-byte vectors when rows allow.
 // Same additions per class (positions of one class that collide in one shared-memory atomic instruction may be
-// serialised in another order than in the dense layout: <= 1 ulp of fp32 on such a class).
+// serialised in another order than in the dense layout: <= 1 ulp of fp32 on such a class).  The bf16 -> bf16 vector path
+// takes its softmax term from ex2.approx (2^-22 relative: a bf16 rounding flips on ~1 element in 1000).
 constexpr int kCtcNoPos = 0x7fffffff;
 template <typename T, typename GT>
 __global__ void __launch_bounds__(256)
@@ -848,19 +887,45 @@ ctc_grad_large_kernel(const T* __restrict__ x, const float* __restrict__ lse, co
   constexpr bool kVec = sizeof(T) == 2 && sizeof(GT) == 2;
   if (kVec && (ldx & 7) == 0 && (ldg & 7) == 0 && ldg <= ldx && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(grad) & 15) == 0) {
+    // bf16 in, bf16 out.  Only the <= S + 1 classes of the utterance's labels (and the blank) carry occupancy: the
+    // row is first written as the plain softmax term, eight classes per lane and trip with no table lookup at all
+    // (ex2.approx of a fused multiply-add: 2^-22, the output rounds to 2^-9), then the occupied classes are rewritten
+    // one by one with the full formula.  The per-class table lookups of the first version were 40 instructions per
+    // class: 152 M warp instructions, issue-bound at 3x the pass's HBM time.
+    const float l2 = -l * 1.4426950408889634f;
+    auto soft = [&](float xv) { return ex2_approx_ftz(fmaf(xv, 1.4426950408889634f, l2)); };
+    const int full = V & ~7;  // classes below `full` sit in complete 8-class vectors
     for (int c0 = lane * 8; c0 < ldg; c0 += 256) {
       const uint4 raw = *reinterpret_cast<const uint4*>(xr + c0);
       const uint32_t wv[4] = {raw.x, raw.y, raw.z, raw.w};
       uint32_t ov[4];
+      if (c0 < full) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float2 xv = bf16x2_to_f32x2(wv[q]);
-        const int c = c0 + 2 * q;
-        const float g0 = c < V ? (expf(xv.x - l) - occupancy(c)) * go : 0.f;
-        const float g1 = c + 1 < V ? (expf(xv.y - l) - occupancy(c + 1)) * go : 0.f;
-        ov[q] = f32x2_to_bf16x2(g0, g1);
+        for (int q = 0; q < 4; ++q) {
+          const float2 xv = bf16x2_to_f32x2(wv[q]);
+          ov[q] = f32x2_to_bf16x2(soft(xv.x) * go, soft(xv.y) * go);
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 xv = bf16x2_to_f32x2(wv[q]);
+          const int c = c0 + 2 * q;
+          ov[q] = f32x2_to_bf16x2(c < V ? soft(xv.x) * go : 0.f, c + 1 < V ? soft(xv.y) * go : 0.f);
+        }
       }
       *reinterpret_cast<uint4*>(gr + c0) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+    }
+    __syncwarp();  // the rewrites below touch addresses other lanes of this warp have just stored to
+    for (int jj = lane; jj <= Sn; jj += 32) {
+      int c;
+      if (jj < Sn) {
+        c = labels[jj];
+        if (rep[jj] != jj || c == blank) continue;  // a later position of a repeated label / the blank: handled once
+      } else {
+        c = blank;
+      }
+      if (c < 0 || c >= V) continue;
+      gr[c] = from_f32<GT>((soft(to_f32<T>(xr[c])) - occupancy(c)) * go);
     }
   } else {
     for (int c = lane; c < ldg; c += 32) {
