@@ -802,8 +802,8 @@ ctc_grad_small_kernel(const T* __restrict__ x, const float* __restrict__ lse, co
 // serialised in another order than in the dense layout: <= 1 ulp of fp32 on such a class).  The bf16 -> bf16 vector path
 // takes its softmax term from ex2.approx (2^-22 relative: a bf16 rounding flips on ~1 element in 1000).
 constexpr int kCtcNoPos = 0x7fffffff;
-template <typename T, typename GT>
-__global__ void __launch_bounds__(256)
+template <typename T, typename GT, bool STAGE>
+__global__ void __launch_bounds__(256, STAGE ? 2 : 6)
 ctc_grad_large_kernel(const T* __restrict__ x, const float* __restrict__ lse, const int64_t* __restrict__ targets,
                       const int32_t* __restrict__ in_len, const int32_t* __restrict__ tgt_len,
                       const float* __restrict__ alpha, const float* __restrict__ beta, const float* __restrict__ nll,
@@ -823,6 +823,21 @@ ctc_grad_large_kernel(const T* __restrict__ x, const float* __restrict__ lse, co
   const int Sn = tgt_len[n];
   const bool built = !(Sn < 0 || Sn > S_max);  // bad lengths: the lattice kernel left alpha / beta unwritten
   const int64_t* tg = targets + static_cast<size_t>(n) * S_max;
+  // STAGE: the warp's score row goes to shared memory in one burst of 16-byte cp.async requests (17 per lane at the
+  // 4334-class vocabulary, all in flight while the CTA builds its tables); the emission gathers of the state pass, the
+  // class pass and the rewrites then read shared memory.  Without it the pass was latency-bound on its global loads
+  // (one 16-byte load in flight per lane in the class pass, scattered 2-byte gathers in the state pass: 70 % of the
+  // warp samples on long-scoreboard stalls) and fetched 448 MB for 304 MB of operands.
+  T* xs = nullptr;
+  if (STAGE) {
+    xs = reinterpret_cast<T*>(gsm + 2 * S_pad + Vp + 8 * static_cast<size_t>(S_pad)) + static_cast<size_t>(w) * ldx;
+    if (t < T_len && t < Tn && built) {
+      const T* src = x + (static_cast<size_t>(n) * T_len + t) * ldx;
+      for (int c0 = lane * 8; c0 < ldx; c0 += 256)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(xs + c0)), "l"(src + c0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (int c = threadIdx.x; c < Vp; c += 256) tab[c] = kCtcNoPos;
   if (built)
     for (int i = threadIdx.x; i < Sn; i += 256) labels[i] = static_cast<int>(tg[i]);
@@ -843,6 +858,11 @@ ctc_grad_large_kernel(const T* __restrict__ x, const float* __restrict__ lse, co
   const int Lp = 2 * Sn + 1;
   const int Lp_max = 2 * S_max + 1;
   const T* xr = x + row * ldx;
+  if (STAGE) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    xr = xs;  // generic pointer into shared memory
+  }
   const float l = lse ? lse[row] : 0.f;
   const float nl = nll[n];
   const float go = grad_out[n];
@@ -1334,9 +1354,31 @@ static int ctc_grad_launch(const void* x, const float* lse, const int64_t* targe
   if (scales == nullptr && V > 128 && !(getenv("LASR_CTC_GRAD_LARGE") != nullptr && atoi(getenv("LASR_CTC_GRAD_LARGE")) == 0)) {
     const int S_pad = (S_max + 3) / 4 * 4, Vp = (V + 3) / 4 * 4;
     const int smem_large = (2 * S_pad + Vp + 8 * S_pad) * static_cast<int>(sizeof(float));
+    // bf16 -> bf16 with vector-friendly rows: the rows of a CTA staged in shared memory (two CTAs per SM)
+    const int smem_stage = smem_large + 8 * ldx * static_cast<int>(sizeof(T));
+    const bool stage = sizeof(T) == 2 && sizeof(GT) == 2 && (ldx & 7) == 0 && (ldg & 7) == 0 && ldg <= ldx &&
+                       (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(grad) & 15) == 0 &&
+                       smem_stage <= 110 * 1024 &&
+                       !(getenv("LASR_CTC_GRAD_STAGE") != nullptr && atoi(getenv("LASR_CTC_GRAD_STAGE")) == 0);
+    if (stage) {
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(ctc_grad_large_kernel<T, GT, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        if (e != cudaSuccess) {
+          lasr_set_cuda_error(e);
+          return LASR_ERR_CUDA;
+        }
+        configured = true;
+      }
+      LASR_CHECK_PDL(launch_pdl(8, ctc_grad_large_kernel<T, GT, true>, dim3(cdiv(Tn, 8), N), dim3(256), smem_stage,
+                                stream, static_cast<const T*>(x), lse, targets, il, tl, alpha, beta, nll, grad_out,
+                                static_cast<GT*>(grad), Tn, V, ldx, ldg, S_max, blank, S_pad, Vp));
+      return LASR_OK;
+    }
     if (smem_large <= 48 * 1024) {
-      LASR_CHECK_PDL(launch_pdl(8, ctc_grad_large_kernel<T, GT>, dim3(cdiv(Tn, 8), N), dim3(256), smem_large, stream,
-                                static_cast<const T*>(x), lse, targets, il, tl, alpha, beta, nll, grad_out,
+      LASR_CHECK_PDL(launch_pdl(8, ctc_grad_large_kernel<T, GT, false>, dim3(cdiv(Tn, 8), N), dim3(256), smem_large,
+                                stream, static_cast<const T*>(x), lse, targets, il, tl, alpha, beta, nll, grad_out,
                                 static_cast<GT*>(grad), Tn, V, ldx, ldg, S_max, blank, S_pad, Vp));
       return LASR_OK;
     }
