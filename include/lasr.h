@@ -274,10 +274,11 @@ int lasr_se_excite_fwd(const float* sums, const float* scale, const float* shift
                        lasr_stream_t stream);
 /* backward of the excitation from lasr_bn_act_bwd_reduce's per_n sums (partials [N*chunks, 3, C] with chunks = 1):
  * dgate[n,c] = sum_t g*BN(y) -> through sigmoid, W2, ReLU, W1 -> extra[n,c] = d s[n,c] / T (the term every frame
- * of (n,c) receives); dW1 += , dW2 += */
+ * of (n,c) receives); dW1 += , dW2 += (one writer per element).  ws: N*(C + C/r) floats of scratch (the per-utterance
+ * gradients at the two linear layers, read by the weight-gradient kernel of the same call). */
 int lasr_se_excite_bwd(const float* partials, int chunks, const float* scale, const float* shift, int T,
                        const float* w1, const float* w2, const float* s, const float* hidden, const float* gate,
-                       float* extra, float* dw1, float* dw2, int N, int C, int Cr, lasr_stream_t stream);
+                       float* extra, float* dw1, float* dw2, float* ws, int N, int C, int Cr, lasr_stream_t stream);
 /* lasr_bn_bwd_finalize for the gated branch (its upstream gradient is g*gate + extra) */
 int lasr_se_bn_bwd_finalize(const float* partials, int N, int chunks, int C, int T, const float* gate,
                             const float* extra, const float* sums_y, const float* gamma, const float* mean,

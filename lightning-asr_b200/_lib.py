@@ -16,7 +16,7 @@ LASR_F32 = 0
 LASR_BF16 = 1
 ACT_NONE = 0
 ACT_RELU = 1
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 def _parse_header(path):
     """Derive the ctypes signatures from include/lasr.h so the binding cannot drift from the C ABI."""

@@ -128,7 +128,7 @@ int lasr_set_sm_budget(int sms) {
   lasr::g_sm_budget = sms;
   return LASR_OK;
 }
-int lasr_abi_version(void) { return 3; }  // 3: series entry points, relu_bits / Toeplitz arguments, CTC scales
+int lasr_abi_version(void) { return 4; }  // 4: lasr_se_excite_bwd takes a scratch buffer (3: series entry points, relu_bits / Toeplitz arguments, CTC scales)
 
 int lasr_set_early_param_loads(int on) { return g_early_params.exchange(on != 0 ? 1 : 0); }
 

@@ -7,11 +7,18 @@
 namespace lasr {
 
 // s = scale*Sy/T + shift ; h = relu(W1 s) ; gate = sigmoid(W2 h)
-__global__ void __launch_bounds__(256)
+// One CTA of 16 warps per utterance.  The MLP is 2 C Cr MACs per utterance -- nothing -- so the kernel is the sum of its
+// dependent L2 round trips: the first version walked W1 one row per warp and trip and W2 one scalar per thread and
+// trip (24 us under ncu at C = 512, Cr = 64).  Here W1 rows are read two per warp and trip in 16-byte vectors, and a
+// thread reads its whole W2 row in 16-byte vectors with four loads in flight.
+constexpr int SE_THREADS = 512;
+__device__ __forceinline__ bool se_al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+__global__ void __launch_bounds__(SE_THREADS)
 se_fwd_kernel(const float* __restrict__ sums, const float* __restrict__ scale, const float* __restrict__ shift,
               float inv_T, const float* __restrict__ w1, const float* __restrict__ w2, float* __restrict__ s_out,
               float* __restrict__ hidden, float* __restrict__ gate, int C, int Cr) {
-  extern __shared__ float sm[];  // s[C], h[Cr]
+  extern __shared__ __align__(16) float sm[];  // s[C], h[Cr]
   float* s = sm;
   float* h = sm + C;
   const int n = blockIdx.x;
@@ -21,36 +28,73 @@ se_fwd_kernel(const float* __restrict__ sums, const float* __restrict__ scale, c
     s_out[static_cast<size_t>(n) * C + c] = v;
   }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < Cr; j += 8) {
-    float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(w1[static_cast<size_t>(j) * C + c], s[c], a);
-    a = warp_sum(a);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const bool vec1 = (C & 3) == 0 && se_al16(w1);
+  for (int j0 = 2 * warp; j0 < Cr; j0 += 2 * nw) {
+    const int j1 = min(j0 + 1, Cr - 1);
+    const float* r0 = w1 + static_cast<size_t>(j0) * C;
+    const float* r1 = w1 + static_cast<size_t>(j1) * C;
+    float a0 = 0.f, a1 = 0.f;
+    if (vec1) {
+      for (int c = lane * 4; c < C; c += 128) {
+        const float4 u = *reinterpret_cast<const float4*>(r0 + c), v = *reinterpret_cast<const float4*>(r1 + c);
+        const float4 x = *reinterpret_cast<const float4*>(s + c);
+        a0 = fmaf(u.x, x.x, fmaf(u.y, x.y, fmaf(u.z, x.z, fmaf(u.w, x.w, a0))));
+        a1 = fmaf(v.x, x.x, fmaf(v.y, x.y, fmaf(v.z, x.z, fmaf(v.w, x.w, a1))));
+      }
+    } else {
+      for (int c = lane; c < C; c += 32) {
+        a0 = fmaf(r0[c], s[c], a0);
+        a1 = fmaf(r1[c], s[c], a1);
+      }
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
     if (lane == 0) {
-      a = fmaxf(a, 0.f);
-      h[j] = a;
-      hidden[static_cast<size_t>(n) * Cr + j] = a;
+      a0 = fmaxf(a0, 0.f);
+      h[j0] = a0;
+      hidden[static_cast<size_t>(n) * Cr + j0] = a0;
+      if (j0 + 1 < Cr) {
+        a1 = fmaxf(a1, 0.f);
+        h[j0 + 1] = a1;
+        hidden[static_cast<size_t>(n) * Cr + j0 + 1] = a1;
+      }
     }
   }
   __syncthreads();
+  const bool vec2 = (Cr & 3) == 0 && se_al16(w2);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f;
-    for (int j = 0; j < Cr; ++j) a = fmaf(w2[static_cast<size_t>(c) * Cr + j], h[j], a);
+    const float* wr = w2 + static_cast<size_t>(c) * Cr;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (vec2) {
+#pragma unroll 4
+      for (int j = 0; j < Cr; j += 4) {
+        const float4 u = *reinterpret_cast<const float4*>(wr + j);
+        a0 = fmaf(u.x, h[j], a0);
+        a1 = fmaf(u.y, h[j + 1], a1);
+        a2 = fmaf(u.z, h[j + 2], a2);
+        a3 = fmaf(u.w, h[j + 3], a3);
+      }
+    } else {
+      for (int j = 0; j < Cr; ++j) a0 = fmaf(wr[j], h[j], a0);
+    }
+    const float a = (a0 + a1) + (a2 + a3);
     gate[static_cast<size_t>(n) * C + c] = 1.f / (1.f + expf(-a));
   }
 }
 
 // dgate[c] = scale*Sgy + shift*Sg (time sums of g*y and g for this utterance, folded from the chunk partials)
-// -> ds ; extra = ds / T ; dW1 += , dW2 +=
-__global__ void __launch_bounds__(256)
+// -> dz = dgate g (1 - g) -> dh = relu'(h) W2^T dz -> ds = W1^T dh ; extra = ds / T.
+// dz [N, C] and dh [N, Cr] are left in `ws` for se_wgrad_kernel: the first version added dz h^T and dh s^T to dW2 / dW1
+// with one global atomic per (utterance, element) -- 4 M atomics on 64 K addresses per launch at N = 64, C = 512.
+__global__ void __launch_bounds__(SE_THREADS)
 se_bwd_kernel(const float* __restrict__ partials, int chunks, const float* __restrict__ scale,
               const float* __restrict__ shift, float inv_T, const float* __restrict__ w1, const float* __restrict__ w2,
-              const float* __restrict__ s_in, const float* __restrict__ hidden, const float* __restrict__ gate,
-              float* __restrict__ extra, float* __restrict__ dw1, float* __restrict__ dw2, int C, int Cr) {
-  extern __shared__ float sm[];  // dz[C], s[C], h[Cr], dh[Cr]
+              const float* __restrict__ hidden, const float* __restrict__ gate, float* __restrict__ extra,
+              float* __restrict__ ws_dz, float* __restrict__ ws_dh, int C, int Cr) {
+  extern __shared__ __align__(16) float sm[];  // dz[C], h[Cr], dh[Cr]
   float* dz = sm;
-  float* s = sm + C;
-  float* h = sm + 2 * C;
+  float* h = sm + C;
   float* dh = h + Cr;
   const int n = blockIdx.x;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -62,33 +106,86 @@ se_bwd_kernel(const float* __restrict__ partials, int chunks, const float* __res
     }
     const float dgate = scale[c] * sgy + shift[c] * sg;
     const float g = gate[static_cast<size_t>(n) * C + c];
-    dz[c] = dgate * g * (1.f - g);
-    s[c] = s_in[static_cast<size_t>(n) * C + c];
+    const float v = dgate * g * (1.f - g);
+    dz[c] = v;
+    ws_dz[static_cast<size_t>(n) * C + c] = v;
   }
-  for (int j = threadIdx.x; j < Cr; j += blockDim.x) h[j] = hidden[static_cast<size_t>(n) * Cr + j];
-  __syncthreads();
-  // dW2[c, j] += dz[c] * h[j]
-  for (int i = threadIdx.x; i < C * Cr; i += blockDim.x) {
-    const int c = i / Cr, j = i - c * Cr;
-    atomicAdd(dw2 + i, dz[c] * h[j]);
-  }
-  // dh[j] = (h[j] > 0) * sum_c W2[c, j] dz[c]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < Cr; j += 8) {
-    float a = 0.f;
-    for (int c = lane; c < C; c += 32) a = fmaf(w2[static_cast<size_t>(c) * Cr + j], dz[c], a);
-    a = warp_sum(a);
-    if (lane == 0) dh[j] = h[j] > 0.f ? a : 0.f;
+  for (int j = threadIdx.x; j < Cr; j += blockDim.x) {
+    h[j] = hidden[static_cast<size_t>(n) * Cr + j];
+    dh[j] = 0.f;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C * Cr; i += blockDim.x) {
-    const int j = i / C, c = i - j * C;
-    atomicAdd(dw1 + i, dh[j] * s[c]);
+  // dh[j] = sum_c W2[c, j] dz[c]: a warp walks rows c of W2 (coalesced over j), four rows in flight, and keeps partial
+  // sums for j = lane + 32 k; the warps' partials meet in shared memory
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int jb = 0; jb < Cr; jb += 128) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int c = warp; c < C; c += nw) {
+      const float* wr = w2 + static_cast<size_t>(c) * Cr + jb;
+      const float z = dz[c];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = jb + lane + 32 * k;
+        if (j < Cr) acc[k] = fmaf(wr[lane + 32 * k], z, acc[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = jb + lane + 32 * k;
+      if (j < Cr) atomicAdd(&dh[j], acc[k]);
+    }
   }
+  __syncthreads();
+  for (int j = threadIdx.x; j < Cr; j += blockDim.x) {
+    const float v = h[j] > 0.f ? dh[j] : 0.f;
+    dh[j] = v;
+    ws_dh[static_cast<size_t>(n) * Cr + j] = v;
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f;
-    for (int j = 0; j < Cr; ++j) a = fmaf(w1[static_cast<size_t>(j) * C + c], dh[j], a);
-    extra[static_cast<size_t>(n) * C + c] = a * inv_T;
+    float a0 = 0.f, a1 = 0.f;
+    int j = 0;
+#pragma unroll 4
+    for (; j + 1 < Cr; j += 2) {
+      a0 = fmaf(w1[static_cast<size_t>(j) * C + c], dh[j], a0);
+      a1 = fmaf(w1[static_cast<size_t>(j + 1) * C + c], dh[j + 1], a1);
+    }
+    if (j < Cr) a0 = fmaf(w1[static_cast<size_t>(j) * C + c], dh[j], a0);
+    extra[static_cast<size_t>(n) * C + c] = (a0 + a1) * inv_T;
+  }
+}
+
+// dW2[c, j] += sum_n dz[n, c] h[n, j] ; dW1[j, c] += sum_n dh[n, j] s[n, c]: one thread, one element, no atomics
+__global__ void __launch_bounds__(256)
+se_wgrad_kernel(const float* __restrict__ ws_dz, const float* __restrict__ ws_dh, const float* __restrict__ s_in,
+                const float* __restrict__ hidden, float* __restrict__ dw1, float* __restrict__ dw2, int N, int C,
+                int Cr) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int total = C * Cr;
+  if (i >= 2 * total) return;
+  float a0 = 0.f, a1 = 0.f;
+  if (i < total) {
+    const int c = i / Cr, j = i - c * Cr;
+    int n = 0;
+#pragma unroll 4
+    for (; n + 1 < N; n += 2) {
+      a0 = fmaf(ws_dz[static_cast<size_t>(n) * C + c], hidden[static_cast<size_t>(n) * Cr + j], a0);
+      a1 = fmaf(ws_dz[static_cast<size_t>(n + 1) * C + c], hidden[static_cast<size_t>(n + 1) * Cr + j], a1);
+    }
+    if (n < N) a0 = fmaf(ws_dz[static_cast<size_t>(n) * C + c], hidden[static_cast<size_t>(n) * Cr + j], a0);
+    dw2[i] += a0 + a1;
+  } else {
+    const int i2 = i - total;
+    const int j = i2 / C, c = i2 - j * C;
+    int n = 0;
+#pragma unroll 4
+    for (; n + 1 < N; n += 2) {
+      a0 = fmaf(ws_dh[static_cast<size_t>(n) * Cr + j], s_in[static_cast<size_t>(n) * C + c], a0);
+      a1 = fmaf(ws_dh[static_cast<size_t>(n + 1) * Cr + j], s_in[static_cast<size_t>(n + 1) * C + c], a1);
+    }
+    if (n < N) a0 = fmaf(ws_dh[static_cast<size_t>(n) * Cr + j], s_in[static_cast<size_t>(n) * C + c], a0);
+    dw1[i2] += a0 + a1;
   }
 }
 
@@ -153,19 +250,25 @@ int lasr_se_excite_fwd(const float* sums, const float* scale, const float* shift
                        lasr_stream_t stream) {
   if (N <= 0 || C <= 0 || Cr <= 0 || T <= 0) return LASR_ERR_BAD_SHAPE;
   const int smem = (C + Cr) * static_cast<int>(sizeof(float));
-  se_fwd_kernel<<<N, 256, smem, stream>>>(sums, scale, shift, 1.f / static_cast<float>(T), w1, w2, s, hidden, gate, C,
-                                          Cr);
+  if (smem > 48 * 1024) return LASR_ERR_UNSUPPORTED;
+  se_fwd_kernel<<<N, SE_THREADS, smem, stream>>>(sums, scale, shift, 1.f / static_cast<float>(T), w1, w2, s, hidden,
+                                                 gate, C, Cr);
   LASR_CHECK_LAUNCH();
   return LASR_OK;
 }
 
 int lasr_se_excite_bwd(const float* partials, int chunks, const float* scale, const float* shift, int T,
                        const float* w1, const float* w2, const float* s, const float* hidden, const float* gate,
-                       float* extra, float* dw1, float* dw2, int N, int C, int Cr, lasr_stream_t stream) {
-  if (N <= 0 || C <= 0 || Cr <= 0 || T <= 0 || chunks <= 0) return LASR_ERR_BAD_SHAPE;
-  const int smem = (2 * C + 2 * Cr) * static_cast<int>(sizeof(float));
-  se_bwd_kernel<<<N, 256, smem, stream>>>(partials, chunks, scale, shift, 1.f / static_cast<float>(T), w1, w2, s,
-                                          hidden, gate, extra, dw1, dw2, C, Cr);
+                       float* extra, float* dw1, float* dw2, float* ws, int N, int C, int Cr, lasr_stream_t stream) {
+  if (N <= 0 || C <= 0 || Cr <= 0 || T <= 0 || chunks <= 0 || ws == nullptr) return LASR_ERR_BAD_SHAPE;
+  const int smem = (C + 2 * Cr) * static_cast<int>(sizeof(float));
+  if (smem > 48 * 1024) return LASR_ERR_UNSUPPORTED;
+  float* ws_dz = ws;
+  float* ws_dh = ws + static_cast<size_t>(N) * C;
+  se_bwd_kernel<<<N, SE_THREADS, smem, stream>>>(partials, chunks, scale, shift, 1.f / static_cast<float>(T), w1, w2,
+                                                 hidden, gate, extra, ws_dz, ws_dh, C, Cr);
+  LASR_CHECK_LAUNCH();
+  se_wgrad_kernel<<<cdiv(2 * C * Cr, 256), 256, 0, stream>>>(ws_dz, ws_dh, s, hidden, dw1, dw2, N, C, Cr);
   LASR_CHECK_LAUNCH();
   return LASR_OK;
 }

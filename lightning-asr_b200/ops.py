@@ -461,7 +461,8 @@ def se_excite_bwd(per_n, scale, shift, T, w1, w2, s, hidden, gate, dw1, dw2):
     N, C = gate.shape
     Cr = w1.shape[0]
     extra = torch.empty((N, C), device=gate.device, dtype=torch.float32)
-    call("lasr_se_excite_bwd", per_n, 1, scale, shift, T, w1, w2, s, hidden, gate, extra, dw1, dw2, N, C, Cr)
+    ws = torch.empty((N * (C + Cr),), device=gate.device, dtype=torch.float32)
+    call("lasr_se_excite_bwd", per_n, 1, scale, shift, T, w1, w2, s, hidden, gate, extra, dw1, dw2, ws, N, C, Cr)
     return extra
 
 
