@@ -274,6 +274,7 @@ class TrainEngine:
         self._loss_evt = [None, None]
         self._host_steps = 0
         self.loss_dev = torch.zeros((), device=self.dev, dtype=torch.float32)
+        self._gout = None  # constant seed of the backward: d mean(nll) / d nll
         self.graph = None
         self.use_graph = graph
         # double-buffered input pipeline: the NEXT batch's H2D runs on a copy stream while this step computes
@@ -321,19 +322,31 @@ class TrainEngine:
             feats, percents = self.frontend(self.static[0], self.static[2], self.uniforms)
             x = m.encoder.encoder.forward_ntc(feats, percents)
             nll, _, _ = m.encoder.fused_ctc_from_encoded(x, percents, self.static[1], self.static[3])
-            loss = torch.mean(nll)
         elif self.fused:
-            loss, _, _ = m.training_step_fused(self.static)
+            nll, _, _ = m.encoder.forward_fused_ctc(self.static[0], self.static[2], self.static[1], self.static[3])
         else:
+            nll = None
             loss, _, _ = m.training_step_tensors(self.static)
-        loss.backward()
+        if nll is not None:
+            # loss = mean(nll) (train.py:64-86): the backward is seeded with the constant d loss / d nll = 1/N and the mean
+            # is written straight into loss_dev -- autograd's own route (ones -> mul -> expand -> contiguous copy, then a
+            # copy of the loss) is four more dependent launches between the CTC lattices and the CTC gradient pass
+            if self._gout is None or self._gout.shape != nll.shape:
+                self._gout = torch.full(nll.shape, 1.0 / nll.numel(), device=nll.device, dtype=torch.float32)
+            nll.backward(gradient=self._gout)
+            loss = None
+        else:
+            loss.backward()
         self.bank.join_side()  # deferred weight-gradient kernels (runtime.defer) are part of this step
         if self.grad_sync is not None:
             self.grad_sync(m)
         if self.optimizer is not None:
             self.optimizer.step()  # optim.Novograd: three launches over the flat buffers, arena still armed
         self.bank.end_step()
-        self.loss_dev.copy_(loss.detach())
+        if loss is None:
+            torch.mean(nll.detach(), dim=0, out=self.loss_dev)
+        else:
+            self.loss_dev.copy_(loss.detach())
 
     def _capture(self):
         # the step's main chain is captured from a HIGH-priority stream; the deferred weight-gradient kernels
