@@ -13,6 +13,8 @@ it takes the reference's [N, 1, F, T] fp32 features and returns [N, T', V+1] fp3
 """
 import os
 
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -282,6 +284,8 @@ class QuartNet12(nn.Module):
             drop = (self.drop_rate, dm.get("last_cnn2")) if (self.drop_rate > 0.0 and self.training) else None
             x = Conv1x1BNReLUFn.apply(x, self.last_cnn2[0].weight, self.last_cnn2[1].weight, self.last_cnn2[1].bias,
                                       _bn_buffers(self.last_cnn2[1]), self.training, True, drop)
+        # the decoder / CTC side needs the same (T' * percents).int(): hand it over with the output it belongs to
+        self._lengths_of = (weakref.ref(x), lengths)
         return x
 
     def forward(self, input, percents, precision=None, drop_masks=None):
@@ -321,7 +325,11 @@ class MyModel2(nn.Module):
         return self.fused_ctc_from_encoded(x, percents, targets, target_lengths)
 
     def fused_ctc_from_encoded(self, x, percents, targets, target_lengths):
-        t_lengths = ops.out_lengths(x.shape[1], percents.to(x.device))
+        held = getattr(self.encoder, "_lengths_of", None)
+        if held is not None and held[0]() is x:  # computed by the encoder pass that produced x: two launches fewer
+            t_lengths = held[1]
+        else:
+            t_lengths = ops.out_lengths(x.shape[1], percents.to(x.device))
         nll, logits = FusedDecoderCTCFn.apply(x, self.decoder.weight, self.decoder.bias,
                                               targets.to(x.device).long().contiguous(), t_lengths,
                                               target_lengths.to(x.device).int().contiguous(), len(self.labels))
