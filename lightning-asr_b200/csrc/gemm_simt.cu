@@ -24,23 +24,44 @@ gemm_simt_nt_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int k0 = 0; k0 < K; k0 += BK) {
-    // A tile: 128 rows x 16 k = 2048 floats, 8 per thread
+  // software pipeline: the next k-tile's 8 + 4 values per thread are fetched into registers before the current tile is
+  // multiplied, and stored to shared memory after it (the unpipelined loop exposed one global-load latency per 16 k:
+  // at M = 2004 rows -- 128 CTAs, less than a wave -- that latency WAS the kernel)
+  float ra[8], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int idx = tid + i * 256;
       const int r = idx >> 4, kk = idx & 15;
       const int gr = m0 + r, gk = k0 + kk;
-      As[kk][r] = (gr < M && gk < K) ? A[static_cast<size_t>(gr) * lda + gk] : 0.f;
+      ra[i] = (gr < M && gk < K) ? A[static_cast<size_t>(gr) * lda + gk] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + i * 256;
       const int r = idx >> 4, kk = idx & 15;
       const int gr = n0 + r, gk = k0 + kk;
-      Bs[kk][r] = (gr < N && gk < K) ? B[static_cast<size_t>(gr) * ldb + gk] : 0.f;
+      rb[i] = (gr < N && gk < K) ? B[static_cast<size_t>(gr) * ldb + gk] : 0.f;
     }
-    __syncthreads();
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 256;
+      As[idx & 15][idx >> 4] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      Bs[idx & 15][idx >> 4] = rb[i];
+    }
+  };
+  fetch(0);
+  stash();
+  __syncthreads();
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    const bool more = k0 + BK < K;
+    if (more) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[8], b[4];
@@ -53,6 +74,8 @@ gemm_simt_nt_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
+    __syncthreads();
+    if (more) stash();
     __syncthreads();
   }
 #pragma unroll
@@ -92,16 +115,31 @@ gemm_simt_tn_kernel(const float* __restrict__ DY, const float* __restrict__ X, f
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = r0; k0 < r1; k0 += BK) {
+  float ra[4], rb[4];  // the next k-tile, fetched while the current one is multiplied (see gemm_simt_nt_kernel)
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + i * 256;
       const int kk = idx >> 6, c = idx & 63;
       const int gr = k0 + kk;
-      As[kk][c] = (gr < r1 && m0 + c < Cout) ? DY[static_cast<size_t>(gr) * lddy + m0 + c] : 0.f;
-      Bs[kk][c] = (gr < r1 && n0 + c < Cin) ? X[static_cast<size_t>(gr) * ldx + n0 + c] : 0.f;
+      ra[i] = (gr < r1 && m0 + c < Cout) ? DY[static_cast<size_t>(gr) * lddy + m0 + c] : 0.f;
+      rb[i] = (gr < r1 && n0 + c < Cin) ? X[static_cast<size_t>(gr) * ldx + n0 + c] : 0.f;
     }
-    __syncthreads();
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      As[idx >> 6][idx & 63] = ra[i];
+      Bs[idx >> 6][idx & 63] = rb[i];
+    }
+  };
+  fetch(r0);
+  stash();
+  __syncthreads();
+  for (int k0 = r0; k0 < r1; k0 += BK) {
+    const bool more = k0 + BK < r1;
+    if (more) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[4], b[4];
@@ -114,6 +152,8 @@ gemm_simt_tn_kernel(const float* __restrict__ DY, const float* __restrict__ X, f
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
+    __syncthreads();
+    if (more) stash();
     __syncthreads();
   }
 #pragma unroll
@@ -167,22 +207,41 @@ gemm_simt_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  float ra[8], rb[4];  // the next k-tile, fetched while the current one is multiplied (see gemm_simt_nt_kernel)
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int idx = tid + i * 256;
       const int r = idx >> 4, kk = idx & 15;
       const int gr = m0 + r, gk = k0 + kk;
-      As[kk][r] = (gr < M && gk < K) ? A[static_cast<size_t>(gr) * lda + gk] : 0.f;
+      ra[i] = (gr < M && gk < K) ? A[static_cast<size_t>(gr) * lda + gk] : 0.f;
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int idx = tid + i * 256;
       const int kk = idx >> 6, c = idx & 63;
       const int gk = k0 + kk, gc = n0 + c;
-      Bs[kk][c] = (gk < K && gc < N) ? B[static_cast<size_t>(gk) * ldb + gc] : 0.f;
+      rb[i] = (gk < K && gc < N) ? B[static_cast<size_t>(gk) * ldb + gc] : 0.f;
     }
-    __syncthreads();
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int idx = tid + i * 256;
+      As[idx & 15][idx >> 4] = ra[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = tid + i * 256;
+      Bs[idx >> 6][idx & 63] = rb[i];
+    }
+  };
+  fetch(0);
+  stash();
+  __syncthreads();
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    const bool more = k0 + BK < K;
+    if (more) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[8], b[4];
@@ -195,6 +254,8 @@ gemm_simt_nn_kernel(const float* __restrict__ A, const float* __restrict__ B, fl
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
+    __syncthreads();
+    if (more) stash();
     __syncthreads();
   }
 #pragma unroll
