@@ -471,15 +471,16 @@ sum_over_time_kernel(const T* __restrict__ y, float* __restrict__ sums, int T_le
   const int CV = C / 8;
   const int rows_par = 256 / CV;
   const int tr = threadIdx.x / CV, cv = threadIdx.x - tr * CV;
-  if (tr >= rows_par) return;
+  __shared__ float red[256 * 8];  // the CTA's row lanes meet here: one global atomic per (CTA, channel), not per thread
+  const bool active = tr < rows_par;
   const int t0 = blockIdx.y * rows_per_chunk;
   const int t1 = min(T_len, t0 + rows_per_chunk);
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   const T* yp = y + static_cast<size_t>(n) * T_len * C + cv * 8;
-  int t = t0 + tr;
-  // four rows in flight per thread (one 16-byte load per trip left the kernel latency-bound: 23 us for 33 MB)
+  int t = active ? t0 + tr : t1;
+  // four rows in flight per thread
   for (; t + 3 * rows_par < t1; t += 4 * rows_par) {
     float a[4][8];
 #pragma unroll
@@ -493,8 +494,17 @@ sum_over_time_kernel(const T* __restrict__ y, float* __restrict__ sums, int T_le
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] += a[i];
   }
+  if (active) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) atomicAdd(sums + static_cast<size_t>(n) * C + cv * 8 + i, acc[i]);
+    for (int i = 0; i < 8; ++i) red[(tr * CV + cv) * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  // thread c < C folds the row lanes of channel c (consecutive threads, consecutive channels)
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float v = 0.f;
+    for (int r = 0; r < rows_par; ++r) v += red[r * C + c];
+    atomicAdd(sums + static_cast<size_t>(n) * C + c, v);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -168,7 +168,7 @@ se_wgrad_kernel(const float* __restrict__ ws_dz, const float* __restrict__ ws_dh
   if (i < total) {
     const int c = i / Cr, j = i - c * Cr;
     int n = 0;
-#pragma unroll 4
+#pragma unroll 8
     for (; n + 1 < N; n += 2) {
       a0 = fmaf(ws_dz[static_cast<size_t>(n) * C + c], hidden[static_cast<size_t>(n) * Cr + j], a0);
       a1 = fmaf(ws_dz[static_cast<size_t>(n + 1) * C + c], hidden[static_cast<size_t>(n + 1) * Cr + j], a1);
@@ -179,7 +179,7 @@ se_wgrad_kernel(const float* __restrict__ ws_dz, const float* __restrict__ ws_dh
     const int i2 = i - total;
     const int j = i2 / C, c = i2 - j * C;
     int n = 0;
-#pragma unroll 4
+#pragma unroll 8
     for (; n + 1 < N; n += 2) {
       a0 = fmaf(ws_dh[static_cast<size_t>(n) * Cr + j], s_in[static_cast<size_t>(n) * C + c], a0);
       a1 = fmaf(ws_dh[static_cast<size_t>(n + 1) * Cr + j], s_in[static_cast<size_t>(n + 1) * C + c], a1);
